@@ -1,0 +1,136 @@
+/*
+ * svdss_b200.h -- C ABI of libsvdss_b200: the B200 (sm_100a) implementation of SVDSS's
+ * data-parallel hot path (SFS extraction by ping-pong FMD search; cluster POA; ksw2 realignment).
+ *
+ * The reference (Parsoa/SVDSS v2.1.1) has no plugin/FFI layer: its hot path is reached by direct
+ * C++ calls into three statically linked C libraries.  Each entry point below names the reference
+ * call it stands in for (file:line relative to the reference tree).  INTEGRATION.md shows the
+ * host-side binding a maintainer would add.
+ *
+ * Conventions: every function returns SVB_OK (0) or a negative errno-style code; no exceptions
+ * cross the ABI; svb_last_error() returns a thread-local message for the last failure; the caller
+ * owns every buffer it passes in; outputs are released with the matching *_free.  `mem` arguments
+ * say where caller buffers live: SVB_MEM_HOST (0) or SVB_MEM_DEVICE (1, a CUDA device pointer on
+ * `device`).  All sequences are nt6-coded bytes ($=0 A=1 C=2 G=3 T=4 N=5; ping_pong.hpp:46-52).
+ * There is NO CPU fallback: without a CUDA device every compute entry fails with SVB_ECUDA.
+ */
+#ifndef SVDSS_B200_H
+#define SVDSS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB_OK 0
+#define SVB_EINVAL (-22)
+#define SVB_ENOMEM (-12)
+#define SVB_ECUDA (-5)
+#define SVB_EIO (-74)
+#define SVB_ERANGE (-34)
+
+#define SVB_MEM_HOST 0
+#define SVB_MEM_DEVICE 1
+
+#define SVB_API __attribute__((visibility("default")))
+
+typedef struct svb_index svb_index_t; /* immutable once built; shareable between host threads */
+typedef struct svb_reads svb_reads_t; /* a batch of reads resident in HBM */
+
+SVB_API const char* svb_last_error(void);
+SVB_API int svb_device_count(void);
+SVB_API const char* svb_version(void);
+
+/* ------------------------------------------------------------------ index (a2, a3, `index`) -- */
+
+typedef struct {
+  int64_t n;           /* BWT length = 2 * sum(len_i + 1)                                        */
+  int64_t acc[7];      /* acc[c] = #symbols < c  (rb3_fmi_t::acc)                    */
+  int64_t n_blocks;
+  int32_t block_bytes; /* 64 or 128                                                              */
+  int32_t block_syms;  /* 128 or 256                                                             */
+  int64_t n_contigs;
+  int64_t device_bytes;
+  int32_t device;
+} svb_index_info_t;
+
+/* Build the FMD index of {S_i, rc(S_i)} on the GPU: suffix sort, BWT, sampled-Occ block array.
+ * Replaces `SVDSS index` = ropebwt3 main_build (main.cpp:15-17,34-37; CMakeLists.txt:154-169).
+ * block_bytes: 64, 128, or 0 for the library default. */
+SVB_API int svb_index_build(const uint8_t* contigs_nt6, const int64_t* offs /* n_contigs+1 */,
+                            int64_t n_contigs, int mem, int device, int block_bytes,
+                            svb_index_t** out);
+/* Build the block array from a ready BWT (nt6 codes). Test hook for the rank / search kernels. */
+SVB_API int svb_index_from_bwt(const uint8_t* bwt, int64_t n, int mem, int device, int block_bytes,
+                               svb_index_t** out);
+/* rb3_fmi_restore(&index, path, 0) (ping_pong.cpp:244-245): load an index file written by
+ * svb_index_save into HBM of `device`.  The file layout is private to this library (the reference
+ * treats .fmd as opaque between `index` and `search`, run_svdss:137-164). */
+SVB_API int svb_index_load(const char* path, int device, svb_index_t** out);
+SVB_API int svb_index_save(const svb_index_t* idx, const char* path);
+SVB_API void svb_index_free(svb_index_t* idx);
+SVB_API int svb_index_info(const svb_index_t* idx, svb_index_info_t* info);
+/* Decode the block array back to BWT symbols (host buffer of n bytes). */
+SVB_API int svb_index_get_bwt(const svb_index_t* idx, uint8_t* bwt_host);
+/* Debug/test: suffix array of a '$'-terminated nt6 text with sentinels ordered by position. */
+SVB_API int svb_suffix_array(const uint8_t* text, int64_t n, int mem, int device, int64_t* sa_host);
+
+/* ------------------------------------------------------------------------------ rank (a2) -- */
+
+/* rb3_fmi_rank2a(f, k, l, ok, ol) for n query pairs: Occ of all six symbols at k[i] and l[i]
+ * (ropebwt3 fm-index.h, reached from ping_pong.cpp:20,35 via rb3_fmd_extend). Host buffers.
+ * ok6/ol6 are n*6 int64. */
+SVB_API int svb_rank2a(const svb_index_t* idx, const int64_t* k, const int64_t* l, int64_t n,
+                       int64_t* ok6, int64_t* ol6);
+
+/* "FMD rank GB/s" microbenchmark: n_queries uniformly random (k, k+delta) pairs, one
+ * backward extension each (Occ of one symbol at both ends), generated on the device; timed with
+ * CUDA events over `iters` launches.  bytes = block_bytes * distinct blocks touched. */
+SVB_API int svb_rank_bench(const svb_index_t* idx, int64_t n_queries, int64_t delta, uint64_t seed,
+                           int iters, float* ms_per_iter, int64_t* blocks_touched_per_iter);
+
+/* ------------------------------------------------------------------ SFS search (a1, a4, a10) -- */
+
+typedef struct {
+  /* results: one record per (assembled) SFS, grouped by read in input order; within a read
+   * ascending qs when assemble != 0 (assembler.cpp:36), descending qs otherwise (emit order of
+   * ping_pong.cpp:39-41).  offs[r]..offs[r+1] indexes the records of read r. */
+  int64_t n_reads;
+  int64_t n_sfs;
+  int64_t* offs; /* n_reads + 1 */
+  int32_t* qs;   /* SFS::qs  (sfs.hpp:36) */
+  int32_t* len;  /* SFS::l   (sfs.hpp:38) */
+  /* measurement (filled by every search call) */
+  int64_t n_ext;            /* backward extensions performed (= rb3_fmd_extend calls)           */
+  int64_t n_blocks_touched; /* sum over extensions of distinct index blocks read (1 or 2)       */
+  float kernel_ms;          /* search kernel only, CUDA events on the launch stream             */
+  float device_ms;          /* whole device pipeline of this call (H2D + kernels + D2H)         */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int32_t launches;         /* kernels launched by this call                                    */
+  int32_t block_bytes;
+} svb_sfs_out_t;
+
+/* PingPong::process_batch (ping_pong.cpp:176-209) for a whole batch: runs
+ * PingPong::ping_pong_search (ping_pong.cpp:4-49) on every read and, if assemble != 0,
+ * Assembler::assemble (assembler.cpp:34-56) per read.  HOST buffers; copies are pipelined with the
+ * kernel internally, the call is synchronous at return.  overlap must be <= 0 (config.hpp:82 fixes
+ * it at -1; 0 is the "relaxed" branch of ping_pong.cpp:44-45).  Reads of length 0 yield nothing.
+ * The BAM-level filters of ping_pong.cpp:66-79,196-203 stay with the caller. */
+SVB_API int svb_sfs_batch(const svb_index_t* idx, const uint8_t* nt6_concat,
+                          const int64_t* offs /* n_reads+1 */, int64_t n_reads, int overlap,
+                          int assemble, svb_sfs_out_t* out);
+
+/* Same search with the batch already resident in HBM (kernel-only measurement; multi-batch reuse). */
+SVB_API int svb_reads_upload(const uint8_t* nt6_concat, const int64_t* offs, int64_t n_reads,
+                             int mem, int device, svb_reads_t** out);
+SVB_API void svb_reads_free(svb_reads_t* reads);
+SVB_API int svb_sfs_resident(const svb_index_t* idx, const svb_reads_t* reads, int overlap,
+                             int assemble, svb_sfs_out_t* out);
+SVB_API void svb_sfs_out_free(svb_sfs_out_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVDSS_B200_H */

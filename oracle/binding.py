@@ -1,0 +1,175 @@
+"""ctypes binding of oracle/_build/liboracle.so (built by oracle/Makefile)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    """Compile the C oracle (gcc). Idempotent."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_text_len.restype = C.c_int64
+        L.orc_text_len.argtypes = [_i64p, C.c_int64]
+        L.orc_build_text.restype = None
+        L.orc_build_text.argtypes = [_u8p, _i64p, C.c_int64, _u8p]
+        L.orc_suffix_array.restype = None
+        L.orc_suffix_array.argtypes = [_u8p, C.c_int64, _i64p]
+        L.orc_bwt_from_sa.restype = None
+        L.orc_bwt_from_sa.argtypes = [_u8p, C.c_int64, _i64p, _u8p]
+        L.orc_sfs_spec.restype = C.c_int64
+        L.orc_sfs_spec.argtypes = [_u8p, C.c_int64, _i64p, _u8p, C.c_int64, _i32p, _i32p, C.c_int64]
+        L.orc_assemble.restype = C.c_int64
+        L.orc_assemble.argtypes = [_i32p, _i32p, C.c_int64, _i32p, _i32p]
+        L.orc_fm_build.restype = C.c_void_p
+        L.orc_fm_build.argtypes = [_u8p, C.c_int64]
+        L.orc_fm_free.restype = None
+        L.orc_fm_free.argtypes = [C.c_void_p]
+        L.orc_fm_acc.restype = None
+        L.orc_fm_acc.argtypes = [C.c_void_p, _i64p]
+        L.orc_fm_rank2a.restype = None
+        L.orc_fm_rank2a.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i64p]
+        L.orc_fm_search_batch.restype = C.c_int64
+        L.orc_fm_search_batch.argtypes = [C.c_void_p, _u8p, _i64p, C.c_int64, C.c_int,
+                                          _i64p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+NT6 = np.full(256, 5, np.uint8)  # ping_pong.hpp:46-52 (index 0 -> 0, everything else non-ACGT -> 5)
+NT6[0] = 0
+for _ch, _v in (("A", 1), ("C", 2), ("G", 3), ("T", 4)):
+    NT6[ord(_ch)] = _v
+    NT6[ord(_ch.lower())] = _v
+
+
+def encode_nt6(s):
+    if isinstance(s, str):
+        s = s.encode()
+    return NT6[np.frombuffer(s, np.uint8)]
+
+
+def concat(seqs):
+    """list of uint8 arrays -> (concat, offs int64[n+1])"""
+    offs = np.zeros(len(seqs) + 1, np.int64)
+    if seqs:
+        offs[1:] = np.cumsum([len(s) for s in seqs])
+        cat = np.ascontiguousarray(np.concatenate(seqs).astype(np.uint8)) if offs[-1] else np.zeros(0, np.uint8)
+    else:
+        cat = np.zeros(0, np.uint8)
+    return cat, offs
+
+
+def build_text(contigs):
+    """contigs: list of nt6 uint8 arrays -> T = S$rc(S)$..."""
+    cat, offs = concat(contigs)
+    n = lib().orc_text_len(offs, len(contigs))
+    T = np.empty(n, np.uint8)
+    lib().orc_build_text(cat if len(cat) else np.zeros(1, np.uint8), offs, len(contigs), T)
+    return T
+
+
+def suffix_array(T):
+    SA = np.empty(len(T), np.int64)
+    lib().orc_suffix_array(np.ascontiguousarray(T), len(T), SA)
+    return SA
+
+
+def bwt_from_sa(T, SA):
+    bwt = np.empty(len(T), np.uint8)
+    lib().orc_bwt_from_sa(np.ascontiguousarray(T), len(T), SA, bwt)
+    return bwt
+
+
+def sfs_spec(T, SA, P, cap=None):
+    """(qs,len) pairs in the reference's emit order (descending qs) for one nt6 read P."""
+    P = np.ascontiguousarray(P, np.uint8)
+    cap = cap or max(16, len(P))
+    qs = np.empty(cap, np.int32)
+    ln = np.empty(cap, np.int32)
+    c = lib().orc_sfs_spec(T, len(T), SA, P if len(P) else np.zeros(1, np.uint8), len(P), qs, ln, cap)
+    assert c <= cap
+    return list(zip(qs[:c].tolist(), ln[:c].tolist()))
+
+
+def assemble(pairs):
+    if not pairs:
+        return []
+    qs = np.array([p[0] for p in pairs], np.int32)
+    ln = np.array([p[1] for p in pairs], np.int32)
+    oq = np.empty_like(qs)
+    ol = np.empty_like(ln)
+    c = lib().orc_assemble(qs, ln, len(pairs), oq, ol)
+    return list(zip(oq[:c].tolist(), ol[:c].tolist()))
+
+
+class FMIndex:
+    """CPU port of the FM index + ping-pong search (oracle statement #2; also the CPU baseline)."""
+
+    def __init__(self, bwt):
+        bwt = np.ascontiguousarray(bwt, np.uint8)
+        self.n = len(bwt)
+        self._h = lib().orc_fm_build(bwt, self.n)
+        if not self._h:
+            raise MemoryError("orc_fm_build")
+        self.acc = np.empty(7, np.int64)
+        lib().orc_fm_acc(self._h, self.acc)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_fm_free(self._h)
+            self._h = None
+
+    def rank2a(self, k, l):
+        ok = np.empty(6, np.int64)
+        ol = np.empty(6, np.int64)
+        lib().orc_fm_rank2a(self._h, int(k), int(l), ok, ol)
+        return ok, ol
+
+    def search_batch(self, reads, offs, threads=0, want_output=True):
+        """returns (counts int64[n], out_off int64[n+1], qs int32[], len int32[], n_extensions)"""
+        reads = np.ascontiguousarray(reads, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        n = len(offs) - 1
+        counts = np.zeros(n, np.int64)
+        if len(reads) == 0:
+            reads = np.zeros(1, np.uint8)
+        ext = lib().orc_fm_search_batch(self._h, reads, offs, n, threads, counts, None, None, None)
+        if not want_output:
+            return counts, None, None, None, ext
+        out_off = np.zeros(n + 1, np.int64)
+        out_off[1:] = np.cumsum(counts)
+        tot = int(out_off[-1])
+        qs = np.empty(max(tot, 1), np.int32)
+        ln = np.empty(max(tot, 1), np.int32)
+        c2 = np.zeros(n, np.int64)
+        lib().orc_fm_search_batch(self._h, reads, offs, n, threads, c2,
+                                  out_off.ctypes.data_as(C.c_void_p), qs.ctypes.data_as(C.c_void_p),
+                                  ln.ctypes.data_as(C.c_void_p))
+        assert (c2 == counts).all()
+        return counts, out_off, qs[:tot], ln[:tot], ext
+
+
+def max_threads():
+    return lib().orc_max_threads()

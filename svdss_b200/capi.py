@@ -1,0 +1,248 @@
+"""ctypes binding of libsvdss_b200.so -- the same C ABI (include/svdss_b200.h) a C++ host links.
+
+There is no CPU fallback: if the library is missing it is an ImportError-class failure, and every
+compute entry returns SVB_ECUDA without a CUDA device, surfaced here as SvbError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsvdss_b200.so")
+
+SVB_MEM_HOST, SVB_MEM_DEVICE = 0, 1
+
+
+class SvbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libsvdss_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("n", C.c_int64), ("acc", C.c_int64 * 7), ("n_blocks", C.c_int64),
+                ("block_bytes", C.c_int32), ("block_syms", C.c_int32), ("n_contigs", C.c_int64),
+                ("device_bytes", C.c_int64), ("device", C.c_int32)]
+
+
+class SfsOut(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_sfs", C.c_int64), ("offs", C.POINTER(C.c_int64)),
+                ("qs", C.POINTER(C.c_int32)), ("len", C.POINTER(C.c_int32)),
+                ("n_ext", C.c_int64), ("n_blocks_touched", C.c_int64), ("kernel_ms", C.c_float),
+                ("device_ms", C.c_float), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("launches", C.c_int32), ("block_bytes", C.c_int32)]
+
+
+_lib = None
+
+# every symbol include/svdss_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "svb_last_error", "svb_device_count", "svb_version",
+    "svb_index_build", "svb_index_from_bwt", "svb_index_load", "svb_index_save", "svb_index_free",
+    "svb_index_info", "svb_index_get_bwt", "svb_suffix_array",
+    "svb_rank2a", "svb_rank_bench",
+    "svb_sfs_batch", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
+]
+
+
+def lib():
+    """Load libsvdss_b200.so (built in-tree by svdss_b200/build.py). Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError("libsvdss_b200.so not built: run `python -m svdss_b200.build` "
+                      "(the CUDA library is the only implementation; there is no CPU path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.svb_last_error.restype = C.c_char_p
+    L.svb_version.restype = C.c_char_p
+    L.svb_device_count.restype = i32
+    L.svb_index_build.argtypes = [vp, vp, i64, i32, i32, i32, C.POINTER(vp)]
+    L.svb_index_from_bwt.argtypes = [vp, i64, i32, i32, i32, C.POINTER(vp)]
+    L.svb_index_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+    L.svb_index_save.argtypes = [vp, C.c_char_p]
+    L.svb_index_free.argtypes = [vp]
+    L.svb_index_free.restype = None
+    L.svb_index_info.argtypes = [vp, C.POINTER(IndexInfo)]
+    L.svb_index_get_bwt.argtypes = [vp, vp]
+    L.svb_suffix_array.argtypes = [vp, i64, i32, i32, vp]
+    L.svb_rank2a.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.svb_rank_bench.argtypes = [vp, i64, i64, C.c_uint64, i32, C.POINTER(C.c_float), C.POINTER(i64)]
+    L.svb_sfs_batch.argtypes = [vp, vp, vp, i64, i32, i32, C.POINTER(SfsOut)]
+    L.svb_reads_upload.argtypes = [vp, vp, i64, i32, i32, C.POINTER(vp)]
+    L.svb_reads_free.argtypes = [vp]
+    L.svb_reads_free.restype = None
+    L.svb_sfs_resident.argtypes = [vp, vp, i32, i32, C.POINTER(SfsOut)]
+    L.svb_sfs_out_free.argtypes = [C.POINTER(SfsOut)]
+    L.svb_sfs_out_free.restype = None
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise SvbError(rc, lib().svb_last_error().decode(errors="replace"))
+
+
+def _ptr(a):
+    """numpy array -> void*, int -> raw (device) pointer"""
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class SfsResult:
+    """Per-batch search result copied out of a svb_sfs_out_t."""
+
+    def __init__(self, out):
+        n, m = out.n_reads, out.n_sfs
+        self.offs = np.ctypeslib.as_array(out.offs, shape=(n + 1,)).copy() if n >= 0 and out.offs else np.zeros(1, np.int64)
+        self.qs = np.ctypeslib.as_array(out.qs, shape=(m,)).copy() if m else np.zeros(0, np.int32)
+        self.len = np.ctypeslib.as_array(out.len, shape=(m,)).copy() if m else np.zeros(0, np.int32)
+        self.n_reads, self.n_sfs = n, m
+        self.n_ext = out.n_ext
+        self.n_blocks_touched = out.n_blocks_touched
+        self.kernel_ms = out.kernel_ms
+        self.device_ms = out.device_ms
+        self.h2d_bytes = out.h2d_bytes
+        self.d2h_bytes = out.d2h_bytes
+        self.launches = out.launches
+        self.block_bytes = out.block_bytes
+
+    def per_read(self, r):
+        a, b = int(self.offs[r]), int(self.offs[r + 1])
+        return list(zip(self.qs[a:b].tolist(), self.len[a:b].tolist()))
+
+
+class Index:
+    """Device-resident FMD index (stands in for rb3_fmi_t, ping_pong.cpp:243-245)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        info = IndexInfo()
+        check(lib().svb_index_info(self._h, C.byref(info)))
+        self.n = info.n
+        self.acc = list(info.acc)
+        self.n_blocks = info.n_blocks
+        self.block_bytes = info.block_bytes
+        self.block_syms = info.block_syms
+        self.device_bytes = info.device_bytes
+        self.device = info.device
+
+    @classmethod
+    def build(cls, contigs_cat, offs, device=0, block_bytes=0, mem=SVB_MEM_HOST):
+        """contigs_cat/offs: numpy arrays (host) or raw device pointers with mem=SVB_MEM_DEVICE."""
+        h = C.c_void_p()
+        n = (len(offs) - 1) if not isinstance(offs, (int, np.integer)) else None
+        if n is None:
+            raise ValueError("pass n_contigs through build_device()")
+        check(lib().svb_index_build(_ptr(contigs_cat), _ptr(offs), n, mem, device, block_bytes, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def build_device(cls, seq_ptr, offs_ptr, n_contigs, device=0, block_bytes=0):
+        h = C.c_void_p()
+        check(lib().svb_index_build(C.c_void_p(seq_ptr), C.c_void_p(offs_ptr), n_contigs, SVB_MEM_DEVICE,
+                                    device, block_bytes, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_bwt(cls, bwt, device=0, block_bytes=0):
+        bwt = np.ascontiguousarray(bwt, np.uint8)
+        h = C.c_void_p()
+        check(lib().svb_index_from_bwt(_ptr(bwt), len(bwt), SVB_MEM_HOST, device, block_bytes, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load(cls, path, device=0):
+        h = C.c_void_p()
+        check(lib().svb_index_load(os.fsencode(path), device, C.byref(h)))
+        return cls(h)
+
+    def save(self, path):
+        check(lib().svb_index_save(self._h, os.fsencode(path)))
+
+    def bwt(self):
+        out = np.empty(self.n, np.uint8)
+        check(lib().svb_index_get_bwt(self._h, _ptr(out)))
+        return out
+
+    def rank2a(self, k, l):
+        k = np.ascontiguousarray(k, np.int64)
+        l = np.ascontiguousarray(l, np.int64)
+        ok = np.empty((len(k), 6), np.int64)
+        ol = np.empty((len(k), 6), np.int64)
+        check(lib().svb_rank2a(self._h, _ptr(k), _ptr(l), len(k), _ptr(ok), _ptr(ol)))
+        return ok, ol
+
+    def rank_bench(self, n_queries, delta, seed=1, iters=5):
+        ms = C.c_float()
+        blk = C.c_int64()
+        check(lib().svb_rank_bench(self._h, n_queries, delta, seed, iters, C.byref(ms), C.byref(blk)))
+        return ms.value, blk.value
+
+    def sfs_batch(self, reads_cat, offs, overlap=-1, assemble=True):
+        """svb_sfs_batch with HOST buffers (numpy)."""
+        reads_cat = np.ascontiguousarray(reads_cat, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        out = SfsOut()
+        check(lib().svb_sfs_batch(self._h, _ptr(reads_cat), _ptr(offs), len(offs) - 1, overlap,
+                                  1 if assemble else 0, C.byref(out)))
+        try:
+            return SfsResult(out)
+        finally:
+            lib().svb_sfs_out_free(C.byref(out))
+
+    def sfs_resident(self, reads, overlap=-1, assemble=True):
+        out = SfsOut()
+        check(lib().svb_sfs_resident(self._h, reads._h, overlap, 1 if assemble else 0, C.byref(out)))
+        try:
+            return SfsResult(out)
+        finally:
+            lib().svb_sfs_out_free(C.byref(out))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().svb_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceReads:
+    """A batch of reads resident in HBM (svb_reads_t)."""
+
+    def __init__(self, reads_cat, offs, device=0, mem=SVB_MEM_HOST, n_reads=None):
+        h = C.c_void_p()
+        if mem == SVB_MEM_HOST:
+            reads_cat = np.ascontiguousarray(reads_cat, np.uint8)
+            offs = np.ascontiguousarray(offs, np.int64)
+            n_reads = len(offs) - 1
+        self._keep = (reads_cat, offs)
+        check(lib().svb_reads_upload(_ptr(reads_cat), _ptr(offs), n_reads, mem, device, C.byref(h)))
+        self._h = h
+        self.n_reads = n_reads
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().svb_reads_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def suffix_array(text, device=0):
+    text = np.ascontiguousarray(text, np.uint8)
+    sa = np.empty(len(text), np.int64)
+    check(lib().svb_suffix_array(_ptr(text), len(text), SVB_MEM_HOST, device, _ptr(sa)))
+    return sa

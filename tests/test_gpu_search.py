@@ -1,0 +1,184 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle, bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from common import load_golden, random_case, oracle_index, fm_results
+from svdss_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+BLOCKS = [64, 128]
+
+
+def _gpu_sfs(idx, reads, assemble):
+    cat, offs = oracle.concat(reads)
+    res = idx.sfs_batch(cat, offs, assemble=assemble)
+    assert res.n_reads == len(reads)
+    return [res.per_read(i) for i in range(len(reads))], res
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_suffix_array_small(seed):
+    rng = np.random.default_rng(seed)
+    contigs, _ = random_case(rng, with_n=bool(seed % 2), n_reads=0, max_contig=2000)
+    if seed == 2:  # long exact repeats and an N run longer than the 21-symbol first-pass key
+        c = contigs[0]
+        contigs.append(np.concatenate([c, c[: len(c) // 2], np.full(90, 5, np.uint8), c[::-1]]))
+    T = oracle.build_text(contigs)
+    assert capi.suffix_array(T).tolist() == oracle.suffix_array(T).tolist()
+
+
+@pytest.mark.parametrize("bb", BLOCKS)
+def test_index_build_bwt_and_acc(bb):
+    contigs = synth.make_reference(300_000, seed=11, contigs=3)
+    T, SA, bwt = oracle_index(contigs)
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs, block_bytes=bb)
+    assert idx.n == len(T) and idx.block_bytes == bb
+    assert idx.acc == oracle.FMIndex(bwt).acc.tolist()
+    assert np.array_equal(idx.bwt(), bwt)
+
+
+@pytest.mark.parametrize("bb", BLOCKS)
+def test_rank2a_parity(bb):
+    rng = np.random.default_rng(5)
+    contigs = synth.make_reference(200_000, seed=12, contigs=2)
+    T, SA, bwt = oracle_index(contigs)
+    fm = oracle.FMIndex(bwt)
+    idx = capi.Index.from_bwt(bwt, block_bytes=bb)
+    n = len(bwt)
+    k = rng.integers(0, n + 1, size=4000)
+    l = np.minimum(n, k + rng.integers(0, 5000, size=4000) * (rng.random(4000) < 0.7))
+    edge = np.array([0, 1, 127, 128, 129, 255, 256, 257, n - 1, n], np.int64)
+    k = np.concatenate([k, edge, np.zeros(1, np.int64)])
+    l = np.concatenate([l, edge, np.array([n], np.int64)])
+    ok, ol = idx.rank2a(k, l)
+    for i in range(len(k)):
+        a, b = fm.rank2a(int(k[i]), int(l[i]))
+        assert ok[i].tolist() == a.tolist() and ol[i].tolist() == b.tolist(), i
+
+
+@pytest.mark.parametrize("bb", BLOCKS)
+def test_golden_fixtures(bb):
+    for contigs, reads, raw, asm in load_golden():
+        cat, offs = oracle.concat(contigs)
+        idx = capi.Index.build(cat, offs, block_bytes=bb)
+        got_raw, _ = _gpu_sfs(idx, reads, assemble=False)
+        got_asm, _ = _gpu_sfs(idx, reads, assemble=True)
+        assert got_raw == raw
+        assert got_asm == asm
+
+
+@pytest.mark.parametrize("bb", BLOCKS)
+@pytest.mark.parametrize("seed", range(3))
+def test_random_small_parity(bb, seed):
+    rng = np.random.default_rng(50 + seed)
+    contigs, reads = random_case(rng, with_n=bool(seed % 2), n_reads=300, max_contig=400)
+    reads += [np.zeros(0, np.uint8), np.array([5], np.uint8), np.array([1], np.uint8),
+              np.full(40, 5, np.uint8), contigs[0].copy(), synth.revcomp6(contigs[-1])]
+    T, SA, bwt = oracle_index(contigs)
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs, block_bytes=bb)
+    exp = [oracle.sfs_spec(T, SA, r) if len(r) else [] for r in reads]
+    got_raw, res = _gpu_sfs(idx, reads, assemble=False)
+    assert got_raw == exp
+    got_asm, _ = _gpu_sfs(idx, reads, assemble=True)
+    assert got_asm == [oracle.assemble(e) for e in exp]
+    # whole contigs (either strand) occur in the index: no SFS
+    assert got_raw[-1] == [] and got_raw[-2] == []
+    fm_exp, ext = fm_results(oracle.FMIndex(bwt), reads)
+    assert res.n_ext == ext  # same number of rb3_fmd_extend calls as the literal CPU port
+
+
+def test_empty_batch_and_bad_args():
+    contigs = [np.array([1, 2, 3, 4, 1, 1, 2], np.uint8)]
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs)
+    res = idx.sfs_batch(np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    assert res.n_reads == 0 and res.n_sfs == 0
+    with pytest.raises(capi.SvbError):
+        idx.sfs_batch(np.array([1, 2], np.uint8), np.array([0, 2], np.int64), overlap=3)
+    with pytest.raises(capi.SvbError):
+        capi.Index.build(cat, offs, block_bytes=96)
+    # overlap == 0 is the "relaxed" branch (ping_pong.cpp:44-45): begin -= 1 after every SFS
+    r = np.array([1, 2, 3, 3, 3, 3, 4, 1, 1, 2], np.uint8)
+    res = idx.sfs_batch(r, np.array([0, len(r)], np.int64), overlap=0, assemble=False)
+    assert res.n_sfs >= 1
+
+
+@pytest.mark.parametrize("bb", BLOCKS)
+def test_config1_full_parity(bb):
+    """1 Mb reference (planted repeats, N runs), 1000 smoothed-shaped 15 kb
+    reads + 200 raw-HiFi-shaped reads. SFS sets bit-identical to the oracle."""
+    contigs = synth.make_reference(1_000_000, seed=1)
+    reads = synth.make_reads(contigs, 1000, seed=2) + synth.make_reads(contigs, 200, seed=3, raw_hifi=True)
+    T, SA, bwt = oracle_index(contigs)
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs, block_bytes=bb)
+    assert np.array_equal(idx.bwt(), bwt)
+    exp, ext = fm_results(oracle.FMIndex(bwt), reads)
+    for i in range(0, len(reads), 37):  # SA-narrowing statement on a sample, FM port on everything
+        assert oracle.sfs_spec(T, SA, reads[i]) == exp[i]
+    got_raw, res = _gpu_sfs(idx, reads, assemble=False)
+    assert got_raw == exp
+    assert res.n_ext == ext
+    assert res.n_ext <= res.n_blocks_touched <= 2 * res.n_ext
+    got_asm, _ = _gpu_sfs(idx, reads, assemble=True)
+    assert got_asm == [oracle.assemble(e) for e in exp]
+    # resident path returns the same thing
+    dr = capi.DeviceReads(*oracle.concat(reads))
+    res2 = idx.sfs_resident(dr, assemble=False)
+    assert [res2.per_read(i) for i in range(len(reads))] == exp
+
+
+def test_index_save_load_roundtrip(tmp_path):
+    contigs = synth.make_reference(100_000, seed=4, contigs=2)
+    reads = synth.make_reads(contigs, 50, seed=5, mean_len=3000, sd_len=500, min_len=500, max_len=6000)
+    cat, offs = oracle.concat(contigs)
+    for bb in BLOCKS:
+        idx = capi.Index.build(cat, offs, block_bytes=bb)
+        a, _ = _gpu_sfs(idx, reads, assemble=True)
+        p = os.path.join(tmp_path, "idx%d.svb" % bb)
+        idx.save(p)
+        idx2 = capi.Index.load(p)
+        assert idx2.n == idx.n and idx2.acc == idx.acc and idx2.block_bytes == bb
+        b, _ = _gpu_sfs(idx2, reads, assemble=True)
+        assert a == b
+    with pytest.raises(capi.SvbError):
+        capi.Index.load(os.path.join(tmp_path, "missing.svb"))
+
+
+def test_medium_scale_properties():
+    """Size-independent properties on a 16 Mb multi-contig reference (32 M-symbol BWT): the BWT is
+    a permutation of the text; every emitted SFS is minimal-absent (checked by the CPU port on the
+    GPU-built BWT and by direct substring search on a sample); assemble output is sorted,
+    non-overlapping and idempotent."""
+    contigs = synth.make_reference(16_000_000, seed=21, contigs=5, n_repeats=40, n_nruns=6, nrun_len=3000)
+    reads = synth.make_reads(contigs, 400, seed=22)
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs, block_bytes=128)
+    T = oracle.build_text(contigs)
+    bwt = idx.bwt()
+    assert np.array_equal(np.bincount(bwt, minlength=6), np.bincount(T, minlength=6))
+    fm = oracle.FMIndex(bwt)
+    exp, ext = fm_results(fm, reads)
+    got, res = _gpu_sfs(idx, reads, assemble=False)
+    assert got == exp and res.n_ext == ext
+    strands = [c.tobytes() for c in contigs] + [synth.revcomp6(c).tobytes() for c in contigs]
+    occurs = lambda w: any(w.tobytes() in s for s in strands)
+    checked = 0
+    for r, g in zip(reads[:40], got[:40]):
+        for qs, ln in g[:3]:
+            w = r[qs:qs + ln]
+            assert not occurs(w)
+            assert ln == 1 or (occurs(w[1:]) and occurs(w[:-1]))
+            checked += 1
+    assert checked > 20
+    asm, _ = _gpu_sfs(idx, reads, assemble=True)
+    for a in asm:
+        assert a == sorted(a)
+        for x, y in zip(a, a[1:]):
+            assert x[0] + x[1] <= y[0]
+        assert oracle.assemble(a) == a
