@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- SFS-extracted reads/sec of the FMD ping-pong search (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload: 3.1 Gb i.i.d. reference in 24 contigs (seed 3), both strands indexed
+(6.2 G-symbol BWT), 1 M smoothed-shaped 15 kb reads per GPU (seed 4 + rank).  A *step* is one pass
+of the search over the whole batch.  `value` times the pass with the batch resident in HBM,
+`e2e` times svb_sfs_batch() with HOST (pinned) buffers: H2D of the reads and D2H of the SFS table
+are inside the timed region.  Multi-GPU: reads shard across ranks (weak scaling, index replicated),
+no data-path collective; timing is max over ranks.
+
+--impl reference times the CPU port of the same path (oracle/, OpenMP, all host cores) on a bounded
+sample of the same workload; the reference binary itself cannot be built offline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+REF_BP = 3_100_000_000
+N_CONTIGS = 24
+READS_PER_GPU = 1_000_000
+HBM_FALLBACK_GBS = 6650.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def contig_offsets(ref_bp, n_contigs):
+    w = np.linspace(2.0, 0.5, n_contigs)
+    cuts = np.floor(np.cumsum(w / w.sum()) * ref_bp).astype(np.int64)
+    cuts[-1] = ref_bp
+    return np.concatenate([[0], cuts]).astype(np.int64)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampler running during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def build_workload(args, rank, local, torch, capi, synth, need_device_reads=True):
+    """Reference on the device, index built on the device, reads materialised on the device."""
+    dev = torch.device("cuda", local)
+    offs = contig_offsets(args.ref_bp, args.contigs)
+    t0 = time.time()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    ref = torch.empty(args.ref_bp, dtype=torch.uint8, device=dev)
+    CH = 1 << 30
+    for a in range(0, args.ref_bp, CH):  # chunked: randint materialises int64 internally
+        b = min(args.ref_bp, a + CH)
+        ref[a:b] = torch.randint(1, 5, (b - a,), dtype=torch.uint8, device=dev, generator=gen)
+    offs_t = torch.from_numpy(offs).to(dev)
+    torch.cuda.synchronize(dev)
+    t1 = time.time()
+    idx = capi.Index.build_device(ref.data_ptr(), offs_t.data_ptr(), args.contigs, device=local,
+                                  block_bytes=args.block_bytes)
+    t2 = time.time()
+    log("[rank %d] reference %.1fs, index build %.1fs (n=%d, %d-byte blocks, %.2f GB)" %
+        (rank, t1 - t0, t2 - t1, idx.n, idx.block_bytes, idx.device_bytes / 1e9))
+    segs = synth.make_read_segments(offs, args.reads, seed=4 + rank)
+    reads_t = synth.materialize_segments_torch(ref, segs)
+    torch.cuda.synchronize(dev)
+    del ref
+    torch.cuda.empty_cache()
+    log("[rank %d] reads: %d, %.2f Gbases, generated in %.1fs" %
+        (rank, args.reads, segs["read_offs"][-1] / 1e9, time.time() - t2))
+    return idx, reads_t, segs["read_offs"], {"ref_s": t1 - t0, "index_build_s": t2 - t1}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from svdss_b200 import build, capi, synth
+    rank, world, local = dist_env()
+    build.build_lib()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsvdss_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    idx, reads_t, read_offs, setup = build_workload(args, rank, local, torch, capi, synth)
+    n_reads = len(read_offs) - 1
+    offs_t = torch.from_numpy(read_offs).to(dev)
+    dreads = capi.DeviceReads(reads_t.data_ptr(), offs_t.data_ptr(), device=local, mem=capi.SVB_MEM_DEVICE,
+                              n_reads=n_reads)
+    # host copy for the end-to-end arm (pinned)
+    total = int(read_offs[-1])
+    host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    host.copy_(reads_t[:total])
+    torch.cuda.synchronize(dev)
+    host_np = host.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        res = []
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            res.append(fn())
+        ev1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return res, float(t[0]), float(t[1]), clocks
+
+    assemble = not args.noassemble
+    # ---- value: batch resident in HBM
+    res, ms_dev, ms_wall, clocks = timed(lambda: idx.sfs_resident(dreads, assemble=assemble), args.steps, args.warmup)
+    ms_step = ms_dev / args.steps
+    kernel_ms = float(np.mean([r.kernel_ms for r in res]))
+    blocks = float(np.mean([r.n_blocks_touched for r in res]))
+    n_ext = float(np.mean([r.n_ext for r in res]))
+    launches = int(sum(r.launches for r in res))
+    n_sfs = res[-1].n_sfs
+    # ---- e2e: host buffers through svb_sfs_batch
+    res_e, ms_dev_e, ms_wall_e, clocks_e = timed(lambda: idx.sfs_batch(host_np, read_offs, assemble=assemble),
+                                                 args.steps, args.warmup)
+    ms_step_e = ms_wall_e / args.steps
+    assert res_e[-1].n_sfs == n_sfs, "resident and host paths disagree"
+    peak, peak_src = hbm_peak()
+    achieved = blocks * idx.block_bytes / (kernel_ms * 1e-3) / 1e9
+    out = {
+        "metric": "SFS-extracted reads/sec (FMD ping-pong search)",
+        "value": world * n_reads / (ms_step * 1e-3),
+        "unit": "reads/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "configs[1]: FMD ping-pong SFS extraction, %.2f Gb reference (%d contigs, both strands "
+                               "indexed), %d smoothed-shaped ~15 kb reads per GPU" % (args.ref_bp / 1e9, args.contigs, n_reads),
+                   "reads_per_gpu": n_reads, "bases_per_gpu": total, "index_symbols": idx.n,
+                   "index_block_bytes": idx.block_bytes, "index_bytes": idx.device_bytes, "assemble": assemble,
+                   "overlap": -1, "parallelism": "read-shard x%d, index replicated, no collective" % world,
+                   "l2": "inputs (%.1f GB reads, %.1f GB index) larger than L2" % (total / 1e9, idx.device_bytes / 1e9),
+                   "sfs_per_step_rank0": int(n_sfs), "extensions_per_step_rank0": int(n_ext),
+                   "index_build_s": round(setup["index_build_s"], 2)},
+        "e2e": {"value": world * n_reads / (ms_step_e * 1e-3), "unit": "reads/s",
+                "h2d_bytes_per_step": int(res_e[-1].h2d_bytes), "d2h_bytes_per_step": int(res_e[-1].d2h_bytes),
+                "ms_per_step": ms_step_e, "device_ms_per_step": ms_dev_e / args.steps},
+        "gpu_launches": launches + int(sum(r.launches for r in res_e)),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_sfs_search<%d>" % (idx.block_bytes // 16), "kernel_ms": kernel_ms,
+                     "algorithmic_bytes": blocks * idx.block_bytes,
+                     "extensions_per_s": n_ext / (kernel_ms * 1e-3)},
+        "clocks": clocks,
+        "clocks_e2e": clocks_e,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(idx, host_np, read_offs, res[-1], assemble, args)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_port_time(fm, host_np, read_offs, target_s, threads):
+    """time the CPU port on a prefix of the reads sized for ~target_s seconds"""
+    n_reads = len(read_offs) - 1
+    probe = min(n_reads, 2000)
+    offs = np.ascontiguousarray(read_offs[:probe + 1])
+    t = time.perf_counter()
+    fm.search_batch(host_np, offs, threads=threads, want_output=False)
+    dt = max(time.perf_counter() - t, 1e-3)
+    m = int(min(n_reads, max(probe, probe * target_s / dt)))
+    offs = np.ascontiguousarray(read_offs[:m + 1])
+    t = time.perf_counter()
+    counts, _, _, _, ext = fm.search_batch(host_np, offs, threads=threads, want_output=False)
+    dt = time.perf_counter() - t
+    return m, dt, int(ext), counts
+
+
+def cpu_baseline(idx, host_np, read_offs, gpu_res, assemble, args):
+    import oracle
+    t = time.time()
+    bwt = idx.bwt()
+    fm = oracle.FMIndex(bwt)
+    del bwt
+    log("cpu_baseline: BWT download + CPU block build %.1fs" % (time.time() - t))
+    threads = oracle.max_threads()
+    m, dt, ext, counts = cpu_port_time(fm, host_np, read_offs, args.cpu_seconds, threads)
+    # parity on the sample: raw SFS sets of the CPU port vs the GPU result
+    parity = None
+    if not assemble:
+        parity = bool(np.array_equal(np.diff(gpu_res.offs[:m + 1]), counts))
+    else:
+        k = min(m, 3000)
+        offs = np.ascontiguousarray(read_offs[:k + 1])
+        c, ooff, qs, ln, _ = fm.search_batch(host_np, offs, threads=threads)
+        ok = True
+        for r in range(k):
+            exp = oracle.assemble(list(zip(qs[ooff[r]:ooff[r + 1]].tolist(), ln[ooff[r]:ooff[r + 1]].tolist())))
+            if exp != gpu_res.per_read(r):
+                ok = False
+                break
+        parity = ok
+    return {"value": m / dt, "unit": "reads/s", "cores": threads, "kind": "port",
+            "sample": "first %d reads of the same batch, %.1f s, %d extensions (%.1f M ext/s)" % (m, dt, ext, ext / dt / 1e6),
+            "parity_vs_gpu_on_sample": parity}
+
+
+def run_reference(args):
+    """CPU port of the reference path on all host cores, same config, bounded sample per step."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    import torch
+    import oracle
+    from svdss_b200 import build, capi, synth
+    build.build_lib()
+    torch.cuda.set_device(local)
+    # setup (untimed): the 6.2 G-symbol BWT is built on the GPU, then handed to the CPU port
+    idx, reads_t, read_offs, setup = build_workload(args, rank, local, torch, capi, synth)
+    total = int(read_offs[-1])
+    # host sample: the first `sample` reads
+    sample = min(len(read_offs) - 1, args.ref_sample)
+    nbytes = int(read_offs[sample])
+    host_np = reads_t[:nbytes].cpu().numpy()
+    offs = np.ascontiguousarray(read_offs[:sample + 1])
+    bwt = idx.bwt()
+    idx.close()
+    del reads_t
+    fm = oracle.FMIndex(bwt)
+    del bwt
+    threads = oracle.max_threads()
+    for _ in range(args.warmup):
+        fm.search_batch(host_np, np.ascontiguousarray(offs[:min(sample, 500) + 1]), threads=threads, want_output=False)
+    t0 = time.perf_counter()
+    ext = 0
+    for _ in range(args.steps):
+        counts, ooff, qs, ln, e = fm.search_batch(host_np, offs, threads=threads)
+        ext += e
+    dt = time.perf_counter() - t0
+    ms_step = dt / args.steps * 1e3
+    v = sample / (ms_step * 1e-3)
+    out = {"impl": "reference", "metric": "SFS-extracted reads/sec (FMD ping-pong search)", "value": v,
+           "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+           "config": {"workload": "configs[1]: FMD ping-pong SFS extraction, %.2f Gb reference, ~15 kb smoothed-shaped reads; "
+                                  "CPU port (oracle/, OpenMP) on a bounded sample" % (args.ref_bp / 1e9),
+                      "index_symbols": int(fm.n), "index_built_on": "gpu (setup, untimed)",
+                      "note": "the reference binary cannot be built offline (ropebwt3/abPOA/ksw2/htslib not vendored)"},
+           "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port",
+                            "sample": "first %d reads per step (%d bases), %.1f M ext/s" % (sample, nbytes, ext / dt / 1e6)},
+           "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-bp", type=int, default=REF_BP)
+    ap.add_argument("--contigs", type=int, default=N_CONTIGS)
+    ap.add_argument("--reads", type=int, default=READS_PER_GPU)
+    ap.add_argument("--block-bytes", type=int, default=0)
+    ap.add_argument("--noassemble", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-sample", type=int, default=20000)
+    args = ap.parse_args()
+    _, world, _ = dist_env()
+    if world != args.gpus and args.impl == "ours" and world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -208,21 +208,32 @@ ORC_API orc_fm_t *orc_fm_build(const uint8_t *bwt, int64_t n) {
   f->nblk = n / 64 + 1;
   if (posix_memalign((void **)&f->blk, 64, (size_t)f->nblk * 64)) return NULL;
   f->cntN = (int64_t *)malloc(sizeof(int64_t) * (size_t)f->nblk);
-  int64_t c[6] = {0, 0, 0, 0, 0, 0};
+  /* pass 1 (parallel): planes + per-block symbol counts (count of A,C,G,T in B[0..3], N in cntN) */
+#pragma omp parallel for schedule(static)
   for (int64_t b = 0; b < f->nblk; ++b) {
     uint64_t *B = f->blk + b * 8;
-    B[0] = (uint64_t)c[1]; B[1] = (uint64_t)c[2]; B[2] = (uint64_t)c[3]; B[3] = (uint64_t)c[4];
-    f->cntN[b] = c[5];
     uint64_t p0 = 0, p1 = 0, p2 = 0;
+    int64_t lc[6] = {0, 0, 0, 0, 0, 0};
     for (int j = 0; j < 64; ++j) {
       int64_t i = b * 64 + j;
       uint8_t s = i < n ? bwt[i] : 7; /* padding code 7 matches no symbol */
-      if (i < n) c[s]++;
+      if (i < n) lc[s]++;
       p0 |= (uint64_t)(s & 1) << j;
       p1 |= (uint64_t)((s >> 1) & 1) << j;
       p2 |= (uint64_t)((s >> 2) & 1) << j;
     }
-    B[4] = p0; B[5] = p1; B[6] = p2; B[7] = 0;
+    B[0] = (uint64_t)lc[1]; B[1] = (uint64_t)lc[2]; B[2] = (uint64_t)lc[3]; B[3] = (uint64_t)lc[4];
+    B[4] = p0; B[5] = p1; B[6] = p2; B[7] = (uint64_t)lc[0];
+    f->cntN[b] = lc[5];
+  }
+  /* pass 2 (serial): exclusive prefix sums */
+  int64_t c[6] = {0, 0, 0, 0, 0, 0};
+  for (int64_t b = 0; b < f->nblk; ++b) {
+    uint64_t *B = f->blk + b * 8;
+    int64_t t;
+    for (int q = 0; q < 4; ++q) { t = (int64_t)B[q]; B[q] = (uint64_t)c[q + 1]; c[q + 1] += t; }
+    t = f->cntN[b]; f->cntN[b] = c[5]; c[5] += t;
+    c[0] += (int64_t)B[7]; B[7] = 0;
   }
   f->acc[0] = 0;
   for (int s = 0; s < 6; ++s) f->acc[s + 1] = f->acc[s] + c[s];

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) k_rank_bench(const SearchParams P, int64_
   unsigned nb = 0;
   for (int64_t q = g0; q < nq; q += ngroups) {
     uint64_t r = splitmix64(seed + (uint64_t)q);
-    uint64_t k = r % (uint64_t)(n - delta);
+    uint64_t k = __umul64hi(r, (uint64_t)(n - delta));  // uniform in [0, n - delta), no 64-bit division
     uint64_t s = (uint64_t)delta;
     int c = 1 + (int)((r >> 60) & 3);
     extend_group<G>(P, c, k, s, lg, gbase, gmask, nb);

@@ -99,3 +99,141 @@ def concat(seqs):
     cat = (np.ascontiguousarray(np.concatenate(seqs), np.uint8) if len(seqs) and offs[-1]
            else np.zeros(0, np.uint8))
     return cat, offs
+
+
+# ---------------------------------------------------------------------------------------------
+# Scale generator (config 2/3): reads are described as *segments* so that the bases can be
+# materialised on the device from a device-resident reference without a 15 GB host round trip.
+# A segment is (kind, start, len, rev): kind 0 = reference slice [start, start+len) of the
+# concatenated contigs (reverse-complemented when rev), kind 1 = `len` hashed random bases.
+# ---------------------------------------------------------------------------------------------
+_M1 = np.int64(-7046029254386353131)   # 0x9E3779B97F4A7C15 as int64
+_M2 = np.int64(-4658895280553007687)   # 0xBF58476D1CE4E5B9 as int64
+
+
+def make_read_segments(contig_offs, n_reads, seed=4, mean_len=15000, sd_len=2000, min_len=5000,
+                       max_len=25000, event_rate=0.5, max_events=4):
+    """Vectorised smoothed-shaped read recipe. contig_offs: int64[m+1] offsets of the contigs in the
+    concatenated reference. Returns dict of numpy arrays describing all segments + read offsets."""
+    rng = np.random.default_rng(seed)
+    contig_offs = np.asarray(contig_offs, np.int64)
+    clen = np.diff(contig_offs)
+    L = np.clip(rng.normal(mean_len, sd_len, n_reads), min_len, max_len).astype(np.int64)
+    ci = rng.choice(len(clen), size=n_reads, p=clen / clen.sum())
+    L = np.minimum(L, clen[ci])
+    st = contig_offs[ci] + (rng.random(n_reads) * (clen[ci] - L + 1)).astype(np.int64)
+    rev = rng.random(n_reads) < 0.5
+    nev = np.minimum(rng.poisson(event_rate, n_reads), max_events)
+    E = max_events
+    kind = rng.integers(0, 3, size=(n_reads, E))            # 0 INS, 1 DEL, 2 clip
+    evlen = rng.integers(30, 501, size=(n_reads, E))
+    cliplen = rng.integers(100, 2001, size=(n_reads, E))
+    pos = np.sort((rng.random((n_reads, E)) * np.maximum(L - 200, 1)[:, None]).astype(np.int64) + 100, axis=1)
+    active = np.arange(E)[None, :] < nev[:, None]
+    # piece list per read: [clip_front?] then for each event e: template[cur:pos_e], (INS random | DEL skip)
+    seg_kind, seg_start, seg_len, seg_rev, seg_read = [], [], [], [], []
+
+    def add(mask, k, s, ln, rv):
+        idx = np.nonzero(mask & (ln > 0))[0]
+        seg_kind.append(np.full(len(idx), k, np.int8)); seg_start.append(s[idx]); seg_len.append(ln[idx])
+        seg_rev.append(rv[idx]); seg_read.append(idx)
+
+    order_key = []  # (read, slot) ordering: slot increases along the read
+    slot = 0
+    is_clip = active & (kind == 2)
+    front = is_clip & (rng.random((n_reads, E)) < 0.5)
+    back = is_clip & ~front
+    zeros = np.zeros(n_reads, np.int64)
+    for e in range(E):   # front clips first
+        add(front[:, e], 1, zeros, cliplen[:, e].astype(np.int64), np.zeros(n_reads, bool)); order_key.append(slot); slot += 1
+    cur = np.zeros(n_reads, np.int64)
+    for e in range(E):
+        ev = active[:, e] & (kind[:, e] != 2)
+        p = np.clip(pos[:, e], cur, L)
+        # template piece [cur, p)
+        a, b = cur, np.where(ev, p, cur)
+        ln = b - a
+        start = np.where(rev, st + L - b, st + a)
+        add(ev, 0, start, ln, rev); order_key.append(slot); slot += 1
+        ins = ev & (kind[:, e] == 0)
+        add(ins, 1, zeros, evlen[:, e].astype(np.int64), np.zeros(n_reads, bool)); order_key.append(slot); slot += 1
+        dele = ev & (kind[:, e] == 1)
+        cur = np.where(ev, p, cur)
+        cur = np.where(dele, np.minimum(cur + evlen[:, e], L), cur)
+    ln = L - cur
+    start = np.where(rev, st, st + cur)
+    add(np.ones(n_reads, bool), 0, start, ln, rev); order_key.append(slot); slot += 1
+    for e in range(E):
+        add(back[:, e], 1, zeros, cliplen[:, e].astype(np.int64), np.zeros(n_reads, bool)); order_key.append(slot); slot += 1
+    slots = np.concatenate([np.full(len(r), k, np.int64) for r, k in zip(seg_read, order_key)])
+    seg_read = np.concatenate(seg_read); seg_kind = np.concatenate(seg_kind)
+    seg_start = np.concatenate(seg_start); seg_len = np.concatenate(seg_len); seg_rev = np.concatenate(seg_rev)
+    o = np.lexsort((slots, seg_read))
+    seg_read, seg_kind, seg_start, seg_len, seg_rev = seg_read[o], seg_kind[o], seg_start[o], seg_len[o], seg_rev[o]
+    seg_out = np.zeros(len(seg_len) + 1, np.int64)
+    seg_out[1:] = np.cumsum(seg_len)
+    read_len = np.bincount(seg_read, weights=seg_len, minlength=n_reads).astype(np.int64)
+    read_offs = np.zeros(n_reads + 1, np.int64)
+    read_offs[1:] = np.cumsum(read_len)
+    return {"kind": seg_kind, "start": seg_start, "len": seg_len, "rev": seg_rev, "read": seg_read,
+            "out": seg_out, "read_offs": read_offs, "seed": seed, "n_events": nev}
+
+
+def _hash_bases_np(gidx, seed):
+    h = (gidx.astype(np.int64) + np.int64(seed)) * _M1
+    h = h ^ ((h >> 29) & np.int64(0x7FFFFFFFF))
+    h = h * _M2
+    return (((h >> 33) & 3) + 1).astype(np.uint8)
+
+
+def materialize_segments_numpy(ref_cat, segs):
+    """Host materialiser (tests)."""
+    total = int(segs["out"][-1])
+    out = np.empty(total, np.uint8)
+    seg_id = np.repeat(np.arange(len(segs["len"])), segs["len"])
+    gidx = np.arange(total, dtype=np.int64)
+    w = gidx - segs["out"][seg_id]
+    rv = segs["rev"][seg_id]
+    src = np.where(rv, segs["start"][seg_id] + segs["len"][seg_id] - 1 - w, segs["start"][seg_id] + w)
+    is_ref = segs["kind"][seg_id] == 0
+    b = ref_cat[np.where(is_ref, src, 0)]
+    b = np.where(rv, comp6(b), b)
+    out[:] = np.where(is_ref, b, _hash_bases_np(gidx, segs["seed"]))
+    return out
+
+
+def materialize_segments_torch(ref_cat_t, segs, out_t=None, chunk_segs=200_000):
+    """Device materialiser: ref_cat_t uint8 CUDA tensor of the concatenated contigs. Returns a uint8
+    CUDA tensor with 64 spare bytes at the end (the search kernel's read-window padding)."""
+    import torch
+    dev = ref_cat_t.device
+    total = int(segs["out"][-1])
+    out = out_t if out_t is not None else torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+    S = len(segs["len"])
+    M1 = torch.tensor(int(_M1), dtype=torch.int64, device=dev)
+    M2 = torch.tensor(int(_M2), dtype=torch.int64, device=dev)
+    for s0 in range(0, S, chunk_segs):
+        s1 = min(S, s0 + chunk_segs)
+        ln = torch.from_numpy(segs["len"][s0:s1]).to(dev)
+        o0 = int(segs["out"][s0]); o1 = int(segs["out"][s1])
+        if o1 == o0:
+            continue
+        seg_id = torch.repeat_interleave(torch.arange(s1 - s0, device=dev), ln)
+        gidx = torch.arange(o0, o1, dtype=torch.int64, device=dev)
+        so = torch.from_numpy(segs["out"][s0:s1]).to(dev)
+        st = torch.from_numpy(segs["start"][s0:s1]).to(dev)
+        rv = torch.from_numpy(segs["rev"][s0:s1]).to(dev)
+        kd = torch.from_numpy(segs["kind"][s0:s1]).to(dev)
+        w = gidx - so[seg_id]
+        rvv = rv[seg_id]
+        src = torch.where(rvv, st[seg_id] + ln[seg_id] - 1 - w, st[seg_id] + w)
+        is_ref = kd[seg_id] == 0
+        b = ref_cat_t[torch.where(is_ref, src, torch.zeros_like(src))]
+        cb = torch.where((b >= 1) & (b <= 4), 5 - b, b)
+        b = torch.where(rvv, cb, b)
+        h = (gidx + int(segs["seed"])) * M1
+        h = h ^ ((h >> 29) & 0x7FFFFFFFF)
+        h = h * M2
+        rb = (((h >> 33) & 3) + 1).to(torch.uint8)
+        out[o0:o1] = torch.where(is_ref, b, rb)
+    return out
