@@ -172,6 +172,8 @@ def run_ours(args):
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
+        if os.environ.get("SVB_PROFILE"):
+            torch.cuda.profiler.start()   # ncu --profile-from-start off: capture the timed region only
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         res = []
@@ -182,6 +184,8 @@ def run_ours(args):
         ev1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
+        if os.environ.get("SVB_PROFILE"):
+            torch.cuda.profiler.stop()
         clocks = sampler.stop()
         ms = ev0.elapsed_time(ev1)
         t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
