@@ -231,7 +231,9 @@ def run_ours(args):
         "gpu_launches": launches + int(sum(r.launches for r in res_e)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "k_sfs_search<%d>" % (idx.block_bytes // 16), "kernel_ms": kernel_ms,
+                     "kernel": ("k_sfs_search_tma<6,1> (thread-per-read, cp.async-staged 128 B blocks)" if idx.block_bytes == 128 and
+                                not os.environ.get("SVB_SEARCH_CFG") else "k_sfs_search cfg=%s" % os.environ.get("SVB_SEARCH_CFG", "4x1")),
+                     "kernel_ms": kernel_ms,
                      "algorithmic_bytes": blocks * idx.block_bytes,
                      "extensions_per_s": n_ext / (kernel_ms * 1e-3)},
         "clocks": clocks,

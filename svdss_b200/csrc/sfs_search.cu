@@ -61,39 +61,68 @@ __device__ __forceinline__ uint4 ldg_slice(const uint4* p) {
 }
 
 // Occ-based backward extension of [k, k+s) by symbol c (1..5) for one G-lane group.
+// A block is NS = G*SPL slices; lane lg owns slices lg, lg+G, .. (SPL of them), so one load
+// instruction of the group covers G*16 contiguous bytes and every 32-byte sector is requested once.
 // lg = lane within group, gbase = first lane of the group, gmask = group's lane mask.
-template <int G>
+template <int G, int SPL>
 __device__ __forceinline__ void extend_group(const SearchParams& P, int c, uint64_t& k, uint64_t& s,
                                              int lg, int gbase, unsigned gmask, unsigned& nblk) {
-  constexpr int LOGB = (G == 4) ? 7 : 8;
+  constexpr int NS = G * SPL;
+  constexpr int LOGB = (NS == 4) ? 7 : 8;
   constexpr unsigned BMASK = (1u << LOGB) - 1;
+  static_assert(NS == 4 || NS == 8, "block is 4 or 8 slices");
   const uint64_t l = k + s;
   const uint64_t bk = k >> LOGB, bl = l >> LOGB;
-  const uint4 sk = ldg_slice(P.blocks + bk * G + lg);
-  uint4 sl = sk;
+  uint4 sk[SPL], sl[SPL];
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) sk[i] = ldg_slice(P.blocks + bk * NS + lg + G * i);
   const bool two = (bl != bk);
-  if (two) sl = ldg_slice(P.blocks + bl * G + lg);
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) sl[i] = sk[i];
+  if (two) {
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) sl[i] = ldg_slice(P.blocks + bl * NS + lg + G * i);
+  }
   nblk += two ? 2u : 1u;
   // superblock bases (L1-resident, tiny): acc[c] + Occ(c, sb << 32)
   const int64_t sbk = __ldg(P.sbase + (k >> 32) * 8 + c);
   const int64_t sbl = __ldg(P.sbase + (l >> 32) * 8 + c);
   const unsigned c0 = (c & 1) ? 0u : ~0u, c1 = (c & 2) ? 0u : ~0u, c2 = (c & 4) ? 0u : ~0u;
-  const unsigned mk = (sk.y ^ c0) & (sk.z ^ c1) & (sk.w ^ c2);
-  const unsigned ml = (sl.y ^ c0) & (sl.z ^ c1) & (sl.w ^ c2);
-  int ok_ = (int)((unsigned)k & BMASK) - 32 * lg;
-  int ol_ = (int)((unsigned)l & BMASK) - 32 * lg;
-  ok_ = max(0, min(32, ok_));
-  ol_ = max(0, min(32, ol_));
-  const unsigned maskk = ok_ >= 32 ? ~0u : ((1u << ok_) - 1u);
-  const unsigned maskl = ol_ >= 32 ? ~0u : ((1u << ol_) - 1u);
-  unsigned v = __popc(mk & maskk) | (__popc(ml & maskl) << 16);
+  const int offk = (int)((unsigned)k & BMASK), offl = (int)((unsigned)l & BMASK);
+  unsigned v = 0;
+#pragma unroll
+  for (int i = 0; i < SPL; ++i) {
+    const int j32 = 32 * (lg + G * i);
+    const unsigned mk = (sk[i].y ^ c0) & (sk[i].z ^ c1) & (sk[i].w ^ c2);
+    const unsigned ml = (sl[i].y ^ c0) & (sl[i].z ^ c1) & (sl[i].w ^ c2);
+    const int nk_ = max(0, min(32, offk - j32));
+    const int nl_ = max(0, min(32, offl - j32));
+    const unsigned maskk = nk_ >= 32 ? ~0u : ((1u << nk_) - 1u);
+    const unsigned maskl = nl_ >= 32 ? ~0u : ((1u << nl_) - 1u);
+    v += __popc(mk & maskk) | (__popc(ml & maskl) << 16);
+  }
 #pragma unroll
   for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(gmask, v, o);
   unsigned ck, cl;
-  if (G == 8 || c <= 4) {
-    ck = __shfl_sync(gmask, sk.x, gbase + c - 1);
-    cl = __shfl_sync(gmask, sl.x, gbase + c - 1);
-  } else {  // G == 4, symbol N: side array
+  if (NS == 8 || c <= 4) {
+    // count slot c-1 lives in slice c-1 = lane (c-1) % G, register (c-1) / G
+    const int slot = c - 1;
+    // mask-select of the register (keeps sk/sl in registers: an if-chain becomes a local array)
+    unsigned xk = 0, xl = 0;
+    const int reg = slot / G;
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      const unsigned m = (reg == i) ? ~0u : 0u;
+      xk |= sk[i].x & m;
+      xl |= sl[i].x & m;
+    }
+    if (G > 1) {
+      ck = __shfl_sync(gmask, xk, gbase + (slot % G));
+      cl = __shfl_sync(gmask, xl, gbase + (slot % G));
+    } else {
+      ck = xk; cl = xl;
+    }
+  } else {  // 64-byte blocks, symbol N: side array
     ck = __ldg(P.cntN + bk);
     cl = __ldg(P.cntN + bl);
   }
@@ -117,7 +146,7 @@ struct ReadWin {
   // character at global byte position gp, walking in direction dir (+1 / -1); group-uniform
   __device__ __forceinline__ int get(const uint8_t* seq, int64_t gp, int dir, int lg, int gbase,
                                      unsigned gmask) {
-    constexpr int LOGW = (G == 4) ? 4 : 5;
+    constexpr int LOGW = (G == 1) ? 2 : (G == 2) ? 3 : (G == 4) ? 4 : 5;
     const int64_t w = gp >> LOGW;
     if (w != id) {
       if (w == id + dir && id >= 0) cur = nxt;
@@ -126,13 +155,13 @@ struct ReadWin {
       const int64_t wn = w + dir;
       nxt = wn >= 0 ? load(seq, wn, lg) : 0u;  // buffer is padded by one window at the end
     }
-    const unsigned v = __shfl_sync(gmask, cur, gbase + (int)((gp >> 2) & (G - 1)));
+    const unsigned v = G > 1 ? __shfl_sync(gmask, cur, gbase + (int)((gp >> 2) & (G - 1))) : cur;
     return (int)((v >> ((gp & 3) * 8)) & 0xffu);
   }
 };
 
-template <int G>
-__global__ void __launch_bounds__(256) k_sfs_search(const SearchParams P) {
+template <int G, int SPL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_sfs_search(const SearchParams P) {
   const int lane = threadIdx.x & 31;
   const int lg = lane & (G - 1);
   const int gbase = lane & ~(G - 1);
@@ -190,7 +219,7 @@ __global__ void __launch_bounds__(256) k_sfs_search(const SearchParams P) {
       if (!have) {
         unsigned long long w = 0;
         if (lg == 0) w = atomicAdd(P.work, 1ull);
-        w = __shfl_sync(gmask, w, gbase);
+        if (G > 1) w = __shfl_sync(gmask, w, gbase);
         if (w >= (unsigned long long)P.n_reads) {
           alive = false;
         } else {
@@ -256,14 +285,14 @@ __global__ void __launch_bounds__(256) k_sfs_search(const SearchParams P) {
       }
     }
     if (do_ext) {
-      extend_group<G>(P, c, k, s, lg, gbase, gmask, n_blk);
+      extend_group<G, SPL>(P, c, k, s, lg, gbase, gmask, n_blk);
       ++n_ext;
     }
   }
 }
 
 // ------------------------------------------------------------------------------ rank kernels
-template <int G>
+template <int G, int SPL>
 __global__ void k_rank2a(const SearchParams P, const int64_t* __restrict__ qk, const int64_t* __restrict__ ql,
                          int64_t nq, int64_t n, int64_t* __restrict__ ok6, int64_t* __restrict__ ol6) {
   const int lane = threadIdx.x & 31;
@@ -272,20 +301,19 @@ __global__ void k_rank2a(const SearchParams P, const int64_t* __restrict__ qk, c
   const unsigned gmask = ((1u << G) - 1u) << gbase;
   const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
   const int64_t g0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  constexpr int LOGB = (G == 4) ? 7 : 8;
   for (int64_t q = g0; q < nq; q += ngroups) {
     int64_t kk = qk[q], ll = ql[q];
     int64_t sumk = 0, suml = 0;
     for (int c = 1; c <= 5; ++c) {
       uint64_t k = (uint64_t)kk, s = (uint64_t)(ll - kk);
       unsigned nb = 0;
-      extend_group<G>(P, c, k, s, lg, gbase, gmask, nb);
+      extend_group<G, SPL>(P, c, k, s, lg, gbase, gmask, nb);
       int64_t okc = (int64_t)k - P.acc[c], olc = okc + (int64_t)s;
       sumk += okc; suml += olc;
       if (lg == 0) { ok6[q * 6 + c] = okc; ol6[q * 6 + c] = olc; }
     }
     if (lg == 0) { ok6[q * 6] = kk - sumk; ol6[q * 6] = ll - suml; }
-    (void)LOGB; (void)n;
+    (void)n;
   }
 }
 
@@ -297,7 +325,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 
 // one extension per query, queries generated on the fly: k uniform in [0, n - delta)
-template <int G>
+template <int G, int SPL>
 __global__ void __launch_bounds__(256) k_rank_bench(const SearchParams P, int64_t nq, int64_t n, int64_t delta,
                                                     uint64_t seed, unsigned long long* __restrict__ sink,
                                                     unsigned long long* __restrict__ blocks_touched) {
@@ -314,13 +342,330 @@ __global__ void __launch_bounds__(256) k_rank_bench(const SearchParams P, int64_
     uint64_t k = __umul64hi(r, (uint64_t)(n - delta));  // uniform in [0, n - delta), no 64-bit division
     uint64_t s = (uint64_t)delta;
     int c = 1 + (int)((r >> 60) & 3);
-    extend_group<G>(P, c, k, s, lg, gbase, gmask, nb);
+    extend_group<G, SPL>(P, c, k, s, lg, gbase, gmask, nb);
     acc += k + s;
   }
   if (lg == 0) {
     atomicAdd(blocks_touched, (unsigned long long)nb);
     if (acc == 0x123456789ULL) atomicAdd(sink, acc);
   }
+}
+
+// ------------------------------------------------------------------------------ v2 kernel
+// Thread-per-read state machine + TMA-staged index blocks (128-byte blocks only).
+//
+// ncu on the lane-group kernel showed it issue-bound (68 % issue slots, ~49 warp instructions per
+// extension: every lane of a group replays the whole state machine) with only 4-8 dependent-load
+// chains per warp.  Here every THREAD walks its own read, so a warp carries 32 chains, and the
+// 128-byte index blocks are fetched by the TMA unit: one cp.async.bulk (UBLKCP) per block straight
+// into the thread's shared-memory slot, completion counted on a per-warp mbarrier.  No register is
+// tied up by a load in flight; one request = one full 128-byte line.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// per-thread read window: 8 bases in a u64 + the prefetched neighbour in walking direction.
+// A direction switch keeps `cur` (the pivot base is in it) and only re-aims the prefetch, so the
+// warp never waits on a read-window load except at the first base of a read.
+struct ReadWin1 {
+  uint64_t cur, nxt;
+  int64_t id, nid;  // window ids held in cur / nxt (-1 = none)
+  __device__ __forceinline__ void reset() { id = -1; nid = -1; cur = 0; nxt = 0; }
+  __device__ __forceinline__ int get(const uint8_t* seq, int64_t gp, int dir) {
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(seq);
+    const int64_t w = gp >> 3;
+    if (w != id) {
+      cur = (w == nid) ? nxt : __ldg(p + w);
+      id = w;
+    }
+    const int64_t wn = w + dir;
+    if (wn != nid) {
+      nid = wn;
+      nxt = wn >= 0 ? __ldg(p + wn) : 0ull;  // consumed >= 1 step later
+    }
+    return (int)((cur >> ((gp & 7) * 8)) & 0xffull);
+  }
+};
+
+// issue the TMA copies of the block(s) needed by the extension of [k, k+s); returns bl != bk
+__device__ __forceinline__ bool tma_issue(const SearchParams& P, uint64_t k, uint64_t s, uint32_t slot, uint32_t bar) {
+  const uint64_t bk = k >> 8, bl = (k + s) >> 8;
+  const bool two = bl != bk;
+  mbar_arrive_expect_tx(bar, two ? 256u : 128u);
+  bulk_g2s(slot, P.blocks + bk * 8, 128u, bar);
+  if (two) bulk_g2s(slot + 128u, P.blocks + bl * 8, 128u, bar);
+  return two;
+}
+
+// finish the extension from the staged blocks (thread-local; slice order rotated by lane so that
+// the 8 threads of an LDS.128 phase hit 8 different 16-byte bank groups)
+__device__ __forceinline__ void tma_consume(const SearchParams& P, const uint4* slot, bool two, int c, uint64_t& k,
+                                            uint64_t& s, int lane) {
+  const uint64_t l = k + s;
+  const int offk = (int)((unsigned)k & 255u), offl = (int)((unsigned)l & 255u);
+  const unsigned c0 = (c & 1) ? 0u : ~0u, c1 = (c & 2) ? 0u : ~0u, c2 = (c & 4) ? 0u : ~0u;
+  unsigned pk = 0, pl = 0, ck = 0, cl = 0;
+  const uint4* sl_ptr = two ? slot + 8 : slot;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = (i + lane) & 7;
+    const uint4 a = slot[j];
+    const uint4 b = sl_ptr[j];
+    const unsigned mk = (a.y ^ c0) & (a.z ^ c1) & (a.w ^ c2);
+    const unsigned ml = (b.y ^ c0) & (b.z ^ c1) & (b.w ^ c2);
+    const int nk_ = max(0, min(32, offk - 32 * j));
+    const int nl_ = max(0, min(32, offl - 32 * j));
+    pk += __popc(mk & (nk_ >= 32 ? ~0u : ((1u << nk_) - 1u)));
+    pl += __popc(ml & (nl_ >= 32 ? ~0u : ((1u << nl_) - 1u)));
+    const unsigned sel = (j == c - 1) ? ~0u : 0u;
+    ck |= a.x & sel;
+    cl |= b.x & sel;
+  }
+  const int64_t sbk = __ldg(P.sbase + (k >> 32) * 8 + c);
+  const int64_t sbl = __ldg(P.sbase + (l >> 32) * 8 + c);
+  const uint64_t nk = (uint64_t)sbk + ck + pk;
+  const uint64_t nl = (uint64_t)sbl + cl + pl;
+  k = nk;
+  s = nl - nk;
+}
+
+// ---- LDGSTS variant of the staging: the warp copies its 32 threads' blocks cooperatively, 8 lanes
+// x 16 bytes per block and 4 blocks per round, so every request is one coalesced 128-byte line and
+// no per-lane TMA issue loop (UBLKCP takes warp-uniform operands) is needed.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// bk/bl: block ids of this thread's pending extension (bl == bk if one block, both NOBLK if none)
+constexpr uint32_t NOBLK = 0xffffffffu;
+__device__ __forceinline__ void cpa_fetch(const SearchParams& P, uint32_t bk, uint32_t bl, uint32_t warp_stage_s,
+                                          int lane) {
+  const int sub = lane >> 3, j = lane & 7;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int t = 4 * r + sub;
+    const uint32_t xk = __shfl_sync(0xffffffffu, bk, t);
+    const uint32_t xl = __shfl_sync(0xffffffffu, bl, t);
+    const uint32_t dst = warp_stage_s + (uint32_t)(t * 256 + j * 16);
+    if (xk != NOBLK) cp_async16(dst, P.blocks + (uint64_t)xk * 8 + j);
+    if (xl != xk) cp_async16(dst + 128u, P.blocks + (uint64_t)xl * 8 + j);
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
+constexpr int TMA_WARPS = 4;  // warps per CTA; 8 KB of staging per warp
+
+template <int MINB, int MODE>  // MODE 0: TMA bulk copies (UBLKCP), 1: cooperative cp.async (LDGSTS)
+__global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const SearchParams P) {
+  __shared__ __align__(128) uint4 stage[TMA_WARPS * 32 * 16];  // [warp][lane][2 blocks][8 slices]
+  __shared__ __align__(8) uint64_t bars[TMA_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t bar = smem_u32(&bars[warp]);
+  uint4* my = stage + (warp * 32 + lane) * 16;
+  const uint32_t my_s = smem_u32(my);
+  if (lane == 0) {
+    mbar_init(bar, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  uint32_t parity = 0;
+
+  bool alive = true, have = false;
+  int phase = 0;
+  uint32_t ridx = 0;
+  int64_t roff = 0;
+  int len = 0, pos = 0, begin = 0;
+  uint64_t k = 0, s = 0;
+  int chain_qs = -1, chain_end = -1;
+  unsigned n_ext = 0, n_blk = 0;
+  ReadWin1 win;
+  win.reset();
+
+  auto emit = [&](int qs, int ln) {
+    unsigned long long o = atomicAdd(P.out_count, 1ull);
+    if (o < P.out_cap) {
+      uint32_t sk = P.assemble ? (uint32_t)qs : ~(uint32_t)qs;
+      P.out_key[o] = ((uint64_t)ridx << 32) | sk;
+      P.out_len[o] = (uint32_t)ln;
+    }
+  };
+  auto on_sfs = [&](int qs, int ln) {
+    if (!P.assemble) { emit(qs, ln); return; }
+    if (chain_qs >= 0 && qs + ln > chain_qs) {
+      chain_qs = qs;
+    } else {
+      if (chain_qs >= 0) emit(chain_qs, chain_end - chain_qs);
+      chain_qs = qs;
+      chain_end = qs + ln;
+    }
+  };
+  auto finish_read = [&]() {
+    if (P.assemble && chain_qs >= 0) emit(chain_qs, chain_end - chain_qs);
+    chain_qs = -1;
+    have = false;
+    atomicAdd(P.stats + 0, (unsigned long long)n_ext);
+    atomicAdd(P.stats + 1, (unsigned long long)n_blk);
+    n_ext = 0; n_blk = 0;
+  };
+  auto set_intv = [&](int c0) {
+    k = (uint64_t)P.acc[c0];
+    s = (uint64_t)(P.acc[c0 + 1] - P.acc[c0]);  // rb3_fmd_set_intv (ping_pong.cpp:12,30)
+  };
+
+  while (__any_sync(0xffffffffu, alive)) {
+    int c = 0;
+    bool do_ext = false;
+    if (alive) {
+      if (!have) {
+        const unsigned long long w = atomicAdd(P.work, 1ull);
+        if (w >= (unsigned long long)P.n_reads) {
+          alive = false;
+        } else {
+          ridx = P.order ? P.order[w] : (uint32_t)w;
+          roff = P.offs[ridx];
+          len = (int)(P.offs[ridx + 1] - roff);
+          if (len > 0) {
+            have = true;
+            phase = 0;
+            pos = len - 1;
+            win.reset();
+            set_intv(win.get(P.seq, roff + pos, -1));
+          }
+        }
+      }
+      // state machine of ping_pong.cpp:15-47, advanced to the next pending extension
+      while (have && !do_ext) {
+        if (phase == 0) {
+          if (s != 0 && pos > 0) {
+            --pos;
+            c = win.get(P.seq, roff + pos, -1);
+            do_ext = true;
+          } else if (s != 0) {
+            finish_read();  // reached the read start still matching (ping_pong.cpp:24-25)
+          } else {
+            begin = pos;
+            phase = 1;
+            set_intv(comp6(win.get(P.seq, roff + pos, +1)));
+          }
+        } else {
+          if (s != 0 && pos + 1 < len) {
+            ++pos;
+            c = comp6(win.get(P.seq, roff + pos, +1));
+            do_ext = true;
+          } else {
+            if (s != 0) ++pos;
+            on_sfs(begin, pos - begin + 1);  // ping_pong.cpp:39-41
+            if (begin == 0) {
+              finish_read();
+            } else {
+              int nb = (P.overlap == 0) ? begin - 1 : pos + P.overlap;  // ping_pong.cpp:44-47
+              if (nb < 0) {
+                finish_read();
+              } else {
+                if (nb > len - 1) nb = len - 1;
+                pos = nb;
+                phase = 0;
+                set_intv(win.get(P.seq, roff + pos, -1));
+              }
+            }
+          }
+        }
+      }
+    }
+    bool two = false;
+    if (MODE == 0) {
+      if (do_ext) two = tma_issue(P, k, s, my_s, bar);
+      else mbar_arrive(bar);
+      while (!mbar_try_wait(bar, parity)) {}
+      parity ^= 1u;
+    } else {
+      const uint32_t bk = do_ext ? (uint32_t)(k >> 8) : NOBLK;
+      const uint32_t bl = do_ext ? (uint32_t)((k + s) >> 8) : NOBLK;
+      two = bl != bk;
+      cpa_fetch(P, bk, bl, smem_u32(stage + warp * 32 * 16), lane);
+    }
+    if (do_ext) {
+      tma_consume(P, my, two, c, k, s, lane);
+      ++n_ext;
+      n_blk += two ? 2u : 1u;
+    }
+    if (MODE == 1) __syncwarp();  // staging slots are rewritten by other lanes next iteration
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TMA_WARPS * 32) k_rank_bench_tma(const SearchParams P, int64_t nq, int64_t n,
+                                                                   int64_t delta, uint64_t seed,
+                                                                   unsigned long long* __restrict__ sink,
+                                                                   unsigned long long* __restrict__ blocks_touched) {
+  __shared__ __align__(128) uint4 stage[TMA_WARPS * 32 * 16];
+  __shared__ __align__(8) uint64_t bars[TMA_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t bar = smem_u32(&bars[warp]);
+  uint4* my = stage + (warp * 32 + lane) * 16;
+  const uint32_t my_s = smem_u32(my);
+  if (lane == 0) {
+    mbar_init(bar, 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  uint32_t parity = 0;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t iters = (nq + nthreads - 1) / nthreads;
+  unsigned long long acc = 0;
+  unsigned nb = 0;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t q = t0 + it * nthreads;
+    const bool act = q < nq;
+    uint64_t r = splitmix64(seed + (uint64_t)q);
+    uint64_t k = __umul64hi(r, (uint64_t)(n - delta));
+    uint64_t s = (uint64_t)delta;
+    int c = 1 + (int)((r >> 60) & 3);
+    bool two = false;
+    if (MODE == 0) {
+      if (act) two = tma_issue(P, k, s, my_s, bar);
+      else mbar_arrive(bar);
+      while (!mbar_try_wait(bar, parity)) {}
+      parity ^= 1u;
+    } else {
+      const uint32_t bk = act ? (uint32_t)(k >> 8) : NOBLK;
+      const uint32_t bl = act ? (uint32_t)((k + s) >> 8) : NOBLK;
+      two = bl != bk;
+      cpa_fetch(P, bk, bl, smem_u32(stage + warp * 32 * 16), lane);
+    }
+    if (act) {
+      tma_consume(P, my, two, c, k, s, lane);
+      nb += two ? 2u : 1u;
+      acc += k + s;
+    }
+    if (MODE == 1) __syncwarp();
+  }
+  atomicAdd(blocks_touched, (unsigned long long)nb);
+  if (acc == 0x123456789ULL) atomicAdd(sink, acc);
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -391,6 +736,41 @@ static int persistent_grid(K kernel, int threads, int device, int* grid) {
   return SVB_OK;
 }
 
+// ---- lane-group configurations: G lanes x SPL slices per lane cover one block (G*SPL = 4 or 8
+// slices).  Fewer lanes per read = more independent chains per warp = more loads in flight.
+// Selected by SVB_SEARCH_CFG ("8x1", "4x2", "2x4", "1x8" for 128-byte blocks; "4x1", "2x2", "1x4"
+// for 64-byte blocks; "cpa" / "tma" = the thread-per-read staged kernels); the default is the
+// fastest measured on B200.
+static int pick_cfg(int slices, int* G) {
+  const char* e = getenv("SVB_SEARCH_CFG");
+  // defaults: 128-byte blocks -> thread-per-read kernel with cooperative cp.async staging ("cpa");
+  //           64-byte blocks  -> 4 lanes per read
+  int g = (slices == 8) ? -1 : 4;
+  if (e && (strcmp(e, "tma") == 0 || strcmp(e, "cpa") == 0)) {  // staged kernels: 128-byte blocks only
+    *G = (slices == 8) ? (e[0] == 't' ? 0 : -1) : g;
+    return SVB_OK;
+  }
+  if (e && *e) {
+    int a = 0, b = 0;
+    if (sscanf(e, "%dx%d", &a, &b) == 2 && a * b == slices && (a == 1 || a == 2 || a == 4 || a == 8)) g = a;
+    else if (sscanf(e, "%dx%d", &a, &b) == 2 && (a * b == 4 || a * b == 8)) { /* other block size: keep default */ }
+    else { set_error("SVB_SEARCH_CFG=%s is not one of tma, cpa, GxS", e); return SVB_EINVAL; }
+  }
+  *G = g;
+  return SVB_OK;
+}
+
+#define SVB_DISPATCH_CFG(slices, G, CALL)                                         \
+  do {                                                                            \
+    if ((slices) == 8) {                                                          \
+      if ((G) == 8) { CALL(8, 1, 5); } else if ((G) == 4) { CALL(4, 2, 5); }      \
+      else if ((G) == 2) { CALL(2, 4, 3); } else { CALL(1, 8, 2); }               \
+    } else {                                                                      \
+      if ((G) == 4) { CALL(4, 1, 5); } else if ((G) == 2) { CALL(2, 2, 4); }      \
+      else { CALL(1, 4, 3); }                                                     \
+    }                                                                             \
+  } while (0)
+
 struct SearchScratch {
   unsigned long long* d_ctr = nullptr;  // [0] work [1] out_count [2] ext [3] blocks
   uint64_t* d_key = nullptr; uint64_t* d_key2 = nullptr;
@@ -422,9 +802,18 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   // first guess of output capacity; exact count is known after the run, rerun once if it overflowed
   unsigned long long cap = assemble ? (unsigned long long)(4 * n_reads + 1024)
                                     : (unsigned long long)(R->total / 8 + 64 * n_reads + 1024);
-  int grid = 0;
-  if (d.G == 4) SVB_TRY(persistent_grid(k_sfs_search<4>, 256, d.device, &grid));
-  else SVB_TRY(persistent_grid(k_sfs_search<8>, 256, d.device, &grid));
+  int grid = 0, cfgG = 0;
+  SVB_TRY(pick_cfg(d.G, &cfgG));
+  const int tma_minb = 6;
+  if (cfgG == 0) {
+    SVB_TRY(persistent_grid(k_sfs_search_tma<tma_minb, 0>, TMA_WARPS * 32, d.device, &grid));
+  } else if (cfgG == -1) {
+    SVB_TRY(persistent_grid(k_sfs_search_tma<tma_minb, 1>, TMA_WARPS * 32, d.device, &grid));
+  } else {
+#define SVB_GRID(g, spl, minb) SVB_TRY(persistent_grid(k_sfs_search<g, spl, minb>, 256, d.device, &grid))
+    SVB_DISPATCH_CFG(d.G, cfgG, SVB_GRID);
+#undef SVB_GRID
+  }
   cudaEvent_t e0, e1;
   SVB_CUDA(cudaEventCreate(&e0));
   SVB_CUDA(cudaEventCreate(&e1));
@@ -438,8 +827,15 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
     P.work = S.d_ctr + 0; P.out_count = S.d_ctr + 1; P.stats = S.d_ctr + 2;
     P.out_key = S.d_key; P.out_len = S.d_len; P.out_cap = cap;
     SVB_CUDA(cudaEventRecord(e0, st));
-    if (d.G == 4) k_sfs_search<4><<<grid, 256, 0, st>>>(P);
-    else k_sfs_search<8><<<grid, 256, 0, st>>>(P);
+    if (cfgG == 0) {
+      k_sfs_search_tma<tma_minb, 0><<<grid, TMA_WARPS * 32, 0, st>>>(P);
+    } else if (cfgG == -1) {
+      k_sfs_search_tma<tma_minb, 1><<<grid, TMA_WARPS * 32, 0, st>>>(P);
+    } else {
+#define SVB_LAUNCH(g, spl, minb) k_sfs_search<g, spl, minb><<<grid, 256, 0, st>>>(P)
+      SVB_DISPATCH_CFG(d.G, cfgG, SVB_LAUNCH);
+#undef SVB_LAUNCH
+    }
     SVB_CUDA(cudaGetLastError());
     SVB_CUDA(cudaEventRecord(e1, st));
     SVB_CUDA(cudaMemcpyAsync(ctr, S.d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, st));
@@ -620,9 +1016,13 @@ int svb_rank2a(const svb_index_t* idx, const int64_t* k, const int64_t* l, int64
   SearchParams P;
   fill_params(P, d);
   int64_t groups = std::min<int64_t>(n, 148 * 64);
-  unsigned grid = (unsigned)((groups * d.G + 255) / 256);
-  if (d.G == 4) k_rank2a<4><<<grid, 256>>>(P, dk, dl, n, d.n, dok, dol);
-  else k_rank2a<8><<<grid, 256>>>(P, dk, dl, n, d.n, dok, dol);
+  int cfgG = 0;
+  SVB_TRY(pick_cfg(d.G, &cfgG));
+  if (cfgG <= 0) cfgG = 8;  // the all-symbol rank entry uses the lane-group kernel
+  unsigned grid = (unsigned)((groups * cfgG + 255) / 256);
+#define SVB_LAUNCH(g, spl, minb) k_rank2a<g, spl><<<grid, 256>>>(P, dk, dl, n, d.n, dok, dol)
+  SVB_DISPATCH_CFG(d.G, cfgG, SVB_LAUNCH);
+#undef SVB_LAUNCH
   SVB_CUDA(cudaGetLastError());
   SVB_CUDA(cudaMemcpy(ok6, dok, n * 48, cudaMemcpyDeviceToHost));
   SVB_CUDA(cudaMemcpy(ol6, dol, n * 48, cudaMemcpyDeviceToHost));
@@ -641,9 +1041,17 @@ int svb_rank_bench(const svb_index_t* idx, int64_t nq, int64_t delta, uint64_t s
   SVB_CUDA(cudaMemset(dctr, 0, 16));
   SearchParams P;
   fill_params(P, d);
-  int grid = 0;
-  if (d.G == 4) SVB_TRY(persistent_grid(k_rank_bench<4>, 256, d.device, &grid));
-  else SVB_TRY(persistent_grid(k_rank_bench<8>, 256, d.device, &grid));
+  int grid = 0, cfgG = 0;
+  SVB_TRY(pick_cfg(d.G, &cfgG));
+  if (cfgG == 0) {
+    SVB_TRY(persistent_grid(k_rank_bench_tma<0>, TMA_WARPS * 32, d.device, &grid));
+  } else if (cfgG == -1) {
+    SVB_TRY(persistent_grid(k_rank_bench_tma<1>, TMA_WARPS * 32, d.device, &grid));
+  } else {
+#define SVB_GRID(g, spl, minb) SVB_TRY(persistent_grid(k_rank_bench<g, spl>, 256, d.device, &grid))
+    SVB_DISPATCH_CFG(d.G, cfgG, SVB_GRID);
+#undef SVB_GRID
+  }
   cudaEvent_t e0, e1;
   SVB_CUDA(cudaEventCreate(&e0));
   SVB_CUDA(cudaEventCreate(&e1));
@@ -651,8 +1059,15 @@ int svb_rank_bench(const svb_index_t* idx, int64_t nq, int64_t delta, uint64_t s
   for (int it = -1; it < iters; ++it) {
     if (it == 0) { SVB_CUDA(cudaMemset(dctr, 0, 16)); SVB_CUDA(cudaEventRecord(e0, 0)); }
     uint64_t sd = seed + 0x1000003ULL * (uint64_t)(it + 1);
-    if (d.G == 4) k_rank_bench<4><<<grid, 256>>>(P, nq, d.n, delta, sd, dctr, dctr + 1);
-    else k_rank_bench<8><<<grid, 256>>>(P, nq, d.n, delta, sd, dctr, dctr + 1);
+    if (cfgG == 0) {
+      k_rank_bench_tma<0><<<grid, TMA_WARPS * 32>>>(P, nq, d.n, delta, sd, dctr, dctr + 1);
+    } else if (cfgG == -1) {
+      k_rank_bench_tma<1><<<grid, TMA_WARPS * 32>>>(P, nq, d.n, delta, sd, dctr, dctr + 1);
+    } else {
+#define SVB_LAUNCH(g, spl, minb) k_rank_bench<g, spl><<<grid, 256>>>(P, nq, d.n, delta, sd, dctr, dctr + 1)
+      SVB_DISPATCH_CFG(d.G, cfgG, SVB_LAUNCH);
+#undef SVB_LAUNCH
+    }
   }
   SVB_CUDA(cudaGetLastError());
   SVB_CUDA(cudaEventRecord(e1, 0));

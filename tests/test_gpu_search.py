@@ -182,3 +182,21 @@ def test_medium_scale_properties():
         for x, y in zip(a, a[1:]):
             assert x[0] + x[1] <= y[0]
         assert oracle.assemble(a) == a
+
+
+@pytest.mark.parametrize("cfg,bb", [("cpa", 128), ("tma", 128), ("8x1", 128), ("4x2", 128), ("2x4", 128), ("1x8", 128),
+                                    ("4x1", 64), ("2x2", 64), ("1x4", 64)])
+def test_all_kernel_configs_agree(cfg, bb, monkeypatch):
+    """every lane-group / staging configuration of the search kernel returns the oracle's SFS sets"""
+    monkeypatch.setenv("SVB_SEARCH_CFG", cfg)
+    contigs = synth.make_reference(400_000, seed=31, contigs=3)
+    reads = synth.make_reads(contigs, 300, seed=32, mean_len=6000, sd_len=1500, min_len=300, max_len=12000)
+    reads += synth.make_reads(contigs, 60, seed=33, mean_len=3000, sd_len=500, min_len=300, max_len=5000, raw_hifi=True)
+    T, SA, bwt = oracle_index(contigs)
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs, block_bytes=bb)
+    exp, ext = fm_results(oracle.FMIndex(bwt), reads)
+    got, res = _gpu_sfs(idx, reads, assemble=False)
+    assert got == exp and res.n_ext == ext
+    got_asm, _ = _gpu_sfs(idx, reads, assemble=True)
+    assert got_asm == [oracle.assemble(e) for e in exp]
