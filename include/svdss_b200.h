@@ -130,6 +130,35 @@ SVB_API int svb_sfs_resident(const svb_index_t* idx, const svb_reads_t* reads, i
                              int assemble, svb_sfs_out_t* out);
 SVB_API void svb_sfs_out_free(svb_sfs_out_t* out);
 
+/* ------------------------------------------------------------------ ksw2 realignment (a6) -- */
+
+typedef struct {
+  int64_t n_pairs;
+  int32_t* score;       /* ez.score per pair (KSW_NEG_INF = -0x40000000 for an empty query/target) */
+  int64_t* cigar_offs;  /* n_pairs + 1, indexes cigar[]                                          */
+  uint32_t* cigar;      /* ez.cigar: len << 4 | op, op 0=M 1=I 2=D (caller.cpp:352-354)          */
+  int64_t n_cigar;
+  int64_t cells;        /* sum of ql*tl                                                          */
+  float kernel_ms;      /* DP + traceback kernels, CUDA events                                   */
+  float device_ms;      /* whole call on the device incl. H2D/D2H                                */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int32_t launches;
+  int32_t waves;        /* batches the pairs were split into to bound traceback memory           */
+} svb_ksw_out_t;
+
+/* ksw_extd2_sse(0, ql, qs, tl, ts, 5, mat, gapo, gape, gapo2, gape2, -1, -1, -1, 0, &ez) for every
+ * (query = consensus, target = reference window) pair of a batch (caller.cpp:332-355): global
+ * alignment, two-piece affine gaps, full matrix, score + left-aligned CIGAR.  Sequences are
+ * _char26_table codes 0..4 (caller.hpp:25-37).  `sc_n` is the score of any pair involving code 4:
+ * ksw2 without KSW_EZ_GENERIC_SC uses -gape2 when mat[24] == 0, which is what the reference passes.
+ * HOST buffers. */
+SVB_API int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_offs /* n_pairs+1 */,
+                                const uint8_t* t_concat, const int64_t* t_offs /* n_pairs+1 */,
+                                int64_t n_pairs, int match, int mismatch, int sc_n, int gapo, int gape,
+                                int gapo2, int gape2, int device, svb_ksw_out_t* out);
+SVB_API void svb_ksw_out_free(svb_ksw_out_t* out);
+
 #ifdef __cplusplus
 }
 #endif

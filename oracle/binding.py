@@ -173,3 +173,61 @@ class FMIndex:
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+# ------------------------------------------------------------------ ksw2 extd2 (oracle/ksw_oracle.c)
+KSW_NEG_INF = -0x40000000
+KSW_PARAMS = dict(a=1, b=-9, sc_n=-1, q=16, e=2, q2=41, e2=1)   # caller.cpp:333-349
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+CHAR26 = np.full(256, 4, np.uint8)   # caller.hpp:25-37 (_char26_table)
+for _i, _v in ((0, 0), (1, 1), (2, 2), (3, 3)):
+    CHAR26[_i] = _v
+for _ch, _v in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("U", 3)):
+    CHAR26[ord(_ch)] = _v
+    CHAR26[ord(_ch.lower())] = _v
+
+
+def _ksw_lib():
+    L = lib()
+    if not hasattr(L, "_ksw_ready"):
+        ci = C.c_int
+        L.orc_ksw_extd2.restype = ci
+        L.orc_ksw_extd2.argtypes = [ci, _u8p, ci, _u8p, ci, ci, ci, ci, ci, ci, ci, _u32p, ci, C.POINTER(ci)]
+        L.orc_affine2_score.restype = ci
+        L.orc_affine2_score.argtypes = [ci, _u8p, ci, _u8p, ci, ci, ci, ci, ci, ci, ci]
+        L.orc_cigar_score.restype = ci
+        L.orc_cigar_score.argtypes = [ci, _u8p, ci, _u8p, ci, ci, ci, ci, ci, ci, ci, _u32p, ci]
+        L._ksw_ready = True
+    return L
+
+
+def _z(a):
+    a = np.ascontiguousarray(a, np.uint8)
+    return a if len(a) else np.zeros(1, np.uint8)
+
+
+def ksw_extd2(query, target, **kw):
+    """(score, cigar list of (len, op) with op in 'MID') as ksw_extd2_sse(flag=0,w=-1) would return."""
+    p = dict(KSW_PARAMS); p.update(kw)
+    cap = len(query) + len(target) + 2
+    cig = np.zeros(cap, np.uint32)
+    n = C.c_int(0)
+    sc = _ksw_lib().orc_ksw_extd2(len(query), _z(query), len(target), _z(target), p["a"], p["b"], p["sc_n"],
+                                  p["q"], p["e"], p["q2"], p["e2"], cig, cap, C.byref(n))
+    return sc, [(int(c >> 4), "MID"[int(c & 0xf)]) for c in cig[:n.value]]
+
+
+def affine2_score(query, target, **kw):
+    p = dict(KSW_PARAMS); p.update(kw)
+    return _ksw_lib().orc_affine2_score(len(query), _z(query), len(target), _z(target), p["a"], p["b"], p["sc_n"],
+                                        p["q"], p["e"], p["q2"], p["e2"])
+
+
+def cigar_score(query, target, cigar, **kw):
+    p = dict(KSW_PARAMS); p.update(kw)
+    cig = np.array([(l << 4) | "MID".index(op) for l, op in cigar], np.uint32)
+    if len(cig) == 0:
+        cig = np.zeros(1, np.uint32)
+    return _ksw_lib().orc_cigar_score(len(query), _z(query), len(target), _z(target), p["a"], p["b"], p["sc_n"],
+                                      p["q"], p["e"], p["q2"], p["e2"], cig, len(cigar))

@@ -34,6 +34,13 @@ class SfsOut(C.Structure):
                 ("launches", C.c_int32), ("block_bytes", C.c_int32)]
 
 
+class KswOut(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("score", C.POINTER(C.c_int32)), ("cigar_offs", C.POINTER(C.c_int64)),
+                ("cigar", C.POINTER(C.c_uint32)), ("n_cigar", C.c_int64), ("cells", C.c_int64),
+                ("kernel_ms", C.c_float), ("device_ms", C.c_float), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("launches", C.c_int32), ("waves", C.c_int32)]
+
+
 _lib = None
 
 # every symbol include/svdss_b200.h declares (tests check the .so exports all of them)
@@ -43,6 +50,7 @@ EXPORTS = [
     "svb_index_info", "svb_index_get_bwt", "svb_suffix_array",
     "svb_rank2a", "svb_rank_bench",
     "svb_sfs_batch", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
+    "svb_ksw_extd2_batch", "svb_ksw_out_free",
 ]
 
 
@@ -77,6 +85,9 @@ def lib():
     L.svb_sfs_resident.argtypes = [vp, vp, i32, i32, C.POINTER(SfsOut)]
     L.svb_sfs_out_free.argtypes = [C.POINTER(SfsOut)]
     L.svb_sfs_out_free.restype = None
+    L.svb_ksw_extd2_batch.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(KswOut)]
+    L.svb_ksw_out_free.argtypes = [C.POINTER(KswOut)]
+    L.svb_ksw_out_free.restype = None
     _lib = L
     return L
 
@@ -246,3 +257,52 @@ def suffix_array(text, device=0):
     sa = np.empty(len(text), np.int64)
     check(lib().svb_suffix_array(_ptr(text), len(text), SVB_MEM_HOST, device, _ptr(sa)))
     return sa
+
+
+# caller.cpp:333-349: match +1, mismatch -9, N -> -gape2, gaps min(16+2k, 41+k)
+KSW_DEFAULTS = dict(match=1, mismatch=-9, sc_n=-1, gapo=16, gape=2, gapo2=41, gape2=1)
+
+
+class KswResult:
+    def __init__(self, out):
+        n = out.n_pairs
+        self.n_pairs = n
+        self.score = np.ctypeslib.as_array(out.score, shape=(n,)).copy() if n else np.zeros(0, np.int32)
+        self.cigar_offs = np.ctypeslib.as_array(out.cigar_offs, shape=(n + 1,)).copy()
+        m = out.n_cigar
+        self.cigar = np.ctypeslib.as_array(out.cigar, shape=(m,)).copy() if m else np.zeros(0, np.uint32)
+        self.cells = out.cells
+        self.kernel_ms = out.kernel_ms
+        self.device_ms = out.device_ms
+        self.h2d_bytes = out.h2d_bytes
+        self.d2h_bytes = out.d2h_bytes
+        self.launches = out.launches
+        self.waves = out.waves
+
+    def cigar_of(self, p):
+        a, b = int(self.cigar_offs[p]), int(self.cigar_offs[p + 1])
+        return [(int(c >> 4), "MID"[int(c & 0xf)]) for c in self.cigar[a:b]]
+
+    def cigar_string(self, p):
+        """the string Caller::pcall builds at caller.cpp:352-355"""
+        return "".join("%d%s" % (l, op) for l, op in self.cigar_of(p))
+
+
+def ksw_extd2_batch(q_cat, q_offs, t_cat, t_offs, device=0, **kw):
+    """svb_ksw_extd2_batch with HOST buffers: sequences are _char26_table codes 0..4."""
+    p = dict(KSW_DEFAULTS)
+    p.update(kw)
+    q_cat = np.ascontiguousarray(q_cat, np.uint8)
+    t_cat = np.ascontiguousarray(t_cat, np.uint8)
+    q_offs = np.ascontiguousarray(q_offs, np.int64)
+    t_offs = np.ascontiguousarray(t_offs, np.int64)
+    if len(q_offs) != len(t_offs):
+        raise ValueError("query and target offset arrays differ in length")
+    out = KswOut()
+    check(lib().svb_ksw_extd2_batch(_ptr(q_cat), _ptr(q_offs), _ptr(t_cat), _ptr(t_offs), len(q_offs) - 1,
+                                    p["match"], p["mismatch"], p["sc_n"], p["gapo"], p["gape"], p["gapo2"],
+                                    p["gape2"], device, C.byref(out)))
+    try:
+        return KswResult(out)
+    finally:
+        lib().svb_ksw_out_free(C.byref(out))
