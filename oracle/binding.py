@@ -53,6 +53,12 @@ def lib():
         L.orc_fm_search_batch.argtypes = [C.c_void_p, _u8p, _i64p, C.c_int64, C.c_int,
                                           _i64p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_max_threads.restype = C.c_int
+        L.orc_fm_search_batch1.restype = C.c_int64
+        L.orc_fm_search_batch1.argtypes = [C.c_void_p, _u8p, _i64p, C.c_int64, C.c_int, _i64p,
+                                           C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_int32)),
+                                           C.POINTER(C.POINTER(C.c_int32))]
+        L.orc_free.restype = None
+        L.orc_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -158,6 +164,38 @@ class FMIndex:
         ext = lib().orc_fm_search_batch(self._h, reads, offs, n, threads, counts, None, None, None)
         if not want_output:
             return counts, None, None, None, ext
+        return self.search_batch1(reads, offs, threads)
+
+    def search_batch1(self, reads, offs, threads=0):
+        """single pass (counts + SFS table), what the timed reference arm runs"""
+        reads = np.ascontiguousarray(reads, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        n = len(offs) - 1
+        counts = np.zeros(n, np.int64)
+        if len(reads) == 0:
+            reads = np.zeros(1, np.uint8)
+        n_out = C.c_int64(0)
+        pq = C.POINTER(C.c_int32)()
+        pl = C.POINTER(C.c_int32)()
+        ext = lib().orc_fm_search_batch1(self._h, reads, offs, n, threads, counts, C.byref(n_out), C.byref(pq), C.byref(pl))
+        tot = n_out.value
+        qs = np.ctypeslib.as_array(pq, shape=(max(tot, 1),))[:tot].copy()
+        ln = np.ctypeslib.as_array(pl, shape=(max(tot, 1),))[:tot].copy()
+        lib().orc_free(pq)
+        lib().orc_free(pl)
+        out_off = np.zeros(n + 1, np.int64)
+        out_off[1:] = np.cumsum(counts)
+        return counts, out_off, qs, ln, ext
+
+    def search_batch2(self, reads, offs, threads=0):
+        """two-pass variant (count, then fill caller-sized arrays)"""
+        reads = np.ascontiguousarray(reads, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        n = len(offs) - 1
+        counts = np.zeros(n, np.int64)
+        if len(reads) == 0:
+            reads = np.zeros(1, np.uint8)
+        ext = lib().orc_fm_search_batch(self._h, reads, offs, n, threads, counts, None, None, None)
         out_off = np.zeros(n + 1, np.int64)
         out_off[1:] = np.cumsum(counts)
         tot = int(out_off[-1])

@@ -326,6 +326,81 @@ ORC_API int64_t orc_fm_search_batch(const orc_fm_t *f, const uint8_t *reads, con
   return total_ext;
 }
 
+
+/* Single-pass batch driver used by the timed reference arm: every thread appends (read, qs, len)
+ * to its own growing buffer (the reference's process_batch also returns per-thread containers,
+ * ping_pong.cpp:176-209), then the buffers are stitched in read order.  Caller frees with
+ * orc_free().  Returns total extensions; *n_out / *o_read / *o_qs / *o_len receive the table. */
+typedef struct { int32_t *r, *q, *l; int64_t n, cap; } tbuf;
+static void tbuf_push(tbuf *b, int32_t r, int32_t q, int32_t l) {
+  if (b->n == b->cap) {
+    b->cap = b->cap ? b->cap * 2 : 4096;
+    b->r = (int32_t *)realloc(b->r, sizeof(int32_t) * (size_t)b->cap);
+    b->q = (int32_t *)realloc(b->q, sizeof(int32_t) * (size_t)b->cap);
+    b->l = (int32_t *)realloc(b->l, sizeof(int32_t) * (size_t)b->cap);
+  }
+  b->r[b->n] = r; b->q[b->n] = q; b->l[b->n] = l; b->n++;
+}
+
+ORC_API int64_t orc_fm_search_batch1(const orc_fm_t *f, const uint8_t *reads, const int64_t *offs,
+                                     int64_t n_reads, int threads, int64_t *counts, int64_t *n_out,
+                                     int32_t **o_qs, int32_t **o_len) {
+  int64_t total_ext = 0;
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+  int nt = omp_get_max_threads();
+#else
+  int nt = 1;
+#endif
+  tbuf *bufs = (tbuf *)calloc((size_t)nt, sizeof(tbuf));
+  int32_t *owner = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_reads ? n_reads : 1));
+  int64_t *start = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_reads ? n_reads : 1));
+#pragma omp parallel reduction(+ : total_ext)
+  {
+#ifdef _OPENMP
+    int me = omp_get_thread_num();
+#else
+    int me = 0;
+#endif
+    tbuf *b = &bufs[me];
+    int32_t tq[64], tl[64];
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t r = 0; r < n_reads; ++r) {
+      int64_t l = offs[r + 1] - offs[r], ext = 0;
+      owner[r] = me; start[r] = b->n;
+      int64_t c = fm_ping_pong(f, reads + offs[r], l, tq, tl, 64, &ext);
+      if (c <= 64) {
+        for (int64_t i = 0; i < c; ++i) tbuf_push(b, (int32_t)r, tq[i], tl[i]);
+      } else { /* rare: redo with a big enough scratch */
+        int32_t *bq = (int32_t *)malloc(sizeof(int32_t) * (size_t)c * 2);
+        int64_t e2 = 0;
+        fm_ping_pong(f, reads + offs[r], l, bq, bq + c, c, &e2);
+        for (int64_t i = 0; i < c; ++i) tbuf_push(b, (int32_t)r, bq[i], bq[c + i]);
+        free(bq);
+      }
+      counts[r] = c;
+      total_ext += ext;
+    }
+  }
+  int64_t tot = 0;
+  for (int64_t r = 0; r < n_reads; ++r) tot += counts[r];
+  int32_t *q = (int32_t *)malloc(sizeof(int32_t) * (size_t)(tot ? tot : 1));
+  int32_t *ln = (int32_t *)malloc(sizeof(int32_t) * (size_t)(tot ? tot : 1));
+  int64_t o = 0;
+  for (int64_t r = 0; r < n_reads; ++r) {
+    tbuf *b = &bufs[owner[r]];
+    memcpy(q + o, b->q + start[r], sizeof(int32_t) * (size_t)counts[r]);
+    memcpy(ln + o, b->l + start[r], sizeof(int32_t) * (size_t)counts[r]);
+    o += counts[r];
+  }
+  for (int t = 0; t < nt; ++t) { free(bufs[t].r); free(bufs[t].q); free(bufs[t].l); }
+  free(bufs); free(owner); free(start);
+  *n_out = tot; *o_qs = q; *o_len = ln;
+  return total_ext;
+}
+
+ORC_API void orc_free(void *p) { free(p); }
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

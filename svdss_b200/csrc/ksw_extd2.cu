@@ -344,7 +344,7 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
       P.q = d_q; P.qoff = d_qoff; P.t = d_t; P.toff = d_toff;
       P.order = d_order + wv.first; P.n = (int)wv.count;
       P.tb_off = d_woff; P.bnd_off = d_woff + wv.count; P.cg_off = d_woff + 2 * wv.count;
-      P.tb = d_tb; P.bnd = d_bnd; P.cg = d_cg; P.cg_n = d_cgn; P.score = d_score; P.work = d_work;
+      P.tb = d_tb; P.bnd = d_bnd; P.cg = d_cg; P.cg_n = d_cgn + wv.first; P.score = d_score; P.work = d_work;
       P.a = match; P.b = mismatch; P.sc_n = sc_n; P.q1 = gapo; P.e1 = gape; P.q2 = gapo2; P.e2 = gape2;
       int64_t warps = std::min<int64_t>(wv.count, (int64_t)sms * 32);
       unsigned grid = (unsigned)((warps + 3) / 4);

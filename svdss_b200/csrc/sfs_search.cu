@@ -50,6 +50,10 @@ struct SearchParams {
   uint64_t* out_key;             // read << 32 | sort key
   uint32_t* out_len;
   unsigned long long out_cap;
+  // streamed batches (svb_sfs_batch): the read bytes arrive chunk by chunk while the kernel runs;
+  // ready[c] != 0 once chunk c (chunk_bytes each) is resident.  nullptr = everything resident.
+  const unsigned int* ready;
+  int64_t chunk_bytes;
 };
 
 __device__ __forceinline__ uint4 ldg_slice(const uint4* p) {
@@ -396,13 +400,13 @@ struct ReadWin1 {
     const uint64_t* p = reinterpret_cast<const uint64_t*>(seq);
     const int64_t w = gp >> 3;
     if (w != id) {
-      cur = (w == nid) ? nxt : __ldg(p + w);
+      cur = (w == nid) ? nxt : __ldcg(p + w);
       id = w;
     }
     const int64_t wn = w + dir;
     if (wn != nid) {
       nid = wn;
-      nxt = wn >= 0 ? __ldg(p + wn) : 0ull;  // consumed >= 1 step later
+      nxt = wn >= 0 ? __ldcg(p + wn) : 0ull;  // consumed >= 1 step later
     }
     return (int)((cur >> ((gp & 7) * 8)) & 0xffull);
   }
@@ -546,6 +550,11 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
           ridx = P.order ? P.order[w] : (uint32_t)w;
           roff = P.offs[ridx];
           len = (int)(P.offs[ridx + 1] - roff);
+          if (P.ready && len > 0) {  // streamed batch: wait until the chunk holding the last base landed
+            const volatile unsigned int* flag = P.ready + (roff + len - 1) / P.chunk_bytes;
+            while (*flag == 0u) __nanosleep(500);
+            __threadfence();
+          }
           if (len > 0) {
             have = true;
             phase = 0;
@@ -677,29 +686,33 @@ static void fill_params(SearchParams& P, const IndexDev& d) {
   memcpy(P.acc, d.acc, sizeof(d.acc));
 }
 
-__global__ void k_read_lengths(const int64_t* __restrict__ offs, int64_t n, uint32_t* __restrict__ keys,
-                               uint32_t* __restrict__ vals) {
+// sort key of a read: (chunk of its last base) << 32 | ~length  -> chunk-major, longest first
+__global__ void k_read_keys(const int64_t* __restrict__ offs, int64_t n, int64_t chunk_bytes,
+                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int64_t l = offs[i + 1] - offs[i];
-  keys[i] = ~(uint32_t)(l > 0xffffffffLL ? 0xffffffffLL : l);  // descending length
+  const int64_t b = offs[i], l = offs[i + 1] - b;
+  const uint64_t chunk = (chunk_bytes > 0 && l > 0) ? (uint64_t)((b + l - 1) / chunk_bytes) : 0ull;
+  keys[i] = (chunk << 32) | (uint32_t)~(uint32_t)(l > 0xffffffffLL ? 0xffffffffLL : l);
   vals[i] = (uint32_t)i;
 }
 
-static int make_order(svb_reads* R, cudaStream_t st) {
+// read indices in hand-out order: longest first (within a chunk when the batch is streamed)
+static int make_order(svb_reads* R, int64_t chunk_bytes, cudaStream_t st) {
   int64_t n = R->n_reads;
   if (n == 0) return SVB_OK;
-  uint32_t *k1 = nullptr, *k2 = nullptr, *v1 = nullptr;
-  SVB_CUDA(cudaMalloc((void**)&k1, n * 4));
-  SVB_CUDA(cudaMalloc((void**)&k2, n * 4));
+  uint64_t *k1 = nullptr, *k2 = nullptr;
+  uint32_t* v1 = nullptr;
+  SVB_CUDA(cudaMalloc((void**)&k1, n * 8));
+  SVB_CUDA(cudaMalloc((void**)&k2, n * 8));
   SVB_CUDA(cudaMalloc((void**)&v1, n * 4));
   SVB_CUDA(cudaMalloc((void**)&R->d_order, n * 4));
-  k_read_lengths<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->d_offs, n, k1, v1);
+  k_read_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->d_offs, n, chunk_bytes, k1, v1);
   size_t bytes = 0;
   void* tmp = nullptr;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k1, k2, v1, R->d_order, n, 0, 32, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k1, k2, v1, R->d_order, n, 0, 64, st);
   SVB_CUDA(cudaMalloc(&tmp, bytes));
-  SVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k1, k2, v1, R->d_order, n, 0, 32, st));
+  SVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k1, k2, v1, R->d_order, n, 0, 64, st));
   SVB_CUDA(cudaStreamSynchronize(st));
   cudaFree(tmp); cudaFree(k1); cudaFree(k2); cudaFree(v1);
   return SVB_OK;
@@ -782,8 +795,18 @@ struct SearchScratch {
 };
 
 // runs the search kernel (+ sort) on reads resident on the device; fills `out` host arrays
+// host source of a streamed batch: bytes are copied chunk by chunk on their own stream while the
+// search kernel (already launched) consumes them
+struct StreamSrc {
+  const uint8_t* host = nullptr;
+  int64_t total = 0, chunk_bytes = 0, n_chunks = 0;
+  unsigned int* d_ready = nullptr;
+  unsigned int* h_one = nullptr;  // pinned word holding 1
+  cudaStream_t copy_stream = nullptr;
+};
+
 static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int assemble, svb_sfs_out_t* out,
-                      cudaStream_t st) {
+                      cudaStream_t st, const StreamSrc* src = nullptr) {
   if (overlap > 0) { set_error("overlap must be <= 0 (config.hpp:82 fixes it at -1)"); return SVB_EINVAL; }
   const int64_t n_reads = R->n_reads;
   out->n_reads = n_reads;
@@ -826,6 +849,8 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
     SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 4 * sizeof(unsigned long long), st));
     P.work = S.d_ctr + 0; P.out_count = S.d_ctr + 1; P.stats = S.d_ctr + 2;
     P.out_key = S.d_key; P.out_len = S.d_len; P.out_cap = cap;
+    P.ready = nullptr; P.chunk_bytes = 0;
+    if (src && attempt == 0) { P.ready = src->d_ready; P.chunk_bytes = src->chunk_bytes; }
     SVB_CUDA(cudaEventRecord(e0, st));
     if (cfgG == 0) {
       k_sfs_search_tma<tma_minb, 0><<<grid, TMA_WARPS * 32, 0, st>>>(P);
@@ -838,6 +863,15 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
     }
     SVB_CUDA(cudaGetLastError());
     SVB_CUDA(cudaEventRecord(e1, st));
+    if (src && attempt == 0) {
+      // feed the running kernel: chunk copy, then its ready flag, in order on the copy stream
+      for (int64_t c = 0; c < src->n_chunks; ++c) {
+        const int64_t o = c * src->chunk_bytes, nb = std::min(src->chunk_bytes, src->total - o);
+        SVB_CUDA(cudaMemcpyAsync(R->d_seq + o, src->host + o, nb, cudaMemcpyHostToDevice, src->copy_stream));
+        // flag written by the copy engine too (a memset could need an SM the persistent kernel holds)
+        SVB_CUDA(cudaMemcpyAsync(src->d_ready + c, src->h_one, sizeof(unsigned int), cudaMemcpyHostToDevice, src->copy_stream));
+      }
+    }
     SVB_CUDA(cudaMemcpyAsync(ctr, S.d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, st));
     SVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -931,7 +965,7 @@ int svb_reads_upload(const uint8_t* seq, const int64_t* offs, int64_t n_reads, i
       R->d_seq = const_cast<uint8_t*>(seq);
       cudaMemcpy(R->d_offs, offs, (n_reads + 1) * 8, cudaMemcpyDeviceToDevice);
     }
-    rc = make_order(R, 0);
+    rc = make_order(R, 0, 0);
   } while (0);
   if (rc == SVB_ENOMEM) set_error("out of device memory uploading reads");
   if (rc != SVB_OK) { svb_reads_free(R); return rc; }
@@ -968,6 +1002,65 @@ int svb_sfs_resident(const svb_index_t* idx, const svb_reads_t* reads, int overl
   return rc;
 }
 
+// streamed variant of svb_sfs_batch: offsets first, kernel launched at once, read bytes follow in
+// 128 MiB chunks on a copy stream while the kernel works (chunk-major hand-out order)
+static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const int64_t* offs, int64_t n_reads,
+                              int overlap, int assemble, svb_sfs_out_t* out) {
+  const IndexDev& d = idx->dev;
+  svb_reads R;
+  R.device = d.device;
+  R.n_reads = n_reads;
+  const int64_t first = offs[0];
+  R.total = offs[n_reads] - first;
+  StreamSrc src;
+  src.host = seq + first;
+  src.total = R.total;
+  src.chunk_bytes = (int64_t)128 << 20;
+  if (const char* e = getenv("SVB_STREAM_CHUNK_BYTES")) { long long v = atoll(e); if (v >= 4096) src.chunk_bytes = (v + 63) & ~63LL; }
+  src.n_chunks = (R.total + src.chunk_bytes - 1) / src.chunk_bytes;
+  cudaStream_t comp = nullptr;
+  int rc = SVB_OK;
+  std::vector<int64_t> rb((size_t)n_reads + 1);
+  for (int64_t i = 0; i <= n_reads; ++i) {
+    rb[i] = offs[i] - first;
+    if (i && rb[i] < rb[i - 1]) { set_error("read offsets must be non-decreasing"); return SVB_EINVAL; }
+  }
+  const size_t padded = ((size_t)R.total + 64 + 63) & ~(size_t)63;
+#define SCHECK(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));       \
+      rc = SVB_ECUDA;                                                                             \
+      goto done;                                                                                  \
+    }                                                                                             \
+  } while (0)
+  SCHECK(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+  SCHECK(cudaStreamCreateWithFlags(&src.copy_stream, cudaStreamNonBlocking));
+  SCHECK(cudaMalloc((void**)&R.d_seq, padded));
+  SCHECK(cudaMalloc((void**)&R.d_offs, (n_reads + 1) * 8));
+  SCHECK(cudaMalloc((void**)&src.d_ready, src.n_chunks * sizeof(unsigned int)));
+  SCHECK(cudaHostAlloc((void**)&src.h_one, sizeof(unsigned int), cudaHostAllocDefault));
+  *src.h_one = 1u;
+  SCHECK(cudaMemsetAsync(src.d_ready, 0, src.n_chunks * sizeof(unsigned int), comp));
+  SCHECK(cudaMemsetAsync(R.d_seq + R.total, 0, padded - R.total, comp));
+  SCHECK(cudaMemcpyAsync(R.d_offs, rb.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, comp));
+  rc = make_order(&R, src.chunk_bytes, comp);
+  if (rc == SVB_OK) rc = run_search(d, &R, overlap, assemble, out, comp, &src);
+  if (rc == SVB_OK) {
+    SCHECK(cudaStreamSynchronize(src.copy_stream));
+    out->h2d_bytes = R.total + (n_reads + 1) * 8 + src.n_chunks * 4;
+    out->launches += 2;  // read keys + order sort
+  }
+done:
+#undef SCHECK
+  if (src.copy_stream) { cudaStreamSynchronize(src.copy_stream); cudaStreamDestroy(src.copy_stream); }
+  if (comp) { cudaStreamSynchronize(comp); cudaStreamDestroy(comp); }
+  cudaFree(R.d_seq); cudaFree(R.d_offs); cudaFree(R.d_order); cudaFree(src.d_ready);
+  if (src.h_one) cudaFreeHost(src.h_one);
+  return rc;
+}
+
 int svb_sfs_batch(const svb_index_t* idx, const uint8_t* seq, const int64_t* offs, int64_t n_reads,
                   int overlap, int assemble, svb_sfs_out_t* out) {
   if (!idx || !offs || !out || n_reads < 0) { set_error("svb_sfs_batch: bad arguments"); return SVB_EINVAL; }
@@ -977,14 +1070,24 @@ int svb_sfs_batch(const svb_index_t* idx, const uint8_t* seq, const int64_t* off
   SVB_CUDA(cudaEventCreate(&e0));
   SVB_CUDA(cudaEventCreate(&e1));
   SVB_CUDA(cudaEventRecord(e0, 0));
-  svb_reads_t* R = nullptr;
-  int rc = svb_reads_upload(seq, offs, n_reads, SVB_MEM_HOST, idx->dev.device, &R);
-  if (rc == SVB_OK) {
-    rc = run_search(idx->dev, R, overlap, assemble, out, 0);
-    out->h2d_bytes = R->total + (n_reads + 1) * 8;
-    out->launches += 2;  // length keys + order sort
+  int rc = SVB_OK, cfgG = 0;
+  rc = pick_cfg(idx->dev.G, &cfgG);
+  const int64_t total = n_reads > 0 ? offs[n_reads] - offs[0] : 0;
+  const char* ns = getenv("SVB_NO_STREAM");
+  int64_t stream_min = (int64_t)32 << 20;  // below this a plain upload is as fast
+  if (const char* e = getenv("SVB_STREAM_MIN_BYTES")) stream_min = atoll(e);
+  if (rc == SVB_OK && cfgG <= 0 && seq && total >= stream_min && total > 0 && !(ns && *ns == '1')) {
+    rc = sfs_batch_streamed(idx, seq, offs, n_reads, overlap, assemble, out);
+  } else if (rc == SVB_OK) {
+    svb_reads_t* R = nullptr;
+    rc = svb_reads_upload(seq, offs, n_reads, SVB_MEM_HOST, idx->dev.device, &R);
+    if (rc == SVB_OK) {
+      rc = run_search(idx->dev, R, overlap, assemble, out, 0);
+      out->h2d_bytes = R->total + (n_reads + 1) * 8;
+      out->launches += 2;  // read keys + order sort
+    }
+    svb_reads_free(R);
   }
-  svb_reads_free(R);
   cudaEventRecord(e1, 0);
   cudaEventSynchronize(e1);
   cudaEventElapsedTime(&out->device_ms, e0, e1);

@@ -200,3 +200,24 @@ def test_all_kernel_configs_agree(cfg, bb, monkeypatch):
     assert got == exp and res.n_ext == ext
     got_asm, _ = _gpu_sfs(idx, reads, assemble=True)
     assert got_asm == [oracle.assemble(e) for e in exp]
+
+
+def test_streamed_host_batch_matches_resident(monkeypatch):
+    """svb_sfs_batch streams the read bytes in chunks behind the running kernel; force that path
+    (tiny chunks) and compare with the oracle and with the resident path"""
+    contigs = synth.make_reference(600_000, seed=41, contigs=2)
+    reads = synth.make_reads(contigs, 500, seed=42, mean_len=8000, sd_len=2500, min_len=200, max_len=20000)
+    reads.insert(3, np.zeros(0, np.uint8))
+    T, SA, bwt = oracle_index(contigs)
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs, block_bytes=128)
+    exp, ext = fm_results(oracle.FMIndex(bwt), reads)
+    monkeypatch.setenv("SVB_STREAM_MIN_BYTES", "1")
+    monkeypatch.setenv("SVB_STREAM_CHUNK_BYTES", "65536")
+    for assemble in (False, True):
+        got, res = _gpu_sfs(idx, reads, assemble=assemble)
+        assert got == (exp if not assemble else [oracle.assemble(e) for e in exp])
+        assert res.n_ext == ext
+    monkeypatch.setenv("SVB_NO_STREAM", "1")
+    got2, _ = _gpu_sfs(idx, reads, assemble=False)
+    assert got2 == exp
