@@ -159,6 +159,33 @@ SVB_API int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_offs /
                                 int gapo2, int gape2, int device, svb_ksw_out_t* out);
 SVB_API void svb_ksw_out_free(svb_ksw_out_t* out);
 
+/* ------------------------------------------------------------------ cluster POA (a7) -- */
+
+typedef struct {
+  int64_t n_clusters;
+  int64_t* cons_offs;   /* n_clusters + 1, indexes cons[]                                         */
+  uint8_t* cons;        /* consensus bases, codes 0..4 (abc->cons_base[0], caller.cpp:292-297)    */
+  int32_t* status;      /* per cluster: 0 ok; bit 1 = workspace overflow, bit 2 = band clamped    */
+  int64_t cells;        /* DP cells computed (sum over reads and rows of the band width)          */
+  float kernel_ms;
+  float device_ms;
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int32_t launches;
+  int32_t reruns;       /* clusters redone with worst-case workspace                              */
+} svb_poa_out_t;
+
+/* Caller::run_poa (caller.cpp:257-308) for every cluster of a batch: abpoa_msa with the reference's
+ * parameters (global, convex gap 4/2 + 24/1, match 2, mismatch 4, adaptive band 10 + 0.01*qlen,
+ * no seeding, not progressive => reads added in input order) and the heaviest-bundling consensus
+ * (max_n_cons = 1).  Sequences are _char26_table codes 0..4; cluster c owns sequences
+ * cluster_offs[c] .. cluster_offs[c+1] of seq_offs.  A cluster without sequences yields an empty
+ * consensus (n_cons == 0 => "" at caller.cpp:294).  HOST buffers. */
+SVB_API int svb_poa_batch(const uint8_t* seqs_concat, const int64_t* seq_offs /* n_seqs+1 */,
+                          const int64_t* cluster_offs /* n_clusters+1 */, int64_t n_clusters, int device,
+                          svb_poa_out_t* out);
+SVB_API void svb_poa_out_free(svb_poa_out_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,3 +269,36 @@ def cigar_score(query, target, cigar, **kw):
         cig = np.zeros(1, np.uint32)
     return _ksw_lib().orc_cigar_score(len(query), _z(query), len(target), _z(target), p["a"], p["b"], p["sc_n"],
                                       p["q"], p["e"], p["q2"], p["e2"], cig, len(cigar))
+
+
+# ------------------------------------------------------------------ POA (oracle/poa_oracle.c)
+POA_PARAMS = dict(match=2, mismatch=4, o1=4, e1=2, o2=24, e2=1, wb=10, wf=0.01)   # abpoa_init_para defaults
+
+
+def _poa_lib():
+    L = lib()
+    if not hasattr(L, "_poa_ready"):
+        ci = C.c_int
+        L.orc_poa.restype = ci
+        L.orc_poa.argtypes = [_u8p, _i64p, ci, ci, ci, ci, ci, ci, ci, ci, ci, C.c_double, _u8p, ci, C.c_void_p]
+        L.orc_edit_distance.restype = ci
+        L.orc_edit_distance.argtypes = [_u8p, ci, _u8p, ci]
+        L._poa_ready = True
+    return L
+
+
+def poa_consensus(seqs, band=False, return_stats=False, **kw):
+    """consensus (codes 0..4) of a cluster's sequences added in input order (Caller::run_poa)."""
+    p = dict(POA_PARAMS); p.update(kw)
+    cat, offs = concat([np.ascontiguousarray(s, np.uint8) for s in seqs])
+    cap = int(2 * max([len(s) for s in seqs] + [1]) + 64)
+    out = np.zeros(cap, np.uint8)
+    stats = np.zeros(3, np.int64)
+    n = _poa_lib().orc_poa(_z(cat), offs, len(seqs), 1 if band else 0, p["match"], p["mismatch"], p["o1"], p["e1"],
+                           p["o2"], p["e2"], p["wb"], p["wf"], out, cap, stats.ctypes.data_as(C.c_void_p))
+    assert n <= cap
+    return (out[:n].copy(), stats) if return_stats else out[:n].copy()
+
+
+def edit_distance(a, b):
+    return _poa_lib().orc_edit_distance(_z(a), len(a), _z(b), len(b))

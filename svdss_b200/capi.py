@@ -41,6 +41,13 @@ class KswOut(C.Structure):
                 ("d2h_bytes", C.c_int64), ("launches", C.c_int32), ("waves", C.c_int32)]
 
 
+class PoaOut(C.Structure):
+    _fields_ = [("n_clusters", C.c_int64), ("cons_offs", C.POINTER(C.c_int64)), ("cons", C.POINTER(C.c_uint8)),
+                ("status", C.POINTER(C.c_int32)), ("cells", C.c_int64), ("kernel_ms", C.c_float),
+                ("device_ms", C.c_float), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("launches", C.c_int32), ("reruns", C.c_int32)]
+
+
 _lib = None
 
 # every symbol include/svdss_b200.h declares (tests check the .so exports all of them)
@@ -51,6 +58,7 @@ EXPORTS = [
     "svb_rank2a", "svb_rank_bench",
     "svb_sfs_batch", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
+    "svb_poa_batch", "svb_poa_out_free",
 ]
 
 
@@ -88,6 +96,9 @@ def lib():
     L.svb_ksw_extd2_batch.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(KswOut)]
     L.svb_ksw_out_free.argtypes = [C.POINTER(KswOut)]
     L.svb_ksw_out_free.restype = None
+    L.svb_poa_batch.argtypes = [vp, vp, vp, i64, i32, C.POINTER(PoaOut)]
+    L.svb_poa_out_free.argtypes = [C.POINTER(PoaOut)]
+    L.svb_poa_out_free.restype = None
     _lib = L
     return L
 
@@ -306,3 +317,45 @@ def ksw_extd2_batch(q_cat, q_offs, t_cat, t_offs, device=0, **kw):
         return KswResult(out)
     finally:
         lib().svb_ksw_out_free(C.byref(out))
+
+
+class PoaResult:
+    def __init__(self, out):
+        n = out.n_clusters
+        self.n_clusters = n
+        self.cons_offs = np.ctypeslib.as_array(out.cons_offs, shape=(n + 1,)).copy()
+        m = int(self.cons_offs[-1])
+        self.cons = np.ctypeslib.as_array(out.cons, shape=(m,)).copy() if m else np.zeros(0, np.uint8)
+        self.status = np.ctypeslib.as_array(out.status, shape=(n,)).copy() if n else np.zeros(0, np.int32)
+        self.cells = out.cells
+        self.kernel_ms = out.kernel_ms
+        self.device_ms = out.device_ms
+        self.h2d_bytes = out.h2d_bytes
+        self.d2h_bytes = out.d2h_bytes
+        self.launches = out.launches
+        self.reruns = out.reruns
+
+    def consensus(self, c):
+        return self.cons[int(self.cons_offs[c]):int(self.cons_offs[c + 1])]
+
+    def consensus_string(self, c):
+        """the string Caller::run_poa returns (caller.cpp:295-297)"""
+        return "".join("ACGTN"[int(b)] for b in self.consensus(c))
+
+
+def poa_batch(clusters, device=0):
+    """clusters: list of lists of uint8 code arrays (0..4). svb_poa_batch with HOST buffers."""
+    seqs = [np.ascontiguousarray(s, np.uint8) for cl in clusters for s in cl]
+    seq_offs = np.zeros(len(seqs) + 1, np.int64)
+    if seqs:
+        seq_offs[1:] = np.cumsum([len(s) for s in seqs])
+    cat = np.ascontiguousarray(np.concatenate(seqs)) if seqs and seq_offs[-1] else np.zeros(1, np.uint8)
+    cl_offs = np.zeros(len(clusters) + 1, np.int64)
+    if clusters:
+        cl_offs[1:] = np.cumsum([len(cl) for cl in clusters])
+    out = PoaOut()
+    check(lib().svb_poa_batch(_ptr(cat), _ptr(seq_offs), _ptr(cl_offs), len(clusters), device, C.byref(out)))
+    try:
+        return PoaResult(out)
+    finally:
+        lib().svb_poa_out_free(C.byref(out))

@@ -1,0 +1,593 @@
+// Cluster-level partial-order alignment + heaviest-bundling consensus on the GPU: the batch
+// equivalent of Caller::run_poa (reference caller.cpp:257-308), which hands a cluster's sub-reads
+// to abPOA (abpoa_msa, global mode, convex gap, adaptive band, reads added in input order) and
+// takes cons_base[0].  abPOA is an un-vendored dependency; its algorithm is restated in SURVEY.md
+// A.3 and, with every tie-break fixed, in oracle/poa_oracle.c's header -- this kernel follows
+// those rules so that it is bit-identical to the banded oracle.
+//
+// Mapping: one warp per cluster (clusters are independent, caller.cpp:312-313; 10^4..10^5 of them).
+// The graph lives in a per-warp global-memory workspace (L2-resident, a few hundred KB).  Reads
+// are added sequentially; for one read the DP runs over graph rows in rank (topological) order and
+// the warp parallelises over the query columns of the row's adaptive band, 32 columns per step:
+// M/E from the predecessor rows are independent per column, the in-row insertion states F1/F2
+// are a max-plus prefix scan (5 shuffle steps each).  Traceback, graph update and consensus are
+// short sequential walks done by lane 0.  Integer SIMT: a max-plus recurrence over a DAG with
+// data-dependent band and predecessors is not a dense contraction, so no tensor cores.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace svb {
+
+int check_device(int device);
+
+constexpr int PNEG = -(1 << 29);
+constexpr int POA_OK = 0, POA_OVERFLOW = 1, POA_CLAMPED = 2;
+
+struct PoaParams {
+  const uint8_t* __restrict__ seqs;
+  const int64_t* __restrict__ seq_offs;      // n_seqs + 1
+  const int64_t* __restrict__ cluster_offs;  // n_clusters + 1 (indexes seq_offs)
+  const uint32_t* __restrict__ order;        // clusters of this launch, biggest first
+  int n;                                     // clusters in this launch
+  unsigned int* work;
+  // workspace, one slot per resident warp
+  uint8_t* ws;
+  int64_t ws_stride;  // bytes per slot
+  int ncap, ecap, wcap, lmax;
+  // outputs
+  uint8_t* cons;                   // cons_cap bytes per cluster, at cons_off[cluster]
+  const int64_t* __restrict__ cons_off;
+  int32_t* cons_len;
+  int32_t* status;
+  unsigned long long* cells;
+  int match, mismatch, o1, e1, o2, e2, wb;
+  float wf;
+};
+
+// per-slot workspace carving (all int32 unless noted); must match poa_ws_bytes()
+struct PoaWs {
+  uint8_t* base;
+  int *rank, *order, *first_in, *last_in, *first_out, *last_out, *ring, *remain, *mpl, *mpr, *beg, *end, *cnt;
+  int *efrom, *eto, *ew, *enin, *enout;
+  int *op_node, *op_q, *new_anchor, *new_id;
+  int *H, *E1, *E2;
+  unsigned* TB;
+};
+
+__host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+__host__ __device__ inline int64_t poa_ws_carve(uint8_t* p, int ncap, int ecap, int wcap, int lmax, PoaWs* w) {
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t at = o; o = align16(o + bytes); return at; };
+  int64_t a;
+#define TAKE_I(f, n) a = take((int64_t)(n) * 4); if (w) w->f = reinterpret_cast<int*>(p + a)
+  a = take(ncap); if (w) w->base = p + a;
+  TAKE_I(rank, ncap); TAKE_I(order, ncap); TAKE_I(first_in, ncap); TAKE_I(last_in, ncap); TAKE_I(first_out, ncap);
+  TAKE_I(last_out, ncap); TAKE_I(ring, ncap); TAKE_I(remain, ncap); TAKE_I(mpl, ncap); TAKE_I(mpr, ncap);
+  TAKE_I(beg, ncap); TAKE_I(end, ncap); TAKE_I(cnt, ncap + 2);
+  TAKE_I(efrom, ecap); TAKE_I(eto, ecap); TAKE_I(ew, ecap); TAKE_I(enin, ecap); TAKE_I(enout, ecap);
+  TAKE_I(op_node, ncap + lmax + 4); TAKE_I(op_q, ncap + lmax + 4); TAKE_I(new_anchor, lmax + 2); TAKE_I(new_id, lmax + 2);
+  TAKE_I(H, (int64_t)ncap * wcap); TAKE_I(E1, (int64_t)ncap * wcap); TAKE_I(E2, (int64_t)ncap * wcap);
+  a = take((int64_t)ncap * wcap * 4); if (w) w->TB = reinterpret_cast<unsigned*>(p + a);
+#undef TAKE_I
+  return align16(o + 240) & ~(int64_t)255;
+}
+
+struct Graph {
+  PoaWs w;
+  int n, ne, ncap, ecap;
+  bool overflow;
+  __device__ int node(uint8_t b) {
+    if (n >= ncap) { overflow = true; return ncap - 1; }
+    const int v = n++;
+    w.base[v] = b; w.rank[v] = -1; w.first_in[v] = w.last_in[v] = w.first_out[v] = w.last_out[v] = -1; w.ring[v] = v;
+    return v;
+  }
+  __device__ void edge(int u, int v) {
+    for (int e = w.first_out[u]; e >= 0; e = w.enout[e])
+      if (w.eto[e] == v) { w.ew[e]++; return; }
+    if (ne >= ecap) { overflow = true; return; }
+    const int e = ne++;
+    w.efrom[e] = u; w.eto[e] = v; w.ew[e] = 1; w.enin[e] = -1; w.enout[e] = -1;
+    if (w.last_out[u] < 0) w.first_out[u] = e; else w.enout[w.last_out[u]] = e;
+    w.last_out[u] = e;
+    if (w.last_in[v] < 0) w.first_in[v] = e; else w.enin[w.last_in[v]] = e;
+    w.last_in[v] = e;
+  }
+};
+
+__device__ __forceinline__ int warp_incl_max(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = max(v, u);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(128) k_poa(const PoaParams P) {
+  const int lane = threadIdx.x & 31;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint8_t* wsp = P.ws + (int64_t)slot * P.ws_stride;
+  Graph g;
+  poa_ws_carve(wsp, P.ncap, P.ecap, P.wcap, P.lmax, &g.w);
+  g.ncap = P.ncap; g.ecap = P.ecap;
+  const PoaWs& W = g.w;
+  const int Wc = P.wcap;
+  const int mm = P.mismatch < 0 ? -P.mismatch : P.mismatch;
+  for (;;) {
+    unsigned wi = 0;
+    if (lane == 0) wi = atomicAdd(P.work, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= (unsigned)P.n) break;
+    const uint32_t cid = P.order[wi];
+    const int64_t s0 = P.cluster_offs[cid], s1 = P.cluster_offs[cid + 1];
+    g.n = 0; g.ne = 0; g.overflow = false;
+    int status = POA_OK;
+    unsigned long long cells = 0;
+    if (lane == 0) { g.node(0); g.node(0); }  // source, sink
+    g.n = 2;
+    __syncwarp();
+    for (int64_t si = s0; si < s1 && !g.overflow; ++si) {
+      const uint8_t* q = P.seqs + P.seq_offs[si];
+      const int ql = (int)(P.seq_offs[si + 1] - P.seq_offs[si]);
+      if (ql <= 0) continue;
+      if (ql > P.lmax) { g.overflow = true; break; }
+      const int N = g.n;
+      if (N == 2) {  // first read: a chain (warp-parallel)
+        if (ql + 2 > g.ncap || ql + 1 > g.ecap) { g.overflow = true; break; }
+        for (int j = lane; j < ql; j += 32) {
+          const int v = 2 + j;
+          W.base[v] = q[j]; W.rank[v] = j; W.ring[v] = v;
+          // edge j: (j ? v-1 : source) -> v ; edge ql: last -> sink
+          W.efrom[j] = j ? v - 1 : 0; W.eto[j] = v; W.ew[j] = 1; W.enin[j] = -1; W.enout[j] = -1;
+          W.first_in[v] = W.last_in[v] = j;
+          W.first_out[v] = W.last_out[v] = j + 1;
+        }
+        if (lane == 0) {
+          W.efrom[ql] = 2 + ql - 1; W.eto[ql] = 1; W.ew[ql] = 1; W.enin[ql] = -1; W.enout[ql] = -1;
+          W.first_out[0] = W.last_out[0] = 0;
+          W.first_in[1] = W.last_in[1] = ql;
+        }
+        g.n = 2 + ql; g.ne = ql + 1;
+        __syncwarp();
+        continue;
+      }
+      const int n_ord = N - 2;
+      for (int v = 2 + lane; v < N; v += 32) { W.order[W.rank[v]] = v; }
+      for (int v = lane; v < N; v += 32) { W.mpl[v] = 0x7fffffff; W.mpr[v] = -1; }
+      for (int s = lane; s <= n_ord + 1; s += 32) W.cnt[s] = 0;
+      __syncwarp();
+      // remain[]: heaviest out-neighbour chain length to the sink (lane 0, reverse rank order)
+      if (lane == 0) {
+        W.remain[1] = 0;
+        for (int r = n_ord - 1; r >= -1; --r) {
+          const int v = r >= 0 ? W.order[r] : 0;
+          int bw = -1, bv = 1;
+          for (int e = W.first_out[v]; e >= 0; e = W.enout[e])
+            if (W.ew[e] > bw) { bw = W.ew[e]; bv = W.eto[e]; }
+          W.remain[v] = W.remain[bv] + 1;
+        }
+      }
+      __syncwarp();
+      const int w = P.wb + (int)(P.wf * (float)ql);
+      // ---- source row
+      {
+        int end0 = min(w, ql);
+        if (end0 + 1 > Wc) { end0 = Wc - 1; status |= POA_CLAMPED; }
+        for (int j = lane; j <= end0; j += 32) {
+          const int c1 = P.o1 + j * P.e1, c2 = P.o2 + j * P.e2;
+          W.H[j] = j ? -min(c1, c2) : 0; W.E1[j] = PNEG; W.E2[j] = PNEG;
+          unsigned t = j ? (c1 <= c2 ? 3u : 4u) : 0u;
+          if (j > 1) t |= (c1 <= c2) ? (1u << 7) : (1u << 8);
+          W.TB[j] = t;
+        }
+        if (lane == 0) {
+          W.beg[0] = 0; W.end[0] = end0;
+          for (int e = W.first_out[0]; e >= 0; e = W.enout[e]) {
+            const int o = W.eto[e];
+            W.mpl[o] = min(W.mpl[o], 1); W.mpr[o] = max(W.mpr[o], 1);
+          }
+        }
+        __syncwarp();
+      }
+      // ---- graph rows in rank order
+      for (int r = 0; r < n_ord; ++r) {
+        const int v = W.order[r];
+        const int c = ql - W.remain[v] + 1;
+        int b = max(0, min(W.mpl[v], c) - w), en = min(ql, max(W.mpr[v], c) + w);
+        if (b > en) b = en;
+        if (en - b + 1 > Wc) { en = b + Wc - 1; status |= POA_CLAMPED; }
+        const int bv = W.base[v];
+        int* hrow = W.H + (int64_t)v * Wc; int* e1row = W.E1 + (int64_t)v * Wc; int* e2row = W.E2 + (int64_t)v * Wc;
+        unsigned* tbrow = W.TB + (int64_t)v * Wc;
+        int carry1 = PNEG, carry2 = PNEG;      // running max of B1/B2 over columns before this segment
+        int prevX1 = PNEG, prevB1 = PNEG, prevX2 = PNEG, prevB2 = PNEG;  // column j-1 of lane 0
+        int rmax = PNEG - 1, rleft = 0, rright = 0;
+        for (int j0 = b; j0 <= en; j0 += 32) {
+          const int j = j0 + lane;
+          const bool act = j <= en;
+          int m = PNEG, x1 = PNEG, x2 = PNEG, pm = 0, p1 = 0, p2 = 0, x1ext = 0, x2ext = 0, ord = 0;
+          const int qb = (act && j >= 1) ? q[j - 1] : 4;
+          for (int e = W.first_in[v]; e >= 0; e = W.enin[e], ++ord) {
+            const int p = W.efrom[e];
+            const int bp = W.beg[p], ep = W.end[p];
+            const int* ph = W.H + (int64_t)p * Wc;
+            if (act && j >= 1 && j - 1 >= bp && j - 1 <= ep) {
+              const int s = (bv >= 4 || qb >= 4) ? 0 : (bv == qb ? P.match : -mm);
+              const int cval = ph[j - 1 - bp] + s;
+              if (cval > m) { m = cval; pm = ord; }
+            }
+            if (act && j >= bp && j <= ep) {
+              const int hj = ph[j - bp];
+              int op = hj - P.o1, ex = W.E1[(int64_t)p * Wc + j - bp];
+              int cval = max(op, ex) - P.e1;
+              if (cval > x1) { x1 = cval; p1 = ord; x1ext = ex > op; }
+              op = hj - P.o2; ex = W.E2[(int64_t)p * Wc + j - bp];
+              cval = max(op, ex) - P.e2;
+              if (cval > x2) { x2 = cval; p2 = ord; x2ext = ex > op; }
+            }
+          }
+          m = max(m, PNEG); x1 = max(x1, PNEG); x2 = max(x2, PNEG);
+          int hp = m; unsigned hps = 0;
+          if (x1 > hp) { hp = x1; hps = 1; }
+          if (x2 > hp) { hp = x2; hps = 2; }
+          // F1/F2: exclusive max-plus prefix scan of B(k) = Hp(k) + k*e over the row
+          const int B1 = act ? hp + j * P.e1 : PNEG, B2 = act ? hp + j * P.e2 : PNEG;
+          const int inc1 = warp_incl_max(B1, lane), inc2 = warp_incl_max(B2, lane);
+          int ex1 = __shfl_up_sync(0xffffffffu, inc1, 1), ex2 = __shfl_up_sync(0xffffffffu, inc2, 1);
+          if (lane == 0) { ex1 = PNEG; ex2 = PNEG; }
+          const int X1 = max(carry1, ex1), X2 = max(carry2, ex2);
+          int f1 = PNEG, f2 = PNEG;
+          if (j > b) { f1 = max(X1 - P.o1 - j * P.e1, PNEG); f2 = max(X2 - P.o2 - j * P.e2, PNEG); }
+          // ext flag of column j: F(j-1) > Hp(j-1) - o  <=>  X(j-1) > B(j-1)
+          int pX1 = __shfl_up_sync(0xffffffffu, X1, 1), pB1 = __shfl_up_sync(0xffffffffu, B1, 1);
+          int pX2 = __shfl_up_sync(0xffffffffu, X2, 1), pB2 = __shfl_up_sync(0xffffffffu, B2, 1);
+          if (lane == 0) { pX1 = prevX1; pB1 = prevB1; pX2 = prevX2; pB2 = prevB2; }
+          const int f1ext = (j > b) && (pX1 > pB1), f2ext = (j > b) && (pX2 > pB2);
+          int hh = hp; unsigned hs = hps;
+          if (f1 > hh) { hh = f1; hs = 3; }
+          if (f2 > hh) { hh = f2; hs = 4; }
+          if (act) {
+            hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2;
+            tbrow[j - b] = hs | (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)f1ext << 7) |
+                           ((unsigned)f2ext << 8) | ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) |
+                           ((unsigned)(p2 & 0x3f) << 26);
+            if (hh > rmax) { rmax = hh; rleft = j; rright = j; }
+            else if (hh == rmax) rright = j;
+          }
+          carry1 = max(carry1, __shfl_sync(0xffffffffu, inc1, 31));
+          carry2 = max(carry2, __shfl_sync(0xffffffffu, inc2, 31));
+          prevX1 = __shfl_sync(0xffffffffu, X1, 31); prevB1 = __shfl_sync(0xffffffffu, B1, 31);
+          prevX2 = __shfl_sync(0xffffffffu, X2, 31); prevB2 = __shfl_sync(0xffffffffu, B2, 31);
+        }
+        cells += (unsigned long long)(en - b + 1);
+        // row maximum, its first and last column (lanes hold strided columns: reduce)
+        int gmax = rmax;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        int l_ = (rmax == gmax) ? rleft : 0x7fffffff, r_ = (rmax == gmax) ? rright : -1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          l_ = min(l_, __shfl_xor_sync(0xffffffffu, l_, o));
+          r_ = max(r_, __shfl_xor_sync(0xffffffffu, r_, o));
+        }
+        if (lane == 0) {
+          W.beg[v] = b; W.end[v] = en;
+          for (int e = W.first_out[v]; e >= 0; e = W.enout[e]) {
+            const int o = W.eto[e];
+            W.mpl[o] = min(W.mpl[o], l_ + 1); W.mpr[o] = max(W.mpr[o], r_ + 1);
+          }
+        }
+        __syncwarp();
+      }
+      // ---- end point, traceback, graph update, re-rank: lane 0
+      if (lane == 0) {
+        int best_p = -1, best = PNEG - 1;
+        for (int e = W.first_in[1]; e >= 0; e = W.enin[e]) {
+          const int p = W.efrom[e];
+          const int val = (ql >= W.beg[p] && ql <= W.end[p]) ? W.H[(int64_t)p * Wc + ql - W.beg[p]] : PNEG;
+          if (val > best) { best = val; best_p = p; }
+        }
+        int nop = 0;
+        {
+          int v = best_p, j = ql, state = 0;  // 0 H, 5 Hp, 1 E1, 2 E2, 3 F1, 4 F2
+          while (v != 0 || j > 0) {
+            if (v == 0) { W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop; --j; continue; }
+            const unsigned t = W.TB[(int64_t)v * Wc + j - W.beg[v]];
+            if (state == 0) state = (int)(t & 7);
+            else if (state == 5) state = (int)((t >> 3) & 3);
+            if (state == 0) {
+              int ord = (int)((t >> 12) & 0xff), e = W.first_in[v];
+              while (ord--) e = W.enin[e];
+              W.op_node[nop] = v; W.op_q[nop] = j - 1; ++nop;
+              v = W.efrom[e]; --j; state = 0;
+            } else if (state == 1 || state == 2) {
+              int ord = (int)((t >> (state == 1 ? 20 : 26)) & 0x3f), e = W.first_in[v];
+              while (ord--) e = W.enin[e];
+              const int ext = (int)((t >> (state == 1 ? 5 : 6)) & 1);
+              W.op_node[nop] = v; W.op_q[nop] = -1; ++nop;
+              v = W.efrom[e];
+              if (!ext) state = 0;
+              if (v == 0) state = 0;
+            } else {
+              const int ext = (int)((t >> (state == 3 ? 7 : 8)) & 1);
+              W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop;
+              --j;
+              if (!ext) state = 5;
+            }
+          }
+        }
+        // graph update (abpoa_add_graph_alignment), forward order
+        int n_new = 0, prev = 0, anchor = 0;
+        const int n_old = N;
+        for (int k = nop - 1; k >= 0 && !g.overflow; --k) {
+          const int v = W.op_node[k], qi = W.op_q[k];
+          if (v >= 0) {
+            int mr = W.rank[v];
+            for (int u = W.ring[v]; u != v; u = W.ring[u]) if (u < n_old && W.rank[u] > mr) mr = W.rank[u];
+            anchor = mr + 1;
+          }
+          if (qi < 0) continue;
+          int use;
+          if (v >= 0) {
+            const uint8_t bq = q[qi];
+            if (W.base[v] == bq) use = v;
+            else {
+              use = -1;
+              for (int u = W.ring[v]; u != v; u = W.ring[u]) if (W.base[u] == bq) { use = u; break; }
+              if (use < 0) {
+                use = g.node(bq);
+                if (g.overflow) break;
+                W.ring[use] = W.ring[v]; W.ring[v] = use;
+                W.new_anchor[n_new] = anchor; W.new_id[n_new] = use; ++n_new; W.cnt[anchor]++;
+              }
+            }
+          } else {
+            use = g.node(q[qi]);
+            if (g.overflow) break;
+            W.new_anchor[n_new] = anchor; W.new_id[n_new] = use; ++n_new; W.cnt[anchor]++;
+          }
+          g.edge(prev, use);
+          prev = use;
+        }
+        if (!g.overflow) g.edge(prev, 1);
+        if (!g.overflow) {
+          // re-rank: exclusive prefix of cnt over slots (slot 0 = source, r+1 = old rank r)
+          int acc = 0;
+          for (int s = 0; s <= n_ord; ++s) { const int c_ = W.cnt[s]; W.cnt[s] = acc; acc += c_; }
+          for (int r = 0; r < n_ord; ++r) W.rank[W.order[r]] = r + W.cnt[r + 1];
+          // new nodes follow their anchor in creation order: reuse mpl[] as the per-slot counter
+          for (int k = 0; k < n_new; ++k) W.mpl[W.new_anchor[k] < N ? W.new_anchor[k] : 0] = 0;
+          for (int k = 0; k < n_new; ++k) {
+            const int s = W.new_anchor[k];
+            // slots range over 0..n_ord <= N-2, so mpl[s] is a valid scratch cell
+            W.rank[W.new_id[k]] = (s - 1 + W.cnt[s]) + 1 + W.mpl[s];
+            W.mpl[s]++;
+          }
+        }
+      }
+      // lane 0's graph size / overflow flag are the truth
+      g.n = __shfl_sync(0xffffffffu, g.n, 0);
+      g.ne = __shfl_sync(0xffffffffu, g.ne, 0);
+      g.overflow = __shfl_sync(0xffffffffu, (int)g.overflow, 0) != 0;
+      __syncwarp();
+    }
+    // ---- consensus: heaviest bundling (lane 0)
+    if (lane == 0) {
+      int len = 0;
+      if (!g.overflow && g.n > 2) {
+        const int N = g.n, n_ord = N - 2;
+        for (int v = 2; v < N; ++v) W.order[W.rank[v]] = v;
+        int* score = W.remain; int* nxt = W.mpr;
+        score[1] = 0;
+        for (int r = n_ord - 1; r >= -1; --r) {
+          const int v = r >= 0 ? W.order[r] : 0;
+          int mw = -1, mi = -1;
+          for (int e = W.first_out[v]; e >= 0; e = W.enout[e]) {
+            const int o = W.eto[e], wgt = W.ew[e];
+            if (mw < wgt) { mw = wgt; mi = o; }
+            else if (mw == wgt && score[mi] <= score[o]) mi = o;
+          }
+          nxt[v] = mi;
+          score[v] = mi >= 0 ? mw + score[mi] : 0;
+        }
+        uint8_t* out = P.cons + P.cons_off[cid];
+        const int cap = (int)(P.cons_off[cid + 1] - P.cons_off[cid]);
+        for (int v = nxt[0]; v > 1; v = nxt[v]) { if (len < cap) out[len] = W.base[v]; ++len; }
+        if (len > cap) { status |= POA_OVERFLOW; }
+      }
+      if (g.overflow) status |= POA_OVERFLOW;
+      P.cons_len[cid] = len;
+      P.status[cid] = status;
+      atomicAdd(P.cells, cells);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const int64_t* cluster_offs,
+                             int64_t n_clusters, int device, svb_poa_out_t* out) {
+  if (!out) { set_error("svb_poa_batch: null out"); return SVB_EINVAL; }
+  memset(out, 0, sizeof(*out));
+  if (!seq_offs || !cluster_offs || n_clusters < 0 || n_clusters > 0x7fffffff) { set_error("svb_poa_batch: bad arguments"); return SVB_EINVAL; }
+  SVB_TRY(check_device(device));
+  out->n_clusters = n_clusters;
+  out->cons_offs = (int64_t*)calloc((size_t)n_clusters + 1, 8);
+  out->status = (int32_t*)calloc((size_t)n_clusters + 1, 4);
+  if (!out->cons_offs || !out->status) { set_error("out of host memory"); return SVB_ENOMEM; }
+  if (n_clusters == 0) return SVB_OK;
+  const int64_t n_seqs = cluster_offs[n_clusters];
+  if (cluster_offs[0] != 0 || n_seqs < 0) { set_error("cluster offsets must start at 0"); return SVB_EINVAL; }
+  const int64_t s_first = seq_offs[0], s_total = seq_offs[n_seqs] - s_first;
+  // per-cluster shape
+  struct Shape { int64_t sum; int lmax, lmin, nreads; double cost; };
+  std::vector<Shape> shp((size_t)n_clusters);
+  std::vector<int64_t> cap_off((size_t)n_clusters + 1, 0);
+  for (int64_t c = 0; c < n_clusters; ++c) {
+    Shape s{0, 0, 0x7fffffff, 0, 0};
+    if (cluster_offs[c + 1] < cluster_offs[c]) { set_error("cluster offsets must be non-decreasing"); return SVB_EINVAL; }
+    for (int64_t i = cluster_offs[c]; i < cluster_offs[c + 1]; ++i) {
+      int64_t l = seq_offs[i + 1] - seq_offs[i];
+      if (l < 0 || l > (1 << 24)) { set_error("sequence %lld has a bad length", (long long)i); return SVB_EINVAL; }
+      if (l == 0) continue;
+      s.sum += l; s.lmax = std::max(s.lmax, (int)l); s.lmin = std::min(s.lmin, (int)l); s.nreads++;
+    }
+    if (!s.nreads) s.lmin = 0;
+    s.cost = (double)s.sum * (s.lmax + 1);
+    shp[c] = s;
+    cap_off[c + 1] = cap_off[c] + ((2 * (int64_t)s.lmax + 64 + 15) & ~15LL);
+  }
+  uint8_t *d_seqs = nullptr, *d_ws = nullptr, *d_cons = nullptr;
+  int64_t *d_soff = nullptr, *d_coff = nullptr, *d_capoff = nullptr;
+  uint32_t* d_order = nullptr;
+  int32_t *d_len = nullptr, *d_status = nullptr;
+  unsigned int* d_work = nullptr;
+  unsigned long long* d_cells = nullptr;
+  int rc = SVB_OK;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  std::vector<int64_t> so((size_t)n_seqs + 1);
+  for (int64_t i = 0; i <= n_seqs; ++i) so[i] = seq_offs[i] - s_first;
+  std::vector<int32_t> h_len((size_t)n_clusters), h_status((size_t)n_clusters);
+  std::vector<uint8_t> h_cons((size_t)std::max<int64_t>(cap_off[n_clusters], 1));
+#define PCHECK(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      rc = SVB_ECUDA;                                                                       \
+      goto done;                                                                            \
+    }                                                                                       \
+  } while (0)
+  {
+    PCHECK(cudaEventCreate(&e0));
+    PCHECK(cudaEventCreate(&e1));
+    PCHECK(cudaEventRecord(e0, 0));
+    PCHECK(cudaMalloc((void**)&d_seqs, std::max<int64_t>(s_total, 1)));
+    PCHECK(cudaMalloc((void**)&d_soff, (n_seqs + 1) * 8));
+    PCHECK(cudaMalloc((void**)&d_coff, (n_clusters + 1) * 8));
+    PCHECK(cudaMalloc((void**)&d_capoff, (n_clusters + 1) * 8));
+    PCHECK(cudaMalloc((void**)&d_order, n_clusters * 4));
+    PCHECK(cudaMalloc((void**)&d_len, n_clusters * 4));
+    PCHECK(cudaMalloc((void**)&d_status, n_clusters * 4));
+    PCHECK(cudaMalloc((void**)&d_cons, std::max<int64_t>(cap_off[n_clusters], 1)));
+    PCHECK(cudaMalloc((void**)&d_work, 4));
+    PCHECK(cudaMalloc((void**)&d_cells, 8));
+    PCHECK(cudaMemset(d_cells, 0, 8));
+    if (s_total) PCHECK(cudaMemcpy(d_seqs, seqs + s_first, s_total, cudaMemcpyHostToDevice));
+    PCHECK(cudaMemcpy(d_soff, so.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice));
+    PCHECK(cudaMemcpy(d_coff, cluster_offs, (n_clusters + 1) * 8, cudaMemcpyHostToDevice));
+    PCHECK(cudaMemcpy(d_capoff, cap_off.data(), (n_clusters + 1) * 8, cudaMemcpyHostToDevice));
+    out->h2d_bytes = s_total + (n_seqs + 1) * 8 + (n_clusters + 1) * 16;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    // pass 0: heuristic capacities; pass 1: worst-case capacities for the clusters that overflowed
+    std::vector<uint32_t> todo((size_t)n_clusters);
+    for (int64_t c = 0; c < n_clusters; ++c) todo[c] = (uint32_t)c;
+    float kms = 0.f;
+    for (int pass = 0; pass < 2 && !todo.empty(); ++pass) {
+      std::stable_sort(todo.begin(), todo.end(), [&](uint32_t a, uint32_t b) { return shp[a].cost > shp[b].cost; });
+      int ncap = 0, wcap = 0, lmax = 1;
+      int64_t ecap = 0;
+      for (uint32_t c : todo) {
+        const Shape& s = shp[c];
+        if (!s.nreads) continue;
+        lmax = std::max(lmax, s.lmax);
+        const int w = 10 + (int)(0.01 * s.lmax);
+        const int diff = s.lmax - s.lmin;
+        int64_t nc, wc;
+        if (pass == 0) {
+          nc = std::min<int64_t>(s.sum + 2, 2 * (int64_t)s.lmax + 32 * s.nreads + 64);
+          wc = std::min<int64_t>(s.lmax + 1, 2 * w + 1 + 4 * diff + 96);
+        } else {
+          nc = s.sum + 2;
+          wc = s.lmax + 1;
+        }
+        ncap = (int)std::max<int64_t>(ncap, nc);
+        wcap = (int)std::max<int64_t>(wcap, wc);
+      }
+      if (ncap == 0) { ncap = 4; wcap = 4; }
+      wcap = (wcap + 31) & ~31;
+      ecap = 3 * (int64_t)ncap + 64;
+      const int64_t stride = poa_ws_carve(nullptr, ncap, (int)ecap, wcap, lmax, nullptr);
+      size_t free_b = 0, total_b = 0;
+      PCHECK(cudaMemGetInfo(&free_b, &total_b));
+      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * 16);
+      const char* eb = getenv("SVB_POA_WS_BYTES");
+      const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
+      slots = std::min<int64_t>(slots, std::max<int64_t>(1, budget / stride));
+      slots = (slots + 3) / 4 * 4;
+      if ((int64_t)slots * stride > (int64_t)free_b) { set_error("POA workspace of %lld bytes per cluster does not fit", (long long)stride); rc = SVB_ENOMEM; goto done; }
+      cudaFree(d_ws); d_ws = nullptr;
+      PCHECK(cudaMalloc((void**)&d_ws, (size_t)slots * stride));
+      PCHECK(cudaMemcpy(d_order, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice));
+      PCHECK(cudaMemset(d_work, 0, 4));
+      PoaParams P;
+      memset(&P, 0, sizeof(P));
+      P.seqs = d_seqs; P.seq_offs = d_soff; P.cluster_offs = d_coff; P.order = d_order; P.n = (int)todo.size();
+      P.work = d_work; P.ws = d_ws; P.ws_stride = stride; P.ncap = ncap; P.ecap = (int)ecap; P.wcap = wcap; P.lmax = lmax;
+      P.cons = d_cons; P.cons_off = d_capoff; P.cons_len = d_len; P.status = d_status; P.cells = d_cells;
+      P.match = 2; P.mismatch = 4; P.o1 = 4; P.e1 = 2; P.o2 = 24; P.e2 = 1; P.wb = 10; P.wf = 0.01f;  // abpoa_init_para
+      cudaEvent_t k0, k1;
+      PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
+      PCHECK(cudaEventRecord(k0, 0));
+      k_poa<<<(unsigned)(slots / 4), 128>>>(P);
+      PCHECK(cudaGetLastError());
+      PCHECK(cudaEventRecord(k1, 0));
+      PCHECK(cudaEventSynchronize(k1));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, k0, k1);
+      cudaEventDestroy(k0); cudaEventDestroy(k1);
+      kms += ms;
+      out->launches += 1;
+      PCHECK(cudaMemcpy(h_status.data(), d_status, n_clusters * 4, cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> again;
+      for (uint32_t c : todo) {
+        // clamped band (pass 0 only) or capacity overflow: redo with worst-case capacities
+        if ((h_status[c] & POA_OVERFLOW) || (pass == 0 && (h_status[c] & POA_CLAMPED))) again.push_back(c);
+      }
+      if (pass == 1 && !again.empty()) { set_error("POA workspace overflow persisted for %zu clusters", again.size()); rc = SVB_ERANGE; goto done; }
+      todo.swap(again);
+      out->reruns += (int32_t)todo.size();
+    }
+    PCHECK(cudaMemcpy(h_len.data(), d_len, n_clusters * 4, cudaMemcpyDeviceToHost));
+    PCHECK(cudaMemcpy(h_status.data(), d_status, n_clusters * 4, cudaMemcpyDeviceToHost));
+    PCHECK(cudaMemcpy(h_cons.data(), d_cons, cap_off[n_clusters], cudaMemcpyDeviceToHost));
+    unsigned long long cells = 0;
+    PCHECK(cudaMemcpy(&cells, d_cells, 8, cudaMemcpyDeviceToHost));
+    out->cells = (int64_t)cells;
+    out->d2h_bytes = cap_off[n_clusters] + n_clusters * 8;
+    for (int64_t c = 0; c < n_clusters; ++c) out->cons_offs[c + 1] = out->cons_offs[c] + h_len[c];
+    out->cons = (uint8_t*)malloc((size_t)std::max<int64_t>(out->cons_offs[n_clusters], 1));
+    if (!out->cons) { set_error("out of host memory"); rc = SVB_ENOMEM; goto done; }
+    for (int64_t c = 0; c < n_clusters; ++c) {
+      memcpy(out->cons + out->cons_offs[c], h_cons.data() + cap_off[c], (size_t)h_len[c]);
+      out->status[c] = h_status[c];
+    }
+    PCHECK(cudaEventRecord(e1, 0));
+    PCHECK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&out->device_ms, e0, e1);
+    out->kernel_ms = kms;
+  }
+done:
+#undef PCHECK
+  cudaFree(d_seqs); cudaFree(d_ws); cudaFree(d_cons); cudaFree(d_soff); cudaFree(d_coff); cudaFree(d_capoff);
+  cudaFree(d_order); cudaFree(d_len); cudaFree(d_status); cudaFree(d_work); cudaFree(d_cells);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (rc != SVB_OK) svb_poa_out_free(out);
+  return rc;
+}
+
+extern "C" void svb_poa_out_free(svb_poa_out_t* out) {
+  if (!out) return;
+  free(out->cons_offs); free(out->cons); free(out->status);
+  out->cons_offs = nullptr; out->cons = nullptr; out->status = nullptr;
+}
