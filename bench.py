@@ -43,6 +43,19 @@ def contig_offsets(ref_bp, n_contigs):
     return np.concatenate([[0], cuts]).astype(np.int64)
 
 
+def ncu_traffic(n_reads, block_bytes):
+    """dram bytes per launch of the search kernel from the committed ncu --set full capture (same
+    workload: 1 M reads of config 2); None when the run does not match that capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)["k_sfs_search_tma<6,1>"]
+        if t["reads_per_launch"] == n_reads and block_bytes == 128 and not os.environ.get("SVB_SEARCH_CFG"):
+            return t["dram_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -203,8 +216,15 @@ def run_ours(args):
     launches = int(sum(r.launches for r in res))
     n_sfs = res[-1].n_sfs
     # ---- e2e: host buffers through svb_sfs_batch
-    res_e, ms_dev_e, ms_wall_e, clocks_e = timed(lambda: idx.sfs_batch(host_np, read_offs, assemble=assemble),
-                                                 args.steps, args.warmup)
+    from svdss_b200 import parallel
+
+    def e2e_step():
+        r = idx.sfs_batch(host_np, read_offs, assemble=assemble)
+        if world > 1:  # the path's only collective: final gather of the SFS tables on rank 0 (NCCL)
+            r.gathered = parallel.gather_sfs(np.diff(r.offs), r.qs, r.len, dist, dst=0, device=dev)
+        return r
+
+    res_e, ms_dev_e, ms_wall_e, clocks_e = timed(e2e_step, args.steps, args.warmup)
     ms_step_e = ms_wall_e / args.steps
     assert res_e[-1].n_sfs == n_sfs, "resident and host paths disagree"
     peak, peak_src = hbm_peak()
@@ -230,7 +250,8 @@ def run_ours(args):
                 "ms_per_step": ms_step_e, "device_ms_per_step": ms_dev_e / args.steps},
         "gpu_launches": launches + int(sum(r.launches for r in res_e)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(n_reads, idx.block_bytes) if args.ref_bp == REF_BP else None,
+                     "peak_source": peak_src,
                      "kernel": ("k_sfs_search_tma<6,1> (thread-per-read, cp.async-staged 128 B blocks)" if idx.block_bytes == 128 and
                                 not os.environ.get("SVB_SEARCH_CFG") else "k_sfs_search cfg=%s" % os.environ.get("SVB_SEARCH_CFG", "4x1")),
                      "kernel_ms": kernel_ms,

@@ -1,0 +1,56 @@
+"""Read sharding across the GPUs of one box and the final SFS gather.
+
+The path has no exchange step: reads are independent (ping_pong.cpp:191-206), so every rank owns
+a contiguous range of the batch and a replica of the index; the only communication is gathering the
+per-read SFS tables on rank 0.  One process per GPU, `torch.distributed` for plumbing
+(NCCL on the GPU box; the same code runs under gloo in the CPU tests)."""
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """contiguous, balanced [lo, hi) of rank"""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_reads_by_bases(offs, world):
+    """cut points that balance BASES (work ~ bases) instead of read counts: list of world+1 indices"""
+    offs = np.asarray(offs, np.int64)
+    total = int(offs[-1] - offs[0])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(offs - offs[0], total * r // world, side="left")))
+    cuts.append(len(offs) - 1)
+    return [min(max(c, cuts[i - 1] if i else 0), len(offs) - 1) for i, c in enumerate(cuts)]
+
+
+def gather_sfs(local_counts, local_qs, local_len, dist, dst=0, device="cpu"):
+    """Gather per-read SFS tables on rank `dst` in global read order.
+    local_counts: int64[n_local_reads]; local_qs/local_len: int32[sum(counts)].
+    Two collectives: all_gather of the (fixed-size) shard sizes, then a padded all_gather of the
+    payload -- the payload is tiny (12 B per SFS), latency- not bandwidth-bound."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = torch.tensor([len(local_counts), len(local_qs)], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [tuple(int(x) for x in s.cpu()) for s in all_sizes]
+    max_r = max(s[0] for s in all_sizes)
+    max_s = max(s[1] for s in all_sizes)
+    pad = torch.zeros(max_r + 2 * max_s, dtype=torch.int64, device=device)
+    pad[:len(local_counts)] = torch.as_tensor(np.asarray(local_counts, np.int64), device=device)
+    pad[max_r:max_r + len(local_qs)] = torch.as_tensor(np.asarray(local_qs, np.int64), device=device)
+    pad[max_r + max_s:max_r + max_s + len(local_len)] = torch.as_tensor(np.asarray(local_len, np.int64), device=device)
+    out = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    if rank != dst:
+        return None
+    counts, qs, ln = [], [], []
+    for (nr, ns), t in zip(all_sizes, out):
+        t = t.cpu().numpy()
+        counts.append(t[:nr]); qs.append(t[max_r:max_r + ns].astype(np.int32)); ln.append(t[max_r + max_s:max_r + max_s + ns].astype(np.int32))
+    counts = np.concatenate(counts)
+    offs = np.zeros(len(counts) + 1, np.int64)
+    offs[1:] = np.cumsum(counts)
+    return offs, np.concatenate(qs), np.concatenate(ln)
