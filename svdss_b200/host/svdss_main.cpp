@@ -1,0 +1,249 @@
+// SVDSS shell for the B200 hot path: `SVDSS index | search` with the reference's flag surface
+// (reference main.cpp:34-81, config.cpp:26-107, config.hpp:68-103), C++14, calling the CUDA
+// library only through the C ABI of include/svdss_b200.h.
+//
+//   SVDSS index  [-t N] [-d] [-o OUT] FASTA          (main_build flags the pipeline uses, run_svdss:142)
+//   SVDSS search --index IDX (--bam BAM | --fastx FQ) [--threads N] [--bsize N] [--noputative]
+//                [--noassemble] [--omax N] [--verbose]        > specifics.sfs
+//
+// stdout = payload, stderr = log, EXIT_FAILURE on bad arguments like the reference.
+// Output order is the reference's (ping_pong.cpp:213-236,329-361): logical batches of --bsize
+// accepted reads, reads dealt round-robin to --threads slots, each slot printed in qname order.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <iostream>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/svdss_b200.h"
+#include "io.hpp"
+#include <unistd.h>
+static long getpid_portable() { return (long)getpid(); }
+
+using namespace std;
+using namespace svdss;
+
+static const char* VERSION = "v2.1.1-b200";
+static const char* MAIN_USAGE =
+    "Usage: SVDSS <index|search|call> --help\n"
+    "  index   build the FMD index of a reference on the GPU\n"
+    "  search  extract sample-specific strings (SFS) from a BAM/FASTX\n"
+    "  call    (POA + realignment core: use the library entries svb_poa_batch / svb_ksw_extd2_batch)";
+static const char* INDEX_USAGE = "Usage: SVDSS index [-t threads] [-d] [-o index] <reference.fa[.gz]>";
+static const char* SEARCH_USAGE =
+    "Usage: SVDSS search --index <index> (--bam <bam> | --fastx <fastx>) [--threads 4] [--bsize 10000]\n"
+    "                    [--noputative] [--noassemble] [--verbose]";
+
+struct Config {
+  string index, bam, fastx, out;
+  int threads = 4, bsize = 10000, omax = 100000, device = 0;
+  bool assemble = true, putative = true, verbose = false, help = false, version = false;
+  int overlap = -1;  // config.hpp:82: never settable from the command line
+};
+
+static void logmsg(const char* lvl, const string& m) { fprintf(stderr, "[svdss-b200] [%s] %s\n", lvl, m.c_str()); }
+
+static bool parse_common(int argc, char** argv, Config& c, vector<string>& positional) {
+  // `SVDSS --version` / `SVDSS --help`: no subcommand, options start at argv[1]
+  for (int i = (argv[1][0] == '-') ? 1 : 2; i < argc; ++i) {
+    string a = argv[i];
+    auto val = [&](string& dst) { if (i + 1 >= argc) return false; dst = argv[++i]; return true; };
+    auto ival = [&](int& dst) { string s; if (!val(s)) return false; dst = atoi(s.c_str()); return true; };
+    bool ok = true;
+    if (a == "--index") ok = val(c.index);
+    else if (a == "--bam") ok = val(c.bam);
+    else if (a == "--fastx") ok = val(c.fastx);
+    else if (a == "--threads" || a == "-t") ok = ival(c.threads);
+    else if (a.size() > 2 && a.compare(0, 2, "-t") == 0 && isdigit((unsigned char)a[2])) c.threads = atoi(a.c_str() + 2);
+    else if (a == "--bsize") ok = ival(c.bsize);
+    else if (a == "--omax") ok = ival(c.omax);
+    else if (a == "--device") ok = ival(c.device);
+    else if (a == "-o") ok = val(c.out);
+    else if (a == "-d") {}
+    else if (a == "--noassemble") c.assemble = false;
+    else if (a == "--noputative") c.putative = false;
+    else if (a == "--verbose") c.verbose = true;
+    else if (a == "--help" || a == "-h") c.help = true;
+    else if (a == "--version") c.version = true;
+    else if (!a.empty() && a[0] == '-') { logmsg("critical", "unknown option " + a); return false; }
+    else positional.push_back(a);
+    if (!ok) { logmsg("critical", "option " + a + " needs a value"); return false; }
+  }
+  if (c.threads < 1) c.threads = 1;
+  c.bsize = (c.bsize / c.threads) * c.threads;  // config.cpp:106
+  if (c.bsize < c.threads) c.bsize = c.threads;
+  return true;
+}
+
+static int run_index(const Config& c, const vector<string>& pos) {
+  if (pos.size() != 1) { cerr << INDEX_USAGE << endl; return EXIT_FAILURE; }
+  FastxReader fx(pos[0]);
+  if (!fx.ok()) { logmsg("critical", "cannot open " + pos[0]); return EXIT_FAILURE; }
+  vector<uint8_t> cat;
+  vector<int64_t> offs(1, 0);
+  FastxRecord r;
+  const uint8_t* t6 = nt6_table();
+  while (fx.next(r)) {
+    for (char ch : r.seq) cat.push_back(t6[(uint8_t)ch]);
+    offs.push_back((int64_t)cat.size());
+  }
+  if (offs.size() < 2) { logmsg("critical", "no sequences in " + pos[0]); return EXIT_FAILURE; }
+  logmsg("info", "indexing " + to_string(offs.size() - 1) + " sequences, " + to_string(cat.size()) + " bp (both strands) on GPU " + to_string(c.device));
+  svb_index_t* idx = nullptr;
+  if (svb_index_build(cat.data(), offs.data(), (int64_t)offs.size() - 1, SVB_MEM_HOST, c.device, 0, &idx) != SVB_OK) {
+    logmsg("critical", string("svb_index_build: ") + svb_last_error());
+    return EXIT_FAILURE;
+  }
+  string out = c.out;
+  const bool to_stdout = out.empty();  // ropebwt3 build writes to stdout without -o (README.md:113)
+  if (to_stdout) out = "/tmp/svdss_b200_index." + to_string((long)getpid_portable());
+  int rc = svb_index_save(idx, out.c_str());
+  svb_index_free(idx);
+  if (rc != SVB_OK) { logmsg("critical", string("svb_index_save: ") + svb_last_error()); return EXIT_FAILURE; }
+  if (to_stdout) {
+    FILE* f = fopen(out.c_str(), "rb");
+    vector<char> buf(1 << 20);
+    size_t n;
+    while (f && (n = fread(buf.data(), 1, buf.size(), f)) > 0) fwrite(buf.data(), 1, n, stdout);
+    if (f) fclose(f);
+    remove(out.c_str());
+  }
+  return EXIT_SUCCESS;
+}
+
+struct PendingRead { string qname; int hp; int64_t lo, hi; bool search; };
+
+// one GPU submission covering many logical batches; prints in the reference's order
+static bool flush(svb_index_t* idx, const Config& c, vector<PendingRead>& reads, vector<uint8_t>& cat,
+                  uint64_t& total_sfs) {
+  if (reads.empty()) return true;
+  vector<int64_t> offs(1, 0);
+  vector<uint8_t> sub;
+  vector<int64_t> slot_of(reads.size(), -1);
+  int64_t n = 0;
+  // reads filtered by the XF rule keep their slot but are not searched (ping_pong.cpp:202-203)
+  for (size_t i = 0; i < reads.size(); ++i)
+    if (reads[i].search) { slot_of[i] = n++; offs.push_back(offs.back() + (reads[i].hi - reads[i].lo)); }
+  sub.reserve((size_t)offs.back());
+  for (size_t i = 0; i < reads.size(); ++i)
+    if (reads[i].search) sub.insert(sub.end(), cat.begin() + reads[i].lo, cat.begin() + reads[i].hi);
+  svb_sfs_out_t out;
+  if (svb_sfs_batch(idx, sub.data(), offs.data(), n, c.overlap, c.assemble ? 1 : 0, &out) != SVB_OK) {
+    logmsg("critical", string("svb_sfs_batch: ") + svb_last_error());
+    return false;
+  }
+  string line;
+  for (size_t b0 = 0; b0 < reads.size(); b0 += (size_t)c.bsize) {          // logical batch
+    const size_t b1 = min(reads.size(), b0 + (size_t)c.bsize);
+    for (int t = 0; t < c.threads; ++t) {                                   // thread slot
+      map<string, vector<size_t>> slot;                                     // batch_type_t is a std::map
+      for (size_t i = b0 + (size_t)t; i < b1; i += (size_t)c.threads)
+        if (reads[i].search) slot[reads[i].qname].push_back(i);
+      for (auto& kv : slot) {
+        bool first = true;
+        for (size_t i : kv.second) {
+          const int64_t r = slot_of[i];
+          for (int64_t k = out.offs[r]; k < out.offs[r + 1]; ++k) {         // ping_pong.cpp:227-228
+            line = (first ? kv.first : string("*")) + "\t" + to_string(out.qs[k]) + "\t" + to_string(out.len[k]) +
+                   "\t" + to_string(reads[i].hp) + "\t\n";
+            fwrite(line.data(), 1, line.size(), stdout);
+            first = false;
+            ++total_sfs;
+          }
+        }
+      }
+    }
+  }
+  svb_sfs_out_free(&out);
+  reads.clear();
+  cat.clear();
+  return true;
+}
+
+static int run_search(const Config& c) {
+  if (c.index.empty() || (c.fastx.empty() && c.bam.empty())) { cerr << SEARCH_USAGE << endl; return EXIT_FAILURE; }
+  logmsg("info", "Restoring index..");
+  svb_index_t* idx = nullptr;
+  if (svb_index_load(c.index.c_str(), c.device, &idx) != SVB_OK) {
+    logmsg("critical", string("svb_index_load: ") + svb_last_error());
+    return EXIT_FAILURE;
+  }
+  // GPU submissions cover as many logical batches as fit ~4 Gbases of reads
+  const size_t gpu_bases = (size_t)4 << 30;
+  vector<PendingRead> reads;
+  vector<uint8_t> cat;
+  uint64_t total_sfs = 0, processed = 0;
+  auto maybe_flush = [&]() {
+    if (cat.size() >= gpu_bases && reads.size() % (size_t)c.bsize == 0) return flush(idx, c, reads, cat, total_sfs);
+    return true;
+  };
+  logmsg("info", "Extracting SFS strings on GPU " + to_string(c.device) + " (ordering as with " + to_string(c.threads) + " threads)..");
+  bool ok = true;
+  if (!c.bam.empty()) {
+    BamReader bam(c.bam);
+    if (!bam.ok()) { logmsg("critical", "cannot read BAM " + c.bam); svb_index_free(idx); return EXIT_FAILURE; }
+    BamRecord r;
+    int st;
+    while (ok && (st = bam.next(r)) == 1) {
+      ++processed;
+      if (r.flag & 0x4 || r.flag & 0x800 || r.flag & 0x100) continue;       // ping_pong.cpp:66-69
+      if (r.l_qseq < 100) {                                                  // :70-75
+        logmsg("warning", "Alignment filtered due to l_qseq. Why are we here? Please check");
+        continue;
+      }
+      if (r.tid < 0) { logmsg("critical", "core.tid < 0. Why are we here? Please check"); svb_index_free(idx); exit(1); }  // :76-79
+      const int xf = r.has_xf ? (int)r.xf : 0, hp = r.has_hp ? (int)r.hp : 0; // :196-201
+      PendingRead pr{r.qname, hp, (int64_t)cat.size(), 0, !(c.putative && xf != 0)};
+      cat.insert(cat.end(), r.nt6.begin(), r.nt6.end());
+      pr.hi = (int64_t)cat.size();
+      reads.push_back(pr);
+      ok = maybe_flush();
+    }
+    if (ok && st < 0) { logmsg("critical", "truncated or corrupt BAM"); ok = false; }
+  } else {
+    logmsg("warning", "FASTX mode is not optimized (higher running times and larger SFSs set).");  // ping_pong.cpp:253-254
+    FastxReader fx(c.fastx);
+    if (!fx.ok()) { logmsg("critical", "cannot open " + c.fastx); svb_index_free(idx); return EXIT_FAILURE; }
+    FastxRecord r;
+    const uint8_t* t6 = nt6_table();
+    while (ok && fx.next(r)) {
+      ++processed;
+      PendingRead pr{r.name, 0, (int64_t)cat.size(), 0, true};
+      for (char ch : r.seq) cat.push_back(t6[(uint8_t)ch]);                  // rb3_char2nt6, ping_pong.cpp:158
+      pr.hi = (int64_t)cat.size();
+      reads.push_back(pr);
+      ok = maybe_flush();
+    }
+  }
+  if (ok) ok = flush(idx, c, reads, cat, total_sfs);
+  fflush(stdout);
+  svb_index_free(idx);
+  if (!ok) return EXIT_FAILURE;
+  logmsg("info", "records read: " + to_string(processed) + ", SFS lines written: " + to_string(total_sfs));
+  return EXIT_SUCCESS;
+}
+
+int main(int argc, char** argv) {
+  time_t t0;
+  time(&t0);
+  if (argc == 1) { cerr << MAIN_USAGE << endl; exit(EXIT_FAILURE); }   // main.cpp:27-31
+  Config c;
+  vector<string> pos;
+  if (!parse_common(argc, argv, c, pos)) exit(EXIT_FAILURE);
+  const string mode = argv[1];
+  if (c.version) { cout << "SVDSS, " << VERSION << endl; exit(EXIT_SUCCESS); }
+  if (c.help) { cerr << (mode == "index" ? INDEX_USAGE : mode == "search" ? SEARCH_USAGE : MAIN_USAGE) << endl; exit(EXIT_SUCCESS); }
+  int rc;
+  if (mode == "index") rc = run_index(c, pos);
+  else if (mode == "search") rc = run_search(c);
+  else { cerr << MAIN_USAGE << endl; exit(EXIT_FAILURE); }
+  if (rc != EXIT_SUCCESS) return rc;
+  time_t t1;
+  time(&t1);
+  logmsg("info", "All done! Runtime: " + to_string((long)(t1 - t0)) + " seconds");   // main.cpp:85
+  return 0;
+}
