@@ -21,6 +21,7 @@
 
 #include "../../include/svdss_b200.h"
 #include "io.hpp"
+#include "call.hpp"
 #include <unistd.h>
 static long getpid_portable() { return (long)getpid(); }
 
@@ -32,14 +33,22 @@ static const char* MAIN_USAGE =
     "Usage: SVDSS <index|search|call> --help\n"
     "  index   build the FMD index of a reference on the GPU\n"
     "  search  extract sample-specific strings (SFS) from a BAM/FASTX\n"
-    "  call    (POA + realignment core: use the library entries svb_poa_batch / svb_ksw_extd2_batch)";
+    "  call    POA consensus + ksw2 realignment + SV extraction from SFS clusters";
 static const char* INDEX_USAGE = "Usage: SVDSS index [-t threads] [-d] [-o index] <reference.fa[.gz]>";
+static const char* CALL_USAGE =
+    "Usage: SVDSS call --reference <fa> (--clusters-in <clusters.txt> | --bam <bam> --sfs <sfs>) [--poa <out.sam>]\n"
+    "                  [--min-cluster-weight 2] [--min-sv-length 25] [-l 0.97]\n"
+    "  The POA + realignment core (Caller::pcall) runs on the GPU. Building clusters from --bam/--sfs\n"
+    "  (Clusterer) is not part of this build: pass the file written by the reference's `call --clusters`.";
 static const char* SEARCH_USAGE =
     "Usage: SVDSS search --index <index> (--bam <bam> | --fastx <fastx>) [--threads 4] [--bsize 10000]\n"
     "                    [--noputative] [--noassemble] [--verbose]";
 
 struct Config {
-  string index, bam, fastx, out;
+  string index, bam, fastx, out, reference, sfs, clusters_in, poa;
+  int min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
+  float min_ratio = 0.97f;
+  bool noht = false, clipped = false;
   int threads = 4, bsize = 10000, omax = 100000, device = 0;
   bool assemble = true, putative = true, verbose = false, help = false, version = false;
   int overlap = -1;  // config.hpp:82: never settable from the command line
@@ -60,6 +69,16 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
     else if (a == "--threads" || a == "-t") ok = ival(c.threads);
     else if (a.size() > 2 && a.compare(0, 2, "-t") == 0 && isdigit((unsigned char)a[2])) c.threads = atoi(a.c_str() + 2);
     else if (a == "--bsize") ok = ival(c.bsize);
+    else if (a == "--reference") ok = val(c.reference);
+    else if (a == "--sfs") ok = val(c.sfs);
+    else if (a == "--clusters-in") ok = val(c.clusters_in);
+    else if (a == "--poa") ok = val(c.poa);
+    else if (a == "--min-cluster-weight") ok = ival(c.min_cluster_weight);
+    else if (a == "--min-sv-length") { ok = ival(c.min_sv_length); c.min_sv_length = max(25, c.min_sv_length); }  // config.cpp:87
+    else if (a == "--min-mapq") ok = ival(c.min_mapq);
+    else if (a == "-l") { string v; ok = val(v); if (ok) c.min_ratio = (float)atof(v.c_str()); }
+    else if (a == "--noht") c.noht = true;
+    else if (a == "--clipped") c.clipped = true;
     else if (a == "--omax") ok = ival(c.omax);
     else if (a == "--device") ok = ival(c.device);
     else if (a == "-o") ok = val(c.out);
@@ -236,10 +255,22 @@ int main(int argc, char** argv) {
   if (!parse_common(argc, argv, c, pos)) exit(EXIT_FAILURE);
   const string mode = argv[1];
   if (c.version) { cout << "SVDSS, " << VERSION << endl; exit(EXIT_SUCCESS); }
-  if (c.help) { cerr << (mode == "index" ? INDEX_USAGE : mode == "search" ? SEARCH_USAGE : MAIN_USAGE) << endl; exit(EXIT_SUCCESS); }
+  if (c.help) { cerr << (mode == "index" ? INDEX_USAGE : mode == "search" ? SEARCH_USAGE : mode == "call" ? CALL_USAGE : MAIN_USAGE) << endl; exit(EXIT_SUCCESS); }
   int rc;
   if (mode == "index") rc = run_index(c, pos);
   else if (mode == "search") rc = run_search(c);
+  else if (mode == "call") {
+    if (c.reference.empty() || (c.clusters_in.empty() && (c.bam.empty() || c.sfs.empty()))) { cerr << CALL_USAGE << endl; exit(EXIT_FAILURE); }  // main.cpp:56-59
+    if (c.clusters_in.empty()) {
+      logmsg("critical", "clustering SFSs from --bam/--sfs (Clusterer) is not built yet; pass --clusters-in (see --help)");
+      exit(EXIT_FAILURE);
+    }
+    CallConfig cc;
+    cc.reference = c.reference; cc.clusters_in = c.clusters_in; cc.poa_out = c.poa;
+    cc.min_cluster_weight = (unsigned)c.min_cluster_weight; cc.min_sv_length = (unsigned)c.min_sv_length;
+    cc.min_ratio = c.min_ratio; cc.device = c.device;
+    rc = run_call(cc, [](const char* l, const string& m) { logmsg(l, m); });
+  }
   else { cerr << MAIN_USAGE << endl; exit(EXIT_FAILURE); }
   if (rc != EXIT_SUCCESS) return rc;
   time_t t1;

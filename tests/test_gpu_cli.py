@@ -126,3 +126,56 @@ def test_search_bam_filters_and_tags(world):
         want = expected_sfs_text(names, exp, htags, searched if putative else [True] * len(names), 4, 40, True)
         assert r.stdout == want
     assert "\t1\t\n" in want or "\t2\t\n" in want    # some HP tag made it to the output
+
+
+def test_call_core_from_clusters_file(world):
+    """`SVDSS call --clusters-in`: POA + ksw2 + CIGAR->SV on the GPU vs the Python restatement over
+    the oracle; planted INS/DEL alleles must come out as SV records with exact coordinates."""
+    import call_model
+    from poa_cases import noisy_copy
+    rng = np.random.default_rng(71)
+    contigs = world["contigs"]
+    ref = {"chr%d" % (i + 1): dec(c).replace("N", "A") for i, c in enumerate(contigs)}
+    fa = os.path.join(world["d"], "ref_call.fa")
+    with open(fa, "w") as f:
+        for k, v in ref.items():
+            f.write(">%s\n%s\n" % (k, v.lower() if k == "chr2" else v))     # load_chromosomes upper-cases
+    clusters, lines = [], []
+    code = lambda s: oracle.CHAR26[np.frombuffer(s.encode(), np.uint8)]
+    for ci in range(14):
+        chrom = "chr%d" % (1 + ci % 3)
+        L = int(rng.integers(300, 900))
+        s = int(rng.integers(1000, len(ref[chrom]) - L - 1000))
+        e = s + L - 1
+        window = code(ref[chrom][s:e + 1])
+        kind = ci % 3
+        p, k = int(rng.integers(60, L - 200)), int(rng.integers(30, 120))
+        if kind == 0:
+            allele = np.concatenate([window[:p], rng.integers(0, 4, size=k).astype(np.uint8), window[p:]])   # INS
+        elif kind == 1:
+            allele = np.concatenate([window[:p], window[p + k:]])                                            # DEL
+        else:
+            allele = window                                                                                   # no SV
+        n = int(rng.integers(1, 9)) if ci != 5 else 1      # ci == 5: below --min-cluster-weight
+        sub = [("r%d_%d" % (ci, j), "".join("ACGT"[c] for c in noisy_copy(rng, allele, 0.002))) for j in range(n)]
+        if ci == 7:   # second length group: reference-length reads next to the allele reads
+            sub += [("w%d_%d" % (ci, j), "".join("ACGT"[c] for c in window)) for j in range(3)]
+        clusters.append((chrom, s, e, sub))
+        lines.append("%s:%d-%d\t%d\t%s" % (chrom, s + 1, e + 1, len(sub), "\t".join("%s:%s" % x for x in sub)))
+    cfile = os.path.join(world["d"], "clusters.txt")
+    open(cfile, "w").write("\n".join(lines) + "\n")
+    sam = os.path.join(world["d"], "poa.sam")
+    r = subprocess.run([world["exe"], "call", "--reference", fa, "--clusters-in", cfile, "--poa", sam,
+                        "--min-cluster-weight", "2", "--min-sv-length", "25"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.splitlines()
+    header = [l for l in out if l.startswith("#")]
+    body = [l for l in out if not l.startswith("#")]
+    assert header[0] == "##fileformat=VCFv4.2" and header[-1].startswith("#CHROM\tPOS\tID\tREF\tALT")
+    assert "##contig=<ID=chr1,length=%d>" % len(ref["chr1"]) in header
+    want = call_model.call_vcf_lines(ref, clusters)
+    assert sorted(body) == sorted(want)
+    assert [l.split("\t")[:2] for l in body] == sorted([l.split("\t")[:2] for l in body], key=lambda x: (x[0], int(x[1])))
+    assert sum("SVTYPE=INS" in l for l in body) >= 3 and sum("SVTYPE=DEL" in l for l in body) >= 3
+    samtxt = open(sam).read().splitlines()
+    assert samtxt[0] == "@HD\tVN:1.4" and sum(1 for l in samtxt if not l.startswith("@")) >= 12
