@@ -564,40 +564,39 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
           }
         }
       }
-      // state machine of ping_pong.cpp:15-47, advanced to the next pending extension
+      // state machine of ping_pong.cpp:15-47, advanced to the next pending extension.  Both
+      // directions share ONE fast path (dir = -1 backward, +1 forward) so that threads in
+      // different phases do not serialise the warp.
       while (have && !do_ext) {
-        if (phase == 0) {
-          if (s != 0 && pos > 0) {
-            --pos;
-            c = win.get(P.seq, roff + pos, -1);
-            do_ext = true;
-          } else if (s != 0) {
+        const int dir = phase ? 1 : -1;
+        const bool room = phase ? (pos + 1 < len) : (pos > 0);
+        if (s != 0 && room) {
+          pos += dir;
+          const int ch = win.get(P.seq, roff + pos, dir);
+          c = phase ? comp6(ch) : ch;
+          do_ext = true;
+        } else if (phase == 0) {
+          if (s != 0) {
             finish_read();  // reached the read start still matching (ping_pong.cpp:24-25)
-          } else {
+          } else {          // mismatch at pos: forward search from here (ping_pong.cpp:27-30)
             begin = pos;
             phase = 1;
             set_intv(comp6(win.get(P.seq, roff + pos, +1)));
           }
         } else {
-          if (s != 0 && pos + 1 < len) {
-            ++pos;
-            c = comp6(win.get(P.seq, roff + pos, +1));
-            do_ext = true;
+          if (s != 0) ++pos;               // defensive: cannot happen (see k_sfs_search)
+          on_sfs(begin, pos - begin + 1);  // ping_pong.cpp:39-41
+          if (begin == 0) {
+            finish_read();
           } else {
-            if (s != 0) ++pos;
-            on_sfs(begin, pos - begin + 1);  // ping_pong.cpp:39-41
-            if (begin == 0) {
+            int nb = (P.overlap == 0) ? begin - 1 : pos + P.overlap;  // ping_pong.cpp:44-47
+            if (nb < 0) {
               finish_read();
             } else {
-              int nb = (P.overlap == 0) ? begin - 1 : pos + P.overlap;  // ping_pong.cpp:44-47
-              if (nb < 0) {
-                finish_read();
-              } else {
-                if (nb > len - 1) nb = len - 1;
-                pos = nb;
-                phase = 0;
-                set_intv(win.get(P.seq, roff + pos, -1));
-              }
+              if (nb > len - 1) nb = len - 1;
+              pos = nb;
+              phase = 0;
+              set_intv(win.get(P.seq, roff + pos, -1));
             }
           }
         }
