@@ -37,7 +37,8 @@ void set_error(const char* fmt, ...);
 // so a G-lane group fetches a whole block with ONE coalesced 16-byte load per lane and every lane
 // owns the 32 symbols whose planes it loaded.
 //   G = 4 : 64-byte blocks, 128 symbols, slots {A,C,G,T};       N from the side array cntN[]
-//   G = 8 : 128-byte blocks, 256 symbols, slots {A,C,G,T,N,$,-,-}
+//   G = 8 : 128-byte blocks, 256 symbols, slots {A,C,G,T,N, cum64, cum128, cum192} where cumX packs,
+//           one byte per symbol A,C,G,T, the in-block count before symbol X (sub-block sampling)
 // Padding symbols past n carry code 7 (matches nothing).  Superblock table:
 //     sbase[sb*8 + c] = acc[c] + Occ(c, sb << 32)           (int64, c = 0..5)
 // ---------------------------------------------------------------------------------------------

@@ -550,6 +550,25 @@ __global__ void k_block_headers(uint4* __restrict__ blocks, const uint64_t* __re
       reinterpret_cast<uint32_t*>(&blocks[b * G + j])[0] = v;
     }
     if (G == 4) cntN[b] = (uint32_t)(occ[5LL * n_blocks + b] - occ[5LL * n_blocks + b0]);
+    if (G == 8) {
+      // in-block sampling for the thread-per-read kernel: slots 5,6,7 hold, one byte per symbol
+      // A,C,G,T, the number of occurrences before symbol 64, 128, 192 of the block (<= 192), so a
+      // rank needs the planes of ONE 64-symbol sub-block instead of the whole block.
+      // (The '$' count that used to sit in slot 5 is never read: rank2a derives it.)
+      unsigned cum[4] = {0, 0, 0, 0};
+      for (int sub = 0; sub < 3; ++sub) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint4 sl = blocks[b * G + 2 * sub + h];
+#pragma unroll
+          for (int sym = 1; sym <= 4; ++sym) {
+            const unsigned c0 = (sym & 1) ? 0u : ~0u, c1 = (sym & 2) ? 0u : ~0u, c2 = (sym & 4) ? 0u : ~0u;
+            cum[sym - 1] += __popc((sl.y ^ c0) & (sl.z ^ c1) & (sl.w ^ c2));
+          }
+        }
+        reinterpret_cast<uint32_t*>(&blocks[b * G + 5 + sub])[0] = cum[0] | (cum[1] << 8) | (cum[2] << 16) | (cum[3] << 24);
+      }
+    }
   }
 }
 
@@ -798,7 +817,7 @@ int svb_index_get_bwt(const svb_index_t* idx, uint8_t* bwt_host) {
 
 // ---- index file: private layout (the reference treats the index file as opaque, run_svdss:137-164)
 struct FileHeader {
-  char magic[8];  // "SVB200I\1"
+  char magic[8];  // "SVB200I\2"
   int32_t G;
   int32_t n_sb;
   int64_t n;
@@ -815,7 +834,7 @@ int svb_index_save(const svb_index_t* idx, const char* path) {
   if (!f) { set_error("cannot open %s for writing", path); return SVB_EIO; }
   FileHeader h;
   memset(&h, 0, sizeof(h));
-  memcpy(h.magic, "SVB200I\1", 8);
+  memcpy(h.magic, "SVB200I\2", 8);
   h.G = d.G; h.n_sb = d.n_sb; h.n = d.n; memcpy(h.acc, d.acc, sizeof(d.acc));
   h.n_blocks = d.n_blocks; h.n_contigs = d.n_contigs;
   bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
@@ -842,7 +861,7 @@ int svb_index_load(const char* path, int device, svb_index_t** out) {
   FILE* f = fopen(path, "rb");
   if (!f) { set_error("cannot open index %s", path); return SVB_EIO; }
   FileHeader h;
-  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "SVB200I\1", 8) != 0 || (h.G != 4 && h.G != 8)) {
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "SVB200I\2", 8) != 0 || (h.G != 4 && h.G != 8)) {
     fclose(f);
     set_error("%s is not a svdss_b200 index (ropebwt3 .fmd files are not readable yet)", path);
     return SVB_EINVAL;

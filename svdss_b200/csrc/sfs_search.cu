@@ -33,6 +33,27 @@ struct svb_reads {
 
 namespace svb {
 
+// Stream-ordered allocations from the device's default memory pool with an unbounded release
+// threshold: repeated batches reuse the same physical memory instead of paying cudaMalloc/cudaFree
+// (tens of ms per call for multi-GB buffers on some hosts) inside every svb_sfs_* call.
+static cudaError_t pmalloc(void** p, size_t bytes, cudaStream_t st) {
+  static thread_local int tuned_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (tuned_dev != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    tuned_dev = dev;
+  }
+  return cudaMallocAsync(p, bytes ? bytes : 1, st);
+}
+static void pfree(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
+
 struct SearchParams {
   const uint4* __restrict__ blocks;
   const uint32_t* __restrict__ cntN;
@@ -422,34 +443,52 @@ __device__ __forceinline__ bool tma_issue(const SearchParams& P, uint64_t k, uin
   return two;
 }
 
-// finish the extension from the staged blocks (thread-local; slice order rotated by lane so that
-// the 8 threads of an LDS.128 phase hit 8 different 16-byte bank groups)
+// rank of symbol c (1..4) at in-block offset `off` from a staged block: base count slot + in-block
+// sample (slots 5..7) + popcount over ONE 64-symbol sub-block.  rot = slice rotation of this thread.
+__device__ __forceinline__ unsigned staged_occ(const uint4* blk, int off, int c, int rot) {
+  const int sub = off >> 6, r = off & 63;
+  const uint4 a = blk[(2 * sub + rot) & 7];
+  const uint4 b = blk[(2 * sub + 1 + rot) & 7];
+  const unsigned c0 = (c & 1) ? 0u : ~0u, c1 = (c & 2) ? 0u : ~0u, c2 = (c & 4) ? 0u : ~0u;
+  const unsigned m0 = (a.y ^ c0) & (a.z ^ c1) & (a.w ^ c2);
+  const unsigned m1 = (b.y ^ c0) & (b.z ^ c1) & (b.w ^ c2);
+  const unsigned k0 = r >= 32 ? ~0u : ((1u << r) - 1u);
+  const unsigned k1 = r > 32 ? ((1u << (r - 32)) - 1u) : 0u;
+  const unsigned base = blk[(c - 1 + rot) & 7].x;
+  const unsigned cum = sub ? ((blk[(4 + sub + rot) & 7].x >> (8 * (c - 1))) & 0xffu) : 0u;
+  return base + cum + __popc(m0 & k0) + __popc(m1 & k1);
+}
+
+// finish the extension from the staged blocks (thread-local).  ACGT take the sub-block path; N
+// (rare: only reads that carry N) scans the whole block.
 __device__ __forceinline__ void tma_consume(const SearchParams& P, const uint4* slot, bool two, int c, uint64_t& k,
-                                            uint64_t& s, int lane) {
+                                            uint64_t& s, int rot) {
   const uint64_t l = k + s;
   const int offk = (int)((unsigned)k & 255u), offl = (int)((unsigned)l & 255u);
-  const unsigned c0 = (c & 1) ? 0u : ~0u, c1 = (c & 2) ? 0u : ~0u, c2 = (c & 4) ? 0u : ~0u;
-  unsigned pk = 0, pl = 0, ck = 0, cl = 0;
   const uint4* sl_ptr = two ? slot + 8 : slot;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int j = (i + lane) & 7;
-    const uint4 a = slot[j];
-    const uint4 b = sl_ptr[j];
-    const unsigned mk = (a.y ^ c0) & (a.z ^ c1) & (a.w ^ c2);
-    const unsigned ml = (b.y ^ c0) & (b.z ^ c1) & (b.w ^ c2);
-    const int nk_ = max(0, min(32, offk - 32 * j));
-    const int nl_ = max(0, min(32, offl - 32 * j));
-    pk += __popc(mk & (nk_ >= 32 ? ~0u : ((1u << nk_) - 1u)));
-    pl += __popc(ml & (nl_ >= 32 ? ~0u : ((1u << nl_) - 1u)));
-    const unsigned sel = (j == c - 1) ? ~0u : 0u;
-    ck |= a.x & sel;
-    cl |= b.x & sel;
+  unsigned rk, rl;
+  if (c <= 4) {
+    rk = staged_occ(slot, offk, c, rot);
+    rl = staged_occ(sl_ptr, offl, c, rot);
+  } else {
+    const unsigned c0 = (c & 1) ? 0u : ~0u, c1 = (c & 2) ? 0u : ~0u, c2 = (c & 4) ? 0u : ~0u;
+    unsigned pk = 0, pl = 0;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      const uint4 a = slot[(j + rot) & 7];
+      const uint4 b = sl_ptr[(j + rot) & 7];
+      const int nk_ = max(0, min(32, offk - 32 * j));
+      const int nl_ = max(0, min(32, offl - 32 * j));
+      pk += __popc((a.y ^ c0) & (a.z ^ c1) & (a.w ^ c2) & (nk_ >= 32 ? ~0u : ((1u << nk_) - 1u)));
+      pl += __popc((b.y ^ c0) & (b.z ^ c1) & (b.w ^ c2) & (nl_ >= 32 ? ~0u : ((1u << nl_) - 1u)));
+    }
+    rk = slot[(4 + rot) & 7].x + pk;    // count slot 4 = N
+    rl = sl_ptr[(4 + rot) & 7].x + pl;
   }
   const int64_t sbk = __ldg(P.sbase + (k >> 32) * 8 + c);
   const int64_t sbl = __ldg(P.sbase + (l >> 32) * 8 + c);
-  const uint64_t nk = (uint64_t)sbk + ck + pk;
-  const uint64_t nl = (uint64_t)sbl + cl + pl;
+  const uint64_t nk = (uint64_t)sbk + rk;
+  const uint64_t nl = (uint64_t)sbl + rl;
   k = nk;
   s = nl - nk;
 }
@@ -470,7 +509,9 @@ __device__ __forceinline__ void cpa_fetch(const SearchParams& P, uint32_t bk, ui
     const int t = 4 * r + sub;
     const uint32_t xk = __shfl_sync(0xffffffffu, bk, t);
     const uint32_t xl = __shfl_sync(0xffffffffu, bl, t);
-    const uint32_t dst = warp_stage_s + (uint32_t)(t * 256 + j * 16);
+    // slice j of thread t's block sits at physical slot (j + t) & 7: threads reading the same logical
+    // slice then hit different shared-memory banks
+    const uint32_t dst = warp_stage_s + (uint32_t)(t * 256 + ((j + t) & 7) * 16);
     if (xk != NOBLK) cp_async16(dst, P.blocks + (uint64_t)xk * 8 + j);
     if (xl != xk) cp_async16(dst + 128u, P.blocks + (uint64_t)xl * 8 + j);
   }
@@ -478,7 +519,7 @@ __device__ __forceinline__ void cpa_fetch(const SearchParams& P, uint32_t bk, ui
   __syncwarp();
 }
 
-constexpr int TMA_WARPS = 4;  // warps per CTA; 8 KB of staging per warp
+constexpr int TMA_WARPS = 3;  // warps per CTA; 8 KB of staging per warp -> 9 CTAs = 27 warps per SM
 
 template <int MINB, int MODE>  // MODE 0: TMA bulk copies (UBLKCP), 1: cooperative cp.async (LDGSTS)
 __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const SearchParams P) {
@@ -615,7 +656,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
       cpa_fetch(P, bk, bl, smem_u32(stage + warp * 32 * 16), lane);
     }
     if (do_ext) {
-      tma_consume(P, my, two, c, k, s, lane);
+      tma_consume(P, my, two, c, k, s, MODE == 1 ? lane : 0);
       ++n_ext;
       n_blk += two ? 2u : 1u;
     }
@@ -666,7 +707,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) k_rank_bench_tma(const SearchP
       cpa_fetch(P, bk, bl, smem_u32(stage + warp * 32 * 16), lane);
     }
     if (act) {
-      tma_consume(P, my, two, c, k, s, lane);
+      tma_consume(P, my, two, c, k, s, MODE == 1 ? lane : 0);
       nb += two ? 2u : 1u;
       acc += k + s;
     }
@@ -702,18 +743,18 @@ static int make_order(svb_reads* R, int64_t chunk_bytes, cudaStream_t st) {
   if (n == 0) return SVB_OK;
   uint64_t *k1 = nullptr, *k2 = nullptr;
   uint32_t* v1 = nullptr;
-  SVB_CUDA(cudaMalloc((void**)&k1, n * 8));
-  SVB_CUDA(cudaMalloc((void**)&k2, n * 8));
-  SVB_CUDA(cudaMalloc((void**)&v1, n * 4));
-  SVB_CUDA(cudaMalloc((void**)&R->d_order, n * 4));
+  SVB_CUDA(pmalloc((void**)&k1, n * 8, st));
+  SVB_CUDA(pmalloc((void**)&k2, n * 8, st));
+  SVB_CUDA(pmalloc((void**)&v1, n * 4, st));
+  SVB_CUDA(pmalloc((void**)&R->d_order, n * 4, st));
   k_read_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->d_offs, n, chunk_bytes, k1, v1);
   size_t bytes = 0;
   void* tmp = nullptr;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, k1, k2, v1, R->d_order, n, 0, 64, st);
-  SVB_CUDA(cudaMalloc(&tmp, bytes));
+  SVB_CUDA(pmalloc(&tmp, bytes, st));
   SVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k1, k2, v1, R->d_order, n, 0, 64, st));
+  pfree(tmp, st); pfree(k1, st); pfree(k2, st); pfree(v1, st);
   SVB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(tmp); cudaFree(k1); cudaFree(k2); cudaFree(v1);
   return SVB_OK;
 }
 
@@ -788,8 +829,9 @@ struct SearchScratch {
   uint64_t* d_key = nullptr; uint64_t* d_key2 = nullptr;
   uint32_t* d_len = nullptr; uint32_t* d_len2 = nullptr;
   void* d_tmp = nullptr;
+  cudaStream_t st = nullptr;
   ~SearchScratch() {
-    cudaFree(d_ctr); cudaFree(d_key); cudaFree(d_key2); cudaFree(d_len); cudaFree(d_len2); cudaFree(d_tmp);
+    pfree(d_ctr, st); pfree(d_key, st); pfree(d_key2, st); pfree(d_len, st); pfree(d_len2, st); pfree(d_tmp, st);
   }
 };
 
@@ -820,13 +862,14 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   P.seq = R->d_seq; P.offs = R->d_offs; P.order = R->d_order; P.n_reads = n_reads;
   P.overlap = overlap; P.assemble = assemble;
   SearchScratch S;
-  SVB_CUDA(cudaMalloc((void**)&S.d_ctr, 4 * sizeof(unsigned long long)));
+  S.st = st;
+  SVB_CUDA(pmalloc((void**)&S.d_ctr, 4 * sizeof(unsigned long long), st));
   // first guess of output capacity; exact count is known after the run, rerun once if it overflowed
   unsigned long long cap = assemble ? (unsigned long long)(4 * n_reads + 1024)
                                     : (unsigned long long)(R->total / 8 + 64 * n_reads + 1024);
   int grid = 0, cfgG = 0;
   SVB_TRY(pick_cfg(d.G, &cfgG));
-  const int tma_minb = 6;
+  const int tma_minb = 9;
   if (cfgG == 0) {
     SVB_TRY(persistent_grid(k_sfs_search_tma<tma_minb, 0>, TMA_WARPS * 32, d.device, &grid));
   } else if (cfgG == -1) {
@@ -842,9 +885,9 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   unsigned long long ctr[4] = {0, 0, 0, 0};
   float kms = 0.f;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    cudaFree(S.d_key); cudaFree(S.d_len); S.d_key = nullptr; S.d_len = nullptr;
-    SVB_CUDA(cudaMalloc((void**)&S.d_key, cap * 8));
-    SVB_CUDA(cudaMalloc((void**)&S.d_len, cap * 4));
+    pfree(S.d_key, st); pfree(S.d_len, st); S.d_key = nullptr; S.d_len = nullptr;
+    SVB_CUDA(pmalloc((void**)&S.d_key, cap * 8, st));
+    SVB_CUDA(pmalloc((void**)&S.d_len, cap * 4, st));
     SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 4 * sizeof(unsigned long long), st));
     P.work = S.d_ctr + 0; P.out_count = S.d_ctr + 1; P.stats = S.d_ctr + 2;
     P.out_key = S.d_key; P.out_len = S.d_len; P.out_cap = cap;
@@ -889,15 +932,15 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   out->n_sfs = m;
   if (m == 0) return SVB_OK;
   // order records by (read, qs asc | emit order)
-  SVB_CUDA(cudaMalloc((void**)&S.d_key2, m * 8));
-  SVB_CUDA(cudaMalloc((void**)&S.d_len2, m * 4));
+  SVB_CUDA(pmalloc((void**)&S.d_key2, m * 8, st));
+  SVB_CUDA(pmalloc((void**)&S.d_len2, m * 4, st));
   cub::DoubleBuffer<uint64_t> dk(S.d_key, S.d_key2);
   cub::DoubleBuffer<uint32_t> dv(S.d_len, S.d_len2);
   int rbits = 1;
   while (rbits < 32 && ((uint64_t)n_reads >> rbits)) ++rbits;
   size_t bytes = 0;
   SVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, m, 0, 32 + rbits, st));
-  SVB_CUDA(cudaMalloc(&S.d_tmp, bytes));
+  SVB_CUDA(pmalloc(&S.d_tmp, bytes, st));
   SVB_CUDA(cub::DeviceRadixSort::SortPairs(S.d_tmp, bytes, dk, dv, m, 0, 32 + rbits, st));
   out->launches += 1;
   std::vector<uint64_t> hkey((size_t)m);
@@ -942,7 +985,7 @@ int svb_reads_upload(const uint8_t* seq, const int64_t* offs, int64_t n_reads, i
   int rc = SVB_OK;
   do {
     if (R->total < 0 || (R->total > 0 && !seq)) { set_error("svb_reads_upload: bad offsets"); rc = SVB_EINVAL; break; }
-    if (cudaMalloc((void**)&R->d_offs, (n_reads + 1) * 8) != cudaSuccess) { rc = SVB_ENOMEM; break; }
+    if (pmalloc((void**)&R->d_offs, (n_reads + 1) * 8, 0) != cudaSuccess) { rc = SVB_ENOMEM; break; }
     if (mem == SVB_MEM_HOST) {
       std::vector<int64_t> rb((size_t)n_reads + 1);
       for (int64_t i = 0; i <= n_reads; ++i) {
@@ -952,7 +995,7 @@ int svb_reads_upload(const uint8_t* seq, const int64_t* offs, int64_t n_reads, i
       if (rc) break;
       // one spare window (<= 32 B) after the last base, rounded to 64 B
       size_t padded = ((size_t)R->total + 64 + 63) & ~(size_t)63;
-      if (cudaMalloc((void**)&R->d_seq, padded) != cudaSuccess) { rc = SVB_ENOMEM; break; }
+      if (pmalloc((void**)&R->d_seq, padded, 0) != cudaSuccess) { rc = SVB_ENOMEM; break; }
       cudaMemcpy(R->d_offs, rb.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice);
       if (R->total) cudaMemcpy(R->d_seq, seq + first, R->total, cudaMemcpyHostToDevice);
       cudaMemset(R->d_seq + R->total, 0, padded - R->total);
@@ -976,9 +1019,9 @@ int svb_reads_upload(const uint8_t* seq, const int64_t* offs, int64_t n_reads, i
 void svb_reads_free(svb_reads_t* R) {
   if (!R) return;
   cudaSetDevice(R->device);
-  if (R->owns_seq && R->d_seq) cudaFree(R->d_seq);
-  if (R->d_offs) cudaFree(R->d_offs);
-  if (R->d_order) cudaFree(R->d_order);
+  if (R->owns_seq && R->d_seq) pfree(R->d_seq, 0);
+  pfree(R->d_offs, 0);
+  pfree(R->d_order, 0);
   delete R;
 }
 
@@ -1036,15 +1079,15 @@ static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const 
   } while (0)
   SCHECK(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
   SCHECK(cudaStreamCreateWithFlags(&src.copy_stream, cudaStreamNonBlocking));
-  SCHECK(cudaMalloc((void**)&R.d_seq, padded));
-  SCHECK(cudaMalloc((void**)&R.d_offs, (n_reads + 1) * 8));
-  SCHECK(cudaMalloc((void**)&src.d_ready, src.n_chunks * sizeof(unsigned int)));
+  SCHECK(pmalloc((void**)&R.d_seq, padded, comp));
+  SCHECK(pmalloc((void**)&R.d_offs, (n_reads + 1) * 8, comp));
+  SCHECK(pmalloc((void**)&src.d_ready, src.n_chunks * sizeof(unsigned int), comp));
   SCHECK(cudaHostAlloc((void**)&src.h_one, sizeof(unsigned int), cudaHostAllocDefault));
   *src.h_one = 1u;
   SCHECK(cudaMemsetAsync(src.d_ready, 0, src.n_chunks * sizeof(unsigned int), comp));
   SCHECK(cudaMemsetAsync(R.d_seq + R.total, 0, padded - R.total, comp));
   SCHECK(cudaMemcpyAsync(R.d_offs, rb.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, comp));
-  rc = make_order(&R, src.chunk_bytes, comp);
+  rc = make_order(&R, src.chunk_bytes, comp);  // synchronises comp: the allocations above are usable on copy_stream
   if (rc == SVB_OK) rc = run_search(d, &R, overlap, assemble, out, comp, &src);
   if (rc == SVB_OK) {
     SCHECK(cudaStreamSynchronize(src.copy_stream));
@@ -1054,8 +1097,11 @@ static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const 
 done:
 #undef SCHECK
   if (src.copy_stream) { cudaStreamSynchronize(src.copy_stream); cudaStreamDestroy(src.copy_stream); }
-  if (comp) { cudaStreamSynchronize(comp); cudaStreamDestroy(comp); }
-  cudaFree(R.d_seq); cudaFree(R.d_offs); cudaFree(R.d_order); cudaFree(src.d_ready);
+  if (comp) {
+    pfree(R.d_seq, comp); pfree(R.d_offs, comp); pfree(R.d_order, comp); pfree(src.d_ready, comp);
+    cudaStreamSynchronize(comp);
+    cudaStreamDestroy(comp);
+  }
   if (src.h_one) cudaFreeHost(src.h_one);
   return rc;
 }
