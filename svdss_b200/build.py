@@ -57,11 +57,11 @@ HOST_BIN = os.path.join(HERE, "SVDSS")
 
 def build_host(force=False):
     """C++14 shell (`SVDSS index | search`) over the C ABI; needs only g++ and zlib."""
-    srcs = [os.path.join(HERE, "host", f) for f in ("svdss_main.cpp", "io.hpp", "call.hpp")]
+    srcs = [os.path.join(HERE, "host", f) for f in ("svdss_main.cpp", "io.hpp", "call.hpp", "clusterer.hpp")]
     if (not force and os.path.exists(HOST_BIN)
             and all(os.path.getmtime(HOST_BIN) >= os.path.getmtime(s) for s in srcs + [LIB])):
         return HOST_BIN
-    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-o", HOST_BIN, srcs[0],
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-fopenmp", "-o", HOST_BIN, srcs[0],
                            "-L" + HERE, "-lsvdss_b200", "-lz", "-Wl,-rpath,$ORIGIN"])
     return HOST_BIN
 

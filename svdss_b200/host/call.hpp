@@ -1,14 +1,16 @@
-// `SVDSS call` compute core on the GPU: Caller::pcall (reference caller.cpp:311-406) --
-// split_cluster -> run_poa -> ksw_extd2_sse -> CIGAR walk -> SV records -> VCF -- with run_poa and
-// ksw2 batched over all sub-clusters through svb_poa_batch / svb_ksw_extd2_batch.
+// `SVDSS call` on the GPU: Caller::run (reference caller.cpp:3-60) -- parse the .sfs file, Clusterer
+// (clusterer.hpp), then Caller::pcall (caller.cpp:311-406): split_cluster -> run_poa ->
+// ksw_extd2_sse -> CIGAR walk -> SV records, with run_poa and ksw2 batched over all sub-clusters
+// through svb_poa_batch / svb_ksw_extd2_batch; then clean_dups, filter_sv_chains, VCF (+ SAM of
+// the consensus alignments with --poa).
 //
-// The reference builds its clusters with Clusterer (clusterer.cpp: BAM + .sfs -> clusters), which
-// is host glue outside this round's scope; this shell therefore takes the clusters
-// from the file the reference itself writes with `--clusters` (clusterer.cpp:613-626):
+// Clusters come either from --bam + --sfs (the reference's own inputs) or from a file in the
+// format the reference writes with `--clusters` (clusterer.cpp:613-626):
 //     chrom:s+1-e+1 <TAB> n { <TAB> name:seq }
-// Sub-read haplotype tags are not part of that file, so every sub-read has htag 0 and
-// split_cluster takes its "no alignment is tagged, use length" branch (caller.cpp:130-150).
-// clean_dups / filter_sv_chains (rapidfuzz, caller.cpp:409-475) are not applied.
+// That file carries no haplotype tags or coverage vectors, so with --clusters-in every sub-read
+// has htag 0, cov = cov0 = n and RVEC is empty.
+// Not carried over: --clipped (Clipper) and the reference's reuse of the OpenMP loop
+// variable `i` inside pcall's encode loops (caller.cpp:339-342), which is undefined behaviour.
 #pragma once
 #include <algorithm>
 #include <map>
@@ -17,23 +19,10 @@
 #include <vector>
 
 #include "../../include/svdss_b200.h"
+#include "clusterer.hpp"
 #include "io.hpp"
 
 namespace svdss {
-
-struct SubRead { std::string name, seq; int htag; size_t size() const { return seq.size(); } };  // clusterer.hpp:24-36
-
-struct Cluster {  // clusterer.hpp:38-139 (fields kept)
-  std::string chrom;
-  int s = 0, e = 0, cov = 0, cov0 = 0, cov1 = 0, cov2 = 0;
-  std::vector<SubRead> subreads;
-  size_t size() const { return subreads.size(); }
-  int get_len() const {  // integer mean, clusterer.hpp:103-111
-    unsigned l = 0, n = 0;
-    for (const auto& sr : subreads) { ++n; l += (unsigned)sr.size(); }
-    return (int)(l / n);
-  }
-};
 
 struct SV {  // sv.hpp:12-62, sv.cpp:7-27
   std::string type, chrom, idx, refall, altall, gt = "./.", cigar, reads, rvec;
@@ -94,27 +83,115 @@ inline std::vector<Cluster> split_cluster_by_len(const Cluster& cluster, float m
   return sub;
 }
 
-// caller.cpp:100-150, untagged branch: the two largest length groups
-inline std::vector<Cluster> split_cluster(const Cluster& cluster, float min_ratio) {
-  Cluster c0 = cluster;
-  c0.cov1 = -1; c0.cov2 = -1;
-  std::vector<Cluster> sub = split_cluster_by_len(c0, min_ratio), out;
-  int i1 = -1, i2 = -1;
-  unsigned v1 = 0, v2 = 0;
-  for (unsigned i = 0; i < sub.size(); ++i) {
-    if (sub[i].size() > v1) { v2 = v1; i2 = i1; v1 = (unsigned)sub[i].size(); i1 = (int)i; }
-    else if (sub[i].size() > v2) { v2 = (unsigned)sub[i].size(); i2 = (int)i; }
+static inline Cluster shell_of(const Cluster& c, int cov, int cov0, int cov1, int cov2) {  // Cluster(chrom,s,e,cov..)
+  Cluster o;
+  o.chrom = c.chrom; o.s = c.s; o.e = c.e; o.cov = cov; o.cov0 = cov0; o.cov1 = cov1; o.cov2 = cov2;
+  return o;
+}
+
+static inline int largest(const std::vector<Cluster>& v) {
+  unsigned v_max = 0; int i_max = -1;
+  for (unsigned i = 0; i < v.size(); ++i) if (v[i].size() > v_max) { v_max = (unsigned)v[i].size(); i_max = (int)i; }
+  return i_max;
+}
+
+// caller.cpp:100-255: by haplotype tag first (unless --noht), by length inside each haplotype;
+// at most two sub-clusters come back
+inline std::vector<Cluster> split_cluster(const Cluster& cluster, float min_ratio, bool useht) {
+  Cluster c0 = shell_of(cluster, cluster.cov, cluster.cov0, cluster.cov1, cluster.cov2), c1 = c0, c2 = c0;
+  for (const SubRead& sr : cluster.subreads) {
+    if (useht && sr.htag == 1) c1.subreads.push_back(sr);
+    else if (useht && sr.htag == 2) c2.subreads.push_back(sr);
+    else c0.subreads.push_back(sr);
   }
-  if (i1 != -1) out.push_back(sub[i1]);
-  if (i2 != -1) out.push_back(sub[i2]);
+  c0.cov1 = -1; c0.cov2 = -1; c1.cov0 = -1; c1.cov2 = -1; c2.cov0 = -1; c2.cov1 = -1;
+  std::vector<Cluster> out;
+  if (c1.size() == 0 && c2.size() == 0) {   // no alignment is tagged, use length: the two largest groups
+    std::vector<Cluster> sub = split_cluster_by_len(c0, min_ratio);
+    int i1 = -1, i2 = -1;
+    unsigned v1 = 0, v2 = 0;
+    for (unsigned i = 0; i < sub.size(); ++i) {
+      if (sub[i].size() > v1) { v2 = v1; i2 = i1; v1 = (unsigned)sub[i].size(); i1 = (int)i; }
+      else if (sub[i].size() > v2) { v2 = (unsigned)sub[i].size(); i2 = (int)i; }
+    }
+    if (i1 != -1) out.push_back(sub[i1]);
+    if (i2 != -1) out.push_back(sub[i2]);
+    return out;
+  }
+  const int both = (c1.size() > 0 ? 1 : 0) + (c2.size() > 0 ? 2 : 0);
+  std::vector<Cluster> sub1 = split_cluster_by_len(c1, min_ratio), sub2 = split_cluster_by_len(c2, min_ratio);
+  Cluster fresh = shell_of(cluster, cluster.cov, cluster.cov0, -1, -1);
+  for (const SubRead& sr : c0.subreads) {
+    const float sl = (float)sr.size();
+    // best_ratio_* are declared int in the reference (caller.cpp:162,172): the ratio truncates
+    // to 0 (or 1 for equal lengths) when stored, so `r > best_ratio` compares against that
+    int best_1 = -1, best_ratio_1 = -1, best_2 = -1, best_ratio_2 = -1;
+    for (unsigned i = 0; i < sub1.size(); i++) {
+      const float cl = (float)sub1[i].get_len(), r = std::min(cl, sl) / std::max(cl, sl);
+      if (r >= min_ratio && r > (float)best_ratio_1) { best_1 = (int)i; best_ratio_1 = (int)r; }
+    }
+    for (unsigned i = 0; i < sub2.size(); i++) {
+      const float cl = (float)sub2[i].get_len(), r = std::min(cl, sl) / std::max(cl, sl);
+      if (r >= min_ratio && r > (float)best_ratio_2) { best_2 = (int)i; best_ratio_2 = (int)r; }
+    }
+    if (both == 1) {
+      if (best_1 == -1) fresh.subreads.push_back(sr);
+      else { sub1[best_1].subreads.push_back(sr); ++sub1[best_1].cov1; --fresh.cov0; }
+    } else if (both == 2) {
+      if (best_2 == -1) fresh.subreads.push_back(sr);
+      else { sub2[best_2].subreads.push_back(sr); ++sub2[best_2].cov2; --fresh.cov0; }
+    } else {
+      if (best_1 != -1 && best_ratio_1 > best_ratio_2) { sub1[best_1].subreads.push_back(sr); ++sub1[best_1].cov1; --fresh.cov0; }
+      else if (best_2 != -1 && best_ratio_2 > best_ratio_1) { sub2[best_2].subreads.push_back(sr); ++sub2[best_2].cov2; --fresh.cov0; }
+    }
+  }
+  int i_max = largest(sub1);
+  if (i_max != -1) out.push_back(sub1[i_max]);
+  i_max = largest(sub2);
+  if (i_max != -1) out.push_back(sub2[i_max]);
+  if (both != 3) {
+    std::vector<Cluster> subn = split_cluster_by_len(fresh, min_ratio);
+    i_max = largest(subn);
+    if (i_max != -1) {
+      if (both == 1) subn[i_max].cov1 = -1; else subn[i_max].cov2 = -1;
+      out.push_back(subn[i_max]);
+    }
+  }
   return out;
 }
 
+// rapidfuzz::fuzz::ratio (caller.cpp:455-458): normalised Indel similarity in percent,
+// 100 * 2*LCS / (|a|+|b|); LCS by the bit-parallel recurrence S' = (S + (S & M)) | (S & ~M)
+inline double fuzz_ratio(const std::string& a, const std::string& b) {
+  const size_t n = a.size(), m = b.size();
+  if (n + m == 0) return 100.0;
+  if (n == 0 || m == 0) return 0.0;
+  const size_t W = (n + 63) / 64;
+  std::vector<uint64_t> pm(256 * W, 0), S(W, ~0ULL);
+  for (size_t i = 0; i < n; ++i) pm[(size_t)(uint8_t)a[i] * W + (i >> 6)] |= 1ULL << (i & 63);
+  for (size_t j = 0; j < m; ++j) {
+    const uint64_t* M = &pm[(size_t)(uint8_t)b[j] * W];
+    unsigned carry = 0;
+    for (size_t w = 0; w < W; ++w) {
+      const uint64_t u = S[w] & M[w];
+      const uint64_t t = S[w] + u;
+      const uint64_t sum = t + carry;
+      carry = (t < S[w]) || (sum < t);
+      S[w] = sum | (S[w] & ~M[w]);
+    }
+  }
+  size_t lcs = 0;
+  for (size_t i = 0; i < n; ++i) lcs += !((S[i >> 6] >> (i & 63)) & 1);
+  return 100.0 * 2.0 * (double)lcs / (double)(n + m);
+}
+
 struct CallConfig {
-  std::string reference, clusters_in, poa_out;
-  unsigned min_cluster_weight = 2, min_sv_length = 25;
+  std::string reference, clusters_in, poa_out, bam, sfs, clusters_out;
+  unsigned min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
   float min_ratio = 0.97f;
-  int device = 0;
+  int device = 0, threads = 4, batch_size = 10000;
+  bool useht = true;
+  bool cluster_only = false;   // stop after the Clusterer (writes --clusters); no GPU needed
 };
 
 inline void print_vcf_header(const std::vector<std::string>& chroms, const std::unordered_map<std::string, std::string>& seqs) {
@@ -158,39 +235,69 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
       seqs[r.name] = r.seq;
     }
   }
-  // clusters (clusterer.cpp:613-626 format)
   std::vector<Cluster> clusters;
-  {
-    GzSource src(c.clusters_in);
-    if (!src.ok()) { log("critical", "cannot open clusters file " + c.clusters_in); return 1; }
-    std::string line;
-    while (src.getline(line)) {
-      if (line.empty()) continue;
-      std::vector<std::string> tok;
-      size_t b = 0;
-      while (true) { size_t t = line.find('\t', b); tok.push_back(line.substr(b, t == std::string::npos ? t : t - b)); if (t == std::string::npos) break; b = t + 1; }
-      size_t colon = tok[0].rfind(':'), dash = tok[0].rfind('-');
-      if (tok.size() < 2 || colon == std::string::npos || dash == std::string::npos || dash < colon) { log("critical", "malformed cluster line"); return 1; }
-      Cluster cl;
-      cl.chrom = tok[0].substr(0, colon);
-      cl.s = atoi(tok[0].substr(colon + 1, dash - colon - 1).c_str()) - 1;
-      cl.e = atoi(tok[0].substr(dash + 1).c_str()) - 1;
-      for (size_t i = 2; i < tok.size(); ++i) {
-        size_t k = tok[i].rfind(':');
-        if (k == std::string::npos) { log("critical", "malformed sub-read in cluster line"); return 1; }
-        cl.subreads.push_back(SubRead{tok[i].substr(0, k), tok[i].substr(k + 1), 0});
+  if (c.clusters_in.empty()) {
+    // Caller::run, caller.cpp:9-13
+    std::unordered_map<std::string, std::vector<SFS>> sfss;
+    size_t total = 0;
+    log("info", "Loading SFSs from " + c.sfs + "..");
+    if (!parse_sfsfile(c.sfs, sfss, total)) { log("critical", "cannot open " + c.sfs); return 1; }
+    log("info", "Loaded " + std::to_string(total) + " SFSs from " + std::to_string(sfss.size()) + " reads.");
+    ClusterConfig cc;
+    cc.bam = c.bam; cc.clusters_out = c.clusters_out; cc.threads = c.threads; cc.batch_size = c.batch_size;
+    cc.min_mapq = c.min_mapq; cc.min_cluster_weight = c.min_cluster_weight;
+    Clusterer C(cc, &sfss, &seqs);
+    log("info", "Placing SFSs on reference genome");
+    if (!C.run()) { log("critical", C.error.empty() ? "cannot write " + c.clusters_out : C.error); return 1; }
+    log("info", std::to_string(C.unplaced) + "/" + std::to_string(C.s_unplaced) + "/" + std::to_string(C.e_unplaced) +
+                    " unplaced SFSs. " + std::to_string(C.unknown) + " erroneus SFSs. 0 clipped SFSs.");
+    log("info", "Clustered " + std::to_string(C.n_extended) + " SFSs. Maximum extended SFS length: " + std::to_string(C.max_ext_len) +
+                    "bp. Using separation distance: " + std::to_string(C.dist) + "bp.");
+    log("info", "Filtered " + std::to_string(C.unextended) + " SFSs. Filtered " + std::to_string(C.small_clusters) +
+                    " clusters. Filtered " + std::to_string(C.small_clusters_2) + " global clusters.");
+    clusters.swap(C.clusters);
+    if (c.cluster_only) return 0;
+  } else {
+    // clusters (clusterer.cpp:613-626 format)
+    {
+      GzSource src(c.clusters_in);
+      if (!src.ok()) { log("critical", "cannot open clusters file " + c.clusters_in); return 1; }
+      std::string line;
+      while (src.getline(line)) {
+        if (line.empty()) continue;
+        std::vector<std::string> tok;
+        size_t b = 0;
+        while (true) { size_t t = line.find('\t', b); tok.push_back(line.substr(b, t == std::string::npos ? t : t - b)); if (t == std::string::npos) break; b = t + 1; }
+        size_t colon = tok[0].rfind(':'), dash = tok[0].rfind('-');
+        if (tok.size() < 2 || colon == std::string::npos || dash == std::string::npos || dash < colon) { log("critical", "malformed cluster line"); return 1; }
+        Cluster cl;
+        cl.chrom = tok[0].substr(0, colon);
+        cl.s = atoi(tok[0].substr(colon + 1, dash - colon - 1).c_str()) - 1;
+        cl.e = atoi(tok[0].substr(dash + 1).c_str()) - 1;
+        for (size_t i = 2; i < tok.size(); ++i) {
+          size_t k = tok[i].rfind(':');
+          if (k == std::string::npos) { log("critical", "malformed sub-read in cluster line"); return 1; }
+          cl.subreads.push_back(SubRead{tok[i].substr(0, k), tok[i].substr(k + 1), 0});
+        }
+        cl.cov = cl.cov0 = (int)cl.size(); cl.cov1 = cl.cov2 = 0;
+        if (!seqs.count(cl.chrom) || cl.s < 1 || cl.e < cl.s || (size_t)cl.e >= seqs[cl.chrom].size()) { log("critical", "cluster " + tok[0] + " is outside the reference"); return 1; }
+        clusters.push_back(cl);
       }
-      cl.cov = cl.cov0 = (int)cl.size(); cl.cov1 = cl.cov2 = 0;
-      if (!seqs.count(cl.chrom) || cl.s < 1 || cl.e < cl.s || (size_t)cl.e >= seqs[cl.chrom].size()) { log("critical", "cluster " + tok[0] + " is outside the reference"); return 1; }
-      clusters.push_back(cl);
     }
   }
   log("info", "Calling SVs from " + std::to_string(clusters.size()) + " clusters..");
   // pcall: collect sub-clusters (caller.cpp:311-330)
   std::vector<Cluster> jobs;
-  for (const Cluster& cl : clusters) {
+  std::vector<size_t> parent;   // index into clusters (thread slot = parent % threads, RVEC source)
+  for (size_t ci = 0; ci < clusters.size(); ++ci) {
+    const Cluster& cl = clusters[ci];
     if (cl.size() < c.min_cluster_weight) continue;   // :316
-    for (const Cluster& sc : split_cluster(cl, c.min_ratio)) jobs.push_back(sc);
+    const std::string& cs = seqs[cl.chrom];
+    if (cl.s < 1 || cl.e < cl.s || (size_t)cl.e >= cs.size()) {   // the reference would read outside the chromosome
+      log("warning", "cluster " + cl.chrom + ":" + std::to_string(cl.s + 1) + "-" + std::to_string(cl.e + 1) + " is outside the reference, skipped");
+      continue;
+    }
+    for (const Cluster& sc : split_cluster(cl, c.min_ratio, c.useht)) { jobs.push_back(sc); parent.push_back(ci); }
   }
   const uint8_t* t26 = char26_table();
   // run_poa for all jobs (caller.cpp:257-308)
@@ -219,9 +326,15 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     log("critical", std::string("svb_ksw_extd2_batch: ") + svb_last_error());
     return 1;
   }
-  std::vector<SV> svs;
-  std::vector<std::string> sam;
+  const size_t T = (size_t)std::max(1, c.threads);
+  std::vector<std::vector<SV>> p_svs(T);
+  std::vector<std::vector<std::string>> p_sam(T);
   for (size_t k = 0; k < jobs.size(); ++k) {
+    std::vector<SV>& svs = p_svs[parent[k] % T];            // schedule(static, 1), caller.cpp:312-314
+    std::vector<std::string>& sam = p_sam[parent[k] % T];
+    std::string rvec;                                        // SV::set_rvec, sv.cpp:42-46
+    for (const auto& r : clusters[parent[k]].reads) rvec += std::to_string(r.first) + ":" + std::to_string(r.second) + "-";
+    if (!rvec.empty()) rvec.pop_back();
     const Cluster& cl = jobs[k];
     const std::string& chromseq = seqs[cl.chrom];
     const int score = ez.score[k];
@@ -258,11 +371,58 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     for (SV& sv : _svs) {  // :396-401
       sv.ngaps = nv; sv.gt = "0/1"; sv.gtq = 100;
       sv.cov = cl.cov; sv.cov0 = cl.cov0; sv.cov1 = cl.cov1; sv.cov2 = cl.cov2;
+      sv.rvec = rvec;
       svs.push_back(sv);
     }
   }
   svb_ksw_out_free(&ez);
-  std::stable_sort(svs.begin(), svs.end());   // caller.cpp:23,28 (clean_dups / filter_sv_chains not applied)
+  // caller.cpp:17-29: per-thread vectors are inserted at the front, then sort / clean_dups /
+  // filter_sv_chains / sort (stable here; the reference's std::sort leaves ties unspecified)
+  std::vector<SV> svs;
+  std::vector<std::string> sam;
+  for (size_t t = 0; t < T; ++t) {
+    svs.insert(svs.begin(), p_svs[t].begin(), p_svs[t].end());
+    sam.insert(sam.begin(), p_sam[t].begin(), p_sam[t].end());
+  }
+  std::stable_sort(svs.begin(), svs.end());
+  {  // clean_dups, caller.cpp:409-427
+    std::vector<SV> keep;
+    std::string last_chrom, last_refall, last_altall;
+    int last_pos = -1;
+    for (const SV& sv : svs) {
+      if (last_chrom != sv.chrom || last_pos != sv.s || last_refall != sv.refall || last_altall != sv.altall) keep.push_back(sv);
+      last_chrom = sv.chrom; last_pos = sv.s; last_refall = sv.refall; last_altall = sv.altall;
+    }
+    svs.swap(keep);
+  }
+  log("info", std::to_string(svs.size()) + " SVs before chain filtering.");
+  if (svs.size() >= 2) {  // filter_sv_chains, caller.cpp:430-475 (`prev` there aliases svs[0] and is assigned through)
+    std::vector<SV> keep;
+    SV prev = svs[0];
+    bool reset = false;
+    for (size_t i = 1; i < svs.size(); i++) {
+      if (reset) { reset = false; prev = svs[i]; continue; }
+      const SV& sv = svs[i];
+      if (sv.chrom == prev.chrom && sv.s - prev.e < 2 * sv.l && prev.type == sv.type) {
+        const double w_r = std::min((double)sv.w, (double)prev.w) / std::max((double)sv.w, (double)prev.w);
+        const double l_r = std::min((double)sv.l, (double)prev.l) / std::max((double)sv.l, (double)prev.l);
+        const int d = sv.s - prev.s;
+        if (d < 100 && w_r >= 0.9 && l_r >= c.min_ratio) {
+          const double sim = sv.type == "DEL" ? fuzz_ratio(sv.refall, prev.refall) : fuzz_ratio(sv.altall, prev.altall);
+          if (sim > 70) {
+            keep.push_back(sv.w > prev.w ? sv : prev);
+            reset = true;
+            continue;
+          }
+        }
+      }
+      keep.push_back(prev);
+      prev = sv;
+    }
+    keep.push_back(prev);
+    svs.swap(keep);
+    std::stable_sort(svs.begin(), svs.end());
+  }
   log("info", "Writing " + std::to_string(svs.size()) + " SVs.");
   print_vcf_header(chroms, seqs);
   for (const SV& sv : svs) { std::string l = sv.vcf_line() + "\n"; fwrite(l.data(), 1, l.size(), stdout); }

@@ -98,9 +98,20 @@ struct BamRecord {
   uint8_t mapq = 0;
   std::string qname;
   std::vector<uint8_t> nt6;   // decoded sequence, nt6 codes (ping_pong.cpp:90-94)
+  std::vector<uint32_t> cigar; // len<<4 | op (MIDNSHP=X), as stored
+  std::vector<uint8_t> seq4;   // 4-bit packed sequence, as stored (Clusterer decodes it on demand)
   bool has_xf = false, has_hp = false;
   int64_t xf = 0, hp = 0;
+  // bam_endpos: pos + reference span of the CIGAR (M,D,N,=,X); pos+1 for an empty span
+  int32_t endpos() const {
+    int64_t span = 0;
+    for (uint32_t c : cigar) { const uint32_t op = c & 0xf; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4; }
+    return (int32_t)(pos + (span ? span : 1));
+  }
 };
+
+// htslib seq_nt16_str: ASCII of one 4-bit code
+inline char nt16_char(unsigned c) { return "=ACMGRSVTWYHKDBN"[c & 15]; }
 
 class BamReader {
  public:
@@ -125,6 +136,8 @@ class BamReader {
   }
   bool ok() const { return ok_; }
   const std::vector<std::string>& ref_names() const { return ref_names_; }
+  // alignment mode (`call`): keep CIGAR + packed sequence instead of decoding nt6 codes
+  void want_alignment(bool on) { want_align_ = on; }
   // 1 = record, 0 = clean EOF, -1 = truncated/corrupt
   int next(BamRecord& r) {
     int32_t bs = 0;
@@ -144,15 +157,22 @@ class BamReader {
     size_t o = 32;
     if (o + l_read_name > (size_t)bs) return -1;
     r.qname.assign((const char*)p + o, l_read_name ? l_read_name - 1 : 0);
-    o += l_read_name + (size_t)n_cigar * 4;
+    o += l_read_name;
+    if (o + (size_t)n_cigar * 4 > (size_t)bs) return -1;
+    if (want_align_) { r.cigar.resize(n_cigar); if (n_cigar) memcpy(r.cigar.data(), p + o, (size_t)n_cigar * 4); }
+    o += (size_t)n_cigar * 4;
     const size_t seq_bytes = ((size_t)r.l_qseq + 1) / 2;
     if (r.l_qseq < 0 || o + seq_bytes + (size_t)r.l_qseq > (size_t)bs) return -1;
     static const char nt16[] = "=ACMGRSVTWYHKDBN";  // htslib seq_nt16_str
     const uint8_t* t6 = nt6_table();
-    r.nt6.resize((size_t)r.l_qseq);
-    for (int32_t i = 0; i < r.l_qseq; ++i) {
-      const uint8_t b = p[o + (i >> 1)];
-      r.nt6[i] = t6[(int)nt16[(i & 1) ? (b & 0xf) : (b >> 4)]];
+    if (want_align_) {
+      r.seq4.assign(p + o, p + o + seq_bytes);
+    } else {
+      r.nt6.resize((size_t)r.l_qseq);
+      for (int32_t i = 0; i < r.l_qseq; ++i) {
+        const uint8_t b = p[o + (i >> 1)];
+        r.nt6[i] = t6[(int)nt16[(i & 1) ? (b & 0xf) : (b >> 4)]];
+      }
     }
     o += seq_bytes + (size_t)r.l_qseq;
     r.has_xf = r.has_hp = false; r.xf = r.hp = 0;
@@ -189,7 +209,7 @@ class BamReader {
   }
  private:
   GzSource src_;
-  bool ok_ = false;
+  bool ok_ = false, want_align_ = false;
   std::string text_;
   std::vector<std::string> ref_names_;
   std::vector<int32_t> ref_lens_;

@@ -36,19 +36,20 @@ static const char* MAIN_USAGE =
     "  call    POA consensus + ksw2 realignment + SV extraction from SFS clusters";
 static const char* INDEX_USAGE = "Usage: SVDSS index [-t threads] [-d] [-o index] <reference.fa[.gz]>";
 static const char* CALL_USAGE =
-    "Usage: SVDSS call --reference <fa> (--clusters-in <clusters.txt> | --bam <bam> --sfs <sfs>) [--poa <out.sam>]\n"
-    "                  [--min-cluster-weight 2] [--min-sv-length 25] [-l 0.97]\n"
-    "  The POA + realignment core (Caller::pcall) runs on the GPU. Building clusters from --bam/--sfs\n"
-    "  (Clusterer) is not part of this build: pass the file written by the reference's `call --clusters`.";
+    "Usage: SVDSS call --reference <fa> (--bam <bam> --sfs <sfs> | --clusters-in <clusters.txt>) [--threads 4]\n"
+    "                  [--min-cluster-weight 2] [--min-sv-length 25] [--min-mapq 20] [-l 0.97] [--noht]\n"
+    "                  [--poa <out.sam>] [--clusters <out.txt>] [--cluster-only]\n"
+    "  Clusters are built on the host from --bam/--sfs (Clusterer) or read back from a `--clusters` file;\n"
+    "  POA consensus + realignment (Caller::pcall) run on the GPU. --cluster-only stops after --clusters.";
 static const char* SEARCH_USAGE =
     "Usage: SVDSS search --index <index> (--bam <bam> | --fastx <fastx>) [--threads 4] [--bsize 10000]\n"
     "                    [--noputative] [--noassemble] [--verbose]";
 
 struct Config {
-  string index, bam, fastx, out, reference, sfs, clusters_in, poa;
+  string index, bam, fastx, out, reference, sfs, clusters_in, clusters_out, poa;
   int min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
   float min_ratio = 0.97f;
-  bool noht = false, clipped = false;
+  bool noht = false, clipped = false, cluster_only = false;
   int threads = 4, bsize = 10000, omax = 100000, device = 0;
   bool assemble = true, putative = true, verbose = false, help = false, version = false;
   int overlap = -1;  // config.hpp:82: never settable from the command line
@@ -72,6 +73,8 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
     else if (a == "--reference") ok = val(c.reference);
     else if (a == "--sfs") ok = val(c.sfs);
     else if (a == "--clusters-in") ok = val(c.clusters_in);
+    else if (a == "--clusters") ok = val(c.clusters_out);
+    else if (a == "--cluster-only") c.cluster_only = true;
     else if (a == "--poa") ok = val(c.poa);
     else if (a == "--min-cluster-weight") ok = ival(c.min_cluster_weight);
     else if (a == "--min-sv-length") { ok = ival(c.min_sv_length); c.min_sv_length = max(25, c.min_sv_length); }  // config.cpp:87
@@ -257,18 +260,22 @@ int main(int argc, char** argv) {
   if (c.version) { cout << "SVDSS, " << VERSION << endl; exit(EXIT_SUCCESS); }
   if (c.help) { cerr << (mode == "index" ? INDEX_USAGE : mode == "search" ? SEARCH_USAGE : mode == "call" ? CALL_USAGE : MAIN_USAGE) << endl; exit(EXIT_SUCCESS); }
   int rc;
+  if (mode == "_ratio") {   // test hook: fuzz_ratio of filter_sv_chains (tests/test_cluster_cpu.py)
+    if (pos.size() != 2) exit(EXIT_FAILURE);
+    printf("%.6f\n", fuzz_ratio(pos[0], pos[1]));
+    return 0;
+  }
   if (mode == "index") rc = run_index(c, pos);
   else if (mode == "search") rc = run_search(c);
   else if (mode == "call") {
     if (c.reference.empty() || (c.clusters_in.empty() && (c.bam.empty() || c.sfs.empty()))) { cerr << CALL_USAGE << endl; exit(EXIT_FAILURE); }  // main.cpp:56-59
-    if (c.clusters_in.empty()) {
-      logmsg("critical", "clustering SFSs from --bam/--sfs (Clusterer) is not built yet; pass --clusters-in (see --help)");
-      exit(EXIT_FAILURE);
-    }
+    if (c.clipped) logmsg("warning", "--clipped (imprecise SVs from clipped alignments) is not part of this build; ignored");
     CallConfig cc;
     cc.reference = c.reference; cc.clusters_in = c.clusters_in; cc.poa_out = c.poa;
     cc.min_cluster_weight = (unsigned)c.min_cluster_weight; cc.min_sv_length = (unsigned)c.min_sv_length;
     cc.min_ratio = c.min_ratio; cc.device = c.device;
+    cc.bam = c.bam; cc.sfs = c.sfs; cc.clusters_out = c.clusters_out; cc.min_mapq = (unsigned)c.min_mapq;
+    cc.threads = c.threads; cc.batch_size = c.bsize; cc.useht = !c.noht; cc.cluster_only = c.cluster_only;
     rc = run_call(cc, [](const char* l, const string& m) { logmsg(l, m); });
   }
   else { cerr << MAIN_USAGE << endl; exit(EXIT_FAILURE); }

@@ -237,3 +237,84 @@ def materialize_segments_torch(ref_cat_t, segs, out_t=None, chunk_segs=200_000):
         rb = (((h >> 33) & 3) + 1).to(torch.uint8)
         out[o0:o1] = torch.where(is_ref, b, rb)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# SV-carrying sample (config 3 shape): a diploid sample = reference + planted INS/DEL catalogue,
+# reads drawn from the two haplotypes with their true alignment (pos + CIGAR) to the reference, as
+# a smoothed BAM would hold them (forward-strand sequence, M blocks identical to the reference).
+# ---------------------------------------------------------------------------------------------
+def make_sv_catalogue(contigs, n_svs, seed=5, min_len=50, max_len=5000, margin=2000, spacing=3000):
+    """Planted het/hom INS/DEL: list of dicts (contig, pos, type, len, seq, gt) sorted by (contig, pos).
+    `pos` is the 0-based reference base AFTER which the event happens (VCF-style anchor = pos)."""
+    rng = np.random.default_rng(seed)
+    lens = np.array([len(c) for c in contigs], np.int64)
+    out, taken = [], [[] for _ in contigs]
+    tries = 0
+    while len(out) < n_svs and tries < 100 * n_svs:
+        tries += 1
+        ci = int(rng.choice(len(contigs), p=lens / lens.sum()))
+        ln = int(np.exp(rng.uniform(np.log(min_len), np.log(max_len))))
+        if lens[ci] < 2 * margin + ln + 10:
+            continue
+        pos = int(rng.integers(margin, lens[ci] - margin - ln))
+        if any(abs(pos - p) < spacing + ln + l2 for p, l2 in taken[ci]):
+            continue
+        typ = "INS" if rng.random() < 0.5 else "DEL"
+        if typ == "DEL" and (contigs[ci][pos:pos + ln + 2] == 5).any():
+            continue
+        seq = rng.integers(1, 5, size=ln, dtype=np.uint8) if typ == "INS" else None
+        gt = (1, 1) if rng.random() < 0.4 else ((1, 0) if rng.random() < 0.5 else (0, 1))
+        taken[ci].append((pos, ln))
+        out.append(dict(contig=ci, pos=pos, type=typ, len=ln, seq=seq, gt=gt))
+    out.sort(key=lambda s: (s["contig"], s["pos"]))
+    return out
+
+
+def make_sample_alignments(contigs, catalogue, coverage=10, seed=6, mean_len=15000, sd_len=2000, min_len=1000,
+                           max_len=25000, tag_hp=True, names=None, clip_rate=0.1):
+    """Reads of a diploid sample with true alignments. Returns a list of dicts: qname, tid, pos, cigar
+    [(len, op)], seq (nt6 array, forward strand), hp (1/2), has_event (bool -> XF:i:0 else XF:i:2).
+    Sorted by (tid, pos) like a coordinate-sorted BAM."""
+    rng = np.random.default_rng(seed)
+    recs = []
+    rid = 0
+    for ci, c in enumerate(contigs):
+        n_reads = max(1, int(len(c) * coverage / mean_len))
+        for hap in (0, 1):
+            evs = [s for s in catalogue if s["contig"] == ci and s["gt"][hap]]
+            for _ in range((n_reads + (1 - hap)) // 2):
+                L = int(np.clip(rng.normal(mean_len, sd_len), min_len, max_len))
+                L = min(L, len(c))
+                a = int(rng.integers(0, len(c) - L + 1))
+                b = a + L
+                pieces, cigar, ref = [], [], a
+                has_event = False
+                for s in evs:
+                    p = s["pos"]
+                    # the event must sit well inside the read: both flanks >= 150 reference bases
+                    lo = p + 1
+                    hi = p + 1 + (s["len"] if s["type"] == "DEL" else 0)
+                    if lo - a < 150 or b - hi < 150 or lo < ref:
+                        continue
+                    pieces.append(c[ref:lo]); cigar.append((lo - ref, "M"))
+                    if s["type"] == "INS":
+                        pieces.append(s["seq"]); cigar.append((s["len"], "I"))
+                    else:
+                        cigar.append((s["len"], "D"))
+                    ref = hi
+                    has_event = True
+                pieces.append(c[ref:b]); cigar.append((b - ref, "M"))
+                if rng.random() < clip_rate:      # soft-clipped random tail (either end)
+                    t = rng.integers(1, 5, size=int(rng.integers(100, 2001)), dtype=np.uint8)
+                    if rng.random() < 0.5:
+                        pieces.append(t); cigar.append((len(t), "S"))
+                    else:
+                        pieces.insert(0, t); cigar.insert(0, (len(t), "S"))
+                    has_event = True
+                seq = np.ascontiguousarray(np.concatenate(pieces), np.uint8)
+                recs.append(dict(qname=(names[rid] if names else "read_%06d" % rid), tid=ci, pos=a, cigar=cigar, seq=seq,
+                                 hp=hap + 1 if tag_hp else 0, has_event=has_event))
+                rid += 1
+    recs.sort(key=lambda r: (r["tid"], r["pos"]))
+    return recs
