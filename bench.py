@@ -43,14 +43,15 @@ def contig_offsets(ref_bp, n_contigs):
     return np.concatenate([[0], cuts]).astype(np.int64)
 
 
-def ncu_traffic(n_reads, block_bytes):
-    """dram bytes per launch of the search kernel from the committed ncu --set full capture (same
-    workload: 1 M reads of config 2); None when the run does not match that capture."""
+def ncu_traffic(n_reads, block_bytes, key="k_sfs_search_tma"):
+    """dram bytes per launch of the search kernel from the committed ncu --set full capture of the
+    same workload (config 2 reads; the capture may hold fewer reads per launch than this run: the
+    per-read traffic is scaled, and the entry says so); None when the run does not match it."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f)["k_sfs_search_tma<6,1>"]
-        if t["reads_per_launch"] == n_reads and block_bytes == 128 and not os.environ.get("SVB_SEARCH_CFG"):
-            return t["dram_bytes"]
+            t = json.load(f)[key]
+        if block_bytes == 128 and not os.environ.get("SVB_SEARCH_CFG"):
+            return t["dram_bytes"] * (n_reads / t["reads_per_launch"])
     except Exception:
         pass
     return None
@@ -213,6 +214,7 @@ def run_ours(args):
     kernel_ms = float(np.mean([r.kernel_ms for r in res]))
     blocks = float(np.mean([r.n_blocks_touched for r in res]))
     n_ext = float(np.mean([r.n_ext for r in res]))
+    text_ext = float(np.mean([r.n_text_ext for r in res]))
     launches = int(sum(r.launches for r in res))
     n_sfs = res[-1].n_sfs
     # ---- e2e: host buffers through svb_sfs_batch
@@ -228,7 +230,30 @@ def run_ours(args):
     ms_step_e = ms_wall_e / args.steps
     assert res_e[-1].n_sfs == n_sfs, "resident and host paths disagree"
     peak, peak_src = hbm_peak()
-    achieved = blocks * idx.block_bytes / (kernel_ms * 1e-3) / 1e9
+    # algorithmic bytes of one launch: 128 B per distinct index block fetched + 2 B (read byte + text
+    # byte) per extension answered in located-match mode
+    alg_bytes = blocks * idx.block_bytes + 2.0 * text_ext
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    # the pure FMD rank walk (every extension = an Occ lookup, SURVEY 8d "FMD rank GB/s"): one extra
+    # untimed-region pass with the located-match mode switched off, same batch, same kernel
+    rank_walk = None
+    if text_ext > 0 and not args.no_rank_walk:
+        os.environ["SVB_SEARCH_TEXT"] = "0"
+        os.environ["SVB_SEARCH_JUMP"] = "0"
+        try:
+            idx.sfs_resident(dreads, assemble=assemble)
+            rr = [idx.sfs_resident(dreads, assemble=assemble) for _ in range(2)]
+        finally:
+            del os.environ["SVB_SEARCH_TEXT"]
+            del os.environ["SVB_SEARCH_JUMP"]
+        assert rr[-1].n_sfs == n_sfs and rr[-1].n_ext == res[-1].n_ext, "rank walk and located-match mode disagree"
+        rk_ms = float(np.mean([r.kernel_ms for r in rr]))
+        rk_bytes = float(np.mean([r.n_blocks_touched for r in rr])) * idx.block_bytes
+        rank_walk = {"bound": "hbm", "achieved": rk_bytes / (rk_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": rk_bytes / (rk_ms * 1e-3) / 1e9 / peak, "kernel_ms": rk_ms, "algorithmic_bytes": rk_bytes,
+                     "reads_per_s": n_reads / (rk_ms * 1e-3), "extensions_per_s": rr[-1].n_ext / (rk_ms * 1e-3),
+                     "traffic": ncu_traffic(n_reads, idx.block_bytes, "k_sfs_search_tma rank walk") if args.ref_bp == REF_BP else None,
+                     "kernel": "k_sfs_search_tma, SVB_SEARCH_TEXT=0 SVB_SEARCH_JUMP=0: every extension is an Occ lookup in a 128 B block"}
     out = {
         "metric": "SFS-extracted reads/sec (FMD ping-pong search)",
         "value": world * n_reads / (ms_step * 1e-3),
@@ -252,11 +277,13 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(n_reads, idx.block_bytes) if args.ref_bp == REF_BP else None,
                      "peak_source": peak_src,
-                     "kernel": ("k_sfs_search_tma<6,1> (thread-per-read, cp.async-staged 128 B blocks)" if idx.block_bytes == 128 and
-                                not os.environ.get("SVB_SEARCH_CFG") else "k_sfs_search cfg=%s" % os.environ.get("SVB_SEARCH_CFG", "4x1")),
+                     "kernel": ("k_sfs_search_tma (thread-per-read; cp.async-staged 128 B index blocks + located-match text compare)"
+                                if idx.block_bytes == 128 and not os.environ.get("SVB_SEARCH_CFG")
+                                else "k_sfs_search cfg=%s" % os.environ.get("SVB_SEARCH_CFG", "4x1")),
                      "kernel_ms": kernel_ms,
-                     "algorithmic_bytes": blocks * idx.block_bytes,
+                     "algorithmic_bytes": alg_bytes, "index_blocks": blocks, "text_extensions": text_ext,
                      "extensions_per_s": n_ext / (kernel_ms * 1e-3)},
+        "roofline_rank_walk": rank_walk,
         "clocks": clocks,
         "clocks_e2e": clocks_e,
     }
@@ -374,6 +401,7 @@ def main():
     ap.add_argument("--block-bytes", type=int, default=0)
     ap.add_argument("--noassemble", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rank-walk", action="store_true", help="skip the extra pure-rank-walk pass")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-sample", type=int, default=20000)
     args = ap.parse_args()

@@ -102,7 +102,7 @@ typedef struct {
   int32_t* qs;   /* SFS::qs  (sfs.hpp:36) */
   int32_t* len;  /* SFS::l   (sfs.hpp:38) */
   /* measurement (filled by every search call) */
-  int64_t n_ext;            /* backward extensions performed (= rb3_fmd_extend calls)           */
+  int64_t n_ext;            /* extensions performed (= rb3_fmd_extend calls of the reference)   */
   int64_t n_blocks_touched; /* sum over extensions of distinct index blocks read (1 or 2)       */
   float kernel_ms;          /* search kernel only, CUDA events on the launch stream             */
   float device_ms;          /* whole device pipeline of this call (H2D + kernels + D2H)         */
@@ -110,6 +110,8 @@ typedef struct {
   int64_t d2h_bytes;
   int32_t launches;         /* kernels launched by this call                                    */
   int32_t block_bytes;
+  int64_t n_text_ext;       /* of n_ext: extensions answered by comparing the read with the text
+                               (located-match mode, 2 bytes each) instead of an index block fetch */
 } svb_sfs_out_t;
 
 /* PingPong::process_batch (ping_pong.cpp:176-209) for a whole batch: runs

@@ -31,7 +31,7 @@ class SfsOut(C.Structure):
                 ("qs", C.POINTER(C.c_int32)), ("len", C.POINTER(C.c_int32)),
                 ("n_ext", C.c_int64), ("n_blocks_touched", C.c_int64), ("kernel_ms", C.c_float),
                 ("device_ms", C.c_float), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("launches", C.c_int32), ("block_bytes", C.c_int32)]
+                ("launches", C.c_int32), ("block_bytes", C.c_int32), ("n_text_ext", C.c_int64)]
 
 
 class KswOut(C.Structure):
@@ -132,6 +132,7 @@ class SfsResult:
         self.d2h_bytes = out.d2h_bytes
         self.launches = out.launches
         self.block_bytes = out.block_bytes
+        self.n_text_ext = out.n_text_ext
 
     def per_read(self, r):
         a, b = int(self.offs[r]), int(self.offs[r + 1])

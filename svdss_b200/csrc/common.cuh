@@ -53,7 +53,34 @@ struct IndexDev {
   int64_t* d_sbase = nullptr;
   int n_sb = 0;
   int64_t n_contigs = 0;
+  // Located-match acceleration (built by svb_index_build / restored by svb_index_load; absent for
+  // svb_index_from_bwt): once a search interval has size 1 and sits on a sampled SA row, the match
+  // is a single text position and every further extension is a byte compare against the text.
+  //   d_text   T itself, one byte per symbol, sentinels remapped to TEXT_SENTINEL (matches no read
+  //            code), TEXT_PAD pad bytes of the same value on both sides
+  //   d_ssa    SA[k] for every k with k % (1 << ss_log) == 0
+  //   d_tstart text start of contig pair r (S_r $ rc(S_r) $), n_contigs + 1 entries: the mirror of
+  //            text position x inside pair r is tstart[r] + tstart[r+1] - 2 - x
+  uint8_t* d_text_alloc = nullptr;
+  uint8_t* d_text = nullptr;
+  uint64_t* d_ssa = nullptr;
+  int64_t n_ssa = 0;
+  int ss_log = 4;
+  int64_t* d_tstart = nullptr;
+  // K-mer jump table (128-byte blocks only; rebuilt from the block array at build / load time):
+  // kmt[code] = interval of the K-mer whose i-th base (text order) sits in bits 2i..2i+1 (A=0..T=3),
+  // packed as start | min(size, KMT_SAT) << 40.  A restart of the ping-pong walk replaces its first
+  // K-1 extensions (all of which succeed when the K-mer occurs) by one 8-byte lookup.
+  uint64_t* d_kmt = nullptr;
+  int kmer_k = 0;
 };
+constexpr uint64_t KMT_SAT = (1ull << 24) - 1;
+
+// sfs_search.cu: fills d_kmt / kmer_k from the block array (no-op for 64-byte blocks)
+int build_kmer_table(IndexDev* idx);
+
+constexpr uint8_t TEXT_SENTINEL = 0xF0;
+constexpr int TEXT_PAD = 64;
 
 }  // namespace svb
 

@@ -636,6 +636,58 @@ int build_blocks(IndexDev* idx, const uint8_t* d_bwt, const uint64_t* d_SA, cons
   return SVB_OK;
 }
 
+// ---- located-match tables (IndexDev::d_text / d_ssa / d_tstart)
+__global__ void k_text_device(const uint8_t* __restrict__ T, int64_t n, uint8_t* __restrict__ out /* n + 2*TEXT_PAD */) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tot = n + 2 * TEXT_PAD;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) {
+    const int64_t j = i - TEXT_PAD;
+    uint8_t v = TEXT_SENTINEL;
+    if (j >= 0 && j < n) { v = T[j]; if (v == 0) v = TEXT_SENTINEL; }
+    out[i] = v;
+  }
+}
+__global__ void k_sample_sa(const uint64_t* __restrict__ SA, int64_t n_ssa, int ss_log, uint64_t* __restrict__ ssa) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ssa; i += stride) ssa[i] = SA[i << ss_log];
+}
+// forward strands of all contigs, two nt6 codes per byte (low nibble first): the on-disk form of T
+__global__ void k_pack_fwd(const uint8_t* __restrict__ text /* d_text */, const int64_t* __restrict__ tstart, int64_t m,
+                           int64_t tot, uint8_t* __restrict__ packed) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, nb = (tot + 1) / 2;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += stride) {
+    uint8_t v = 0;
+    for (int h = 0; h < 2; ++h) {
+      const int64_t i = 2 * b + h;
+      if (i >= tot) break;
+      // contig r holds forward bases [ (tstart[r]-2r)/2, (tstart[r+1]-2(r+1))/2 )
+      int64_t lo = 0, hi = m - 1;
+      while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if ((tstart[mid] - 2 * mid) / 2 <= i) lo = mid; else hi = mid - 1; }
+      const uint8_t c = text[tstart[lo] + (i - (tstart[lo] - 2 * lo) / 2)];
+      v |= (uint8_t)((c & 15) << (4 * h));
+    }
+    packed[b] = v;
+  }
+}
+__global__ void k_unpack_fwd(const uint8_t* __restrict__ packed, int64_t tot, uint8_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) out[i] = (packed[i >> 1] >> (4 * (i & 1))) & 15;
+}
+
+// keeps T (device, n bytes) as IndexDev::d_text and uploads the contig-pair starts
+static int attach_text(IndexDev* idx, const uint8_t* d_T, const std::vector<int64_t>& offs0 /* m+1, offs0[0] == 0 */) {
+  const int64_t n = idx->n, m = (int64_t)offs0.size() - 1;
+  SVB_CUDA(cudaMalloc((void**)&idx->d_text_alloc, (size_t)n + 2 * TEXT_PAD));
+  idx->d_text = idx->d_text_alloc + TEXT_PAD;
+  k_text_device<<<grid_for(n + 2 * TEXT_PAD, 256, 8), 256>>>(d_T, n, idx->d_text_alloc);
+  SVB_CUDA(cudaGetLastError());
+  std::vector<int64_t> ts((size_t)m + 1);
+  for (int64_t r = 0; r <= m; ++r) ts[r] = 2 * offs0[r] + 2 * r;
+  SVB_CUDA(cudaMalloc((void**)&idx->d_tstart, (size_t)(m + 1) * 8));
+  SVB_CUDA(cudaMemcpy(idx->d_tstart, ts.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice));
+  SVB_CUDA(cudaDeviceSynchronize());
+  return SVB_OK;
+}
+
 template <int G>
 __global__ void k_decode_bwt(const uint4* __restrict__ blocks, int64_t n, uint8_t* __restrict__ out) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -728,6 +780,7 @@ int svb_index_build(const uint8_t* contigs, const int64_t* offs, int64_t m, int 
   for (int64_t i = 0; i < m; ++i)
     if (hoffs[i + 1] < hoffs[i]) { set_error("contig offsets must be non-decreasing"); return SVB_EINVAL; }
   int64_t n = 2 * (hoffs[m] - hoffs[0] + m);
+  for (int64_t i = m; i >= 0; --i) hoffs[i] -= hoffs[0];   // k_build_text lays the text out from offs[0]
   DevBuf<uint8_t> T;
   SVB_CUDA(T.alloc(n));
   k_build_text<<<grid_for(n, 256, 4), 256>>>(d_seqs, d_offs_p, m, n, T.p);
@@ -746,7 +799,19 @@ int svb_index_build(const uint8_t* contigs, const int64_t* offs, int64_t m, int 
     if (e != cudaSuccess) { set_error("cudaMalloc SA failed: %s", cudaGetErrorString(e)); delete idx; return SVB_ENOMEM; }
     rc = build_suffix_array(T.p, n, SA.p, 0);
     if (rc == SVB_OK) rc = build_blocks(&idx->dev, nullptr, SA.p, T.p, 0);
+    if (rc == SVB_OK) {
+      IndexDev& d = idx->dev;
+      d.n_ssa = ((n - 1) >> d.ss_log) + 1;
+      if (cudaMalloc((void**)&d.d_ssa, (size_t)d.n_ssa * 8) != cudaSuccess) { set_error("cudaMalloc of the SA samples failed"); rc = SVB_ENOMEM; }
+      else {
+        k_sample_sa<<<grid_for(d.n_ssa, 256, 4), 256>>>(SA.p, d.n_ssa, d.ss_log, d.d_ssa);
+        if (cudaDeviceSynchronize() != cudaSuccess) { set_error("k_sample_sa failed"); rc = SVB_ECUDA; }
+      }
+    }
   }
+  if (rc == SVB_OK) rc = attach_text(&idx->dev, T.p, hoffs);
+  T.release();
+  if (rc == SVB_OK) rc = build_kmer_table(&idx->dev);
   if (rc != SVB_OK) { svb_index_free(idx); return rc; }
   *out = idx;
   return SVB_OK;
@@ -780,6 +845,10 @@ void svb_index_free(svb_index_t* idx) {
   if (idx->dev.d_blocks) cudaFree(idx->dev.d_blocks);
   if (idx->dev.d_cntN) cudaFree(idx->dev.d_cntN);
   if (idx->dev.d_sbase) cudaFree(idx->dev.d_sbase);
+  if (idx->dev.d_text_alloc) cudaFree(idx->dev.d_text_alloc);
+  if (idx->dev.d_ssa) cudaFree(idx->dev.d_ssa);
+  if (idx->dev.d_tstart) cudaFree(idx->dev.d_tstart);
+  if (idx->dev.d_kmt) cudaFree(idx->dev.d_kmt);
   delete idx;
 }
 
@@ -792,7 +861,9 @@ int svb_index_info(const svb_index_t* idx, svb_index_info_t* info) {
   info->block_bytes = d.G * 16;
   info->block_syms = d.G * 32;
   info->n_contigs = d.n_contigs;
-  info->device_bytes = d.n_blocks * d.G * 16 + (d.G == 4 ? d.n_blocks * 4 : 0) + (int64_t)d.n_sb * 64;
+  info->device_bytes = d.n_blocks * d.G * 16 + (d.G == 4 ? d.n_blocks * 4 : 0) + (int64_t)d.n_sb * 64 +
+                       (d.d_text ? d.n + 2 * TEXT_PAD + d.n_ssa * 8 + (d.n_contigs + 1) * 8 : 0) +
+                       (d.d_kmt ? (int64_t)8 << (2 * d.kmer_k) : 0);
   info->device = d.device;
   return SVB_OK;
 }
@@ -817,13 +888,16 @@ int svb_index_get_bwt(const svb_index_t* idx, uint8_t* bwt_host) {
 
 // ---- index file: private layout (the reference treats the index file as opaque, run_svdss:137-164)
 struct FileHeader {
-  char magic[8];  // "SVB200I\2"
+  char magic[8];  // "SVB200I\3"
   int32_t G;
   int32_t n_sb;
   int64_t n;
   int64_t acc[7];
   int64_t n_blocks;
   int64_t n_contigs;
+  int32_t has_text;  // 1: tstart[n_contigs+1], 4-bit packed forward strands, SA samples follow the blocks
+  int32_t ss_log;
+  int64_t n_ssa;
 };
 
 int svb_index_save(const svb_index_t* idx, const char* path) {
@@ -834,9 +908,10 @@ int svb_index_save(const svb_index_t* idx, const char* path) {
   if (!f) { set_error("cannot open %s for writing", path); return SVB_EIO; }
   FileHeader h;
   memset(&h, 0, sizeof(h));
-  memcpy(h.magic, "SVB200I\2", 8);
+  memcpy(h.magic, "SVB200I\3", 8);
   h.G = d.G; h.n_sb = d.n_sb; h.n = d.n; memcpy(h.acc, d.acc, sizeof(d.acc));
   h.n_blocks = d.n_blocks; h.n_contigs = d.n_contigs;
+  h.has_text = d.d_text ? 1 : 0; h.ss_log = d.ss_log; h.n_ssa = d.n_ssa;
   bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
   const size_t CH = (size_t)256 << 20;
   std::vector<uint8_t> buf(CH);
@@ -850,6 +925,18 @@ int svb_index_save(const svb_index_t* idx, const char* path) {
   dump(d.d_sbase, (size_t)d.n_sb * 64);
   dump(d.d_blocks, (size_t)d.n_blocks * d.G * 16);
   if (d.G == 4) dump(d.d_cntN, (size_t)d.n_blocks * 4);
+  if (d.d_text) {
+    const int64_t tot = (d.n - 2 * d.n_contigs) / 2;
+    DevBuf<uint8_t> packed;
+    if (packed.alloc((size_t)std::max<int64_t>((tot + 1) / 2, 1)) != cudaSuccess) ok = false;
+    else {
+      k_pack_fwd<<<grid_for((tot + 1) / 2, 256, 4), 256>>>(d.d_text, d.d_tstart, d.n_contigs, tot, packed.p);
+      ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+      dump(d.d_tstart, (size_t)(d.n_contigs + 1) * 8);
+      dump(packed.p, (size_t)((tot + 1) / 2));
+      dump(d.d_ssa, (size_t)d.n_ssa * 8);
+    }
+  }
   ok = (fclose(f) == 0) && ok;
   if (!ok) { set_error("short write to %s", path); return SVB_EIO; }
   return SVB_OK;
@@ -861,7 +948,7 @@ int svb_index_load(const char* path, int device, svb_index_t** out) {
   FILE* f = fopen(path, "rb");
   if (!f) { set_error("cannot open index %s", path); return SVB_EIO; }
   FileHeader h;
-  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "SVB200I\2", 8) != 0 || (h.G != 4 && h.G != 8)) {
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "SVB200I\3", 8) != 0 || (h.G != 4 && h.G != 8)) {
     fclose(f);
     set_error("%s is not a svdss_b200 index (ropebwt3 .fmd files are not readable yet)", path);
     return SVB_EINVAL;
@@ -885,8 +972,29 @@ int svb_index_load(const char* path, int device, svb_index_t** out) {
   slurp(d.d_sbase, (size_t)d.n_sb * 64);
   slurp(d.d_blocks, (size_t)d.n_blocks * d.G * 16);
   if (d.G == 4) slurp(d.d_cntN, (size_t)d.n_blocks * 4);
+  if (ok && h.has_text) {
+    const int64_t m = d.n_contigs, tot = (d.n - 2 * m) / 2;
+    d.ss_log = h.ss_log; d.n_ssa = h.n_ssa;
+    std::vector<int64_t> ts((size_t)m + 1), offs0((size_t)m + 1);
+    ok = fread(ts.data(), 8, (size_t)m + 1, f) == (size_t)m + 1;
+    for (int64_t r = 0; ok && r <= m; ++r) offs0[r] = (ts[r] - 2 * r) / 2;
+    DevBuf<uint8_t> packed, fwd, T;
+    DevBuf<int64_t> d_offs;
+    ok = ok && tot >= 0 && offs0[m] == tot && packed.alloc((size_t)std::max<int64_t>((tot + 1) / 2, 1)) == cudaSuccess &&
+         fwd.alloc((size_t)std::max<int64_t>(tot, 1)) == cudaSuccess && T.alloc((size_t)d.n) == cudaSuccess &&
+         d_offs.alloc((size_t)m + 1) == cudaSuccess && cudaMalloc((void**)&d.d_ssa, (size_t)d.n_ssa * 8) == cudaSuccess;
+    slurp(packed.p, (size_t)((tot + 1) / 2));
+    slurp(d.d_ssa, (size_t)d.n_ssa * 8);
+    if (ok) {
+      k_unpack_fwd<<<grid_for(tot, 256, 8), 256>>>(packed.p, tot, fwd.p);
+      ok = cudaMemcpy(d_offs.p, offs0.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+      k_build_text<<<grid_for(d.n, 256, 4), 256>>>(fwd.p, d_offs.p, m, d.n, T.p);
+      ok = ok && cudaDeviceSynchronize() == cudaSuccess && attach_text(&d, T.p, offs0) == SVB_OK;
+    }
+  }
   fclose(f);
   if (!ok) { svb_index_free(idx); set_error("failed to load index %s (truncated file or out of device memory)", path); return SVB_EIO; }
+  { const int rc = build_kmer_table(&d); if (rc != SVB_OK) { svb_index_free(idx); return rc; } }
   *out = idx;
   return SVB_OK;
 }

@@ -67,7 +67,16 @@ struct SearchParams {
   int assemble;
   unsigned long long* work;      // next read to hand out
   unsigned long long* out_count; // records appended
-  unsigned long long* stats;     // [0] extensions, [1] blocks touched
+  unsigned long long* stats;     // [0] extensions, [1] blocks touched, [2] extensions answered from the text
+  // located-match mode (IndexDev::d_text / d_ssa / d_tstart); text == nullptr: rank mode only
+  const uint8_t* __restrict__ text;
+  const uint64_t* __restrict__ ssa;
+  const int64_t* __restrict__ tstart;
+  int64_t n_contigs;
+  int ss_log;
+  // K-mer jump table (IndexDev::d_kmt); kmt == nullptr: every restart walks from one base
+  const uint64_t* __restrict__ kmt;
+  int kmer_k;
   uint64_t* out_key;             // read << 32 | sort key
   uint32_t* out_len;
   unsigned long long out_cap;
@@ -519,6 +528,92 @@ __device__ __forceinline__ void cpa_fetch(const SearchParams& P, uint32_t bk, ui
   __syncwarp();
 }
 
+// ---- located-match mode -------------------------------------------------------------------
+// Once the interval of the current match has size 1 and its row carries an SA sample, the match is
+// ONE text position p and "does cW occur" is "T[p-1] == c".  The ping-pong walk then turns into a
+// byte compare of the read against the text: the backward phase walks both downwards; the forward
+// phase (a backward search of rc(P[b..e])) is mirrored onto the other strand, where the same
+// occurrence reads P[b..e] left to right, so it walks both upwards.  Results are identical to the
+// rank walk by construction (same occurrence set); 16 bases cost ~30 instructions and two
+// sequential 24-byte reads instead of 16 random 128-byte block fetches.
+__device__ __forceinline__ uint64_t funnel64(uint64_t lo, uint64_t hi, int sh) {  // bytes [sh/8, sh/8+8) of hi:lo
+  return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+}
+struct Win16 { uint64_t w0, w1, w2; int sh; };
+// the 16 bytes at [a, a+16) of `base` (a may be < 0: those bytes are never looked at)
+__device__ __forceinline__ void load16(const uint8_t* base, int64_t a, Win16& w, int64_t min_word) {
+  const uint64_t* p = reinterpret_cast<const uint64_t*>(base);
+  const int64_t i = a >> 3;
+  w.sh = (int)(a & 7) * 8;
+  w.w0 = __ldcg(p + max(i, min_word));
+  w.w1 = __ldcg(p + max(i + 1, min_word));
+  w.w2 = __ldcg(p + max(i + 2, min_word));
+}
+// text position of the mirror image (other strand) of text position x
+__device__ __forceinline__ int64_t mirror_pos(const SearchParams& P, int64_t x) {
+  int64_t lo = 0, hi = P.n_contigs - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if (__ldg(P.tstart + mid) <= x) lo = mid; else hi = mid - 1;
+  }
+  return __ldg(P.tstart + lo) + __ldg(P.tstart + lo + 1) - 2 - x;
+}
+
+// ---- K-mer jump table ----------------------------------------------------------------------
+// 2-bit codes of the first K (<= 16) bytes of a 16-byte window; false if one of them is not A,C,G,T
+__device__ __forceinline__ bool words_kmer(uint64_t lo, uint64_t hi, int K, uint32_t& code);
+__device__ __forceinline__ bool window_kmer(const Win16& w, int K, uint32_t& code) {
+  return words_kmer(funnel64(w.w0, w.w1, w.sh), funnel64(w.w1, w.w2, w.sh), K, code);
+}
+// lo = bytes 0..7, hi = bytes 8..15 of the window
+__device__ __forceinline__ bool words_kmer(uint64_t lo, uint64_t hi, int K, uint32_t& code) {
+  const uint64_t H = 0x8080808080808080ull, L1 = 0x0101010101010101ull;
+  const uint64_t rlo = (lo | H) - L1, rhi = (hi | H) - L1;   // per byte: 0x80 + (b - 1), no borrow across bytes
+  uint64_t blo = ((rlo ^ H) & 0xFCFCFCFCFCFCFCFCull) | (lo & 0xF8F8F8F8F8F8F8F8ull);
+  uint64_t bhi = ((rhi ^ H) & 0xFCFCFCFCFCFCFCFCull) | (hi & 0xF8F8F8F8F8F8F8F8ull);
+  if (K < 8) blo &= (1ull << (8 * K)) - 1ull;
+  if (K <= 8) bhi = 0; else if (K < 16) bhi &= (1ull << (8 * (K - 8))) - 1ull;
+  if (blo | bhi) return false;
+  auto squeeze = [](uint64_t x) {   // bits 8i..8i+1 of x -> bits 2i..2i+1
+    x &= 0x0303030303030303ull;
+    x = (x | (x >> 6)) & 0x000F000F000F000Full;
+    x = (x | (x >> 12)) & 0x000000FF000000FFull;
+    x = (x | (x >> 24)) & 0xFFFFull;
+    return (uint32_t)x;
+  };
+  code = squeeze(rlo) | (squeeze(rhi) << 16);
+  if (K < 16) code &= (1u << (2 * K)) - 1u;
+  return true;
+}
+// code of the reverse complement of a K-mer code
+__device__ __forceinline__ uint32_t kmer_rc(uint32_t code, int K) {
+  uint32_t r = __brev(~code);                                             // complement, then reverse bits
+  r = ((r & 0xAAAAAAAAu) >> 1) | ((r & 0x55555555u) << 1);                // un-reverse inside each 2-bit group
+  return K < 16 ? r >> (32 - 2 * K) : r;
+}
+// acc[c] + Occ(c, pos) straight from global memory (128-byte blocks with in-block samples)
+__device__ __forceinline__ uint64_t occ_global(const SearchParams& P, int c, uint64_t pos) {
+  return (uint64_t)__ldg(P.sbase + (pos >> 32) * 8 + c) + staged_occ(P.blocks + (pos >> 8) * 8, (int)((unsigned)pos & 255u), c, 0);
+}
+// level j of the table from level j-1: interval(cX) = extend(interval(X), c); first base in the low bits.
+// Intermediate levels keep exact (start, size) pairs; the last level is packed into the table.
+__global__ void k_kmer_level(const SearchParams P, const ulonglong2* __restrict__ prev, ulonglong2* __restrict__ cur,
+                             uint64_t* __restrict__ packed, int j, const int64_t n) {
+  const uint64_t total = 1ull << (2 * j), stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t y = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; y < total; y += stride) {
+    ulonglong2 e = make_ulonglong2(0ull, (unsigned long long)n);
+    if (j > 1) e = prev[y >> 2];
+    ulonglong2 o = make_ulonglong2(0ull, 0ull);
+    if (e.y != 0) {
+      const int c = (int)(y & 3) + 1;
+      const uint64_t nk = occ_global(P, c, e.x), nl = occ_global(P, c, e.x + e.y);
+      o = make_ulonglong2(nk, nl - nk);
+    }
+    if (packed) packed[y] = o.x | (min((uint64_t)o.y, KMT_SAT) << 40);
+    else cur[y] = o;
+  }
+}
+
 constexpr int TMA_WARPS = 3;  // warps per CTA; 8 KB of staging per warp -> 9 CTAs = 27 warps per SM
 
 template <int MINB, int MODE>  // MODE 0: TMA bulk copies (UBLKCP), 1: cooperative cp.async (LDGSTS)
@@ -544,7 +639,10 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
   int len = 0, pos = 0, begin = 0;
   uint64_t k = 0, s = 0;
   int chain_qs = -1, chain_end = -1;
-  unsigned n_ext = 0, n_blk = 0;
+  unsigned n_ext = 0, n_blk = 0, n_txt = 0;
+  bool tmode = false;   // located-match mode: T[g + delta] is aligned with read byte g
+  int64_t delta = 0;
+  const unsigned ss_mask = (1u << P.ss_log) - 1u;
   ReadWin1 win;
   win.reset();
 
@@ -570,18 +668,46 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
     if (P.assemble && chain_qs >= 0) emit(chain_qs, chain_end - chain_qs);
     chain_qs = -1;
     have = false;
-    atomicAdd(P.stats + 0, (unsigned long long)n_ext);
+    tmode = false;
+    atomicAdd(P.stats + 0, (unsigned long long)n_ext + n_txt);
     atomicAdd(P.stats + 1, (unsigned long long)n_blk);
-    n_ext = 0; n_blk = 0;
+    if (n_txt) atomicAdd(P.stats + 2, (unsigned long long)n_txt);
+    n_ext = 0; n_blk = 0; n_txt = 0;
   };
   auto set_intv = [&](int c0) {
     k = (uint64_t)P.acc[c0];
     s = (uint64_t)(P.acc[c0 + 1] - P.acc[c0]);  // rb3_fmd_set_intv (ping_pong.cpp:12,30)
+    tmode = false;
+  };
+  // (re)start the walk at pivot `pos` in the direction of `phase`: rb3_fmd_set_intv + the first K-1
+  // extensions in one table lookup when the K-mer at the pivot occurs, else from the pivot base alone
+  auto start_walk = [&]() {
+    const int K = P.kmer_k;
+    if (P.kmt != nullptr && (phase ? pos + K <= len : pos + 1 >= K)) {
+      Win16 w;
+      load16(P.seq, roff + (phase ? pos : pos - K + 1), w, 0);
+      uint32_t code;
+      if (window_kmer(w, K, code)) {
+        const uint64_t e = __ldg(P.kmt + (phase ? kmer_rc(code, K) : code));
+        const uint64_t sz = e >> 40;
+        if (sz != 0 && sz != KMT_SAT) {
+          k = e & ((1ull << 40) - 1ull);
+          s = sz;
+          pos += phase ? K - 1 : -(K - 1);
+          n_ext += (unsigned)(K - 1);
+          tmode = false;
+          win.id = -1; win.nid = -1;
+          return;
+        }
+      }
+    }
+    const int ch = win.get(P.seq, roff + pos, phase ? 1 : -1);
+    set_intv(phase ? comp6(ch) : ch);
   };
 
   while (__any_sync(0xffffffffu, alive)) {
     int c = 0;
-    bool do_ext = false;
+    bool do_ext = false, do_txt = false;
     if (alive) {
       if (!have) {
         const unsigned long long w = atomicAdd(P.work, 1ull);
@@ -601,28 +727,39 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
             phase = 0;
             pos = len - 1;
             win.reset();
-            set_intv(win.get(P.seq, roff + pos, -1));
+            start_walk();
           }
         }
       }
       // state machine of ping_pong.cpp:15-47, advanced to the next pending extension.  Both
       // directions share ONE fast path (dir = -1 backward, +1 forward) so that threads in
       // different phases do not serialise the warp.
-      while (have && !do_ext) {
+      while (have && !do_ext && !do_txt) {
         const int dir = phase ? 1 : -1;
         const bool room = phase ? (pos + 1 < len) : (pos > 0);
         if (s != 0 && room) {
-          pos += dir;
-          const int ch = win.get(P.seq, roff + pos, dir);
-          c = phase ? comp6(ch) : ch;
-          do_ext = true;
+          if (!tmode && P.text != nullptr && s == 1 && ((unsigned)k & ss_mask) == 0u) {
+            // unique and on a sampled row: locate.  Backward: P[pos..] starts at T[p].  Forward:
+            // rc(P[begin..pos]) starts at T[p]; its mirror image is P[begin..pos] read left to right.
+            const int64_t p = (int64_t)__ldg(P.ssa + (k >> P.ss_log));
+            delta = phase ? mirror_pos(P, p + (pos - begin)) - (roff + begin) : p - (roff + pos);
+            tmode = true;
+          }
+          if (tmode) {
+            do_txt = true;
+          } else {
+            pos += dir;
+            const int ch = win.get(P.seq, roff + pos, dir);
+            c = phase ? comp6(ch) : ch;
+            do_ext = true;
+          }
         } else if (phase == 0) {
           if (s != 0) {
             finish_read();  // reached the read start still matching (ping_pong.cpp:24-25)
           } else {          // mismatch at pos: forward search from here (ping_pong.cpp:27-30)
             begin = pos;
             phase = 1;
-            set_intv(comp6(win.get(P.seq, roff + pos, +1)));
+            start_walk();
           }
         } else {
           if (s != 0) ++pos;               // defensive: cannot happen (see k_sfs_search)
@@ -637,11 +774,20 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
               if (nb > len - 1) nb = len - 1;
               pos = nb;
               phase = 0;
-              set_intv(win.get(P.seq, roff + pos, -1));
+              start_walk();
             }
           }
         }
       }
+    }
+    // located threads: issue the loads of the next 16 read / text bytes now, so that they are in
+    // flight together with the index blocks of the warp's rank-mode threads
+    Win16 rw, tw;
+    int64_t a0 = 0;
+    if (do_txt) {
+      a0 = roff + pos + (phase ? 1 : -16);   // window [a0, a0+16): above pos (forward) / below pos (backward)
+      load16(P.seq, a0, rw, 0);
+      load16(P.text, a0 + delta, tw, -(int64_t)(TEXT_PAD / 8));
     }
     bool two = false;
     if (MODE == 0) {
@@ -660,7 +806,348 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
       ++n_ext;
       n_blk += two ? 2u : 1u;
     }
+    if (do_txt) {
+      const uint64_t xlo = funnel64(rw.w0, rw.w1, rw.sh) ^ funnel64(tw.w0, tw.w1, tw.sh);   // bytes a0 .. a0+7
+      const uint64_t xhi = funnel64(rw.w1, rw.w2, rw.sh) ^ funnel64(tw.w1, tw.w2, tw.sh);   // bytes a0+8 .. a0+15
+      int nb, mt;  // bases available in walking direction (<= 16), leading bases that match
+      if (phase) {
+        nb = min(16, len - 1 - pos);
+        mt = xlo ? (__ffsll((long long)xlo) - 1) >> 3 : 8 + (xhi ? (__ffsll((long long)xhi) - 1) >> 3 : 8);
+      } else {
+        nb = min(16, pos);
+        mt = xhi ? __clzll((long long)xhi) >> 3 : 8 + (xlo ? __clzll((long long)xlo) >> 3 : 8);
+      }
+      const int dir = phase ? 1 : -1;
+      if (mt >= nb) {          // all nb extensions succeed (interval stays of size 1)
+        pos += dir * nb;
+        n_txt += (unsigned)nb;
+      } else {                 // extension number mt+1 fails: same state as a rank walk ending in s == 0
+        pos += dir * (mt + 1);
+        n_txt += (unsigned)(mt + 1);
+        s = 0;
+        tmode = false;
+      }
+      win.id = -1; win.nid = -1;   // the byte window no longer follows pos
+    }
     if (MODE == 1) __syncwarp();  // staging slots are rewritten by other lanes next iteration
+  }
+}
+
+// 32-byte window at an arbitrary byte address: three aligned 16-byte loads
+struct Win32 { uint4 q0, q1, q2; int sh; };   // sh = byte offset of the window inside q0 (0..15)
+__device__ __forceinline__ void load32(const uint8_t* base, int64_t a, Win32& w, int64_t min_q) {
+  const uint4* p = reinterpret_cast<const uint4*>(base);
+  const int64_t i = a >> 4;
+  w.sh = (int)(a & 15);
+  w.q0 = __ldcg(p + max(i, min_q));
+  w.q1 = __ldcg(p + max(i + 1, min_q));
+  w.q2 = __ldcg(p + max(i + 2, min_q));
+}
+// the four 8-byte words of the window, lowest address first
+__device__ __forceinline__ void win32_words(const Win32& w, uint64_t o[4]) {
+  const uint64_t v0 = (uint64_t)w.q0.x | ((uint64_t)w.q0.y << 32), v1 = (uint64_t)w.q0.z | ((uint64_t)w.q0.w << 32);
+  const uint64_t v2 = (uint64_t)w.q1.x | ((uint64_t)w.q1.y << 32), v3 = (uint64_t)w.q1.z | ((uint64_t)w.q1.w << 32);
+  const uint64_t v4 = (uint64_t)w.q2.x | ((uint64_t)w.q2.y << 32), v5 = (uint64_t)w.q2.z | ((uint64_t)w.q2.w << 32);
+  const bool hi = w.sh >= 8;
+  const int sh = (w.sh & 7) * 8;
+  const uint64_t a0 = hi ? v1 : v0, a1 = hi ? v2 : v1, a2 = hi ? v3 : v2, a3 = hi ? v4 : v3, a4 = hi ? v5 : v4;
+  o[0] = funnel64(a0, a1, sh); o[1] = funnel64(a1, a2, sh); o[2] = funnel64(a2, a3, sh); o[3] = funnel64(a3, a4, sh);
+}
+// staging for the lanes that have an extension pending (a minority once located matches and the jump
+// table carry most of the walk): four of them per round, eight lanes x 16 bytes per block
+__device__ __forceinline__ void cpa_fetch_sparse(const SearchParams& P, uint32_t bk, uint32_t bl, uint32_t warp_stage_s,
+                                                 int lane) {
+  unsigned m = __ballot_sync(0xffffffffu, bk != NOBLK);
+  const int sub = lane >> 3, j = lane & 7;
+  while (m) {
+    const unsigned t = __fns(m, 0, sub + 1);   // the sub-th pending lane of this round (0xffffffff: none)
+    const bool on = t < 32u;
+    const uint32_t xk = __shfl_sync(0xffffffffu, bk, on ? (int)t : 0);
+    const uint32_t xl = __shfl_sync(0xffffffffu, bl, on ? (int)t : 0);
+    if (on) {
+      const uint32_t dst = warp_stage_s + (uint32_t)(t * 256u + ((j + t) & 7u) * 16u);
+      cp_async16(dst, P.blocks + (uint64_t)xk * 8 + j);
+      if (xl != xk) cp_async16(dst + 128u, P.blocks + (uint64_t)xl * 8 + j);
+    }
+    m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------ v3 kernel
+// Micro-op pipeline.  ncu on the hybrid version of k_sfs_search_tma (profiles/r01e_*) showed a warp
+// iteration lasting ~12 us at 31 % issue utilisation: every divergent path of the state machine
+// (K-mer window load -> table lookup, SA sample, read window refill, text compare, index blocks) did
+// its own blocking round trip to memory, one after the other.  Here a thread's walk is cut into
+// micro-ops that each need ONE batch of loads whose addresses are known up front; per iteration
+// every lane (1) advances its state machine without touching memory, (2) issues the loads of its
+// micro-op from code all lanes share, (3) waits once together with the warp's cp.async staging,
+// (4) consumes.  A warp iteration is then one memory round trip whatever mix of ops its lanes hold.
+//   OP_EXT   rank extension: 1-2 index blocks staged by the warp (cp.async, as in k_sfs_search_tma)
+//   OP_TXT   located match: 32 read bytes against 32 text bytes
+//   OP_KMER  restart, step 1: the K read bytes at the pivot (skipped when the bases just walked are
+//            still in the thread's 16-base history register, which is the rule inside novel sequence)
+//   OP_KMT   restart, step 2: the jump-table entry of that K-mer
+//   OP_SSA   locate: the SA sample of the row (forward phase: + contig lookup for the mirror image)
+enum : int { OP_NONE = 0, OP_EXT = 1, OP_TXT = 2, OP_KMER = 3, OP_KMT = 4, OP_SSA = 5 };
+enum : int { ST_START = 0, ST_WALK = 1, ST_KMT = 2 };
+
+template <int MINB>
+__global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const SearchParams P) {
+  __shared__ __align__(128) uint4 stage[TMA_WARPS * 32 * 16];  // [warp][lane][2 blocks][8 slices]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4* my = stage + (warp * 32 + lane) * 16;
+  const uint32_t warp_stage_s = smem_u32(stage + warp * 32 * 16);
+
+  bool alive = true, have = false;
+  int st = ST_START, phase = 0;
+  uint32_t ridx = 0, kcode = 0;
+  int64_t roff = 0;
+  int len = 0, pos = 0, begin = 0;
+  uint64_t k = 0, s = 0;
+  int chain_qs = -1, chain_end = -1;
+  unsigned n_ext = 0, n_blk = 0, n_txt = 0;
+  bool tmode = false;
+  int64_t delta = 0;
+  // the last bases walked, 2 bits each, in read order: a backward walk keeps the base at `pos` in the
+  // low bits (higher positions above it), a forward walk keeps the base at `pos` in the top bits;
+  // hv = how many of them are valid (0 after an N, a text-mode step or a fresh read)
+  uint32_t hist = 0;
+  int hv = 0;
+  const unsigned ss_mask = (1u << P.ss_log) - 1u;
+  const int K = P.kmer_k;
+  ReadWin1 win;
+  win.reset();
+
+  auto emit = [&](int qs, int ln) {
+    unsigned long long o = atomicAdd(P.out_count, 1ull);
+    if (o < P.out_cap) {
+      uint32_t sk = P.assemble ? (uint32_t)qs : ~(uint32_t)qs;
+      P.out_key[o] = ((uint64_t)ridx << 32) | sk;
+      P.out_len[o] = (uint32_t)ln;
+    }
+  };
+  auto on_sfs = [&](int qs, int ln) {
+    if (!P.assemble) { emit(qs, ln); return; }
+    if (chain_qs >= 0 && qs + ln > chain_qs) {
+      chain_qs = qs;
+    } else {
+      if (chain_qs >= 0) emit(chain_qs, chain_end - chain_qs);
+      chain_qs = qs;
+      chain_end = qs + ln;
+    }
+  };
+  auto finish_read = [&]() {
+    if (P.assemble && chain_qs >= 0) emit(chain_qs, chain_end - chain_qs);
+    chain_qs = -1;
+    have = false;
+    tmode = false;
+    atomicAdd(P.stats + 0, (unsigned long long)n_ext + n_txt);
+    atomicAdd(P.stats + 1, (unsigned long long)n_blk);
+    if (n_txt) atomicAdd(P.stats + 2, (unsigned long long)n_txt);
+    n_ext = 0; n_blk = 0; n_txt = 0;
+  };
+  auto set_intv = [&](int c0) {
+    k = (uint64_t)P.acc[c0];
+    s = (uint64_t)(P.acc[c0 + 1] - P.acc[c0]);  // rb3_fmd_set_intv (ping_pong.cpp:12,30)
+    tmode = false;
+    st = ST_WALK;
+  };
+  auto push_hist = [&](int ch) {   // ch = read base (nt6 code) at the new `pos`
+    if (ch >= 1 && ch <= 4) {
+      hist = phase ? (hist >> 2) | ((uint32_t)(ch - 1) << 30) : (hist << 2) | (uint32_t)(ch - 1);
+      hv = min(16, hv + 1);
+    } else {
+      hv = 0;
+    }
+  };
+  auto set_intv_at_pivot = [&]() {
+    const int ch = win.get(P.seq, roff + pos, phase ? 1 : -1);
+    set_intv(phase ? comp6(ch) : ch);
+    hv = 0;
+    push_hist(ch);
+  };
+
+  while (__any_sync(0xffffffffu, alive)) {
+    // ---- (1) advance to the next micro-op (ping_pong.cpp:15-47); no waits on memory except the
+    //          hand-out of a new read and the rare walk that starts without the jump table
+    int op = OP_NONE, c = 0;
+    while (alive && op == OP_NONE) {
+      if (!have) {
+        const unsigned long long w = atomicAdd(P.work, 1ull);
+        if (w >= (unsigned long long)P.n_reads) { alive = false; break; }
+        ridx = P.order ? P.order[w] : (uint32_t)w;
+        roff = P.offs[ridx];
+        len = (int)(P.offs[ridx + 1] - roff);
+        if (len <= 0) continue;
+        if (P.ready) {  // streamed batch: wait until the chunk holding the last base landed
+          const volatile unsigned int* flag = P.ready + (roff + len - 1) / P.chunk_bytes;
+          while (*flag == 0u) __nanosleep(500);
+          __threadfence();
+        }
+        have = true;
+        phase = 0;
+        pos = len - 1;
+        st = ST_START;
+        tmode = false;
+        hv = 0;
+        win.reset();
+      }
+      if (st == ST_START) {   // (re)start at pivot `pos`: jump table if K bases are there, else one base
+        if (P.kmt != nullptr && (phase ? pos + K <= len : pos + 1 >= K)) {
+          // hv > 0 here means the history was left by the walk that ended at the pivot's neighbour:
+          //   forward restart at begin (= the base the backward walk failed on): low bits = P[begin..]
+          //   backward restart at the base below the forward mismatch: top bits = P[..pos+1]
+          if (phase && hv >= K) {
+            kcode = kmer_rc(hist & ((1u << (2 * K)) - 1u), K);
+            st = ST_KMT;
+          } else if (!phase && hv >= K + 1 && P.overlap == -1) {
+            kcode = (hist >> (30 - 2 * K)) & ((1u << (2 * K)) - 1u);
+            st = ST_KMT;
+          } else {
+            op = OP_KMER;
+          }
+        } else {
+          set_intv_at_pivot();
+        }
+        continue;
+      }
+      if (st == ST_KMT) { op = OP_KMT; continue; }
+      const int dir = phase ? 1 : -1;
+      const bool room = phase ? (pos + 1 < len) : (pos > 0);
+      if (s != 0 && room) {
+        if (tmode) {
+          op = OP_TXT;
+        } else if (P.text != nullptr && s == 1 && ((unsigned)k & ss_mask) == 0u) {
+          op = OP_SSA;
+        } else {
+          pos += dir;
+          const int ch = win.get(P.seq, roff + pos, dir);
+          push_hist(ch);
+          c = phase ? comp6(ch) : ch;
+          op = OP_EXT;
+        }
+      } else if (phase == 0) {
+        if (s != 0) {
+          finish_read();  // reached the read start still matching (ping_pong.cpp:24-25)
+        } else {          // mismatch at pos: forward search from here (ping_pong.cpp:27-30)
+          begin = pos;
+          phase = 1;
+          st = ST_START;
+        }
+      } else {
+        if (s != 0) ++pos;               // defensive: cannot happen (see k_sfs_search)
+        on_sfs(begin, pos - begin + 1);  // ping_pong.cpp:39-41
+        if (begin == 0) {
+          finish_read();
+        } else {
+          int nb = (P.overlap == 0) ? begin - 1 : pos + P.overlap;  // ping_pong.cpp:44-47
+          if (nb < 0) {
+            finish_read();
+          } else {
+            if (nb > len - 1) nb = len - 1;
+            pos = nb;
+            phase = 0;
+            st = ST_START;
+          }
+        }
+      }
+    }
+    // ---- (2) issue: every load of this iteration leaves from here
+    Win32 rw, tw;
+    uint64_t one = 0;
+    if (op == OP_TXT || op == OP_KMER) {
+      const int64_t a0 = roff + (op == OP_TXT ? pos + (phase ? 1 : -32) : (phase ? pos : pos - K + 1));
+      load32(P.seq, a0, rw, 0);
+      if (op == OP_TXT) load32(P.text, a0 + delta, tw, -(int64_t)(TEXT_PAD / 16));
+    } else if (op == OP_KMT) {
+      one = __ldg(P.kmt + kcode);
+    } else if (op == OP_SSA) {
+      one = __ldg(P.ssa + (k >> P.ss_log));
+    }
+    const uint32_t bk = op == OP_EXT ? (uint32_t)(k >> 8) : NOBLK;
+    const uint32_t bl = op == OP_EXT ? (uint32_t)((k + s) >> 8) : NOBLK;
+    // ---- (3) one wait for the warp
+    cpa_fetch_sparse(P, bk, bl, warp_stage_s, lane);
+    // ---- (4) consume
+    if (op == OP_EXT) {
+      const bool two = bl != bk;
+      tma_consume(P, my, two, c, k, s, lane);
+      ++n_ext;
+      n_blk += two ? 2u : 1u;
+    } else if (op == OP_TXT) {
+      uint64_t r[4], t[4];
+      win32_words(rw, r);
+      win32_words(tw, t);
+      const uint64_t x0 = r[0] ^ t[0], x1 = r[1] ^ t[1], x2 = r[2] ^ t[2], x3 = r[3] ^ t[3];
+      int nb, mt;  // bases available in walking direction (<= 32), leading bases that match
+      if (phase) {
+        nb = min(32, len - 1 - pos);
+        mt = x0 ? (__ffsll((long long)x0) - 1) >> 3
+           : x1 ? 8 + ((__ffsll((long long)x1) - 1) >> 3)
+           : x2 ? 16 + ((__ffsll((long long)x2) - 1) >> 3)
+           : x3 ? 24 + ((__ffsll((long long)x3) - 1) >> 3) : 32;
+      } else {
+        nb = min(32, pos);
+        mt = x3 ? __clzll((long long)x3) >> 3
+           : x2 ? 8 + (__clzll((long long)x2) >> 3)
+           : x1 ? 16 + (__clzll((long long)x1) >> 3)
+           : x0 ? 24 + (__clzll((long long)x0) >> 3) : 32;
+      }
+      const int dir = phase ? 1 : -1;
+      if (mt >= nb) {          // all nb extensions succeed (the interval stays of size 1)
+        pos += dir * nb;
+        n_txt += (unsigned)nb;
+      } else {                 // extension mt+1 fails: the state a rank walk ends in with s == 0
+        pos += dir * (mt + 1);
+        n_txt += (unsigned)(mt + 1);
+        s = 0;
+        tmode = false;
+      }
+      hv = 0;
+      win.id = -1; win.nid = -1;
+    } else if (op == OP_KMER) {
+      uint64_t r[4];
+      win32_words(rw, r);
+      uint32_t code;
+      if (words_kmer(r[0], r[1], K, code)) {
+        kcode = phase ? kmer_rc(code, K) : code;
+        // the K bases become the history of the walk that continues from the jump
+        hist = phase ? code << (32 - 2 * K) : code;
+        hv = -K;               // negative: valid only if the jump succeeds (flipped in OP_KMT)
+        st = ST_KMT;
+      } else {                 // an N among the K bases: walk from the pivot base
+        set_intv_at_pivot();
+      }
+    } else if (op == OP_KMT) {
+      const uint64_t sz = one >> 40;
+      if (sz != 0 && sz != KMT_SAT) {   // the K-mer occurs: rb3_fmd_set_intv + K-1 successful extensions
+        k = one & ((1ull << 40) - 1ull);
+        s = sz;
+        pos += phase ? K - 1 : -(K - 1);
+        n_ext += (unsigned)(K - 1);
+        tmode = false;
+        st = ST_WALK;
+        win.id = -1; win.nid = -1;
+        if (hv < 0) {
+          hv = -hv;                     // history = the K-mer read by OP_KMER
+        } else {                        // the K-mer came out of the history register: re-aim it
+          const uint32_t code = phase ? kmer_rc(kcode, K) : kcode;   // bases in read order, lowest position first
+          hist = phase ? code << (32 - 2 * K) : code;
+          hv = K;
+        }
+      } else {                          // absent (the walk fails within K bases) or saturated entry
+        set_intv_at_pivot();
+      }
+    } else if (op == OP_SSA) {
+      // Backward: P[pos..] starts at T[p].  Forward: rc(P[begin..pos]) starts at T[p]; its mirror
+      // image on the other strand is P[begin..pos] read left to right.
+      const int64_t p = (int64_t)one;
+      delta = phase ? mirror_pos(P, p + (pos - begin)) - (roff + begin) : p - (roff + pos);
+      tmode = true;
+    }
+    __syncwarp();  // staging slots are rewritten by other lanes next iteration
   }
 }
 
@@ -724,6 +1211,12 @@ static void fill_params(SearchParams& P, const IndexDev& d) {
   P.cntN = d.d_cntN;
   P.sbase = d.d_sbase;
   memcpy(P.acc, d.acc, sizeof(d.acc));
+  const char* e = getenv("SVB_SEARCH_TEXT");   // SVB_SEARCH_TEXT=0: rank walk only (the pure FMD kernel)
+  if (d.d_text && !(e && *e == '0')) {
+    P.text = d.d_text; P.ssa = d.d_ssa; P.tstart = d.d_tstart; P.n_contigs = d.n_contigs; P.ss_log = d.ss_log;
+  }
+  const char* ej = getenv("SVB_SEARCH_JUMP");   // SVB_SEARCH_JUMP=0: restarts walk from one base
+  if (d.d_kmt && !(ej && *ej == '0')) { P.kmt = d.d_kmt; P.kmer_k = d.kmer_k; }
 }
 
 // sort key of a read: (chunk of its last base) << 32 | ~length  -> chunk-major, longest first
@@ -765,6 +1258,49 @@ int check_device(int device);
 using namespace svb;
 
 namespace svb {
+// K = floor(log4(n)) - 1 keeps the expected number of occurrences of a random K-mer in [4, 16): the
+// jump almost always lands on a non-empty interval a few extensions away from a unique match.
+// SVB_KMER_K overrides (0 disables the table).  8 bytes per entry: K = 15 is 8.6 GB next to a
+// 6.2 G-symbol index.
+int build_kmer_table(IndexDev* idx) {
+  if (idx->G != 8 || idx->d_kmt) return SVB_OK;
+  int K = 0;
+  while (K < 16 && (idx->n >> (2 * (K + 1))) > 0) ++K;   // floor(log4 n)
+  K = std::min(15, K - 1);
+  if (const char* e = getenv("SVB_KMER_K")) K = std::min(15, atoi(e));
+  if (K < 2) return SVB_OK;
+  SearchParams P;
+  fill_params(P, *idx);
+  const size_t entries = (size_t)1 << (2 * K);
+  ulonglong2 *a = nullptr, *b = nullptr;
+  uint64_t* kmt = nullptr;
+  cudaError_t e1 = cudaMalloc((void**)&kmt, entries * 8);
+  cudaError_t e2 = K > 1 ? cudaMalloc((void**)&a, (entries / 4) * 16) : cudaSuccess;
+  cudaError_t e3 = K > 2 ? cudaMalloc((void**)&b, (entries / 16) * 16) : cudaSuccess;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    cudaFree(kmt); cudaFree(a); cudaFree(b);
+    cudaGetLastError();
+    return SVB_OK;   // not enough memory for the table: restarts simply walk from one base
+  }
+  // levels alternate between the two scratch buffers so that level K-1 ends in `a` (the larger one)
+  ulonglong2* bufs[2] = {a, b};
+  for (int j = 1; j <= K; ++j) {
+    const uint64_t total = 1ull << (2 * j);
+    const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 32);
+    const ulonglong2* prev = j > 1 ? bufs[(K - j) & 1] : nullptr;      // level j-1 lives in bufs[(K-1-(j-1)) & 1]
+    ulonglong2* cur = j < K ? bufs[(K - 1 - j) & 1] : nullptr;
+    k_kmer_level<<<grid, 256>>>(P, prev, cur, j == K ? kmt : nullptr, j, idx->n);
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  cudaFree(a); cudaFree(b);
+  if (e != cudaSuccess) { cudaFree(kmt); set_error("k_kmer_level failed: %s", cudaGetErrorString(e)); return SVB_ECUDA; }
+  idx->d_kmt = kmt;
+  idx->kmer_k = K;
+  return SVB_OK;
+}
+}  // namespace svb
+
+namespace svb {
 int check_device(int device) {
   int cnt = 0;
   cudaError_t e = cudaGetDeviceCount(&cnt);
@@ -798,9 +1334,10 @@ static int pick_cfg(int slices, int* G) {
   const char* e = getenv("SVB_SEARCH_CFG");
   // defaults: 128-byte blocks -> thread-per-read kernel with cooperative cp.async staging ("cpa");
   //           64-byte blocks  -> 4 lanes per read
-  int g = (slices == 8) ? -1 : 4;
-  if (e && (strcmp(e, "tma") == 0 || strcmp(e, "cpa") == 0)) {  // staged kernels: 128-byte blocks only
-    *G = (slices == 8) ? (e[0] == 't' ? 0 : -1) : g;
+  // ("mop" = micro-op pipeline kernel, the default for 128-byte blocks; "cpa" = its predecessor)
+  int g = (slices == 8) ? -2 : 4;
+  if (e && (strcmp(e, "tma") == 0 || strcmp(e, "cpa") == 0 || strcmp(e, "mop") == 0)) {  // staged kernels: 128-byte blocks only
+    *G = (slices == 8) ? (e[0] == 't' ? 0 : e[0] == 'c' ? -1 : -2) : g;
     return SVB_OK;
   }
   if (e && *e) {
@@ -825,7 +1362,7 @@ static int pick_cfg(int slices, int* G) {
   } while (0)
 
 struct SearchScratch {
-  unsigned long long* d_ctr = nullptr;  // [0] work [1] out_count [2] ext [3] blocks
+  unsigned long long* d_ctr = nullptr;  // [0] work [1] out_count [2] ext [3] blocks [4] text extensions
   uint64_t* d_key = nullptr; uint64_t* d_key2 = nullptr;
   uint32_t* d_len = nullptr; uint32_t* d_len2 = nullptr;
   void* d_tmp = nullptr;
@@ -863,14 +1400,16 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   P.overlap = overlap; P.assemble = assemble;
   SearchScratch S;
   S.st = st;
-  SVB_CUDA(pmalloc((void**)&S.d_ctr, 4 * sizeof(unsigned long long), st));
+  SVB_CUDA(pmalloc((void**)&S.d_ctr, 5 * sizeof(unsigned long long), st));
   // first guess of output capacity; exact count is known after the run, rerun once if it overflowed
   unsigned long long cap = assemble ? (unsigned long long)(4 * n_reads + 1024)
                                     : (unsigned long long)(R->total / 8 + 64 * n_reads + 1024);
   int grid = 0, cfgG = 0;
   SVB_TRY(pick_cfg(d.G, &cfgG));
   const int tma_minb = 9;
-  if (cfgG == 0) {
+  if (cfgG == -2) {
+    SVB_TRY(persistent_grid(k_sfs_search_mop<tma_minb>, TMA_WARPS * 32, d.device, &grid));
+  } else if (cfgG == 0) {
     SVB_TRY(persistent_grid(k_sfs_search_tma<tma_minb, 0>, TMA_WARPS * 32, d.device, &grid));
   } else if (cfgG == -1) {
     SVB_TRY(persistent_grid(k_sfs_search_tma<tma_minb, 1>, TMA_WARPS * 32, d.device, &grid));
@@ -882,19 +1421,21 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   cudaEvent_t e0, e1;
   SVB_CUDA(cudaEventCreate(&e0));
   SVB_CUDA(cudaEventCreate(&e1));
-  unsigned long long ctr[4] = {0, 0, 0, 0};
+  unsigned long long ctr[5] = {0, 0, 0, 0, 0};
   float kms = 0.f;
   for (int attempt = 0; attempt < 2; ++attempt) {
     pfree(S.d_key, st); pfree(S.d_len, st); S.d_key = nullptr; S.d_len = nullptr;
     SVB_CUDA(pmalloc((void**)&S.d_key, cap * 8, st));
     SVB_CUDA(pmalloc((void**)&S.d_len, cap * 4, st));
-    SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 4 * sizeof(unsigned long long), st));
+    SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 5 * sizeof(unsigned long long), st));
     P.work = S.d_ctr + 0; P.out_count = S.d_ctr + 1; P.stats = S.d_ctr + 2;
     P.out_key = S.d_key; P.out_len = S.d_len; P.out_cap = cap;
     P.ready = nullptr; P.chunk_bytes = 0;
     if (src && attempt == 0) { P.ready = src->d_ready; P.chunk_bytes = src->chunk_bytes; }
     SVB_CUDA(cudaEventRecord(e0, st));
-    if (cfgG == 0) {
+    if (cfgG == -2) {
+      k_sfs_search_mop<tma_minb><<<grid, TMA_WARPS * 32, 0, st>>>(P);
+    } else if (cfgG == 0) {
       k_sfs_search_tma<tma_minb, 0><<<grid, TMA_WARPS * 32, 0, st>>>(P);
     } else if (cfgG == -1) {
       k_sfs_search_tma<tma_minb, 1><<<grid, TMA_WARPS * 32, 0, st>>>(P);
@@ -928,6 +1469,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   out->kernel_ms = kms;
   out->n_ext = (int64_t)ctr[2];
   out->n_blocks_touched = (int64_t)ctr[3];
+  out->n_text_ext = (int64_t)ctr[4];
   const int64_t m = (int64_t)ctr[1];
   out->n_sfs = m;
   if (m == 0) return SVB_OK;
@@ -1191,6 +1733,7 @@ int svb_rank_bench(const svb_index_t* idx, int64_t nq, int64_t delta, uint64_t s
   fill_params(P, d);
   int grid = 0, cfgG = 0;
   SVB_TRY(pick_cfg(d.G, &cfgG));
+  if (cfgG == -2) cfgG = -1;  // the microbenchmark has one cp.async-staged variant
   if (cfgG == 0) {
     SVB_TRY(persistent_grid(k_rank_bench_tma<0>, TMA_WARPS * 32, d.device, &grid));
   } else if (cfgG == -1) {

@@ -202,7 +202,7 @@ def materialize_segments_numpy(ref_cat, segs):
     return out
 
 
-def materialize_segments_torch(ref_cat_t, segs, out_t=None, chunk_segs=200_000):
+def materialize_segments_torch(ref_cat_t, segs, out_t=None, chunk_segs=40_000):
     """Device materialiser: ref_cat_t uint8 CUDA tensor of the concatenated contigs. Returns a uint8
     CUDA tensor with 64 spare bytes at the end (the search kernel's read-window padding)."""
     import torch

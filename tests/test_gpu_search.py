@@ -124,7 +124,10 @@ def test_config1_full_parity(bb):
     got_raw, res = _gpu_sfs(idx, reads, assemble=False)
     assert got_raw == exp
     assert res.n_ext == ext
-    assert res.n_ext <= res.n_blocks_touched <= 2 * res.n_ext
+    rank_ext = res.n_ext - res.n_text_ext       # extensions answered from index blocks or the K-mer table
+    assert 0 < res.n_blocks_touched <= 2 * rank_ext
+    if bb == 128:   # the default kernel; the 64-byte-block lane-group kernels are rank walk only
+        assert res.n_text_ext > res.n_ext // 2      # smoothed reads: most of the walk is a located match
     got_asm, _ = _gpu_sfs(idx, reads, assemble=True)
     assert got_asm == [oracle.assemble(e) for e in exp]
     # resident path returns the same thing
@@ -144,8 +147,9 @@ def test_index_save_load_roundtrip(tmp_path):
         idx.save(p)
         idx2 = capi.Index.load(p)
         assert idx2.n == idx.n and idx2.acc == idx.acc and idx2.block_bytes == bb
-        b, _ = _gpu_sfs(idx2, reads, assemble=True)
+        b, rb = _gpu_sfs(idx2, reads, assemble=True)
         assert a == b
+        assert bb == 64 or rb.n_text_ext > 0   # text, SA samples and contig starts came back from the file
     with pytest.raises(capi.SvbError):
         capi.Index.load(os.path.join(tmp_path, "missing.svb"))
 
@@ -184,7 +188,7 @@ def test_medium_scale_properties():
         assert oracle.assemble(a) == a
 
 
-@pytest.mark.parametrize("cfg,bb", [("cpa", 128), ("tma", 128), ("8x1", 128), ("4x2", 128), ("2x4", 128), ("1x8", 128),
+@pytest.mark.parametrize("cfg,bb", [("mop", 128), ("cpa", 128), ("tma", 128), ("8x1", 128), ("4x2", 128), ("2x4", 128), ("1x8", 128),
                                     ("4x1", 64), ("2x2", 64), ("1x4", 64)])
 def test_all_kernel_configs_agree(cfg, bb, monkeypatch):
     """every lane-group / staging configuration of the search kernel returns the oracle's SFS sets"""
@@ -221,3 +225,55 @@ def test_streamed_host_batch_matches_resident(monkeypatch):
     monkeypatch.setenv("SVB_NO_STREAM", "1")
     got2, _ = _gpu_sfs(idx, reads, assemble=False)
     assert got2 == exp
+
+
+def test_located_match_mode_equals_rank_walk(monkeypatch):
+    """The located-match mode (unique interval on a sampled SA row -> byte compare against the text,
+    forward phase mirrored onto the other strand) must give the SFS sets AND the extension count of
+    the pure rank walk: many short contigs (mirror / sentinel / text-start edges), N runs, reads
+    ending inside matches, both assemble modes; an index built from a bare BWT has no text."""
+    rng = np.random.default_rng(77)
+    contigs = [rng.integers(1, 5, size=int(rng.integers(40, 4000)), dtype=np.uint8) for _ in range(60)]
+    contigs[3][100:130] = 5
+    contigs.append(contigs[5][200:900].copy())                 # an exact repeat: intervals of size 2
+    contigs.append(synth.revcomp6(contigs[7][50:1500]))
+    reads = []
+    for _ in range(600):
+        c = contigs[int(rng.integers(len(contigs)))]
+        a = int(rng.integers(0, max(1, len(c) - 30)))
+        b = int(rng.integers(a + 1, len(c) + 1))
+        r = c[a:b].copy()
+        if rng.random() < 0.5:
+            r = synth.revcomp6(r)
+        k = int(rng.integers(0, 4))
+        if k == 1 and len(r) > 10:
+            p = int(rng.integers(0, len(r))); r[p] = (r[p] % 4) + 1
+        elif k == 2:
+            p = int(rng.integers(0, len(r) + 1)); r = np.concatenate([r[:p], rng.integers(1, 5, size=int(rng.integers(1, 60)), dtype=np.uint8), r[p:]])
+        elif k == 3 and len(r) > 40:
+            p = int(rng.integers(0, len(r) - 20)); r = np.concatenate([r[:p], r[p + int(rng.integers(1, 20)):]])
+        reads.append(np.ascontiguousarray(r, np.uint8))
+    T, SA, bwt = oracle_index(contigs)
+    cat, offs = oracle.concat(contigs)
+    exp, ext = fm_results(oracle.FMIndex(bwt), reads)
+    for spec_i in range(0, len(reads), 41):
+        assert oracle.sfs_spec(T, SA, reads[spec_i]) == exp[spec_i]
+    idx = capi.Index.build(cat, offs, block_bytes=128)
+    got, res = _gpu_sfs(idx, reads, assemble=False)
+    assert got == exp and res.n_ext == ext and res.n_text_ext > 0
+    got_asm, _ = _gpu_sfs(idx, reads, assemble=True)
+    assert got_asm == [oracle.assemble(e) for e in exp]
+    monkeypatch.setenv("SVB_SEARCH_TEXT", "0")
+    got0, res0 = _gpu_sfs(idx, reads, assemble=False)
+    assert got0 == exp and res0.n_ext == ext and res0.n_text_ext == 0
+    # K-mer jump table off as well: the plain rank walk touches the most blocks
+    monkeypatch.setenv("SVB_SEARCH_JUMP", "0")
+    got00, res00 = _gpu_sfs(idx, reads, assemble=False)
+    assert got00 == exp and res00.n_ext == ext and res00.n_blocks_touched > res0.n_blocks_touched
+    monkeypatch.delenv("SVB_SEARCH_TEXT")
+    got01, res01 = _gpu_sfs(idx, reads, assemble=False)      # located matches without the jump table
+    assert got01 == exp and res01.n_ext == ext and res01.n_text_ext > 0
+    monkeypatch.delenv("SVB_SEARCH_JUMP")
+    idx_b = capi.Index.from_bwt(bwt, block_bytes=128)
+    got_b, res_b = _gpu_sfs(idx_b, reads, assemble=False)
+    assert got_b == exp and res_b.n_text_ext == 0

@@ -1,0 +1,17 @@
+#!/bin/bash
+# one reduced-section ncu capture of the search kernel (few replay passes: the process holds tens of
+# GB that ncu saves/restores around every pass) + raw/source CSV pages next to the report
+set -x
+mkdir -p gpurun_out
+READS=${READS:-100000}
+TAG=${TAG:-quick}
+export SVB_NO_STREAM=1
+SVB_PROFILE=1 timeout ${NCU_TIMEOUT:-900} ncu --profile-from-start off --clock-control none --import-source on -k regex:k_sfs_search -c 1 \
+  --section SpeedOfLight --section SchedulerStats --section WarpStateStats --section MemoryWorkloadAnalysis \
+  --section SourceCounters --section LaunchStats --section Occupancy --section InstructionStats \
+  --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active \
+  -o gpurun_out/prof_$TAG -f python bench.py --reads $READS --steps 1 --warmup 0 --no-cpu-baseline --no-rank-walk $EXTRA > gpurun_out/prof_bench_$TAG.log 2>&1
+tail -3 gpurun_out/prof_bench_$TAG.log
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --csv > gpurun_out/prof_${TAG}_source.csv 2>/dev/null
+ls -la gpurun_out | tail -5
