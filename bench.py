@@ -168,12 +168,23 @@ def run_ours(args):
     offs_t = torch.from_numpy(read_offs).to(dev)
     dreads = capi.DeviceReads(reads_t.data_ptr(), offs_t.data_ptr(), device=local, mem=capi.SVB_MEM_DEVICE,
                               n_reads=n_reads)
-    # host copy for the end-to-end arm (pinned)
+    # host copies for the end-to-end arms (pinned): the reads as BAM stores them (4 bits per base, what
+    # the reference's loader receives from bam_get_seq) and, for comparison, one nt6 byte per base
     total = int(read_offs[-1])
     host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
     host.copy_(reads_t[:total])
-    torch.cuda.synchronize(dev)
     host_np = host.numpy()
+    l_qseq = np.diff(read_offs).astype(np.int32)
+    seq4_offs = np.zeros(n_reads + 1, np.int64)
+    seq4_offs[1:] = np.cumsum((l_qseq.astype(np.int64) + 1) // 2)
+    s4o_t = torch.from_numpy(seq4_offs).to(dev)
+    packed_t = torch.empty(int(seq4_offs[-1]) + 16, dtype=torch.uint8, device=dev)
+    capi.pack4_device(reads_t.data_ptr(), offs_t.data_ptr(), s4o_t.data_ptr(), n_reads, packed_t.data_ptr(), device=local)
+    host4 = torch.empty(int(seq4_offs[-1]), dtype=torch.uint8, pin_memory=True)
+    host4.copy_(packed_t[:int(seq4_offs[-1])])
+    torch.cuda.synchronize(dev)
+    del packed_t, s4o_t
+    torch.cuda.empty_cache()
 
     def barrier():
         if world > 1:
@@ -220,8 +231,11 @@ def run_ours(args):
     # ---- e2e: host buffers through svb_sfs_batch
     from svdss_b200 import parallel
 
-    def e2e_step():
-        r = idx.sfs_batch(host_np, read_offs, assemble=assemble)
+    def e2e_step(packed=True):
+        if packed:
+            r = idx.sfs_batch_bam4(host4.data_ptr(), seq4_offs, l_qseq, assemble=assemble)
+        else:
+            r = idx.sfs_batch(host_np, read_offs, assemble=assemble)
         if world > 1:  # the path's only collective: final gather of the SFS tables on rank 0 (NCCL)
             r.gathered = parallel.gather_sfs(np.diff(r.offs), r.qs, r.len, dist, dst=0, device=dev)
         return r
@@ -229,6 +243,8 @@ def run_ours(args):
     res_e, ms_dev_e, ms_wall_e, clocks_e = timed(e2e_step, args.steps, args.warmup)
     ms_step_e = ms_wall_e / args.steps
     assert res_e[-1].n_sfs == n_sfs, "resident and host paths disagree"
+    res_b, ms_dev_b, ms_wall_b, _ = timed(lambda: e2e_step(False), max(1, args.steps - 1), 1)
+    assert res_b[-1].n_sfs == n_sfs, "resident and host (byte) paths disagree"
     peak, peak_src = hbm_peak()
     # algorithmic bytes of one launch: 128 B per distinct index block fetched + 2 B (read byte + text
     # byte) per extension answered in located-match mode
@@ -272,7 +288,11 @@ def run_ours(args):
                    "index_build_s": round(setup["index_build_s"], 2)},
         "e2e": {"value": world * n_reads / (ms_step_e * 1e-3), "unit": "reads/s",
                 "h2d_bytes_per_step": int(res_e[-1].h2d_bytes), "d2h_bytes_per_step": int(res_e[-1].d2h_bytes),
-                "ms_per_step": ms_step_e, "device_ms_per_step": ms_dev_e / args.steps},
+                "ms_per_step": ms_step_e, "device_ms_per_step": ms_dev_e / args.steps,
+                "api": "svb_sfs_batch_bam4: pinned host buffer of 4-bit BAM-native reads (bam_get_seq layout), decoded on the GPU"},
+        "e2e_nt6_bytes": {"value": world * n_reads / (ms_wall_b / max(1, args.steps - 1) * 1e-3), "unit": "reads/s",
+                          "h2d_bytes_per_step": int(res_b[-1].h2d_bytes), "d2h_bytes_per_step": int(res_b[-1].d2h_bytes),
+                          "api": "svb_sfs_batch: one nt6 byte per base, the reference's in-memory form after its host decode"},
         "gpu_launches": launches + int(sum(r.launches for r in res_e)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(n_reads, idx.block_bytes) if args.ref_bp == REF_BP else None,

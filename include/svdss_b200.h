@@ -124,6 +124,20 @@ SVB_API int svb_sfs_batch(const svb_index_t* idx, const uint8_t* nt6_concat,
                           const int64_t* offs /* n_reads+1 */, int64_t n_reads, int overlap,
                           int assemble, svb_sfs_out_t* out);
 
+/* The same call for reads as BAM stores them -- what load_batch_bam gets from bam_get_seq before its
+ * decode loop (ping_pong.cpp:88-94): 4 bits per base, two bases per byte, first base in the high
+ * nibble, htslib nt16 codes (=ACMGRSVTWYHKDBN), every read starting on a byte boundary.
+ * seq4_offs[r] is the byte offset of read r in seq4 (n_reads + 1 entries), l_qseq[r] its length in
+ * bases (bam1_core_t::l_qseq).  The nt16 -> ASCII -> nt6 decode of ping_pong.cpp:90-94 runs on the
+ * GPU, so half as many bytes cross PCIe and the host does not touch the bases at all.  Results are
+ * identical to svb_sfs_batch on the decoded reads.  128-byte-block indexes only.  HOST buffers. */
+SVB_API int svb_sfs_batch_bam4(const svb_index_t* idx, const uint8_t* seq4, const int64_t* seq4_offs /* n_reads+1 */,
+                               const int32_t* l_qseq /* n_reads */, int64_t n_reads, int overlap, int assemble,
+                               svb_sfs_out_t* out);
+/* Test / bench utility: pack nt6 reads resident on `device` into that BAM layout (device buffers). */
+SVB_API int svb_pack4_device(const uint8_t* d_nt6_concat, const int64_t* d_offs /* n_reads+1 */,
+                             const int64_t* d_seq4_offs /* n_reads+1 */, int64_t n_reads, int device, uint8_t* d_out);
+
 /* Same search with the batch already resident in HBM (kernel-only measurement; multi-batch reuse). */
 SVB_API int svb_reads_upload(const uint8_t* nt6_concat, const int64_t* offs, int64_t n_reads,
                              int mem, int device, svb_reads_t** out);

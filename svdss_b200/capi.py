@@ -56,7 +56,7 @@ EXPORTS = [
     "svb_index_build", "svb_index_from_bwt", "svb_index_load", "svb_index_save", "svb_index_free",
     "svb_index_info", "svb_index_get_bwt", "svb_suffix_array",
     "svb_rank2a", "svb_rank_bench",
-    "svb_sfs_batch", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
+    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
     "svb_poa_batch", "svb_poa_out_free",
 ]
@@ -87,6 +87,8 @@ def lib():
     L.svb_rank2a.argtypes = [vp, vp, vp, i64, vp, vp]
     L.svb_rank_bench.argtypes = [vp, i64, i64, C.c_uint64, i32, C.POINTER(C.c_float), C.POINTER(i64)]
     L.svb_sfs_batch.argtypes = [vp, vp, vp, i64, i32, i32, C.POINTER(SfsOut)]
+    L.svb_sfs_batch_bam4.argtypes = [vp, vp, vp, vp, i64, i32, i32, C.POINTER(SfsOut)]
+    L.svb_pack4_device.argtypes = [vp, vp, vp, i64, i32, vp]
     L.svb_reads_upload.argtypes = [vp, vp, i64, i32, i32, C.POINTER(vp)]
     L.svb_reads_free.argtypes = [vp]
     L.svb_reads_free.restype = None
@@ -213,6 +215,24 @@ class Index:
         out = SfsOut()
         check(lib().svb_sfs_batch(self._h, _ptr(reads_cat), _ptr(offs), len(offs) - 1, overlap,
                                   1 if assemble else 0, C.byref(out)))
+        try:
+            return SfsResult(out)
+        finally:
+            lib().svb_sfs_out_free(C.byref(out))
+
+    def sfs_batch_bam4(self, seq4, seq4_offs, l_qseq, overlap=-1, assemble=True):
+        """svb_sfs_batch_bam4: reads as BAM stores them (4-bit nt16, one read per byte-aligned run).
+        seq4 may be a numpy array or an integer host address (pinned buffer)."""
+        seq4_offs = np.ascontiguousarray(seq4_offs, np.int64)
+        l_qseq = np.ascontiguousarray(l_qseq, np.int32)
+        if isinstance(seq4, np.ndarray):
+            seq4 = np.ascontiguousarray(seq4, np.uint8)
+            p = _ptr(seq4)
+        else:
+            p = C.c_void_p(int(seq4))
+        out = SfsOut()
+        check(lib().svb_sfs_batch_bam4(self._h, p, _ptr(seq4_offs), _ptr(l_qseq), len(l_qseq), overlap,
+                                       1 if assemble else 0, C.byref(out)))
         try:
             return SfsResult(out)
         finally:
@@ -360,3 +380,26 @@ def poa_batch(clusters, device=0):
         return PoaResult(out)
     finally:
         lib().svb_poa_out_free(C.byref(out))
+
+
+NT16_OF_NT6 = np.array([15, 1, 2, 4, 8, 15], np.uint8)   # nt6 code -> htslib nt16 code (N for $ / N)
+
+
+def pack_bam4(reads):
+    """Host helper (tests): list of nt6 arrays -> (seq4 bytes, byte offsets, l_qseq) in BAM's layout:
+    two bases per byte, first base in the high nibble, every read starting on a byte boundary."""
+    l_qseq = np.array([len(r) for r in reads], np.int32)
+    offs = np.zeros(len(reads) + 1, np.int64)
+    offs[1:] = np.cumsum((l_qseq.astype(np.int64) + 1) // 2)
+    out = np.zeros(int(offs[-1]), np.uint8)
+    for r, o in zip(reads, offs[:-1]):
+        c = NT16_OF_NT6[np.minimum(np.asarray(r, np.uint8), 5)]
+        if len(c) & 1:
+            c = np.concatenate([c, np.zeros(1, np.uint8)])
+        out[o:o + len(c) // 2] = (c[0::2] << 4) | c[1::2]
+    return out, offs, l_qseq
+
+
+def pack4_device(d_seq_ptr, d_offs_ptr, d_seq4_offs_ptr, n_reads, d_out_ptr, device=0):
+    check(lib().svb_pack4_device(C.c_void_p(d_seq_ptr), C.c_void_p(d_offs_ptr), C.c_void_p(d_seq4_offs_ptr), n_reads,
+                                 device, C.c_void_p(d_out_ptr)))

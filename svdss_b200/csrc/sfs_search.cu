@@ -67,7 +67,7 @@ struct SearchParams {
   int assemble;
   unsigned long long* work;      // next read to hand out
   unsigned long long* out_count; // records appended
-  unsigned long long* stats;     // [0] extensions, [1] blocks touched, [2] extensions answered from the text
+  unsigned long long* stats;     // [0] extensions, [1] blocks touched, [2] extensions answered from the text, [3] stream stalled
   // located-match mode (IndexDev::d_text / d_ssa / d_tstart); text == nullptr: rank mode only
   const uint8_t* __restrict__ text;
   const uint64_t* __restrict__ ssa;
@@ -84,6 +84,20 @@ struct SearchParams {
   // ready[c] != 0 once chunk c (chunk_bytes each) is resident.  nullptr = everything resident.
   const unsigned int* ready;
   int64_t chunk_bytes;
+  // packed streamed batches (svb_sfs_batch_bam4): the first n_unpack CTAs of the grid do not search;
+  // they turn each chunk of 4-bit reads into bytes as soon as the copy engine has delivered it
+  // (arrived[c]) and raise ready[c] themselves.  Part of the same launch, so they are resident
+  // next to the searching CTAs by construction.
+  const uint8_t* seq4;
+  const int64_t* seq4_offs;
+  const unsigned int* arrived;
+  unsigned int* ready_w;
+  unsigned int* chunk_done;
+  const int64_t* chunk_r0;   // first / last read reaching into chunk c
+  const int64_t* chunk_r1;
+  uint8_t* seq_w;            // = seq, writable
+  int64_t total;
+  int n_chunks, n_unpack;
 };
 
 __device__ __forceinline__ uint4 ldg_slice(const uint4* p) {
@@ -419,6 +433,28 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// streamed batch: wait until the chunk holding a read's last base has landed.  The chunks are fed by
+// copies (and, for packed input, unpack kernels) queued behind this kernel; if they never arrive --
+// a scheduling assumption broken -- give up after 20 s instead of hanging the device: stats[3] tells
+// the host, which fails the call.
+__device__ __forceinline__ bool wait_chunk(const volatile unsigned int* flag, unsigned long long* stall_flag) {
+  if (*flag != 0u) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  while (*flag == 0u) {
+    __nanosleep(500);
+    if (globaltimer_ns() - t0 > 20000000000ull || *reinterpret_cast<volatile unsigned long long*>(stall_flag) != 0ull) {
+      atomicExch(stall_flag, 1ull);
+      return false;
+    }
+  }
+  return true;
+}
+
 // per-thread read window: 8 bases in a u64 + the prefetched neighbour in walking direction.
 // A direction switch keeps `cur` (the pivot base is in it) and only re-aims the prefetch, so the
 // warp never waits on a read-window load except at the first base of a read.
@@ -718,8 +754,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
           roff = P.offs[ridx];
           len = (int)(P.offs[ridx + 1] - roff);
           if (P.ready && len > 0) {  // streamed batch: wait until the chunk holding the last base landed
-            const volatile unsigned int* flag = P.ready + (roff + len - 1) / P.chunk_bytes;
-            while (*flag == 0u) __nanosleep(500);
+            if (!wait_chunk(P.ready + (roff + len - 1) / P.chunk_bytes, P.stats + 3)) { alive = false; len = 0; }
             __threadfence();
           }
           if (len > 0) {
@@ -833,6 +868,98 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_tma(const S
   }
 }
 
+// ping_pong.cpp:90-94 on the device: htslib nt16 code -> ASCII (seq_nt16_str) -> nt6 (seq_nt6_table):
+// A=1 C=2 G=4 T=8 map to 1..4, every other code (=, IUPAC, N) to 5
+__device__ __forceinline__ uint8_t nt16_to_nt6(unsigned c) {
+  return c == 1u ? 1 : c == 2u ? 2 : c == 4u ? 3 : c == 8u ? 4 : 5;
+}
+// 16 bases of one read, starting at base j (any parity), as 16 nt6 bytes.  The nine packed bytes that
+// can hold them are taken from two aligned 8-byte loads.
+__device__ __forceinline__ uint4 unpack16(const uint8_t* __restrict__ seq4, int64_t byte0, int odd) {
+  const uint64_t* p = reinterpret_cast<const uint64_t*>(seq4);
+  const int64_t wi = byte0 >> 3;
+  const int sh = (int)(byte0 & 7) * 8;
+  const uint64_t w0 = __ldcg(p + wi), w1 = __ldcg(p + wi + 1);
+  uint64_t x = funnel64(w0, w1, sh);                              // packed bytes byte0 .. byte0+7
+  const uint64_t ninth = (w1 >> sh) & 0xffull;                    // packed byte byte0+8
+  // BAM keeps the first base of a byte in the HIGH nibble: swap so that nibble k of x is base k
+  x = ((x & 0x0F0F0F0F0F0F0F0Full) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0Full);
+  if (odd) x = (x >> 4) | ((ninth >> 4) << 60);
+  // nt16 -> nt6 through a 16-entry nibble table: 1 -> 1, 2 -> 2, 4 -> 3, 8 -> 4, everything else -> 5
+  const uint64_t LUT = 0x5555555455535215ull;
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const unsigned n = (unsigned)(x >> (4 * (4 * q + t))) & 15u;
+      v |= (uint32_t)((LUT >> (4 * n)) & 15ull) << (8 * t);
+    }
+    o[q] = v;
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// one warp unpacks the bases of read r that fall into base positions [A, B).  Lanes own 16-byte
+// aligned groups of the OUTPUT (coalesced 16-byte stores, two groups per lane and step); the ragged
+// head and tail of the range go base by base.
+__device__ __forceinline__ void unpack4_read(const uint8_t* __restrict__ seq4, const int64_t* __restrict__ seq4_offs,
+                                             const int64_t* __restrict__ offs, int64_t r, int64_t A, int64_t B,
+                                             uint8_t* __restrict__ out, int lane) {
+  const int64_t o = offs[r], l = offs[r + 1] - o, pb = seq4_offs[r];
+  const int64_t lo = max(o, A), hi = min(o + l, B);
+  if (lo >= hi) return;
+  auto one = [&](int64_t g) {   // output position g
+    const int64_t j = g - o;
+    const uint8_t b = __ldcg(seq4 + pb + (j >> 1));
+    out[g] = nt16_to_nt6((j & 1) ? (b & 15u) : (unsigned)(b >> 4));
+  };
+  const int64_t body0 = min(hi, (int64_t)((lo + 15) & ~15LL)), body1 = body0 + ((hi - body0) & ~15LL);
+  if (lo + lane < body0) one(lo + lane);                       // head: fewer than 16 positions
+  for (int64_t g = body0 + 16 * lane; g < body1; g += 1024) {
+    const int64_t g2 = g + 512;
+    const int64_t j = g - o, j2 = g2 - o;
+    const uint4 v = unpack16(seq4, pb + (j >> 1), (int)(j & 1));
+    uint4 v2 = make_uint4(0, 0, 0, 0);
+    if (g2 < body1) v2 = unpack16(seq4, pb + (j2 >> 1), (int)(j2 & 1));
+    *reinterpret_cast<uint4*>(out + g) = v;
+    if (g2 < body1) *reinterpret_cast<uint4*>(out + g2) = v2;
+  }
+  if (body1 + lane < hi) one(body1 + lane);                    // tail: fewer than 16 positions
+}
+// whole batch at once (small batches, no streaming)
+__global__ void __launch_bounds__(128) k_unpack4(const uint8_t* __restrict__ seq4, const int64_t* __restrict__ seq4_offs,
+                                                  const int64_t* __restrict__ offs, int64_t n_reads, int64_t total,
+                                                  uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += nwarps)
+    unpack4_read(seq4, seq4_offs, offs, r, 0, total, out, lane);
+}
+// the unpacking CTAs of a packed streamed launch (SearchParams::n_unpack of them): chunk after chunk,
+// wait for the copy engine, unpack this CTA's share of the chunk's reads, count in; the last CTA to
+// finish a chunk raises its ready flag for the searching CTAs
+__device__ void unpack_cta_loop(const SearchParams& P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)P.n_unpack * (blockDim.x >> 5);
+  const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int c = 0; c < P.n_chunks; ++c) {
+    if (!wait_chunk(P.arrived + c, P.stats + 3)) return;
+    __threadfence();
+    const int64_t A = (int64_t)c * P.chunk_bytes, B = min(A + P.chunk_bytes, P.total);
+    for (int64_t r = P.chunk_r0[c] + w0; r <= P.chunk_r1[c]; r += nwarps)
+      unpack4_read(P.seq4, P.seq4_offs, P.offs, r, A, B, P.seq_w, lane);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(P.chunk_done + c, 1u) == (unsigned)P.n_unpack - 1u) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(P.ready_w + c) = 1u;
+      }
+    }
+  }
+}
+
 // 32-byte window at an arbitrary byte address: three aligned 16-byte loads
 struct Win32 { uint4 q0, q1, q2; int sh; };   // sh = byte offset of the window inside q0 (0..15)
 __device__ __forceinline__ void load32(const uint8_t* base, int64_t a, Win32& w, int64_t min_q) {
@@ -899,6 +1026,10 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint4* my = stage + (warp * 32 + lane) * 16;
   const uint32_t warp_stage_s = smem_u32(stage + warp * 32 * 16);
+  if (P.n_unpack > 0 && (int)blockIdx.x < P.n_unpack) {   // packed streamed batch: this CTA feeds the others
+    unpack_cta_loop(P);
+    return;
+  }
 
   bool alive = true, have = false;
   int st = ST_START, phase = 0;
@@ -982,8 +1113,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
         len = (int)(P.offs[ridx + 1] - roff);
         if (len <= 0) continue;
         if (P.ready) {  // streamed batch: wait until the chunk holding the last base landed
-          const volatile unsigned int* flag = P.ready + (roff + len - 1) / P.chunk_bytes;
-          while (*flag == 0u) __nanosleep(500);
+          if (!wait_chunk(P.ready + (roff + len - 1) / P.chunk_bytes, P.stats + 3)) { alive = false; break; }
           __threadfence();
         }
         have = true;
@@ -1362,7 +1492,7 @@ static int pick_cfg(int slices, int* G) {
   } while (0)
 
 struct SearchScratch {
-  unsigned long long* d_ctr = nullptr;  // [0] work [1] out_count [2] ext [3] blocks [4] text extensions
+  unsigned long long* d_ctr = nullptr;  // [0] work [1] out_count [2] ext [3] blocks [4] text extensions [5] stream stalled
   uint64_t* d_key = nullptr; uint64_t* d_key2 = nullptr;
   uint32_t* d_len = nullptr; uint32_t* d_len2 = nullptr;
   void* d_tmp = nullptr;
@@ -1381,6 +1511,20 @@ struct StreamSrc {
   unsigned int* d_ready = nullptr;
   unsigned int* h_one = nullptr;  // pinned word holding 1
   cudaStream_t copy_stream = nullptr;
+  // BAM-native input (svb_sfs_batch_bam4): `host` holds 4-bit packed reads; a chunk is still a range
+  // of UNPACKED base positions, fed by copying the packed bytes that cover it and unpacking them on
+  // the device (k_unpack4) before its flag goes up
+  bool packed = false;
+  uint8_t* d_seq4 = nullptr;            // device copy of the packed bytes
+  const int64_t* d_seq4_offs = nullptr; // n_reads + 1 byte offsets (device)
+  const int64_t* h_offs = nullptr;      // n_reads + 1 base offsets (host), for the chunk -> read ranges
+  const int64_t* h_seq4_offs = nullptr; // n_reads + 1 byte offsets (host)
+  const int64_t* h_chunk_r = nullptr;   // [2][n_chunks] (host)
+  int64_t n_reads = 0;
+  unsigned int* d_arrived = nullptr;    // per chunk: packed bytes delivered (copy engine)
+  unsigned int* d_done = nullptr;       // per chunk: unpacking CTAs finished
+  int64_t* d_chunk_r = nullptr;         // [2][n_chunks] first / last read of each chunk
+  int n_unpack = 0;
 };
 
 static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int assemble, svb_sfs_out_t* out,
@@ -1400,7 +1544,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   P.overlap = overlap; P.assemble = assemble;
   SearchScratch S;
   S.st = st;
-  SVB_CUDA(pmalloc((void**)&S.d_ctr, 5 * sizeof(unsigned long long), st));
+  SVB_CUDA(pmalloc((void**)&S.d_ctr, 6 * sizeof(unsigned long long), st));
   // first guess of output capacity; exact count is known after the run, rerun once if it overflowed
   unsigned long long cap = assemble ? (unsigned long long)(4 * n_reads + 1024)
                                     : (unsigned long long)(R->total / 8 + 64 * n_reads + 1024);
@@ -1418,20 +1562,28 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
     SVB_DISPATCH_CFG(d.G, cfgG, SVB_GRID);
 #undef SVB_GRID
   }
+  if (src && src->packed && cfgG != -2) { set_error("packed streamed batches need the default search kernel"); return SVB_EINVAL; }
   cudaEvent_t e0, e1;
   SVB_CUDA(cudaEventCreate(&e0));
   SVB_CUDA(cudaEventCreate(&e1));
-  unsigned long long ctr[5] = {0, 0, 0, 0, 0};
+  unsigned long long ctr[6] = {0, 0, 0, 0, 0, 0};
   float kms = 0.f;
   for (int attempt = 0; attempt < 2; ++attempt) {
     pfree(S.d_key, st); pfree(S.d_len, st); S.d_key = nullptr; S.d_len = nullptr;
     SVB_CUDA(pmalloc((void**)&S.d_key, cap * 8, st));
     SVB_CUDA(pmalloc((void**)&S.d_len, cap * 4, st));
-    SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 5 * sizeof(unsigned long long), st));
+    SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 6 * sizeof(unsigned long long), st));
     P.work = S.d_ctr + 0; P.out_count = S.d_ctr + 1; P.stats = S.d_ctr + 2;
     P.out_key = S.d_key; P.out_len = S.d_len; P.out_cap = cap;
-    P.ready = nullptr; P.chunk_bytes = 0;
-    if (src && attempt == 0) { P.ready = src->d_ready; P.chunk_bytes = src->chunk_bytes; }
+    P.ready = nullptr; P.chunk_bytes = 0; P.n_unpack = 0;
+    if (src && attempt == 0) {
+      P.ready = src->d_ready; P.chunk_bytes = src->chunk_bytes;
+      if (src->packed) {
+        P.seq4 = src->d_seq4; P.seq4_offs = src->d_seq4_offs; P.arrived = src->d_arrived; P.ready_w = src->d_ready;
+        P.chunk_done = src->d_done; P.chunk_r0 = src->d_chunk_r; P.chunk_r1 = src->d_chunk_r + src->n_chunks;
+        P.seq_w = R->d_seq; P.total = src->total; P.n_chunks = (int)src->n_chunks; P.n_unpack = src->n_unpack;
+      }
+    }
     SVB_CUDA(cudaEventRecord(e0, st));
     if (cfgG == -2) {
       k_sfs_search_mop<tma_minb><<<grid, TMA_WARPS * 32, 0, st>>>(P);
@@ -1450,9 +1602,21 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
       // feed the running kernel: chunk copy, then its ready flag, in order on the copy stream
       for (int64_t c = 0; c < src->n_chunks; ++c) {
         const int64_t o = c * src->chunk_bytes, nb = std::min(src->chunk_bytes, src->total - o);
-        SVB_CUDA(cudaMemcpyAsync(R->d_seq + o, src->host + o, nb, cudaMemcpyHostToDevice, src->copy_stream));
-        // flag written by the copy engine too (a memset could need an SM the persistent kernel holds)
-        SVB_CUDA(cudaMemcpyAsync(src->d_ready + c, src->h_one, sizeof(unsigned int), cudaMemcpyHostToDevice, src->copy_stream));
+        if (!src->packed) {
+          SVB_CUDA(cudaMemcpyAsync(R->d_seq + o, src->host + o, nb, cudaMemcpyHostToDevice, src->copy_stream));
+          // flag written by the copy engine too (a memset could need an SM the persistent kernel holds)
+          SVB_CUDA(cudaMemcpyAsync(src->d_ready + c, src->h_one, sizeof(unsigned int), cudaMemcpyHostToDevice, src->copy_stream));
+        } else {
+          // the packed bytes holding the chunk's bases (neighbouring chunks may share a byte: copied
+          // twice, harmless); the unpacking CTAs of the running kernel take it from there
+          const int64_t r_lo = src->h_chunk_r[c], r_hi = src->h_chunk_r[src->n_chunks + c];
+          const int64_t* ho = src->h_offs;
+          const int64_t pa = src->h_seq4_offs[r_lo] + (std::max<int64_t>(o - ho[r_lo], 0) >> 1);
+          const int64_t last = std::min(o + nb, ho[r_hi + 1]) - 1 - ho[r_hi];   // last base of r_hi in the chunk
+          const int64_t pe = last >= 0 ? src->h_seq4_offs[r_hi] + (last >> 1) + 1 : src->h_seq4_offs[r_hi];
+          if (pe > pa) SVB_CUDA(cudaMemcpyAsync(src->d_seq4 + pa, src->host + pa, pe - pa, cudaMemcpyHostToDevice, src->copy_stream));
+          SVB_CUDA(cudaMemcpyAsync(src->d_arrived + c, src->h_one, sizeof(unsigned int), cudaMemcpyHostToDevice, src->copy_stream));
+        }
       }
     }
     SVB_CUDA(cudaMemcpyAsync(ctr, S.d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost, st));
@@ -1461,6 +1625,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
     SVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     kms += ms;
     out->launches += 1;
+    if (ctr[5]) { set_error("the read stream stalled: chunks queued behind the search kernel never arrived"); return SVB_ECUDA; }
     if (ctr[1] <= cap) break;
     cap = ctr[1];
     if (attempt == 1) { set_error("output overflow persisted"); return SVB_ERANGE; }
@@ -1588,8 +1753,12 @@ int svb_sfs_resident(const svb_index_t* idx, const svb_reads_t* reads, int overl
 
 // streamed variant of svb_sfs_batch: offsets first, kernel launched at once, read bytes follow in
 // 128 MiB chunks on a copy stream while the kernel works (chunk-major hand-out order)
+// packed mode (seq4_offs != nullptr): `seq` holds BAM-native 4-bit reads, `offs` their base offsets
+// (offs[0] == 0) and seq4_offs their byte offsets; with stream == false everything is copied and
+// unpacked before the kernel starts (small batches)
 static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const int64_t* offs, int64_t n_reads,
-                              int overlap, int assemble, svb_sfs_out_t* out) {
+                              int overlap, int assemble, svb_sfs_out_t* out, const int64_t* seq4_offs = nullptr,
+                              bool stream = true) {
   const IndexDev& d = idx->dev;
   svb_reads R;
   R.device = d.device;
@@ -1597,8 +1766,13 @@ static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const 
   const int64_t first = offs[0];
   R.total = offs[n_reads] - first;
   StreamSrc src;
-  src.host = seq + first;
+  src.host = seq4_offs ? seq + seq4_offs[0] : seq + first;
   src.total = R.total;
+  src.packed = seq4_offs != nullptr;
+  src.n_reads = n_reads;
+  int64_t* d_s4o = nullptr;
+  std::vector<int64_t> s4rb, chunk_r;
+  const int64_t packed_total = seq4_offs ? seq4_offs[n_reads] - seq4_offs[0] : 0;
   src.chunk_bytes = (int64_t)128 << 20;
   if (const char* e = getenv("SVB_STREAM_CHUNK_BYTES")) { long long v = atoll(e); if (v >= 4096) src.chunk_bytes = (v + 63) & ~63LL; }
   src.n_chunks = (R.total + src.chunk_bytes - 1) / src.chunk_bytes;
@@ -1629,11 +1803,55 @@ static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const 
   SCHECK(cudaMemsetAsync(src.d_ready, 0, src.n_chunks * sizeof(unsigned int), comp));
   SCHECK(cudaMemsetAsync(R.d_seq + R.total, 0, padded - R.total, comp));
   SCHECK(cudaMemcpyAsync(R.d_offs, rb.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, comp));
+  if (src.packed) {
+    s4rb.resize((size_t)n_reads + 1);
+    for (int64_t i = 0; i <= n_reads; ++i) s4rb[i] = seq4_offs[i] - seq4_offs[0];
+    SCHECK(pmalloc((void**)&src.d_seq4, (size_t)packed_total + 16, comp));
+    SCHECK(pmalloc((void**)&d_s4o, (n_reads + 1) * 8, comp));
+    SCHECK(cudaMemcpyAsync(d_s4o, s4rb.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, comp));
+    src.d_seq4_offs = d_s4o;
+    src.h_offs = rb.data();
+    src.h_seq4_offs = s4rb.data();
+    if (stream) {
+      // reads reaching into each chunk of base positions; flags; how many CTAs unpack
+      chunk_r.assign((size_t)src.n_chunks * 2, 0);
+      int64_t r_lo = 0;
+      for (int64_t c = 0; c < src.n_chunks; ++c) {
+        const int64_t o = c * src.chunk_bytes, nb = std::min(src.chunk_bytes, src.total - o);
+        while (r_lo + 1 < n_reads && rb[r_lo + 1] <= o) ++r_lo;
+        int64_t r_hi = r_lo;
+        while (r_hi + 1 < n_reads && rb[r_hi + 1] < o + nb) ++r_hi;
+        chunk_r[c] = r_lo; chunk_r[src.n_chunks + c] = r_hi;
+      }
+      src.h_chunk_r = chunk_r.data();
+      SCHECK(pmalloc((void**)&src.d_chunk_r, src.n_chunks * 16, comp));
+      SCHECK(pmalloc((void**)&src.d_arrived, src.n_chunks * 4, comp));
+      SCHECK(pmalloc((void**)&src.d_done, src.n_chunks * 4, comp));
+      SCHECK(cudaMemcpyAsync(src.d_chunk_r, chunk_r.data(), src.n_chunks * 16, cudaMemcpyHostToDevice, comp));
+      SCHECK(cudaMemsetAsync(src.d_arrived, 0, src.n_chunks * 4, comp));
+      SCHECK(cudaMemsetAsync(src.d_done, 0, src.n_chunks * 4, comp));
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device);
+      src.n_unpack = sms;   // one CTA in nine: ~23 GB of streaming traffic per 1 M reads, far below their share
+      if (const char* e = getenv("SVB_UNPACK_CTAS")) src.n_unpack = std::max(1, atoi(e));
+    }
+  }
+  if (!stream) {   // small packed batch: copy, unpack, then search the resident reads
+    if (packed_total) SCHECK(cudaMemcpyAsync(src.d_seq4, src.host, packed_total, cudaMemcpyHostToDevice, comp));
+    if (n_reads && R.total) {
+      k_unpack4<<<(unsigned)std::min<int64_t>((n_reads + 3) / 4, 148 * 8), 128, 0, comp>>>(src.d_seq4, d_s4o, R.d_offs, n_reads, R.total, R.d_seq);
+      SCHECK(cudaGetLastError());
+    }
+    rc = make_order(&R, 0, comp);
+    if (rc == SVB_OK) rc = run_search(d, &R, overlap, assemble, out, comp, nullptr);
+    if (rc == SVB_OK) { out->h2d_bytes = packed_total + (n_reads + 1) * 16; out->launches += 3; }
+    goto done;
+  }
   rc = make_order(&R, src.chunk_bytes, comp);  // synchronises comp: the allocations above are usable on copy_stream
   if (rc == SVB_OK) rc = run_search(d, &R, overlap, assemble, out, comp, &src);
   if (rc == SVB_OK) {
     SCHECK(cudaStreamSynchronize(src.copy_stream));
-    out->h2d_bytes = R.total + (n_reads + 1) * 8 + src.n_chunks * 4;
+    out->h2d_bytes = (src.packed ? packed_total + (n_reads + 1) * 8 : R.total) + (n_reads + 1) * 8 + src.n_chunks * 4;
     out->launches += 2;  // read keys + order sort
   }
 done:
@@ -1641,6 +1859,7 @@ done:
   if (src.copy_stream) { cudaStreamSynchronize(src.copy_stream); cudaStreamDestroy(src.copy_stream); }
   if (comp) {
     pfree(R.d_seq, comp); pfree(R.d_offs, comp); pfree(R.d_order, comp); pfree(src.d_ready, comp);
+    pfree(src.d_seq4, comp); pfree(d_s4o, comp); pfree(src.d_chunk_r, comp); pfree(src.d_arrived, comp); pfree(src.d_done, comp);
     cudaStreamSynchronize(comp);
     cudaStreamDestroy(comp);
   }
@@ -1681,6 +1900,70 @@ int svb_sfs_batch(const svb_index_t* idx, const uint8_t* seq, const int64_t* off
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (rc != SVB_OK) svb_sfs_out_free(out);
   return rc;
+}
+
+int svb_sfs_batch_bam4(const svb_index_t* idx, const uint8_t* seq4, const int64_t* seq4_offs, const int32_t* l_qseq,
+                       int64_t n_reads, int overlap, int assemble, svb_sfs_out_t* out) {
+  if (!idx || !seq4_offs || !out || n_reads < 0 || (n_reads > 0 && !l_qseq)) { set_error("svb_sfs_batch_bam4: bad arguments"); return SVB_EINVAL; }
+  memset(out, 0, sizeof(*out));
+  SVB_TRY(check_device(idx->dev.device));
+  int cfgG = 0;
+  SVB_TRY(pick_cfg(idx->dev.G, &cfgG));
+  if (cfgG > 0) { set_error("svb_sfs_batch_bam4 needs a 128-byte-block index (the staged search kernels)"); return SVB_EINVAL; }
+  std::vector<int64_t> offs((size_t)n_reads + 1, 0);
+  for (int64_t i = 0; i < n_reads; ++i) {
+    const int64_t l = l_qseq[i], pb = seq4_offs[i + 1] - seq4_offs[i];
+    if (l < 0 || pb < 0 || (l + 1) / 2 > pb) { set_error("read %lld: l_qseq %lld does not fit its %lld packed bytes", (long long)i, (long long)l, (long long)pb); return SVB_EINVAL; }
+    offs[i + 1] = offs[i] + l;
+  }
+  if (offs[n_reads] > 0 && !seq4) { set_error("svb_sfs_batch_bam4: null sequence buffer"); return SVB_EINVAL; }
+  cudaEvent_t e0, e1;
+  SVB_CUDA(cudaEventCreate(&e0));
+  SVB_CUDA(cudaEventCreate(&e1));
+  SVB_CUDA(cudaEventRecord(e0, 0));
+  const char* ns = getenv("SVB_NO_STREAM");
+  int64_t stream_min = (int64_t)32 << 20;
+  if (const char* e = getenv("SVB_STREAM_MIN_BYTES")) stream_min = atoll(e);
+  const bool stream = offs[n_reads] >= stream_min && !(ns && *ns == '1');
+  int rc = SVB_OK;
+  if (n_reads == 0 || offs[n_reads] == 0) {
+    out->n_reads = n_reads;
+    out->offs = (int64_t*)calloc((size_t)n_reads + 1, sizeof(int64_t));
+    if (!out->offs) { set_error("out of host memory"); rc = SVB_ENOMEM; }
+  } else {
+    rc = sfs_batch_streamed(idx, seq4, offs.data(), n_reads, overlap, assemble, out, seq4_offs, stream);
+  }
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&out->device_ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc != SVB_OK) svb_sfs_out_free(out);
+  return rc;
+}
+
+// test / bench utility: nt6 bytes (device) -> BAM-native 4-bit reads (device), every read starting
+// on a byte boundary; out_offs[r] = sum over earlier reads of (len + 1) / 2
+__global__ void k_pack4(const uint8_t* __restrict__ seq, const int64_t* __restrict__ offs, const int64_t* __restrict__ poffs,
+                        int64_t n, uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += nwarps) {
+    const int64_t o = offs[r], l = offs[r + 1] - o, pb = poffs[r];
+    for (int64_t b = lane; b < (l + 1) / 2; b += 32) {
+      auto enc = [](uint8_t c) -> unsigned { return c == 1 ? 1u : c == 2 ? 2u : c == 3 ? 4u : c == 4 ? 8u : 15u; };
+      const unsigned hi = enc(seq[o + 2 * b]), lo = (2 * b + 1 < l) ? enc(seq[o + 2 * b + 1]) : 0u;
+      out[pb + b] = (uint8_t)((hi << 4) | lo);
+    }
+  }
+}
+int svb_pack4_device(const uint8_t* d_seq, const int64_t* d_offs, const int64_t* d_seq4_offs, int64_t n_reads, int device,
+                     uint8_t* d_out) {
+  SVB_TRY(check_device(device));
+  if (n_reads <= 0) return SVB_OK;
+  k_pack4<<<(unsigned)std::min<int64_t>((n_reads + 3) / 4, 148 * 16), 128>>>(d_seq, d_offs, d_seq4_offs, n_reads, d_out);
+  SVB_CUDA(cudaGetLastError());
+  SVB_CUDA(cudaDeviceSynchronize());
+  return SVB_OK;
 }
 
 void svb_sfs_out_free(svb_sfs_out_t* out) {

@@ -277,3 +277,42 @@ def test_located_match_mode_equals_rank_walk(monkeypatch):
     idx_b = capi.Index.from_bwt(bwt, block_bytes=128)
     got_b, res_b = _gpu_sfs(idx_b, reads, assemble=False)
     assert got_b == exp and res_b.n_text_ext == 0
+
+
+def test_bam4_packed_input_matches_byte_input(monkeypatch):
+    """svb_sfs_batch_bam4: reads handed over as BAM stores them (4-bit nt16, byte-aligned per read) are
+    decoded on the GPU (ping_pong.cpp:90-94) and must give the oracle's SFS sets: odd and even lengths,
+    empty reads, N and IUPAC codes (all -> code 5), plain upload and the streamed path with tiny chunks
+    (chunk boundaries inside reads and inside bytes)."""
+    contigs = synth.make_reference(500_000, seed=51, contigs=3)
+    reads = synth.make_reads(contigs, 400, seed=52, mean_len=7000, sd_len=2500, min_len=150, max_len=18000)
+    reads += synth.make_reads(contigs, 40, seed=53, mean_len=3001, sd_len=400, min_len=301, max_len=5001, raw_hifi=True)
+    reads.insert(5, np.zeros(0, np.uint8))
+    reads.insert(77, reads[10][:1].copy())
+    reads[20] = reads[20].copy(); reads[20][100:104] = 5
+    T, SA, bwt = oracle_index(contigs)
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs, block_bytes=128)
+    exp, ext = fm_results(oracle.FMIndex(bwt), reads)
+    seq4, s4o, lq = capi.pack_bam4(reads)
+    seq4 = seq4.copy()
+    # an IUPAC code (R = 5) where read 20 has its N run decodes to N as well
+    b = int(s4o[20]) + 50
+    seq4[b] = (5 << 4) | 5
+    monkeypatch.setenv("SVB_NO_STREAM", "1")
+    res = idx.sfs_batch_bam4(seq4, s4o, lq, assemble=False)
+    assert [res.per_read(i) for i in range(len(reads))] == exp and res.n_ext == ext
+    assert res.h2d_bytes < sum(len(r) for r in reads) * 0.6 + 16 * len(reads) + 64
+    monkeypatch.delenv("SVB_NO_STREAM")
+    monkeypatch.setenv("SVB_STREAM_MIN_BYTES", "1")
+    for chunk in ("65536", "100032"):
+        monkeypatch.setenv("SVB_STREAM_CHUNK_BYTES", chunk)
+        for assemble in (False, True):
+            res = idx.sfs_batch_bam4(seq4, s4o, lq, assemble=assemble)
+            got = [res.per_read(i) for i in range(len(reads))]
+            assert got == (exp if not assemble else [oracle.assemble(e) for e in exp])
+            assert res.n_ext == ext
+    empty = idx.sfs_batch_bam4(np.zeros(0, np.uint8), np.zeros(1, np.int64), np.zeros(0, np.int32))
+    assert empty.n_reads == 0 and empty.n_sfs == 0
+    with pytest.raises(capi.SvbError):
+        idx.sfs_batch_bam4(seq4, s4o, lq + 4)          # lengths that do not fit their packed bytes
