@@ -6,7 +6,9 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -57,6 +59,97 @@ class GzSource {
   }
  private:
   gzFile f_;
+};
+
+// BGZF byte source with parallel inflate: BGZF members (<= 64 KiB each, size in the BC extra field)
+// are independent deflate streams, so a window of them is read sequentially and inflated by all
+// host threads at once -- the reference does the same through htslib's bgzf_mt(.., 8, ..)
+// (ping_pong.cpp:249, clusterer.cpp:13).  Files that are not BGZF go through plain zlib.
+class BgzfSource {
+ public:
+  explicit BgzfSource(const std::string& path) : f_(fopen(path.c_str(), "rb")) {
+    if (!f_) return;
+    uint8_t h[18];
+    const size_t got = fread(h, 1, 18, f_);
+    bgzf_ = got == 18 && h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
+    if (bgzf_) fseek(f_, 0, SEEK_SET);
+    else { fclose(f_); f_ = nullptr; plain_.reset(new GzSource(path)); }
+  }
+  ~BgzfSource() { if (f_) fclose(f_); }
+  bool ok() const { return bgzf_ ? f_ != nullptr : (plain_ && plain_->ok()); }
+  bool read_exact(void* dst, size_t n) {
+    if (!bgzf_) return plain_->read_exact(dst, n);
+    uint8_t* p = static_cast<uint8_t*>(dst);
+    while (n) {
+      if (pos_ == out_.size() && !refill()) return false;
+      const size_t k = std::min(n, out_.size() - pos_);
+      memcpy(p, out_.data() + pos_, k);
+      p += k; pos_ += k; n -= k;
+    }
+    return true;
+  }
+ private:
+  bool refill() {
+    struct Blk { size_t in_off, in_len, out_off, out_len; };
+    std::vector<Blk> blks;
+    in_.clear();
+    size_t out_total = 0;
+    const size_t window = (size_t)64 << 20;   // compressed bytes per refill
+    while (in_.size() < window) {
+      uint8_t h[18];
+      const size_t got = fread(h, 1, 18, f_);
+      if (got == 0) break;
+      if (got != 18 || h[0] != 31 || h[1] != 139 || !(h[3] & 4)) return false;
+      // walk the extra field for the BC subfield (SAM spec 4.1)
+      const unsigned xlen = h[10] | (h[11] << 8);
+      std::vector<uint8_t> extra(xlen);
+      memcpy(extra.data(), h + 12, std::min<size_t>(6, xlen));
+      if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != xlen - 6) return false;
+      int bsize = -1;
+      for (size_t o = 0; o + 4 <= xlen;) {
+        const unsigned sl = extra[o + 2] | (extra[o + 3] << 8);
+        if (extra[o] == 'B' && extra[o + 1] == 'C' && sl == 2 && o + 6 <= xlen) bsize = extra[o + 4] | (extra[o + 5] << 8);
+        o += 4 + sl;
+      }
+      if (bsize < 0) return false;
+      const size_t total = (size_t)bsize + 1, head = 12 + xlen;
+      if (total < head + 8) return false;
+      const size_t body = total - head;       // deflate data + CRC32 + ISIZE
+      const size_t at = in_.size();
+      in_.resize(at + body);
+      if (fread(in_.data() + at, 1, body, f_) != body) return false;
+      uint32_t isize;
+      memcpy(&isize, in_.data() + at + body - 4, 4);
+      if (isize > (1u << 16)) return false;
+      blks.push_back(Blk{at, body - 8, out_total, isize});
+      out_total += isize;
+    }
+    if (blks.empty()) return false;
+    out_.resize(out_total);
+    pos_ = 0;
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : bad)
+    for (long long i = 0; i < (long long)blks.size(); ++i) {
+      const Blk& b = blks[(size_t)i];
+      if (b.out_len == 0) continue;
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, -15) != Z_OK) { ++bad; continue; }
+      zs.next_in = in_.data() + b.in_off; zs.avail_in = (uInt)b.in_len;
+      zs.next_out = out_.data() + b.out_off; zs.avail_out = (uInt)b.out_len;
+      const int rc = inflate(&zs, Z_FINISH);
+      if (rc != Z_STREAM_END || zs.avail_out != 0) ++bad;
+      inflateEnd(&zs);
+    }
+    return bad == 0 && out_total > 0 ? true : (bad == 0 && refill_empty_ok());
+  }
+  // a window holding only empty members (the EOF marker): keep reading
+  bool refill_empty_ok() { return !feof(f_) && refill(); }
+  FILE* f_ = nullptr;
+  bool bgzf_ = false;
+  std::unique_ptr<GzSource> plain_;
+  std::vector<uint8_t> in_, out_;
+  size_t pos_ = 0;
 };
 
 struct FastxRecord { std::string name, seq; };
@@ -208,7 +301,7 @@ class BamReader {
     return 1;
   }
  private:
-  GzSource src_;
+  BgzfSource src_;
   bool ok_ = false, want_align_ = false;
   std::string text_;
   std::vector<std::string> ref_names_;

@@ -137,25 +137,30 @@ static int run_index(const Config& c, const vector<string>& pos) {
   return EXIT_SUCCESS;
 }
 
-struct PendingRead { string qname; int hp; int64_t lo, hi; bool search; };
+struct PendingRead { string qname; int hp; int64_t lo, hi; bool search; int32_t l_qseq; };
 
-// one GPU submission covering many logical batches; prints in the reference's order
+// one GPU submission covering many logical batches; prints in the reference's order.
+// packed == false: `cat` holds one nt6 byte per base (FASTX);  packed == true: `cat` holds the reads
+// as the BAM stores them (4 bits per base) and the decode of ping_pong.cpp:90-94 runs on the GPU.
 static bool flush(svb_index_t* idx, const Config& c, vector<PendingRead>& reads, vector<uint8_t>& cat,
-                  uint64_t& total_sfs) {
+                  uint64_t& total_sfs, bool packed) {
   if (reads.empty()) return true;
   vector<int64_t> offs(1, 0);
+  vector<int32_t> lq;
   vector<uint8_t> sub;
   vector<int64_t> slot_of(reads.size(), -1);
   int64_t n = 0;
   // reads filtered by the XF rule keep their slot but are not searched (ping_pong.cpp:202-203)
   for (size_t i = 0; i < reads.size(); ++i)
-    if (reads[i].search) { slot_of[i] = n++; offs.push_back(offs.back() + (reads[i].hi - reads[i].lo)); }
+    if (reads[i].search) { slot_of[i] = n++; offs.push_back(offs.back() + (reads[i].hi - reads[i].lo)); lq.push_back(reads[i].l_qseq); }
   sub.reserve((size_t)offs.back());
   for (size_t i = 0; i < reads.size(); ++i)
     if (reads[i].search) sub.insert(sub.end(), cat.begin() + reads[i].lo, cat.begin() + reads[i].hi);
   svb_sfs_out_t out;
-  if (svb_sfs_batch(idx, sub.data(), offs.data(), n, c.overlap, c.assemble ? 1 : 0, &out) != SVB_OK) {
-    logmsg("critical", string("svb_sfs_batch: ") + svb_last_error());
+  const int rc = packed ? svb_sfs_batch_bam4(idx, sub.data(), offs.data(), lq.data(), n, c.overlap, c.assemble ? 1 : 0, &out)
+                        : svb_sfs_batch(idx, sub.data(), offs.data(), n, c.overlap, c.assemble ? 1 : 0, &out);
+  if (rc != SVB_OK) {
+    logmsg("critical", string(packed ? "svb_sfs_batch_bam4: " : "svb_sfs_batch: ") + svb_last_error());
     return false;
   }
   string line;
@@ -199,8 +204,9 @@ static int run_search(const Config& c) {
   vector<PendingRead> reads;
   vector<uint8_t> cat;
   uint64_t total_sfs = 0, processed = 0;
+  const bool packed = !c.bam.empty();   // BAM records are handed to the GPU as stored: 4 bits per base
   auto maybe_flush = [&]() {
-    if (cat.size() >= gpu_bases && reads.size() % (size_t)c.bsize == 0) return flush(idx, c, reads, cat, total_sfs);
+    if (cat.size() >= (packed ? gpu_bases / 2 : gpu_bases) && reads.size() % (size_t)c.bsize == 0) return flush(idx, c, reads, cat, total_sfs, packed);
     return true;
   };
   logmsg("info", "Extracting SFS strings on GPU " + to_string(c.device) + " (ordering as with " + to_string(c.threads) + " threads)..");
@@ -208,6 +214,7 @@ static int run_search(const Config& c) {
   if (!c.bam.empty()) {
     BamReader bam(c.bam);
     if (!bam.ok()) { logmsg("critical", "cannot read BAM " + c.bam); svb_index_free(idx); return EXIT_FAILURE; }
+    bam.want_alignment(true);   // keep the packed sequence; no host-side decode
     BamRecord r;
     int st;
     while (ok && (st = bam.next(r)) == 1) {
@@ -219,8 +226,8 @@ static int run_search(const Config& c) {
       }
       if (r.tid < 0) { logmsg("critical", "core.tid < 0. Why are we here? Please check"); svb_index_free(idx); exit(1); }  // :76-79
       const int xf = r.has_xf ? (int)r.xf : 0, hp = r.has_hp ? (int)r.hp : 0; // :196-201
-      PendingRead pr{r.qname, hp, (int64_t)cat.size(), 0, !(c.putative && xf != 0)};
-      cat.insert(cat.end(), r.nt6.begin(), r.nt6.end());
+      PendingRead pr{r.qname, hp, (int64_t)cat.size(), 0, !(c.putative && xf != 0), r.l_qseq};
+      cat.insert(cat.end(), r.seq4.begin(), r.seq4.end());
       pr.hi = (int64_t)cat.size();
       reads.push_back(pr);
       ok = maybe_flush();
@@ -234,14 +241,14 @@ static int run_search(const Config& c) {
     const uint8_t* t6 = nt6_table();
     while (ok && fx.next(r)) {
       ++processed;
-      PendingRead pr{r.name, 0, (int64_t)cat.size(), 0, true};
+      PendingRead pr{r.name, 0, (int64_t)cat.size(), 0, true, (int32_t)r.seq.size()};
       for (char ch : r.seq) cat.push_back(t6[(uint8_t)ch]);                  // rb3_char2nt6, ping_pong.cpp:158
       pr.hi = (int64_t)cat.size();
       reads.push_back(pr);
       ok = maybe_flush();
     }
   }
-  if (ok) ok = flush(idx, c, reads, cat, total_sfs);
+  if (ok) ok = flush(idx, c, reads, cat, total_sfs, packed);
   fflush(stdout);
   svb_index_free(idx);
   if (!ok) return EXIT_FAILURE;
