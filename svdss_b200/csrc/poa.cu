@@ -43,6 +43,7 @@ struct PoaParams {
   int32_t* cons_len;
   int32_t* status;
   unsigned long long* cells;
+  unsigned long long* phase;   // SVB_POA_TIMING: clock cycles per phase, summed over warps (lane 0)
   int match, mismatch, o1, e1, o2, e2, wb;
   float wf;
 };
@@ -108,7 +109,10 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
   return v;
 }
 
-__global__ void __launch_bounds__(128) k_poa(const PoaParams P) {
+#ifndef SVB_POA_MINB
+#define SVB_POA_MINB 6
+#endif
+__global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   const int lane = threadIdx.x & 31;
   const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint8_t* wsp = P.ws + (int64_t)slot * P.ws_stride;
@@ -128,6 +132,8 @@ __global__ void __launch_bounds__(128) k_poa(const PoaParams P) {
     g.n = 0; g.ne = 0; g.overflow = false;
     int status = POA_OK;
     unsigned long long cells = 0;
+    long long t_setup = 0, t_dp = 0, t_tb = 0, t_upd = 0, t_cons = 0, tc = clock64();
+#define PHASE(acc) do { if (P.phase) { const long long _n = clock64(); acc += _n - tc; tc = _n; } } while (0)
     if (lane == 0) { g.node(0); g.node(0); }  // source, sink
     g.n = 2;
     __syncwarp();
@@ -174,6 +180,7 @@ __global__ void __launch_bounds__(128) k_poa(const PoaParams P) {
       }
       __syncwarp();
       const int w = P.wb + (int)(P.wf * (float)ql);
+      PHASE(t_setup);
       // ---- source row
       {
         int end0 = min(w, ql);
@@ -284,6 +291,7 @@ __global__ void __launch_bounds__(128) k_poa(const PoaParams P) {
         }
         __syncwarp();
       }
+      PHASE(t_dp);
       // ---- end point, traceback, graph update, re-rank: lane 0
       if (lane == 0) {
         int best_p = -1, best = PNEG - 1;
@@ -321,6 +329,7 @@ __global__ void __launch_bounds__(128) k_poa(const PoaParams P) {
             }
           }
         }
+        PHASE(t_tb);
         // graph update (abpoa_add_graph_alignment), forward order
         int n_new = 0, prev = 0, anchor = 0;
         const int n_old = N;
@@ -370,6 +379,7 @@ __global__ void __launch_bounds__(128) k_poa(const PoaParams P) {
           }
         }
       }
+      PHASE(t_upd);
       // lane 0's graph size / overflow flag are the truth
       g.n = __shfl_sync(0xffffffffu, g.n, 0);
       g.ne = __shfl_sync(0xffffffffu, g.ne, 0);
@@ -404,6 +414,12 @@ __global__ void __launch_bounds__(128) k_poa(const PoaParams P) {
       P.cons_len[cid] = len;
       P.status[cid] = status;
       atomicAdd(P.cells, cells);
+      PHASE(t_cons);
+      if (P.phase) {
+        atomicAdd(P.phase + 0, (unsigned long long)t_setup); atomicAdd(P.phase + 1, (unsigned long long)t_dp);
+        atomicAdd(P.phase + 2, (unsigned long long)t_tb); atomicAdd(P.phase + 3, (unsigned long long)t_upd);
+        atomicAdd(P.phase + 4, (unsigned long long)t_cons);
+      }
     }
     __syncwarp();
   }
@@ -451,6 +467,7 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
   int32_t *d_len = nullptr, *d_status = nullptr;
   unsigned int* d_work = nullptr;
   unsigned long long* d_cells = nullptr;
+  unsigned long long* d_phase = nullptr;
   int rc = SVB_OK;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   std::vector<int64_t> so((size_t)n_seqs + 1);
@@ -481,6 +498,7 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
     PCHECK(cudaMalloc((void**)&d_work, 4));
     PCHECK(cudaMalloc((void**)&d_cells, 8));
     PCHECK(cudaMemset(d_cells, 0, 8));
+    if (getenv("SVB_POA_TIMING")) { PCHECK(cudaMalloc((void**)&d_phase, 40)); PCHECK(cudaMemset(d_phase, 0, 40)); }
     if (s_total) PCHECK(cudaMemcpy(d_seqs, seqs + s_first, s_total, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_soff, so.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_coff, cluster_offs, (n_clusters + 1) * 8, cudaMemcpyHostToDevice));
@@ -519,7 +537,7 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
       const int64_t stride = poa_ws_carve(nullptr, ncap, (int)ecap, wcap, lmax, nullptr);
       size_t free_b = 0, total_b = 0;
       PCHECK(cudaMemGetInfo(&free_b, &total_b));
-      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * 16);
+      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * 4 * SVB_POA_MINB);
       const char* eb = getenv("SVB_POA_WS_BYTES");
       const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
       slots = std::min<int64_t>(slots, std::max<int64_t>(1, budget / stride));
@@ -533,7 +551,7 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
       memset(&P, 0, sizeof(P));
       P.seqs = d_seqs; P.seq_offs = d_soff; P.cluster_offs = d_coff; P.order = d_order; P.n = (int)todo.size();
       P.work = d_work; P.ws = d_ws; P.ws_stride = stride; P.ncap = ncap; P.ecap = (int)ecap; P.wcap = wcap; P.lmax = lmax;
-      P.cons = d_cons; P.cons_off = d_capoff; P.cons_len = d_len; P.status = d_status; P.cells = d_cells;
+      P.cons = d_cons; P.cons_off = d_capoff; P.cons_len = d_len; P.status = d_status; P.cells = d_cells; P.phase = d_phase;
       P.match = 2; P.mismatch = 4; P.o1 = 4; P.e1 = 2; P.o2 = 24; P.e2 = 1; P.wb = 10; P.wf = 0.01f;  // abpoa_init_para
       cudaEvent_t k0, k1;
       PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
@@ -563,6 +581,13 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
     unsigned long long cells = 0;
     PCHECK(cudaMemcpy(&cells, d_cells, 8, cudaMemcpyDeviceToHost));
     out->cells = (int64_t)cells;
+    if (d_phase) {
+      unsigned long long ph[5];
+      PCHECK(cudaMemcpy(ph, d_phase, 40, cudaMemcpyDeviceToHost));
+      const double tot = (double)(ph[0] + ph[1] + ph[2] + ph[3] + ph[4]);
+      fprintf(stderr, "[k_poa phases, %% of warp cycles] setup %.1f  dp rows %.1f  traceback %.1f  graph update + re-rank %.1f  consensus %.1f\n",
+              100 * ph[0] / tot, 100 * ph[1] / tot, 100 * ph[2] / tot, 100 * ph[3] / tot, 100 * ph[4] / tot);
+    }
     out->d2h_bytes = cap_off[n_clusters] + n_clusters * 8;
     for (int64_t c = 0; c < n_clusters; ++c) out->cons_offs[c + 1] = out->cons_offs[c] + h_len[c];
     out->cons = (uint8_t*)malloc((size_t)std::max<int64_t>(out->cons_offs[n_clusters], 1));
@@ -579,7 +604,7 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
 done:
 #undef PCHECK
   cudaFree(d_seqs); cudaFree(d_ws); cudaFree(d_cons); cudaFree(d_soff); cudaFree(d_coff); cudaFree(d_capoff);
-  cudaFree(d_order); cudaFree(d_len); cudaFree(d_status); cudaFree(d_work); cudaFree(d_cells);
+  cudaFree(d_order); cudaFree(d_len); cudaFree(d_status); cudaFree(d_work); cudaFree(d_cells); cudaFree(d_phase);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (rc != SVB_OK) svb_poa_out_free(out);

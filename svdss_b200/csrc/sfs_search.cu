@@ -27,6 +27,7 @@ struct svb_reads {
   uint8_t* d_seq = nullptr;    // padded to 64 B beyond total
   int64_t* d_offs = nullptr;   // n_reads + 1
   uint32_t* d_order = nullptr; // read indices, longest first
+  ulonglong2* d_sched = nullptr; // hand-out order: {offset, len << 32 | read index} (one 16-byte load per read)
   bool owns_seq = true;
   int64_t max_len = 0;
 };
@@ -62,6 +63,7 @@ struct SearchParams {
   const uint8_t* __restrict__ seq;
   const int64_t* __restrict__ offs;
   const uint32_t* __restrict__ order;
+  const ulonglong2* __restrict__ sched;  // hand-out slot w -> {offs[r], len << 32 | r}; nullptr: use order / offs
   int64_t n_reads;
   int overlap;
   int assemble;
@@ -987,16 +989,19 @@ __device__ __forceinline__ void cpa_fetch_sparse(const SearchParams& P, uint32_t
   unsigned m = __ballot_sync(0xffffffffu, bk != NOBLK);
   const int sub = lane >> 3, j = lane & 7;
   while (m) {
-    const unsigned t = __fns(m, 0, sub + 1);   // the sub-th pending lane of this round (0xffffffff: none)
-    const bool on = t < 32u;
-    const uint32_t xk = __shfl_sync(0xffffffffu, bk, on ? (int)t : 0);
-    const uint32_t xl = __shfl_sync(0xffffffffu, bl, on ? (int)t : 0);
+    // the four lowest pending lanes of this round (warp-uniform), one per 8-lane group
+    const unsigned m1 = m & (m - 1), m2 = m1 & (m1 - 1), m3 = m2 & (m2 - 1);
+    const unsigned pick = sub == 0 ? m : sub == 1 ? m1 : sub == 2 ? m2 : m3;
+    const bool on = pick != 0u;
+    const unsigned t = on ? (unsigned)(__ffs((int)pick) - 1) : 0u;
+    const uint32_t xk = __shfl_sync(0xffffffffu, bk, (int)t);
+    const uint32_t xl = __shfl_sync(0xffffffffu, bl, (int)t);
     if (on) {
       const uint32_t dst = warp_stage_s + (uint32_t)(t * 256u + ((j + t) & 7u) * 16u);
       cp_async16(dst, P.blocks + (uint64_t)xk * 8 + j);
       if (xl != xk) cp_async16(dst + 128u, P.blocks + (uint64_t)xl * 8 + j);
     }
-    m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;
+    m = m3 & (m3 - 1);
   }
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncwarp();
@@ -1108,9 +1113,14 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
       if (!have) {
         const unsigned long long w = atomicAdd(P.work, 1ull);
         if (w >= (unsigned long long)P.n_reads) { alive = false; break; }
-        ridx = P.order ? P.order[w] : (uint32_t)w;
-        roff = P.offs[ridx];
-        len = (int)(P.offs[ridx + 1] - roff);
+        if (P.sched) {
+          const ulonglong2 e = __ldg(P.sched + w);
+          roff = (int64_t)e.x; ridx = (uint32_t)e.y; len = (int)(e.y >> 32);
+        } else {
+          ridx = P.order ? P.order[w] : (uint32_t)w;
+          roff = P.offs[ridx];
+          len = (int)(P.offs[ridx + 1] - roff);
+        }
         if (len <= 0) continue;
         if (P.ready) {  // streamed batch: wait until the chunk holding the last base landed
           if (!wait_chunk(P.ready + (roff + len - 1) / P.chunk_bytes, P.stats + 3)) { alive = false; break; }
@@ -1187,10 +1197,21 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     // ---- (2) issue: every load of this iteration leaves from here
     Win32 rw, tw;
     uint64_t one = 0;
-    if (op == OP_TXT || op == OP_KMER) {
-      const int64_t a0 = roff + (op == OP_TXT ? pos + (phase ? 1 : -32) : (phase ? pos : pos - K + 1));
-      load32(P.seq, a0, rw, 0);
-      if (op == OP_TXT) load32(P.text, a0 + delta, tw, -(int64_t)(TEXT_PAD / 16));
+    int skip = 0;
+    if (op == OP_TXT) {
+      // 32-byte window on the READ's 16-byte grid (two aligned loads, no shifting): forward it starts
+      // at or below the next base, backward it ends at or above the last matched one; `skip` bytes
+      // of it lie behind the walk.  The text side is wherever delta puts it (three loads + funnel).
+      const int64_t g = roff + pos;
+      const int64_t a0 = phase ? ((g + 1) & ~15LL) : (((g + 15) & ~15LL) - 32);
+      skip = phase ? (int)(g + 1 - a0) : (int)(a0 + 32 - g);
+      const uint4* rp = reinterpret_cast<const uint4*>(P.seq);
+      const int64_t qi = a0 >> 4;
+      rw.q0 = __ldcg(rp + max(qi, (int64_t)0));
+      rw.q1 = __ldcg(rp + max(qi + 1, (int64_t)0));
+      load32(P.text, a0 + delta, tw, -(int64_t)(TEXT_PAD / 16));
+    } else if (op == OP_KMER) {
+      load32(P.seq, roff + (phase ? pos : pos - K + 1), rw, 0);
     } else if (op == OP_KMT) {
       one = __ldg(P.kmt + kcode);
     } else if (op == OP_SSA) {
@@ -1207,23 +1228,25 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
       ++n_ext;
       n_blk += two ? 2u : 1u;
     } else if (op == OP_TXT) {
-      uint64_t r[4], t[4];
-      win32_words(rw, r);
+      uint64_t t[4];
       win32_words(tw, t);
-      const uint64_t x0 = r[0] ^ t[0], x1 = r[1] ^ t[1], x2 = r[2] ^ t[2], x3 = r[3] ^ t[3];
-      int nb, mt;  // bases available in walking direction (<= 32), leading bases that match
-      if (phase) {
-        nb = min(32, len - 1 - pos);
-        mt = x0 ? (__ffsll((long long)x0) - 1) >> 3
+      uint64_t x0 = ((uint64_t)rw.q0.x | ((uint64_t)rw.q0.y << 32)) ^ t[0], x1 = ((uint64_t)rw.q0.z | ((uint64_t)rw.q0.w << 32)) ^ t[1];
+      uint64_t x2 = ((uint64_t)rw.q1.x | ((uint64_t)rw.q1.y << 32)) ^ t[2], x3 = ((uint64_t)rw.q1.z | ((uint64_t)rw.q1.w << 32)) ^ t[3];
+      int nb, mt;  // bases available in walking direction (<= 32 - skip), leading bases that match
+      if (phase) {           // bytes 0 .. skip-1 of the window are behind the walk: make them match
+        if (skip >= 8) { x0 = 0; x1 &= ~0ull << (8 * (skip - 8)); } else { x0 &= ~0ull << (8 * skip); }
+        nb = min(32 - skip, len - 1 - pos);
+        mt = (x0 ? (__ffsll((long long)x0) - 1) >> 3
            : x1 ? 8 + ((__ffsll((long long)x1) - 1) >> 3)
            : x2 ? 16 + ((__ffsll((long long)x2) - 1) >> 3)
-           : x3 ? 24 + ((__ffsll((long long)x3) - 1) >> 3) : 32;
-      } else {
-        nb = min(32, pos);
-        mt = x3 ? __clzll((long long)x3) >> 3
+           : x3 ? 24 + ((__ffsll((long long)x3) - 1) >> 3) : 32) - skip;
+      } else {               // bytes 32-skip .. 31 are behind the walk
+        if (skip >= 8) { x3 = 0; x2 &= ~0ull >> (8 * (skip - 8)); } else { x3 &= ~0ull >> (8 * skip); }
+        nb = min(32 - skip, pos);
+        mt = (x3 ? __clzll((long long)x3) >> 3
            : x2 ? 8 + (__clzll((long long)x2) >> 3)
            : x1 ? 16 + (__clzll((long long)x1) >> 3)
-           : x0 ? 24 + (__clzll((long long)x0) >> 3) : 32;
+           : x0 ? 24 + (__clzll((long long)x0) >> 3) : 32) - skip;
       }
       const int dir = phase ? 1 : -1;
       if (mt >= nb) {          // all nb extensions succeed (the interval stays of size 1)
@@ -1360,6 +1383,15 @@ __global__ void k_read_keys(const int64_t* __restrict__ offs, int64_t n, int64_t
   vals[i] = (uint32_t)i;
 }
 
+__global__ void k_make_sched(const uint32_t* __restrict__ order, const int64_t* __restrict__ offs, int64_t n,
+                             ulonglong2* __restrict__ sched) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = order[i];
+  const int64_t b = offs[r], l = offs[r + 1] - b;
+  sched[i] = make_ulonglong2((unsigned long long)b, ((unsigned long long)(l > 0x7fffffffLL ? 0x7fffffffLL : l) << 32) | r);
+}
+
 // read indices in hand-out order: longest first (within a chunk when the batch is streamed)
 static int make_order(svb_reads* R, int64_t chunk_bytes, cudaStream_t st) {
   int64_t n = R->n_reads;
@@ -1376,6 +1408,9 @@ static int make_order(svb_reads* R, int64_t chunk_bytes, cudaStream_t st) {
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, k1, k2, v1, R->d_order, n, 0, 64, st);
   SVB_CUDA(pmalloc(&tmp, bytes, st));
   SVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, k1, k2, v1, R->d_order, n, 0, 64, st));
+  SVB_CUDA(pmalloc((void**)&R->d_sched, n * 16, st));
+  k_make_sched<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->d_order, R->d_offs, n, R->d_sched);
+  SVB_CUDA(cudaGetLastError());
   pfree(tmp, st); pfree(k1, st); pfree(k2, st); pfree(v1, st);
   SVB_CUDA(cudaStreamSynchronize(st));
   return SVB_OK;
@@ -1540,7 +1575,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
 
   SearchParams P;
   fill_params(P, d);
-  P.seq = R->d_seq; P.offs = R->d_offs; P.order = R->d_order; P.n_reads = n_reads;
+  P.seq = R->d_seq; P.offs = R->d_offs; P.order = R->d_order; P.sched = R->d_sched; P.n_reads = n_reads;
   P.overlap = overlap; P.assemble = assemble;
   SearchScratch S;
   S.st = st;
@@ -1729,6 +1764,7 @@ void svb_reads_free(svb_reads_t* R) {
   if (R->owns_seq && R->d_seq) pfree(R->d_seq, 0);
   pfree(R->d_offs, 0);
   pfree(R->d_order, 0);
+  pfree(R->d_sched, 0);
   delete R;
 }
 
@@ -1858,7 +1894,7 @@ done:
 #undef SCHECK
   if (src.copy_stream) { cudaStreamSynchronize(src.copy_stream); cudaStreamDestroy(src.copy_stream); }
   if (comp) {
-    pfree(R.d_seq, comp); pfree(R.d_offs, comp); pfree(R.d_order, comp); pfree(src.d_ready, comp);
+    pfree(R.d_seq, comp); pfree(R.d_offs, comp); pfree(R.d_order, comp); pfree(R.d_sched, comp); pfree(src.d_ready, comp);
     pfree(src.d_seq4, comp); pfree(d_s4o, comp); pfree(src.d_chunk_r, comp); pfree(src.d_arrived, comp); pfree(src.d_done, comp);
     cudaStreamSynchronize(comp);
     cudaStreamDestroy(comp);

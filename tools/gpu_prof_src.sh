@@ -13,5 +13,5 @@ SVB_PROFILE=1 timeout ${NCU_TIMEOUT:-900} ncu --profile-from-start off --clock-c
 tail -3 gpurun_out/prof_bench_$TAG.log | cut -c1-300
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --csv > gpurun_out/prof_${TAG}_source.csv 2>/dev/null
-rm -f gpurun_out/prof_$TAG.ncu-rep
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --print-source cuda --csv > gpurun_out/prof_${TAG}_cuda.csv 2>/dev/null
 ls -la gpurun_out | tail -4
