@@ -152,6 +152,62 @@ class BgzfSource {
   size_t pos_ = 0;
 };
 
+// BGZF writer with parallel deflate (the reference writes its smoothed BAM through htslib with
+// bgzf_mt(.., 8, ..), smoother.cpp:362-363): payload is cut into 0xff00-byte members like htslib,
+// a window of them is deflated by all host threads, then written in order; close() adds the EOF member.
+class BgzfWriter {
+ public:
+  explicit BgzfWriter(FILE* f, int level = 6) : f_(f), level_(level) {}
+  bool write(const void* p, size_t n) {
+    const uint8_t* b = static_cast<const uint8_t*>(p);
+    buf_.insert(buf_.end(), b, b + n);
+    return buf_.size() < ((size_t)64 << 20) || flush(false);
+  }
+  bool close() {
+    if (!flush(true)) return false;
+    static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    return fwrite(eof, 1, 28, f_) == 28 && fflush(f_) == 0;
+  }
+ private:
+  bool flush(bool all) {
+    const size_t BS = 0xff00;
+    const size_t nblk = all ? (buf_.size() + BS - 1) / BS : buf_.size() / BS;
+    if (nblk == 0) return true;
+    std::vector<std::vector<uint8_t>> out(nblk);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : bad)
+    for (long long i = 0; i < (long long)nblk; ++i) {
+      const size_t o = (size_t)i * BS, len = std::min(BS, buf_.size() - o);
+      std::vector<uint8_t>& m = out[(size_t)i];
+      m.resize(18 + compressBound((uLong)len) + 8);
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ++bad; continue; }
+      zs.next_in = const_cast<uint8_t*>(buf_.data() + o); zs.avail_in = (uInt)len;
+      zs.next_out = m.data() + 18; zs.avail_out = (uInt)(m.size() - 26);
+      const int rc = deflate(&zs, Z_FINISH);
+      const size_t clen = zs.total_out;
+      deflateEnd(&zs);
+      if (rc != Z_STREAM_END || 18 + clen + 8 > 65536) { ++bad; continue; }
+      const uint8_t head[16] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0};
+      memcpy(m.data(), head, 16);
+      const uint16_t bsize = (uint16_t)(18 + clen + 8 - 1);
+      memcpy(m.data() + 16, &bsize, 2);
+      const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_.data() + o, (uInt)len), isz = (uint32_t)len;
+      memcpy(m.data() + 18 + clen, &crc, 4);
+      memcpy(m.data() + 18 + clen + 4, &isz, 4);
+      m.resize(18 + clen + 8);
+    }
+    if (bad) return false;
+    for (const auto& m : out) if (fwrite(m.data(), 1, m.size(), f_) != m.size()) return false;
+    buf_.erase(buf_.begin(), buf_.begin() + (std::ptrdiff_t)std::min(buf_.size(), nblk * BS));
+    return true;
+  }
+  FILE* f_;
+  int level_;
+  std::vector<uint8_t> buf_;
+};
+
 struct FastxRecord { std::string name, seq; };
 
 // kseq-style reader (fastq.hpp / kseq.h): multi-line FASTA and FASTQ
@@ -195,6 +251,9 @@ struct BamRecord {
   std::vector<uint8_t> seq4;   // 4-bit packed sequence, as stored (Clusterer decodes it on demand)
   bool has_xf = false, has_hp = false;
   int64_t xf = 0, hp = 0;
+  // raw mode (`smooth`): the record body as stored (without its 4-byte length) and where its parts start
+  std::vector<uint8_t> raw;
+  size_t off_cigar = 0, off_seq = 0, off_qual = 0, off_aux = 0;
   // bam_endpos: pos + reference span of the CIGAR (M,D,N,=,X); pos+1 for an empty span
   int32_t endpos() const {
     int64_t span = 0;
@@ -231,6 +290,10 @@ class BamReader {
   const std::vector<std::string>& ref_names() const { return ref_names_; }
   // alignment mode (`call`): keep CIGAR + packed sequence instead of decoding nt6 codes
   void want_alignment(bool on) { want_align_ = on; }
+  // raw mode (`smooth`): additionally keep the whole record body
+  void want_raw(bool on) { want_raw_ = on; if (on) want_align_ = true; }
+  const std::string& header_text() const { return text_; }
+  const std::vector<int32_t>& ref_lens() const { return ref_lens_; }
   // 1 = record, 0 = clean EOF, -1 = truncated/corrupt
   int next(BamRecord& r) {
     int32_t bs = 0;
@@ -251,6 +314,7 @@ class BamReader {
     if (o + l_read_name > (size_t)bs) return -1;
     r.qname.assign((const char*)p + o, l_read_name ? l_read_name - 1 : 0);
     o += l_read_name;
+    r.off_cigar = o;
     if (o + (size_t)n_cigar * 4 > (size_t)bs) return -1;
     if (want_align_) { r.cigar.resize(n_cigar); if (n_cigar) memcpy(r.cigar.data(), p + o, (size_t)n_cigar * 4); }
     o += (size_t)n_cigar * 4;
@@ -267,7 +331,10 @@ class BamReader {
         r.nt6[i] = t6[(int)nt16[(i & 1) ? (b & 0xf) : (b >> 4)]];
       }
     }
+    r.off_seq = o; r.off_qual = o + seq_bytes;
     o += seq_bytes + (size_t)r.l_qseq;
+    r.off_aux = o;
+    if (want_raw_) r.raw.assign(buf_.begin(), buf_.end());
     r.has_xf = r.has_hp = false; r.xf = r.hp = 0;
     // aux fields (bam_aux_get + bam_aux2i for XF / HP, ping_pong.cpp:196-201)
     while (o + 3 <= (size_t)bs) {
@@ -302,7 +369,7 @@ class BamReader {
   }
  private:
   BgzfSource src_;
-  bool ok_ = false, want_align_ = false;
+  bool ok_ = false, want_align_ = false, want_raw_ = false;
   std::string text_;
   std::vector<std::string> ref_names_;
   std::vector<int32_t> ref_lens_;

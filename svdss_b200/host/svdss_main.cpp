@@ -22,6 +22,7 @@
 #include "../../include/svdss_b200.h"
 #include "io.hpp"
 #include "call.hpp"
+#include "smoother.hpp"
 #include <unistd.h>
 static long getpid_portable() { return (long)getpid(); }
 
@@ -30,8 +31,9 @@ using namespace svdss;
 
 static const char* VERSION = "v2.1.1-b200";
 static const char* MAIN_USAGE =
-    "Usage: SVDSS <index|search|call> --help\n"
+    "Usage: SVDSS <index|smooth|search|call> --help\n"
     "  index   build the FMD index of a reference on the GPU\n"
+    "  smooth  remove everything but putative SVs from the alignments of a BAM\n"
     "  search  extract sample-specific strings (SFS) from a BAM/FASTX\n"
     "  call    POA consensus + ksw2 realignment + SV extraction from SFS clusters";
 static const char* INDEX_USAGE = "Usage: SVDSS index [-t threads] [-d] [-o index] <reference.fa[.gz]>";
@@ -41,6 +43,8 @@ static const char* CALL_USAGE =
     "                  [--poa <out.sam>] [--clusters <out.txt>] [--cluster-only]\n"
     "  Clusters are built on the host from --bam/--sfs (Clusterer) or read back from a `--clusters` file;\n"
     "  POA consensus + realignment (Caller::pcall) run on the GPU. --cluster-only stops after --clusters.";
+static const char* SMOOTH_USAGE =
+    "Usage: SVDSS smooth --reference <fa> --bam <bam> [--threads 4] [--min-mapq 20] [--accp 0.98] > smoothed.bam";
 static const char* SEARCH_USAGE =
     "Usage: SVDSS search --index <index> (--bam <bam> | --fastx <fastx>) [--threads 4] [--bsize 10000]\n"
     "                    [--noputative] [--noassemble] [--verbose]";
@@ -48,7 +52,7 @@ static const char* SEARCH_USAGE =
 struct Config {
   string index, bam, fastx, out, reference, sfs, clusters_in, clusters_out, poa;
   int min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
-  float min_ratio = 0.97f;
+  float min_ratio = 0.97f, accp = 0.98f;
   bool noht = false, clipped = false, cluster_only = false;
   int threads = 4, bsize = 10000, omax = 100000, device = 0;
   bool assemble = true, putative = true, verbose = false, help = false, version = false;
@@ -80,6 +84,7 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
     else if (a == "--min-sv-length") { ok = ival(c.min_sv_length); c.min_sv_length = max(25, c.min_sv_length); }  // config.cpp:87
     else if (a == "--min-mapq") ok = ival(c.min_mapq);
     else if (a == "-l") { string v; ok = val(v); if (ok) c.min_ratio = (float)atof(v.c_str()); }
+    else if (a == "--accp") { string v; ok = val(v); if (ok) c.accp = (float)atof(v.c_str()); }
     else if (a == "--noht") c.noht = true;
     else if (a == "--clipped") c.clipped = true;
     else if (a == "--omax") ok = ival(c.omax);
@@ -265,7 +270,7 @@ int main(int argc, char** argv) {
   if (!parse_common(argc, argv, c, pos)) exit(EXIT_FAILURE);
   const string mode = argv[1];
   if (c.version) { cout << "SVDSS, " << VERSION << endl; exit(EXIT_SUCCESS); }
-  if (c.help) { cerr << (mode == "index" ? INDEX_USAGE : mode == "search" ? SEARCH_USAGE : mode == "call" ? CALL_USAGE : MAIN_USAGE) << endl; exit(EXIT_SUCCESS); }
+  if (c.help) { cerr << (mode == "index" ? INDEX_USAGE : mode == "smooth" ? SMOOTH_USAGE : mode == "search" ? SEARCH_USAGE : mode == "call" ? CALL_USAGE : MAIN_USAGE) << endl; exit(EXIT_SUCCESS); }
   int rc;
   if (mode == "_ratio") {   // test hook: fuzz_ratio of filter_sv_chains (tests/test_cluster_cpu.py)
     if (pos.size() != 2) exit(EXIT_FAILURE);
@@ -273,6 +278,12 @@ int main(int argc, char** argv) {
     return 0;
   }
   if (mode == "index") rc = run_index(c, pos);
+  else if (mode == "smooth") {
+    if (c.reference.empty() || c.bam.empty()) { cerr << SMOOTH_USAGE << endl; exit(EXIT_FAILURE); }   // main.cpp:72-75
+    SmoothConfig sc;
+    sc.bam = c.bam; sc.reference = c.reference; sc.min_mapq = (unsigned)c.min_mapq; sc.accp = c.accp; sc.threads = c.threads;
+    rc = run_smooth(sc, [](const char* l, const string& m) { logmsg(l, m); });
+  }
   else if (mode == "search") rc = run_search(c);
   else if (mode == "call") {
     if (c.reference.empty() || (c.clusters_in.empty() && (c.bam.empty() || c.sfs.empty()))) { cerr << CALL_USAGE << endl; exit(EXIT_FAILURE); }  // main.cpp:56-59

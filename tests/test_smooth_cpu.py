@@ -1,0 +1,130 @@
+"""CPU: `SVDSS smooth` (svdss_b200/host/smoother.hpp, reference smoother.cpp) against the literal Python
+transcription in tests/smooth_model.py: every output record -- order, CIGAR, sequence, qualities, XF tag,
+untouched fields and tags -- on a raw-HiFi-shaped BAM with sequencing errors, short and long indels,
+soft clips, an existing XF tag, and the records the filters must drop."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import smooth_model
+from bam_writer import write_bam, read_bam
+from svdss_b200 import build, synth
+
+L = "$ACGTN"
+
+
+def dec(a):
+    return "".join(L[int(x)] for x in a)
+
+
+@pytest.fixture(scope="module")
+def exe():
+    build.build_lib()
+    return build.build_host()
+
+
+def make_records(rng, contigs, names, n):
+    recs = []
+    for i in range(n):
+        ci = int(rng.integers(len(contigs)))
+        c = contigs[ci]
+        ln = int(rng.integers(300, 4000))
+        a = int(rng.integers(0, len(c) - ln - 100))
+        ref = a
+        seq, cigar = [], []
+        noisy = rng.random() < 0.08                      # a few dirty reads -> XF 1
+        if rng.random() < 0.25:
+            k = int(rng.integers(5, 200)); seq.append(dec(rng.integers(1, 5, size=k))); cigar.append((k, "S"))
+        n_blocks = int(rng.integers(1, 6))
+        for b in range(n_blocks):
+            m = int(rng.integers(40, max(41, ln // n_blocks)))
+            blk = c[ref:ref + m].copy()
+            for p in np.nonzero(rng.random(m) < (0.05 if noisy else 0.002))[0]:
+                blk[p] = (blk[p] % 4) + 1                # substitution
+            seq.append(dec(blk)); cigar.append((m, "M=X"[int(rng.integers(3))] if b % 2 else "M")); ref += m
+            if b + 1 < n_blocks:
+                kind = int(rng.integers(4))
+                k = int(rng.integers(1, 21)) if kind < 2 else int(rng.integers(21, 300))
+                if kind % 2 == 0:
+                    seq.append(dec(rng.integers(1, 5, size=k))); cigar.append((k, "I"))
+                else:
+                    cigar.append((k, "D")); ref += k
+        if rng.random() < 0.25:
+            k = int(rng.integers(5, 200)); seq.append(dec(rng.integers(1, 5, size=k))); cigar.append((k, "S"))
+        s = "".join(seq)
+        tags = {"NM": int(rng.integers(0, 50)), "RG": "grp%d" % (i % 3)}
+        if i % 7 == 0:
+            tags["XF"] = ("i", 7)                       # stale tag: must be replaced, not duplicated
+        if i % 5 == 0:
+            tags["HP"] = ("C", 1 + i % 2)
+        recs.append(dict(qname="r%05d" % i, flag=16 if i % 2 else 0, tid=ci, pos=a, mapq=60, seq=s, cigar=cigar,
+                         qual=bytes(rng.integers(0, 60, size=len(s), dtype=np.uint8).tolist()), tags=tags))
+    recs.sort(key=lambda r: (r["tid"], r["pos"]))
+    recs[3]["mapq"] = 3
+    recs[5]["flag"] |= 0x100
+    recs[8]["flag"] |= 0x800
+    recs.insert(9, dict(qname="unmapped", flag=4, tid=0, pos=0, mapq=0, seq="ACGTACGT", cigar=[], tags={}))
+    recs.insert(11, dict(qname="tiny", flag=0, tid=0, pos=10, mapq=60, seq="A", cigar=[(1, "M")], tags={}))
+    recs.append(dict(qname="elsewhere", flag=0, tid=len(names) - 1, pos=5, mapq=60, seq="ACGTAC", cigar=[(6, "M")], tags={}))
+    return recs
+
+
+def test_smooth_matches_the_transcription(exe, tmp_path):
+    rng = np.random.default_rng(123)
+    contigs = synth.make_reference(120_000, seed=91, contigs=2, n_repeats=3, n_nruns=1, nrun_len=40)
+    names = ["chrA", "chrB", "chrUn"]                    # chrUn is in the BAM header but not in the FASTA
+    ref_seqs = {"chrA": dec(contigs[0]), "chrB": dec(contigs[1])}
+    fa = tmp_path / "ref.fa"
+    fa.write_text("".join(">%s\n%s\n" % (n, ref_seqs[n].lower() if n == "chrB" else ref_seqs[n]) for n in ("chrA", "chrB")))
+    recs = make_records(rng, contigs, names, 400)
+    bam = str(tmp_path / "in.bam")
+    write_bam(bam, [("chrA", len(contigs[0])), ("chrB", len(contigs[1])), ("chrUn", 1000)], recs)
+    out = str(tmp_path / "smoothed.bam")
+    with open(out, "wb") as f:
+        r = subprocess.run([exe, "smooth", "--reference", str(fa), "--bam", bam, "--threads", "3"], stdout=f, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    text_in, refs_in, parsed_in = read_bam(bam)
+    text, refs, got = read_bam(out)
+    assert text == text_in and refs == refs_in
+    model_in = [dict(r, qual=r["qual"], hp=None) for r in parsed_in]
+    want, al = smooth_model.run(model_in, names, ref_seqs)
+    assert ("accuracy: %.6f" % al) in r.stderr
+    assert len(got) == len(want) and len(got) >= 390
+    n_xf = [0, 0, 0]
+    for g, w in zip(got, want):
+        assert g["qname"] == w["qname"]
+        assert (g["flag"], g["tid"], g["pos"], g["mapq"]) == (w["flag"], w["tid"], w["pos"], w["mapq"])
+        assert g["cigar"] == w["cigar"], g["qname"]
+        assert g["seq"] == w["seq"] and g["qual"] == w["qual"], g["qname"]
+        assert g["tags"]["XF"][1] == w["xf"]
+        others = {k: v for k, v in g["tags"].items() if k != "XF"}
+        assert others == {k: v for k, v in w["tags"].items() if k != "XF"}
+        n_xf[w["xf"]] += 1
+    assert min(n_xf) >= 5                                 # all three outcomes are exercised
+    # smoothed reads differ from the reference only at long indels / clips: M blocks are reference copies
+    for g in got:
+        if g["tags"]["XF"][1] != 0:
+            continue
+        ref, rd = g["pos"], 0
+        for ln, op in g["cigar"]:
+            assert op in "MIDS"
+            if op == "M":
+                assert g["seq"][rd:rd + ln] == ref_seqs[names[g["tid"]]][ref:ref + ln]
+                ref += ln; rd += ln
+            elif op == "D":
+                assert ln > 20; ref += ln
+            elif op == "I":
+                assert ln > 20; rd += ln
+            else:
+                rd += ln
+        assert rd == len(g["seq"])
+
+
+def test_smooth_usage(exe, tmp_path):
+    r = subprocess.run([exe, "smooth", "--bam", "x.bam"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage: SVDSS smooth" in r.stderr
+    (tmp_path / "r.fa").write_text(">c\nACGT\n")
+    r = subprocess.run([exe, "smooth", "--reference", str(tmp_path / "r.fa"), "--bam", str(tmp_path / "no.bam")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot read BAM" in r.stderr
