@@ -271,11 +271,41 @@ def make_sv_catalogue(contigs, n_svs, seed=5, min_len=50, max_len=5000, margin=2
     return out
 
 
+def _add_noise(rng, pieces, cigar, sub_rate, indel_rate):
+    """sequencing noise on the M blocks of one alignment: substitutions in place, 1-bp insertions and
+    deletions that split the block (first / last 20 bases of a block stay clean)"""
+    out_p, out_c = [], []
+    pi = 0
+    for ln, op in cigar:
+        if op == "D":
+            out_c.append((ln, op))
+            continue
+        blk = pieces[pi].copy(); pi += 1
+        if op != "M" or ln < 60:
+            out_p.append(blk); out_c.append((ln, op))
+            continue
+        subs = np.nonzero(rng.random(ln) < sub_rate)[0]
+        blk[subs] = (blk[subs] % 4) + 1
+        cuts = sorted(set((np.nonzero(rng.random(ln - 40) < indel_rate)[0] + 20).tolist()))
+        last = 0
+        for cpos in cuts:
+            if cpos - last < 2:
+                continue
+            out_p.append(blk[last:cpos]); out_c.append((cpos - last, "M"))
+            if rng.random() < 0.5:
+                out_p.append(rng.integers(1, 5, size=1, dtype=np.uint8)); out_c.append((1, "I")); last = cpos
+            else:
+                out_c.append((1, "D")); last = cpos + 1
+        out_p.append(blk[last:]); out_c.append((ln - last, "M"))
+    return out_p, out_c
+
+
 def make_sample_alignments(contigs, catalogue, coverage=10, seed=6, mean_len=15000, sd_len=2000, min_len=1000,
-                           max_len=25000, tag_hp=True, names=None, clip_rate=0.1):
+                           max_len=25000, tag_hp=True, names=None, clip_rate=0.1, sub_rate=0.0, indel_rate=0.0):
     """Reads of a diploid sample with true alignments. Returns a list of dicts: qname, tid, pos, cigar
     [(len, op)], seq (nt6 array, forward strand), hp (1/2), has_event (bool -> XF:i:0 else XF:i:2).
-    Sorted by (tid, pos) like a coordinate-sorted BAM."""
+    Sorted by (tid, pos) like a coordinate-sorted BAM.  sub_rate / indel_rate > 0 make the reads
+    raw-HiFi-shaped (substitutions inside M blocks, 1-bp I/D splitting them): the input of `smooth`."""
     rng = np.random.default_rng(seed)
     recs = []
     rid = 0
@@ -312,6 +342,8 @@ def make_sample_alignments(contigs, catalogue, coverage=10, seed=6, mean_len=150
                     else:
                         pieces.insert(0, t); cigar.insert(0, (len(t), "S"))
                     has_event = True
+                if sub_rate > 0 or indel_rate > 0:
+                    pieces, cigar = _add_noise(rng, pieces, cigar, sub_rate, indel_rate)
                 seq = np.ascontiguousarray(np.concatenate(pieces), np.uint8)
                 recs.append(dict(qname=(names[rid] if names else "read_%06d" % rid), tid=ci, pos=a, cigar=cigar, seq=seq,
                                  hp=hap + 1 if tag_hp else 0, has_event=has_event))
