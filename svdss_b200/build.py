@@ -61,7 +61,7 @@ def build_host(force=False):
     if (not force and os.path.exists(HOST_BIN)
             and all(os.path.getmtime(HOST_BIN) >= os.path.getmtime(s) for s in srcs + [LIB])):
         return HOST_BIN
-    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-fopenmp", "-o", HOST_BIN, srcs[0],
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-fopenmp", "-pthread", "-o", HOST_BIN, srcs[0],
                            "-L" + HERE, "-lsvdss_b200", "-lz", "-Wl,-rpath,$ORIGIN"])
     return HOST_BIN
 

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <future>
 #include <memory>
 #include <string>
 #include <vector>
@@ -75,7 +76,7 @@ class BgzfSource {
     if (bgzf_) fseek(f_, 0, SEEK_SET);
     else { fclose(f_); f_ = nullptr; plain_.reset(new GzSource(path)); }
   }
-  ~BgzfSource() { if (f_) fclose(f_); }
+  ~BgzfSource() { if (pending_.valid()) pending_.wait(); if (f_) fclose(f_); }
   bool ok() const { return bgzf_ ? f_ != nullptr : (plain_ && plain_->ok()); }
   bool read_exact(void* dst, size_t n) {
     if (!bgzf_) return plain_->read_exact(dst, n);
@@ -88,67 +89,87 @@ class BgzfSource {
     }
     return true;
   }
+ public:
+  // zero-copy access for record parsers: n contiguous bytes of the current window, or nullptr if the
+  // window ends before (then read_exact copies across the boundary)
+  const uint8_t* peek(size_t n) const { return bgzf_ && out_.size() - pos_ >= n ? out_.data() + pos_ : nullptr; }
+  void skip(size_t n) { pos_ += n; }
  private:
+  // the next window is read and inflated by a background task while the caller consumes this one
   bool refill() {
-    struct Blk { size_t in_off, in_len, out_off, out_len; };
-    std::vector<Blk> blks;
-    in_.clear();
-    size_t out_total = 0;
-    const size_t window = (size_t)64 << 20;   // compressed bytes per refill
-    while (in_.size() < window) {
-      uint8_t h[18];
-      const size_t got = fread(h, 1, 18, f_);
-      if (got == 0) break;
-      if (got != 18 || h[0] != 31 || h[1] != 139 || !(h[3] & 4)) return false;
-      // walk the extra field for the BC subfield (SAM spec 4.1)
-      const unsigned xlen = h[10] | (h[11] << 8);
-      std::vector<uint8_t> extra(xlen);
-      memcpy(extra.data(), h + 12, std::min<size_t>(6, xlen));
-      if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != xlen - 6) return false;
-      int bsize = -1;
-      for (size_t o = 0; o + 4 <= xlen;) {
-        const unsigned sl = extra[o + 2] | (extra[o + 3] << 8);
-        if (extra[o] == 'B' && extra[o + 1] == 'C' && sl == 2 && o + 6 <= xlen) bsize = extra[o + 4] | (extra[o + 5] << 8);
-        o += 4 + sl;
-      }
-      if (bsize < 0) return false;
-      const size_t total = (size_t)bsize + 1, head = 12 + xlen;
-      if (total < head + 8) return false;
-      const size_t body = total - head;       // deflate data + CRC32 + ISIZE
-      const size_t at = in_.size();
-      in_.resize(at + body);
-      if (fread(in_.data() + at, 1, body, f_) != body) return false;
-      uint32_t isize;
-      memcpy(&isize, in_.data() + at + body - 4, 4);
-      if (isize > (1u << 16)) return false;
-      blks.push_back(Blk{at, body - 8, out_total, isize});
-      out_total += isize;
-    }
-    if (blks.empty()) return false;
-    out_.resize(out_total);
+    bool ok;
+    if (pending_.valid()) ok = pending_.get();
+    else ok = fill(in_next_, out_next_);
+    if (!ok) { out_.clear(); pos_ = 0; return false; }
+    out_.swap(out_next_);
     pos_ = 0;
-    int bad = 0;
-#pragma omp parallel for schedule(dynamic, 8) reduction(+ : bad)
-    for (long long i = 0; i < (long long)blks.size(); ++i) {
-      const Blk& b = blks[(size_t)i];
-      if (b.out_len == 0) continue;
-      z_stream zs;
-      memset(&zs, 0, sizeof(zs));
-      if (inflateInit2(&zs, -15) != Z_OK) { ++bad; continue; }
-      zs.next_in = in_.data() + b.in_off; zs.avail_in = (uInt)b.in_len;
-      zs.next_out = out_.data() + b.out_off; zs.avail_out = (uInt)b.out_len;
-      const int rc = inflate(&zs, Z_FINISH);
-      if (rc != Z_STREAM_END || zs.avail_out != 0) ++bad;
-      inflateEnd(&zs);
-    }
-    return bad == 0 && out_total > 0 ? true : (bad == 0 && refill_empty_ok());
+    pending_ = std::async(std::launch::async, [this]() { return fill(in_next_, out_next_); });
+    return true;
   }
-  // a window holding only empty members (the EOF marker): keep reading
-  bool refill_empty_ok() { return !feof(f_) && refill(); }
+  // one window: up to 64 MiB of BGZF members read sequentially, inflated in parallel.  false at EOF
+  // (no payload left) or on a malformed file.
+  bool fill(std::vector<uint8_t>& in, std::vector<uint8_t>& out) {
+    struct Blk { size_t in_off, in_len, out_off, out_len; };
+    for (;;) {
+      std::vector<Blk> blks;
+      in.clear();
+      size_t out_total = 0;
+      const size_t window = (size_t)64 << 20;   // compressed bytes per window
+      while (in.size() < window) {
+        uint8_t h[18];
+        const size_t got = fread(h, 1, 18, f_);
+        if (got == 0) break;
+        if (got != 18 || h[0] != 31 || h[1] != 139 || !(h[3] & 4)) return false;
+        // walk the extra field for the BC subfield (SAM spec 4.1)
+        const unsigned xlen = h[10] | (h[11] << 8);
+        std::vector<uint8_t> extra(xlen);
+        memcpy(extra.data(), h + 12, std::min<size_t>(6, xlen));
+        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != xlen - 6) return false;
+        int bsize = -1;
+        for (size_t o = 0; o + 4 <= xlen;) {
+          const unsigned sl = extra[o + 2] | (extra[o + 3] << 8);
+          if (extra[o] == 'B' && extra[o + 1] == 'C' && sl == 2 && o + 6 <= xlen) bsize = extra[o + 4] | (extra[o + 5] << 8);
+          o += 4 + sl;
+        }
+        if (bsize < 0) return false;
+        const size_t total = (size_t)bsize + 1, head = 12 + xlen;
+        if (total < head + 8) return false;
+        const size_t body = total - head;       // deflate data + CRC32 + ISIZE
+        const size_t at = in.size();
+        in.resize(at + body);
+        if (fread(in.data() + at, 1, body, f_) != body) return false;
+        uint32_t isize;
+        memcpy(&isize, in.data() + at + body - 4, 4);
+        if (isize > (1u << 16)) return false;
+        blks.push_back(Blk{at, body - 8, out_total, isize});
+        out_total += isize;
+      }
+      if (blks.empty()) return false;
+      out.resize(out_total);
+      int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : bad)
+      for (long long i = 0; i < (long long)blks.size(); ++i) {
+        const Blk& b = blks[(size_t)i];
+        if (b.out_len == 0) continue;
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { ++bad; continue; }
+        zs.next_in = in.data() + b.in_off; zs.avail_in = (uInt)b.in_len;
+        zs.next_out = out.data() + b.out_off; zs.avail_out = (uInt)b.out_len;
+        const int rc = inflate(&zs, Z_FINISH);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) ++bad;
+        inflateEnd(&zs);
+      }
+      if (bad) return false;
+      if (out_total > 0) return true;
+      // a window holding only empty members (the EOF marker): keep reading
+    }
+  }
   FILE* f_ = nullptr;
   bool bgzf_ = false;
   std::unique_ptr<GzSource> plain_;
-  std::vector<uint8_t> in_, out_;
+  std::vector<uint8_t> out_, in_next_, out_next_;
+  std::future<bool> pending_;
   size_t pos_ = 0;
 };
 
@@ -299,9 +320,13 @@ class BamReader {
     int32_t bs = 0;
     if (!src_.read_exact(&bs, 4)) return 0;
     if (bs < 32) return -1;
-    buf_.resize((size_t)bs);
-    if (!src_.read_exact(buf_.data(), (size_t)bs)) return -1;
-    const uint8_t* p = buf_.data();
+    const uint8_t* p = src_.peek((size_t)bs);   // the record as it lies in the inflated window
+    if (p) src_.skip((size_t)bs);
+    else {
+      buf_.resize((size_t)bs);
+      if (!src_.read_exact(buf_.data(), (size_t)bs)) return -1;
+      p = buf_.data();
+    }
     auto rd32 = [&](size_t o) { int32_t v; memcpy(&v, p + o, 4); return v; };
     auto rd16 = [&](size_t o) { uint16_t v; memcpy(&v, p + o, 2); return v; };
     r.tid = rd32(0); r.pos = rd32(4);
@@ -334,7 +359,7 @@ class BamReader {
     r.off_seq = o; r.off_qual = o + seq_bytes;
     o += seq_bytes + (size_t)r.l_qseq;
     r.off_aux = o;
-    if (want_raw_) r.raw.assign(buf_.begin(), buf_.end());
+    if (want_raw_) r.raw.assign(p, p + bs);
     r.has_xf = r.has_hp = false; r.xf = r.hp = 0;
     // aux fields (bam_aux_get + bam_aux2i for XF / HP, ping_pong.cpp:196-201)
     while (o + 3 <= (size_t)bs) {

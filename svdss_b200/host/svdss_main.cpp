@@ -10,6 +10,7 @@
 // Output order is the reference's (ping_pong.cpp:213-236,329-361): logical batches of --bsize
 // accepted reads, reads dealt round-robin to --threads slots, each slot printed in qname order.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -142,6 +143,9 @@ static int run_index(const Config& c, const vector<string>& pos) {
   return EXIT_SUCCESS;
 }
 
+static double g_gpu_s = 0;   // wall time inside svb_sfs_batch* (stage report of `search`)
+static double now_s() { return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); }
+
 struct PendingRead { string qname; int hp; int64_t lo, hi; bool search; int32_t l_qseq; };
 
 // one GPU submission covering many logical batches; prints in the reference's order.
@@ -150,20 +154,20 @@ struct PendingRead { string qname; int hp; int64_t lo, hi; bool search; int32_t 
 static bool flush(svb_index_t* idx, const Config& c, vector<PendingRead>& reads, vector<uint8_t>& cat,
                   uint64_t& total_sfs, bool packed) {
   if (reads.empty()) return true;
+  // `cat` holds the sequences of the searched reads only, in read order (reads filtered by the XF rule
+  // keep their slot in the output order but carry no bases, ping_pong.cpp:202-203)
   vector<int64_t> offs(1, 0);
   vector<int32_t> lq;
-  vector<uint8_t> sub;
   vector<int64_t> slot_of(reads.size(), -1);
   int64_t n = 0;
-  // reads filtered by the XF rule keep their slot but are not searched (ping_pong.cpp:202-203)
   for (size_t i = 0; i < reads.size(); ++i)
-    if (reads[i].search) { slot_of[i] = n++; offs.push_back(offs.back() + (reads[i].hi - reads[i].lo)); lq.push_back(reads[i].l_qseq); }
-  sub.reserve((size_t)offs.back());
-  for (size_t i = 0; i < reads.size(); ++i)
-    if (reads[i].search) sub.insert(sub.end(), cat.begin() + reads[i].lo, cat.begin() + reads[i].hi);
+    if (reads[i].search) { slot_of[i] = n++; offs.push_back(reads[i].hi); lq.push_back(reads[i].l_qseq); }
+  const vector<uint8_t>& sub = cat;
   svb_sfs_out_t out;
+  const double t_gpu = now_s();
   const int rc = packed ? svb_sfs_batch_bam4(idx, sub.data(), offs.data(), lq.data(), n, c.overlap, c.assemble ? 1 : 0, &out)
                         : svb_sfs_batch(idx, sub.data(), offs.data(), n, c.overlap, c.assemble ? 1 : 0, &out);
+  g_gpu_s += now_s() - t_gpu;
   if (rc != SVB_OK) {
     logmsg("critical", string(packed ? "svb_sfs_batch_bam4: " : "svb_sfs_batch: ") + svb_last_error());
     return false;
@@ -198,12 +202,14 @@ static bool flush(svb_index_t* idx, const Config& c, vector<PendingRead>& reads,
 
 static int run_search(const Config& c) {
   if (c.index.empty() || (c.fastx.empty() && c.bam.empty())) { cerr << SEARCH_USAGE << endl; return EXIT_FAILURE; }
+  const double t_start = now_s();
   logmsg("info", "Restoring index..");
   svb_index_t* idx = nullptr;
   if (svb_index_load(c.index.c_str(), c.device, &idx) != SVB_OK) {
     logmsg("critical", string("svb_index_load: ") + svb_last_error());
     return EXIT_FAILURE;
   }
+  const double t_loaded = now_s();
   // GPU submissions cover as many logical batches as fit ~4 Gbases of reads
   const size_t gpu_bases = (size_t)4 << 30;
   vector<PendingRead> reads;
@@ -232,7 +238,7 @@ static int run_search(const Config& c) {
       if (r.tid < 0) { logmsg("critical", "core.tid < 0. Why are we here? Please check"); svb_index_free(idx); exit(1); }  // :76-79
       const int xf = r.has_xf ? (int)r.xf : 0, hp = r.has_hp ? (int)r.hp : 0; // :196-201
       PendingRead pr{r.qname, hp, (int64_t)cat.size(), 0, !(c.putative && xf != 0), r.l_qseq};
-      cat.insert(cat.end(), r.seq4.begin(), r.seq4.end());
+      if (pr.search) cat.insert(cat.end(), r.seq4.begin(), r.seq4.end());
       pr.hi = (int64_t)cat.size();
       reads.push_back(pr);
       ok = maybe_flush();
@@ -257,7 +263,10 @@ static int run_search(const Config& c) {
   fflush(stdout);
   svb_index_free(idx);
   if (!ok) return EXIT_FAILURE;
-  logmsg("info", "records read: " + to_string(processed) + ", SFS lines written: " + to_string(total_sfs));
+  char tbuf[160];
+  snprintf(tbuf, sizeof(tbuf), " (index load %.2f s, input + output %.2f s, GPU calls %.2f s)", t_loaded - t_start,
+           now_s() - t_loaded - g_gpu_s, g_gpu_s);
+  logmsg("info", "records read: " + to_string(processed) + ", SFS lines written: " + to_string(total_sfs) + tbuf);
   return EXIT_SUCCESS;
 }
 
