@@ -984,7 +984,7 @@ __device__ __forceinline__ void win32_words(const Win32& w, uint64_t o[4]) {
 }
 // staging for the lanes that have an extension pending (a minority once located matches and the jump
 // table carry most of the walk): four of them per round, eight lanes x 16 bytes per block
-__device__ __forceinline__ void cpa_fetch_sparse(const SearchParams& P, uint32_t bk, uint32_t bl, uint32_t warp_stage_s,
+__device__ __forceinline__ void cpa_issue_sparse(const SearchParams& P, uint32_t bk, uint32_t bl, uint32_t warp_stage_s,
                                                  int lane) {
   unsigned m = __ballot_sync(0xffffffffu, bk != NOBLK);
   const int sub = lane >> 3, j = lane & 7;
@@ -1003,8 +1003,59 @@ __device__ __forceinline__ void cpa_fetch_sparse(const SearchParams& P, uint32_t
     }
     m = m3 & (m3 - 1);
   }
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cpa_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
+}
+
+// Located match, warp-cooperative: all 32 lanes compare 32 bytes each of ONE lane's read against the
+// text -- 1024 bases per step from coalesced loads (the read window of lane L is the L-th 32-byte
+// group on the read's 16-byte grid in walking direction; the text side is funnel-shifted).
+// g = global position of the last matched base, lim = bases left in walking direction (>= 1).
+// Returns the number of extensions that succeed (<= lim); *mismatch says whether the next one fails.
+__device__ __forceinline__ int coop_text_step(const SearchParams& P, int64_t g, int64_t delta, int fwd, int lim, int lane,
+                                              bool* mismatch) {
+  const int64_t a0 = fwd ? ((g + 1) & ~15LL) : ((g + 15) & ~15LL);   // forward: first window starts here; backward: ends here
+  const int skip = fwd ? (int)(g + 1 - a0) : (int)(a0 - g);          // bytes of the first window behind the walk
+  const int64_t aw = fwd ? a0 + 32 * lane : a0 - 32 * (lane + 1);    // this lane's window [aw, aw + 32)
+  const int nvalid = max(0, min(32, lim + skip - 32 * lane));        // its leading bytes (walking order) inside the limit
+  int mi = 32;                                                        // leading bytes that match (walking order)
+  if (nvalid > 0) {
+    const uint4* rp = reinterpret_cast<const uint4*>(P.seq);
+    const int64_t qi = aw >> 4;
+    const uint4 r0 = __ldcg(rp + max(qi, (int64_t)0)), r1 = __ldcg(rp + max(qi + 1, (int64_t)0));
+    Win32 tw;
+    load32(P.text, aw + delta, tw, -(int64_t)(TEXT_PAD / 16));
+    uint64_t t[4];
+    win32_words(tw, t);
+    uint64_t x0 = ((uint64_t)r0.x | ((uint64_t)r0.y << 32)) ^ t[0], x1 = ((uint64_t)r0.z | ((uint64_t)r0.w << 32)) ^ t[1];
+    uint64_t x2 = ((uint64_t)r1.x | ((uint64_t)r1.y << 32)) ^ t[2], x3 = ((uint64_t)r1.z | ((uint64_t)r1.w << 32)) ^ t[3];
+    const int sk = lane == 0 ? skip : 0;
+    if (fwd) {             // walking order = ascending bytes; bytes 0 .. sk-1 are behind the walk
+      if (sk >= 8) { x0 = 0; x1 &= ~0ull << (8 * (sk - 8)); } else { x0 &= ~0ull << (8 * sk); }
+      mi = x0 ? (__ffsll((long long)x0) - 1) >> 3
+         : x1 ? 8 + ((__ffsll((long long)x1) - 1) >> 3)
+         : x2 ? 16 + ((__ffsll((long long)x2) - 1) >> 3)
+         : x3 ? 24 + ((__ffsll((long long)x3) - 1) >> 3) : 32;
+    } else {               // walking order = descending bytes; the top sk bytes are behind the walk
+      if (sk >= 8) { x3 = 0; x2 &= ~0ull >> (8 * (sk - 8)); } else { x3 &= ~0ull >> (8 * sk); }
+      mi = x3 ? __clzll((long long)x3) >> 3
+         : x2 ? 8 + (__clzll((long long)x2) >> 3)
+         : x1 ? 16 + (__clzll((long long)x1) >> 3)
+         : x0 ? 24 + (__clzll((long long)x0) >> 3) : 32;
+    }
+  }
+  const int got = min(mi, nvalid);                    // window bytes consumed before a mismatch or the limit
+  const unsigned stop = __ballot_sync(0xffffffffu, got < 32);
+  const int first = stop ? __ffs((int)stop) - 1 : 32;
+  const int got_f = __shfl_sync(0xffffffffu, got, first & 31);
+  const int mi_f = __shfl_sync(0xffffffffu, mi, first & 31);
+  const int nv_f = __shfl_sync(0xffffffffu, nvalid, first & 31);
+  if (first == 32) { *mismatch = false; return 1024 - skip; }
+  *mismatch = mi_f < nv_f;
+  return 32 * first + got_f - skip;
 }
 
 // ------------------------------------------------------------------------------ v3 kernel
@@ -1195,21 +1246,10 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
       }
     }
     // ---- (2) issue: every load of this iteration leaves from here
-    Win32 rw, tw;
+    Win32 rw;
     uint64_t one = 0;
-    int skip = 0;
     if (op == OP_TXT) {
-      // 32-byte window on the READ's 16-byte grid (two aligned loads, no shifting): forward it starts
-      // at or below the next base, backward it ends at or above the last matched one; `skip` bytes
-      // of it lie behind the walk.  The text side is wherever delta puts it (three loads + funnel).
-      const int64_t g = roff + pos;
-      const int64_t a0 = phase ? ((g + 1) & ~15LL) : (((g + 15) & ~15LL) - 32);
-      skip = phase ? (int)(g + 1 - a0) : (int)(a0 + 32 - g);
-      const uint4* rp = reinterpret_cast<const uint4*>(P.seq);
-      const int64_t qi = a0 >> 4;
-      rw.q0 = __ldcg(rp + max(qi, (int64_t)0));
-      rw.q1 = __ldcg(rp + max(qi + 1, (int64_t)0));
-      load32(P.text, a0 + delta, tw, -(int64_t)(TEXT_PAD / 16));
+      // served below, one lane at a time, by the whole warp
     } else if (op == OP_KMER) {
       load32(P.seq, roff + (phase ? pos : pos - K + 1), rw, 0);
     } else if (op == OP_KMT) {
@@ -1219,47 +1259,40 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     }
     const uint32_t bk = op == OP_EXT ? (uint32_t)(k >> 8) : NOBLK;
     const uint32_t bl = op == OP_EXT ? (uint32_t)((k + s) >> 8) : NOBLK;
+    cpa_issue_sparse(P, bk, bl, warp_stage_s, lane);
+    // located matches: the warp walks up to 1024 bases for each lane that is in that mode, while
+    // the index blocks of the other lanes are on their way
+    for (unsigned tmask = __ballot_sync(0xffffffffu, op == OP_TXT); tmask; tmask &= tmask - 1) {
+      const int src = __ffs((int)tmask) - 1;
+      const int64_t g = __shfl_sync(0xffffffffu, roff + pos, src);
+      const int64_t dl = __shfl_sync(0xffffffffu, delta, src);
+      const int fwd = __shfl_sync(0xffffffffu, phase, src);
+      const int lim = __shfl_sync(0xffffffffu, phase ? len - 1 - pos : pos, src);
+      bool mism;
+      const int adv = coop_text_step(P, g, dl, fwd, lim, lane, &mism);
+      if (lane == src) {
+        const int dir = phase ? 1 : -1;
+        if (!mism) {             // all adv extensions succeed (the interval stays of size 1)
+          pos += dir * adv;
+          n_txt += (unsigned)adv;
+        } else {                 // extension adv+1 fails: the state a rank walk ends in with s == 0
+          pos += dir * (adv + 1);
+          n_txt += (unsigned)(adv + 1);
+          s = 0;
+          tmode = false;
+        }
+        hv = 0;
+        win.id = -1; win.nid = -1;
+      }
+    }
     // ---- (3) one wait for the warp
-    cpa_fetch_sparse(P, bk, bl, warp_stage_s, lane);
+    cpa_wait();
     // ---- (4) consume
     if (op == OP_EXT) {
       const bool two = bl != bk;
       tma_consume(P, my, two, c, k, s, lane);
       ++n_ext;
       n_blk += two ? 2u : 1u;
-    } else if (op == OP_TXT) {
-      uint64_t t[4];
-      win32_words(tw, t);
-      uint64_t x0 = ((uint64_t)rw.q0.x | ((uint64_t)rw.q0.y << 32)) ^ t[0], x1 = ((uint64_t)rw.q0.z | ((uint64_t)rw.q0.w << 32)) ^ t[1];
-      uint64_t x2 = ((uint64_t)rw.q1.x | ((uint64_t)rw.q1.y << 32)) ^ t[2], x3 = ((uint64_t)rw.q1.z | ((uint64_t)rw.q1.w << 32)) ^ t[3];
-      int nb, mt;  // bases available in walking direction (<= 32 - skip), leading bases that match
-      if (phase) {           // bytes 0 .. skip-1 of the window are behind the walk: make them match
-        if (skip >= 8) { x0 = 0; x1 &= ~0ull << (8 * (skip - 8)); } else { x0 &= ~0ull << (8 * skip); }
-        nb = min(32 - skip, len - 1 - pos);
-        mt = (x0 ? (__ffsll((long long)x0) - 1) >> 3
-           : x1 ? 8 + ((__ffsll((long long)x1) - 1) >> 3)
-           : x2 ? 16 + ((__ffsll((long long)x2) - 1) >> 3)
-           : x3 ? 24 + ((__ffsll((long long)x3) - 1) >> 3) : 32) - skip;
-      } else {               // bytes 32-skip .. 31 are behind the walk
-        if (skip >= 8) { x3 = 0; x2 &= ~0ull >> (8 * (skip - 8)); } else { x3 &= ~0ull >> (8 * skip); }
-        nb = min(32 - skip, pos);
-        mt = (x3 ? __clzll((long long)x3) >> 3
-           : x2 ? 8 + (__clzll((long long)x2) >> 3)
-           : x1 ? 16 + (__clzll((long long)x1) >> 3)
-           : x0 ? 24 + (__clzll((long long)x0) >> 3) : 32) - skip;
-      }
-      const int dir = phase ? 1 : -1;
-      if (mt >= nb) {          // all nb extensions succeed (the interval stays of size 1)
-        pos += dir * nb;
-        n_txt += (unsigned)nb;
-      } else {                 // extension mt+1 fails: the state a rank walk ends in with s == 0
-        pos += dir * (mt + 1);
-        n_txt += (unsigned)(mt + 1);
-        s = 0;
-        tmode = false;
-      }
-      hv = 0;
-      win.id = -1; win.nid = -1;
     } else if (op == OP_KMER) {
       uint64_t r[4];
       win32_words(rw, r);
