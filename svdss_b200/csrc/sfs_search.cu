@@ -69,7 +69,8 @@ struct SearchParams {
   int assemble;
   unsigned long long* work;      // next read to hand out
   unsigned long long* out_count; // records appended
-  unsigned long long* stats;     // [0] extensions, [1] blocks touched, [2] extensions answered from the text, [3] stream stalled
+  unsigned long long* stats;     // [0] extensions, [1] blocks touched, [2] extensions answered from the text, [3] stream stalled,
+                                 // [4] first thread in / [5] queue ran dry / [6] last warp out (globaltimer ns)
   // located-match mode (IndexDev::d_text / d_ssa / d_tstart); text == nullptr: rank mode only
   const uint8_t* __restrict__ text;
   const uint64_t* __restrict__ ssa;
@@ -1086,6 +1087,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     unpack_cta_loop(P);
     return;
   }
+  if (threadIdx.x == 0) atomicMin(P.stats + 4, globaltimer_ns());
 
   bool alive = true, have = false;
   int st = ST_START, phase = 0;
@@ -1163,7 +1165,11 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     while (alive && op == OP_NONE) {
       if (!have) {
         const unsigned long long w = atomicAdd(P.work, 1ull);
-        if (w >= (unsigned long long)P.n_reads) { alive = false; break; }
+        if (w >= (unsigned long long)P.n_reads) {
+          if (w == (unsigned long long)P.n_reads) atomicMin(P.stats + 5, globaltimer_ns());   // the queue just ran dry
+          alive = false;
+          break;
+        }
         if (P.sched) {
           const ulonglong2 e = __ldg(P.sched + w);
           roff = (int64_t)e.x; ridx = (uint32_t)e.y; len = (int)(e.y >> 32);
@@ -1335,6 +1341,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     }
     __syncwarp();  // staging slots are rewritten by other lanes next iteration
   }
+  if (lane == 0) atomicMax(P.stats + 6, globaltimer_ns());
 }
 
 template <int MODE>
@@ -1612,7 +1619,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   P.overlap = overlap; P.assemble = assemble;
   SearchScratch S;
   S.st = st;
-  SVB_CUDA(pmalloc((void**)&S.d_ctr, 6 * sizeof(unsigned long long), st));
+  SVB_CUDA(pmalloc((void**)&S.d_ctr, 10 * sizeof(unsigned long long), st));
   // first guess of output capacity; exact count is known after the run, rerun once if it overflowed
   unsigned long long cap = assemble ? (unsigned long long)(4 * n_reads + 1024)
                                     : (unsigned long long)(R->total / 8 + 64 * n_reads + 1024);
@@ -1634,13 +1641,14 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   cudaEvent_t e0, e1;
   SVB_CUDA(cudaEventCreate(&e0));
   SVB_CUDA(cudaEventCreate(&e1));
-  unsigned long long ctr[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long ctr[10] = {0};
   float kms = 0.f;
   for (int attempt = 0; attempt < 2; ++attempt) {
     pfree(S.d_key, st); pfree(S.d_len, st); S.d_key = nullptr; S.d_len = nullptr;
     SVB_CUDA(pmalloc((void**)&S.d_key, cap * 8, st));
     SVB_CUDA(pmalloc((void**)&S.d_len, cap * 4, st));
-    SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 6 * sizeof(unsigned long long), st));
+    SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 10 * sizeof(unsigned long long), st));
+    SVB_CUDA(cudaMemsetAsync(S.d_ctr + 6, 0xff, 2 * sizeof(unsigned long long), st));   // [6] first thread in, [7] queue empty: minima
     P.work = S.d_ctr + 0; P.out_count = S.d_ctr + 1; P.stats = S.d_ctr + 2;
     P.out_key = S.d_key; P.out_len = S.d_len; P.out_cap = cap;
     P.ready = nullptr; P.chunk_bytes = 0; P.n_unpack = 0;
@@ -1703,6 +1711,9 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   out->n_ext = (int64_t)ctr[2];
   out->n_blocks_touched = (int64_t)ctr[3];
   out->n_text_ext = (int64_t)ctr[4];
+  if (getenv("SVB_SEARCH_STATS") && ctr[8])   // k_sfs_search_mop only
+    fprintf(stderr, "[k_sfs_search_mop] ext %llu blocks %llu text %llu | work queue empty after %.1f ms, last thread done after %.1f ms\n",
+            ctr[2], ctr[3], ctr[4], (ctr[7] - ctr[6]) * 1e-6, (ctr[8] - ctr[6]) * 1e-6);
   const int64_t m = (int64_t)ctr[1];
   out->n_sfs = m;
   if (m == 0) return SVB_OK;
