@@ -101,6 +101,14 @@ struct SearchParams {
   uint8_t* seq_w;            // = seq, writable
   int64_t total;
   int n_chunks, n_unpack;
+  // two-phase launch of k_sfs_search_mop: when the work queue runs dry the main kernel parks every
+  // unfinished walk in cont[] and ends; the tail kernel finishes them one per WARP (see Cont)
+  struct Cont* cont;
+  unsigned long long* n_cont;   // continuations written (main) / to hand out (tail)
+  unsigned int* dry;            // raised by the first thread that finds the queue empty
+  const unsigned int* last_ready;  // streamed batch: flag of the last chunk (walks are parked only once it is up:
+                                   // before that the queue is "empty" merely because every thread holds a
+                                   // reservation for a read that has not arrived yet)
 };
 
 __device__ __forceinline__ uint4 ldg_slice(const uint4* p) {
@@ -1059,6 +1067,84 @@ __device__ __forceinline__ int coop_text_step(const SearchParams& P, int64_t g, 
   return 32 * first + got_f - skip;
 }
 
+// A parked walk: everything k_sfs_search_mop keeps per thread between two iterations.
+struct Cont {
+  int64_t roff, delta;
+  uint64_t k, s;
+  uint32_t ridx, hist, kcode;
+  int len, pos, begin, chain_qs, chain_end, hv;
+  unsigned n_ext, n_blk, n_txt;
+  uint8_t phase, st, tmode, spr;
+};
+
+// ---- tail sprint ---------------------------------------------------------------------------------
+// One read's walk is a serial chain: restart s -> (b(s), e(b)) -> next restart e - 1.  Inside novel
+// sequence every link costs ~7 dependent memory round trips and moves the restart by about one base,
+// and in a warp whose 32 lanes all carry reads a lane gets one micro-op per ~5 us iteration: a read
+// with a kilobase of clipped or inserted sequence takes tens of milliseconds, which is what is left
+// running when the work queue is empty.  The tail kernel therefore gives a whole warp to one parked
+// walk: lane j computes the link of restart s - j on its own (same table jump + rank steps, straight
+// from global memory), then the chain is resolved over the 32 precomputed links with shuffles.  Links
+// are pure functions of the restart position, so the SFSs and the extension count are those of the
+// serial walk; a link that runs long (the restart sits in matching sequence) is abandoned and the
+// owner carries on from there by itself.
+struct Link { int b, e, cnt, blk, status; };   // status 0: SFS [b, e]; 1: read start reached still matching; 2: abandoned
+__device__ __forceinline__ Link lane_link(const SearchParams& P, const uint8_t* __restrict__ rd, int len, int s0, int K,
+                                          int budget) {
+  Link r;
+  r.b = r.e = r.cnt = r.blk = 0; r.status = 2;
+  if (s0 < 0 || s0 >= len) return r;
+  uint64_t k = 0, sz = 0;
+  int pos = s0;
+  // rd = P.seq + roff is not 8-byte aligned in general: address the words from the buffer start
+  const int64_t roff = rd - P.seq;
+  const int64_t min_word = 0;
+  auto base = [&](int i) { return (int)__ldcg(rd + i); };
+  auto start = [&](bool fwd) {   // rb3_fmd_set_intv at `pos` (+ K-1 extensions through the jump table); false: N in the way
+    if (fwd ? pos + K <= len : pos + 1 >= K) {
+      Win16 w;   // the K bases in one round trip (three aligned 8-byte loads), not K byte loads in a row
+      load16(P.seq, roff + (fwd ? pos : pos - K + 1), w, min_word);
+      uint32_t code;
+      if (!window_kmer(w, K, code)) return false;
+      const uint64_t e = __ldg(P.kmt + (fwd ? kmer_rc(code, K) : code));
+      const uint64_t z = e >> 40;
+      if (z != 0 && z != KMT_SAT) { k = e & ((1ull << 40) - 1ull); sz = z; pos += fwd ? K - 1 : -(K - 1); r.cnt += K - 1; return true; }
+    }
+    const int c = base(pos);
+    if (c < 1 || c > 4) return false;
+    const int cc = fwd ? 5 - c : c;
+    k = (uint64_t)P.acc[cc]; sz = (uint64_t)(P.acc[cc + 1] - P.acc[cc]);
+    return true;
+  };
+  auto extend = [&](int c) {
+    const uint64_t l = k + sz;
+    r.blk += ((l >> 8) != (k >> 8)) ? 2 : 1;
+    const uint64_t nk = occ_global(P, c, k), nl = occ_global(P, c, l);
+    k = nk; sz = nl - nk; ++r.cnt;
+  };
+  if (!start(false)) return r;
+  while (sz != 0 && pos > 0) {               // backward (ping_pong.cpp:15-22)
+    if (--budget < 0) return r;
+    const int c = base(--pos);
+    if (c < 1 || c > 4) return r;
+    extend(c);
+  }
+  if (sz != 0) { r.status = 1; return r; }   // ping_pong.cpp:24-25
+  r.b = pos;
+  if (!start(true)) return r;                // forward from begin (ping_pong.cpp:27-37)
+  while (sz != 0 && pos + 1 < len) {
+    if (--budget < 0) return r;
+    const int c = base(++pos);
+    if (c < 1 || c > 4) return r;
+    extend(5 - c);
+  }
+  if (sz != 0) return r;                     // cannot happen (see k_sfs_search); leave it to the owner
+  r.e = pos;
+  r.status = 0;
+  return r;
+}
+constexpr int SPRINT_BUDGET = 12;     // rank steps a helper spends on one link before giving it up
+
 // ------------------------------------------------------------------------------ v3 kernel
 // Micro-op pipeline.  ncu on the hybrid version of k_sfs_search_tma (profiles/r01e_*) showed a warp
 // iteration lasting ~12 us at 31 % issue utilisation: every divergent path of the state machine
@@ -1074,10 +1160,13 @@ __device__ __forceinline__ int coop_text_step(const SearchParams& P, int64_t g, 
 //            still in the thread's 16-base history register, which is the rule inside novel sequence)
 //   OP_KMT   restart, step 2: the jump-table entry of that K-mer
 //   OP_SSA   locate: the SA sample of the row (forward phase: + contig lookup for the mirror image)
-enum : int { OP_NONE = 0, OP_EXT = 1, OP_TXT = 2, OP_KMER = 3, OP_KMT = 4, OP_SSA = 5 };
+enum : int { OP_NONE = 0, OP_EXT = 1, OP_TXT = 2, OP_KMER = 3, OP_KMT = 4, OP_SSA = 5, OP_SPRINT = 6 };
 enum : int { ST_START = 0, ST_WALK = 1, ST_KMT = 2 };
 
-template <int MINB>
+// TAIL = false: the main kernel, thread per read; parks unfinished walks once the queue is dry (if P.cont).
+// TAIL = true: the tail kernel, WARP per parked walk: lane 0 owns it, the other lanes serve its
+// cooperative steps (located-match compare, sprint, block staging).
+template <int MINB, bool TAIL>
 __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const SearchParams P) {
   __shared__ __align__(128) uint4 stage[TMA_WARPS * 32 * 16];  // [warp][lane][2 blocks][8 slices]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1087,9 +1176,11 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     unpack_cta_loop(P);
     return;
   }
-  if (threadIdx.x == 0) atomicMin(P.stats + 4, globaltimer_ns());
+  if (!TAIL && threadIdx.x == 0) atomicMin(P.stats + 4, globaltimer_ns());
 
-  bool alive = true, have = false;
+  bool alive = !TAIL || lane == 0, have = false;
+  bool spr = false;   // the pending backward restart follows an SFS found by rank steps alone (novel sequence)
+  unsigned it = 0;
   int st = ST_START, phase = 0;
   uint32_t ridx = 0, kcode = 0;
   int64_t roff = 0;
@@ -1162,11 +1253,39 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     // ---- (1) advance to the next micro-op (ping_pong.cpp:15-47); no waits on memory except the
     //          hand-out of a new read and the rare walk that starts without the jump table
     int op = OP_NONE, c = 0;
+    if (!TAIL && P.cont != nullptr && (++it & 7u) == 0u && *reinterpret_cast<volatile unsigned int*>(P.dry) != 0u &&
+        (P.last_ready == nullptr || *reinterpret_cast<const volatile unsigned int*>(P.last_ready) != 0u)) {
+      // the queue is dry: park the walk for the tail kernel instead of finishing it at one micro-op
+      // per (slow) iteration of a warp that is emptying
+      if (alive && have) {
+        Cont ct;
+        ct.roff = roff; ct.delta = delta; ct.k = k; ct.s = s; ct.ridx = ridx; ct.hist = hist; ct.kcode = kcode;
+        ct.len = len; ct.pos = pos; ct.begin = begin; ct.chain_qs = chain_qs; ct.chain_end = chain_end; ct.hv = hv;
+        ct.n_ext = n_ext; ct.n_blk = n_blk; ct.n_txt = n_txt;
+        ct.phase = (uint8_t)phase; ct.st = (uint8_t)st; ct.tmode = tmode ? 1 : 0; ct.spr = spr ? 1 : 0;
+        P.cont[atomicAdd(P.n_cont, 1ull)] = ct;
+        have = false;
+      }
+      alive = false;
+    }
     while (alive && op == OP_NONE) {
+      if (TAIL && !have) {
+        const unsigned long long w = atomicAdd(P.work, 1ull);
+        if (w >= *P.n_cont) { alive = false; break; }
+        const Cont ct = P.cont[w];
+        roff = ct.roff; delta = ct.delta; k = ct.k; s = ct.s; ridx = ct.ridx; hist = ct.hist; kcode = ct.kcode;
+        len = ct.len; pos = ct.pos; begin = ct.begin; chain_qs = ct.chain_qs; chain_end = ct.chain_end; hv = ct.hv;
+        n_ext = ct.n_ext; n_blk = ct.n_blk; n_txt = ct.n_txt;
+        phase = ct.phase; st = ct.st; tmode = ct.tmode != 0; spr = ct.spr != 0;
+        have = true;
+        win.reset();
+        continue;
+      }
       if (!have) {
         const unsigned long long w = atomicAdd(P.work, 1ull);
         if (w >= (unsigned long long)P.n_reads) {
           if (w == (unsigned long long)P.n_reads) atomicMin(P.stats + 5, globaltimer_ns());   // the queue just ran dry
+          if (P.dry) *reinterpret_cast<volatile unsigned int*>(P.dry) = 1u;
           alive = false;
           break;
         }
@@ -1189,9 +1308,11 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
         st = ST_START;
         tmode = false;
         hv = 0;
+        spr = false;
         win.reset();
       }
       if (st == ST_START) {   // (re)start at pivot `pos`: jump table if K bases are there, else one base
+        if (TAIL && !phase && spr && P.kmt != nullptr && P.overlap == -1) { op = OP_SPRINT; continue; }
         if (P.kmt != nullptr && (phase ? pos + K <= len : pos + 1 >= K)) {
           // hv > 0 here means the history was left by the walk that ended at the pivot's neighbour:
           //   forward restart at begin (= the base the backward walk failed on): low bits = P[begin..]
@@ -1247,7 +1368,45 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
             pos = nb;
             phase = 0;
             st = ST_START;
+            spr = hv >= K + 1;
           }
+        }
+      }
+    }
+    // ---- tail sprint: the links of 32 consecutive restarts in one go
+    if (TAIL) {
+      for (unsigned smask = __ballot_sync(0xffffffffu, op == OP_SPRINT); smask; smask &= smask - 1) {
+        const int src = __ffs((int)smask) - 1;
+        const int64_t ro = __shfl_sync(0xffffffffu, roff, src);
+        const int ln = __shfl_sync(0xffffffffu, len, src);
+        const int s0 = __shfl_sync(0xffffffffu, pos, src);
+        const Link lk = lane_link(P, P.seq + ro, ln, s0 - lane, K, SPRINT_BUDGET);
+        unsigned blk_sum = (unsigned)lk.blk;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) blk_sum += __shfl_xor_sync(0xffffffffu, blk_sum, o);
+        int cur = s0;
+        bool done = false;
+        while (s0 - cur < 32 && cur >= 0) {       // warp-uniform: every lane follows the same chain
+          const int j = s0 - cur;
+          const int st_j = __shfl_sync(0xffffffffu, lk.status, j);
+          if (st_j == 2) break;                   // abandoned link: the owner walks on from `cur`
+          const int b_j = __shfl_sync(0xffffffffu, lk.b, j), e_j = __shfl_sync(0xffffffffu, lk.e, j);
+          const int cnt_j = __shfl_sync(0xffffffffu, lk.cnt, j);
+          if (lane == src) n_ext += (unsigned)cnt_j;
+          if (st_j == 1) { done = true; break; }                // reached the read start still matching
+          if (lane == src) on_sfs(b_j, e_j - b_j + 1);          // ping_pong.cpp:39-41
+          if (b_j == 0 || e_j - 1 < 0) { done = true; break; }  // ping_pong.cpp:42-47 with overlap = -1
+          cur = e_j - 1;
+        }
+        if (lane == src) {
+          n_blk += blk_sum;
+          if (done) finish_read();
+          else { pos = cur; phase = 0; st = ST_START; }
+          spr = !done && cur < s0;                 // no progress (first link abandoned): walk the next one alone
+          hv = 0;                                  // the history register does not follow the sprint
+          tmode = false;
+          win.id = -1; win.nid = -1;
+          op = OP_NONE;
         }
       }
     }
@@ -1571,8 +1730,10 @@ struct SearchScratch {
   uint64_t* d_key = nullptr; uint64_t* d_key2 = nullptr;
   uint32_t* d_len = nullptr; uint32_t* d_len2 = nullptr;
   void* d_tmp = nullptr;
+  void* d_cont = nullptr;   // parked walks between the main and the tail kernel
   cudaStream_t st = nullptr;
   ~SearchScratch() {
+    pfree(d_cont, st);
     pfree(d_ctr, st); pfree(d_key, st); pfree(d_key2, st); pfree(d_len, st); pfree(d_len2, st); pfree(d_tmp, st);
   }
 };
@@ -1619,15 +1780,20 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   P.overlap = overlap; P.assemble = assemble;
   SearchScratch S;
   S.st = st;
-  SVB_CUDA(pmalloc((void**)&S.d_ctr, 10 * sizeof(unsigned long long), st));
+  SVB_CUDA(pmalloc((void**)&S.d_ctr, 16 * sizeof(unsigned long long), st));
   // first guess of output capacity; exact count is known after the run, rerun once if it overflowed
   unsigned long long cap = assemble ? (unsigned long long)(4 * n_reads + 1024)
                                     : (unsigned long long)(R->total / 8 + 64 * n_reads + 1024);
   int grid = 0, cfgG = 0;
   SVB_TRY(pick_cfg(d.G, &cfgG));
   const int tma_minb = 9;
+  const int tail_minb = 8;   // the tail kernel carries the sprint: a few more registers
+  int tail_grid = 0;
+  const char* e2p = getenv("SVB_SEARCH_TAIL");   // SVB_SEARCH_TAIL=0: one kernel, every walk finished where it started
+  const bool two_phase = !(e2p && *e2p == '0');
   if (cfgG == -2) {
-    SVB_TRY(persistent_grid(k_sfs_search_mop<tma_minb>, TMA_WARPS * 32, d.device, &grid));
+    SVB_TRY(persistent_grid(k_sfs_search_mop<tma_minb, false>, TMA_WARPS * 32, d.device, &grid));
+    SVB_TRY(persistent_grid(k_sfs_search_mop<tail_minb, true>, TMA_WARPS * 32, d.device, &tail_grid));
   } else if (cfgG == 0) {
     SVB_TRY(persistent_grid(k_sfs_search_tma<tma_minb, 0>, TMA_WARPS * 32, d.device, &grid));
   } else if (cfgG == -1) {
@@ -1641,13 +1807,13 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   cudaEvent_t e0, e1;
   SVB_CUDA(cudaEventCreate(&e0));
   SVB_CUDA(cudaEventCreate(&e1));
-  unsigned long long ctr[10] = {0};
+  unsigned long long ctr[16] = {0};
   float kms = 0.f;
   for (int attempt = 0; attempt < 2; ++attempt) {
     pfree(S.d_key, st); pfree(S.d_len, st); S.d_key = nullptr; S.d_len = nullptr;
     SVB_CUDA(pmalloc((void**)&S.d_key, cap * 8, st));
     SVB_CUDA(pmalloc((void**)&S.d_len, cap * 4, st));
-    SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 10 * sizeof(unsigned long long), st));
+    SVB_CUDA(cudaMemsetAsync(S.d_ctr, 0, 16 * sizeof(unsigned long long), st));
     SVB_CUDA(cudaMemsetAsync(S.d_ctr + 6, 0xff, 2 * sizeof(unsigned long long), st));   // [6] first thread in, [7] queue empty: minima
     P.work = S.d_ctr + 0; P.out_count = S.d_ctr + 1; P.stats = S.d_ctr + 2;
     P.out_key = S.d_key; P.out_len = S.d_len; P.out_cap = cap;
@@ -1662,7 +1828,18 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
     }
     SVB_CUDA(cudaEventRecord(e0, st));
     if (cfgG == -2) {
-      k_sfs_search_mop<tma_minb><<<grid, TMA_WARPS * 32, 0, st>>>(P);
+      if (two_phase) {
+        if (!S.d_cont) SVB_CUDA(pmalloc(&S.d_cont, (size_t)grid * TMA_WARPS * 32 * sizeof(Cont), st));
+        P.cont = static_cast<Cont*>(S.d_cont); P.n_cont = S.d_ctr + 10; P.dry = reinterpret_cast<unsigned int*>(S.d_ctr + 11);
+        P.last_ready = (src && attempt == 0) ? src->d_ready + (src->n_chunks - 1) : nullptr;
+      }
+      k_sfs_search_mop<tma_minb, false><<<grid, TMA_WARPS * 32, 0, st>>>(P);
+      if (two_phase) {
+        SearchParams Q = P;
+        Q.work = S.d_ctr + 12; Q.ready = nullptr; Q.n_unpack = 0; Q.dry = nullptr;
+        k_sfs_search_mop<tail_minb, true><<<tail_grid, TMA_WARPS * 32, 0, st>>>(Q);
+        out->launches += 1;
+      }
     } else if (cfgG == 0) {
       k_sfs_search_tma<tma_minb, 0><<<grid, TMA_WARPS * 32, 0, st>>>(P);
     } else if (cfgG == -1) {
@@ -1712,8 +1889,8 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   out->n_blocks_touched = (int64_t)ctr[3];
   out->n_text_ext = (int64_t)ctr[4];
   if (getenv("SVB_SEARCH_STATS") && ctr[8])   // k_sfs_search_mop only
-    fprintf(stderr, "[k_sfs_search_mop] ext %llu blocks %llu text %llu | work queue empty after %.1f ms, last thread done after %.1f ms\n",
-            ctr[2], ctr[3], ctr[4], (ctr[7] - ctr[6]) * 1e-6, (ctr[8] - ctr[6]) * 1e-6);
+    fprintf(stderr, "[k_sfs_search_mop] ext %llu blocks %llu text %llu | work queue empty after %.1f ms, last warp done after %.1f ms, %llu walks finished by the tail kernel\n",
+            ctr[2], ctr[3], ctr[4], (ctr[7] - ctr[6]) * 1e-6, (ctr[8] - ctr[6]) * 1e-6, ctr[10]);
   const int64_t m = (int64_t)ctr[1];
   out->n_sfs = m;
   if (m == 0) return SVB_OK;
