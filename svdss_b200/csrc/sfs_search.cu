@@ -106,6 +106,7 @@ struct SearchParams {
   struct Cont* cont;
   unsigned long long* n_cont;   // continuations written (main) / to hand out (tail)
   unsigned int* dry;            // raised by the first thread that finds the queue empty
+  int sprint_budget;               // rank steps a helper lane spends on one link before giving it up
   const unsigned int* last_ready;  // streamed batch: flag of the last chunk (walks are parked only once it is up:
                                    // before that the queue is "empty" merely because every thread holds a
                                    // reservation for a read that has not arrived yet)
@@ -1143,7 +1144,8 @@ __device__ __forceinline__ Link lane_link(const SearchParams& P, const uint8_t* 
   r.status = 0;
   return r;
 }
-constexpr int SPRINT_BUDGET = 12;     // rank steps a helper spends on one link before giving it up
+constexpr int TAIL_OWNERS = 1;        // lanes of a tail-kernel warp that own a parked walk (the rest only help)
+constexpr int SPRINT_BUDGET = 16;     // rank steps a helper spends on one link before giving it up
 
 // ------------------------------------------------------------------------------ v3 kernel
 // Micro-op pipeline.  ncu on the hybrid version of k_sfs_search_tma (profiles/r01e_*) showed a warp
@@ -1164,8 +1166,9 @@ enum : int { OP_NONE = 0, OP_EXT = 1, OP_TXT = 2, OP_KMER = 3, OP_KMT = 4, OP_SS
 enum : int { ST_START = 0, ST_WALK = 1, ST_KMT = 2 };
 
 // TAIL = false: the main kernel, thread per read; parks unfinished walks once the queue is dry (if P.cont).
-// TAIL = true: the tail kernel, WARP per parked walk: lane 0 owns it, the other lanes serve its
-// cooperative steps (located-match compare, sprint, block staging).
+// TAIL = true: the tail kernel: TAIL_OWNERS lanes of a warp own one parked walk each, the other lanes
+// only serve the cooperative steps (located-match compare, sprint, block staging) -- few walks per warp
+// keep an iteration short, which is what a long serial walk needs.
 template <int MINB, bool TAIL>
 __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const SearchParams P) {
   __shared__ __align__(128) uint4 stage[TMA_WARPS * 32 * 16];  // [warp][lane][2 blocks][8 slices]
@@ -1178,7 +1181,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
   }
   if (!TAIL && threadIdx.x == 0) atomicMin(P.stats + 4, globaltimer_ns());
 
-  bool alive = !TAIL || lane == 0, have = false;
+  bool alive = !TAIL || (lane & (32 / TAIL_OWNERS - 1)) == 0, have = false;
   bool spr = false;   // the pending backward restart follows an SFS found by rank steps alone (novel sequence)
   unsigned it = 0;
   int st = ST_START, phase = 0;
@@ -1380,7 +1383,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
         const int64_t ro = __shfl_sync(0xffffffffu, roff, src);
         const int ln = __shfl_sync(0xffffffffu, len, src);
         const int s0 = __shfl_sync(0xffffffffu, pos, src);
-        const Link lk = lane_link(P, P.seq + ro, ln, s0 - lane, K, SPRINT_BUDGET);
+        const Link lk = lane_link(P, P.seq + ro, ln, s0 - lane, K, P.sprint_budget);
         unsigned blk_sum = (unsigned)lk.blk;
 #pragma unroll
         for (int o = 16; o; o >>= 1) blk_sum += __shfl_xor_sync(0xffffffffu, blk_sum, o);
@@ -1567,6 +1570,8 @@ static void fill_params(SearchParams& P, const IndexDev& d) {
   if (d.d_text && !(e && *e == '0')) {
     P.text = d.d_text; P.ssa = d.d_ssa; P.tstart = d.d_tstart; P.n_contigs = d.n_contigs; P.ss_log = d.ss_log;
   }
+  P.sprint_budget = SPRINT_BUDGET;
+  if (const char* eb = getenv("SVB_SPRINT_BUDGET")) P.sprint_budget = atoi(eb);
   const char* ej = getenv("SVB_SEARCH_JUMP");   // SVB_SEARCH_JUMP=0: restarts walk from one base
   if (d.d_kmt && !(ej && *ej == '0')) { P.kmt = d.d_kmt; P.kmer_k = d.kmer_k; }
 }

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 READS=${READS:-1000000}
 TAG=${TAG:-src}
 export SVB_NO_STREAM=1
-SVB_PROFILE=1 timeout ${NCU_TIMEOUT:-900} ncu --profile-from-start off --clock-control none --import-source on -k regex:k_sfs_search -c 1 \
+SVB_PROFILE=1 timeout ${NCU_TIMEOUT:-900} ncu --profile-from-start off --clock-control none --import-source on -k regex:k_sfs_search ${NCU_SKIP:+--launch-skip $NCU_SKIP} -c 1 \
   --section SourceCounters --section WarpStateStats --section SchedulerStats \
   --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,gpu__time_duration.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum,l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active \
   -o gpurun_out/prof_$TAG -f python bench.py --reads $READS --steps 1 --warmup 0 --no-cpu-baseline --no-rank-walk $EXTRA > gpurun_out/prof_bench_$TAG.log 2>&1
