@@ -106,6 +106,7 @@ struct SearchParams {
   struct Cont* cont;
   unsigned long long* n_cont;   // continuations written (main) / to hand out (tail)
   unsigned int* dry;            // raised by the first thread that finds the queue empty
+  int stats_on;                    // SVB_SEARCH_STATS: extra counters
   int sprint_budget;               // rank steps a helper lane spends on one link before giving it up
   const unsigned int* last_ready;  // streamed batch: flag of the last chunk (walks are parked only once it is up:
                                    // before that the queue is "empty" merely because every thread holds a
@@ -1090,21 +1091,23 @@ struct Cont {
 // serial walk; a link that runs long (the restart sits in matching sequence) is abandoned and the
 // owner carries on from there by itself.
 struct Link { int b, e, cnt, blk, status; };   // status 0: SFS [b, e]; 1: read start reached still matching; 2: abandoned
-__device__ __forceinline__ Link lane_link(const SearchParams& P, const uint8_t* __restrict__ rd, int len, int s0, int K,
-                                          int budget) {
+// All 32 lanes walk their links in lockstep: per round every lane names the index blocks of its next
+// rank extension, the warp stages them together (cpa_fetch: coalesced 128-byte lines, as in the rank
+// walk kernel) and each lane finishes from shared memory.  Per-lane global loads of the blocks made
+// the first version of the sprint L1-request bound (profiles/r01i_sfs_tail_src.txt).
+__device__ __forceinline__ Link sprint_links(const SearchParams& P, int64_t roff, int len, int s_lane, int K, int budget,
+                                             int lane, const uint4* my, uint32_t warp_stage_s) {
   Link r;
   r.b = r.e = r.cnt = r.blk = 0; r.status = 2;
-  if (s0 < 0 || s0 >= len) return r;
+  const uint8_t* rd = P.seq + roff;
   uint64_t k = 0, sz = 0;
-  int pos = s0;
-  // rd = P.seq + roff is not 8-byte aligned in general: address the words from the buffer start
-  const int64_t roff = rd - P.seq;
-  const int64_t min_word = 0;
+  int pos = s_lane;
+  int phs = (s_lane < 0 || s_lane >= len) ? 4 : 0;   // 0/2: start backward/forward, 1/3: walking backward/forward, 4: done
   auto base = [&](int i) { return (int)__ldcg(rd + i); };
   auto start = [&](bool fwd) {   // rb3_fmd_set_intv at `pos` (+ K-1 extensions through the jump table); false: N in the way
     if (fwd ? pos + K <= len : pos + 1 >= K) {
-      Win16 w;   // the K bases in one round trip (three aligned 8-byte loads), not K byte loads in a row
-      load16(P.seq, roff + (fwd ? pos : pos - K + 1), w, min_word);
+      Win16 w;   // the K bases in one round trip (three aligned 8-byte loads)
+      load16(P.seq, roff + (fwd ? pos : pos - K + 1), w, 0);
       uint32_t code;
       if (!window_kmer(w, K, code)) return false;
       const uint64_t e = __ldg(P.kmt + (fwd ? kmer_rc(code, K) : code));
@@ -1117,31 +1120,34 @@ __device__ __forceinline__ Link lane_link(const SearchParams& P, const uint8_t* 
     k = (uint64_t)P.acc[cc]; sz = (uint64_t)(P.acc[cc + 1] - P.acc[cc]);
     return true;
   };
-  auto extend = [&](int c) {
-    const uint64_t l = k + sz;
-    r.blk += ((l >> 8) != (k >> 8)) ? 2 : 1;
-    const uint64_t nk = occ_global(P, c, k), nl = occ_global(P, c, l);
-    k = nk; sz = nl - nk; ++r.cnt;
-  };
-  if (!start(false)) return r;
-  while (sz != 0 && pos > 0) {               // backward (ping_pong.cpp:15-22)
-    if (--budget < 0) return r;
-    const int c = base(--pos);
-    if (c < 1 || c > 4) return r;
-    extend(c);
+  for (;;) {
+    if (phs == 0 || phs == 2) phs = start(phs == 2) ? phs + 1 : 4;
+    bool ext = false;
+    int c = 0;
+    if (phs == 1) {                               // backward (ping_pong.cpp:15-25)
+      if (sz != 0 && pos > 0) {
+        c = --budget < 0 ? 0 : base(--pos);
+        if (c < 1 || c > 4) phs = 4; else ext = true;
+      } else if (sz != 0) { r.status = 1; phs = 4; }
+      else { r.b = pos; phs = 2; }
+    } else if (phs == 3) {                        // forward from begin (ping_pong.cpp:27-41)
+      if (sz != 0 && pos + 1 < len) {
+        c = --budget < 0 ? 0 : base(++pos);
+        if (c < 1 || c > 4) phs = 4; else { c = 5 - c; ext = true; }
+      } else if (sz != 0) { phs = 4; }            // cannot happen (see k_sfs_search); leave it to the owner
+      else { r.e = pos; r.status = 0; phs = 4; }
+    }
+    if (!__any_sync(0xffffffffu, phs != 4)) break;
+    const uint32_t bk = ext ? (uint32_t)(k >> 8) : NOBLK, bl = ext ? (uint32_t)((k + sz) >> 8) : NOBLK;
+    cpa_fetch(P, bk, bl, warp_stage_s, lane);
+    if (ext) {
+      const bool two = bl != bk;
+      tma_consume(P, my, two, c, k, sz, lane);
+      ++r.cnt;
+      r.blk += two ? 2 : 1;
+    }
+    __syncwarp();
   }
-  if (sz != 0) { r.status = 1; return r; }   // ping_pong.cpp:24-25
-  r.b = pos;
-  if (!start(true)) return r;                // forward from begin (ping_pong.cpp:27-37)
-  while (sz != 0 && pos + 1 < len) {
-    if (--budget < 0) return r;
-    const int c = base(++pos);
-    if (c < 1 || c > 4) return r;
-    extend(5 - c);
-  }
-  if (sz != 0) return r;                     // cannot happen (see k_sfs_search); leave it to the owner
-  r.e = pos;
-  r.status = 0;
   return r;
 }
 constexpr int TAIL_OWNERS = 1;        // lanes of a tail-kernel warp that own a parked walk (the rest only help)
@@ -1172,14 +1178,19 @@ enum : int { ST_START = 0, ST_WALK = 1, ST_KMT = 2 };
 template <int MINB, bool TAIL>
 __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const SearchParams P) {
   __shared__ __align__(128) uint4 stage[TMA_WARPS * 32 * 16];  // [warp][lane][2 blocks][8 slices]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   uint4* my = stage + (warp * 32 + lane) * 16;
-  const uint32_t warp_stage_s = smem_u32(stage + warp * 32 * 16);
+  uint32_t warp_stage_s = smem_u32(stage + warp * 32 * 16);
+  // pin these in registers: under the register cap the compiler otherwise re-derives them (S2R + cvta)
+  // inside the hot loops -- 31 % of the tail kernel's instructions in profiles/r01k_sfs_tail_lines.txt
+  if (TAIL) asm volatile("" : "+r"(lane), "+r"(warp_stage_s), "+l"(my));
   if (P.n_unpack > 0 && (int)blockIdx.x < P.n_unpack) {   // packed streamed batch: this CTA feeds the others
     unpack_cta_loop(P);
     return;
   }
   if (!TAIL && threadIdx.x == 0) atomicMin(P.stats + 4, globaltimer_ns());
+  const unsigned long long t_begin = TAIL ? globaltimer_ns() : 0ull;
 
   bool alive = !TAIL || (lane & (32 / TAIL_OWNERS - 1)) == 0, have = false;
   bool spr = false;   // the pending backward restart follows an SFS found by rank steps alone (novel sequence)
@@ -1274,7 +1285,11 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     while (alive && op == OP_NONE) {
       if (TAIL && !have) {
         const unsigned long long w = atomicAdd(P.work, 1ull);
-        if (w >= *P.n_cont) { alive = false; break; }
+        if (w >= *P.n_cont) {
+          if (P.stats_on) atomicAdd(P.stats + 7, globaltimer_ns() - t_begin);   // this warp's busy time
+          alive = false;
+          break;
+        }
         const Cont ct = P.cont[w];
         roff = ct.roff; delta = ct.delta; k = ct.k; s = ct.s; ridx = ct.ridx; hist = ct.hist; kcode = ct.kcode;
         len = ct.len; pos = ct.pos; begin = ct.begin; chain_qs = ct.chain_qs; chain_end = ct.chain_end; hv = ct.hv;
@@ -1383,16 +1398,17 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
         const int64_t ro = __shfl_sync(0xffffffffu, roff, src);
         const int ln = __shfl_sync(0xffffffffu, len, src);
         const int s0 = __shfl_sync(0xffffffffu, pos, src);
-        const Link lk = lane_link(P, P.seq + ro, ln, s0 - lane, K, P.sprint_budget);
+        const Link lk = sprint_links(P, ro, ln, s0 - lane, K, P.sprint_budget, lane, my, warp_stage_s);
         unsigned blk_sum = (unsigned)lk.blk;
 #pragma unroll
         for (int o = 16; o; o >>= 1) blk_sum += __shfl_xor_sync(0xffffffffu, blk_sum, o);
-        int cur = s0;
-        bool done = false;
+        int cur = s0, n_links = 0;
+        bool done = false, gave_up = false;
         while (s0 - cur < 32 && cur >= 0) {       // warp-uniform: every lane follows the same chain
           const int j = s0 - cur;
           const int st_j = __shfl_sync(0xffffffffu, lk.status, j);
-          if (st_j == 2) break;                   // abandoned link: the owner walks on from `cur`
+          if (st_j == 2) { gave_up = true; break; }   // abandoned link: the owner walks on from `cur`
+          ++n_links;
           const int b_j = __shfl_sync(0xffffffffu, lk.b, j), e_j = __shfl_sync(0xffffffffu, lk.e, j);
           const int cnt_j = __shfl_sync(0xffffffffu, lk.cnt, j);
           if (lane == src) n_ext += (unsigned)cnt_j;
@@ -1403,6 +1419,10 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
         }
         if (lane == src) {
           n_blk += blk_sum;
+          if (P.stats_on) {
+            atomicAdd(P.stats + 11, 1ull); atomicAdd(P.stats + 12, (unsigned long long)n_links);
+            if (gave_up) atomicAdd(P.stats + 13, 1ull);
+          }
           if (done) finish_read();
           else { pos = cur; phase = 0; st = ST_START; }
           spr = !done && cur < s0;                 // no progress (first link abandoned): walk the next one alone
@@ -1570,6 +1590,7 @@ static void fill_params(SearchParams& P, const IndexDev& d) {
   if (d.d_text && !(e && *e == '0')) {
     P.text = d.d_text; P.ssa = d.d_ssa; P.tstart = d.d_tstart; P.n_contigs = d.n_contigs; P.ss_log = d.ss_log;
   }
+  P.stats_on = getenv("SVB_SEARCH_STATS") != nullptr;
   P.sprint_budget = SPRINT_BUDGET;
   if (const char* eb = getenv("SVB_SPRINT_BUDGET")) P.sprint_budget = atoi(eb);
   const char* ej = getenv("SVB_SEARCH_JUMP");   // SVB_SEARCH_JUMP=0: restarts walk from one base
@@ -1792,7 +1813,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   int grid = 0, cfgG = 0;
   SVB_TRY(pick_cfg(d.G, &cfgG));
   const int tma_minb = 9;
-  const int tail_minb = 8;   // the tail kernel carries the sprint: a few more registers
+  const int tail_minb = 6;   // the tail kernel carries the sprint: more registers, 18 warps per SM
   int tail_grid = 0;
   const char* e2p = getenv("SVB_SEARCH_TAIL");   // SVB_SEARCH_TAIL=0: one kernel, every walk finished where it started
   const bool two_phase = !(e2p && *e2p == '0');
@@ -1896,6 +1917,9 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   if (getenv("SVB_SEARCH_STATS") && ctr[8])   // k_sfs_search_mop only
     fprintf(stderr, "[k_sfs_search_mop] ext %llu blocks %llu text %llu | work queue empty after %.1f ms, last warp done after %.1f ms, %llu walks finished by the tail kernel\n",
             ctr[2], ctr[3], ctr[4], (ctr[7] - ctr[6]) * 1e-6, (ctr[8] - ctr[6]) * 1e-6, ctr[10]);
+  if (getenv("SVB_SEARCH_STATS") && ctr[13])
+    fprintf(stderr, "[k_sfs_search_mop tail] sprints %llu, links resolved by them %llu (%.1f per sprint), sprints ended by an abandoned link %llu; mean busy time of a warp %.1f ms\n",
+            ctr[13], ctr[14], ctr[14] / (double)ctr[13], ctr[15], ctr[9] * 1e-6 / (double)(tail_grid * TMA_WARPS));
   const int64_t m = (int64_t)ctr[1];
   out->n_sfs = m;
   if (m == 0) return SVB_OK;
