@@ -299,7 +299,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(n_reads, idx.block_bytes, "k_sfs_search_mop") if args.ref_bp == REF_BP else None,
                      "peak_source": peak_src,
-                     "kernel": ("k_sfs_search_mop (thread-per-read micro-op pipeline: cp.async-staged 128 B index blocks, located-match text compare, K-mer jump table)"
+                     "kernel": ("k_sfs_search_mop main + tail launch (thread-per-read micro-op pipeline: cp.async-staged 128 B index blocks, warp-cooperative located-match compare, K-mer jump table; parked walks finished warp-per-walk with sprints)"
                                 if idx.block_bytes == 128 and not os.environ.get("SVB_SEARCH_CFG")
                                 else "k_sfs_search cfg=%s" % os.environ.get("SVB_SEARCH_CFG", "4x1")),
                      "kernel_ms": kernel_ms,

@@ -164,7 +164,6 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       }
       const int n_ord = N - 2;
       for (int v = 2 + lane; v < N; v += 32) { W.order[W.rank[v]] = v; }
-      for (int v = lane; v < N; v += 32) { W.mpl[v] = 0x7fffffff; W.mpr[v] = -1; }
       for (int s = lane; s <= n_ord + 1; s += 32) W.cnt[s] = 0;
       __syncwarp();
       // remain[]: heaviest out-neighbour chain length to the sink (lane 0, reverse rank order)
@@ -192,20 +191,24 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           if (j > 1) t |= (c1 <= c2) ? (1u << 7) : (1u << 8);
           W.TB[j] = t;
         }
-        if (lane == 0) {
-          W.beg[0] = 0; W.end[0] = end0;
-          for (int e = W.first_out[0]; e >= 0; e = W.enout[e]) {
-            const int o = W.eto[e];
-            W.mpl[o] = min(W.mpl[o], 1); W.mpr[o] = max(W.mpr[o], 1);
-          }
-        }
+        // mpl[v] / mpr[v] = (first / last column of row v's maximum) + 1: what v offers to its
+        // successors' bands.  A row PULLS the min / max over its in-edges (the same min / max abPOA
+        // pushes along out-edges after each row) -- no out-edge walk, no per-read reset of the arrays.
+        if (lane == 0) { W.beg[0] = 0; W.end[0] = end0; W.mpl[0] = 1; W.mpr[0] = 1; }
         __syncwarp();
       }
       // ---- graph rows in rank order
+      int v_next = n_ord > 0 ? W.order[0] : 0;
       for (int r = 0; r < n_ord; ++r) {
-        const int v = W.order[r];
+        const int v = v_next;
+        if (r + 1 < n_ord) v_next = W.order[r + 1];   // in flight while this row is computed
         const int c = ql - W.remain[v] + 1;
-        int b = max(0, min(W.mpl[v], c) - w), en = min(ql, max(W.mpr[v], c) + w);
+        int pl = 0x7fffffff, pr = -1;
+        for (int e = W.first_in[v]; e >= 0; e = W.enin[e]) {
+          const int p = W.efrom[e];
+          pl = min(pl, W.mpl[p]); pr = max(pr, W.mpr[p]);
+        }
+        int b = max(0, min(pl, c) - w), en = min(ql, max(pr, c) + w);
         if (b > en) b = en;
         if (en - b + 1 > Wc) { en = b + Wc - 1; status |= POA_CLAMPED; }
         const int bv = W.base[v];
@@ -282,13 +285,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           l_ = min(l_, __shfl_xor_sync(0xffffffffu, l_, o));
           r_ = max(r_, __shfl_xor_sync(0xffffffffu, r_, o));
         }
-        if (lane == 0) {
-          W.beg[v] = b; W.end[v] = en;
-          for (int e = W.first_out[v]; e >= 0; e = W.enout[e]) {
-            const int o = W.eto[e];
-            W.mpl[o] = min(W.mpl[o], l_ + 1); W.mpr[o] = max(W.mpr[o], r_ + 1);
-          }
-        }
+        if (lane == 0) { W.beg[v] = b; W.end[v] = en; W.mpl[v] = l_ + 1; W.mpr[v] = r_ + 1; }
         __syncwarp();
       }
       PHASE(t_dp);

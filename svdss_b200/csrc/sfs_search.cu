@@ -453,14 +453,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 // streamed batch: wait until the chunk holding a read's last base has landed.  The chunks are fed by
 // copies (and, for packed input, unpack kernels) queued behind this kernel; if they never arrive --
-// a scheduling assumption broken -- give up after 20 s instead of hanging the device: stats[3] tells
+// a scheduling assumption broken -- give up after 60 s instead of hanging the device: stats[3] tells
 // the host, which fails the call.
 __device__ __forceinline__ bool wait_chunk(const volatile unsigned int* flag, unsigned long long* stall_flag) {
   if (*flag != 0u) return true;
   const unsigned long long t0 = globaltimer_ns();
   while (*flag == 0u) {
     __nanosleep(500);
-    if (globaltimer_ns() - t0 > 20000000000ull || *reinterpret_cast<volatile unsigned long long*>(stall_flag) != 0ull) {
+    if (globaltimer_ns() - t0 > 60000000000ull || *reinterpret_cast<volatile unsigned long long*>(stall_flag) != 0ull) {
       atomicExch(stall_flag, 1ull);
       return false;
     }
