@@ -276,6 +276,15 @@ def run_ours(args):
                      "reads_per_s": n_reads / (rk_ms * 1e-3), "extensions_per_s": rr[-1].n_ext / (rk_ms * 1e-3),
                      "traffic": ncu_traffic(n_reads, idx.block_bytes, "k_sfs_search_tma rank walk") if args.ref_bp == REF_BP else None,
                      "kernel": "k_sfs_search_tma<9,1> (SVB_SEARCH_CFG=cpa SVB_SEARCH_TEXT=0 SVB_SEARCH_JUMP=0): every extension is an Occ lookup in a 128 B block"}
+    # "FMD rank GB/s" (SURVEY 8d): 2^26 device-generated random (k, k+delta) extensions on this index
+    fmd_rank = None
+    if not args.no_rank_walk and idx.block_bytes == 128:
+        fmd_rank = []
+        for delta in (1, 1 << 10, 1 << 20):
+            ms, blk = idx.rank_bench(1 << 26, delta, seed=7, iters=3)
+            gbs = blk * idx.block_bytes / ms / 1e6
+            fmd_rank.append({"delta": delta, "GB_s": gbs, "frac_of_peak": gbs / peak, "blocks_per_extension": blk / float(1 << 26),
+                             "G_extensions_per_s": (1 << 26) / ms / 1e6})
     out = {
         "metric": "SFS-extracted reads/sec (FMD ping-pong search)",
         "value": world * n_reads / (ms_step * 1e-3),
@@ -311,6 +320,7 @@ def run_ours(args):
                      "algorithmic_bytes": alg_bytes, "index_blocks": blocks, "text_extensions": text_ext,
                      "extensions_per_s": n_ext / (kernel_ms * 1e-3)},
         "roofline_rank_walk": rank_walk,
+        "fmd_rank_microbench": fmd_rank,
         "clocks": clocks,
         "clocks_e2e": clocks_e,
     }
