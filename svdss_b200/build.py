@@ -48,7 +48,7 @@ def build_lib(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         sys.stderr.write("\n".join(log))
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++"])
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++"])
     return LIB
 
 
