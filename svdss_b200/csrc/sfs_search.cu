@@ -996,15 +996,16 @@ __device__ __forceinline__ void win32_words(const Win32& w, uint64_t o[4]) {
 // staging for the lanes that have an extension pending (a minority once located matches and the jump
 // table carry most of the walk): four of them per round, eight lanes x 16 bytes per block
 __device__ __forceinline__ void cpa_issue_sparse(const SearchParams& P, uint32_t bk, uint32_t bl, uint32_t warp_stage_s,
-                                                 int lane) {
-  unsigned m = __ballot_sync(0xffffffffu, bk != NOBLK);
+                                                 int lane, uint8_t* pend /* 32 bytes of shared memory per warp */) {
+  // compact the pending lanes into pend[0..n): rank among the pending = popcount of the lower lanes
+  const unsigned m = __ballot_sync(0xffffffffu, bk != NOBLK);
+  const int n = __popc(m);
+  if (bk != NOBLK) pend[__popc(m & ((1u << lane) - 1u))] = (uint8_t)lane;
+  __syncwarp();
   const int sub = lane >> 3, j = lane & 7;
-  while (m) {
-    // the four lowest pending lanes of this round (warp-uniform), one per 8-lane group
-    const unsigned m1 = m & (m - 1), m2 = m1 & (m1 - 1), m3 = m2 & (m2 - 1);
-    const unsigned pick = sub == 0 ? m : sub == 1 ? m1 : sub == 2 ? m2 : m3;
-    const bool on = pick != 0u;
-    const unsigned t = on ? (unsigned)(__ffs((int)pick) - 1) : 0u;
+  for (int i = sub; i < ((n + 3) & ~3); i += 4) {   // warp-uniform trip count; 8-lane group `sub` takes entry i
+    const bool on = i < n;
+    const unsigned t = on ? pend[i] : 0u;
     const uint32_t xk = __shfl_sync(0xffffffffu, bk, (int)t);
     const uint32_t xl = __shfl_sync(0xffffffffu, bl, (int)t);
     if (on) {
@@ -1012,7 +1013,6 @@ __device__ __forceinline__ void cpa_issue_sparse(const SearchParams& P, uint32_t
       cp_async16(dst, P.blocks + (uint64_t)xk * 8 + j);
       if (xl != xk) cp_async16(dst + 128u, P.blocks + (uint64_t)xl * 8 + j);
     }
-    m = m3 & (m3 - 1);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -1178,6 +1178,7 @@ enum : int { ST_START = 0, ST_WALK = 1, ST_KMT = 2 };
 template <int MINB, bool TAIL>
 __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const SearchParams P) {
   __shared__ __align__(128) uint4 stage[TMA_WARPS * 32 * 16];  // [warp][lane][2 blocks][8 slices]
+  __shared__ uint8_t pend_all[TMA_WARPS * 32];                  // per warp: lanes with an extension pending
   int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   uint4* my = stage + (warp * 32 + lane) * 16;
@@ -1447,7 +1448,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
     }
     const uint32_t bk = op == OP_EXT ? (uint32_t)(k >> 8) : NOBLK;
     const uint32_t bl = op == OP_EXT ? (uint32_t)((k + s) >> 8) : NOBLK;
-    cpa_issue_sparse(P, bk, bl, warp_stage_s, lane);
+    cpa_issue_sparse(P, bk, bl, warp_stage_s, lane, pend_all + warp * 32);
     // located matches: the warp walks up to 1024 bases for each lane that is in that mode, while
     // the index blocks of the other lanes are on their way
     for (unsigned tmask = __ballot_sync(0xffffffffu, op == OP_TXT); tmask; tmask &= tmask - 1) {
