@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <memory>
@@ -114,7 +115,8 @@ class BgzfSource {
       std::vector<Blk> blks;
       in.clear();
       size_t out_total = 0;
-      const size_t window = (size_t)64 << 20;   // compressed bytes per window
+      size_t window = (size_t)64 << 20;         // compressed bytes per window
+      if (const char* e = getenv("SVB_BGZF_WINDOW")) { const long long v = atoll(e); if (v > 0) window = (size_t)v; }   // tests: force records across windows
       while (in.size() < window) {
         uint8_t h[18];
         const size_t got = fread(h, 1, 18, f_);

@@ -121,3 +121,25 @@ def test_fuzz_ratio_matches_lcs_definition(exe):
         assert r.returncode == 0
         assert abs(float(r.stdout) - call_model.fuzz_ratio(a, b)) < 1e-5, (a, b)
     assert abs(call_model.fuzz_ratio(*cases[0]) - 96.5517241) < 1e-6
+
+
+def test_bam_reader_records_across_inflate_windows(exe, world, tmp_path):
+    """The BAM reader parses records in place inside an inflated window and copies only the ones that
+    straddle two windows; a one-block window forces that path on (nearly) every record. Same clusters,
+    and `smooth` writes the same records."""
+    base, _ = run_clusterer(exe, world, 4)
+    env = dict(os.environ, SVB_BGZF_WINDOW="1")
+    out = os.path.join(world["d"], "clusters_win.txt")
+    r = subprocess.run([exe, "call", "--reference", world["fa"], "--bam", world["bam"], "--sfs", world["sfs"], "--threads", "4",
+                        "--cluster-only", "--clusters", out], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert open(out).read() == base
+    outs = []
+    for e in (os.environ, env):
+        p = str(tmp_path / ("s%d.bam" % len(outs)))
+        with open(p, "wb") as f:
+            r = subprocess.run([exe, "smooth", "--reference", world["fa"], "--bam", world["bam"]], stdout=f, stderr=subprocess.PIPE, env=dict(e))
+        assert r.returncode == 0
+        from bam_writer import read_bam
+        outs.append(read_bam(p))
+    assert outs[0] == outs[1] and len(outs[0][2]) > 100
