@@ -83,3 +83,48 @@ def test_assemble_edge_cases():
     assert oracle.assemble([(8, 2), (5, 3)]) == [(5, 3), (8, 2)]
     assert oracle.assemble([(7, 4), (5, 3)]) == [(5, 6)]
     assert ref_model.assemble([(7, 4), (5, 3), (20, 2), (10, 1)]) == oracle.assemble([(7, 4), (5, 3), (20, 2), (10, 1)])
+
+
+def test_property_three_statements_agree():
+    """hypothesis: on arbitrary small references and reads (N included, both strands, empty and
+    one-base reads) the literal ping_pong.cpp transcription over a bidirectional FMD, the
+    occurrence-only definition and the C oracle give the same SFS list, with strictly
+    decreasing starts and ends, and every SFS is absent from the reference while both of its
+    one-base-shorter ends occur."""
+    from hypothesis import given, settings, strategies as st
+
+    base = st.integers(min_value=1, max_value=5)
+    contig = st.lists(base, min_size=1, max_size=60)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(contig, min_size=1, max_size=3), st.lists(st.lists(base, min_size=0, max_size=50), min_size=1, max_size=4),
+           st.data())
+    def check(contigs, reads, data):
+        contigs = [np.array(c, np.uint8) for c in contigs]
+        # half of the reads are cut out of the reference (either strand) so that long matches occur
+        for i in range(len(reads)):
+            if data.draw(st.booleans()):
+                c = contigs[data.draw(st.integers(0, len(contigs) - 1))]
+                a = data.draw(st.integers(0, len(c) - 1)); b = data.draw(st.integers(a + 1, len(c)))
+                piece = c[a:b] if data.draw(st.booleans()) else synth.revcomp6(c[a:b])
+                reads[i] = reads[i][:len(reads[i]) // 2] + [int(x) for x in piece] + reads[i][len(reads[i]) // 2:]
+        fmd = ref_model.NaiveFMD(contigs)
+        T, SA, bwt = oracle_index(contigs)
+        fm = oracle.FMIndex(bwt)
+        arrs = [np.array(r, np.uint8) for r in reads]
+        got_fm, _ = fm_results(fm, arrs)
+        strands = [c.tobytes() for c in contigs] + [synth.revcomp6(c).tobytes() for c in contigs]
+        occurs = lambda w: any(w.tobytes() in s for s in strands)
+        for r, g in zip(arrs, got_fm):
+            if len(r) == 0:
+                assert g == []
+                continue
+            a = ref_model.ping_pong_search(fmd, [int(x) for x in r] + [0])
+            assert a == ref_model.sfs_definition(contigs, r) == oracle.sfs_spec(T, SA, r) == g
+            for x, y in zip(a, a[1:]):
+                assert y[0] < x[0] and y[0] + y[1] < x[0] + x[1]
+            for qs, ln in a:
+                w = r[qs:qs + ln]
+                assert not occurs(w) and (ln == 1 or (occurs(w[1:]) and occurs(w[:-1])))
+
+    check()
