@@ -51,7 +51,7 @@ struct PoaParams {
 // per-slot workspace carving (all int32 unless noted); must match poa_ws_bytes()
 struct PoaWs {
   uint8_t* base;
-  int *rank, *order, *first_in, *last_in, *first_out, *last_out, *ring, *remain, *mpl, *mpr, *beg, *end, *cnt;
+  int *rank, *order, *first_in, *last_in, *first_out, *last_out, *ring, *remain, *mpl, *mpr, *beg, *end, *cnt, *in1;
   int *efrom, *eto, *ew, *enin, *enout;
   int *op_node, *op_q, *new_anchor, *new_id;
   int *H, *E1, *E2;
@@ -68,7 +68,7 @@ __host__ __device__ inline int64_t poa_ws_carve(uint8_t* p, int ncap, int ecap, 
   a = take(ncap); if (w) w->base = p + a;
   TAKE_I(rank, ncap); TAKE_I(order, ncap); TAKE_I(first_in, ncap); TAKE_I(last_in, ncap); TAKE_I(first_out, ncap);
   TAKE_I(last_out, ncap); TAKE_I(ring, ncap); TAKE_I(remain, ncap); TAKE_I(mpl, ncap); TAKE_I(mpr, ncap);
-  TAKE_I(beg, ncap); TAKE_I(end, ncap); TAKE_I(cnt, ncap + 2);
+  TAKE_I(beg, ncap); TAKE_I(end, ncap); TAKE_I(cnt, ncap + 2); TAKE_I(in1, ncap);
   TAKE_I(efrom, ecap); TAKE_I(eto, ecap); TAKE_I(ew, ecap); TAKE_I(enin, ecap); TAKE_I(enout, ecap);
   TAKE_I(op_node, ncap + lmax + 4); TAKE_I(op_q, ncap + lmax + 4); TAKE_I(new_anchor, lmax + 2); TAKE_I(new_id, lmax + 2);
   TAKE_I(H, (int64_t)ncap * wcap); TAKE_I(E1, (int64_t)ncap * wcap); TAKE_I(E2, (int64_t)ncap * wcap);
@@ -84,7 +84,7 @@ struct Graph {
   __device__ int node(uint8_t b) {
     if (n >= ncap) { overflow = true; return ncap - 1; }
     const int v = n++;
-    w.base[v] = b; w.rank[v] = -1; w.first_in[v] = w.last_in[v] = w.first_out[v] = w.last_out[v] = -1; w.ring[v] = v;
+    w.base[v] = b; w.rank[v] = -1; w.first_in[v] = w.last_in[v] = w.first_out[v] = w.last_out[v] = -1; w.ring[v] = v; w.in1[v] = 0;
     return v;
   }
   __device__ void edge(int u, int v) {
@@ -95,7 +95,7 @@ struct Graph {
     w.efrom[e] = u; w.eto[e] = v; w.ew[e] = 1; w.enin[e] = -1; w.enout[e] = -1;
     if (w.last_out[u] < 0) w.first_out[u] = e; else w.enout[w.last_out[u]] = e;
     w.last_out[u] = e;
-    if (w.last_in[v] < 0) w.first_in[v] = e; else w.enin[w.last_in[v]] = e;
+    if (w.last_in[v] < 0) { w.first_in[v] = e; w.in1[v] = u << 1; } else { w.enin[w.last_in[v]] = e; w.in1[v] |= 1; }
     w.last_in[v] = e;
   }
 };
@@ -110,7 +110,7 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
 }
 
 #ifndef SVB_POA_MINB
-#define SVB_POA_MINB 6
+#define SVB_POA_MINB 5
 #endif
 __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   const int lane = threadIdx.x & 31;
@@ -150,13 +150,13 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           W.base[v] = q[j]; W.rank[v] = j; W.ring[v] = v;
           // edge j: (j ? v-1 : source) -> v ; edge ql: last -> sink
           W.efrom[j] = j ? v - 1 : 0; W.eto[j] = v; W.ew[j] = 1; W.enin[j] = -1; W.enout[j] = -1;
-          W.first_in[v] = W.last_in[v] = j;
+          W.first_in[v] = W.last_in[v] = j; W.in1[v] = (j ? v - 1 : 0) << 1;
           W.first_out[v] = W.last_out[v] = j + 1;
         }
         if (lane == 0) {
           W.efrom[ql] = 2 + ql - 1; W.eto[ql] = 1; W.ew[ql] = 1; W.enin[ql] = -1; W.enout[ql] = -1;
           W.first_out[0] = W.last_out[0] = 0;
-          W.first_in[1] = W.last_in[1] = ql;
+          W.first_in[1] = W.last_in[1] = ql; W.in1[1] = (2 + ql - 1) << 1;
         }
         g.n = 2 + ql; g.ne = ql + 1;
         __syncwarp();
@@ -198,20 +198,37 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         __syncwarp();
       }
       // ---- graph rows in rank order
+      // Row r needs: its node v (rank order), v's fields, its in-edges, the predecessors' bands, their
+      // score rows -- a chain of dependent loads.  The node fields of row r+1 are fetched while row r is
+      // computed, the first predecessor sits next to them (in1 = pred << 1 | has-more-in-edges), and a
+      // predecessor that is the row just finished hands its band over in registers: the common row
+      // (one in-edge, from the previous row) waits for its predecessor's scores only.
       int v_next = n_ord > 0 ? W.order[0] : 0;
+      int nx_in1 = W.in1[v_next], nx_remain = W.remain[v_next], nx_base = W.base[v_next];
+      int v_prev = 0, b_prev = 0, en_prev = W.end[0], l_prev = 1, r_prev = 1;   // the source row
       for (int r = 0; r < n_ord; ++r) {
-        const int v = v_next;
-        if (r + 1 < n_ord) v_next = W.order[r + 1];   // in flight while this row is computed
-        const int c = ql - W.remain[v] + 1;
-        int pl = 0x7fffffff, pr = -1;
-        for (int e = W.first_in[v]; e >= 0; e = W.enin[e]) {
-          const int p = W.efrom[e];
-          pl = min(pl, W.mpl[p]); pr = max(pr, W.mpr[p]);
+        const int v = v_next, in1 = nx_in1, bv = nx_base;
+        const int c = ql - nx_remain + 1;
+        if (r + 1 < n_ord) {                          // in flight while this row is computed
+          v_next = W.order[r + 1];
+          nx_in1 = W.in1[v_next]; nx_remain = W.remain[v_next]; nx_base = W.base[v_next];
+        }
+        const bool single = !(in1 & 1);
+        const int p0 = in1 >> 1;
+        int p0b, p0e, pl, pr;
+        if (single) {
+          if (p0 == v_prev) { p0b = b_prev; p0e = en_prev; pl = l_prev; pr = r_prev; }
+          else { p0b = W.beg[p0]; p0e = W.end[p0]; pl = W.mpl[p0]; pr = W.mpr[p0]; }
+        } else {
+          p0b = 0; p0e = -1; pl = 0x7fffffff; pr = -1;
+          for (int e = W.first_in[v]; e >= 0; e = W.enin[e]) {
+            const int p = W.efrom[e];
+            pl = min(pl, W.mpl[p]); pr = max(pr, W.mpr[p]);
+          }
         }
         int b = max(0, min(pl, c) - w), en = min(ql, max(pr, c) + w);
         if (b > en) b = en;
         if (en - b + 1 > Wc) { en = b + Wc - 1; status |= POA_CLAMPED; }
-        const int bv = W.base[v];
         int* hrow = W.H + (int64_t)v * Wc; int* e1row = W.E1 + (int64_t)v * Wc; int* e2row = W.E2 + (int64_t)v * Wc;
         unsigned* tbrow = W.TB + (int64_t)v * Wc;
         int carry1 = PNEG, carry2 = PNEG;      // running max of B1/B2 over columns before this segment
@@ -220,11 +237,9 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         for (int j0 = b; j0 <= en; j0 += 32) {
           const int j = j0 + lane;
           const bool act = j <= en;
-          int m = PNEG, x1 = PNEG, x2 = PNEG, pm = 0, p1 = 0, p2 = 0, x1ext = 0, x2ext = 0, ord = 0;
+          int m = PNEG, x1 = PNEG, x2 = PNEG, pm = 0, p1 = 0, p2 = 0, x1ext = 0, x2ext = 0;
           const int qb = (act && j >= 1) ? q[j - 1] : 4;
-          for (int e = W.first_in[v]; e >= 0; e = W.enin[e], ++ord) {
-            const int p = W.efrom[e];
-            const int bp = W.beg[p], ep = W.end[p];
+          auto consider = [&](int p, int bp, int ep, int ord) {   // predecessor p with band [bp, ep], in-edge ordinal ord
             const int* ph = W.H + (int64_t)p * Wc;
             if (act && j >= 1 && j - 1 >= bp && j - 1 <= ep) {
               const int s = (bv >= 4 || qb >= 4) ? 0 : (bv == qb ? P.match : -mm);
@@ -239,6 +254,15 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
               op = hj - P.o2; ex = W.E2[(int64_t)p * Wc + j - bp];
               cval = max(op, ex) - P.e2;
               if (cval > x2) { x2 = cval; p2 = ord; x2ext = ex > op; }
+            }
+          };
+          if (single) {
+            consider(p0, p0b, p0e, 0);
+          } else {
+            int ord = 0;
+            for (int e = W.first_in[v]; e >= 0; e = W.enin[e], ++ord) {
+              const int p = W.efrom[e];
+              consider(p, W.beg[p], W.end[p], ord);
             }
           }
           m = max(m, PNEG); x1 = max(x1, PNEG); x2 = max(x2, PNEG);
@@ -286,6 +310,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           r_ = max(r_, __shfl_xor_sync(0xffffffffu, r_, o));
         }
         if (lane == 0) { W.beg[v] = b; W.end[v] = en; W.mpl[v] = l_ + 1; W.mpr[v] = r_ + 1; }
+        v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1;
         __syncwarp();
       }
       PHASE(t_dp);
