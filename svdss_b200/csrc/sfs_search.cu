@@ -1400,9 +1400,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
         const int ln = __shfl_sync(0xffffffffu, len, src);
         const int s0 = __shfl_sync(0xffffffffu, pos, src);
         const Link lk = sprint_links(P, ro, ln, s0 - lane, K, P.sprint_budget, lane, my, warp_stage_s);
-        unsigned blk_sum = (unsigned)lk.blk;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) blk_sum += __shfl_xor_sync(0xffffffffu, blk_sum, o);
+        unsigned blk_used = 0;   // index blocks of the links the chain actually takes (the others are waste, not work)
         int cur = s0, n_links = 0;
         bool done = false, gave_up = false;
         while (s0 - cur < 32 && cur >= 0) {       // warp-uniform: every lane follows the same chain
@@ -1412,6 +1410,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
           ++n_links;
           const int b_j = __shfl_sync(0xffffffffu, lk.b, j), e_j = __shfl_sync(0xffffffffu, lk.e, j);
           const int cnt_j = __shfl_sync(0xffffffffu, lk.cnt, j);
+          blk_used += (unsigned)__shfl_sync(0xffffffffu, lk.blk, j);
           if (lane == src) n_ext += (unsigned)cnt_j;
           if (st_j == 1) { done = true; break; }                // reached the read start still matching
           if (lane == src) on_sfs(b_j, e_j - b_j + 1);          // ping_pong.cpp:39-41
@@ -1419,7 +1418,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
           cur = e_j - 1;
         }
         if (lane == src) {
-          n_blk += blk_sum;
+          n_blk += blk_used;
           if (P.stats_on) {
             atomicAdd(P.stats + 11, 1ull); atomicAdd(P.stats + 12, (unsigned long long)n_links);
             if (gave_up) atomicAdd(P.stats + 13, 1ull);
