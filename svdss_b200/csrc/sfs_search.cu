@@ -2,17 +2,21 @@
 // (reference ping_pong.cpp:4-49) for a whole batch of reads, with Assembler::assemble
 // (assembler.cpp:34-56) fused as a streaming epilogue.
 //
-// Work decomposition: one G-lane *group* (G = 4 for 64-byte index blocks, 8 for 128-byte blocks)
-// walks one read; a warp therefore carries 32/G independent dependent-load chains.  Per backward
-// extension each lane issues ONE 16-byte load per index block (the group's G loads coalesce into
-// one 64/128-byte request), counts matches in its own 32-symbol slice with LOP3+POPC and the group
-// reduces with warp shuffles.  Groups pull reads (longest first) from a global work counter, so
-// the grid is persistent: #CTAs = #SMs x occupancy.
-//
 // Only Occ(c, k) and Occ(c, k + size) of ONE symbol are needed per step: every direction switch in
 // ping_pong.cpp restarts from rb3_fmd_set_intv (:12, :30), so the bidirectional bookkeeping of
 // rb3_fmd_extend is never observed; the forward phase is a backward search with complemented
 // characters on the same (strand-closed) BWT.
+//
+// Three generations of the kernel live here (DESIGN.md 3.1 has the measurements behind each step):
+//   k_sfs_search<G,SPL>   one G-lane group per read, each lane loads 16 bytes of the index block; the
+//                         only kernel for 64-byte blocks; persistent grid, reads pulled from a counter
+//   k_sfs_search_tma      thread per read, 128-byte blocks staged into shared memory by the warp
+//                         (cp.async or TMA bulk copies): the pure rank walk at 0.69-0.72 of HBM peak
+//   k_sfs_search_mop      the default: thread per read, micro-op pipeline over three ways of answering
+//                         an extension (index blocks, located-match text compare done by the whole warp,
+//                         K-mer jump table), main launch + tail launch (parked walks, one per warp, with
+//                         32-link sprints through novel sequence); also unpacks BAM-native 4-bit reads
+//                         streamed from the host in dedicated CTAs of the same launch
 #include <cub/cub.cuh>
 
 #include <algorithm>
