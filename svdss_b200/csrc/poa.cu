@@ -110,7 +110,7 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
 }
 
 #ifndef SVB_POA_MINB
-#define SVB_POA_MINB 5
+#define SVB_POA_MINB 4
 #endif
 __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   const int lane = threadIdx.x & 31;
