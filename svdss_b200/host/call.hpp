@@ -9,8 +9,9 @@
 //     chrom:s+1-e+1 <TAB> n { <TAB> name:seq }
 // That file carries no haplotype tags or coverage vectors, so with --clusters-in every sub-read
 // has htag 0, cov = cov0 = n and RVEC is empty.
-// Not carried over: --clipped (Clipper) and the reference's reuse of the OpenMP loop
-// variable `i` inside pcall's encode loops (caller.cpp:339-342), which is undefined behaviour.
+// --clipped (caller.cpp:37-55) appends the Clipper's imprecise records (clipper.hpp) after the VCF body.
+// Not carried over: the reference's reuse of the OpenMP loop variable `i` inside pcall's encode
+// loops (caller.cpp:339-342), which is undefined behaviour.
 #pragma once
 #include <algorithm>
 #include <map>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include "../../include/svdss_b200.h"
+#include "clipper.hpp"
 #include "clusterer.hpp"
 #include "io.hpp"
 
@@ -186,11 +188,12 @@ inline double fuzz_ratio(const std::string& a, const std::string& b) {
 }
 
 struct CallConfig {
-  std::string reference, clusters_in, poa_out, bam, sfs, clusters_out;
+  std::string reference, clusters_in, poa_out, bam, sfs, clusters_out, clips_out;
   unsigned min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
   float min_ratio = 0.97f;
   int device = 0, threads = 4, batch_size = 10000;
   bool useht = true;
+  bool clipped = false;        // --clipped: imprecise SVs from clipped SFSs (experimental in the reference)
   bool cluster_only = false;   // stop after the Clusterer (writes --clusters); no GPU needed
 };
 
@@ -220,6 +223,22 @@ inline void print_vcf_header(const std::vector<std::string>& chroms, const std::
   fwrite(h.data(), 1, h.size(), stdout);
 }
 
+// Clipper::call + the collection loop of caller.cpp:45-52: per-thread vectors are inserted at the front
+inline std::vector<SV> clipped_calls(const std::vector<Clip>& clips, const std::vector<std::string>& chroms,
+                                     const std::unordered_map<std::string, std::string>& seqs, int threads,
+                                     const std::vector<std::pair<int, int>>& sv_regions, Clipper* keep = nullptr) {
+  Clipper clipper(clips, &chroms, &seqs);
+  clipper.call(threads, sv_regions);
+  std::vector<SV> out;
+  for (const auto& slot : clipper.p_calls) {
+    std::vector<SV> v;
+    for (const Clipper::Call& k : slot) v.push_back(SV(k.type, k.chrom, k.s, k.refbase, "<" + k.type + ">", k.w, 0, 0, 0, true, k.l, "."));
+    out.insert(out.begin(), v.begin(), v.end());
+  }
+  if (keep) *keep = clipper;
+  return out;
+}
+
 // returns process exit code; `log` prints to stderr
 inline int run_call(const CallConfig& c, void (*log)(const char*, const std::string&)) {
   // load_chromosomes (chromosomes.cpp:10-27): upper-cased
@@ -236,6 +255,7 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     }
   }
   std::vector<Cluster> clusters;
+  std::vector<Clip> clips;
   if (c.clusters_in.empty()) {
     // Caller::run, caller.cpp:9-13
     std::unordered_map<std::string, std::vector<SFS>> sfss;
@@ -246,16 +266,18 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     ClusterConfig cc;
     cc.bam = c.bam; cc.clusters_out = c.clusters_out; cc.threads = c.threads; cc.batch_size = c.batch_size;
     cc.min_mapq = c.min_mapq; cc.min_cluster_weight = c.min_cluster_weight;
+    cc.clipped = c.clipped; cc.clips_out = c.clips_out;
     Clusterer C(cc, &sfss, &seqs);
     log("info", "Placing SFSs on reference genome");
     if (!C.run()) { log("critical", C.error.empty() ? "cannot write " + c.clusters_out : C.error); return 1; }
     log("info", std::to_string(C.unplaced) + "/" + std::to_string(C.s_unplaced) + "/" + std::to_string(C.e_unplaced) +
-                    " unplaced SFSs. " + std::to_string(C.unknown) + " erroneus SFSs. 0 clipped SFSs.");
+                    " unplaced SFSs. " + std::to_string(C.unknown) + " erroneus SFSs. " + std::to_string(C.clips.size()) + " clipped SFSs.");
     log("info", "Clustered " + std::to_string(C.n_extended) + " SFSs. Maximum extended SFS length: " + std::to_string(C.max_ext_len) +
                     "bp. Using separation distance: " + std::to_string(C.dist) + "bp.");
     log("info", "Filtered " + std::to_string(C.unextended) + " SFSs. Filtered " + std::to_string(C.small_clusters) +
                     " clusters. Filtered " + std::to_string(C.small_clusters_2) + " global clusters.");
     clusters.swap(C.clusters);
+    clips.swap(C.clips);
     if (c.cluster_only) return 0;
   } else {
     // clusters (clusterer.cpp:613-626 format)
@@ -433,6 +455,15 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     for (const auto& ch : chroms) fprintf(f, "@SQ\tSN:%s\tLN:%zu\n", ch.c_str(), seqs[ch].size());
     for (const auto& a : sam) fprintf(f, "%s\n", a.c_str());
     fclose(f);
+  }
+  if (c.clipped) {  // caller.cpp:37-55
+    log("warning", "Calling imprecise SVs from clipped alignments is experimental");
+    if (!c.clusters_in.empty()) log("warning", "--clusters-in carries no alignments, hence no clips");
+    std::vector<std::pair<int, int>> regions;
+    for (const SV& sv : svs) regions.emplace_back(sv.s - 1000, sv.e + 1000);
+    const std::vector<SV> clipped_svs = clipped_calls(clips, chroms, seqs, c.threads, regions);
+    log("info", "Predicted " + std::to_string(clipped_svs.size()) + " SVs from clipped alignments");
+    for (const SV& sv : clipped_svs) { std::string l = sv.vcf_line() + "\n"; fwrite(l.data(), 1, l.size(), stdout); }
   }
   return 0;
 }

@@ -97,9 +97,23 @@ inline AlPairs get_aligned_pairs(int32_t pos, const std::vector<uint32_t>& cigar
 }
 
 struct ClusterConfig {
-  std::string bam, clusters_out;
+  std::string bam, clusters_out, clips_out;
   int threads = 4, batch_size = 10000;
   unsigned flank = 100, ksize = 7, min_mapq = 20, min_cluster_weight = 2;  // config.hpp:84-89
+  bool clipped = false;                                                    // config.hpp:94 (--clipped)
+};
+
+// clipper.hpp:21-43: a soft clip whose bases carry an SFS that could not be placed on the reference.
+// `p` = alignment start (left clip, starting) or bam_endpos (right clip); `l` = clipped bases.
+struct Clip {
+  std::string name, chrom;
+  unsigned p = 0, l = 0;
+  bool starting = false;
+  unsigned w = 0;
+  Clip() {}
+  Clip(const std::string& name_, const std::string& chrom_, unsigned p_, unsigned l_, bool starting_, unsigned w_ = 0)
+      : name(name_), chrom(chrom_), p(p_), l(l_), starting(starting_), w(w_) {}
+  bool operator<(const Clip& c) const { return p < c.p; }
 };
 
 class Clusterer {
@@ -109,6 +123,7 @@ class Clusterer {
       : cfg_(c), SFSs_(sfss), chroms_(chromosome_seqs) {}
 
   std::vector<Cluster> clusters;
+  std::vector<Clip> clips;   // clusterer.hpp:183; filled only with --clipped
   // book keeping (clusterer.hpp:150-160)
   unsigned unplaced = 0, s_unplaced = 0, e_unplaced = 0, unknown = 0, unextended = 0, small_clusters = 0, small_clusters_2 = 0;
   size_t n_extended = 0;
@@ -117,6 +132,7 @@ class Clusterer {
 
   bool run() {
     if (!scan()) return false;
+    if (!cfg_.clips_out.empty() && !store_clips()) return false;
     if (extended_.empty()) return true;
     cluster_by_proximity();
     fill_clusters();
@@ -174,14 +190,26 @@ class Clusterer {
     // extend_alignment per accepted read; thread slot = n % threads (batch_size is a multiple of threads)
     std::vector<std::vector<SFS>> per_read(accepted.size());
     std::vector<unsigned> cnt(accepted.size() * 4, 0);
+    std::vector<std::pair<unsigned, unsigned>> lr_clip(cfg_.clipped ? accepted.size() * 2 : 0, std::make_pair(0u, 0u));
 #pragma omp parallel for schedule(dynamic, 64)
     for (long long n = 0; n < (long long)accepted.size(); ++n)
-      extend_alignment(alns_[accepted[(size_t)n]], per_read[(size_t)n], &cnt[(size_t)n * 4]);
+      extend_alignment(alns_[accepted[(size_t)n]], per_read[(size_t)n], &cnt[(size_t)n * 4],
+                       cfg_.clipped ? &lr_clip[(size_t)n * 2] : nullptr);
+    std::vector<std::vector<Clip>> p_clips((size_t)T);
     for (size_t n = 0; n < accepted.size(); ++n) {
       for (auto& s : per_read[n]) p_ext[n % (size_t)T].push_back(std::move(s));
       unplaced += cnt[n * 4]; s_unplaced += cnt[n * 4 + 1]; e_unplaced += cnt[n * 4 + 2]; unknown += cnt[n * 4 + 3];
+      if (cfg_.clipped) {                                                                             // :339-345
+        const Aln& a = alns_[accepted[n]];
+        const std::string& chrom = ref_names_[(size_t)a.tid];
+        if (lr_clip[n * 2].second > 0) p_clips[n % (size_t)T].push_back(Clip(a.qname, chrom, lr_clip[n * 2].first, lr_clip[n * 2].second, true));
+        if (lr_clip[n * 2 + 1].second > 0) p_clips[n % (size_t)T].push_back(Clip(a.qname, chrom, lr_clip[n * 2 + 1].first, lr_clip[n * 2 + 1].second, false));
+      }
     }
-    for (int t = 0; t < T; ++t) for (auto& s : p_ext[(size_t)t]) extended_.push_back(std::move(s));   // :21-25
+    for (int t = 0; t < T; ++t) {
+      for (auto& s : p_ext[(size_t)t]) extended_.push_back(std::move(s));                            // :21-25
+      clips.insert(clips.begin(), p_clips[(size_t)t].begin(), p_clips[(size_t)t].end());             // :24 (front insertion)
+    }
     n_extended = extended_.size();
     // region-fetch tables
     pmax_end_.resize(by_tid_.size());
@@ -200,12 +228,15 @@ class Clusterer {
   }
 
   // clusterer.cpp:156-345
-  void extend_alignment(const Aln& aln, std::vector<SFS>& out, unsigned* cnt) const {
+  // `lr` (only with --clipped): [0] = left clip (alignment start, clipped bases), [1] = right clip
+  // (bam_endpos, clipped bases) of a read whose SFS lies in a soft clip (:211-226)
+  void extend_alignment(const Aln& aln, std::vector<SFS>& out, unsigned* cnt, std::pair<unsigned, unsigned>* lr) const {
     const std::string& chrom = ref_names_[(size_t)aln.tid];
     auto cit = chroms_->find(chrom);
     if (cit == chroms_->end()) return;                                   // :162-163
     const std::string& cseq = cit->second;
-    const AlPairs alpairs = get_aligned_pairs(aln.pos, payload_[(size_t)aln.payload].cigar);
+    const std::vector<uint32_t>& cig = payload_[(size_t)aln.payload].cigar;
+    const AlPairs alpairs = get_aligned_pairs(aln.pos, cig);
     int last_pos = 0;
     std::vector<SFS> local;
     for (const SFS& sfs : SFSs_->at(aln.qname)) {
@@ -218,8 +249,17 @@ class Clusterer {
         else if (q > e) { refe = r; aln_end = (int)i; break; }
       }
       if (refs == -1 && refe == -1) { ++cnt[0]; continue; }              // :206-211
-      else if (refs == -1) { ++cnt[1]; continue; }                       // :211-218 (clips: Clipper, out of scope)
-      else if (refe == -1) { ++cnt[2]; continue; }                       // :219-226
+      else if (refs == -1) {                                             // :211-218
+        const uint32_t c0 = cig.empty() ? 0 : cig.front();
+        if (lr && (c0 & 0xf) == 4) lr[0] = std::make_pair((unsigned)aln.pos, (unsigned)(c0 >> 4));
+        else ++cnt[1];
+        continue;
+      } else if (refe == -1) {                                           // :219-226
+        const uint32_t c1 = cig.empty() ? 0 : cig.back();
+        if (lr && (c1 & 0xf) == 4) lr[1] = std::make_pair((unsigned)aln.end, (unsigned)(c1 >> 4));
+        else ++cnt[2];
+        continue;
+      }
       AlPairs local_alpairs;
       {
         int last_r = refs - 1;
@@ -420,6 +460,14 @@ class Clusterer {
       }
     }
     for (size_t ci = 0; ci < clusters.size(); ++ci) { small_clusters += cnt[ci * 3]; unextended += cnt[ci * 3 + 1]; small_clusters_2 += cnt[ci * 3 + 2]; }
+  }
+
+  // test/debug output of `--clips FILE` (no reference counterpart): name, chrom, p, l, L|R in `clips` order
+  bool store_clips() const {
+    std::ofstream f(cfg_.clips_out);
+    if (!f.is_open()) return false;
+    for (const Clip& c : clips) f << c.name << "\t" << c.chrom << "\t" << c.p << "\t" << c.l << "\t" << (c.starting ? "L" : "R") << "\n";
+    return true;
   }
 
   // clusterer.cpp:613-626

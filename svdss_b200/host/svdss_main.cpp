@@ -16,8 +16,10 @@
 #include <cstring>
 #include <ctime>
 #include <iostream>
+#include <fstream>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/svdss_b200.h"
@@ -41,7 +43,7 @@ static const char* INDEX_USAGE = "Usage: SVDSS index [-t threads] [-d] [-o index
 static const char* CALL_USAGE =
     "Usage: SVDSS call --reference <fa> (--bam <bam> --sfs <sfs> | --clusters-in <clusters.txt>) [--threads 4]\n"
     "                  [--min-cluster-weight 2] [--min-sv-length 25] [--min-mapq 20] [-l 0.97] [--noht]\n"
-    "                  [--poa <out.sam>] [--clusters <out.txt>] [--cluster-only]\n"
+    "                  [--poa <out.sam>] [--clusters <out.txt>] [--cluster-only] [--clipped [--clips <out.tsv>]]\n"
     "  Clusters are built on the host from --bam/--sfs (Clusterer) or read back from a `--clusters` file;\n"
     "  POA consensus + realignment (Caller::pcall) run on the GPU. --cluster-only stops after --clusters.";
 static const char* SMOOTH_USAGE =
@@ -51,7 +53,7 @@ static const char* SEARCH_USAGE =
     "                    [--noputative] [--noassemble] [--verbose]";
 
 struct Config {
-  string index, bam, fastx, out, reference, sfs, clusters_in, clusters_out, poa;
+  string index, bam, fastx, out, reference, sfs, clusters_in, clusters_out, poa, clips_out, clips_in, regions_in;
   int min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
   float min_ratio = 0.97f, accp = 0.98f;
   bool noht = false, clipped = false, cluster_only = false;
@@ -80,6 +82,9 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
     else if (a == "--clusters-in") ok = val(c.clusters_in);
     else if (a == "--clusters") ok = val(c.clusters_out);
     else if (a == "--cluster-only") c.cluster_only = true;
+    else if (a == "--clips") ok = val(c.clips_out);
+    else if (a == "--clips-in") ok = val(c.clips_in);
+    else if (a == "--regions-in") ok = val(c.regions_in);
     else if (a == "--poa") ok = val(c.poa);
     else if (a == "--min-cluster-weight") ok = ival(c.min_cluster_weight);
     else if (a == "--min-sv-length") { ok = ival(c.min_sv_length); c.min_sv_length = max(25, c.min_sv_length); }  // config.cpp:87
@@ -270,6 +275,45 @@ static int run_search(const Config& c) {
   return EXIT_SUCCESS;
 }
 
+// `SVDSS _clipper --reference FA --clips-in CLIPS.tsv [--regions-in REGIONS.tsv] [--threads N] [--verbose]`:
+// clips in the format of `call --clipped --clips` (name chrom p l L|R), regions as `low high` lines;
+// prints the imprecise records like the tail of `call --clipped`; --verbose lists the combined
+// breakpoints in the order they reach Clipper::cluster (std::unordered_map iteration order).
+static int run_clipper_hook(const Config& c) {
+  if (c.reference.empty() || c.clips_in.empty()) return EXIT_FAILURE;
+  vector<string> chroms;
+  unordered_map<string, string> seqs;
+  FastxReader fx(c.reference);
+  if (!fx.ok()) return EXIT_FAILURE;
+  FastxRecord r;
+  while (fx.next(r)) { for (auto& ch : r.seq) ch = (char)toupper((unsigned char)ch); chroms.push_back(r.name); seqs[r.name] = r.seq; }
+  vector<Clip> clips;
+  {
+    ifstream f(c.clips_in);
+    if (!f.is_open()) return EXIT_FAILURE;
+    string name, chrom, side;
+    unsigned p, l;
+    while (f >> name >> chrom >> p >> l >> side) clips.push_back(Clip(name, chrom, p, l, side == "L"));
+  }
+  vector<pair<int, int>> regions;
+  if (!c.regions_in.empty()) {
+    ifstream f(c.regions_in);
+    if (!f.is_open()) return EXIT_FAILURE;
+    int lo, hi;
+    while (f >> lo >> hi) regions.emplace_back(lo, hi);
+  }
+  Clipper kept(clips, &chroms, &seqs);
+  const vector<SV> svs = clipped_calls(clips, chroms, seqs, c.threads, regions, &kept);
+  if (c.verbose) {
+    for (const Clip& k : kept.r_combined) fprintf(stderr, "combined\tR\t%s\t%u\t%u\t%u\n", k.chrom.c_str(), k.p, k.l, k.w);
+    for (const Clip& k : kept.l_combined) fprintf(stderr, "combined\tL\t%s\t%u\t%u\t%u\n", k.chrom.c_str(), k.p, k.l, k.w);
+    for (const Clip& k : kept.rclips) fprintf(stderr, "clustered\tR\t%s\t%u\t%u\t%u\n", k.chrom.c_str(), k.p, k.l, k.w);
+    for (const Clip& k : kept.lclips) fprintf(stderr, "clustered\tL\t%s\t%u\t%u\t%u\n", k.chrom.c_str(), k.p, k.l, k.w);
+  }
+  for (const SV& sv : svs) cout << sv.vcf_line() << "\n";
+  return EXIT_SUCCESS;
+}
+
 int main(int argc, char** argv) {
   time_t t0;
   time(&t0);
@@ -286,6 +330,7 @@ int main(int argc, char** argv) {
     printf("%.6f\n", fuzz_ratio(pos[0], pos[1]));
     return 0;
   }
+  if (mode == "_clipper") return run_clipper_hook(c);   // test hook: Clipper::call without the GPU stages (tests/test_clipper_cpu.py)
   if (mode == "index") rc = run_index(c, pos);
   else if (mode == "smooth") {
     if (c.reference.empty() || c.bam.empty()) { cerr << SMOOTH_USAGE << endl; exit(EXIT_FAILURE); }   // main.cpp:72-75
@@ -296,13 +341,13 @@ int main(int argc, char** argv) {
   else if (mode == "search") rc = run_search(c);
   else if (mode == "call") {
     if (c.reference.empty() || (c.clusters_in.empty() && (c.bam.empty() || c.sfs.empty()))) { cerr << CALL_USAGE << endl; exit(EXIT_FAILURE); }  // main.cpp:56-59
-    if (c.clipped) logmsg("warning", "--clipped (imprecise SVs from clipped alignments) is not part of this build; ignored");
     CallConfig cc;
     cc.reference = c.reference; cc.clusters_in = c.clusters_in; cc.poa_out = c.poa;
     cc.min_cluster_weight = (unsigned)c.min_cluster_weight; cc.min_sv_length = (unsigned)c.min_sv_length;
     cc.min_ratio = c.min_ratio; cc.device = c.device;
     cc.bam = c.bam; cc.sfs = c.sfs; cc.clusters_out = c.clusters_out; cc.min_mapq = (unsigned)c.min_mapq;
     cc.threads = c.threads; cc.batch_size = c.bsize; cc.useht = !c.noht; cc.cluster_only = c.cluster_only;
+    cc.clipped = c.clipped; cc.clips_out = c.clips_out;
     rc = run_call(cc, [](const char* l, const string& m) { logmsg(l, m); });
   }
   else { cerr << MAIN_USAGE << endl; exit(EXIT_FAILURE); }

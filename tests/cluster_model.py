@@ -55,10 +55,12 @@ def get_unique_kmers(alpairs, k, from_end, cseq):       # clusterer.cpp:350-403
     return last
 
 
-def extend_alignment(rec, sfs_list, chrom, cseq, flank=100, ksize=7):   # clusterer.cpp:156-345
+def extend_alignment(rec, sfs_list, chrom, cseq, flank=100, ksize=7, clips=None):   # clusterer.cpp:156-345
+    """clips: None (no --clipped) or a list that receives (qname, chrom, p, l, starting) tuples."""
     alpairs = get_aligned_pairs(rec["pos"], rec["cigar"])
     last_pos = 0
     local = []
+    lclip = rclip = (0, 0)
     for qs_, l_, htag in sfs_list:
         s, e = qs_, qs_ + l_ - 1
         aln_start = aln_end = refs = refe = -1
@@ -71,7 +73,17 @@ def extend_alignment(rec, sfs_list, chrom, cseq, flank=100, ksize=7):   # cluste
             elif q > e:
                 refe = r; aln_end = i
                 break
-        if refs == -1 or refe == -1:
+        if refs == -1 and refe == -1:                    # :206-210
+            continue
+        elif refs == -1:                                 # :211-218
+            ln, op = rec["cigar"][0]
+            if op == "S" and clips is not None:
+                lclip = (rec["pos"], ln)
+            continue
+        elif refe == -1:                                 # :219-226
+            ln, op = rec["cigar"][-1]
+            if op == "S" and clips is not None:
+                rclip = (endpos(rec), ln)
             continue
         local_al = []
         last_r = refs - 1
@@ -108,6 +120,11 @@ def extend_alignment(rec, sfs_list, chrom, cseq, flank=100, ksize=7):   # cluste
                 break
         else:
             merged.append(dict(x))
+    if clips is not None:                                # :339-345
+        if lclip[1] > 0:
+            clips.append((rec["qname"], chrom, lclip[0], lclip[1], True))
+        if rclip[1] > 0:
+            clips.append((rec["qname"], chrom, rclip[0], rclip[1], False))
     return merged
 
 
@@ -120,19 +137,26 @@ def endpos(rec):
     return rec["pos"] + (span if span else 1)
 
 
-def run(records, ref_names, ref_seqs, sfs_by_read, threads=4, min_mapq=20, min_cluster_weight=2):
+def run(records, ref_names, ref_seqs, sfs_by_read, threads=4, min_mapq=20, min_cluster_weight=2, clips_out=None):
     """Returns the clusters in the reference's order for `threads`: list of dicts chrom, s, e, cov
-    (cov0,cov1,cov2), reads [(0/1, hp)], subreads [(name, seq, hp)]."""
+    (cov0,cov1,cov2), reads [(0/1, hp)], subreads [(name, seq, hp)].  With `clips_out` (a list) the
+    run is `--clipped`: it receives the Clusterer's clips (qname, chrom, p, l, starting) in the
+    reference's order (per-slot vectors inserted at the front, clusterer.cpp:24)."""
     # pass 1: accepted reads dealt round-robin to thread slots (clusterer.cpp:109-133)
     p_ext = [[] for _ in range(threads)]
+    p_clips = [[] for _ in range(threads)]
     n = 0
     for rec in records:
         if not primary(rec) or rec.get("mapq", 60) < min_mapq or rec["qname"] not in sfs_by_read:
             continue
         chrom = ref_names[rec["tid"]]
         if chrom in ref_seqs:
-            p_ext[n % threads].extend(extend_alignment(rec, sfs_by_read[rec["qname"]], chrom, ref_seqs[chrom]))
+            p_ext[n % threads].extend(extend_alignment(rec, sfs_by_read[rec["qname"]], chrom, ref_seqs[chrom],
+                                                       clips=p_clips[n % threads] if clips_out is not None else None))
         n += 1
+    if clips_out is not None:
+        for t in range(threads):
+            clips_out[0:0] = p_clips[t]
     ext = [x for t in p_ext for x in t]
     if not ext:
         return []
