@@ -67,8 +67,18 @@ static void logmsg(const char* lvl, const string& m) { fprintf(stderr, "[svdss-b
 static bool parse_common(int argc, char** argv, Config& c, vector<string>& positional) {
   // `SVDSS --version` / `SVDSS --help`: no subcommand, options start at argv[1]
   for (int i = (argv[1][0] == '-') ? 1 : 2; i < argc; ++i) {
-    string a = argv[i];
-    auto val = [&](string& dst) { if (i + 1 >= argc) return false; dst = argv[++i]; return true; };
+    string a = argv[i], attached;
+    bool has_attached = false;   // cxxopts also takes `--option=value`
+    if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+      const size_t eq = a.find('=');
+      if (eq != string::npos) { attached = a.substr(eq + 1); a.resize(eq); has_attached = true; }
+    }
+    auto val = [&](string& dst) {
+      if (has_attached) { dst = attached; return true; }
+      if (i + 1 >= argc) return false;
+      dst = argv[++i];
+      return true;
+    };
     auto ival = [&](int& dst) { string s; if (!val(s)) return false; dst = atoi(s.c_str()); return true; };
     bool ok = true;
     if (a == "--index") ok = val(c.index);
@@ -94,6 +104,8 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
     else if (a == "--noht") c.noht = true;
     else if (a == "--clipped") c.clipped = true;
     else if (a == "--omax") ok = ival(c.omax);
+    else if (a == "--append") { string unused; ok = val(unused); }   // registered by the reference (config.cpp:35), read nowhere
+    else if (a == "--binary") {}                                       // config.cpp:51,96: parsed, never used
     else if (a == "--device") ok = ival(c.device);
     else if (a == "-o") ok = val(c.out);
     else if (a == "-d") {}

@@ -36,3 +36,15 @@ def test_search_fails_loudly_without_index_or_gpu(exe, tmp_path):
     r = subprocess.run([exe, "search", "--index", str(tmp_path / "none.idx"), "--fastx", str(fq)],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "svb_index_load" in r.stderr and r.stdout == ""
+
+
+def test_cxxopts_spellings_are_accepted(exe, tmp_path):
+    """config.cpp:26-57: every registered option parses, also as `--option=value`; --binary and
+    --append are registered but read nowhere."""
+    fq = tmp_path / "r.fq"
+    fq.write_text("@r1\nACGT\n+\nIIII\n")
+    r = subprocess.run([exe, "search", "--index=" + str(tmp_path / "none.idx"), "--fastx=" + str(fq), "--threads=2", "--bsize=10",
+                        "--binary", "--append", "x", "--omax=5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "svb_index_load" in r.stderr and "unknown option" not in r.stderr
+    r = subprocess.run([exe, "call", "--reference=x.fa", "--clipped"], capture_output=True, text=True)   # still needs --bam/--sfs
+    assert r.returncode == 1 and "Usage" in r.stderr
