@@ -9,6 +9,7 @@
 // Output order = input order of the accepted records, which is what the reference's batch layout
 // (k-major, thread-minor, smoother.cpp:424-450) produces for any --threads.
 #pragma once
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -203,25 +204,32 @@ inline int run_smooth(const SmoothConfig& c, void (*log)(const char*, const std:
   }
   // pass 1 (compute_maxaccuracy, :267-345): accp-percentile of the mismatch rate of the first 10000 accepted alignments
   double al_accuracy = 0;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_pass1 = now(), t_read = 0, t_smooth = 0, t_write = 0;
   {
     BamReader bam(c.bam);
     if (!bam.ok()) { log("critical", "cannot read BAM " + c.bam); return 1; }
     bam.want_alignment(true);
-    std::vector<double> acc;
+    std::vector<BamRecord> first;
     BamRecord r;
-    while (acc.size() < 10000 && bam.next(r) == 1) {
-      if (!smooth_accept(r, c.min_mapq, bam.ref_names(), seqs, nullptr, nullptr)) continue;
-      acc.push_back(mismatch_rate(r, decode_seq(r), seqs[bam.ref_names()[(size_t)r.tid]]));
-    }
+    while (first.size() < 10000 && bam.next(r) == 1)
+      if (smooth_accept(r, c.min_mapq, bam.ref_names(), seqs, nullptr, nullptr)) first.push_back(r);
+    std::vector<double> acc(first.size());
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long i = 0; i < (long long)first.size(); ++i)
+      acc[(size_t)i] = mismatch_rate(first[(size_t)i], decode_seq(first[(size_t)i]), seqs.at(bam.ref_names()[(size_t)first[(size_t)i].tid]));
     if (acc.empty()) { log("critical", "no usable alignment in " + c.bam); return 1; }
     std::sort(acc.begin(), acc.end());
     al_accuracy = percentile(acc, c.accp);
   }
   log("info", "Max allowed alignment accuracy: " + std::to_string(al_accuracy));
+  t_pass1 = now() - t_pass1;
   BamReader bam(c.bam);
   if (!bam.ok()) { log("critical", "cannot read BAM " + c.bam); return 1; }
   bam.want_raw(true);
-  BgzfWriter out(stdout);
+  int level = 6;   // zlib's default, what hts_open("-", "wb") uses (smoother.cpp:362)
+  if (const char* e = getenv("SVB_BGZF_LEVEL")) level = std::max(0, std::min(9, atoi(e)));
+  BgzfWriter out(stdout, level);
   {  // sam_hdr_write: the header as it came
     std::vector<uint8_t> h;
     auto put32 = [&](int32_t v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); h.insert(h.end(), p, p + 4); };
@@ -247,6 +255,7 @@ inline int run_smooth(const SmoothConfig& c, void (*log)(const char*, const std:
   bool eof = false;
   int st = 1;
   while (!eof) {
+    double t0 = now();
     batch.clear();
     BamRecord r;
     while (batch.size() < BATCH && (st = bam.next(r)) == 1) {
@@ -257,6 +266,7 @@ inline int run_smooth(const SmoothConfig& c, void (*log)(const char*, const std:
     if (st < 0) { log("critical", "truncated or corrupt BAM"); return 1; }
     bodies.assign(batch.size(), std::vector<uint8_t>());
     std::vector<int> xf(batch.size(), 0);
+    t_read += now() - t0; t0 = now();
 #pragma omp parallel for schedule(dynamic, 64)
     for (long long i = 0; i < (long long)batch.size(); ++i) {
       const BamRecord& b = batch[(size_t)i];
@@ -268,15 +278,20 @@ inline int run_smooth(const SmoothConfig& c, void (*log)(const char*, const std:
       bodies[(size_t)i].swap(body);
       xf[(size_t)i] = s.xf;
     }
+    t_smooth += now() - t0; t0 = now();
     for (size_t i = 0; i < bodies.size(); ++i) {
       const int32_t bs = (int32_t)bodies[i].size();
       if (!out.write(&bs, 4) || !out.write(bodies[i].data(), bodies[i].size())) { log("critical", "Can't write corrected BAM record, aborting.."); return 1; }
       ++written; ++counts[xf[i] & 3];
     }
+    t_write += now() - t0;
   }
-  if (!out.close()) { log("critical", "Can't write corrected BAM record, aborting.."); return 1; }
+  { const double t0 = now(); const bool okc = out.close(); t_write += now() - t0; if (!okc) { log("critical", "Can't write corrected BAM record, aborting.."); return 1; } }
   log("info", "Alignments processed: " + std::to_string(processed) + ", written: " + std::to_string(written) + " (XF 0/1/2: " +
                   std::to_string(counts[0]) + "/" + std::to_string(counts[1]) + "/" + std::to_string(counts[2]) + ")");
+  char tb[160];
+  snprintf(tb, sizeof(tb), "Stages: accuracy pass %.2f s, read %.2f s, smooth %.2f s, deflate + write %.2f s", t_pass1, t_read, t_smooth, t_write);
+  log("info", tb);
   return 0;
 }
 
