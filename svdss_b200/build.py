@@ -57,7 +57,7 @@ HOST_BIN = os.path.join(HERE, "SVDSS")
 
 def build_host(force=False):
     """C++14 shell (`SVDSS index | search`) over the C ABI; needs only g++ and zlib."""
-    srcs = [os.path.join(HERE, "host", f) for f in ("svdss_main.cpp", "io.hpp", "call.hpp", "clusterer.hpp", "smoother.hpp")]
+    srcs = [os.path.join(HERE, "host", f) for f in ("svdss_main.cpp", "io.hpp", "call.hpp", "clusterer.hpp", "smoother.hpp", "clipper.hpp", "rld.hpp")]
     if (not force and os.path.exists(HOST_BIN)
             and all(os.path.getmtime(HOST_BIN) >= os.path.getmtime(s) for s in srcs + [LIB])):
         return HOST_BIN

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <ctime>
 #include <iostream>
+#include <iterator>
 #include <fstream>
 #include <map>
 #include <string>
@@ -26,6 +27,7 @@
 #include "io.hpp"
 #include "call.hpp"
 #include "smoother.hpp"
+#include "rld.hpp"
 #include <unistd.h>
 static long getpid_portable() { return (long)getpid(); }
 
@@ -39,7 +41,11 @@ static const char* MAIN_USAGE =
     "  smooth  remove everything but putative SVs from the alignments of a BAM\n"
     "  search  extract sample-specific strings (SFS) from a BAM/FASTX\n"
     "  call    POA consensus + ksw2 realignment + SV extraction from SFS clusters";
-static const char* INDEX_USAGE = "Usage: SVDSS index [-t threads] [-d] [-o index] <reference.fa[.gz]>";
+static const char* INDEX_USAGE =
+    "Usage: SVDSS index [-t threads] [-d] [-o index] [--fmd <out.fmd>] <reference.fa[.gz]>\n"
+    "       SVDSS index --from-fmd <ropebwt3.fmd> [-o index]\n"
+    "  --fmd       also dump the BWT in ropebwt3's FMD format (what the reference's `index -d` writes)\n"
+    "  --from-fmd  convert an index built by the reference (ropebwt3 FMD) instead of reading a FASTA";
 static const char* CALL_USAGE =
     "Usage: SVDSS call --reference <fa> (--bam <bam> --sfs <sfs> | --clusters-in <clusters.txt>) [--threads 4]\n"
     "                  [--min-cluster-weight 2] [--min-sv-length 25] [--min-mapq 20] [-l 0.97] [--noht]\n"
@@ -53,7 +59,7 @@ static const char* SEARCH_USAGE =
     "                    [--noputative] [--noassemble] [--verbose]";
 
 struct Config {
-  string index, bam, fastx, out, reference, sfs, clusters_in, clusters_out, poa, clips_out, clips_in, regions_in;
+  string index, bam, fastx, out, reference, sfs, clusters_in, clusters_out, poa, clips_out, clips_in, regions_in, fmd_out, fmd_in;
   int min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
   float min_ratio = 0.97f, accp = 0.98f;
   bool noht = false, clipped = false, cluster_only = false;
@@ -62,6 +68,7 @@ struct Config {
   int overlap = -1;  // config.hpp:82: never settable from the command line
 };
 
+static double now_s() { return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); }
 static void logmsg(const char* lvl, const string& m) { fprintf(stderr, "[svdss-b200] [%s] %s\n", lvl, m.c_str()); }
 
 static bool parse_common(int argc, char** argv, Config& c, vector<string>& positional) {
@@ -92,6 +99,8 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
     else if (a == "--clusters-in") ok = val(c.clusters_in);
     else if (a == "--clusters") ok = val(c.clusters_out);
     else if (a == "--cluster-only") c.cluster_only = true;
+    else if (a == "--fmd") ok = val(c.fmd_out);
+    else if (a == "--from-fmd") ok = val(c.fmd_in);
     else if (a == "--clips") ok = val(c.clips_out);
     else if (a == "--clips-in") ok = val(c.clips_in);
     else if (a == "--regions-in") ok = val(c.regions_in);
@@ -124,24 +133,73 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
   return true;
 }
 
+// ropebwt3 FMD -> the forward strands it indexes (rld.hpp): decode, invert the BWT, drop one strand of every pair
+static bool fmd_to_contigs(const string& path, vector<uint8_t>& cat, vector<int64_t>& offs) {
+  const double t0 = now_s();
+  RldFile rf;
+  string err;
+  vector<uint8_t> bwt;
+  if (!Rld::read(path, rf, err) || !Rld::decode_bwt(rf, bwt, err)) { logmsg("critical", err); return false; }
+  if (rf.asize != 6) { logmsg("critical", path + ": alphabet of " + to_string(rf.asize) + " symbols, expected 6 ($ACGTN)"); return false; }
+  rf.words.clear(); rf.words.shrink_to_fit();
+  const double t1 = now_s();
+  vector<string> seqs;
+  {
+    BwtInverter inv(bwt.data(), bwt.size());
+    if (!inv.sequences(seqs)) { logmsg("critical", path + ": the BWT does not invert to '$'-terminated sequences"); return false; }
+  }
+  bwt.clear(); bwt.shrink_to_fit();
+  vector<size_t> keep;
+  if (!forward_strands(seqs, keep)) {
+    logmsg("critical", path + ": some sequences have no reverse complement in the index (built with ropebwt3 -R?); SVDSS searches both strands");
+    return false;
+  }
+  cat.clear(); offs.assign(1, 0);
+  for (size_t k : keep) {
+    cat.insert(cat.end(), seqs[k].begin(), seqs[k].end());
+    offs.push_back((int64_t)cat.size());
+    string().swap(seqs[k]);
+  }
+  char tb[200];
+  snprintf(tb, sizeof(tb), "ropebwt3 FMD index: %zu sequences (%zu after dropping reverse strands), %zu bp; decode %.2f s, BWT inversion %.2f s",
+           seqs.size(), keep.size(), cat.size(), t1 - t0, now_s() - t1);
+  logmsg("info", tb);
+  return true;
+}
+
 static int run_index(const Config& c, const vector<string>& pos) {
-  if (pos.size() != 1) { cerr << INDEX_USAGE << endl; return EXIT_FAILURE; }
-  FastxReader fx(pos[0]);
-  if (!fx.ok()) { logmsg("critical", "cannot open " + pos[0]); return EXIT_FAILURE; }
   vector<uint8_t> cat;
   vector<int64_t> offs(1, 0);
-  FastxRecord r;
-  const uint8_t* t6 = nt6_table();
-  while (fx.next(r)) {
-    for (char ch : r.seq) cat.push_back(t6[(uint8_t)ch]);
-    offs.push_back((int64_t)cat.size());
+  if (!c.fmd_in.empty()) {
+    if (!pos.empty()) { cerr << INDEX_USAGE << endl; return EXIT_FAILURE; }
+    if (!fmd_to_contigs(c.fmd_in, cat, offs)) return EXIT_FAILURE;
+  } else {
+    if (pos.size() != 1) { cerr << INDEX_USAGE << endl; return EXIT_FAILURE; }
+    FastxReader fx(pos[0]);
+    if (!fx.ok()) { logmsg("critical", "cannot open " + pos[0]); return EXIT_FAILURE; }
+    FastxRecord r;
+    const uint8_t* t6 = nt6_table();
+    while (fx.next(r)) {
+      for (char ch : r.seq) cat.push_back(t6[(uint8_t)ch]);
+      offs.push_back((int64_t)cat.size());
+    }
+    if (offs.size() < 2) { logmsg("critical", "no sequences in " + pos[0]); return EXIT_FAILURE; }
   }
-  if (offs.size() < 2) { logmsg("critical", "no sequences in " + pos[0]); return EXIT_FAILURE; }
   logmsg("info", "indexing " + to_string(offs.size() - 1) + " sequences, " + to_string(cat.size()) + " bp (both strands) on GPU " + to_string(c.device));
   svb_index_t* idx = nullptr;
   if (svb_index_build(cat.data(), offs.data(), (int64_t)offs.size() - 1, SVB_MEM_HOST, c.device, 0, &idx) != SVB_OK) {
     logmsg("critical", string("svb_index_build: ") + svb_last_error());
     return EXIT_FAILURE;
+  }
+  if (!c.fmd_out.empty()) {   // the reference's own index format, for the reference's own `search`
+    svb_index_info_t info;
+    vector<uint8_t> bwt;
+    string err;
+    bool ok = svb_index_info(idx, &info) == SVB_OK;
+    if (ok) { bwt.resize((size_t)info.n); ok = svb_index_get_bwt(idx, bwt.data()) == SVB_OK; }
+    if (!ok) { logmsg("critical", string("svb_index_get_bwt: ") + svb_last_error()); svb_index_free(idx); return EXIT_FAILURE; }
+    if (!Rld::write(c.fmd_out, bwt.data(), bwt.size(), err)) { logmsg("critical", err); svb_index_free(idx); return EXIT_FAILURE; }
+    logmsg("info", "BWT written in ropebwt3 FMD format to " + c.fmd_out);
   }
   string out = c.out;
   const bool to_stdout = out.empty();  // ropebwt3 build writes to stdout without -o (README.md:113)
@@ -161,7 +219,6 @@ static int run_index(const Config& c, const vector<string>& pos) {
 }
 
 static double g_gpu_s = 0;   // wall time inside svb_sfs_batch* (stage report of `search`)
-static double now_s() { return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct PendingRead { string qname; int hp; int64_t lo, hi; bool search; int32_t l_qseq; };
 
@@ -222,7 +279,16 @@ static int run_search(const Config& c) {
   const double t_start = now_s();
   logmsg("info", "Restoring index..");
   svb_index_t* idx = nullptr;
-  if (svb_index_load(c.index.c_str(), c.device, &idx) != SVB_OK) {
+  if (Rld::is_rld(c.index)) {   // an index written by the reference's `index -d` (ropebwt3 FMD)
+    logmsg("warning", "ropebwt3 FMD index: re-indexing on the GPU for this run; convert it once with `SVDSS index --from-fmd`");
+    vector<uint8_t> cat;
+    vector<int64_t> offs;
+    if (!fmd_to_contigs(c.index, cat, offs)) return EXIT_FAILURE;
+    if (svb_index_build(cat.data(), offs.data(), (int64_t)offs.size() - 1, SVB_MEM_HOST, c.device, 0, &idx) != SVB_OK) {
+      logmsg("critical", string("svb_index_build: ") + svb_last_error());
+      return EXIT_FAILURE;
+    }
+  } else if (svb_index_load(c.index.c_str(), c.device, &idx) != SVB_OK) {
     logmsg("critical", string("svb_index_load: ") + svb_last_error());
     return EXIT_FAILURE;
   }
@@ -326,6 +392,41 @@ static int run_clipper_hook(const Config& c) {
   return EXIT_SUCCESS;
 }
 
+// `SVDSS _fmd encode BWT.bin OUT.fmd | decode IN.fmd BWT.bin | contigs IN.fmd OUT.fa`: rld.hpp without the
+// GPU (tests/test_fmd_cpu.py).  BWT.bin = one nt6 code per byte; OUT.fa = the forward strands, named seq<k>.
+static int run_fmd_hook(const vector<string>& pos) {
+  if (pos.size() != 3) return EXIT_FAILURE;
+  string err;
+  if (pos[0] == "encode") {
+    ifstream f(pos[1], ios::binary);
+    if (!f.is_open()) return EXIT_FAILURE;
+    vector<uint8_t> bwt((istreambuf_iterator<char>(f)), istreambuf_iterator<char>());
+    if (!Rld::write(pos[2], bwt.data(), bwt.size(), err)) { logmsg("critical", err); return EXIT_FAILURE; }
+    return EXIT_SUCCESS;
+  }
+  if (pos[0] == "decode") {
+    RldFile rf;
+    vector<uint8_t> bwt;
+    if (!Rld::read(pos[1], rf, err) || !Rld::decode_bwt(rf, bwt, err)) { logmsg("critical", err); return EXIT_FAILURE; }
+    ofstream o(pos[2], ios::binary);
+    o.write((const char*)bwt.data(), (streamsize)bwt.size());
+    return o.good() ? EXIT_SUCCESS : EXIT_FAILURE;
+  }
+  if (pos[0] == "contigs") {
+    vector<uint8_t> cat;
+    vector<int64_t> offs;
+    if (!fmd_to_contigs(pos[1], cat, offs)) return EXIT_FAILURE;
+    ofstream o(pos[2]);
+    for (size_t k = 0; k + 1 < offs.size(); ++k) {
+      o << ">seq" << k << "\n";
+      for (int64_t i = offs[k]; i < offs[k + 1]; ++i) o << "$ACGTN"[cat[(size_t)i]];
+      o << "\n";
+    }
+    return o.good() ? EXIT_SUCCESS : EXIT_FAILURE;
+  }
+  return EXIT_FAILURE;
+}
+
 int main(int argc, char** argv) {
   time_t t0;
   time(&t0);
@@ -342,6 +443,7 @@ int main(int argc, char** argv) {
     printf("%.6f\n", fuzz_ratio(pos[0], pos[1]));
     return 0;
   }
+  if (mode == "_fmd") return run_fmd_hook(pos);
   if (mode == "_clipper") return run_clipper_hook(c);   // test hook: Clipper::call without the GPU stages (tests/test_clipper_cpu.py)
   if (mode == "index") rc = run_index(c, pos);
   else if (mode == "smooth") {
