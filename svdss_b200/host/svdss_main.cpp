@@ -42,10 +42,14 @@ static const char* MAIN_USAGE =
     "  search  extract sample-specific strings (SFS) from a BAM/FASTX\n"
     "  call    POA consensus + ksw2 realignment + SV extraction from SFS clusters";
 static const char* INDEX_USAGE =
-    "Usage: SVDSS index [-t threads] [-d] [-o index] [--fmd <out.fmd>] <reference.fa[.gz]>\n"
-    "       SVDSS index --from-fmd <ropebwt3.fmd> [-o index]\n"
+    "Usage: SVDSS index [-t threads] [-d] [-o index] [--fmd <out.fmd>] <reference.fa[.gz]> [...]\n"
+    "       SVDSS index --from-fmd <ropebwt3.fmd> [-o index]          (same as -i <ropebwt3.fmd>)\n"
+    "  -o FILE     output [stdout]\n"
+    "  -L          one sequence per line\n"
     "  --fmd       also dump the BWT in ropebwt3's FMD format (what the reference's `index -d` writes)\n"
-    "  --from-fmd  convert an index built by the reference (ropebwt3 FMD) instead of reading a FASTA";
+    "  --from-fmd  convert an index built by the reference (ropebwt3 FMD) instead of reading a FASTA\n"
+    "  ropebwt3 build's tuning flags (-m -l -n -p NUM, -2 -s -r -d) are accepted and have no effect on\n"
+    "  search results; -F / -R (one strand only), -b and -T (other output formats) are refused.";
 static const char* CALL_USAGE =
     "Usage: SVDSS call --reference <fa> (--bam <bam> --sfs <sfs> | --clusters-in <clusters.txt>) [--threads 4]\n"
     "                  [--min-cluster-weight 2] [--min-sv-length 25] [--min-mapq 20] [-l 0.97] [--noht]\n"
@@ -62,7 +66,7 @@ struct Config {
   string index, bam, fastx, out, reference, sfs, clusters_in, clusters_out, poa, clips_out, clips_in, regions_in, fmd_out, fmd_in;
   int min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
   float min_ratio = 0.97f, accp = 0.98f;
-  bool noht = false, clipped = false, cluster_only = false;
+  bool noht = false, clipped = false, cluster_only = false, line_input = false;
   int threads = 4, bsize = 10000, omax = 100000, device = 0;
   bool assemble = true, putative = true, verbose = false, help = false, version = false;
   int overlap = -1;  // config.hpp:82: never settable from the command line
@@ -167,21 +171,74 @@ static bool fmd_to_contigs(const string& path, vector<uint8_t>& cat, vector<int6
   return true;
 }
 
+// `SVDSS index` = ropebwt3's `build` command line (main.cpp:34-37 hands argv to main_build): getopt-style
+// short options, values attached or separate, several input files.  Returns false on a usage error.
+static bool parse_index(int argc, char** argv, Config& c, vector<string>& positional) {
+  for (int i = 2; i < argc; ++i) {
+    const string a = argv[i];
+    if (a == "--fmd" || a == "--from-fmd" || a == "--device" || a == "--threads") {
+      if (i + 1 >= argc) { logmsg("critical", "option " + a + " needs a value"); return false; }
+      const string v = argv[++i];
+      if (a == "--fmd") c.fmd_out = v; else if (a == "--from-fmd") c.fmd_in = v; else if (a == "--device") c.device = atoi(v.c_str()); else c.threads = atoi(v.c_str());
+      continue;
+    }
+    if (a == "--help") { c.help = true; continue; }
+    if (a == "--version") { c.version = true; continue; }
+    if (a.size() < 2 || a[0] != '-' || a == "-") { positional.push_back(a); continue; }
+    if (a[1] == '-') { logmsg("critical", "unknown option " + a); return false; }
+    for (size_t k = 1; k < a.size(); ++k) {            // a cluster of short options, like getopt
+      const char o = a[k];
+      if (strchr("tomlnpiS", o)) {                       // options with a value: rest of the word, or the next word
+        string v = a.substr(k + 1);
+        if (v.empty()) { if (i + 1 >= argc) { logmsg("critical", string("option -") + o + " needs a value"); return false; } v = argv[++i]; }
+        if (o == 't') c.threads = atoi(v.c_str());
+        else if (o == 'o') c.out = v;
+        else if (o == 'i') c.fmd_in = v;                 // ropebwt3: read an existing FMD/FMR index
+        else if (o == 'S') { logmsg("critical", "-S (save after each input file) is not supported"); return false; }
+        break;                                           // -m -l -n -p: tuning of ropebwt3's builder, nothing to tune here
+      }
+      if (o == 'd' || o == '2' || o == 's' || o == 'r') continue;   // FMD output is implied; BCR / RLO / RCLO only permute the BWT
+      if (o == 'L') { c.line_input = true; continue; }
+      if (o == 'h') { c.help = true; continue; }
+      if (o == 'F' || o == 'R') { logmsg("critical", string("-") + o + ": SVDSS search needs both strands in the index"); return false; }
+      if (o == 'b' || o == 'T') { logmsg("critical", string("-") + o + ": only this library's index format (and --fmd) can be written"); return false; }
+      logmsg("critical", string("unknown option -") + o);
+      return false;
+    }
+  }
+  if (c.threads < 1) c.threads = 1;
+  return true;
+}
+
 static int run_index(const Config& c, const vector<string>& pos) {
   vector<uint8_t> cat;
   vector<int64_t> offs(1, 0);
   if (!c.fmd_in.empty()) {
-    if (!pos.empty()) { cerr << INDEX_USAGE << endl; return EXIT_FAILURE; }
+    if (!pos.empty()) { logmsg("critical", "adding sequences to an existing index is not supported"); return EXIT_FAILURE; }
+    if (!Rld::is_rld(c.fmd_in)) { logmsg("critical", c.fmd_in + " is not a ropebwt3 FMD (RLD\\3) file"); return EXIT_FAILURE; }
     if (!fmd_to_contigs(c.fmd_in, cat, offs)) return EXIT_FAILURE;
   } else {
-    if (pos.size() != 1) { cerr << INDEX_USAGE << endl; return EXIT_FAILURE; }
-    FastxReader fx(pos[0]);
-    if (!fx.ok()) { logmsg("critical", "cannot open " + pos[0]); return EXIT_FAILURE; }
-    FastxRecord r;
+    if (pos.empty()) { cerr << INDEX_USAGE << endl; return EXIT_FAILURE; }
     const uint8_t* t6 = nt6_table();
-    while (fx.next(r)) {
-      for (char ch : r.seq) cat.push_back(t6[(uint8_t)ch]);
-      offs.push_back((int64_t)cat.size());
+    for (const string& path : pos) {                     // ropebwt3 build takes any number of input files
+      if (c.line_input) {                                // -L: one sequence per line
+        GzSource src(path);
+        if (!src.ok()) { logmsg("critical", "cannot open " + path); return EXIT_FAILURE; }
+        string line;
+        while (src.getline(line)) {
+          if (line.empty()) continue;
+          for (char ch : line) cat.push_back(t6[(uint8_t)ch]);
+          offs.push_back((int64_t)cat.size());
+        }
+        continue;
+      }
+      FastxReader fx(path);
+      if (!fx.ok()) { logmsg("critical", "cannot open " + path); return EXIT_FAILURE; }
+      FastxRecord r;
+      while (fx.next(r)) {
+        for (char ch : r.seq) cat.push_back(t6[(uint8_t)ch]);
+        offs.push_back((int64_t)cat.size());
+      }
     }
     if (offs.size() < 2) { logmsg("critical", "no sequences in " + pos[0]); return EXIT_FAILURE; }
   }
@@ -433,8 +490,8 @@ int main(int argc, char** argv) {
   if (argc == 1) { cerr << MAIN_USAGE << endl; exit(EXIT_FAILURE); }   // main.cpp:27-31
   Config c;
   vector<string> pos;
-  if (!parse_common(argc, argv, c, pos)) exit(EXIT_FAILURE);
   const string mode = argv[1];
+  if (mode == "index" ? !parse_index(argc, argv, c, pos) : !parse_common(argc, argv, c, pos)) exit(EXIT_FAILURE);
   if (c.version) { cout << "SVDSS, " << VERSION << endl; exit(EXIT_SUCCESS); }
   if (c.help) { cerr << (mode == "index" ? INDEX_USAGE : mode == "smooth" ? SMOOTH_USAGE : mode == "search" ? SEARCH_USAGE : mode == "call" ? CALL_USAGE : MAIN_USAGE) << endl; exit(EXIT_SUCCESS); }
   int rc;

@@ -48,3 +48,26 @@ def test_cxxopts_spellings_are_accepted(exe, tmp_path):
     assert r.returncode == 1 and "svb_index_load" in r.stderr and "unknown option" not in r.stderr
     r = subprocess.run([exe, "call", "--reference=x.fa", "--clipped"], capture_output=True, text=True)   # still needs --bam/--sfs
     assert r.returncode == 1 and "Usage" in r.stderr
+
+
+def test_index_takes_ropebwt3_build_options(exe, tmp_path):
+    """`SVDSS index` is ropebwt3's `build` (main.cpp:34-37; run_svdss:142 `-t N -d FA -o OUT`, README.md:113
+    `-t16 -d FA > OUT`): getopt clusters and tuning flags parse, strand/format changes are refused."""
+    fa = tmp_path / "r.fa"
+    fa.write_text(">a\nACGTACGTAC\n>b\nGGGTTTAACC\n")
+    for args in (["-t16", "-d", str(fa)], ["-t", "4", "-d", str(fa), "-o", str(tmp_path / "x.idx")], ["-dt2", "-m", "1G", "-l512", "-2s", str(fa)],
+                 ["-L", str(fa), str(fa)]):
+        r = subprocess.run([exe, "index"] + args, capture_output=True, text=True)
+        assert "unknown option" not in r.stderr and "needs a value" not in r.stderr, r.stderr
+        assert "indexing" in r.stderr                      # reached the GPU build (which fails loudly without a GPU)
+        if r.returncode != 0:
+            assert "svb_index_build" in r.stderr
+    r = subprocess.run([exe, "index", "-d", str(fa), str(fa)], capture_output=True, text=True)
+    assert "indexing 4 sequences, 40 bp" in r.stderr      # several input files, like ropebwt3 build
+    r = subprocess.run([exe, "index", "-L", str(tmp_path / "r.fa")], capture_output=True, text=True)
+    assert "indexing 4 sequences" in r.stderr             # -L: every line is a sequence (headers included, as in ropebwt3)
+    for bad in (["-R", str(fa)], ["-F", str(fa)], ["-b", str(fa)], ["-q", str(fa)], ["-o"], []):
+        r = subprocess.run([exe, "index"] + bad, capture_output=True, text=True)
+        assert r.returncode == 1 and "indexing" not in r.stderr, bad
+    r = subprocess.run([exe, "index", "-i", str(fa)], capture_output=True, text=True)
+    assert r.returncode == 1 and "not a ropebwt3 FMD" in r.stderr
