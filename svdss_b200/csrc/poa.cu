@@ -112,7 +112,15 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
 #ifndef SVB_POA_MINB
 #define SVB_POA_MINB 4
 #endif
+// SMEM: the scores (H, E1, E2) of the row just finished are also kept in shared memory (two buffers per
+// warp, 6 * wcap ints), and a row whose predecessor is that row -- the common case, a chain -- reads them
+// from there instead of from the workspace.  The workspace of all resident warps is far larger than L2
+// (profiles/r01_poa_full.txt: 21 % L2 hit rate, long-scoreboard stalls dominate), so without this every
+// row waits for a DRAM round trip on values the warp itself produced a microsecond earlier.  Results are
+// identical (same values, same order of comparisons); selected by the host when the buffers fit.
+template <bool SMEM>
 __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
+  extern __shared__ int poa_smem[];
   const int lane = threadIdx.x & 31;
   const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint8_t* wsp = P.ws + (int64_t)slot * P.ws_stride;
@@ -122,6 +130,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   const PoaWs& W = g.w;
   const int Wc = P.wcap;
   const int mm = P.mismatch < 0 ? -P.mismatch : P.mismatch;
+  int* const sbuf = SMEM ? poa_smem + (threadIdx.x >> 5) * 6 * Wc : nullptr;   // [2 buffers][H, E1, E2][Wc]
   for (;;) {
     unsigned wi = 0;
     if (lane == 0) wi = atomicAdd(P.work, 1u);
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         for (int j = lane; j <= end0; j += 32) {
           const int c1 = P.o1 + j * P.e1, c2 = P.o2 + j * P.e2;
           W.H[j] = j ? -min(c1, c2) : 0; W.E1[j] = PNEG; W.E2[j] = PNEG;
+          if (SMEM) { sbuf[j] = j ? -min(c1, c2) : 0; sbuf[Wc + j] = PNEG; sbuf[2 * Wc + j] = PNEG; }   // buffer 0 = the row before rank 0
           unsigned t = j ? (c1 <= c2 ? 3u : 4u) : 0u;
           if (j > 1) t |= (c1 <= c2) ? (1u << 7) : (1u << 8);
           W.TB[j] = t;
@@ -231,6 +241,8 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         if (en - b + 1 > Wc) { en = b + Wc - 1; status |= POA_CLAMPED; }
         int* hrow = W.H + (int64_t)v * Wc; int* e1row = W.E1 + (int64_t)v * Wc; int* e2row = W.E2 + (int64_t)v * Wc;
         unsigned* tbrow = W.TB + (int64_t)v * Wc;
+        const int* const sprev = SMEM ? sbuf + (r & 1) * 3 * Wc : nullptr;        // scores of row v_prev
+        int* const scur = SMEM ? sbuf + ((r + 1) & 1) * 3 * Wc : nullptr;
         int carry1 = PNEG, carry2 = PNEG;      // running max of B1/B2 over columns before this segment
         int prevX1 = PNEG, prevB1 = PNEG, prevX2 = PNEG, prevB2 = PNEG;  // column j-1 of lane 0
         int rmax = PNEG - 1, rleft = 0, rright = 0;
@@ -241,6 +253,9 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           const int qb = (act && j >= 1) ? q[j - 1] : 4;
           auto consider = [&](int p, int bp, int ep, int ord) {   // predecessor p with band [bp, ep], in-edge ordinal ord
             const int* ph = W.H + (int64_t)p * Wc;
+            const int* pe1 = W.E1 + (int64_t)p * Wc;
+            const int* pe2 = W.E2 + (int64_t)p * Wc;
+            if (SMEM && p == v_prev) { ph = sprev; pe1 = sprev + Wc; pe2 = sprev + 2 * Wc; }
             if (act && j >= 1 && j - 1 >= bp && j - 1 <= ep) {
               const int s = (bv >= 4 || qb >= 4) ? 0 : (bv == qb ? P.match : -mm);
               const int cval = ph[j - 1 - bp] + s;
@@ -248,10 +263,10 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
             }
             if (act && j >= bp && j <= ep) {
               const int hj = ph[j - bp];
-              int op = hj - P.o1, ex = W.E1[(int64_t)p * Wc + j - bp];
+              int op = hj - P.o1, ex = pe1[j - bp];
               int cval = max(op, ex) - P.e1;
               if (cval > x1) { x1 = cval; p1 = ord; x1ext = ex > op; }
-              op = hj - P.o2; ex = W.E2[(int64_t)p * Wc + j - bp];
+              op = hj - P.o2; ex = pe2[j - bp];
               cval = max(op, ex) - P.e2;
               if (cval > x2) { x2 = cval; p2 = ord; x2ext = ex > op; }
             }
@@ -287,6 +302,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           if (f2 > hh) { hh = f2; hs = 4; }
           if (act) {
             hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2;
+            if (SMEM) { scur[j - b] = hh; scur[Wc + j - b] = x1; scur[2 * Wc + j - b] = x2; }
             tbrow[j - b] = hs | (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)f1ext << 7) |
                            ((unsigned)f2ext << 8) | ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) |
                            ((unsigned)(p2 & 0x3f) << 26);
@@ -578,7 +594,17 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
       cudaEvent_t k0, k1;
       PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
       PCHECK(cudaEventRecord(k0, 0));
-      k_poa<<<(unsigned)(slots / 4), 128>>>(P);
+      // shared-memory copy of the previous row (k_poa<true>): 2 buffers x 3 arrays x wcap ints per warp; used
+      // when SVB_POA_SMEM=1 and SVB_POA_MINB CTAs of it still fit an SM (else the rows come from the workspace)
+      const size_t smem = (size_t)4 * 6 * (size_t)wcap * sizeof(int);
+      const char* es = getenv("SVB_POA_SMEM");
+      const bool use_smem = es && atoi(es) != 0 && smem * SVB_POA_MINB <= (size_t)224 * 1024 && smem <= (size_t)200 * 1024;
+      if (use_smem) {
+        PCHECK(cudaFuncSetAttribute(k_poa<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_poa<true><<<(unsigned)(slots / 4), 128, smem>>>(P);
+      } else {
+        k_poa<false><<<(unsigned)(slots / 4), 128>>>(P);
+      }
       PCHECK(cudaGetLastError());
       PCHECK(cudaEventRecord(k1, 0));
       PCHECK(cudaEventSynchronize(k1));
