@@ -343,20 +343,24 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           int v = best_p, j = ql, state = 0;  // 0 H, 5 Hp, 1 E1, 2 E2, 3 F1, 4 F2
           while (v != 0 || j > 0) {
             if (v == 0) { W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop; --j; continue; }
+            // SMEM variant: the first predecessor comes from in1[v] (= efrom[first_in[v]] << 1 | more), loaded next
+            // to beg[v] instead of through first_in -> efrom after the traceback word: two dependent loads per step, not four
+            const int in1v = SMEM ? W.in1[v] : 0;
             const unsigned t = W.TB[(int64_t)v * Wc + j - W.beg[v]];
             if (state == 0) state = (int)(t & 7);
             else if (state == 5) state = (int)((t >> 3) & 3);
             if (state == 0) {
-              int ord = (int)((t >> 12) & 0xff), e = W.first_in[v];
-              while (ord--) e = W.enin[e];
+              int ord = (int)((t >> 12) & 0xff);
               W.op_node[nop] = v; W.op_q[nop] = j - 1; ++nop;
-              v = W.efrom[e]; --j; state = 0;
+              if (SMEM && ord == 0) v = in1v >> 1;
+              else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
+              --j; state = 0;
             } else if (state == 1 || state == 2) {
-              int ord = (int)((t >> (state == 1 ? 20 : 26)) & 0x3f), e = W.first_in[v];
-              while (ord--) e = W.enin[e];
+              int ord = (int)((t >> (state == 1 ? 20 : 26)) & 0x3f);
               const int ext = (int)((t >> (state == 1 ? 5 : 6)) & 1);
               W.op_node[nop] = v; W.op_q[nop] = -1; ++nop;
-              v = W.efrom[e];
+              if (SMEM && ord == 0) v = in1v >> 1;
+              else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
               if (!ext) state = 0;
               if (v == 0) state = 0;
             } else {
