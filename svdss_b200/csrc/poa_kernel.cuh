@@ -1,0 +1,455 @@
+// Device code of the cluster POA (see poa.cu for the design notes): parameters, workspace layout, graph
+// primitives and the k_poa kernel.  Kept free of host / runtime-API code so that tests/emul can compile
+// the very same source for the CPU with a lock-step warp emulator (tests/emul/warp_emul.hpp) and check
+// kernel variants against the oracle without a GPU.
+#pragma once
+#include <stdint.h>
+
+namespace svb {
+
+constexpr int PNEG = -(1 << 29);
+constexpr int POA_OK = 0, POA_OVERFLOW = 1, POA_CLAMPED = 2;
+
+struct PoaParams {
+  const uint8_t* __restrict__ seqs;
+  const int64_t* __restrict__ seq_offs;      // n_seqs + 1
+  const int64_t* __restrict__ cluster_offs;  // n_clusters + 1 (indexes seq_offs)
+  const uint32_t* __restrict__ order;        // clusters of this launch, biggest first
+  int n;                                     // clusters in this launch
+  unsigned int* work;
+  // workspace, one slot per resident warp
+  uint8_t* ws;
+  int64_t ws_stride;  // bytes per slot
+  int ncap, ecap, wcap, lmax;
+  // outputs
+  uint8_t* cons;                   // cons_cap bytes per cluster, at cons_off[cluster]
+  const int64_t* __restrict__ cons_off;
+  int32_t* cons_len;
+  int32_t* status;
+  unsigned long long* cells;
+  unsigned long long* phase;   // SVB_POA_TIMING: clock cycles per phase, summed over warps (lane 0)
+  int match, mismatch, o1, e1, o2, e2, wb;
+  float wf;
+};
+
+// per-slot workspace carving (all int32 unless noted); must match poa_ws_bytes()
+struct PoaWs {
+  uint8_t* base;
+  int *rank, *order, *first_in, *last_in, *first_out, *last_out, *ring, *remain, *mpl, *mpr, *beg, *end, *cnt, *in1;
+  int *efrom, *eto, *ew, *enin, *enout;
+  int *op_node, *op_q, *new_anchor, *new_id;
+  int *H, *E1, *E2;
+  unsigned* TB;
+};
+
+__host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+__host__ __device__ inline int64_t poa_ws_carve(uint8_t* p, int ncap, int ecap, int wcap, int lmax, PoaWs* w) {
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t at = o; o = align16(o + bytes); return at; };
+  int64_t a;
+#define TAKE_I(f, n) a = take((int64_t)(n) * 4); if (w) w->f = reinterpret_cast<int*>(p + a)
+  a = take(ncap); if (w) w->base = p + a;
+  TAKE_I(rank, ncap); TAKE_I(order, ncap); TAKE_I(first_in, ncap); TAKE_I(last_in, ncap); TAKE_I(first_out, ncap);
+  TAKE_I(last_out, ncap); TAKE_I(ring, ncap); TAKE_I(remain, ncap); TAKE_I(mpl, ncap); TAKE_I(mpr, ncap);
+  TAKE_I(beg, ncap); TAKE_I(end, ncap); TAKE_I(cnt, ncap + 2); TAKE_I(in1, ncap);
+  TAKE_I(efrom, ecap); TAKE_I(eto, ecap); TAKE_I(ew, ecap); TAKE_I(enin, ecap); TAKE_I(enout, ecap);
+  TAKE_I(op_node, ncap + lmax + 4); TAKE_I(op_q, ncap + lmax + 4); TAKE_I(new_anchor, lmax + 2); TAKE_I(new_id, lmax + 2);
+  TAKE_I(H, (int64_t)ncap * wcap); TAKE_I(E1, (int64_t)ncap * wcap); TAKE_I(E2, (int64_t)ncap * wcap);
+  a = take((int64_t)ncap * wcap * 4); if (w) w->TB = reinterpret_cast<unsigned*>(p + a);
+#undef TAKE_I
+  return align16(o + 240) & ~(int64_t)255;
+}
+
+struct Graph {
+  PoaWs w;
+  int n, ne, ncap, ecap;
+  bool overflow;
+  __device__ int node(uint8_t b) {
+    if (n >= ncap) { overflow = true; return ncap - 1; }
+    const int v = n++;
+    w.base[v] = b; w.rank[v] = -1; w.first_in[v] = w.last_in[v] = w.first_out[v] = w.last_out[v] = -1; w.ring[v] = v; w.in1[v] = 0;
+    return v;
+  }
+  __device__ void edge(int u, int v) {
+    for (int e = w.first_out[u]; e >= 0; e = w.enout[e])
+      if (w.eto[e] == v) { w.ew[e]++; return; }
+    if (ne >= ecap) { overflow = true; return; }
+    const int e = ne++;
+    w.efrom[e] = u; w.eto[e] = v; w.ew[e] = 1; w.enin[e] = -1; w.enout[e] = -1;
+    if (w.last_out[u] < 0) w.first_out[u] = e; else w.enout[w.last_out[u]] = e;
+    w.last_out[u] = e;
+    if (w.last_in[v] < 0) { w.first_in[v] = e; w.in1[v] = u << 1; } else { w.enin[w.last_in[v]] = e; w.in1[v] |= 1; }
+    w.last_in[v] = e;
+  }
+};
+
+__device__ __forceinline__ int warp_incl_max(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = max(v, u);
+  }
+  return v;
+}
+
+#ifndef SVB_POA_MINB
+#define SVB_POA_MINB 4
+#endif
+// SMEM: the scores (H, E1, E2) of the row just finished are also kept in shared memory (two buffers per
+// warp, 6 * wcap ints), and a row whose predecessor is that row -- the common case, a chain -- reads them
+// from there instead of from the workspace.  The workspace of all resident warps is far larger than L2
+// (profiles/r01_poa_full.txt: 21 % L2 hit rate, long-scoreboard stalls dominate), so without this every
+// row waits for a DRAM round trip on values the warp itself produced a microsecond earlier.  Results are
+// identical (same values, same order of comparisons); selected by the host when the buffers fit.
+template <bool SMEM>
+__global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
+  extern __shared__ int poa_smem[];
+  const int lane = threadIdx.x & 31;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint8_t* wsp = P.ws + (int64_t)slot * P.ws_stride;
+  Graph g;
+  poa_ws_carve(wsp, P.ncap, P.ecap, P.wcap, P.lmax, &g.w);
+  g.ncap = P.ncap; g.ecap = P.ecap;
+  const PoaWs& W = g.w;
+  const int Wc = P.wcap;
+  const int mm = P.mismatch < 0 ? -P.mismatch : P.mismatch;
+  int* const sbuf = SMEM ? poa_smem + (threadIdx.x >> 5) * 6 * Wc : nullptr;   // [2 buffers][H, E1, E2][Wc]
+  for (;;) {
+    unsigned wi = 0;
+    if (lane == 0) wi = atomicAdd(P.work, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= (unsigned)P.n) break;
+    const uint32_t cid = P.order[wi];
+    const int64_t s0 = P.cluster_offs[cid], s1 = P.cluster_offs[cid + 1];
+    g.n = 0; g.ne = 0; g.overflow = false;
+    int status = POA_OK;
+    unsigned long long cells = 0;
+    long long t_setup = 0, t_dp = 0, t_tb = 0, t_upd = 0, t_cons = 0, tc = clock64();
+#define PHASE(acc) do { if (P.phase) { const long long _n = clock64(); acc += _n - tc; tc = _n; } } while (0)
+    if (lane == 0) { g.node(0); g.node(0); }  // source, sink
+    g.n = 2;
+    __syncwarp();
+    for (int64_t si = s0; si < s1 && !g.overflow; ++si) {
+      const uint8_t* q = P.seqs + P.seq_offs[si];
+      const int ql = (int)(P.seq_offs[si + 1] - P.seq_offs[si]);
+      if (ql <= 0) continue;
+      if (ql > P.lmax) { g.overflow = true; break; }
+      const int N = g.n;
+      if (N == 2) {  // first read: a chain (warp-parallel)
+        if (ql + 2 > g.ncap || ql + 1 > g.ecap) { g.overflow = true; break; }
+        for (int j = lane; j < ql; j += 32) {
+          const int v = 2 + j;
+          W.base[v] = q[j]; W.rank[v] = j; W.ring[v] = v;
+          // edge j: (j ? v-1 : source) -> v ; edge ql: last -> sink
+          W.efrom[j] = j ? v - 1 : 0; W.eto[j] = v; W.ew[j] = 1; W.enin[j] = -1; W.enout[j] = -1;
+          W.first_in[v] = W.last_in[v] = j; W.in1[v] = (j ? v - 1 : 0) << 1;
+          W.first_out[v] = W.last_out[v] = j + 1;
+        }
+        if (lane == 0) {
+          W.efrom[ql] = 2 + ql - 1; W.eto[ql] = 1; W.ew[ql] = 1; W.enin[ql] = -1; W.enout[ql] = -1;
+          W.first_out[0] = W.last_out[0] = 0;
+          W.first_in[1] = W.last_in[1] = ql; W.in1[1] = (2 + ql - 1) << 1;
+        }
+        g.n = 2 + ql; g.ne = ql + 1;
+        __syncwarp();
+        continue;
+      }
+      const int n_ord = N - 2;
+      for (int v = 2 + lane; v < N; v += 32) { W.order[W.rank[v]] = v; }
+      for (int s = lane; s <= n_ord + 1; s += 32) W.cnt[s] = 0;
+      __syncwarp();
+      // remain[]: heaviest out-neighbour chain length to the sink (lane 0, reverse rank order)
+      if (lane == 0) {
+        W.remain[1] = 0;
+        for (int r = n_ord - 1; r >= -1; --r) {
+          const int v = r >= 0 ? W.order[r] : 0;
+          int bw = -1, bv = 1;
+          for (int e = W.first_out[v]; e >= 0; e = W.enout[e])
+            if (W.ew[e] > bw) { bw = W.ew[e]; bv = W.eto[e]; }
+          W.remain[v] = W.remain[bv] + 1;
+        }
+      }
+      __syncwarp();
+      const int w = P.wb + (int)(P.wf * (float)ql);
+      PHASE(t_setup);
+      // ---- source row
+      {
+        int end0 = min(w, ql);
+        if (end0 + 1 > Wc) { end0 = Wc - 1; status |= POA_CLAMPED; }
+        for (int j = lane; j <= end0; j += 32) {
+          const int c1 = P.o1 + j * P.e1, c2 = P.o2 + j * P.e2;
+          W.H[j] = j ? -min(c1, c2) : 0; W.E1[j] = PNEG; W.E2[j] = PNEG;
+          if (SMEM) { sbuf[j] = j ? -min(c1, c2) : 0; sbuf[Wc + j] = PNEG; sbuf[2 * Wc + j] = PNEG; }   // buffer 0 = the row before rank 0
+          unsigned t = j ? (c1 <= c2 ? 3u : 4u) : 0u;
+          if (j > 1) t |= (c1 <= c2) ? (1u << 7) : (1u << 8);
+          W.TB[j] = t;
+        }
+        // mpl[v] / mpr[v] = (first / last column of row v's maximum) + 1: what v offers to its
+        // successors' bands.  A row PULLS the min / max over its in-edges (the same min / max abPOA
+        // pushes along out-edges after each row) -- no out-edge walk, no per-read reset of the arrays.
+        if (lane == 0) { W.beg[0] = 0; W.end[0] = end0; W.mpl[0] = 1; W.mpr[0] = 1; }
+        __syncwarp();
+      }
+      // ---- graph rows in rank order
+      // Row r needs: its node v (rank order), v's fields, its in-edges, the predecessors' bands, their
+      // score rows -- a chain of dependent loads.  The node fields of row r+1 are fetched while row r is
+      // computed, the first predecessor sits next to them (in1 = pred << 1 | has-more-in-edges), and a
+      // predecessor that is the row just finished hands its band over in registers: the common row
+      // (one in-edge, from the previous row) waits for its predecessor's scores only.
+      int v_next = n_ord > 0 ? W.order[0] : 0;
+      int nx_in1 = W.in1[v_next], nx_remain = W.remain[v_next], nx_base = W.base[v_next];
+      int v_prev = 0, b_prev = 0, en_prev = W.end[0], l_prev = 1, r_prev = 1;   // the source row
+      for (int r = 0; r < n_ord; ++r) {
+        const int v = v_next, in1 = nx_in1, bv = nx_base;
+        const int c = ql - nx_remain + 1;
+        if (r + 1 < n_ord) {                          // in flight while this row is computed
+          v_next = W.order[r + 1];
+          nx_in1 = W.in1[v_next]; nx_remain = W.remain[v_next]; nx_base = W.base[v_next];
+        }
+        const bool single = !(in1 & 1);
+        const int p0 = in1 >> 1;
+        int p0b, p0e, pl, pr;
+        if (single) {
+          if (p0 == v_prev) { p0b = b_prev; p0e = en_prev; pl = l_prev; pr = r_prev; }
+          else { p0b = W.beg[p0]; p0e = W.end[p0]; pl = W.mpl[p0]; pr = W.mpr[p0]; }
+        } else {
+          p0b = 0; p0e = -1; pl = 0x7fffffff; pr = -1;
+          for (int e = W.first_in[v]; e >= 0; e = W.enin[e]) {
+            const int p = W.efrom[e];
+            pl = min(pl, W.mpl[p]); pr = max(pr, W.mpr[p]);
+          }
+        }
+        int b = max(0, min(pl, c) - w), en = min(ql, max(pr, c) + w);
+        if (b > en) b = en;
+        if (en - b + 1 > Wc) { en = b + Wc - 1; status |= POA_CLAMPED; }
+        int* hrow = W.H + (int64_t)v * Wc; int* e1row = W.E1 + (int64_t)v * Wc; int* e2row = W.E2 + (int64_t)v * Wc;
+        unsigned* tbrow = W.TB + (int64_t)v * Wc;
+        const int* const sprev = SMEM ? sbuf + (r & 1) * 3 * Wc : nullptr;        // scores of row v_prev
+        int* const scur = SMEM ? sbuf + ((r + 1) & 1) * 3 * Wc : nullptr;
+        int carry1 = PNEG, carry2 = PNEG;      // running max of B1/B2 over columns before this segment
+        int prevX1 = PNEG, prevB1 = PNEG, prevX2 = PNEG, prevB2 = PNEG;  // column j-1 of lane 0
+        int rmax = PNEG - 1, rleft = 0, rright = 0;
+        for (int j0 = b; j0 <= en; j0 += 32) {
+          const int j = j0 + lane;
+          const bool act = j <= en;
+          int m = PNEG, x1 = PNEG, x2 = PNEG, pm = 0, p1 = 0, p2 = 0, x1ext = 0, x2ext = 0;
+          const int qb = (act && j >= 1) ? q[j - 1] : 4;
+          auto consider = [&](int p, int bp, int ep, int ord) {   // predecessor p with band [bp, ep], in-edge ordinal ord
+            const int* ph = W.H + (int64_t)p * Wc;
+            const int* pe1 = W.E1 + (int64_t)p * Wc;
+            const int* pe2 = W.E2 + (int64_t)p * Wc;
+            if (SMEM && p == v_prev) { ph = sprev; pe1 = sprev + Wc; pe2 = sprev + 2 * Wc; }
+            if (act && j >= 1 && j - 1 >= bp && j - 1 <= ep) {
+              const int s = (bv >= 4 || qb >= 4) ? 0 : (bv == qb ? P.match : -mm);
+              const int cval = ph[j - 1 - bp] + s;
+              if (cval > m) { m = cval; pm = ord; }
+            }
+            if (act && j >= bp && j <= ep) {
+              const int hj = ph[j - bp];
+              int op = hj - P.o1, ex = pe1[j - bp];
+              int cval = max(op, ex) - P.e1;
+              if (cval > x1) { x1 = cval; p1 = ord; x1ext = ex > op; }
+              op = hj - P.o2; ex = pe2[j - bp];
+              cval = max(op, ex) - P.e2;
+              if (cval > x2) { x2 = cval; p2 = ord; x2ext = ex > op; }
+            }
+          };
+          if (single) {
+            consider(p0, p0b, p0e, 0);
+          } else {
+            int ord = 0;
+            for (int e = W.first_in[v]; e >= 0; e = W.enin[e], ++ord) {
+              const int p = W.efrom[e];
+              consider(p, W.beg[p], W.end[p], ord);
+            }
+          }
+          m = max(m, PNEG); x1 = max(x1, PNEG); x2 = max(x2, PNEG);
+          int hp = m; unsigned hps = 0;
+          if (x1 > hp) { hp = x1; hps = 1; }
+          if (x2 > hp) { hp = x2; hps = 2; }
+          // F1/F2: exclusive max-plus prefix scan of B(k) = Hp(k) + k*e over the row
+          const int B1 = act ? hp + j * P.e1 : PNEG, B2 = act ? hp + j * P.e2 : PNEG;
+          const int inc1 = warp_incl_max(B1, lane), inc2 = warp_incl_max(B2, lane);
+          int ex1 = __shfl_up_sync(0xffffffffu, inc1, 1), ex2 = __shfl_up_sync(0xffffffffu, inc2, 1);
+          if (lane == 0) { ex1 = PNEG; ex2 = PNEG; }
+          const int X1 = max(carry1, ex1), X2 = max(carry2, ex2);
+          int f1 = PNEG, f2 = PNEG;
+          if (j > b) { f1 = max(X1 - P.o1 - j * P.e1, PNEG); f2 = max(X2 - P.o2 - j * P.e2, PNEG); }
+          // ext flag of column j: F(j-1) > Hp(j-1) - o  <=>  X(j-1) > B(j-1)
+          int pX1 = __shfl_up_sync(0xffffffffu, X1, 1), pB1 = __shfl_up_sync(0xffffffffu, B1, 1);
+          int pX2 = __shfl_up_sync(0xffffffffu, X2, 1), pB2 = __shfl_up_sync(0xffffffffu, B2, 1);
+          if (lane == 0) { pX1 = prevX1; pB1 = prevB1; pX2 = prevX2; pB2 = prevB2; }
+          const int f1ext = (j > b) && (pX1 > pB1), f2ext = (j > b) && (pX2 > pB2);
+          int hh = hp; unsigned hs = hps;
+          if (f1 > hh) { hh = f1; hs = 3; }
+          if (f2 > hh) { hh = f2; hs = 4; }
+          if (act) {
+            hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2;
+            if (SMEM) { scur[j - b] = hh; scur[Wc + j - b] = x1; scur[2 * Wc + j - b] = x2; }
+            tbrow[j - b] = hs | (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)f1ext << 7) |
+                           ((unsigned)f2ext << 8) | ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) |
+                           ((unsigned)(p2 & 0x3f) << 26);
+            if (hh > rmax) { rmax = hh; rleft = j; rright = j; }
+            else if (hh == rmax) rright = j;
+          }
+          carry1 = max(carry1, __shfl_sync(0xffffffffu, inc1, 31));
+          carry2 = max(carry2, __shfl_sync(0xffffffffu, inc2, 31));
+          prevX1 = __shfl_sync(0xffffffffu, X1, 31); prevB1 = __shfl_sync(0xffffffffu, B1, 31);
+          prevX2 = __shfl_sync(0xffffffffu, X2, 31); prevB2 = __shfl_sync(0xffffffffu, B2, 31);
+        }
+        cells += (unsigned long long)(en - b + 1);
+        // row maximum, its first and last column (lanes hold strided columns: reduce)
+        int gmax = rmax;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        int l_ = (rmax == gmax) ? rleft : 0x7fffffff, r_ = (rmax == gmax) ? rright : -1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          l_ = min(l_, __shfl_xor_sync(0xffffffffu, l_, o));
+          r_ = max(r_, __shfl_xor_sync(0xffffffffu, r_, o));
+        }
+        if (lane == 0) { W.beg[v] = b; W.end[v] = en; W.mpl[v] = l_ + 1; W.mpr[v] = r_ + 1; }
+        v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1;
+        __syncwarp();
+      }
+      PHASE(t_dp);
+      // ---- end point, traceback, graph update, re-rank: lane 0
+      if (lane == 0) {
+        int best_p = -1, best = PNEG - 1;
+        for (int e = W.first_in[1]; e >= 0; e = W.enin[e]) {
+          const int p = W.efrom[e];
+          const int val = (ql >= W.beg[p] && ql <= W.end[p]) ? W.H[(int64_t)p * Wc + ql - W.beg[p]] : PNEG;
+          if (val > best) { best = val; best_p = p; }
+        }
+        int nop = 0;
+        {
+          int v = best_p, j = ql, state = 0;  // 0 H, 5 Hp, 1 E1, 2 E2, 3 F1, 4 F2
+          while (v != 0 || j > 0) {
+            if (v == 0) { W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop; --j; continue; }
+            // SMEM variant: the first predecessor comes from in1[v] (= efrom[first_in[v]] << 1 | more), loaded next
+            // to beg[v] instead of through first_in -> efrom after the traceback word: two dependent loads per step, not four
+            const int in1v = SMEM ? W.in1[v] : 0;
+            const unsigned t = W.TB[(int64_t)v * Wc + j - W.beg[v]];
+            if (state == 0) state = (int)(t & 7);
+            else if (state == 5) state = (int)((t >> 3) & 3);
+            if (state == 0) {
+              int ord = (int)((t >> 12) & 0xff);
+              W.op_node[nop] = v; W.op_q[nop] = j - 1; ++nop;
+              if (SMEM && ord == 0) v = in1v >> 1;
+              else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
+              --j; state = 0;
+            } else if (state == 1 || state == 2) {
+              int ord = (int)((t >> (state == 1 ? 20 : 26)) & 0x3f);
+              const int ext = (int)((t >> (state == 1 ? 5 : 6)) & 1);
+              W.op_node[nop] = v; W.op_q[nop] = -1; ++nop;
+              if (SMEM && ord == 0) v = in1v >> 1;
+              else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
+              if (!ext) state = 0;
+              if (v == 0) state = 0;
+            } else {
+              const int ext = (int)((t >> (state == 3 ? 7 : 8)) & 1);
+              W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop;
+              --j;
+              if (!ext) state = 5;
+            }
+          }
+        }
+        PHASE(t_tb);
+        // graph update (abpoa_add_graph_alignment), forward order
+        int n_new = 0, prev = 0, anchor = 0;
+        const int n_old = N;
+        for (int k = nop - 1; k >= 0 && !g.overflow; --k) {
+          const int v = W.op_node[k], qi = W.op_q[k];
+          if (v >= 0) {
+            int mr = W.rank[v];
+            for (int u = W.ring[v]; u != v; u = W.ring[u]) if (u < n_old && W.rank[u] > mr) mr = W.rank[u];
+            anchor = mr + 1;
+          }
+          if (qi < 0) continue;
+          int use;
+          if (v >= 0) {
+            const uint8_t bq = q[qi];
+            if (W.base[v] == bq) use = v;
+            else {
+              use = -1;
+              for (int u = W.ring[v]; u != v; u = W.ring[u]) if (W.base[u] == bq) { use = u; break; }
+              if (use < 0) {
+                use = g.node(bq);
+                if (g.overflow) break;
+                W.ring[use] = W.ring[v]; W.ring[v] = use;
+                W.new_anchor[n_new] = anchor; W.new_id[n_new] = use; ++n_new; W.cnt[anchor]++;
+              }
+            }
+          } else {
+            use = g.node(q[qi]);
+            if (g.overflow) break;
+            W.new_anchor[n_new] = anchor; W.new_id[n_new] = use; ++n_new; W.cnt[anchor]++;
+          }
+          g.edge(prev, use);
+          prev = use;
+        }
+        if (!g.overflow) g.edge(prev, 1);
+        if (!g.overflow) {
+          // re-rank: exclusive prefix of cnt over slots (slot 0 = source, r+1 = old rank r)
+          int acc = 0;
+          for (int s = 0; s <= n_ord; ++s) { const int c_ = W.cnt[s]; W.cnt[s] = acc; acc += c_; }
+          for (int r = 0; r < n_ord; ++r) W.rank[W.order[r]] = r + W.cnt[r + 1];
+          // new nodes follow their anchor in creation order: reuse mpl[] as the per-slot counter
+          for (int k = 0; k < n_new; ++k) W.mpl[W.new_anchor[k] < N ? W.new_anchor[k] : 0] = 0;
+          for (int k = 0; k < n_new; ++k) {
+            const int s = W.new_anchor[k];
+            // slots range over 0..n_ord <= N-2, so mpl[s] is a valid scratch cell
+            W.rank[W.new_id[k]] = (s - 1 + W.cnt[s]) + 1 + W.mpl[s];
+            W.mpl[s]++;
+          }
+        }
+      }
+      PHASE(t_upd);
+      // lane 0's graph size / overflow flag are the truth
+      g.n = __shfl_sync(0xffffffffu, g.n, 0);
+      g.ne = __shfl_sync(0xffffffffu, g.ne, 0);
+      g.overflow = __shfl_sync(0xffffffffu, (int)g.overflow, 0) != 0;
+      __syncwarp();
+    }
+    // ---- consensus: heaviest bundling (lane 0)
+    if (lane == 0) {
+      int len = 0;
+      if (!g.overflow && g.n > 2) {
+        const int N = g.n, n_ord = N - 2;
+        for (int v = 2; v < N; ++v) W.order[W.rank[v]] = v;
+        int* score = W.remain; int* nxt = W.mpr;
+        score[1] = 0;
+        for (int r = n_ord - 1; r >= -1; --r) {
+          const int v = r >= 0 ? W.order[r] : 0;
+          int mw = -1, mi = -1;
+          for (int e = W.first_out[v]; e >= 0; e = W.enout[e]) {
+            const int o = W.eto[e], wgt = W.ew[e];
+            if (mw < wgt) { mw = wgt; mi = o; }
+            else if (mw == wgt && score[mi] <= score[o]) mi = o;
+          }
+          nxt[v] = mi;
+          score[v] = mi >= 0 ? mw + score[mi] : 0;
+        }
+        uint8_t* out = P.cons + P.cons_off[cid];
+        const int cap = (int)(P.cons_off[cid + 1] - P.cons_off[cid]);
+        for (int v = nxt[0]; v > 1; v = nxt[v]) { if (len < cap) out[len] = W.base[v]; ++len; }
+        if (len > cap) { status |= POA_OVERFLOW; }
+      }
+      if (g.overflow) status |= POA_OVERFLOW;
+      P.cons_len[cid] = len;
+      P.status[cid] = status;
+      atomicAdd(P.cells, cells);
+      PHASE(t_cons);
+      if (P.phase) {
+        atomicAdd(P.phase + 0, (unsigned long long)t_setup); atomicAdd(P.phase + 1, (unsigned long long)t_dp);
+        atomicAdd(P.phase + 2, (unsigned long long)t_tb); atomicAdd(P.phase + 3, (unsigned long long)t_upd);
+        atomicAdd(P.phase + 4, (unsigned long long)t_cons);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+
+}  // namespace svb

@@ -1,0 +1,121 @@
+// Lock-step warp emulator for tests: compiles warp-synchronous CUDA device code (a kernel that only
+// uses 32-lane shuffles with the full mask, __syncwarp, shared memory and global atomics) for the
+// CPU, so that a kernel variant can be checked against the oracle where no GPU is available.
+//
+// One warp = 32 fibers (ucontext) on one OS thread, resumed round-robin.  A warp-wide primitive is a
+// barrier: a lane that reaches it yields until the other 31 have arrived, so lanes interleave only at
+// the points where the hardware would also let them observe each other, and code that lane 0 runs
+// alone between two __syncwarp() calls runs to completion while the others wait, as on the device.
+// Memory is sequentially consistent here, so this checks the algorithm (indexing, tie-breaks, which
+// lane holds what), not fences or races.  Test infrastructure only.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <ucontext.h>
+
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__
+
+struct EmuDim3 { unsigned x, y, z; };
+static EmuDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {32, 1, 1}, gridDim = {1, 1, 1};
+
+namespace emu {
+
+struct Warp {
+  ucontext_t sched;
+  ucontext_t ctx[32];
+  std::vector<char> stack[32];
+  bool done[32];
+  int cur = 0;
+  int arrived = 0;
+  unsigned long generation = 0;
+  uint32_t slots[2][32];
+  void (*body)(void*) = nullptr;
+  void* arg = nullptr;
+};
+static Warp* g_warp = nullptr;
+
+inline void yield_lane() { swapcontext(&g_warp->ctx[g_warp->cur], &g_warp->sched); }
+
+inline void barrier() {
+  Warp* w = g_warp;
+  const unsigned long my = w->generation;
+  if (++w->arrived == 32) { w->arrived = 0; ++w->generation; }
+  else while (w->generation == my) yield_lane();
+}
+
+inline uint32_t exchange(uint32_t v, int src_of_me) {
+  Warp* w = g_warp;
+  const int par = (int)(w->generation & 1);
+  w->slots[par][w->cur] = v;
+  barrier();
+  return w->slots[par][src_of_me & 31];
+}
+
+static void trampoline() {
+  Warp* w = g_warp;
+  w->body(w->arg);
+  w->done[w->cur] = true;
+  swapcontext(&w->ctx[w->cur], &w->sched);
+}
+
+// runs body(arg) on 32 lanes (threadIdx.x = lane) until all have returned; false if the warp deadlocks
+// (some lanes wait at a barrier the others never reach: divergent use of a full-mask primitive)
+inline bool run_warp(void (*body)(void*), void* arg, size_t stack_bytes = 1 << 20) {
+  Warp w;
+  g_warp = &w;
+  w.body = body; w.arg = arg;
+  for (int l = 0; l < 32; ++l) {
+    w.done[l] = false;
+    w.stack[l].resize(stack_bytes);
+    getcontext(&w.ctx[l]);
+    w.ctx[l].uc_stack.ss_sp = w.stack[l].data();
+    w.ctx[l].uc_stack.ss_size = stack_bytes;
+    w.ctx[l].uc_link = &w.sched;
+    makecontext(&w.ctx[l], (void (*)())trampoline, 0);
+  }
+  int live = 32;
+  unsigned long idle_rounds = 0, last_gen = 0;
+  while (live > 0) {
+    int ran = 0;
+    for (int l = 0; l < 32; ++l) {
+      if (w.done[l]) continue;
+      w.cur = l;
+      threadIdx.x = (unsigned)l;
+      swapcontext(&w.sched, &w.ctx[l]);
+      ++ran;
+      if (w.done[l]) --live;
+    }
+    if (w.generation == last_gen && live > 0 && live < 32) { if (++idle_rounds > 4) { g_warp = nullptr; return false; } }
+    else idle_rounds = 0;
+    last_gen = w.generation;
+    (void)ran;
+  }
+  g_warp = nullptr;
+  return true;
+}
+
+}  // namespace emu
+
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { static_assert(sizeof(T) == 4, "32-bit shuffles only"); uint32_t u; __builtin_memcpy(&u, &v, 4); u = emu::exchange(u, src); __builtin_memcpy(&v, &u, 4); return v; }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) { const int lane = emu::g_warp->cur; uint32_t u; __builtin_memcpy(&u, &v, 4); u = emu::exchange(u, lane >= (int)d ? lane - (int)d : lane); __builtin_memcpy(&v, &u, 4); return v; }
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { const int lane = emu::g_warp->cur; uint32_t u; __builtin_memcpy(&u, &v, 4); u = emu::exchange(u, lane + (int)d < 32 ? lane + (int)d : lane); __builtin_memcpy(&v, &u, 4); return v; }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { const int lane = emu::g_warp->cur; uint32_t u; __builtin_memcpy(&u, &v, 4); u = emu::exchange(u, lane ^ m); __builtin_memcpy(&v, &u, 4); return v; }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
+inline unsigned __ballot_sync(unsigned, int pred) { unsigned r = 0; for (int l = 0; l < 32; ++l) r |= (emu::exchange(pred ? 1u : 0u, l) & 1u) << l; return r; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline long long clock64() { return 0; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }

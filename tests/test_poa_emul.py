@@ -1,0 +1,114 @@
+"""CPU: the POA kernel source itself (svdss_b200/csrc/poa_kernel.cuh) compiled for the host with the
+lock-step warp emulator of tests/emul/ -- both variants, k_poa<false> (default) and k_poa<true>
+(SVB_POA_SMEM=1: previous row in shared memory, first predecessor from in1 in the traceback) -- must
+give the banded oracle's consensus, and the same cell count as each other.  This is how a kernel
+variant written without GPU time gets checked before it is ever launched."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from poa_cases import make_cluster
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(HERE, "emul", "poa_emul.cpp")
+    out = os.path.join(HERE, "emul", "_build", "libpoa_emul.so")
+    deps = [src, os.path.join(HERE, "emul", "warp_emul.hpp"), os.path.join(ROOT, "svdss_b200", "csrc", "poa_kernel.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    lib = C.CDLL(out)
+    lib.emul_poa.restype = C.c_int
+    return lib
+
+
+def run(lib, clusters, smem, worst_case=False):
+    seqs = [np.ascontiguousarray(s, np.uint8) for cl in clusters for s in cl]
+    so = np.zeros(len(seqs) + 1, np.int64)
+    so[1:] = np.cumsum([len(s) for s in seqs])
+    cat = np.concatenate(seqs + [np.zeros(1, np.uint8)])
+    co = np.zeros(len(clusters) + 1, np.int64)
+    co[1:] = np.cumsum([len(cl) for cl in clusters])
+    # capacities as svb_poa_batch computes them (pass 0 heuristic / pass 1 worst case)
+    ncap = wcap = 4
+    lmax = 1
+    for cl in clusters:
+        ls = [len(s) for s in cl if len(s)]
+        if not ls:
+            continue
+        lmax = max(lmax, max(ls))
+        w = 10 + int(0.01 * max(ls))
+        if worst_case:
+            nc, wc = sum(ls) + 2, max(ls) + 1
+        else:
+            nc = min(sum(ls) + 2, 2 * max(ls) + 32 * len(ls) + 64)
+            wc = min(max(ls) + 1, 2 * w + 1 + 4 * (max(ls) - min(ls)) + 96)
+        ncap, wcap = max(ncap, nc), max(wcap, wc)
+    wcap = (wcap + 31) & ~31
+    ecap = 3 * ncap + 64
+    cap = np.zeros(len(clusters) + 1, np.int64)
+    cap[1:] = np.cumsum([(2 * max([len(s) for s in cl] + [0]) + 64 + 15) & ~15 for cl in clusters])
+    cons = np.zeros(int(cap[-1]) + 1, np.uint8)
+    clen = np.zeros(len(clusters), np.int32)
+    status = np.zeros(len(clusters), np.int32)
+    cells = C.c_ulonglong(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emul_poa(p(cat), p(so), p(co), len(clusters), int(smem), ncap, ecap, wcap, lmax, p(cons), p(cap), p(clen), p(status), C.byref(cells))
+    assert rc == 0, "emulated warp deadlocked or shared buffer too small (%d)" % rc
+    return [cons[int(cap[i]):int(cap[i]) + int(clen[i])].copy() for i in range(len(clusters))], status, cells.value
+
+
+def clusters_small(seed, n):
+    rng = np.random.default_rng(seed)
+    out = [make_cluster(rng, n_reads=int(rng.integers(2, 9)), tlen=int(rng.integers(30, 160)), rate=0.02)[1] for _ in range(n)]
+    out.append([out[0][0]])                              # single read
+    out.append([])                                       # empty cluster
+    out.append([np.zeros(0, np.uint8), out[1][0], out[1][0]])
+    return out
+
+
+@pytest.mark.parametrize("smem", [0, 1])
+def test_emulated_kernel_equals_banded_oracle(emul, smem):
+    clusters = clusters_small(41, 14)
+    got, status, cells = run(emul, clusters, smem)
+    assert not status.any() and cells > 0
+    for c, reads in enumerate(clusters):
+        exp = oracle.poa_consensus(reads, band=True) if reads else np.zeros(0, np.uint8)
+        assert np.array_equal(got[c], exp), (c, len(got[c]), len(exp))
+
+
+def test_variants_agree_on_wider_rows_and_planted_alleles(emul):
+    """reads long enough for rows of more than one 32-column step, planted indels (multi-predecessor rows,
+    bands that move left and right), an SV allele carried by the majority"""
+    rng = np.random.default_rng(42)
+    clusters = [make_cluster(rng, n_reads=int(rng.integers(4, 8)), tlen=int(rng.integers(250, 420)), rate=0.01)[1] for _ in range(3)]
+    t = rng.integers(0, 4, size=300).astype(np.uint8)
+    alt = np.concatenate([t[:140], rng.integers(0, 4, size=40).astype(np.uint8), t[140:]])
+    clusters.append([alt, t, alt, alt, t, alt])
+    a, sa, ca = run(emul, clusters, 0)
+    b, sb, cb = run(emul, clusters, 1)
+    assert ca == cb and np.array_equal(sa, sb)
+    for c, reads in enumerate(clusters):
+        assert np.array_equal(a[c], b[c]), c
+        assert np.array_equal(b[c], oracle.poa_consensus(reads, band=True)), c
+    assert np.array_equal(b[-1], alt)
+
+
+def test_overflow_status_and_worst_case_rerun(emul):
+    """unrelated reads blow the heuristic node capacity: both variants flag it, and agree with the oracle
+    once run with worst-case capacities (what svb_poa_batch does in its second pass)"""
+    rng = np.random.default_rng(43)
+    reads = [rng.integers(0, 4, size=int(rng.integers(60, 100))).astype(np.uint8) for _ in range(10)]
+    for smem in (0, 1):
+        _, status, _ = run(emul, [reads], smem)
+        got, status2, _ = run(emul, [reads], smem, worst_case=True)
+        assert status2[0] == 0
+        assert np.array_equal(got[0], oracle.poa_consensus(reads, band=True))
