@@ -159,8 +159,34 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       for (int v = 2 + lane; v < N; v += 32) { W.order[W.rank[v]] = v; }
       for (int s = lane; s <= n_ord + 1; s += 32) W.cnt[s] = 0;
       __syncwarp();
-      // remain[]: heaviest out-neighbour chain length to the sink (lane 0, reverse rank order)
-      if (lane == 0) {
+      // remain[]: heaviest out-neighbour chain length to the sink, reverse rank order
+      if (SMEM) {
+        // 32 ranks at a time: every lane finds the heaviest out-neighbour bv of its own node (independent
+        // walks, their latencies overlap), then the recurrence remain[v] = remain[bv] + 1 is resolved inside
+        // the chunk with shuffles -- lanes hold descending ranks, a node's successors have higher ranks, so
+        // lane s is final once lanes < s are.  Two shuffles per node instead of four dependent loads.
+        if (lane == 0) W.remain[1] = 0;
+        __syncwarp();
+        for (int r0 = n_ord - 1; r0 >= -1; r0 -= 32) {
+          const int r = r0 - lane;
+          const bool valid = r >= -1;
+          int v = -1, bv = 1;
+          if (valid) {
+            v = r >= 0 ? W.order[r] : 0;
+            int bw = -1;
+            for (int e = W.first_out[v]; e >= 0; e = W.enout[e])
+              if (W.ew[e] > bw) { bw = W.ew[e]; bv = W.eto[e]; }
+          }
+          int rem = valid ? W.remain[bv] : 0;      // final unless bv sits in this chunk (then replaced below)
+          for (int s = 0; s < 32; ++s) {
+            const int vs = __shfl_sync(0xffffffffu, v, s);
+            const int rs = __shfl_sync(0xffffffffu, rem, s) + 1;   // remain[vs], final at step s
+            if (lane > s && valid && bv == vs) rem = rs;
+          }
+          if (valid) W.remain[v] = rem + 1;
+          __syncwarp();
+        }
+      } else if (lane == 0) {
         W.remain[1] = 0;
         for (int r = n_ord - 1; r >= -1; --r) {
           const int v = r >= 0 ? W.order[r] : 0;
@@ -315,6 +341,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       }
       PHASE(t_dp);
       // ---- end point, traceback, graph update, re-rank: lane 0
+      int n_new_b = 0;
       if (lane == 0) {
         int best_p = -1, best = PNEG - 1;
         for (int e = W.first_in[1]; e >= 0; e = W.enin[e]) {
@@ -390,7 +417,8 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           prev = use;
         }
         if (!g.overflow) g.edge(prev, 1);
-        if (!g.overflow) {
+        n_new_b = n_new;
+        if (!SMEM && !g.overflow) {
           // re-rank: exclusive prefix of cnt over slots (slot 0 = source, r+1 = old rank r)
           int acc = 0;
           for (int s = 0; s <= n_ord; ++s) { const int c_ = W.cnt[s]; W.cnt[s] = acc; acc += c_; }
@@ -402,6 +430,36 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
             // slots range over 0..n_ord <= N-2, so mpl[s] is a valid scratch cell
             W.rank[W.new_id[k]] = (s - 1 + W.cnt[s]) + 1 + W.mpl[s];
             W.mpl[s]++;
+          }
+        }
+      }
+      if (SMEM) {
+        // the same re-rank by the whole warp: exclusive scan of cnt over the slots, old nodes shifted by the
+        // new nodes anchored before them; only the (few) new nodes are placed by lane 0
+        const bool ovf = __shfl_sync(0xffffffffu, (int)g.overflow, 0) != 0;
+        const int n_new = __shfl_sync(0xffffffffu, n_new_b, 0);
+        __syncwarp();
+        if (!ovf) {
+          int carry = 0;
+          for (int s0 = 0; s0 <= n_ord; s0 += 32) {
+            const int s_ = s0 + lane;
+            const int c_ = s_ <= n_ord ? W.cnt[s_] : 0;
+            int inc = c_;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            if (s_ <= n_ord) W.cnt[s_] = carry + inc - c_;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+          }
+          __syncwarp();
+          for (int r = lane; r < n_ord; r += 32) W.rank[W.order[r]] = r + W.cnt[r + 1];
+          __syncwarp();
+          if (lane == 0) {
+            for (int k = 0; k < n_new; ++k) W.mpl[W.new_anchor[k] < N ? W.new_anchor[k] : 0] = 0;
+            for (int k = 0; k < n_new; ++k) {
+              const int s_ = W.new_anchor[k];
+              W.rank[W.new_id[k]] = (s_ - 1 + W.cnt[s_]) + 1 + W.mpl[s_];
+              W.mpl[s_]++;
+            }
           }
         }
       }
