@@ -156,17 +156,28 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
       cudaEvent_t k0, k1;
       PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
       PCHECK(cudaEventRecord(k0, 0));
-      // shared-memory copy of the previous row (k_poa<true>): 2 buffers x 3 arrays x wcap ints per warp; used
-      // when SVB_POA_SMEM=1 and SVB_POA_MINB CTAs of it still fit an SM (else the rows come from the workspace)
+      // kernel variant (poa_kernel.cuh): SVB_POA_VARIANT = bit mask, 0 = the kernel measured in round 1 (default).
+      // Variants with the shared-memory copy of the previous row need 2 buffers x 3 arrays x wcap ints per warp;
+      // when SVB_POA_MINB CTAs of that no longer fit an SM the bit is dropped for this launch.
       const size_t smem = (size_t)4 * 6 * (size_t)wcap * sizeof(int);
-      const char* es = getenv("SVB_POA_SMEM");
-      const bool use_smem = es && atoi(es) != 0 && smem * SVB_POA_MINB <= (size_t)224 * 1024 && smem <= (size_t)200 * 1024;
-      if (use_smem) {
-        PCHECK(cudaFuncSetAttribute(k_poa<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_poa<true><<<(unsigned)(slots / 4), 128, smem>>>(P);
-      } else {
-        k_poa<false><<<(unsigned)(slots / 4), 128>>>(P);
+      const char* ev = getenv("SVB_POA_VARIANT");
+      int variant = ev ? atoi(ev) : 0;
+      if (const char* es = getenv("SVB_POA_SMEM")) if (atoi(es) != 0) variant |= POA_V_SMEM | POA_V_TBIN1 | POA_V_PARN;   // round-1 name of variant 7
+      if ((variant & POA_V_SMEM) && !(smem * SVB_POA_MINB <= (size_t)224 * 1024 && smem <= (size_t)200 * 1024)) variant &= ~POA_V_SMEM;
+      const unsigned grid = (unsigned)(slots / 4);
+#define POA_LAUNCH(VV)                                                                                              \
+  case VV:                                                                                                          \
+    if ((VV) & POA_V_SMEM) {                                                                                        \
+      PCHECK(cudaFuncSetAttribute(k_poa<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+      k_poa<VV><<<grid, 128, smem>>>(P);                                                                            \
+    } else k_poa<VV><<<grid, 128>>>(P);                                                                             \
+    break;
+      switch (variant) {
+        POA_LAUNCH(0) POA_LAUNCH(1) POA_LAUNCH(2) POA_LAUNCH(3) POA_LAUNCH(4) POA_LAUNCH(6) POA_LAUNCH(7)
+        POA_LAUNCH(8) POA_LAUNCH(14) POA_LAUNCH(15)
+        default: set_error("SVB_POA_VARIANT=%d is not built (0 1 2 3 4 6 7 8 14 15)", variant); rc = SVB_EINVAL; goto done;
       }
+#undef POA_LAUNCH
       PCHECK(cudaGetLastError());
       PCHECK(cudaEventRecord(k1, 0));
       PCHECK(cudaEventSynchronize(k1));

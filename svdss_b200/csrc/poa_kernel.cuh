@@ -96,15 +96,32 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
 #ifndef SVB_POA_MINB
 #define SVB_POA_MINB 4
 #endif
-// SMEM: the scores (H, E1, E2) of the row just finished are also kept in shared memory (two buffers per
-// warp, 6 * wcap ints), and a row whose predecessor is that row -- the common case, a chain -- reads them
-// from there instead of from the workspace.  The workspace of all resident warps is far larger than L2
-// (profiles/r01_poa_full.txt: 21 % L2 hit rate, long-scoreboard stalls dominate), so without this every
-// row waits for a DRAM round trip on values the warp itself produced a microsecond earlier.  Results are
-// identical (same values, same order of comparisons); selected by the host when the buffers fit.
-template <bool SMEM>
+// Variants (template bit mask V, SVB_POA_VARIANT on the host; 0 = the kernel measured in round 1).  The
+// workspace of all resident warps is far larger than L2 (profiles/r01_poa_full.txt: 21 % L2 hit rate,
+// long-scoreboard stalls dominate), so every dependent load of a warp's own graph or score rows is a DRAM
+// round trip; each bit removes some of them and none changes a result (same values, same comparisons):
+//  1 SMEM   the scores (H, E1, E2) of the row just finished are also kept in shared memory (two buffers per
+//           warp, 6 * wcap ints); a row whose predecessor is that row -- the common case, a chain -- reads
+//           them from there.  Needs the dynamic shared memory the host sizes from wcap.
+//  2 TBIN1  traceback: the first predecessor comes from in1[v], loaded next to beg[v], instead of through
+//           first_in -> efrom after the traceback word: two dependent loads per step, not four
+//  4 PARN   the two per-read loops over all nodes (remain[], re-rank) are done by the whole warp
+//  8 PREF   graph update: before lane 0 walks a window of 32 alignment ops, all lanes touch the node and
+//           edge fields it is going to read (prefetch.global.L1), so its dependent loads hit L1
+constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8;
+
+__device__ __forceinline__ void poa_prefetch(const void* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+template <int V>
 __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   extern __shared__ int poa_smem[];
+  constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0;
   const int lane = threadIdx.x & 31;
   const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint8_t* wsp = P.ws + (int64_t)slot * P.ws_stride;
@@ -160,7 +177,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       for (int s = lane; s <= n_ord + 1; s += 32) W.cnt[s] = 0;
       __syncwarp();
       // remain[]: heaviest out-neighbour chain length to the sink, reverse rank order
-      if (SMEM) {
+      if (PARN) {
         // 32 ranks at a time: every lane finds the heaviest out-neighbour bv of its own node (independent
         // walks, their latencies overlap), then the recurrence remain[v] = remain[bv] + 1 is resolved inside
         // the chunk with shuffles -- lanes hold descending ranks, a node's successors have higher ranks, so
@@ -341,7 +358,61 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       }
       PHASE(t_dp);
       // ---- end point, traceback, graph update, re-rank: lane 0
-      int n_new_b = 0;
+      int n_new_b = 0, nop_b = 0;
+      // graph update (abpoa_add_graph_alignment), one alignment op at a time in forward order; lane 0's copies
+      // of the state are the ones that count
+      int u_n_new = 0, u_prev = 0, u_anchor = 0;
+      const int n_old = N;
+      auto add_op = [&](int k) -> bool {   // false: capacity overflow, stop
+        if (g.overflow) return false;
+        const int v = W.op_node[k], qi = W.op_q[k];
+        if (v >= 0) {
+          int mr = W.rank[v];
+          for (int u = W.ring[v]; u != v; u = W.ring[u]) if (u < n_old && W.rank[u] > mr) mr = W.rank[u];
+          u_anchor = mr + 1;
+        }
+        if (qi < 0) return true;
+        int use;
+        if (v >= 0) {
+          const uint8_t bq = q[qi];
+          if (W.base[v] == bq) use = v;
+          else {
+            use = -1;
+            for (int u = W.ring[v]; u != v; u = W.ring[u]) if (W.base[u] == bq) { use = u; break; }
+            if (use < 0) {
+              use = g.node(bq);
+              if (g.overflow) return false;
+              W.ring[use] = W.ring[v]; W.ring[v] = use;
+              W.new_anchor[u_n_new] = u_anchor; W.new_id[u_n_new] = use; ++u_n_new; W.cnt[u_anchor]++;
+            }
+          }
+        } else {
+          use = g.node(q[qi]);
+          if (g.overflow) return false;
+          W.new_anchor[u_n_new] = u_anchor; W.new_id[u_n_new] = use; ++u_n_new; W.cnt[u_anchor]++;
+        }
+        g.edge(u_prev, use);
+        u_prev = use;
+        return true;
+      };
+      auto finish_update = [&]() {
+        if (!g.overflow) g.edge(u_prev, 1);
+        n_new_b = u_n_new;
+        if (!PARN && !g.overflow) {
+          // re-rank: exclusive prefix of cnt over slots (slot 0 = source, r+1 = old rank r)
+          int acc = 0;
+          for (int s = 0; s <= n_ord; ++s) { const int c_ = W.cnt[s]; W.cnt[s] = acc; acc += c_; }
+          for (int r = 0; r < n_ord; ++r) W.rank[W.order[r]] = r + W.cnt[r + 1];
+          // new nodes follow their anchor in creation order: reuse mpl[] as the per-slot counter
+          for (int k = 0; k < u_n_new; ++k) W.mpl[W.new_anchor[k] < N ? W.new_anchor[k] : 0] = 0;
+          for (int k = 0; k < u_n_new; ++k) {
+            const int s = W.new_anchor[k];
+            // slots range over 0..n_ord <= N-2, so mpl[s] is a valid scratch cell
+            W.rank[W.new_id[k]] = (s - 1 + W.cnt[s]) + 1 + W.mpl[s];
+            W.mpl[s]++;
+          }
+        }
+      };
       if (lane == 0) {
         int best_p = -1, best = PNEG - 1;
         for (int e = W.first_in[1]; e >= 0; e = W.enin[e]) {
@@ -354,23 +425,22 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           int v = best_p, j = ql, state = 0;  // 0 H, 5 Hp, 1 E1, 2 E2, 3 F1, 4 F2
           while (v != 0 || j > 0) {
             if (v == 0) { W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop; --j; continue; }
-            // SMEM variant: the first predecessor comes from in1[v] (= efrom[first_in[v]] << 1 | more), loaded next
-            // to beg[v] instead of through first_in -> efrom after the traceback word: two dependent loads per step, not four
-            const int in1v = SMEM ? W.in1[v] : 0;
+            // TBIN1: the first predecessor comes from in1[v] (= efrom[first_in[v]] << 1 | more), loaded next to beg[v]
+            const int in1v = TBIN1 ? W.in1[v] : 0;
             const unsigned t = W.TB[(int64_t)v * Wc + j - W.beg[v]];
             if (state == 0) state = (int)(t & 7);
             else if (state == 5) state = (int)((t >> 3) & 3);
             if (state == 0) {
               int ord = (int)((t >> 12) & 0xff);
               W.op_node[nop] = v; W.op_q[nop] = j - 1; ++nop;
-              if (SMEM && ord == 0) v = in1v >> 1;
+              if (TBIN1 && ord == 0) v = in1v >> 1;
               else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
               --j; state = 0;
             } else if (state == 1 || state == 2) {
               int ord = (int)((t >> (state == 1 ? 20 : 26)) & 0x3f);
               const int ext = (int)((t >> (state == 1 ? 5 : 6)) & 1);
               W.op_node[nop] = v; W.op_q[nop] = -1; ++nop;
-              if (SMEM && ord == 0) v = in1v >> 1;
+              if (TBIN1 && ord == 0) v = in1v >> 1;
               else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
               if (!ext) state = 0;
               if (v == 0) state = 0;
@@ -383,57 +453,32 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           }
         }
         PHASE(t_tb);
-        // graph update (abpoa_add_graph_alignment), forward order
-        int n_new = 0, prev = 0, anchor = 0;
-        const int n_old = N;
-        for (int k = nop - 1; k >= 0 && !g.overflow; --k) {
-          const int v = W.op_node[k], qi = W.op_q[k];
-          if (v >= 0) {
-            int mr = W.rank[v];
-            for (int u = W.ring[v]; u != v; u = W.ring[u]) if (u < n_old && W.rank[u] > mr) mr = W.rank[u];
-            anchor = mr + 1;
-          }
-          if (qi < 0) continue;
-          int use;
-          if (v >= 0) {
-            const uint8_t bq = q[qi];
-            if (W.base[v] == bq) use = v;
-            else {
-              use = -1;
-              for (int u = W.ring[v]; u != v; u = W.ring[u]) if (W.base[u] == bq) { use = u; break; }
-              if (use < 0) {
-                use = g.node(bq);
-                if (g.overflow) break;
-                W.ring[use] = W.ring[v]; W.ring[v] = use;
-                W.new_anchor[n_new] = anchor; W.new_id[n_new] = use; ++n_new; W.cnt[anchor]++;
-              }
-            }
-          } else {
-            use = g.node(q[qi]);
-            if (g.overflow) break;
-            W.new_anchor[n_new] = anchor; W.new_id[n_new] = use; ++n_new; W.cnt[anchor]++;
-          }
-          g.edge(prev, use);
-          prev = use;
-        }
-        if (!g.overflow) g.edge(prev, 1);
-        n_new_b = n_new;
-        if (!SMEM && !g.overflow) {
-          // re-rank: exclusive prefix of cnt over slots (slot 0 = source, r+1 = old rank r)
-          int acc = 0;
-          for (int s = 0; s <= n_ord; ++s) { const int c_ = W.cnt[s]; W.cnt[s] = acc; acc += c_; }
-          for (int r = 0; r < n_ord; ++r) W.rank[W.order[r]] = r + W.cnt[r + 1];
-          // new nodes follow their anchor in creation order: reuse mpl[] as the per-slot counter
-          for (int k = 0; k < n_new; ++k) W.mpl[W.new_anchor[k] < N ? W.new_anchor[k] : 0] = 0;
-          for (int k = 0; k < n_new; ++k) {
-            const int s = W.new_anchor[k];
-            // slots range over 0..n_ord <= N-2, so mpl[s] is a valid scratch cell
-            W.rank[W.new_id[k]] = (s - 1 + W.cnt[s]) + 1 + W.mpl[s];
-            W.mpl[s]++;
-          }
+        nop_b = nop;
+        if (!PREF) {
+          for (int k = nop - 1; k >= 0; --k) if (!add_op(k)) break;
+          finish_update();
         }
       }
-      if (SMEM) {
+      if (PREF) {
+        // the same update in windows of 32 ops: first all lanes touch what lane 0 is about to read
+        const int nop_all = __shfl_sync(0xffffffffu, nop_b, 0);
+        for (int k0 = nop_all - 1; k0 >= 0; k0 -= 32) {
+          const int kk = k0 - lane;
+          if (kk >= 0) {
+            const int v = W.op_node[kk];
+            if (v >= 0) {
+              poa_prefetch(&W.rank[v]); poa_prefetch(&W.ring[v]); poa_prefetch(&W.base[v]); poa_prefetch(&W.last_out[v]);
+              const int e = W.first_out[v];
+              if (e >= 0) { poa_prefetch(&W.eto[e]); poa_prefetch(&W.ew[e]); poa_prefetch(&W.enout[e]); }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) for (int k = k0; k > k0 - 32 && k >= 0; --k) if (!add_op(k)) break;
+          __syncwarp();
+        }
+        if (lane == 0) finish_update();
+      }
+      if (PARN) {
         // the same re-rank by the whole warp: exclusive scan of cnt over the slots, old nodes shifted by the
         // new nodes anchored before them; only the (few) new nodes are placed by lane 0
         const bool ovf = __shfl_sync(0xffffffffu, (int)g.overflow, 0) != 0;

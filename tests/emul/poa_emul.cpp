@@ -8,17 +8,22 @@
 
 namespace svb { int poa_smem[1 << 18]; }
 
-struct Launch { svb::PoaParams P; int smem; };
+struct Launch { svb::PoaParams P; int variant; };
 
 static void body(void* a) {
   Launch* l = static_cast<Launch*>(a);
-  if (l->smem) svb::k_poa<true>(l->P); else svb::k_poa<false>(l->P);
+  switch (l->variant) {
+#define CASE(V) case V: svb::k_poa<V>(l->P); break;
+    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(6) CASE(7) CASE(8) CASE(14) CASE(15)
+#undef CASE
+    default: break;
+  }
 }
 
 extern "C" int emul_poa(const uint8_t* seqs, const int64_t* seq_offs, const int64_t* cluster_offs, int n_clusters, int smem,
                         int ncap, int ecap, int wcap, int lmax, uint8_t* cons, const int64_t* cons_off, int32_t* cons_len,
                         int32_t* status, unsigned long long* cells) {
-  if (smem && 6 * (long long)wcap > (long long)(sizeof(svb::poa_smem) / sizeof(int))) return -2;
+  if ((smem & 1) && 6 * (long long)wcap > (long long)(sizeof(svb::poa_smem) / sizeof(int))) return -2;
   const int64_t stride = svb::poa_ws_carve(nullptr, ncap, ecap, wcap, lmax, nullptr);
   std::vector<uint8_t> ws((size_t)stride + 256, 0xA5);   // not zeroed, like a cudaMalloc'ed workspace
   std::vector<uint32_t> order((size_t)n_clusters);
@@ -26,7 +31,7 @@ extern "C" int emul_poa(const uint8_t* seqs, const int64_t* seq_offs, const int6
   unsigned work = 0;
   Launch l;
   memset(&l, 0, sizeof(l));
-  l.smem = smem;
+  l.variant = smem;
   svb::PoaParams& P = l.P;
   P.seqs = seqs; P.seq_offs = seq_offs; P.cluster_offs = cluster_offs; P.order = order.data(); P.n = n_clusters;
   P.work = &work; P.ws = ws.data(); P.ws_stride = stride; P.ncap = ncap; P.ecap = ecap; P.wcap = wcap; P.lmax = lmax;
