@@ -143,6 +143,55 @@ def dist_env():
     return rank, world, local
 
 
+def gpu_numa_cpus(local, torch):
+    """(NUMA node of GPU `local`, the CPUs of that node this process may use), or (None, None)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        if all(hasattr(p, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        else:
+            out = subprocess.check_output(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"], text=True)
+            bdf = out.strip().lower()[-12:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else (None, None)
+    except Exception:
+        return None, None
+
+
+class near_gpu:
+    """Host allocations made inside this block are first touched on the NUMA node the GPU hangs off
+    (the rank's pinned staging buffers: with several ranks per host, copies that cross the socket
+    interconnect share its bandwidth).  The thread's affinity is restored on exit."""
+
+    def __init__(self, local, torch):
+        self.node, self.cpus = gpu_numa_cpus(local, torch)
+        self.saved = None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except Exception:
+                self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
 def build_workload(args, rank, local, torch, capi, synth, need_device_reads=True):
     """Reference on the device, index built on the device, reads materialised on the device."""
     dev = torch.device("cuda", local)
@@ -194,8 +243,10 @@ def run_ours(args):
     # the reference's loader receives from bam_get_seq) and, for comparison, one nt6 byte per base
     total = int(read_offs[-1])
     host_np = None
+    numa = near_gpu(local, torch)
     if world == 1:   # the byte-per-base comparison arm runs on one GPU only (15 GB of pinned memory per rank)
-        host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        with numa:
+            host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
         host.copy_(reads_t[:total])
         host_np = host.numpy()
     l_qseq = np.diff(read_offs).astype(np.int32)
@@ -204,7 +255,8 @@ def run_ours(args):
     s4o_t = torch.from_numpy(seq4_offs).to(dev)
     packed_t = torch.empty(int(seq4_offs[-1]) + 16, dtype=torch.uint8, device=dev)
     capi.pack4_device(reads_t.data_ptr(), offs_t.data_ptr(), s4o_t.data_ptr(), n_reads, packed_t.data_ptr(), device=local)
-    host4 = torch.empty(int(seq4_offs[-1]), dtype=torch.uint8, pin_memory=True)
+    with numa:
+        host4 = torch.empty(int(seq4_offs[-1]), dtype=torch.uint8, pin_memory=True)
     host4.copy_(packed_t[:int(seq4_offs[-1])])
     torch.cuda.synchronize(dev)
     del packed_t, s4o_t
@@ -326,7 +378,8 @@ def run_ours(args):
         "e2e": {"value": world * n_reads / (ms_step_e * 1e-3), "unit": "reads/s",
                 "h2d_bytes_per_step": int(res_e[-1].h2d_bytes), "d2h_bytes_per_step": int(res_e[-1].d2h_bytes),
                 "ms_per_step": ms_step_e, "device_ms_per_step": ms_dev_e / args.steps,
-                "api": "svb_sfs_batch_bam4: pinned host buffer of 4-bit BAM-native reads (bam_get_seq layout), decoded on the GPU"},
+                "api": "svb_sfs_batch_bam4: pinned host buffer of 4-bit BAM-native reads (bam_get_seq layout), decoded on the GPU",
+                "host_buffer_numa_node": numa.node},
         "e2e_nt6_bytes": None if res_b is None else {
             "value": world * n_reads / (ms_wall_b / max(1, args.steps - 1) * 1e-3), "unit": "reads/s",
             "h2d_bytes_per_step": int(res_b[-1].h2d_bytes), "d2h_bytes_per_step": int(res_b[-1].d2h_bytes),
