@@ -174,8 +174,8 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
     break;
       switch (variant) {
         POA_LAUNCH(0) POA_LAUNCH(1) POA_LAUNCH(2) POA_LAUNCH(3) POA_LAUNCH(4) POA_LAUNCH(6) POA_LAUNCH(7)
-        POA_LAUNCH(8) POA_LAUNCH(14) POA_LAUNCH(15)
-        default: set_error("SVB_POA_VARIANT=%d is not built (0 1 2 3 4 6 7 8 14 15)", variant); rc = SVB_EINVAL; goto done;
+        POA_LAUNCH(8) POA_LAUNCH(14) POA_LAUNCH(15) POA_LAUNCH(16) POA_LAUNCH(18) POA_LAUNCH(30) POA_LAUNCH(31)
+        default: set_error("SVB_POA_VARIANT=%d is not built (0 1 2 3 4 6 7 8 14 15 16 18 30 31)", variant); rc = SVB_EINVAL; goto done;
       }
 #undef POA_LAUNCH
       PCHECK(cudaGetLastError());

@@ -108,7 +108,8 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
 //  4 PARN   the two per-read loops over all nodes (remain[], re-rank) are done by the whole warp
 //  8 PREF   graph update: before lane 0 walks a window of 32 alignment ops, all lanes touch the node and
 //           edge fields it is going to read (prefetch.global.L1), so its dependent loads hit L1
-constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8;
+// 16 TBPF   traceback in windows of 32 steps whose traceback words all lanes prefetch along the predicted path
+constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, POA_V_TBPF = 16;
 
 __device__ __forceinline__ void poa_prefetch(const void* p) {
 #ifdef __CUDA_ARCH__
@@ -121,7 +122,8 @@ __device__ __forceinline__ void poa_prefetch(const void* p) {
 template <int V>
 __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   extern __shared__ int poa_smem[];
-  constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0;
+  constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0,
+                 TBPF = (V & POA_V_TBPF) != 0;
   const int lane = threadIdx.x & 31;
   const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint8_t* wsp = P.ws + (int64_t)slot * P.ws_stride;
@@ -413,6 +415,38 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           }
         }
       };
+      // traceback state (lane 0's copies count): position (t_v, t_j), DP state, ops written so far
+      int t_v = 0, t_j = 0, t_state = 0, nop = 0;   // state: 0 H, 5 Hp, 1 E1, 2 E2, 3 F1, 4 F2
+      auto tb_step = [&]() {
+        int v = t_v, j = t_j, state = t_state;
+        if (v == 0) { W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop; t_j = j - 1; return; }
+        // TBIN1: the first predecessor comes from in1[v] (= efrom[first_in[v]] << 1 | more), loaded next to beg[v]
+        const int in1v = TBIN1 ? W.in1[v] : 0;
+        const unsigned t = W.TB[(int64_t)v * Wc + j - W.beg[v]];
+        if (state == 0) state = (int)(t & 7);
+        else if (state == 5) state = (int)((t >> 3) & 3);
+        if (state == 0) {
+          int ord = (int)((t >> 12) & 0xff);
+          W.op_node[nop] = v; W.op_q[nop] = j - 1; ++nop;
+          if (TBIN1 && ord == 0) v = in1v >> 1;
+          else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
+          --j; state = 0;
+        } else if (state == 1 || state == 2) {
+          int ord = (int)((t >> (state == 1 ? 20 : 26)) & 0x3f);
+          const int ext = (int)((t >> (state == 1 ? 5 : 6)) & 1);
+          W.op_node[nop] = v; W.op_q[nop] = -1; ++nop;
+          if (TBIN1 && ord == 0) v = in1v >> 1;
+          else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
+          if (!ext) state = 0;
+          if (v == 0) state = 0;
+        } else {
+          const int ext = (int)((t >> (state == 3 ? 7 : 8)) & 1);
+          W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop;
+          --j;
+          if (!ext) state = 5;
+        }
+        t_v = v; t_j = j; t_state = state;
+      };
       if (lane == 0) {
         int best_p = -1, best = PNEG - 1;
         for (int e = W.first_in[1]; e >= 0; e = W.enin[e]) {
@@ -420,38 +454,34 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           const int val = (ql >= W.beg[p] && ql <= W.end[p]) ? W.H[(int64_t)p * Wc + ql - W.beg[p]] : PNEG;
           if (val > best) { best = val; best_p = p; }
         }
-        int nop = 0;
-        {
-          int v = best_p, j = ql, state = 0;  // 0 H, 5 Hp, 1 E1, 2 E2, 3 F1, 4 F2
-          while (v != 0 || j > 0) {
-            if (v == 0) { W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop; --j; continue; }
-            // TBIN1: the first predecessor comes from in1[v] (= efrom[first_in[v]] << 1 | more), loaded next to beg[v]
-            const int in1v = TBIN1 ? W.in1[v] : 0;
-            const unsigned t = W.TB[(int64_t)v * Wc + j - W.beg[v]];
-            if (state == 0) state = (int)(t & 7);
-            else if (state == 5) state = (int)((t >> 3) & 3);
-            if (state == 0) {
-              int ord = (int)((t >> 12) & 0xff);
-              W.op_node[nop] = v; W.op_q[nop] = j - 1; ++nop;
-              if (TBIN1 && ord == 0) v = in1v >> 1;
-              else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
-              --j; state = 0;
-            } else if (state == 1 || state == 2) {
-              int ord = (int)((t >> (state == 1 ? 20 : 26)) & 0x3f);
-              const int ext = (int)((t >> (state == 1 ? 5 : 6)) & 1);
-              W.op_node[nop] = v; W.op_q[nop] = -1; ++nop;
-              if (TBIN1 && ord == 0) v = in1v >> 1;
-              else { int e = W.first_in[v]; while (ord--) e = W.enin[e]; v = W.efrom[e]; }
-              if (!ext) state = 0;
-              if (v == 0) state = 0;
-            } else {
-              const int ext = (int)((t >> (state == 3 ? 7 : 8)) & 1);
-              W.op_node[nop] = -1; W.op_q[nop] = j - 1; ++nop;
-              --j;
-              if (!ext) state = 5;
+        t_v = best_p; t_j = ql; t_state = 0;
+        if (!TBPF) while (t_v != 0 || t_j > 0) tb_step();
+      }
+      if (TBPF) {
+        // The traceback words were written rows ago and have left the caches: every step of the walk is a DRAM
+        // round trip.  The path mostly runs down a chain of consecutive node ids one column per row, so before
+        // lane 0 walks 32 steps all lanes prefetch the words (and predecessor fields) the path would touch 32..63
+        // steps ahead if it stayed on that diagonal (and 0..31 ahead for the first window).  A wrong guess costs
+        // a wasted prefetch, nothing else.
+        bool first = true;
+        for (;;) {
+          const int cv = __shfl_sync(0xffffffffu, t_v, 0), cj = __shfl_sync(0xffffffffu, t_j, 0);
+          if (cv == 0 && cj <= 0) break;
+          for (int d = first ? lane : 32 + lane; d < 64; d += 32) {
+            const int pv = cv - d, pj = cj - d;
+            if (pv >= 2 && pv < N && pj >= 0) {
+              const int ix = pj - W.beg[pv];
+              if (ix >= 0 && ix < Wc) poa_prefetch(&W.TB[(int64_t)pv * Wc + ix]);
+              poa_prefetch(&W.in1[pv]);
             }
           }
+          first = false;
+          __syncwarp();
+          if (lane == 0) for (int st = 0; st < 32 && (t_v != 0 || t_j > 0); ++st) tb_step();
+          __syncwarp();
         }
+      }
+      if (lane == 0) {
         PHASE(t_tb);
         nop_b = nop;
         if (!PREF) {

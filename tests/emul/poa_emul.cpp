@@ -14,7 +14,7 @@ static void body(void* a) {
   Launch* l = static_cast<Launch*>(a);
   switch (l->variant) {
 #define CASE(V) case V: svb::k_poa<V>(l->P); break;
-    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(6) CASE(7) CASE(8) CASE(14) CASE(15)
+    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(6) CASE(7) CASE(8) CASE(14) CASE(15) CASE(16) CASE(18) CASE(30) CASE(31)
 #undef CASE
     default: break;
   }

@@ -26,7 +26,7 @@ clusters.append([rng.integers(0, 4, size=int(rng.integers(150, 260))).astype(np.
 os.environ["SVB_POA_VARIANT"] = "0"
 a = capi.poa_batch(clusters)
 times = ["0: %.2f" % a.kernel_ms]
-for variant in (1, 3, 7, 15):
+for variant in (1, 3, 7, 15, 31):
     os.environ["SVB_POA_VARIANT"] = str(variant)
     b = capi.poa_batch(clusters)
     assert a.cells == b.cells, (variant, a.cells, b.cells)

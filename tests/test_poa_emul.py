@@ -1,7 +1,7 @@
 """CPU: the POA kernel source itself (svdss_b200/csrc/poa_kernel.cuh) compiled for the host with the
 lock-step warp emulator of tests/emul/ -- the default kernel k_poa<0> and the variants selected by
 SVB_POA_VARIANT (bit 1 previous row in shared memory, 2 first predecessor from in1 in the traceback,
-4 remain[] / re-rank by the whole warp, 8 windowed graph update) -- must give the banded oracle's
+4 remain[] / re-rank by the whole warp, 8 windowed graph update, 16 windowed traceback) -- must give the banded oracle's
 consensus, and the same cell count as each other.  This is how a kernel variant written without GPU
 time gets checked before it is ever launched."""
 import ctypes as C
@@ -76,9 +76,9 @@ def clusters_small(seed, n):
     return out
 
 
-@pytest.mark.parametrize("smem", [0, 1, 2, 4, 8, 15])
+@pytest.mark.parametrize("smem", [0, 1, 2, 4, 8, 16, 31])
 def test_emulated_kernel_equals_banded_oracle(emul, smem):
-    clusters = clusters_small(41, 14 if smem in (0, 15) else 5)
+    clusters = clusters_small(41, 14 if smem in (0, 31) else 5)
     got, status, cells = run(emul, clusters, smem)
     assert not status.any() and cells > 0
     for c, reads in enumerate(clusters):
@@ -95,7 +95,7 @@ def test_variants_agree_on_wider_rows_and_planted_alleles(emul):
     alt = np.concatenate([t[:140], rng.integers(0, 4, size=40).astype(np.uint8), t[140:]])
     clusters.append([alt, t, alt, alt, t, alt])
     a, sa, ca = run(emul, clusters, 0)
-    for variant in (7, 15):
+    for variant in (7, 31):
         b, sb, cb = run(emul, clusters, variant)
         assert ca == cb and np.array_equal(sa, sb)
         for c, reads in enumerate(clusters):
@@ -109,7 +109,7 @@ def test_overflow_status_and_worst_case_rerun(emul):
     once run with worst-case capacities (what svb_poa_batch does in its second pass)"""
     rng = np.random.default_rng(43)
     reads = [rng.integers(0, 4, size=int(rng.integers(60, 100))).astype(np.uint8) for _ in range(10)]
-    for smem in (0, 7, 15):
+    for smem in (0, 31):
         _, status, _ = run(emul, [reads], smem)
         got, status2, _ = run(emul, [reads], smem, worst_case=True)
         assert status2[0] == 0
