@@ -137,11 +137,15 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
       const int64_t stride = poa_ws_carve(nullptr, ncap, (int)ecap, wcap, lmax, nullptr);
       size_t free_b = 0, total_b = 0;
       PCHECK(cudaMemGetInfo(&free_b, &total_b));
-      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * 4 * SVB_POA_MINB);
+      const char* eg = getenv("SVB_POA_GROUP");
+      const int group = eg ? atoi(eg) : 32;
+      if (group != 32 && group != 16 && group != 8) { set_error("SVB_POA_GROUP must be 32, 16 or 8"); rc = SVB_EINVAL; goto done; }
+      const int per_cta = 128 / group;   // clusters in flight per CTA
+      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * per_cta * SVB_POA_MINB);
       const char* eb = getenv("SVB_POA_WS_BYTES");
       const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
       slots = std::min<int64_t>(slots, std::max<int64_t>(1, budget / stride));
-      slots = (slots + 3) / 4 * 4;
+      slots = (slots + per_cta - 1) / per_cta * per_cta;
       if ((int64_t)slots * stride > (int64_t)free_b) { set_error("POA workspace of %lld bytes per cluster does not fit", (long long)stride); rc = SVB_ENOMEM; goto done; }
       cudaFree(d_ws); d_ws = nullptr;
       PCHECK(cudaMalloc((void**)&d_ws, (size_t)slots * stride));
@@ -156,27 +160,31 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
       cudaEvent_t k0, k1;
       PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
       PCHECK(cudaEventRecord(k0, 0));
-      // kernel variant (poa_kernel.cuh): SVB_POA_VARIANT = bit mask, 0 = the kernel measured in round 1 (default).
-      // Variants with the shared-memory copy of the previous row need 2 buffers x 3 arrays x wcap ints per warp;
-      // when SVB_POA_MINB CTAs of that no longer fit an SM the bit is dropped for this launch.
-      const size_t smem = (size_t)4 * 6 * (size_t)wcap * sizeof(int);
+      // kernel variant (poa_kernel.cuh): SVB_POA_VARIANT = bit mask, 0 = the kernel measured in round 1 (default);
+      // SVB_POA_GROUP = lanes per cluster (32 default, 16, 8).  Variants with the shared-memory copy of the
+      // previous row use 2 buffers x 3 arrays x swcap ints per cluster in flight.
       const char* ev = getenv("SVB_POA_VARIANT");
       int variant = ev ? atoi(ev) : 0;
       if (const char* es = getenv("SVB_POA_SMEM")) if (atoi(es) != 0) variant |= POA_V_SMEM | POA_V_TBIN1 | POA_V_PARN;   // round-1 name of variant 7
-      if ((variant & POA_V_SMEM) && !(smem * SVB_POA_MINB <= (size_t)224 * 1024 && smem <= (size_t)200 * 1024)) variant &= ~POA_V_SMEM;
-      const unsigned grid = (unsigned)(slots / 4);
-#define POA_LAUNCH(VV)                                                                                              \
-  case VV:                                                                                                          \
-    if ((VV) & POA_V_SMEM) {                                                                                        \
-      PCHECK(cudaFuncSetAttribute(k_poa<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-      k_poa<VV><<<grid, 128, smem>>>(P);                                                                            \
-    } else k_poa<VV><<<grid, 128>>>(P);                                                                             \
+      P.swcap = std::min(wcap, 128);
+      const size_t smem = (variant & POA_V_SMEM) ? (size_t)(128 / group) * 6 * (size_t)P.swcap * sizeof(int) : 0;
+      const unsigned grid = (unsigned)((slots * group + 127) / 128);
+#define POA_LAUNCH_G(VV, GG)                                                                                        \
+  case (GG) * 100 + (VV):                                                                                           \
+    if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<VV, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_poa<VV, GG><<<grid, 128, smem>>>(P);                                                                          \
     break;
-      switch (variant) {
+#define POA_LAUNCH(VV) POA_LAUNCH_G(VV, 32)
+      switch (group * 100 + variant) {
         POA_LAUNCH(0) POA_LAUNCH(1) POA_LAUNCH(2) POA_LAUNCH(3) POA_LAUNCH(4) POA_LAUNCH(6) POA_LAUNCH(7)
         POA_LAUNCH(8) POA_LAUNCH(14) POA_LAUNCH(15) POA_LAUNCH(16) POA_LAUNCH(18) POA_LAUNCH(30) POA_LAUNCH(31)
-        default: set_error("SVB_POA_VARIANT=%d is not built (0 1 2 3 4 6 7 8 14 15 16 18 30 31)", variant); rc = SVB_EINVAL; goto done;
+        POA_LAUNCH_G(0, 16) POA_LAUNCH_G(7, 16) POA_LAUNCH_G(31, 16) POA_LAUNCH_G(0, 8) POA_LAUNCH_G(7, 8) POA_LAUNCH_G(31, 8)
+        default:
+          set_error("SVB_POA_VARIANT=%d with SVB_POA_GROUP=%d is not built (group 32: 0 1 2 3 4 6 7 8 14 15 16 18 30 31; 16 and 8: 0 7 31)", variant, group);
+          rc = SVB_EINVAL;
+          goto done;
       }
+#undef POA_LAUNCH_G
 #undef POA_LAUNCH
       PCHECK(cudaGetLastError());
       PCHECK(cudaEventRecord(k1, 0));

@@ -21,6 +21,7 @@ struct PoaParams {
   uint8_t* ws;
   int64_t ws_stride;  // bytes per slot
   int ncap, ecap, wcap, lmax;
+  int swcap;          // columns per array of the shared-memory row copy (variants with POA_V_SMEM)
   // outputs
   uint8_t* cons;                   // cons_cap bytes per cluster, at cons_off[cluster]
   const int64_t* __restrict__ cons_off;
@@ -84,10 +85,11 @@ struct Graph {
   }
 };
 
-__device__ __forceinline__ int warp_incl_max(int v, int lane) {
+template <int G>
+__device__ __forceinline__ int warp_incl_max(int v, int lane, unsigned gmask) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int u = __shfl_up_sync(0xffffffffu, v, o);
+  for (int o = 1; o < G; o <<= 1) {
+    const int u = __shfl_up_sync(gmask, v, o, G);
     if (lane >= o) v = max(v, u);
   }
   return v;
@@ -119,13 +121,20 @@ __device__ __forceinline__ void poa_prefetch(const void* p) {
 #endif
 }
 
-template <int V>
+// G = lanes per cluster (32, 16 or 8; SVB_POA_GROUP on the host).  With G < 32 a warp carries 32/G clusters,
+// each on its own group of lanes with its own control flow (group-masked shuffles and __syncwarp): the kernel
+// is bound by the latency of dependent loads at a quarter of the issue rate, a band is 35-60 columns wide, and
+// the sequential walks use one lane -- so more, narrower instruction streams per warp hide more latency with
+// the same registers.  Everything below is written for a "group" of G lanes; `lane` is the lane in the group.
+template <int V, int G = 32>
 __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   extern __shared__ int poa_smem[];
   constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0,
                  TBPF = (V & POA_V_TBPF) != 0;
-  const int lane = threadIdx.x & 31;
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  static_assert(G == 32 || G == 16 || G == 8, "group width");
+  const int lane = threadIdx.x & (G - 1);
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   uint8_t* wsp = P.ws + (int64_t)slot * P.ws_stride;
   Graph g;
   poa_ws_carve(wsp, P.ncap, P.ecap, P.wcap, P.lmax, &g.w);
@@ -133,11 +142,16 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   const PoaWs& W = g.w;
   const int Wc = P.wcap;
   const int mm = P.mismatch < 0 ? -P.mismatch : P.mismatch;
-  int* const sbuf = SMEM ? poa_smem + (threadIdx.x >> 5) * 6 * Wc : nullptr;   // [2 buffers][H, E1, E2][Wc]
+  // shared copy of the row just finished: [2 buffers][H, E1, E2][Ws] per group.  Ws = P.swcap may be smaller than
+  // the workspace row (wcap is a worst-case bound, a band is usually 35-60 columns): a row wider than Ws is simply
+  // not copied and its successor reads the workspace (prev_sm says which).
+  const int Ws = SMEM ? P.swcap : 0;
+  int* const sbuf = SMEM ? poa_smem + (threadIdx.x / G) * 6 * Ws : nullptr;
+  bool prev_sm = false;
   for (;;) {
     unsigned wi = 0;
     if (lane == 0) wi = atomicAdd(P.work, 1u);
-    wi = __shfl_sync(0xffffffffu, wi, 0);
+    wi = __shfl_sync(gmask, wi, 0, G);
     if (wi >= (unsigned)P.n) break;
     const uint32_t cid = P.order[wi];
     const int64_t s0 = P.cluster_offs[cid], s1 = P.cluster_offs[cid + 1];
@@ -148,7 +162,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
 #define PHASE(acc) do { if (P.phase) { const long long _n = clock64(); acc += _n - tc; tc = _n; } } while (0)
     if (lane == 0) { g.node(0); g.node(0); }  // source, sink
     g.n = 2;
-    __syncwarp();
+    __syncwarp(gmask);
     for (int64_t si = s0; si < s1 && !g.overflow; ++si) {
       const uint8_t* q = P.seqs + P.seq_offs[si];
       const int ql = (int)(P.seq_offs[si + 1] - P.seq_offs[si]);
@@ -157,7 +171,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       const int N = g.n;
       if (N == 2) {  // first read: a chain (warp-parallel)
         if (ql + 2 > g.ncap || ql + 1 > g.ecap) { g.overflow = true; break; }
-        for (int j = lane; j < ql; j += 32) {
+        for (int j = lane; j < ql; j += G) {
           const int v = 2 + j;
           W.base[v] = q[j]; W.rank[v] = j; W.ring[v] = v;
           // edge j: (j ? v-1 : source) -> v ; edge ql: last -> sink
@@ -171,13 +185,13 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           W.first_in[1] = W.last_in[1] = ql; W.in1[1] = (2 + ql - 1) << 1;
         }
         g.n = 2 + ql; g.ne = ql + 1;
-        __syncwarp();
+        __syncwarp(gmask);
         continue;
       }
       const int n_ord = N - 2;
-      for (int v = 2 + lane; v < N; v += 32) { W.order[W.rank[v]] = v; }
-      for (int s = lane; s <= n_ord + 1; s += 32) W.cnt[s] = 0;
-      __syncwarp();
+      for (int v = 2 + lane; v < N; v += G) { W.order[W.rank[v]] = v; }
+      for (int s = lane; s <= n_ord + 1; s += G) W.cnt[s] = 0;
+      __syncwarp(gmask);
       // remain[]: heaviest out-neighbour chain length to the sink, reverse rank order
       if (PARN) {
         // 32 ranks at a time: every lane finds the heaviest out-neighbour bv of its own node (independent
@@ -185,8 +199,8 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         // the chunk with shuffles -- lanes hold descending ranks, a node's successors have higher ranks, so
         // lane s is final once lanes < s are.  Two shuffles per node instead of four dependent loads.
         if (lane == 0) W.remain[1] = 0;
-        __syncwarp();
-        for (int r0 = n_ord - 1; r0 >= -1; r0 -= 32) {
+        __syncwarp(gmask);
+        for (int r0 = n_ord - 1; r0 >= -1; r0 -= G) {
           const int r = r0 - lane;
           const bool valid = r >= -1;
           int v = -1, bv = 1;
@@ -197,13 +211,13 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
               if (W.ew[e] > bw) { bw = W.ew[e]; bv = W.eto[e]; }
           }
           int rem = valid ? W.remain[bv] : 0;      // final unless bv sits in this chunk (then replaced below)
-          for (int s = 0; s < 32; ++s) {
-            const int vs = __shfl_sync(0xffffffffu, v, s);
-            const int rs = __shfl_sync(0xffffffffu, rem, s) + 1;   // remain[vs], final at step s
+          for (int s = 0; s < G; ++s) {
+            const int vs = __shfl_sync(gmask, v, s, G);
+            const int rs = __shfl_sync(gmask, rem, s, G) + 1;   // remain[vs], final at step s
             if (lane > s && valid && bv == vs) rem = rs;
           }
           if (valid) W.remain[v] = rem + 1;
-          __syncwarp();
+          __syncwarp(gmask);
         }
       } else if (lane == 0) {
         W.remain[1] = 0;
@@ -215,17 +229,17 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           W.remain[v] = W.remain[bv] + 1;
         }
       }
-      __syncwarp();
+      __syncwarp(gmask);
       const int w = P.wb + (int)(P.wf * (float)ql);
       PHASE(t_setup);
       // ---- source row
       {
         int end0 = min(w, ql);
         if (end0 + 1 > Wc) { end0 = Wc - 1; status |= POA_CLAMPED; }
-        for (int j = lane; j <= end0; j += 32) {
+        for (int j = lane; j <= end0; j += G) {
           const int c1 = P.o1 + j * P.e1, c2 = P.o2 + j * P.e2;
           W.H[j] = j ? -min(c1, c2) : 0; W.E1[j] = PNEG; W.E2[j] = PNEG;
-          if (SMEM) { sbuf[j] = j ? -min(c1, c2) : 0; sbuf[Wc + j] = PNEG; sbuf[2 * Wc + j] = PNEG; }   // buffer 0 = the row before rank 0
+          if (SMEM && end0 < Ws) { sbuf[j] = j ? -min(c1, c2) : 0; sbuf[Ws + j] = PNEG; sbuf[2 * Ws + j] = PNEG; }   // buffer 0 = the row before rank 0
           unsigned t = j ? (c1 <= c2 ? 3u : 4u) : 0u;
           if (j > 1) t |= (c1 <= c2) ? (1u << 7) : (1u << 8);
           W.TB[j] = t;
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         // successors' bands.  A row PULLS the min / max over its in-edges (the same min / max abPOA
         // pushes along out-edges after each row) -- no out-edge walk, no per-read reset of the arrays.
         if (lane == 0) { W.beg[0] = 0; W.end[0] = end0; W.mpl[0] = 1; W.mpr[0] = 1; }
-        __syncwarp();
+        __syncwarp(gmask);
       }
       // ---- graph rows in rank order
       // Row r needs: its node v (rank order), v's fields, its in-edges, the predecessors' bands, their
@@ -245,6 +259,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       int v_next = n_ord > 0 ? W.order[0] : 0;
       int nx_in1 = W.in1[v_next], nx_remain = W.remain[v_next], nx_base = W.base[v_next];
       int v_prev = 0, b_prev = 0, en_prev = W.end[0], l_prev = 1, r_prev = 1;   // the source row
+      prev_sm = SMEM && en_prev < Ws;
       for (int r = 0; r < n_ord; ++r) {
         const int v = v_next, in1 = nx_in1, bv = nx_base;
         const int c = ql - nx_remain + 1;
@@ -270,12 +285,13 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         if (en - b + 1 > Wc) { en = b + Wc - 1; status |= POA_CLAMPED; }
         int* hrow = W.H + (int64_t)v * Wc; int* e1row = W.E1 + (int64_t)v * Wc; int* e2row = W.E2 + (int64_t)v * Wc;
         unsigned* tbrow = W.TB + (int64_t)v * Wc;
-        const int* const sprev = SMEM ? sbuf + (r & 1) * 3 * Wc : nullptr;        // scores of row v_prev
-        int* const scur = SMEM ? sbuf + ((r + 1) & 1) * 3 * Wc : nullptr;
+        const int* const sprev = SMEM ? sbuf + (r & 1) * 3 * Ws : nullptr;        // scores of row v_prev (if prev_sm)
+        int* const scur = SMEM ? sbuf + ((r + 1) & 1) * 3 * Ws : nullptr;
+        const bool cur_sm = SMEM && en - b + 1 <= Ws;
         int carry1 = PNEG, carry2 = PNEG;      // running max of B1/B2 over columns before this segment
         int prevX1 = PNEG, prevB1 = PNEG, prevX2 = PNEG, prevB2 = PNEG;  // column j-1 of lane 0
         int rmax = PNEG - 1, rleft = 0, rright = 0;
-        for (int j0 = b; j0 <= en; j0 += 32) {
+        for (int j0 = b; j0 <= en; j0 += G) {
           const int j = j0 + lane;
           const bool act = j <= en;
           int m = PNEG, x1 = PNEG, x2 = PNEG, pm = 0, p1 = 0, p2 = 0, x1ext = 0, x2ext = 0;
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
             const int* ph = W.H + (int64_t)p * Wc;
             const int* pe1 = W.E1 + (int64_t)p * Wc;
             const int* pe2 = W.E2 + (int64_t)p * Wc;
-            if (SMEM && p == v_prev) { ph = sprev; pe1 = sprev + Wc; pe2 = sprev + 2 * Wc; }
+            if (SMEM && prev_sm && p == v_prev) { ph = sprev; pe1 = sprev + Ws; pe2 = sprev + 2 * Ws; }
             if (act && j >= 1 && j - 1 >= bp && j - 1 <= ep) {
               const int s = (bv >= 4 || qb >= 4) ? 0 : (bv == qb ? P.match : -mm);
               const int cval = ph[j - 1 - bp] + s;
@@ -315,15 +331,15 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           if (x2 > hp) { hp = x2; hps = 2; }
           // F1/F2: exclusive max-plus prefix scan of B(k) = Hp(k) + k*e over the row
           const int B1 = act ? hp + j * P.e1 : PNEG, B2 = act ? hp + j * P.e2 : PNEG;
-          const int inc1 = warp_incl_max(B1, lane), inc2 = warp_incl_max(B2, lane);
-          int ex1 = __shfl_up_sync(0xffffffffu, inc1, 1), ex2 = __shfl_up_sync(0xffffffffu, inc2, 1);
+          const int inc1 = warp_incl_max<G>(B1, lane, gmask), inc2 = warp_incl_max<G>(B2, lane, gmask);
+          int ex1 = __shfl_up_sync(gmask, inc1, 1, G), ex2 = __shfl_up_sync(gmask, inc2, 1, G);
           if (lane == 0) { ex1 = PNEG; ex2 = PNEG; }
           const int X1 = max(carry1, ex1), X2 = max(carry2, ex2);
           int f1 = PNEG, f2 = PNEG;
           if (j > b) { f1 = max(X1 - P.o1 - j * P.e1, PNEG); f2 = max(X2 - P.o2 - j * P.e2, PNEG); }
           // ext flag of column j: F(j-1) > Hp(j-1) - o  <=>  X(j-1) > B(j-1)
-          int pX1 = __shfl_up_sync(0xffffffffu, X1, 1), pB1 = __shfl_up_sync(0xffffffffu, B1, 1);
-          int pX2 = __shfl_up_sync(0xffffffffu, X2, 1), pB2 = __shfl_up_sync(0xffffffffu, B2, 1);
+          int pX1 = __shfl_up_sync(gmask, X1, 1, G), pB1 = __shfl_up_sync(gmask, B1, 1, G);
+          int pX2 = __shfl_up_sync(gmask, X2, 1, G), pB2 = __shfl_up_sync(gmask, B2, 1, G);
           if (lane == 0) { pX1 = prevX1; pB1 = prevB1; pX2 = prevX2; pB2 = prevB2; }
           const int f1ext = (j > b) && (pX1 > pB1), f2ext = (j > b) && (pX2 > pB2);
           int hh = hp; unsigned hs = hps;
@@ -331,32 +347,32 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           if (f2 > hh) { hh = f2; hs = 4; }
           if (act) {
             hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2;
-            if (SMEM) { scur[j - b] = hh; scur[Wc + j - b] = x1; scur[2 * Wc + j - b] = x2; }
+            if (cur_sm) { scur[j - b] = hh; scur[Ws + j - b] = x1; scur[2 * Ws + j - b] = x2; }
             tbrow[j - b] = hs | (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)f1ext << 7) |
                            ((unsigned)f2ext << 8) | ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) |
                            ((unsigned)(p2 & 0x3f) << 26);
             if (hh > rmax) { rmax = hh; rleft = j; rright = j; }
             else if (hh == rmax) rright = j;
           }
-          carry1 = max(carry1, __shfl_sync(0xffffffffu, inc1, 31));
-          carry2 = max(carry2, __shfl_sync(0xffffffffu, inc2, 31));
-          prevX1 = __shfl_sync(0xffffffffu, X1, 31); prevB1 = __shfl_sync(0xffffffffu, B1, 31);
-          prevX2 = __shfl_sync(0xffffffffu, X2, 31); prevB2 = __shfl_sync(0xffffffffu, B2, 31);
+          carry1 = max(carry1, __shfl_sync(gmask, inc1, G - 1, G));
+          carry2 = max(carry2, __shfl_sync(gmask, inc2, G - 1, G));
+          prevX1 = __shfl_sync(gmask, X1, G - 1, G); prevB1 = __shfl_sync(gmask, B1, G - 1, G);
+          prevX2 = __shfl_sync(gmask, X2, G - 1, G); prevB2 = __shfl_sync(gmask, B2, G - 1, G);
         }
         cells += (unsigned long long)(en - b + 1);
         // row maximum, its first and last column (lanes hold strided columns: reduce)
         int gmax = rmax;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        for (int o = G / 2; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(gmask, gmax, o, G));
         int l_ = (rmax == gmax) ? rleft : 0x7fffffff, r_ = (rmax == gmax) ? rright : -1;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          l_ = min(l_, __shfl_xor_sync(0xffffffffu, l_, o));
-          r_ = max(r_, __shfl_xor_sync(0xffffffffu, r_, o));
+        for (int o = G / 2; o; o >>= 1) {
+          l_ = min(l_, __shfl_xor_sync(gmask, l_, o, G));
+          r_ = max(r_, __shfl_xor_sync(gmask, r_, o, G));
         }
         if (lane == 0) { W.beg[v] = b; W.end[v] = en; W.mpl[v] = l_ + 1; W.mpr[v] = r_ + 1; }
-        v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1;
-        __syncwarp();
+        v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1; prev_sm = cur_sm;
+        __syncwarp(gmask);
       }
       PHASE(t_dp);
       // ---- end point, traceback, graph update, re-rank: lane 0
@@ -465,9 +481,9 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         // a wasted prefetch, nothing else.
         bool first = true;
         for (;;) {
-          const int cv = __shfl_sync(0xffffffffu, t_v, 0), cj = __shfl_sync(0xffffffffu, t_j, 0);
+          const int cv = __shfl_sync(gmask, t_v, 0, G), cj = __shfl_sync(gmask, t_j, 0, G);
           if (cv == 0 && cj <= 0) break;
-          for (int d = first ? lane : 32 + lane; d < 64; d += 32) {
+          for (int d = first ? lane : G + lane; d < 2 * G; d += G) {
             const int pv = cv - d, pj = cj - d;
             if (pv >= 2 && pv < N && pj >= 0) {
               const int ix = pj - W.beg[pv];
@@ -476,9 +492,9 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
             }
           }
           first = false;
-          __syncwarp();
-          if (lane == 0) for (int st = 0; st < 32 && (t_v != 0 || t_j > 0); ++st) tb_step();
-          __syncwarp();
+          __syncwarp(gmask);
+          if (lane == 0) for (int st = 0; st < G && (t_v != 0 || t_j > 0); ++st) tb_step();
+          __syncwarp(gmask);
         }
       }
       if (lane == 0) {
@@ -491,8 +507,8 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       }
       if (PREF) {
         // the same update in windows of 32 ops: first all lanes touch what lane 0 is about to read
-        const int nop_all = __shfl_sync(0xffffffffu, nop_b, 0);
-        for (int k0 = nop_all - 1; k0 >= 0; k0 -= 32) {
+        const int nop_all = __shfl_sync(gmask, nop_b, 0, G);
+        for (int k0 = nop_all - 1; k0 >= 0; k0 -= G) {
           const int kk = k0 - lane;
           if (kk >= 0) {
             const int v = W.op_node[kk];
@@ -502,32 +518,32 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
               if (e >= 0) { poa_prefetch(&W.eto[e]); poa_prefetch(&W.ew[e]); poa_prefetch(&W.enout[e]); }
             }
           }
-          __syncwarp();
-          if (lane == 0) for (int k = k0; k > k0 - 32 && k >= 0; --k) if (!add_op(k)) break;
-          __syncwarp();
+          __syncwarp(gmask);
+          if (lane == 0) for (int k = k0; k > k0 - G && k >= 0; --k) if (!add_op(k)) break;
+          __syncwarp(gmask);
         }
         if (lane == 0) finish_update();
       }
       if (PARN) {
         // the same re-rank by the whole warp: exclusive scan of cnt over the slots, old nodes shifted by the
         // new nodes anchored before them; only the (few) new nodes are placed by lane 0
-        const bool ovf = __shfl_sync(0xffffffffu, (int)g.overflow, 0) != 0;
-        const int n_new = __shfl_sync(0xffffffffu, n_new_b, 0);
-        __syncwarp();
+        const bool ovf = __shfl_sync(gmask, (int)g.overflow, 0, G) != 0;
+        const int n_new = __shfl_sync(gmask, n_new_b, 0, G);
+        __syncwarp(gmask);
         if (!ovf) {
           int carry = 0;
-          for (int s0 = 0; s0 <= n_ord; s0 += 32) {
+          for (int s0 = 0; s0 <= n_ord; s0 += G) {
             const int s_ = s0 + lane;
             const int c_ = s_ <= n_ord ? W.cnt[s_] : 0;
             int inc = c_;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            for (int o = 1; o < G; o <<= 1) { const int u = __shfl_up_sync(gmask, inc, o, G); if (lane >= o) inc += u; }
             if (s_ <= n_ord) W.cnt[s_] = carry + inc - c_;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
+            carry += __shfl_sync(gmask, inc, G - 1, G);
           }
-          __syncwarp();
-          for (int r = lane; r < n_ord; r += 32) W.rank[W.order[r]] = r + W.cnt[r + 1];
-          __syncwarp();
+          __syncwarp(gmask);
+          for (int r = lane; r < n_ord; r += G) W.rank[W.order[r]] = r + W.cnt[r + 1];
+          __syncwarp(gmask);
           if (lane == 0) {
             for (int k = 0; k < n_new; ++k) W.mpl[W.new_anchor[k] < N ? W.new_anchor[k] : 0] = 0;
             for (int k = 0; k < n_new; ++k) {
@@ -540,10 +556,10 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       }
       PHASE(t_upd);
       // lane 0's graph size / overflow flag are the truth
-      g.n = __shfl_sync(0xffffffffu, g.n, 0);
-      g.ne = __shfl_sync(0xffffffffu, g.ne, 0);
-      g.overflow = __shfl_sync(0xffffffffu, (int)g.overflow, 0) != 0;
-      __syncwarp();
+      g.n = __shfl_sync(gmask, g.n, 0, G);
+      g.ne = __shfl_sync(gmask, g.ne, 0, G);
+      g.overflow = __shfl_sync(gmask, (int)g.overflow, 0, G) != 0;
+      __syncwarp(gmask);
     }
     // ---- consensus: heaviest bundling (lane 0)
     if (lane == 0) {
@@ -580,7 +596,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         atomicAdd(P.phase + 4, (unsigned long long)t_cons);
       }
     }
-    __syncwarp();
+    __syncwarp(gmask);
   }
 }
 

@@ -2,8 +2,9 @@
 // uses 32-lane shuffles with the full mask, __syncwarp, shared memory and global atomics) for the
 // CPU, so that a kernel variant can be checked against the oracle where no GPU is available.
 //
-// One warp = 32 fibers (ucontext) on one OS thread, resumed round-robin.  A warp-wide primitive is a
-// barrier: a lane that reaches it yields until the other 31 have arrived, so lanes interleave only at
+// One warp = 32 fibers (ucontext) on one OS thread, resumed round-robin.  A warp-wide (or, with a partial
+// mask, group-wide) primitive is a barrier among the lanes of its mask: a lane that reaches it yields until
+// the others have arrived, so lanes interleave only at
 // the points where the hardware would also let them observe each other, and code that lane 0 runs
 // alone between two __syncwarp() calls runs to completion while the others wait, as on the device.
 // Memory is sequentially consistent here, so this checks the algorithm (indexing, tie-breaks, which
@@ -34,8 +35,10 @@ struct Warp {
   std::vector<char> stack[32];
   bool done[32];
   int cur = 0;
-  int arrived = 0;
-  unsigned long generation = 0;
+  // one barrier per group of lanes (a group = the set bits of the mask its members pass; keyed by the
+  // lowest lane of the mask): sub-warp groups with their own control flow synchronise independently
+  int arrived[32];
+  unsigned long generation[32];
   uint32_t slots[2][32];
   void (*body)(void*) = nullptr;
   void* arg = nullptr;
@@ -44,19 +47,22 @@ static Warp* g_warp = nullptr;
 
 inline void yield_lane() { swapcontext(&g_warp->ctx[g_warp->cur], &g_warp->sched); }
 
-inline void barrier() {
+inline void barrier(unsigned mask = 0xffffffffu) {
   Warp* w = g_warp;
-  const unsigned long my = w->generation;
-  if (++w->arrived == 32) { w->arrived = 0; ++w->generation; }
-  else while (w->generation == my) yield_lane();
+  const int key = __builtin_ctz(mask), need = __builtin_popcount(mask);
+  if (!((mask >> w->cur) & 1u)) { fprintf(stderr, "warp_emul: lane %d is not in the mask %08x it passed\n", w->cur, mask); abort(); }
+  const unsigned long my = w->generation[key];
+  if (++w->arrived[key] == need) { w->arrived[key] = 0; ++w->generation[key]; }
+  else while (w->generation[key] == my) yield_lane();
 }
 
-inline uint32_t exchange(uint32_t v, int src_of_me) {
+inline uint32_t exchange(unsigned mask, uint32_t v, int src_lane) {
   Warp* w = g_warp;
-  const int par = (int)(w->generation & 1);
+  const int key = __builtin_ctz(mask);
+  const int par = (int)(w->generation[key] & 1);
   w->slots[par][w->cur] = v;
-  barrier();
-  return w->slots[par][src_of_me & 31];
+  barrier(mask);
+  return w->slots[par][src_lane & 31];
 }
 
 static void trampoline() {
@@ -73,7 +79,7 @@ inline bool run_warp(void (*body)(void*), void* arg, size_t stack_bytes = 1 << 2
   g_warp = &w;
   w.body = body; w.arg = arg;
   for (int l = 0; l < 32; ++l) {
-    w.done[l] = false;
+    w.done[l] = false; w.arrived[l] = 0; w.generation[l] = 0;
     w.stack[l].resize(stack_bytes);
     getcontext(&w.ctx[l]);
     w.ctx[l].uc_stack.ss_sp = w.stack[l].data();
@@ -82,21 +88,22 @@ inline bool run_warp(void (*body)(void*), void* arg, size_t stack_bytes = 1 << 2
     makecontext(&w.ctx[l], (void (*)())trampoline, 0);
   }
   int live = 32;
-  unsigned long idle_rounds = 0, last_gen = 0;
+  unsigned long idle_rounds = 0, last_sum = 0;
   while (live > 0) {
-    int ran = 0;
     for (int l = 0; l < 32; ++l) {
       if (w.done[l]) continue;
       w.cur = l;
       threadIdx.x = (unsigned)l;
       swapcontext(&w.sched, &w.ctx[l]);
-      ++ran;
       if (w.done[l]) --live;
     }
-    if (w.generation == last_gen && live > 0 && live < 32) { if (++idle_rounds > 4) { g_warp = nullptr; return false; } }
+    unsigned long sum = (unsigned long)(32 - live);
+    for (int l = 0; l < 32; ++l) sum += w.generation[l];
+    // a full round in which no barrier completed and no lane finished: the remaining lanes wait for lanes that
+    // will never arrive (divergent use of a masked primitive)
+    if (sum == last_sum && live > 0) { if (++idle_rounds > 4) { g_warp = nullptr; return false; } }
     else idle_rounds = 0;
-    last_gen = w.generation;
-    (void)ran;
+    last_sum = sum;
   }
   g_warp = nullptr;
   return true;
@@ -104,12 +111,16 @@ inline bool run_warp(void (*body)(void*), void* arg, size_t stack_bytes = 1 << 2
 
 }  // namespace emu
 
-template <class T> inline T __shfl_sync(unsigned, T v, int src) { static_assert(sizeof(T) == 4, "32-bit shuffles only"); uint32_t u; __builtin_memcpy(&u, &v, 4); u = emu::exchange(u, src); __builtin_memcpy(&v, &u, 4); return v; }
-template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) { const int lane = emu::g_warp->cur; uint32_t u; __builtin_memcpy(&u, &v, 4); u = emu::exchange(u, lane >= (int)d ? lane - (int)d : lane); __builtin_memcpy(&v, &u, 4); return v; }
-template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d) { const int lane = emu::g_warp->cur; uint32_t u; __builtin_memcpy(&u, &v, 4); u = emu::exchange(u, lane + (int)d < 32 ? lane + (int)d : lane); __builtin_memcpy(&v, &u, 4); return v; }
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { const int lane = emu::g_warp->cur; uint32_t u; __builtin_memcpy(&u, &v, 4); u = emu::exchange(u, lane ^ m); __builtin_memcpy(&v, &u, 4); return v; }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
-inline unsigned __ballot_sync(unsigned, int pred) { unsigned r = 0; for (int l = 0; l < 32; ++l) r |= (emu::exchange(pred ? 1u : 0u, l) & 1u) << l; return r; }
+namespace emu {
+template <class T> inline T xchg(unsigned mask, T v, int src) { static_assert(sizeof(T) == 4, "32-bit shuffles only"); uint32_t u; __builtin_memcpy(&u, &v, 4); u = exchange(mask, u, src); __builtin_memcpy(&v, &u, 4); return v; }
+}
+// `width` as in CUDA: lanes are cut into segments of `width`, source lanes are relative to the caller's segment
+template <class T> inline T __shfl_sync(unsigned m, T v, int src, int width = 32) { const int lane = emu::g_warp->cur; return emu::xchg(m, v, (lane & ~(width - 1)) | (src & (width - 1))); }
+template <class T> inline T __shfl_up_sync(unsigned m, T v, unsigned d, int width = 32) { const int lane = emu::g_warp->cur; return emu::xchg(m, v, (lane & (width - 1)) >= (int)d ? lane - (int)d : lane); }
+template <class T> inline T __shfl_down_sync(unsigned m, T v, unsigned d, int width = 32) { const int lane = emu::g_warp->cur; return emu::xchg(m, v, (lane & (width - 1)) + (int)d < width ? lane + (int)d : lane); }
+template <class T> inline T __shfl_xor_sync(unsigned m, T v, int x, int width = 32) { const int lane = emu::g_warp->cur; const int t = lane ^ x; return emu::xchg(m, v, (t & ~(width - 1)) == (lane & ~(width - 1)) ? t : lane); }
+inline void __syncwarp(unsigned m = 0xffffffffu) { emu::barrier(m); }
+inline unsigned __ballot_sync(unsigned m, int pred) { unsigned r = 0; for (int l = 0; l < 32; ++l) if ((m >> l) & 1u) r |= (emu::exchange(m, pred ? 1u : 0u, l) & 1u) << l; return r; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 inline long long clock64() { return 0; }

@@ -1,5 +1,6 @@
 """GPU: the k_poa variants of SVB_POA_VARIANT (previous row's scores in shared memory, in1 traceback,
-warp-wide remain[] / re-rank, windowed graph update; poa_kernel.cuh) give the same consensus, status
+warp-wide remain[] / re-rank, windowed graph update and traceback) and of SVB_POA_GROUP (16 or 8 lanes per
+cluster, several clusters per warp; poa_kernel.cuh) give the same consensus, status
 and cell count as the default kernel and as the banded oracle.  They are off by default until they
 have been measured, and run in a child process so that a fault in one cannot take the CUDA context
 of the other tests with it."""
@@ -26,15 +27,16 @@ clusters.append([rng.integers(0, 4, size=int(rng.integers(150, 260))).astype(np.
 os.environ["SVB_POA_VARIANT"] = "0"
 a = capi.poa_batch(clusters)
 times = ["0: %.2f" % a.kernel_ms]
-for variant in (1, 3, 7, 15, 31):
+for variant, group in ((1, 32), (3, 32), (7, 32), (15, 32), (31, 32), (0, 16), (7, 16), (31, 16), (0, 8), (7, 8), (31, 8)):
     os.environ["SVB_POA_VARIANT"] = str(variant)
+    os.environ["SVB_POA_GROUP"] = str(group)
     b = capi.poa_batch(clusters)
     assert a.cells == b.cells, (variant, a.cells, b.cells)
     for c, reads in enumerate(clusters):
         assert np.array_equal(a.consensus(c), b.consensus(c)), (variant, c)
         if c % 4 == 0 and reads:
-            assert np.array_equal(b.consensus(c), oracle.poa_consensus(reads, band=True)), (variant, c)
-    times.append("%d: %.2f" % (variant, b.kernel_ms))
+            assert np.array_equal(b.consensus(c), oracle.poa_consensus(reads, band=True)), (variant, group, c)
+    times.append("%d/g%d: %.2f" % (variant, group, b.kernel_ms))
 print("POA_VARIANTS_OK kernel ms by variant  " + "  ".join(times))
 """
 

@@ -31,7 +31,7 @@ def emul():
     return lib
 
 
-def run(lib, clusters, smem, worst_case=False):
+def run(lib, clusters, smem, worst_case=False, group=32, swcap=0):
     seqs = [np.ascontiguousarray(s, np.uint8) for cl in clusters for s in cl]
     so = np.zeros(len(seqs) + 1, np.int64)
     so[1:] = np.cumsum([len(s) for s in seqs])
@@ -62,7 +62,7 @@ def run(lib, clusters, smem, worst_case=False):
     status = np.zeros(len(clusters), np.int32)
     cells = C.c_ulonglong(0)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.emul_poa(p(cat), p(so), p(co), len(clusters), int(smem), ncap, ecap, wcap, lmax, p(cons), p(cap), p(clen), p(status), C.byref(cells))
+    rc = lib.emul_poa(p(cat), p(so), p(co), len(clusters), int(smem), int(group), ncap, ecap, wcap, lmax, int(swcap), p(cons), p(cap), p(clen), p(status), C.byref(cells))
     assert rc == 0, "emulated warp deadlocked or shared buffer too small (%d)" % rc
     return [cons[int(cap[i]):int(cap[i]) + int(clen[i])].copy() for i in range(len(clusters))], status, cells.value
 
@@ -114,3 +114,31 @@ def test_overflow_status_and_worst_case_rerun(emul):
         got, status2, _ = run(emul, [reads], smem, worst_case=True)
         assert status2[0] == 0
         assert np.array_equal(got[0], oracle.poa_consensus(reads, band=True))
+
+
+@pytest.mark.parametrize("group,variant", [(16, 0), (8, 0), (16, 31), (8, 31), (8, 7)])
+def test_sub_warp_groups(emul, group, variant):
+    """G lanes per cluster: 32/G clusters run side by side in one warp, each group with its own control flow
+    (clusters of different sizes, so the groups diverge and finish at different times)"""
+    rng = np.random.default_rng(44)
+    clusters = clusters_small(45, 7)
+    clusters += [make_cluster(rng, n_reads=5, tlen=int(t), rate=0.01)[1] for t in (260, 90, 330)]
+    got, status, cells = run(emul, clusters, variant, group=group)
+    ref, status0, cells0 = run(emul, clusters, 0)
+    assert cells == cells0 and np.array_equal(status, status0)
+    for c, reads in enumerate(clusters):
+        assert np.array_equal(got[c], ref[c]), c
+        exp = oracle.poa_consensus(reads, band=True) if reads else np.zeros(0, np.uint8)
+        assert np.array_equal(got[c], exp), c
+
+
+def test_rows_wider_than_the_shared_copy_fall_back_to_the_workspace(emul):
+    """swcap smaller than most bands: rows alternate between the shared copy and the workspace"""
+    rng = np.random.default_rng(46)
+    clusters = [make_cluster(rng, n_reads=5, tlen=int(t), rate=0.01)[1] for t in (60, 200, 340)]
+    ref, _, cells0 = run(emul, clusters, 0)
+    for swcap in (24, 33):
+        got, status, cells = run(emul, clusters, 31, swcap=swcap)
+        assert cells == cells0 and not status.any()
+        for c in range(len(clusters)):
+            assert np.array_equal(got[c], ref[c]), (swcap, c)
