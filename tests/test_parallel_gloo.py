@@ -60,3 +60,64 @@ def test_two_rank_gather_matches_single_process():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert status == "ok" and n_sfs > 0
+
+
+def _call_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import oracle
+    from poa_cases import make_cluster
+    from svdss_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(53)
+    clusters = [make_cluster(rng, n_reads=int(rng.integers(2, 7)), tlen=int(rng.integers(30, 140)), rate=0.02)[1] for _ in range(13)]
+    clusters.insert(4, [])                                             # an empty cluster keeps its (empty) slot
+    costs = parallel.cluster_cost([len(c) for c in clusters], [max([len(r) for r in c] + [0]) for c in clusters])
+    mine = parallel.shard_clusters_by_cost(costs, world)[rank]
+    # per-rank stand-in for svb_poa_batch + svb_ksw_extd2_batch on CPU: the oracle
+    cons = [oracle.poa_consensus(clusters[c], band=True) if clusters[c] else np.zeros(0, np.uint8) for c in mine]
+    offs = np.zeros(len(mine) + 1, np.int64); offs[1:] = np.cumsum([len(x) for x in cons])
+    got = parallel.gather_ragged(mine, offs, np.concatenate(cons + [np.zeros(0, np.uint8)]), len(clusters), dist, dst=0)
+    cig = [np.array([(l << 4) | "MID".index(op) for l, op in oracle.ksw_extd2(x, clusters[c][0])[1]], np.uint32) if len(x) else np.zeros(0, np.uint32)
+           for c, x in zip(mine, cons)]
+    coffs = np.zeros(len(mine) + 1, np.int64); coffs[1:] = np.cumsum([len(x) for x in cig])
+    got_c = parallel.gather_ragged(mine, coffs, np.concatenate(cig + [np.zeros(0, np.uint32)]), len(clusters), dist, dst=0)
+    if rank == 0:
+        ok = got[1].dtype == np.uint8 and got_c[1].dtype == np.uint32
+        for c, reads in enumerate(clusters):
+            exp = oracle.poa_consensus(reads, band=True) if reads else np.zeros(0, np.uint8)
+            ok &= bool(np.array_equal(got[1][got[0][c]:got[0][c + 1]], exp))
+            if len(exp):
+                ec = [(l << 4) | "MID".index(op) for l, op in oracle.ksw_extd2(exp, reads[0])[1]]
+                ok &= got_c[1][got_c[0][c]:got_c[0][c + 1]].tolist() == ec
+        q.put(("ok" if ok else "mismatch", [len(m) for m in parallel.shard_clusters_by_cost(costs, world)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cluster_sharding_by_cost():
+    from svdss_b200 import parallel
+    costs = parallel.cluster_cost([10, 2, 50, 7, 7, 30], [100, 2000, 300, 400, 400, 100])
+    sh = parallel.shard_clusters_by_cost(costs, 2)
+    assert sorted(np.concatenate(sh).tolist()) == list(range(6))
+    assert sh[0].tolist() == [1, 3, 5] and sh[1].tolist() == [0, 2, 4]      # 8e6 | 4.5e6 | 1.12e6 1.12e6 | 3e5 | 1e5, dealt in turn
+    tot = [costs[s].sum() for s in sh]
+    assert max(tot) / sum(tot) < 0.7
+    assert [len(s) for s in parallel.shard_clusters_by_cost(costs, 8)] == [1, 1, 1, 1, 1, 1, 0, 0]
+
+
+def test_two_rank_call_gather_matches_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 300
+    procs = [ctx.Process(target=_call_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    status, sizes = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert status == "ok" and sizes == [7, 7]
