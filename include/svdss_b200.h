@@ -64,9 +64,13 @@ SVB_API int svb_index_build(const uint8_t* contigs_nt6, const int64_t* offs /* n
 /* Build the block array from a ready BWT (nt6 codes). Test hook for the rank / search kernels. */
 SVB_API int svb_index_from_bwt(const uint8_t* bwt, int64_t n, int mem, int device, int block_bytes,
                                svb_index_t** out);
-/* rb3_fmi_restore(&index, path, 0) (ping_pong.cpp:244-245): load an index file written by
- * svb_index_save into HBM of `device`.  The file layout is private to this library (the reference
- * treats .fmd as opaque between `index` and `search`, run_svdss:137-164). */
+/* rb3_fmi_restore(&index, path, 0) (ping_pong.cpp:244-245): load an index file into HBM of `device`.
+ * Two formats, told apart by their magic: the file svb_index_save writes (layout private to this
+ * library; the reference treats the index as opaque between `index` and `search`, run_svdss:137-164),
+ * and the file the reference's own `index -d` writes -- ropebwt3's FMD ("RLD\3", rld0.c) -- which is
+ * decoded, inverted to the sequences it indexes and re-indexed on the GPU (1-2 minutes of host work
+ * for a human genome; the FMD layout is restated from memory, ropebwt3 not being vendored by the
+ * reference: see svdss_b200/host/rld.hpp). */
 SVB_API int svb_index_load(const char* path, int device, svb_index_t** out);
 SVB_API int svb_index_save(const svb_index_t* idx, const char* path);
 SVB_API void svb_index_free(svb_index_t* idx);

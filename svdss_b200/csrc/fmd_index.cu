@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "../host/rld.hpp"   // ropebwt3 .fmd reader + BWT inversion (host code, header only)
 
 namespace svb {
 
@@ -948,9 +949,44 @@ int svb_index_load(const char* path, int device, svb_index_t** out) {
   FILE* f = fopen(path, "rb");
   if (!f) { set_error("cannot open index %s", path); return SVB_EIO; }
   FileHeader h;
-  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "SVB200I\3", 8) != 0 || (h.G != 4 && h.G != 8)) {
+  memset(&h, 0, sizeof(h));
+  const bool got = fread(&h, sizeof(h), 1, f) == 1;
+  if (memcmp(h.magic, "RLD\3", 4) == 0) {
+    // An index written by the reference itself (`SVDSS index -d` = ropebwt3 build -d): decode the
+    // run-length-delta stream, invert the BWT, keep one strand of every (S, rc S) pair and index that here --
+    // what rb3_fmi_restore(&index, path, 0) at ping_pong.cpp:244-245 is handed.  Host work of 1-2 minutes for
+    // a human genome; `SVDSS index --from-fmd` converts once.  Layout restated from memory (host/rld.hpp).
     fclose(f);
-    set_error("%s is not a svdss_b200 index (ropebwt3 .fmd files are not readable yet)", path);
+    svdss::RldFile rf;
+    std::string err;
+    std::vector<uint8_t> bwt;
+    if (!svdss::Rld::read(path, rf, err) || !svdss::Rld::decode_bwt(rf, bwt, err)) { set_error("%s", err.c_str()); return SVB_EIO; }
+    if (rf.asize != 6) { set_error("%s: alphabet of %d symbols, expected 6 ($ACGTN)", path, rf.asize); return SVB_EINVAL; }
+    rf.words.clear(); rf.words.shrink_to_fit();
+    std::vector<std::string> seqs;
+    {
+      svdss::BwtInverter inv(bwt.data(), bwt.size());
+      if (!inv.sequences(seqs)) { set_error("%s: the BWT does not invert to '$'-terminated sequences", path); return SVB_EINVAL; }
+    }
+    bwt.clear(); bwt.shrink_to_fit();
+    std::vector<size_t> keep;
+    if (!svdss::forward_strands(seqs, keep) || keep.empty()) {
+      set_error("%s: sequences without their reverse complement (ropebwt3 build -R?); the search needs both strands", path);
+      return SVB_EINVAL;
+    }
+    std::vector<uint8_t> cat;
+    std::vector<int64_t> offs(1, 0);
+    for (size_t k : keep) {
+      cat.insert(cat.end(), seqs[k].begin(), seqs[k].end());
+      offs.push_back((int64_t)cat.size());
+      std::string().swap(seqs[k]);
+    }
+    if (cat.empty()) cat.push_back(0);
+    return svb_index_build(cat.data(), offs.data(), (int64_t)offs.size() - 1, SVB_MEM_HOST, device, 0, out);
+  }
+  if (!got || memcmp(h.magic, "SVB200I\3", 8) != 0 || (h.G != 4 && h.G != 8)) {
+    fclose(f);
+    set_error("%s is neither a svdss_b200 index nor a ropebwt3 .fmd (RLD\\3) file", path);
     return SVB_EINVAL;
   }
   svb_index* idx = new svb_index();

@@ -29,14 +29,39 @@
 // counts before that block), ibits = ilog2(n / n_blocks) + 4: the reader's entry points for rank.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 namespace svdss {
+
+// fn(i) for i in [0, n), dealt in chunks to all hardware threads.  std::thread rather than OpenMP so that
+// the same header serves the shell (g++ -fopenmp) and libsvdss_b200 (nvcc host pass, no OpenMP).
+template <class F>
+inline void rld_parallel_for(uint64_t n, uint64_t chunk, F fn) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  const uint64_t n_chunks = (n + chunk - 1) / chunk;
+  if (nt > n_chunks) nt = (unsigned)n_chunks;
+  if (nt <= 1) { for (uint64_t i = 0; i < n; ++i) fn(i); return; }
+  std::atomic<uint64_t> next(0);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        const uint64_t c = next.fetch_add(1);
+        if (c >= n_chunks) return;
+        const uint64_t hi = std::min(n, (c + 1) * chunk);
+        for (uint64_t i = c * chunk; i < hi; ++i) fn(i);
+      }
+    });
+  for (auto& x : th) x.join();
+}
 
 struct RldFile {
   int asize = 6, sbits = 3;
@@ -101,9 +126,8 @@ class Rld {
     const uint64_t n = r.n_symbols();
     if (start[n_blocks] != n) { err = "RLD block counters do not add up to the symbol counts of the header"; return false; }
     bwt.assign((size_t)n, 0);
-    int bad = 0;
-#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : bad)
-    for (long long b = 0; b < (long long)n_blocks; ++b) {
+    std::atomic<int> bad(0);
+    rld_parallel_for((uint64_t)n_blocks, 4096, [&](uint64_t b) {
       const uint64_t o = ((uint64_t)b) << r.sbits;
       uint64_t out = start[(size_t)b];
       const uint64_t out_end = start[(size_t)b + 1];
@@ -119,9 +143,9 @@ class Rld {
         per_code[c] += (uint64_t)l;
       }
       for (int c = 0; ok && c < r.asize; ++c) ok = per_code[c] == header_count(r, o + ssize, c + 1);   // the next block's counters
-      if (!ok) ++bad;
-    }
-    if (bad) { err = "corrupt RLD block (pairs do not match the block counters)"; return false; }
+      if (!ok) bad.fetch_add(1);
+    });
+    if (bad.load()) { err = "corrupt RLD block (pairs do not match the block counters)"; return false; }
     return true;
   }
 
@@ -300,13 +324,12 @@ class BwtInverter {
     const uint64_t nb = (n + STEP - 1) / STEP + 1;
     occ_.assign((size_t)nb * 6, 0);
     // per-block histograms in parallel, then a serial prefix sum over the blocks
-#pragma omp parallel for schedule(static)
-    for (long long b = 0; b < (long long)nb - 1; ++b) {
+    rld_parallel_for(nb - 1, 8192, [&](uint64_t b) {
       uint64_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const uint64_t lo = (uint64_t)b * STEP, hi = std::min(n, lo + STEP);
       for (uint64_t i = lo; i < hi; ++i) ++h[bwt[i] & 7];
       for (int c = 0; c < 6; ++c) occ_[((size_t)b + 1) * 6 + (size_t)c] = h[c];
-    }
+    });
     for (uint64_t b = 1; b < nb; ++b) for (int c = 0; c < 6; ++c) occ_[(size_t)b * 6 + (size_t)c] += occ_[(size_t)(b - 1) * 6 + (size_t)c];
     acc_[0] = 0;
     for (int c = 0; c < 6; ++c) acc_[c + 1] = acc_[c] + occ_[(size_t)(nb - 1) * 6 + (size_t)c];
@@ -322,21 +345,20 @@ class BwtInverter {
   bool sequences(std::vector<std::string>& out) const {
     const uint64_t m = n_sequences();
     out.assign((size_t)m, std::string());
-    int bad = 0;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : bad)
-    for (long long k = 0; k < (long long)m; ++k) {
+    std::atomic<int> bad(0);
+    rld_parallel_for(m, 1, [&](uint64_t k) {
       std::string& s = out[(size_t)k];
       uint64_t i = (uint64_t)k, steps = 0;
       while (true) {
         const int c = bwt_[i];
         if (c == 0) break;
-        if (c > 5 || ++steps > n_) { ++bad; break; }
+        if (c > 5 || ++steps > n_) { bad.fetch_add(1); break; }
         s.push_back((char)c);
         i = acc_[c] + rank(c, i);
       }
       std::reverse(s.begin(), s.end());
-    }
-    return bad == 0;
+    });
+    return bad.load() == 0;
   }
  private:
   static const uint64_t STEP = 128;

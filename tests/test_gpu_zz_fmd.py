@@ -47,3 +47,10 @@ def test_fmd_round_trip_through_the_shell(tmp_path):
         assert r.returncode == 0, r.stderr
         outs.append(r.stdout)
     assert outs[0] and outs[1] == outs[0] and outs[2] == outs[0]
+    # the same through the C ABI: svb_index_load tells the two formats apart by their magic
+    from svdss_b200 import capi
+    a, b = capi.Index.load(idx), capi.Index.load(fmd)
+    assert a.n == b.n == len(bwt)
+    cat, offs = synth.concat(reads)
+    ra, rb = a.sfs_batch(cat, offs, assemble=True), b.sfs_batch(cat, offs, assemble=True)
+    assert ra.n_sfs == rb.n_sfs > 0 and all(ra.per_read(i) == rb.per_read(i) for i in range(len(reads)))
