@@ -31,7 +31,7 @@ def emul():
     return lib
 
 
-def run(lib, clusters, smem, worst_case=False, group=32, swcap=0):
+def run(lib, clusters, smem, worst_case=False, group=32, swcap=0, ncap_limit=None):
     seqs = [np.ascontiguousarray(s, np.uint8) for cl in clusters for s in cl]
     so = np.zeros(len(seqs) + 1, np.int64)
     so[1:] = np.cumsum([len(s) for s in seqs])
@@ -53,6 +53,8 @@ def run(lib, clusters, smem, worst_case=False, group=32, swcap=0):
             nc = min(sum(ls) + 2, 2 * max(ls) + 32 * len(ls) + 64)
             wc = min(max(ls) + 1, 2 * w + 1 + 4 * (max(ls) - min(ls)) + 96)
         ncap, wcap = max(ncap, nc), max(wcap, wc)
+    if ncap_limit:
+        ncap = min(ncap, ncap_limit)
     wcap = (wcap + 31) & ~31
     ecap = 3 * ncap + 64
     cap = np.zeros(len(clusters) + 1, np.int64)
@@ -105,13 +107,16 @@ def test_variants_agree_on_wider_rows_and_planted_alleles(emul):
 
 
 def test_overflow_status_and_worst_case_rerun(emul):
-    """unrelated reads blow the heuristic node capacity: both variants flag it, and agree with the oracle
-    once run with worst-case capacities (what svb_poa_batch does in its second pass)"""
+    """a node capacity too small for one cluster: the kernel flags that cluster (status bit 1) and leaves the
+    clusters next to it alone; with worst-case capacities (svb_poa_batch's second pass) it matches the oracle"""
     rng = np.random.default_rng(43)
     reads = [rng.integers(0, 4, size=int(rng.integers(60, 100))).astype(np.uint8) for _ in range(10)]
-    for smem in (0, 31):
-        _, status, _ = run(emul, [reads], smem)
-        got, status2, _ = run(emul, [reads], smem, worst_case=True)
+    _, ok = make_cluster(rng, n_reads=4, tlen=80)
+    for smem, group in ((0, 32), (31, 32), (31, 8)):
+        got1, status, _ = run(emul, [reads, ok, ok], smem, group=group, ncap_limit=150)   # too few nodes for the first cluster only
+        assert status[0] != 0 and status[1] == 0 and status[2] == 0
+        assert np.array_equal(got1[1], oracle.poa_consensus(ok, band=True)) and np.array_equal(got1[2], got1[1])
+        got, status2, _ = run(emul, [reads], smem, worst_case=True, group=group)
         assert status2[0] == 0
         assert np.array_equal(got[0], oracle.poa_consensus(reads, band=True))
 
