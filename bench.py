@@ -417,20 +417,18 @@ def call_stage_sample(capi, n_clusters=1500, n_pairs=20000):
     """The `call` half of the path on bounded samples of SURVEY 8(d) configs 4 and 5 (they are parity-test
     cases, not the bench line: reported next to it so that one run shows both halves).  POA: clusters of
     20-60 reads x 200-2000 bp; ksw2: consensus x window pairs up to 3 kb (the pipeline's range)."""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import bench_call
+    from svdss_b200 import synth
     rng = np.random.default_rng(6)
-    cl = bench_call.gen_clusters(rng, n_clusters)
+    cl = synth.gen_clusters(rng, n_clusters)
     capi.poa_batch(cl[:64])
     r = capi.poa_batch(cl)
     out = {"poa": {"clusters": len(cl), "reads": int(sum(len(c) for c in cl)), "kernel_ms": float(r.kernel_ms), "device_ms": float(r.device_ms),
                    "clusters_per_s": len(cl) / (r.device_ms * 1e-3), "GCUPS": r.cells / (r.kernel_ms * 1e-3) / 1e9, "launches": int(r.launches),
                    "variant": int(os.environ.get("SVB_POA_VARIANT", "0")), "lanes_per_cluster": int(os.environ.get("SVB_POA_GROUP", "32")),
                    "api": "svb_poa_batch (host buffers; H2D + kernel + D2H in device_ms)"}}
-    import oracle
-    pr = bench_call.gen_pairs(rng, n_pairs, hi=3000)
-    qc, qo = oracle.concat([p[0] for p in pr])
-    tc, to = oracle.concat([p[1] for p in pr])
+    pr = synth.gen_pairs(rng, n_pairs, hi=3000)
+    qc, qo = synth.concat([p[0] for p in pr])
+    tc, to = synth.concat([p[1] for p in pr])
     capi.ksw_extd2_batch(qc[:qo[64]], qo[:65], tc[:to[64]], to[:65])
     k = capi.ksw_extd2_batch(qc, qo, tc, to)
     out["ksw2"] = {"pairs": len(pr), "kernel_ms": float(k.kernel_ms), "device_ms": float(k.device_ms), "pairs_per_s": len(pr) / (k.device_ms * 1e-3),

@@ -8,40 +8,7 @@ import oracle
 from svdss_b200 import build, capi
 
 
-def gen_clusters(rng, n, lo=200, hi=2000):
-    out = []
-    for _ in range(n):
-        tlen = int(np.exp(rng.uniform(np.log(lo), np.log(hi))))
-        nr = int(rng.integers(20, 61))
-        tpl = rng.integers(0, 4, size=tlen).astype(np.uint8)
-        reads = []
-        for _r in range(nr):
-            r = tpl.copy()
-            m = rng.random(tlen) < 0.001
-            r[m] = (r[m] + rng.integers(1, 4, size=int(m.sum()))) % 4
-            if rng.random() < 0.5:
-                L = int(rng.integers(1, max(2, int(tlen * 0.03))))
-                p = int(rng.integers(1, max(2, tlen - L - 1)))
-                r = np.concatenate([r[:p], rng.integers(0, 4, size=L).astype(np.uint8), r[p:]]) if rng.random() < 0.5 \
-                    else np.concatenate([r[:p], r[p + L:]])
-            reads.append(r)
-        out.append(reads)
-    return out
-
-
-def gen_pairs(rng, n, lo=100, hi=10000):
-    out = []
-    for _ in range(n):
-        tl = int(np.exp(rng.uniform(np.log(lo), np.log(hi))))
-        t = rng.integers(0, 4, size=tl).astype(np.uint8)
-        L = int(min(rng.integers(50, 1001), max(1, tl // 2)))
-        p = int(rng.integers(1, max(2, tl - L - 1)))
-        q = np.concatenate([t[:p], rng.integers(0, 4, size=L).astype(np.uint8), t[p:]]) if rng.random() < 0.5 \
-            else np.concatenate([t[:p], t[p + L:]])
-        m = rng.random(len(q)) < 0.002
-        q[m] = (q[m] + rng.integers(1, 4, size=int(m.sum()))) % 4
-        out.append((q, t))
-    return out
+from svdss_b200.synth import gen_clusters, gen_pairs  # noqa: E402  (SURVEY 8d config 4 / 5 shapes)
 
 
 def main():
