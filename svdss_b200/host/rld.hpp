@@ -33,6 +33,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -98,6 +99,13 @@ class Rld {
       r.asize = (int)(a >> 16); r.sbits = (int)(a & 0xffff);
       ok = r.asize >= 1 && r.asize <= 15 && r.sbits >= 3 && r.sbits <= 16 && n_words < ((uint64_t)1 << 40) && r.n_frames < ((uint64_t)1 << 40);
     }
+    if (ok) {   // the sizes the header announces must fit the file (checked before anything is allocated)
+      const long at = ftell(f);
+      ok = at >= 0 && fseek(f, 0, SEEK_END) == 0;
+      const long fsize = ok ? ftell(f) : -1;
+      ok = ok && fsize >= 0 && fseek(f, at, SEEK_SET) == 0 &&
+           (unsigned long long)fsize >= 24ull + 8ull * (unsigned)r.asize + 8ull * n_words + 8ull * r.n_frames * (unsigned)(r.asize + 1);
+    }
     if (ok) {
       r.mcnt.resize((size_t)r.asize);
       ok = fread(r.mcnt.data(), 8, (size_t)r.asize, f) == (size_t)r.asize;
@@ -125,7 +133,8 @@ class Rld {
     for (size_t b = 0; b < n_blocks; ++b) start[b + 1] = start[b] + header_total(r.words[(size_t)(((uint64_t)b + 1) << r.sbits)]);
     const uint64_t n = r.n_symbols();
     if (start[n_blocks] != n) { err = "RLD block counters do not add up to the symbol counts of the header"; return false; }
-    bwt.assign((size_t)n, 0);
+    if (n > ((uint64_t)1 << 40)) { err = "RLD header announces more than 2^40 symbols"; return false; }
+    try { bwt.assign((size_t)n, 0); } catch (const std::bad_alloc&) { err = "not enough host memory for a BWT of " + std::to_string(n) + " symbols"; return false; }
     std::atomic<int> bad(0);
     rld_parallel_for((uint64_t)n_blocks, 4096, [&](uint64_t b) {
       const uint64_t o = ((uint64_t)b) << r.sbits;
