@@ -14,6 +14,7 @@
 // short sequential walks done by lane 0.  Integer SIMT: a max-plus recurrence over a DAG with
 // data-dependent band and predecessors is not a dense contraction, so no tensor cores.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -112,93 +113,122 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
     float kms = 0.f;
     for (int pass = 0; pass < 2 && !todo.empty(); ++pass) {
       std::stable_sort(todo.begin(), todo.end(), [&](uint32_t a, uint32_t b) { return shp[a].cost > shp[b].cost; });
-      int ncap = 0, wcap = 0, lmax = 1;
-      int64_t ecap = 0;
-      for (uint32_t c : todo) {
-        const Shape& s = shp[c];
-        if (!s.nreads) continue;
-        lmax = std::max(lmax, s.lmax);
-        const int w = 10 + (int)(0.01 * s.lmax);
-        const int diff = s.lmax - s.lmin;
-        int64_t nc, wc;
-        if (pass == 0) {
-          nc = std::min<int64_t>(s.sum + 2, 2 * (int64_t)s.lmax + 32 * s.nreads + 64);
-          wc = std::min<int64_t>(s.lmax + 1, 2 * w + 1 + 4 * diff + 96);
-        } else {
-          nc = s.sum + 2;
-          wc = s.lmax + 1;
+      // One launch sizes every workspace slot for its largest cluster.  SVB_POA_BUCKETS=K (default 1) cuts the
+      // clusters of a pass into up to K launches by footprint (nodes x band columns, geometric thresholds), so
+      // that small clusters get small slots: more of them fit the workspace budget (what narrow groups need)
+      // and a warp's rows lie closer together.  Results do not depend on it.
+      std::vector<std::vector<uint32_t>> parts;
+      {
+        const char* ek = getenv("SVB_POA_BUCKETS");
+        const int K = std::max(1, std::min(16, ek ? atoi(ek) : 1));
+        auto foot = [&](uint32_t c) {
+          const Shape& s = shp[c];
+          if (!s.nreads) return 1.0;
+          const int w = 10 + (int)(0.01 * s.lmax);
+          const double nc = pass == 0 ? (double)std::min<int64_t>(s.sum + 2, 2 * (int64_t)s.lmax + 32 * s.nreads + 64) : (double)(s.sum + 2);
+          const double wc = pass == 0 ? (double)std::min<int64_t>(s.lmax + 1, 2 * w + 1 + 4 * (s.lmax - s.lmin) + 96) : (double)(s.lmax + 1);
+          return nc * wc;
+        };
+        double fmax = 1.0, fmin = 1e300;
+        for (uint32_t c : todo) { const double f = foot(c); fmax = std::max(fmax, f); fmin = std::min(fmin, f); }
+        const double ratio = K > 1 && fmax > fmin ? pow(fmax / fmin, 1.0 / K) : 0.0;
+        parts.assign((size_t)K, std::vector<uint32_t>());
+        for (uint32_t c : todo) {   // todo is cost-sorted; every part keeps that order
+          int b = 0;
+          if (ratio > 1.0) b = std::min(K - 1, (int)(log(fmax / foot(c)) / log(ratio)));
+          parts[(size_t)b].push_back(c);
         }
-        ncap = (int)std::max<int64_t>(ncap, nc);
-        wcap = (int)std::max<int64_t>(wcap, wc);
       }
-      if (ncap == 0) { ncap = 4; wcap = 4; }
-      wcap = (wcap + 31) & ~31;
-      ecap = 3 * (int64_t)ncap + 64;
-      const int64_t stride = poa_ws_carve(nullptr, ncap, (int)ecap, wcap, lmax, nullptr);
-      size_t free_b = 0, total_b = 0;
-      PCHECK(cudaMemGetInfo(&free_b, &total_b));
-      const char* eg = getenv("SVB_POA_GROUP");
-      const int group = eg ? atoi(eg) : 32;
-      if (group != 32 && group != 16 && group != 8) { set_error("SVB_POA_GROUP must be 32, 16 or 8"); rc = SVB_EINVAL; goto done; }
-      const int per_cta = 128 / group;   // clusters in flight per CTA
-      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * per_cta * SVB_POA_MINB);
-      const char* eb = getenv("SVB_POA_WS_BYTES");
-      const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
-      slots = std::min<int64_t>(slots, std::max<int64_t>(1, budget / stride));
-      slots = (slots + per_cta - 1) / per_cta * per_cta;
-      if ((int64_t)slots * stride > (int64_t)free_b) { set_error("POA workspace of %lld bytes per cluster does not fit", (long long)stride); rc = SVB_ENOMEM; goto done; }
-      cudaFree(d_ws); d_ws = nullptr;
-      PCHECK(cudaMalloc((void**)&d_ws, (size_t)slots * stride));
-      PCHECK(cudaMemcpy(d_order, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice));
-      PCHECK(cudaMemset(d_work, 0, 4));
-      PoaParams P;
-      memset(&P, 0, sizeof(P));
-      P.seqs = d_seqs; P.seq_offs = d_soff; P.cluster_offs = d_coff; P.order = d_order; P.n = (int)todo.size();
-      P.work = d_work; P.ws = d_ws; P.ws_stride = stride; P.ncap = ncap; P.ecap = (int)ecap; P.wcap = wcap; P.lmax = lmax;
-      P.cons = d_cons; P.cons_off = d_capoff; P.cons_len = d_len; P.status = d_status; P.cells = d_cells; P.phase = d_phase;
-      P.match = 2; P.mismatch = 4; P.o1 = 4; P.e1 = 2; P.o2 = 24; P.e2 = 1; P.wb = 10; P.wf = 0.01f;  // abpoa_init_para
-      cudaEvent_t k0, k1;
-      PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
-      PCHECK(cudaEventRecord(k0, 0));
-      // kernel variant (poa_kernel.cuh): SVB_POA_VARIANT = bit mask, 0 = the kernel measured in round 1 (default);
-      // SVB_POA_GROUP = lanes per cluster (32 default, 16, 8).  Variants with the shared-memory copy of the
-      // previous row use 2 buffers x 3 arrays x swcap ints per cluster in flight.
-      const char* ev = getenv("SVB_POA_VARIANT");
-      int variant = ev ? atoi(ev) : 0;
-      if (const char* es = getenv("SVB_POA_SMEM")) if (atoi(es) != 0) variant |= POA_V_SMEM | POA_V_TBIN1 | POA_V_PARN;   // round-1 name of variant 7
-      P.swcap = std::min(wcap, 128);
-      const size_t smem = (variant & POA_V_SMEM) ? (size_t)(128 / group) * 6 * (size_t)P.swcap * sizeof(int) : 0;
-      const unsigned grid = (unsigned)((slots * group + 127) / 128);
-#define POA_LAUNCH_G(VV, GG)                                                                                        \
-  case (GG) * 100 + (VV):                                                                                           \
-    if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<VV, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_poa<VV, GG><<<grid, 128, smem>>>(P);                                                                          \
-    break;
-#define POA_LAUNCH(VV) POA_LAUNCH_G(VV, 32)
-      switch (group * 100 + variant) {
-        POA_LAUNCH(0) POA_LAUNCH(1) POA_LAUNCH(2) POA_LAUNCH(3) POA_LAUNCH(4) POA_LAUNCH(6) POA_LAUNCH(7)
-        POA_LAUNCH(8) POA_LAUNCH(14) POA_LAUNCH(15) POA_LAUNCH(16) POA_LAUNCH(18) POA_LAUNCH(30) POA_LAUNCH(31)
-        POA_LAUNCH_G(0, 16) POA_LAUNCH_G(7, 16) POA_LAUNCH_G(31, 16) POA_LAUNCH_G(0, 8) POA_LAUNCH_G(7, 8) POA_LAUNCH_G(31, 8)
-        default:
-          set_error("SVB_POA_VARIANT=%d with SVB_POA_GROUP=%d is not built (group 32: 0 1 2 3 4 6 7 8 14 15 16 18 30 31; 16 and 8: 0 7 31)", variant, group);
-          rc = SVB_EINVAL;
-          goto done;
-      }
-#undef POA_LAUNCH_G
-#undef POA_LAUNCH
-      PCHECK(cudaGetLastError());
-      PCHECK(cudaEventRecord(k1, 0));
-      PCHECK(cudaEventSynchronize(k1));
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, k0, k1);
-      cudaEventDestroy(k0); cudaEventDestroy(k1);
-      kms += ms;
-      out->launches += 1;
-      PCHECK(cudaMemcpy(h_status.data(), d_status, n_clusters * 4, cudaMemcpyDeviceToHost));
       std::vector<uint32_t> again;
-      for (uint32_t c : todo) {
-        // clamped band (pass 0 only) or capacity overflow: redo with worst-case capacities
-        if ((h_status[c] & POA_OVERFLOW) || (pass == 0 && (h_status[c] & POA_CLAMPED))) again.push_back(c);
+      for (const std::vector<uint32_t>& part : parts) {
+        if (part.empty()) continue;
+        int ncap = 0, wcap = 0, lmax = 1;
+        int64_t ecap = 0;
+        for (uint32_t c : part) {
+          const Shape& s = shp[c];
+          if (!s.nreads) continue;
+          lmax = std::max(lmax, s.lmax);
+          const int w = 10 + (int)(0.01 * s.lmax);
+          const int diff = s.lmax - s.lmin;
+          int64_t nc, wc;
+          if (pass == 0) {
+            nc = std::min<int64_t>(s.sum + 2, 2 * (int64_t)s.lmax + 32 * s.nreads + 64);
+            wc = std::min<int64_t>(s.lmax + 1, 2 * w + 1 + 4 * diff + 96);
+          } else {
+            nc = s.sum + 2;
+            wc = s.lmax + 1;
+          }
+          ncap = (int)std::max<int64_t>(ncap, nc);
+          wcap = (int)std::max<int64_t>(wcap, wc);
+        }
+        if (ncap == 0) { ncap = 4; wcap = 4; }
+        wcap = (wcap + 31) & ~31;
+        ecap = 3 * (int64_t)ncap + 64;
+        const int64_t stride = poa_ws_carve(nullptr, ncap, (int)ecap, wcap, lmax, nullptr);
+        size_t free_b = 0, total_b = 0;
+        PCHECK(cudaMemGetInfo(&free_b, &total_b));
+        const char* eg = getenv("SVB_POA_GROUP");
+        const int group = eg ? atoi(eg) : 32;
+        if (group != 32 && group != 16 && group != 8) { set_error("SVB_POA_GROUP must be 32, 16 or 8"); rc = SVB_EINVAL; goto done; }
+        const int per_cta = 128 / group;   // clusters in flight per CTA
+        int64_t slots = std::min<int64_t>((int64_t)part.size(), (int64_t)sms * per_cta * SVB_POA_MINB);
+        const char* eb = getenv("SVB_POA_WS_BYTES");
+        const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
+        slots = std::min<int64_t>(slots, std::max<int64_t>(1, budget / stride));
+        slots = (slots + per_cta - 1) / per_cta * per_cta;
+        if ((int64_t)slots * stride > (int64_t)free_b) { set_error("POA workspace of %lld bytes per cluster does not fit", (long long)stride); rc = SVB_ENOMEM; goto done; }
+        cudaFree(d_ws); d_ws = nullptr;
+        PCHECK(cudaMalloc((void**)&d_ws, (size_t)slots * stride));
+        PCHECK(cudaMemcpy(d_order, part.data(), part.size() * 4, cudaMemcpyHostToDevice));
+        PCHECK(cudaMemset(d_work, 0, 4));
+        PoaParams P;
+        memset(&P, 0, sizeof(P));
+        P.seqs = d_seqs; P.seq_offs = d_soff; P.cluster_offs = d_coff; P.order = d_order; P.n = (int)part.size();
+        P.work = d_work; P.ws = d_ws; P.ws_stride = stride; P.ncap = ncap; P.ecap = (int)ecap; P.wcap = wcap; P.lmax = lmax;
+        P.cons = d_cons; P.cons_off = d_capoff; P.cons_len = d_len; P.status = d_status; P.cells = d_cells; P.phase = d_phase;
+        P.match = 2; P.mismatch = 4; P.o1 = 4; P.e1 = 2; P.o2 = 24; P.e2 = 1; P.wb = 10; P.wf = 0.01f;  // abpoa_init_para
+        cudaEvent_t k0, k1;
+        PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
+        PCHECK(cudaEventRecord(k0, 0));
+        // kernel variant (poa_kernel.cuh): SVB_POA_VARIANT = bit mask, 0 = the kernel measured in round 1 (default);
+        // SVB_POA_GROUP = lanes per cluster (32 default, 16, 8).  Variants with the shared-memory copy of the
+        // previous row use 2 buffers x 3 arrays x swcap ints per cluster in flight.
+        const char* ev = getenv("SVB_POA_VARIANT");
+        int variant = ev ? atoi(ev) : 0;
+        if (const char* es = getenv("SVB_POA_SMEM")) if (atoi(es) != 0) variant |= POA_V_SMEM | POA_V_TBIN1 | POA_V_PARN;   // round-1 name of variant 7
+        P.swcap = std::min(wcap, 128);
+        const size_t smem = (variant & POA_V_SMEM) ? (size_t)(128 / group) * 6 * (size_t)P.swcap * sizeof(int) : 0;
+        const unsigned grid = (unsigned)((slots * group + 127) / 128);
+  #define POA_LAUNCH_G(VV, GG)                                                                                        \
+    case (GG) * 100 + (VV):                                                                                           \
+      if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<VV, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_poa<VV, GG><<<grid, 128, smem>>>(P);                                                                          \
+      break;
+  #define POA_LAUNCH(VV) POA_LAUNCH_G(VV, 32)
+        switch (group * 100 + variant) {
+          POA_LAUNCH(0) POA_LAUNCH(1) POA_LAUNCH(2) POA_LAUNCH(3) POA_LAUNCH(4) POA_LAUNCH(6) POA_LAUNCH(7)
+          POA_LAUNCH(8) POA_LAUNCH(14) POA_LAUNCH(15) POA_LAUNCH(16) POA_LAUNCH(18) POA_LAUNCH(30) POA_LAUNCH(31)
+          POA_LAUNCH_G(0, 16) POA_LAUNCH_G(7, 16) POA_LAUNCH_G(31, 16) POA_LAUNCH_G(0, 8) POA_LAUNCH_G(7, 8) POA_LAUNCH_G(31, 8)
+          default:
+            set_error("SVB_POA_VARIANT=%d with SVB_POA_GROUP=%d is not built (group 32: 0 1 2 3 4 6 7 8 14 15 16 18 30 31; 16 and 8: 0 7 31)", variant, group);
+            rc = SVB_EINVAL;
+            goto done;
+        }
+  #undef POA_LAUNCH_G
+  #undef POA_LAUNCH
+        PCHECK(cudaGetLastError());
+        PCHECK(cudaEventRecord(k1, 0));
+        PCHECK(cudaEventSynchronize(k1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, k0, k1);
+        cudaEventDestroy(k0); cudaEventDestroy(k1);
+        kms += ms;
+        out->launches += 1;
+        PCHECK(cudaMemcpy(h_status.data(), d_status, n_clusters * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t c : part) {
+          // clamped band (pass 0 only) or capacity overflow: redo with worst-case capacities
+          if ((h_status[c] & POA_OVERFLOW) || (pass == 0 && (h_status[c] & POA_CLAMPED))) again.push_back(c);
+        }
       }
       if (pass == 1 && !again.empty()) { set_error("POA workspace overflow persisted for %zu clusters", again.size()); rc = SVB_ERANGE; goto done; }
       todo.swap(again);

@@ -37,6 +37,14 @@ for variant, group in ((1, 32), (3, 32), (7, 32), (15, 32), (31, 32), (0, 16), (
         if c % 4 == 0 and reads:
             assert np.array_equal(b.consensus(c), oracle.poa_consensus(reads, band=True)), (variant, group, c)
     times.append("%d/g%d: %.2f" % (variant, group, b.kernel_ms))
+os.environ["SVB_POA_BUCKETS"] = "5"                                   # several launches per pass: same results
+for variant, group in ((0, 32), (31, 8)):
+    os.environ["SVB_POA_VARIANT"] = str(variant)
+    os.environ["SVB_POA_GROUP"] = str(group)
+    b = capi.poa_batch(clusters)
+    assert a.cells == b.cells and b.launches > a.launches, (variant, group, a.launches, b.launches)
+    for c in range(len(clusters)):
+        assert np.array_equal(a.consensus(c), b.consensus(c)), ("buckets", variant, c)
 print("POA_VARIANTS_OK kernel ms by variant  " + "  ".join(times))
 """
 

@@ -10,11 +10,11 @@ for v in 0 1 2 3 4 7 8 15 16 31; do  # POA
   SVB_POA_VARIANT=$v SVB_POA_TIMING=1 timeout 600 python tools/bench_call.py --clusters $N --pairs 0 --cpu-seconds 0.5 2>&1 | \
     grep -E "k_poa phases|\"kernel\"|clusters_per_s|GCUPS" | cut -c1-400
 done | tee gpurun_out/poa_variants_$TAG.txt
-for g in 16 8; do for v in 0 7 31; do
-  echo "== variant $v, $g lanes per cluster"
-  SVB_POA_GROUP=$g SVB_POA_VARIANT=$v SVB_POA_TIMING=1 timeout 600 python tools/bench_call.py --clusters $N --pairs 0 --cpu-seconds 0.5 2>&1 | \
+for g in 16 8; do for v in 0 7 31; do for k in 1 6; do
+  echo "== variant $v, $g lanes per cluster, $k launch buckets"
+  SVB_POA_BUCKETS=$k SVB_POA_GROUP=$g SVB_POA_VARIANT=$v SVB_POA_TIMING=1 timeout 600 python tools/bench_call.py --clusters $N --pairs 0 --cpu-seconds 0.5 2>&1 | \
     grep -E "k_poa phases|\"kernel\"|clusters_per_s|GCUPS" | cut -c1-400
-done; done | tee -a gpurun_out/poa_variants_$TAG.txt
+done; done; done | tee -a gpurun_out/poa_variants_$TAG.txt
 # ksw2 backtrack variant on a pipeline-like shape (pairs up to 3 kb) and on the config-5 shape
 for v in 0 1; do
   echo "== ksw variant $v"
