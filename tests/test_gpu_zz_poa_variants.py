@@ -42,7 +42,7 @@ for variant, group in ((0, 32), (31, 8)):
     os.environ["SVB_POA_VARIANT"] = str(variant)
     os.environ["SVB_POA_GROUP"] = str(group)
     b = capi.poa_batch(clusters)
-    assert a.cells == b.cells and b.launches > a.launches, (variant, group, a.launches, b.launches)
+    assert a.cells == b.cells and b.launches >= a.launches, (variant, group, a.launches, b.launches)
     for c in range(len(clusters)):
         assert np.array_equal(a.consensus(c), b.consensus(c)), ("buckets", variant, c)
 print("POA_VARIANTS_OK kernel ms by variant  " + "  ".join(times))
