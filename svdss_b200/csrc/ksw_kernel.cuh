@@ -34,7 +34,7 @@ __device__ __forceinline__ int gapcost(int k, int q1, int e1, int q2, int e2) { 
 
 __device__ __forceinline__ void ksw_prefetch(const void* p) {
 #ifdef __CUDA_ARCH__
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  asm volatile("{ .reg .u64 a; cvta.to.global.u64 a, %0; prefetch.global.L1 [a]; }" ::"l"(p));
 #else
   (void)p;
 #endif

@@ -115,7 +115,7 @@ constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, P
 
 __device__ __forceinline__ void poa_prefetch(const void* p) {
 #ifdef __CUDA_ARCH__
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+  asm volatile("{ .reg .u64 a; cvta.to.global.u64 a, %0; prefetch.global.L1 [a]; }" ::"l"(p));
 #else
   (void)p;
 #endif
