@@ -58,12 +58,16 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
   size_t free_b = 0, total_b = 0;
   SVB_CUDA(cudaMemGetInfo(&free_b, &total_b));
   const char* eb = getenv("SVB_KSW_TB_BYTES");
-  int64_t budget = eb ? atoll(eb) : (int64_t)std::min<size_t>(free_b / 2, (size_t)48 << 30);
-  auto tb_bytes = [&](uint32_t p) -> int64_t {
-    int64_t ql = q_offs[p + 1] - q_offs[p], tl = t_offs[p + 1] - t_offs[p];
-    if (ql <= 0 || tl <= 0) return 0;
-    return ((tl + KBAND - 1) / KBAND) * (ql + 31) * KBAND;
-  };
+  // one traceback byte per cell: the budget bounds the cells in flight, hence -- for 10 kb x 10 kb pairs of
+  // 100 MB each -- the number of warps that have work.  Most of the free HBM by default (round 1 used
+  // min(free / 2, 48 GB): 480 such pairs for 2 960 warp slots).
+  int64_t budget = eb ? atoll(eb) : (int64_t)std::min<size_t>((size_t)(free_b * 0.8), (size_t)128 << 30);
+  // kernel variant (ksw_kernel.cuh): bit 1 = windowed backtrack with prefetch, bit 2 = checkpointed traceback for
+  // pairs of several bands; default 0 = the kernel measured in round 1
+  const char* evar = getenv("SVB_KSW_VARIANT");
+  const int variant = evar ? atoi(evar) : 0;
+  if (variant < 0 || variant > 3) { set_error("SVB_KSW_VARIANT must be 0..3"); return SVB_EINVAL; }
+  auto tb_bytes = [&](uint32_t p) -> int64_t { return ksw_tb_bytes(variant, q_offs[p + 1] - q_offs[p], t_offs[p + 1] - t_offs[p]); };
   if (tb_bytes(order[0]) > budget) budget = tb_bytes(order[0]);
 
   uint8_t *d_q = nullptr, *d_t = nullptr, *d_tb = nullptr;
@@ -117,7 +121,7 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
           int64_t ql = qo[id + 1] - qo[id], tl = to[id + 1] - to[id];
           woff[p * 3 + 0] = wv.tb; woff[p * 3 + 1] = wv.bnd; woff[p * 3 + 2] = wv.cg;
           wv.tb += (tbb + 127) & ~127LL;
-          wv.bnd += 3 * ql;
+          wv.bnd += ksw_bnd_ints(variant, ql, tl);
           wv.cg += ql + tl + 2;
           ++wv.count; ++p;
         }
@@ -161,10 +165,11 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
       cudaEvent_t k0, k1;
       KCHECK(cudaEventCreate(&k0)); KCHECK(cudaEventCreate(&k1));
       KCHECK(cudaEventRecord(k0, 0));
-      {
-        const char* ev = getenv("SVB_KSW_VARIANT");   // 1 = windowed backtrack with prefetch (ksw_kernel.cuh); default 0 = the kernel measured in round 1
-        if (ev && atoi(ev) == 1) k_ksw_extd2<true><<<grid, 128>>>(P);
-        else k_ksw_extd2<false><<<grid, 128>>>(P);
+      switch (variant) {
+        case 1: k_ksw_extd2<1><<<grid, 128>>>(P); break;
+        case 2: k_ksw_extd2<2><<<grid, 128>>>(P); break;
+        case 3: k_ksw_extd2<3><<<grid, 128>>>(P); break;
+        default: k_ksw_extd2<0><<<grid, 128>>>(P); break;
       }
       KCHECK(cudaGetLastError());
       KCHECK(cudaEventRecord(k1, 0));

@@ -40,13 +40,39 @@ __device__ __forceinline__ void ksw_prefetch(const void* p) {
 #endif
 }
 
-// TBPF (SVB_KSW_VARIANT=1): the backtrack reads one traceback byte per step, each in a different 128-byte
-// line (a diagonal step moves one wavefront step back), written long before: a cache-missing dependent walk
-// by one lane.  With TBPF it runs in windows of 32 steps, and before each window all lanes prefetch the bytes
-// the path would read 32..63 steps ahead if it stayed on its diagonal (0..31 as well for the first window).
-// Addresses are pure arithmetic on (i, j); a wrong guess is a wasted prefetch.  Results are identical.
-template <bool TBPF>
-__global__ void __launch_bounds__(128) k_ksw_extd2(const KswParams P) {
+// Variants (template bit mask KV, SVB_KSW_VARIANT on the host; 0 = the kernel measured in round 1):
+//  1 TBPF  the backtrack reads one traceback byte per step, each in a different 128-byte line (a diagonal
+//          step moves one wavefront step back), written long before: a cache-missing dependent walk by one
+//          lane.  With TBPF it runs in windows of 32 steps, and before each window all lanes prefetch the
+//          bytes the path would read 32..63 steps ahead if it stayed on its diagonal (0..31 as well for the
+//          first window).  Addresses are pure arithmetic on (i, j); a wrong guess is a wasted prefetch.
+//  2 CKPT  checkpointed traceback for pairs of at least KSW_CKPT_BANDS bands.  One traceback byte per cell
+//          makes a 10 kb x 10 kb pair cost 100 MB, so the memory budget -- not the GPU -- decides how many
+//          such pairs are in flight (a few hundred for 2 960 warp slots).  With CKPT the forward pass stores
+//          no traceback, only the boundary row (H, E, E2) under every band: 12 bytes x ql per band.  The
+//          backtrack then walks the bands from the last to the first, recomputing one band at a time -- only
+//          the columns left of the path's current position -- into a single band-sized traceback buffer.
+//          About 1.5x the cells for a tenth of the memory, hence ten times the pairs in flight.
+// Scores and CIGARs are identical in every variant.
+constexpr int KSW_V_TBPF = 1, KSW_V_CKPT = 2;
+constexpr int KSW_CKPT_BANDS = 4;
+
+// bytes of traceback / boundary ints a pair needs (host wave planner and kernel agree through these)
+__host__ __device__ inline bool ksw_uses_ckpt(int variant, int64_t tl) { return (variant & KSW_V_CKPT) && (tl + KBAND - 1) / KBAND >= KSW_CKPT_BANDS; }
+__host__ __device__ inline int64_t ksw_tb_bytes(int variant, int64_t ql, int64_t tl) {
+  if (ql <= 0 || tl <= 0) return 0;
+  const int64_t nbands = (tl + KBAND - 1) / KBAND, nsteps = ql + 31;
+  return (ksw_uses_ckpt(variant, tl) ? 1 : nbands) * nsteps * KBAND;
+}
+__host__ __device__ inline int64_t ksw_bnd_ints(int variant, int64_t ql, int64_t tl) {
+  if (ql <= 0 || tl <= 0) return 0;
+  const int64_t nbands = (tl + KBAND - 1) / KBAND;
+  return (ksw_uses_ckpt(variant, tl) ? nbands : 1) * 3 * ql;
+}
+
+template <int KV>
+__global__ void __launch_bounds__(128, 5) k_ksw_extd2(const KswParams P) {   // 5 CTAs per SM (<= 102 registers), as measured in round 1
+  constexpr bool TBPF = (KV & KSW_V_TBPF) != 0;
   const int lane = threadIdx.x & 31;
   const int NEG = -0x1fffffff;
   int q1 = P.q1, e1 = P.e1, q2 = P.q2, e2 = P.e2;
@@ -66,11 +92,14 @@ __global__ void __launch_bounds__(128) k_ksw_extd2(const KswParams P) {
       continue;
     }
     uint8_t* tb = P.tb + P.tb_off[w];
-    int32_t* bnd = P.bnd + P.bnd_off[w];  // [3][ql]: H, E, E2 of the row above the current band
+    int32_t* bnd = P.bnd + P.bnd_off[w];  // [3][ql]: H, E, E2 of the row above the current band (CKPT: one such slab per band)
     const int nbands = (tl + KBAND - 1) / KBAND;
     const int nsteps = ql + 31;
+    const bool ckpt = ksw_uses_ckpt(KV, tl);
     int final_score = 0;
-    for (int band = 0; band < nbands; ++band) {
+    // one band of 128 target rows over the first `nst` wavefront steps: boundary row above from `bin` (band > 0),
+    // boundary row below to `bout` (or nullptr), traceback bytes to `tbb` (or nullptr)
+    auto run_band = [&](int band, const int32_t* bin, int32_t* bout, uint8_t* tbb, int nst) {
       const int i0 = band * KBAND + lane * KR;  // first row of this lane
       uint8_t tc[KR];
       int hl[KR], f[KR], f2[KR];
@@ -89,8 +118,7 @@ __global__ void __launch_bounds__(128) k_ksw_extd2(const KswParams P) {
       int qc = 4, qnext = 4;
       int bh = 0, be = NEG, be2 = NEG;  // lane 0's boundary inputs, prefetched 32 columns at a time
       int wh = 0, we = NEG, we2 = NEG;  // lane 31's boundary outputs, flushed 32 columns at a time
-      uint8_t* tbb = tb + (size_t)band * nsteps * KBAND;
-      for (int t = 0; t < nsteps; ++t) {
+      for (int t = 0; t < nst; ++t) {
         // ---- inputs for this step
         if ((t & 31) == 0) {
           const int jj = t + lane;  // cooperative prefetch of 32 columns of query + boundary
@@ -99,7 +127,7 @@ __global__ void __launch_bounds__(128) k_ksw_extd2(const KswParams P) {
             bh = jj < ql ? -gapcost(jj + 1, q1, e1, q2, e2) : 0;  // H(-1,j)
             be = NEG; be2 = NEG;
           } else if (jj < ql) {
-            bh = bnd[jj]; be = bnd[ql + jj]; be2 = bnd[2 * ql + jj];
+            bh = bin[jj]; be = bin[ql + jj]; be2 = bin[2 * ql + jj];
           }
         }
         // query char: lane 0 takes column t, others inherit from the lane above (one step later)
@@ -147,10 +175,10 @@ __global__ void __launch_bounds__(128) k_ksw_extd2(const KswParams P) {
             if (j == ql - 1 && i0 + r == tl - 1) final_score = h;
           }
           out_h = hup; out_e = eup; out_e2 = e2up;
-          *reinterpret_cast<unsigned*>(tbb + (size_t)t * KBAND + lane * KR) = tbw;
+          if (tbb) *reinterpret_cast<unsigned*>(tbb + (size_t)t * KBAND + lane * KR) = tbw;
         }
         // ---- lane 31 hands its last row to the next band: collect 32 columns, flush coalesced
-        if (band + 1 < nbands) {
+        if (bout) {
           const int j31 = t - 31;  // column lane 31 just finished
           const int s_h = __shfl_sync(0xffffffffu, out_h, 31);
           const int s_e = __shfl_sync(0xffffffffu, out_e, 31);
@@ -159,12 +187,21 @@ __global__ void __launch_bounds__(128) k_ksw_extd2(const KswParams P) {
             if ((j31 & 31) == lane) { wh = s_h; we = s_e; we2 = s_e2; }
             if ((j31 & 31) == 31 || j31 == ql - 1) {
               const int jj = (j31 & ~31) + lane;
-              if (jj <= j31) { bnd[jj] = wh; bnd[ql + jj] = we; bnd[2 * ql + jj] = we2; }
+              if (jj <= j31) { bout[jj] = wh; bout[ql + jj] = we; bout[2 * ql + jj] = we2; }
             }
           }
         }
       }
       __syncwarp();
+    };
+    if (!ckpt) {
+      // the boundary buffer is reused in place: a band reads columns ahead of the ones it writes
+      for (int band = 0; band < nbands; ++band)
+        run_band(band, bnd, band + 1 < nbands ? bnd : nullptr, tb + (size_t)band * nsteps * KBAND, nsteps);
+    } else {
+      // forward pass without traceback: band b reads slab b - 1, writes slab b
+      for (int band = 0; band < nbands; ++band)
+        run_band(band, band ? bnd + (size_t)(band - 1) * 3 * ql : nullptr, band + 1 < nbands ? bnd + (size_t)band * 3 * ql : nullptr, nullptr, nsteps);
     }
     // score lives in the lane that owned row tl-1
     {
@@ -181,32 +218,47 @@ __global__ void __launch_bounds__(128) k_ksw_extd2(const KswParams P) {
         if (last && (last & 0xfu) == op) last += len << 4;
         else { if (last) cg[n++] = last; last = (len << 4) | op; }
       };
-      auto tb_addr = [&](int ii, int jj) -> const uint8_t* {
-        const int bnd_ = ii / KBAND, l = (ii % KBAND) / KR, r = ii % KR;
-        return tb + (size_t)bnd_ * nsteps * KBAND + (size_t)(jj + l) * KBAND + l * KR + r;
+      // traceback byte of cell (ii, jj); `band_base` = first row of the band the buffer `tbp` holds
+      auto tb_addr = [&](const uint8_t* tbp, int band_base, int ii, int jj) -> const uint8_t* {
+        const int l = ((ii - band_base) % KBAND) / KR, r = ii % KR;
+        return tbp + (size_t)((ii - band_base) / KBAND) * nsteps * KBAND + (size_t)(jj + l) * KBAND + l * KR + r;
       };
-      auto step = [&]() {
-        const unsigned tmp = *tb_addr(i, j);
-        if (state == 0) state = tmp & 7;
-        else if (!((tmp >> (state + 2)) & 1)) state = 0;
-        if (state == 0) state = tmp & 7;
-        if (state == 0) { push(0, 1); --i; --j; }
-        else if (state == 1 || state == 3) { push(2, 1); --i; }
-        else { push(1, 1); --j; }
+      // walk while the path stays at or below row `i_min` (0 for the whole matrix)
+      auto walk = [&](const uint8_t* tbp, int band_base, int i_min) {
+        auto step = [&]() {
+          const unsigned tmp = *tb_addr(tbp, band_base, i, j);
+          if (state == 0) state = tmp & 7;
+          else if (!((tmp >> (state + 2)) & 1)) state = 0;
+          if (state == 0) state = tmp & 7;
+          if (state == 0) { push(0, 1); --i; --j; }
+          else if (state == 1 || state == 3) { push(2, 1); --i; }
+          else { push(1, 1); --j; }
+        };
+        if (!TBPF) {
+          if (lane == 0) while (i >= i_min && j >= 0) step();
+        } else {
+          bool first = true;
+          for (;;) {
+            const int ci = __shfl_sync(0xffffffffu, i, 0), cj = __shfl_sync(0xffffffffu, j, 0);
+            if (ci < i_min || cj < 0) break;
+            for (int d = first ? lane : 32 + lane; d < 64; d += 32)
+              if (ci - d >= i_min && cj - d >= 0) ksw_prefetch(tb_addr(tbp, band_base, ci - d, cj - d));
+            first = false;
+            __syncwarp();
+            if (lane == 0) for (int st = 0; st < 32 && i >= i_min && j >= 0; ++st) step();
+            __syncwarp();
+          }
+        }
       };
-      if (!TBPF) {
-        if (lane == 0) while (i >= 0 && j >= 0) step();
-      } else {
-        bool first = true;
-        for (;;) {
+      if (!ckpt) walk(tb, 0, 0);
+      else {
+        for (int band = nbands - 1; band >= 0; --band) {
           const int ci = __shfl_sync(0xffffffffu, i, 0), cj = __shfl_sync(0xffffffffu, j, 0);
           if (ci < 0 || cj < 0) break;
-          for (int d = first ? lane : 32 + lane; d < 64; d += 32)
-            if (ci - d >= 0 && cj - d >= 0) ksw_prefetch(tb_addr(ci - d, cj - d));
-          first = false;
-          __syncwarp();
-          if (lane == 0) for (int st = 0; st < 32 && i >= 0 && j >= 0; ++st) step();
-          __syncwarp();
+          if (ci < band * KBAND) continue;            // the path has already left this band (a long deletion)
+          // the path never moves right: columns beyond cj are not needed (lane l reaches column cj at step cj + l)
+          run_band(band, band ? bnd + (size_t)(band - 1) * 3 * ql : nullptr, nullptr, tb, min(nsteps, cj + 32));
+          walk(tb, band * KBAND, band * KBAND);
         }
       }
       if (lane == 0) {

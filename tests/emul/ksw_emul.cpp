@@ -10,7 +10,12 @@ struct Launch { svb::KswParams P; int variant; };
 
 static void body(void* a) {
   Launch* l = static_cast<Launch*>(a);
-  if (l->variant) svb::k_ksw_extd2<true>(l->P); else svb::k_ksw_extd2<false>(l->P);
+  switch (l->variant) {
+    case 1: svb::k_ksw_extd2<1>(l->P); break;
+    case 2: svb::k_ksw_extd2<2>(l->P); break;
+    case 3: svb::k_ksw_extd2<3>(l->P); break;
+    default: svb::k_ksw_extd2<0>(l->P); break;
+  }
 }
 
 // cigar_out: forward-order ops of pair p at cigar_off[p] (capacity ql + tl + 2 each), n_cigar[p] ops
@@ -22,9 +27,8 @@ extern "C" int emul_ksw(const uint8_t* q, const int64_t* qoff, const uint8_t* t,
   for (int p = 0; p < n_pairs; ++p) {
     order[(size_t)p] = (uint32_t)p;
     const int64_t ql = qoff[p + 1] - qoff[p], tl = toff[p + 1] - toff[p];
-    const int64_t nbands = (tl + svb::KBAND - 1) / svb::KBAND, nsteps = ql + 31;
-    tb_off[(size_t)p + 1] = tb_off[(size_t)p] + nbands * nsteps * svb::KBAND;
-    bnd_off[(size_t)p + 1] = bnd_off[(size_t)p] + 3 * ql;
+    tb_off[(size_t)p + 1] = tb_off[(size_t)p] + svb::ksw_tb_bytes(variant, ql, tl);     // as the host wave planner sizes them
+    bnd_off[(size_t)p + 1] = bnd_off[(size_t)p] + svb::ksw_bnd_ints(variant, ql, tl);
     cg_off[(size_t)p + 1] = cg_off[(size_t)p] + ql + tl + 2;
   }
   std::vector<uint8_t> tb((size_t)tb_off[(size_t)n_pairs] + 16, 0xEE);     // not zeroed, like a cudaMalloc'ed buffer

@@ -1,6 +1,7 @@
 """CPU: the ksw2 kernel source itself (svdss_b200/csrc/ksw_kernel.cuh) compiled for the host with the
-lock-step warp emulator of tests/emul/ -- the default kernel and the SVB_KSW_VARIANT=1 backtrack
-(windows of 32 steps with the traceback bytes prefetched) -- must give the oracle's score and CIGAR."""
+lock-step warp emulator of tests/emul/ -- the default kernel and the SVB_KSW_VARIANT bits (1: backtrack in
+windows of 32 steps with the traceback bytes prefetched, 2: checkpointed traceback, bands recomputed during the
+backtrack) -- must give the oracle's score and CIGAR."""
 import ctypes as C
 import os
 import subprocess
@@ -67,9 +68,16 @@ def make_pairs(seed, n, lo, hi):
     return out
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_emulated_kernel_equals_oracle(emul, variant):
     pairs = make_pairs(51, 24, 1, 90) + make_pairs(52, 6, 120, 300)      # one band, and several bands (KBAND = 128 target rows)
+    if variant & 2:                                                       # checkpointed traceback needs >= 4 bands (target > 384)
+        pairs = pairs[:8] + make_pairs(53, 5, 390, 700)
+        rng = np.random.default_rng(54)
+        t = rng.integers(0, 4, size=600).astype(np.uint8)
+        pairs.append((np.concatenate([t[:100], t[420:]]), t))             # a deletion longer than two bands: the path runs down one column
+        pairs.append((np.concatenate([t[:300], rng.integers(0, 4, size=200).astype(np.uint8), t[300:]]), t))   # long insertion inside a band
+        pairs.append((t[:40].copy(), t))                                  # short query against a long target
     pairs.append((np.zeros(0, np.uint8), pairs[0][1]))                   # empty query: KSW_NEG_INF, no CIGAR
     got = run(emul, pairs, variant)
     for i, (q, t) in enumerate(pairs):

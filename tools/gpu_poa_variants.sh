@@ -16,7 +16,7 @@ for g in 16 8; do for v in 0 7 31; do for k in 1 6; do
     grep -E "k_poa phases|\"kernel\"|clusters_per_s|GCUPS" | cut -c1-400
 done; done; done | tee -a gpurun_out/poa_variants_$TAG.txt
 # ksw2 backtrack variant on a pipeline-like shape (pairs up to 3 kb) and on the config-5 shape
-for v in 0 1; do
+for v in 0 1 2 3; do
   echo "== ksw variant $v"
   SVB_KSW_VARIANT=$v timeout 600 python tools/bench_call.py --clusters 0 --pairs 20000 --max-len 3000 --cpu-seconds 0.5 2>&1 | grep k_ksw | cut -c1-300
   SVB_KSW_VARIANT=$v timeout 600 python tools/bench_call.py --clusters 0 --pairs 20000 --cpu-seconds 0.5 2>&1 | grep k_ksw | cut -c1-300
