@@ -13,9 +13,26 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
-#include <ucontext.h>
-
 #include <vector>
+
+// Fiber switch: on x86-64 a dozen instructions (callee-saved registers + stack pointer); elsewhere ucontext,
+// whose swapcontext makes two system calls per switch.
+#if defined(__x86_64__) && !defined(EMU_USE_UCONTEXT)
+#define EMU_FAST_SWITCH 1
+extern "C" void emu_switch(void** save_sp, void* const* load_sp);
+asm(".text\n"
+    ".p2align 4\n"
+    ".type emu_switch,@function\n"
+    "emu_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq (%rsi), %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size emu_switch,.-emu_switch\n");
+#else
+#include <ucontext.h>
+#endif
 
 #define __global__
 #define __device__
@@ -30,8 +47,13 @@ static EmuDim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {32, 1, 1
 namespace emu {
 
 struct Warp {
+#ifdef EMU_FAST_SWITCH
+  void* sched = nullptr;   // saved stack pointers
+  void* ctx[32];
+#else
   ucontext_t sched;
   ucontext_t ctx[32];
+#endif
   std::vector<char> stack[32];
   bool done[32];
   int cur = 0;
@@ -45,7 +67,14 @@ struct Warp {
 };
 static Warp* g_warp = nullptr;
 
-inline void yield_lane() { swapcontext(&g_warp->ctx[g_warp->cur], &g_warp->sched); }
+#ifdef EMU_FAST_SWITCH
+inline void to_sched() { emu_switch(&g_warp->ctx[g_warp->cur], &g_warp->sched); }
+inline void to_lane(int l) { emu_switch(&g_warp->sched, &g_warp->ctx[l]); }
+#else
+inline void to_sched() { swapcontext(&g_warp->ctx[g_warp->cur], &g_warp->sched); }
+inline void to_lane(int l) { swapcontext(&g_warp->sched, &g_warp->ctx[l]); }
+#endif
+inline void yield_lane() { to_sched(); }
 
 inline void barrier(unsigned mask = 0xffffffffu) {
   Warp* w = g_warp;
@@ -69,7 +98,8 @@ static void trampoline() {
   Warp* w = g_warp;
   w->body(w->arg);
   w->done[w->cur] = true;
-  swapcontext(&w->ctx[w->cur], &w->sched);
+  to_sched();
+  abort();   // a finished lane is never resumed
 }
 
 // runs body(arg) on 32 lanes (threadIdx.x = lane) until all have returned; false if the warp deadlocks
@@ -81,11 +111,22 @@ inline bool run_warp(void (*body)(void*), void* arg, size_t stack_bytes = 1 << 2
   for (int l = 0; l < 32; ++l) {
     w.done[l] = false; w.arrived[l] = 0; w.generation[l] = 0;
     w.stack[l].resize(stack_bytes);
+#ifdef EMU_FAST_SWITCH
+    // a fresh stack that emu_switch "returns" into: six zeroed callee-saved slots, the entry point as the return
+    // address, one pad word so that the entry sees the alignment of a called function
+    uintptr_t top = ((uintptr_t)w.stack[l].data() + stack_bytes) & ~(uintptr_t)15;
+    void** sp = (void**)top - 8;
+    for (int k = 0; k < 6; ++k) sp[k] = nullptr;
+    sp[6] = (void*)trampoline;
+    sp[7] = nullptr;
+    w.ctx[l] = (void*)sp;
+#else
     getcontext(&w.ctx[l]);
     w.ctx[l].uc_stack.ss_sp = w.stack[l].data();
     w.ctx[l].uc_stack.ss_size = stack_bytes;
     w.ctx[l].uc_link = &w.sched;
     makecontext(&w.ctx[l], (void (*)())trampoline, 0);
+#endif
   }
   int live = 32;
   unsigned long idle_rounds = 0, last_sum = 0;
@@ -94,7 +135,7 @@ inline bool run_warp(void (*body)(void*), void* arg, size_t stack_bytes = 1 << 2
       if (w.done[l]) continue;
       w.cur = l;
       threadIdx.x = (unsigned)l;
-      swapcontext(&w.sched, &w.ctx[l]);
+      to_lane(l);
       if (w.done[l]) --live;
     }
     unsigned long sum = (unsigned long)(32 - live);

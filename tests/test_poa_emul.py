@@ -147,3 +147,15 @@ def test_rows_wider_than_the_shared_copy_fall_back_to_the_workspace(emul):
         assert cells == cells0 and not status.any()
         for c in range(len(clusters)):
             assert np.array_equal(got[c], ref[c]), (swcap, c)
+
+
+def test_config4_shaped_cluster(emul):
+    """SURVEY 8(d) config-4 shape (20-60 reads x 200-2000 bp, 0.1 % noise, half the reads with a planted indel):
+    the default kernel and the most different build (all variant bits, 8 lanes per cluster)"""
+    rng = np.random.default_rng(47)
+    clusters = [make_cluster(rng, n_reads=21, tlen=700)[1], make_cluster(rng, n_reads=24, tlen=260)[1]]
+    exp = [oracle.poa_consensus(c, band=True) for c in clusters]
+    for variant, group in ((0, 32), (31, 8)):
+        got, status, _ = run(emul, clusters, variant, group=group)
+        assert not status.any()
+        assert all(np.array_equal(g, e) for g, e in zip(got, exp)), (variant, group)
