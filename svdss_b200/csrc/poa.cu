@@ -208,9 +208,11 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
         switch (group * 100 + variant) {
           POA_LAUNCH(0) POA_LAUNCH(1) POA_LAUNCH(2) POA_LAUNCH(3) POA_LAUNCH(4) POA_LAUNCH(6) POA_LAUNCH(7)
           POA_LAUNCH(8) POA_LAUNCH(14) POA_LAUNCH(15) POA_LAUNCH(16) POA_LAUNCH(18) POA_LAUNCH(30) POA_LAUNCH(31)
-          POA_LAUNCH_G(0, 16) POA_LAUNCH_G(7, 16) POA_LAUNCH_G(31, 16) POA_LAUNCH_G(0, 8) POA_LAUNCH_G(7, 8) POA_LAUNCH_G(31, 8)
+          POA_LAUNCH(32) POA_LAUNCH(33) POA_LAUNCH(39) POA_LAUNCH(63)
+          POA_LAUNCH_G(0, 16) POA_LAUNCH_G(7, 16) POA_LAUNCH_G(31, 16) POA_LAUNCH_G(63, 16)
+          POA_LAUNCH_G(0, 8) POA_LAUNCH_G(7, 8) POA_LAUNCH_G(31, 8) POA_LAUNCH_G(63, 8)
           default:
-            set_error("SVB_POA_VARIANT=%d with SVB_POA_GROUP=%d is not built (group 32: 0 1 2 3 4 6 7 8 14 15 16 18 30 31; 16 and 8: 0 7 31)", variant, group);
+            set_error("SVB_POA_VARIANT=%d with SVB_POA_GROUP=%d is not built (group 32: 0 1 2 3 4 6 7 8 14 15 16 18 30 31 32 33 39 63; 16 and 8: 0 7 31 63)", variant, group);
             rc = SVB_EINVAL;
             goto done;
         }

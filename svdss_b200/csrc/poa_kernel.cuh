@@ -111,7 +111,10 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane, unsigned gmask) {
 //  8 PREF   graph update: before lane 0 walks a window of 32 alignment ops, all lanes touch the node and
 //           edge fields it is going to read (prefetch.global.L1), so its dependent loads hit L1
 // 16 TBPF   traceback in windows of 32 steps whose traceback words all lanes prefetch along the predicted path
-constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, POA_V_TBPF = 16;
+// 32 LEAN   DP rows with fewer dependent shuffles: the row maximum and its first / last column through REDUX
+//           (__reduce_max_sync / __reduce_min_sync, 3 instructions instead of 15 shuffle steps), the two
+//           "gap was extended" comparisons handed to the next lane as two bits instead of their four operands
+constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, POA_V_TBPF = 16, POA_V_LEAN = 32;
 
 __device__ __forceinline__ void poa_prefetch(const void* p) {
 #ifdef __CUDA_ARCH__
@@ -130,7 +133,7 @@ template <int V, int G = 32>
 __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   extern __shared__ int poa_smem[];
   constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0,
-                 TBPF = (V & POA_V_TBPF) != 0;
+                 TBPF = (V & POA_V_TBPF) != 0, LEAN = (V & POA_V_LEAN) != 0;
   static_assert(G == 32 || G == 16 || G == 8, "group width");
   const int lane = threadIdx.x & (G - 1);
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         const bool cur_sm = SMEM && en - b + 1 <= Ws;
         int carry1 = PNEG, carry2 = PNEG;      // running max of B1/B2 over columns before this segment
         int prevX1 = PNEG, prevB1 = PNEG, prevX2 = PNEG, prevB2 = PNEG;  // column j-1 of lane 0
+        int prevflags = 0;                                               // LEAN: the same as two bits
         int rmax = PNEG - 1, rleft = 0, rright = 0;
         for (int j0 = b; j0 <= en; j0 += G) {
           const int j = j0 + lane;
@@ -338,10 +342,18 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           int f1 = PNEG, f2 = PNEG;
           if (j > b) { f1 = max(X1 - P.o1 - j * P.e1, PNEG); f2 = max(X2 - P.o2 - j * P.e2, PNEG); }
           // ext flag of column j: F(j-1) > Hp(j-1) - o  <=>  X(j-1) > B(j-1)
-          int pX1 = __shfl_up_sync(gmask, X1, 1, G), pB1 = __shfl_up_sync(gmask, B1, 1, G);
-          int pX2 = __shfl_up_sync(gmask, X2, 1, G), pB2 = __shfl_up_sync(gmask, B2, 1, G);
-          if (lane == 0) { pX1 = prevX1; pB1 = prevB1; pX2 = prevX2; pB2 = prevB2; }
-          const int f1ext = (j > b) && (pX1 > pB1), f2ext = (j > b) && (pX2 > pB2);
+          int f1ext, f2ext;
+          const int myflags = (X1 > B1 ? 1 : 0) | (X2 > B2 ? 2 : 0);   // LEAN: the two comparisons travel, not the four operands
+          if (LEAN) {
+            int pf = __shfl_up_sync(gmask, myflags, 1, G);
+            if (lane == 0) pf = prevflags;
+            f1ext = (j > b) && (pf & 1); f2ext = (j > b) && (pf & 2);
+          } else {
+            int pX1 = __shfl_up_sync(gmask, X1, 1, G), pB1 = __shfl_up_sync(gmask, B1, 1, G);
+            int pX2 = __shfl_up_sync(gmask, X2, 1, G), pB2 = __shfl_up_sync(gmask, B2, 1, G);
+            if (lane == 0) { pX1 = prevX1; pB1 = prevB1; pX2 = prevX2; pB2 = prevB2; }
+            f1ext = (j > b) && (pX1 > pB1); f2ext = (j > b) && (pX2 > pB2);
+          }
           int hh = hp; unsigned hs = hps;
           if (f1 > hh) { hh = f1; hs = 3; }
           if (f2 > hh) { hh = f2; hs = 4; }
@@ -356,19 +368,28 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           }
           carry1 = max(carry1, __shfl_sync(gmask, inc1, G - 1, G));
           carry2 = max(carry2, __shfl_sync(gmask, inc2, G - 1, G));
-          prevX1 = __shfl_sync(gmask, X1, G - 1, G); prevB1 = __shfl_sync(gmask, B1, G - 1, G);
-          prevX2 = __shfl_sync(gmask, X2, G - 1, G); prevB2 = __shfl_sync(gmask, B2, G - 1, G);
+          if (LEAN) prevflags = __shfl_sync(gmask, myflags, G - 1, G);
+          else {
+            prevX1 = __shfl_sync(gmask, X1, G - 1, G); prevB1 = __shfl_sync(gmask, B1, G - 1, G);
+            prevX2 = __shfl_sync(gmask, X2, G - 1, G); prevB2 = __shfl_sync(gmask, B2, G - 1, G);
+          }
         }
         cells += (unsigned long long)(en - b + 1);
         // row maximum, its first and last column (lanes hold strided columns: reduce)
-        int gmax = rmax;
+        int gmax = rmax, l_, r_;
+        if (LEAN) {   // REDUX: one instruction per reduction instead of log2(G) shuffle steps
+          gmax = __reduce_max_sync(gmask, rmax);
+          l_ = __reduce_min_sync(gmask, (rmax == gmax) ? rleft : 0x7fffffff);
+          r_ = __reduce_max_sync(gmask, (rmax == gmax) ? rright : -1);
+        } else {
 #pragma unroll
-        for (int o = G / 2; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(gmask, gmax, o, G));
-        int l_ = (rmax == gmax) ? rleft : 0x7fffffff, r_ = (rmax == gmax) ? rright : -1;
+          for (int o = G / 2; o; o >>= 1) gmax = max(gmax, __shfl_xor_sync(gmask, gmax, o, G));
+          l_ = (rmax == gmax) ? rleft : 0x7fffffff; r_ = (rmax == gmax) ? rright : -1;
 #pragma unroll
-        for (int o = G / 2; o; o >>= 1) {
-          l_ = min(l_, __shfl_xor_sync(gmask, l_, o, G));
-          r_ = max(r_, __shfl_xor_sync(gmask, r_, o, G));
+          for (int o = G / 2; o; o >>= 1) {
+            l_ = min(l_, __shfl_xor_sync(gmask, l_, o, G));
+            r_ = max(r_, __shfl_xor_sync(gmask, r_, o, G));
+          }
         }
         if (lane == 0) { W.beg[v] = b; W.end[v] = en; W.mpl[v] = l_ + 1; W.mpr[v] = r_ + 1; }
         v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1; prev_sm = cur_sm;

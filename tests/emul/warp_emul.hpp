@@ -161,6 +161,9 @@ template <class T> inline T __shfl_up_sync(unsigned m, T v, unsigned d, int widt
 template <class T> inline T __shfl_down_sync(unsigned m, T v, unsigned d, int width = 32) { const int lane = emu::g_warp->cur; return emu::xchg(m, v, (lane & (width - 1)) + (int)d < width ? lane + (int)d : lane); }
 template <class T> inline T __shfl_xor_sync(unsigned m, T v, int x, int width = 32) { const int lane = emu::g_warp->cur; const int t = lane ^ x; return emu::xchg(m, v, (t & ~(width - 1)) == (lane & ~(width - 1)) ? t : lane); }
 inline void __syncwarp(unsigned m = 0xffffffffu) { emu::barrier(m); }
+// REDUX (sm_80+): reduction over the lanes of the mask, every lane gets the result
+inline int __reduce_max_sync(unsigned m, int v) { int r = v; bool any = false; for (int l = 0; l < 32; ++l) if ((m >> l) & 1u) { const int u = emu::xchg(m, v, l); r = any ? (u > r ? u : r) : u; any = true; } return r; }
+inline int __reduce_min_sync(unsigned m, int v) { int r = v; bool any = false; for (int l = 0; l < 32; ++l) if ((m >> l) & 1u) { const int u = emu::xchg(m, v, l); r = any ? (u < r ? u : r) : u; any = true; } return r; }
 inline unsigned __ballot_sync(unsigned m, int pred) { unsigned r = 0; for (int l = 0; l < 32; ++l) if ((m >> l) & 1u) r |= (emu::exchange(m, pred ? 1u : 0u, l) & 1u) << l; return r; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }

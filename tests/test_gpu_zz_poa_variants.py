@@ -27,7 +27,8 @@ clusters.append([rng.integers(0, 4, size=int(rng.integers(150, 260))).astype(np.
 os.environ["SVB_POA_VARIANT"] = "0"
 a = capi.poa_batch(clusters)
 times = ["0: %.2f" % a.kernel_ms]
-for variant, group in ((1, 32), (3, 32), (7, 32), (15, 32), (31, 32), (0, 16), (7, 16), (31, 16), (0, 8), (7, 8), (31, 8)):
+for variant, group in ((1, 32), (3, 32), (7, 32), (15, 32), (31, 32), (32, 32), (39, 32), (63, 32), (0, 16), (7, 16), (31, 16), (63, 16),
+                       (0, 8), (7, 8), (31, 8), (63, 8)):
     os.environ["SVB_POA_VARIANT"] = str(variant)
     os.environ["SVB_POA_GROUP"] = str(group)
     b = capi.poa_batch(clusters)

@@ -1,7 +1,7 @@
 """CPU: the POA kernel source itself (svdss_b200/csrc/poa_kernel.cuh) compiled for the host with the
 lock-step warp emulator of tests/emul/ -- the default kernel k_poa<0> and the variants selected by
 SVB_POA_VARIANT (bit 1 previous row in shared memory, 2 first predecessor from in1 in the traceback,
-4 remain[] / re-rank by the whole warp, 8 windowed graph update, 16 windowed traceback) -- must give the banded oracle's
+4 remain[] / re-rank by the whole warp, 8 windowed graph update, 16 windowed traceback, 32 leaner DP rows) -- must give the banded oracle's
 consensus, and the same cell count as each other.  This is how a kernel variant written without GPU
 time gets checked before it is ever launched."""
 import ctypes as C
@@ -78,9 +78,9 @@ def clusters_small(seed, n):
     return out
 
 
-@pytest.mark.parametrize("smem", [0, 1, 2, 4, 8, 16, 31])
+@pytest.mark.parametrize("smem", [0, 1, 2, 4, 8, 16, 32, 63])
 def test_emulated_kernel_equals_banded_oracle(emul, smem):
-    clusters = clusters_small(41, 14 if smem in (0, 31) else 5)
+    clusters = clusters_small(41, 14 if smem in (0, 63) else 5)
     got, status, cells = run(emul, clusters, smem)
     assert not status.any() and cells > 0
     for c, reads in enumerate(clusters):
@@ -97,7 +97,7 @@ def test_variants_agree_on_wider_rows_and_planted_alleles(emul):
     alt = np.concatenate([t[:140], rng.integers(0, 4, size=40).astype(np.uint8), t[140:]])
     clusters.append([alt, t, alt, alt, t, alt])
     a, sa, ca = run(emul, clusters, 0)
-    for variant in (7, 31):
+    for variant in (7, 31, 63):
         b, sb, cb = run(emul, clusters, variant)
         assert ca == cb and np.array_equal(sa, sb)
         for c, reads in enumerate(clusters):
@@ -121,7 +121,7 @@ def test_overflow_status_and_worst_case_rerun(emul):
         assert np.array_equal(got[0], oracle.poa_consensus(reads, band=True))
 
 
-@pytest.mark.parametrize("group,variant", [(16, 0), (8, 0), (16, 31), (8, 31), (8, 7)])
+@pytest.mark.parametrize("group,variant", [(16, 0), (8, 0), (16, 31), (8, 31), (8, 7), (16, 63), (8, 63)])
 def test_sub_warp_groups(emul, group, variant):
     """G lanes per cluster: 32/G clusters run side by side in one warp, each group with its own control flow
     (clusters of different sizes, so the groups diverge and finish at different times)"""
@@ -155,7 +155,7 @@ def test_config4_shaped_cluster(emul):
     rng = np.random.default_rng(47)
     clusters = [make_cluster(rng, n_reads=21, tlen=700)[1], make_cluster(rng, n_reads=24, tlen=260)[1]]
     exp = [oracle.poa_consensus(c, band=True) for c in clusters]
-    for variant, group in ((0, 32), (31, 8)):
+    for variant, group in ((0, 32), (31, 8), (63, 32), (63, 16)):
         got, status, _ = run(emul, clusters, variant, group=group)
         assert not status.any()
         assert all(np.array_equal(g, e) for g, e in zip(got, exp)), (variant, group)
