@@ -9,6 +9,7 @@
 // Output order = input order of the accepted records, which is what the reference's batch layout
 // (k-major, thread-minor, smoother.cpp:424-450) produces for any --threads.
 #pragma once
+#include <future>
 #include <chrono>
 #include <algorithm>
 #include <cmath>
@@ -247,23 +248,33 @@ inline int run_smooth(const SmoothConfig& c, void (*log)(const char*, const std:
   }
   log("info", "Smoothing alignments on " + std::to_string(c.threads) + " threads..");
   std::set<std::string> warned;
-  const size_t BATCH = 20000;
-  std::vector<BamRecord> batch;
+  const size_t BATCH = 4096;
+  std::vector<BamRecord> batch, next_batch;
   std::vector<std::vector<uint8_t>> bodies;
   uint64_t processed = 0, written = 0;
   int counts[4] = {0, 0, 0, 0};
   bool eof = false;
-  int st = 1;
+  // The record parse is the one serial part of the loop (the reference loads its next batch on a thread of
+  // its own, smoother.cpp:412-460): batch k+1 is read by a helper thread while batch k is smoothed and written.
+  // Only the helper touches the reader, `warned` and `processed` while it runs.
+  auto read_batch = [&](std::vector<BamRecord>* dst) -> int {
+    dst->clear();
+    BamRecord r;
+    int st_ = 1;
+    while (dst->size() < BATCH && (st_ = bam.next(r)) == 1) {
+      ++processed;
+      if (smooth_accept(r, c.min_mapq, bam.ref_names(), seqs, &warned, log)) { dst->emplace_back(std::move(r)); r = BamRecord(); }
+    }
+    return st_;
+  };
+  std::future<int> pending = std::async(std::launch::async, read_batch, &next_batch);
   while (!eof) {
     double t0 = now();
-    batch.clear();
-    BamRecord r;
-    while (batch.size() < BATCH && (st = bam.next(r)) == 1) {
-      ++processed;
-      if (smooth_accept(r, c.min_mapq, bam.ref_names(), seqs, &warned, log)) batch.push_back(r);
-    }
+    const int st = pending.get();
+    batch.swap(next_batch);
     if (st != 1) eof = true;
     if (st < 0) { log("critical", "truncated or corrupt BAM"); return 1; }
+    if (!eof) pending = std::async(std::launch::async, read_batch, &next_batch);
     bodies.assign(batch.size(), std::vector<uint8_t>());
     std::vector<int> xf(batch.size(), 0);
     t_read += now() - t0; t0 = now();
@@ -290,7 +301,7 @@ inline int run_smooth(const SmoothConfig& c, void (*log)(const char*, const std:
   log("info", "Alignments processed: " + std::to_string(processed) + ", written: " + std::to_string(written) + " (XF 0/1/2: " +
                   std::to_string(counts[0]) + "/" + std::to_string(counts[1]) + "/" + std::to_string(counts[2]) + ")");
   char tb[160];
-  snprintf(tb, sizeof(tb), "Stages: accuracy pass %.2f s, read %.2f s, smooth %.2f s, deflate + write %.2f s", t_pass1, t_read, t_smooth, t_write);
+  snprintf(tb, sizeof(tb), "Stages: accuracy pass %.2f s, waiting for the reader %.2f s, smooth %.2f s, deflate + write %.2f s", t_pass1, t_read, t_smooth, t_write);
   log("info", tb);
   return 0;
 }
