@@ -8,7 +8,10 @@ Workload: 3.1 Gb i.i.d. reference in 24 contigs (seed 3), b
 of the search over the whole batch.  `value` times the pass with the batch resident in HBM,
 `e2e` times svb_sfs_batch() with HOST (pinned) buffers: H2D of the reads and D2H of the SFS table
 are inside the timed region.  Multi-GPU: reads shard across ranks (weak scaling, index replicated),
-no data-path collective; timing is max over ranks.
+no data-path collective; timing is max over ranks; each rank's pinned staging buffers are allocated on
+the NUMA node of its GPU.  At N=1 the line also carries `cpu_baseline` (the CPU port on a bounded
+sample), `roofline_rank_walk` / `fmd_rank_microbench` (the "FMD rank GB/s" half of the metric) and
+`call_stage` (POA and ksw2 kernels on bounded samples of configs 4 and 5, after everything else).
 
 --impl reference times the CPU port of the same path (oracle/, OpenMP, all host cores) on a bounded
 sample of the same workload; the reference binary itself cannot be built offline.
