@@ -17,11 +17,17 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def host_sources():
+    """plain C++ translation units of the library (g++: SIMD intrinsics the nvcc front end need not see)"""
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cpp"))
+
+
 def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    deps = sources() + host_sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    deps.append(os.path.join(HERE, "host", "rld.hpp"))
     deps.append(os.path.join(HERE, "..", "include", "svdss_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -37,13 +43,18 @@ def build_lib(force=False, verbose=False):
         objs.append(obj)
         cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src in host_sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src)[:-4] + ".o")
+        objs.append(obj)
+        cmd = ["/usr/bin/g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-pthread", "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
         out, _ = p.communicate()
         log.append(out)
         if p.returncode != 0:
             sys.stderr.write(out)
-            raise RuntimeError("nvcc failed on %s" % src)
+            raise RuntimeError("compiler failed on %s" % src)
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

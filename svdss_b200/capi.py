@@ -56,7 +56,7 @@ EXPORTS = [
     "svb_index_build", "svb_index_from_bwt", "svb_index_load", "svb_index_save", "svb_index_free",
     "svb_index_info", "svb_index_get_bwt", "svb_suffix_array",
     "svb_rank2a", "svb_rank_bench",
-    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
+    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
     "svb_poa_batch", "svb_poa_out_free",
 ]
@@ -398,6 +398,22 @@ def pack_bam4(reads):
             c = np.concatenate([c, np.zeros(1, np.uint8)])
         out[o:o + len(c) // 2] = (c[0::2] << 4) | c[1::2]
     return out, offs, l_qseq
+
+
+def pack2_host(seq4, seq4_offs, l_qseq, threads=0):
+    """svb_pack2_host: BAM-native 4-bit reads -> 2 bits per base on the host.  Returns (packed bytes, byte offsets
+    [n+1], exception flags [n])."""
+    seq4 = np.ascontiguousarray(seq4, np.uint8)
+    seq4_offs = np.ascontiguousarray(seq4_offs, np.int64)
+    l_qseq = np.ascontiguousarray(l_qseq, np.int32)
+    n = len(l_qseq)
+    out_offs = np.zeros(n + 1, np.int64)
+    out_offs[1:] = np.cumsum((l_qseq.astype(np.int64) + 3) // 4)
+    out = np.zeros(max(1, int(out_offs[-1])), np.uint8)
+    exc = np.zeros(max(1, n), np.uint8)
+    check(lib().svb_pack2_host(_ptr(seq4 if len(seq4) else np.zeros(1, np.uint8)), _ptr(seq4_offs), _ptr(l_qseq if n else np.zeros(1, np.int32)), n,
+                               _ptr(out), _ptr(out_offs), _ptr(exc), int(threads)))
+    return out[:int(out_offs[-1])], out_offs, exc[:n]
 
 
 def pack4_device(d_seq_ptr, d_offs_ptr, d_seq4_offs_ptr, n_reads, d_out_ptr, device=0):

@@ -49,3 +49,28 @@ def test_product_does_not_import_oracle():
                 assert "liboracle" not in src, f
                 assert not re.search(r"#\s*include[^\n]*oracle", src), f
                 assert not re.search(r"(dlopen|CDLL|LoadLibrary)[^\n]*oracle", src), f
+
+
+def test_pack2_host_round_trip(L):
+    """svb_pack2_host (host-only utility): 4 bits -> 2 bits per base, exceptions flagged, every length mod 4,
+    reads long enough for the SIMD path, odd input offsets, and a thread count of 1 and of all cores"""
+    rng = np.random.default_rng(8)
+    lens = [0, 1, 2, 3, 4, 5, 6, 7, 8, 63, 64, 65, 127, 128, 129, 130, 131, 257, 1000, 4099, 15001] + [int(x) for x in rng.integers(1, 3000, 40)]
+    reads = [rng.integers(1, 5, size=l).astype(np.uint8) for l in lens]        # nt6 codes A C G T
+    for k in (5, 17, 30, 44):                                                  # reads with an N somewhere (first, last, middle base)
+        if len(reads[k]):
+            reads[k][[0, len(reads[k]) - 1, len(reads[k]) // 2][k % 3]] = 5
+    seq4, offs, lq = capi.pack_bam4(reads)
+    for threads in (1, 0):
+        out, ooffs, exc = capi.pack2_host(seq4, offs, lq, threads=threads)
+        for i, r in enumerate(reads):
+            has_n = bool((r == 5).any())
+            assert bool(exc[i]) == has_n, (i, len(r))
+            if has_n:
+                continue
+            p = out[int(ooffs[i]):int(ooffs[i + 1])]
+            assert len(p) == (len(r) + 3) // 4
+            codes = np.stack([(p >> 6) & 3, (p >> 4) & 3, (p >> 2) & 3, p & 3], axis=1).reshape(-1)[:len(r)]
+            assert np.array_equal(codes + 1, r), (i, len(r))
+            if len(r) % 4:                                                      # pad positions are zero
+                assert not (int(p[-1]) & ((1 << (2 * (4 - len(r) % 4))) - 1))
