@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "unpack2.cuh"   // 2-bit read transport, device side (compiled and emulator-tested; not wired in yet)
 
 struct svb_reads {
   int device = 0;
