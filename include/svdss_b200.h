@@ -150,6 +150,10 @@ SVB_API int svb_pack2_host(const uint8_t* seq4, const int64_t* seq4_offs /* n_re
                            int64_t n_reads, uint8_t* out, const int64_t* out_offs /* n_reads */,
                            uint8_t* exception /* n_reads */, int threads);
 
+/* Test utility for the other half: decode such a batch on `device` (k_unpack2) and return one nt6 byte per base. */
+SVB_API int svb_unpack2_device(const uint8_t* packed, const int64_t* packed_offs /* n_reads+1 */,
+                               const int64_t* offs /* n_reads+1, bases */, int64_t n_reads, int device, uint8_t* out_host);
+
 /* Same search with the batch already resident in HBM (kernel-only measurement; multi-batch reuse). */
 SVB_API int svb_reads_upload(const uint8_t* nt6_concat, const int64_t* offs, int64_t n_reads,
                              int mem, int device, svb_reads_t** out);

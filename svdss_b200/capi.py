@@ -56,7 +56,7 @@ EXPORTS = [
     "svb_index_build", "svb_index_from_bwt", "svb_index_load", "svb_index_save", "svb_index_free",
     "svb_index_info", "svb_index_get_bwt", "svb_suffix_array",
     "svb_rank2a", "svb_rank_bench",
-    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
+    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_unpack2_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
     "svb_poa_batch", "svb_poa_out_free",
 ]
@@ -414,6 +414,16 @@ def pack2_host(seq4, seq4_offs, l_qseq, threads=0):
     check(lib().svb_pack2_host(_ptr(seq4 if len(seq4) else np.zeros(1, np.uint8)), _ptr(seq4_offs), _ptr(l_qseq if n else np.zeros(1, np.int32)), n,
                                _ptr(out), _ptr(out_offs), _ptr(exc), int(threads)))
     return out[:int(out_offs[-1])], out_offs, exc[:n]
+
+
+def unpack2_device(packed, packed_offs, offs, device=0):
+    """svb_unpack2_device: decode a batch packed by pack2_host on the GPU -> nt6 bytes (numpy)."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    packed_offs = np.ascontiguousarray(packed_offs, np.int64)
+    offs = np.ascontiguousarray(offs, np.int64)
+    out = np.zeros(max(1, int(offs[-1])), np.uint8)
+    check(lib().svb_unpack2_device(_ptr(packed if len(packed) else np.zeros(1, np.uint8)), _ptr(packed_offs), _ptr(offs), len(offs) - 1, device, _ptr(out)))
+    return out[:int(offs[-1])]
 
 
 def pack4_device(d_seq_ptr, d_offs_ptr, d_seq4_offs_ptr, n_reads, d_out_ptr, device=0):

@@ -2257,6 +2257,39 @@ int svb_pack4_device(const uint8_t* d_seq, const int64_t* d_offs, const int64_t*
   return SVB_OK;
 }
 
+// Test / bench utility: decode a batch packed 2 bits per base by svb_pack2_host (HOST buffers: packed bytes with
+// their n_reads + 1 byte offsets, the n_reads + 1 base offsets) on `device` and return the nt6 bytes (host,
+// offs[n_reads] bytes).  Reads flagged as exceptions by the packer have no 2-bit form and must not be passed.
+int svb_unpack2_device(const uint8_t* pk, const int64_t* pk_offs, const int64_t* offs, int64_t n_reads, int device, uint8_t* out_host) {
+  if (!pk_offs || !offs || !out_host || n_reads < 0) { set_error("svb_unpack2_device: bad arguments"); return SVB_EINVAL; }
+  SVB_TRY(check_device(device));
+  if (n_reads == 0 || offs[n_reads] - offs[0] <= 0) return SVB_OK;
+  if (!pk || offs[0] != 0 || pk_offs[0] != 0) { set_error("svb_unpack2_device: offsets must start at 0"); return SVB_EINVAL; }
+  const int64_t total = offs[n_reads], pbytes = pk_offs[n_reads];
+  uint8_t *d_pk = nullptr, *d_out = nullptr;
+  int64_t *d_po = nullptr, *d_o = nullptr;
+  int rc = SVB_OK;
+  auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == SVB_OK) { set_error("svb_unpack2_device: %s", cudaGetErrorString(e)); rc = SVB_ECUDA; } };
+  fail(cudaMalloc((void**)&d_pk, (size_t)pbytes + 16));
+  fail(cudaMalloc((void**)&d_out, (size_t)total + 64));
+  fail(cudaMalloc((void**)&d_po, (size_t)(n_reads + 1) * 8));
+  fail(cudaMalloc((void**)&d_o, (size_t)(n_reads + 1) * 8));
+  if (rc == SVB_OK) {
+    fail(cudaMemset(d_pk + pbytes, 0, 16));
+    fail(cudaMemcpy(d_pk, pk, (size_t)pbytes, cudaMemcpyHostToDevice));
+    fail(cudaMemcpy(d_po, pk_offs, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice));
+    fail(cudaMemcpy(d_o, offs, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice));
+  }
+  if (rc == SVB_OK) {
+    k_unpack2<<<(unsigned)std::min<int64_t>((n_reads + 3) / 4, 148 * 8), 128>>>(d_pk, d_po, d_o, n_reads, total, d_out);
+    fail(cudaGetLastError());
+    fail(cudaDeviceSynchronize());
+    fail(cudaMemcpy(out_host, d_out, (size_t)total, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_pk); cudaFree(d_out); cudaFree(d_po); cudaFree(d_o);
+  return rc;
+}
+
 void svb_sfs_out_free(svb_sfs_out_t* out) {
   if (!out) return;
   free(out->offs); free(out->qs); free(out->len);
