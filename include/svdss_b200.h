@@ -150,6 +150,13 @@ SVB_API int svb_pack2_host(const uint8_t* seq4, const int64_t* seq4_offs /* n_re
                            int64_t n_reads, uint8_t* out, const int64_t* out_offs /* n_reads */,
                            uint8_t* exception /* n_reads */, int threads);
 
+/* The streamed form of the same packing: the part of reads r_lo..r_hi inside base positions [o, o + nb) of the
+ * concatenated batch, widened to whole packed bytes, into `stage` = bytes [*pa2, *pe2) of the packed layout;
+ * positions of bases without a 2-bit form (they all decode to N) go to exc_pos (*n_exc of them). */
+SVB_API int svb_pack2_chunk(const uint8_t* seq4, const int64_t* seq4_offs, const int64_t* offs, const int64_t* packed_offs,
+                            int64_t r_lo, int64_t r_hi, int64_t o, int64_t nb, uint8_t* stage, int64_t stage_cap,
+                            int64_t* pa2, int64_t* pe2, int64_t* exc_pos, int64_t exc_cap, int64_t* n_exc, int threads);
+
 /* Test utility for the other half: decode such a batch on `device` (k_unpack2) and return one nt6 byte per base. */
 SVB_API int svb_unpack2_device(const uint8_t* packed, const int64_t* packed_offs /* n_reads+1 */,
                                const int64_t* offs /* n_reads+1, bases */, int64_t n_reads, int device, uint8_t* out_host);

@@ -56,7 +56,7 @@ EXPORTS = [
     "svb_index_build", "svb_index_from_bwt", "svb_index_load", "svb_index_save", "svb_index_free",
     "svb_index_info", "svb_index_get_bwt", "svb_suffix_array",
     "svb_rank2a", "svb_rank_bench",
-    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_unpack2_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
+    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_pack2_chunk", "svb_unpack2_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
     "svb_poa_batch", "svb_poa_out_free",
 ]

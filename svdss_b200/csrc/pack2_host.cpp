@@ -115,3 +115,68 @@ extern "C" SVB_API int svb_pack2_host(const uint8_t* seq4, const int64_t* seq4_o
   for (auto& x : th) x.join();
   return SVB_OK;
 }
+
+// The streamed form: one chunk of the batch = the base positions [o, o + nb) of the concatenated reads (the unit
+// the search kernel waits for).  Packs, with all host threads, the part of every read r_lo..r_hi that falls into
+// the chunk -- widened to whole packed bytes, so neighbouring chunks may both carry a byte they share -- into
+// `stage`, which then holds the bytes [*pa2, *pe2) of the batch's packed layout (read r at pk_offs[r]).  Bases
+// that are not A, C, G or T have no 2-bit form: their positions (all of them decode to nt6 N) are appended to
+// exc_pos, to be patched on the device after the chunk has been decoded; *n_exc receives how many (if it
+// exceeds exc_cap the chunk should travel in the 4-bit form instead).
+extern "C" SVB_API int svb_pack2_chunk(const uint8_t* seq4, const int64_t* seq4_offs, const int64_t* offs, const int64_t* pk_offs,
+                                       int64_t r_lo, int64_t r_hi, int64_t o, int64_t nb, uint8_t* stage, int64_t stage_cap,
+                                       int64_t* pa2, int64_t* pe2, int64_t* exc_pos, int64_t exc_cap, int64_t* n_exc, int threads) {
+  if (!seq4 || !seq4_offs || !offs || !pk_offs || !stage || !pa2 || !pe2 || !n_exc || r_lo < 0 || r_hi < r_lo || nb <= 0) return SVB_EINVAL;
+  auto span = [&](int64_t r, int64_t& q0, int64_t& q1, int64_t& l) {   // packed bytes [q0, q1) of read r hold its bases inside the chunk
+    l = offs[r + 1] - offs[r];
+    const int64_t j0 = o > offs[r] ? o - offs[r] : 0, j1 = (o + nb < offs[r + 1] ? o + nb : offs[r + 1]) - offs[r];
+    if (j1 <= j0) { q0 = q1 = 0; return false; }
+    q0 = j0 >> 2; q1 = (j1 + 3) >> 2;
+    return true;
+  };
+  int64_t q0, q1, l;
+  *pa2 = *pe2 = pk_offs[r_lo];
+  bool any = false;
+  for (int64_t r = r_lo; r <= r_hi; ++r)
+    if (span(r, q0, q1, l)) { if (!any) *pa2 = pk_offs[r] + q0; *pe2 = pk_offs[r] + q1; any = true; }
+  *n_exc = 0;
+  if (!any) return SVB_OK;
+  if (*pe2 - *pa2 > stage_cap) return SVB_ERANGE;
+  const int64_t base = *pa2;
+  unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  const int64_t CH = 128, n = r_hi - r_lo + 1;
+  std::atomic<int64_t> next(0), n_bad(0);
+  std::vector<std::vector<int64_t>> bad_reads(nt);
+  auto worker = [&](unsigned t) {
+    for (;;) {
+      const int64_t k0 = next.fetch_add(CH);
+      if (k0 >= n) return;
+      for (int64_t r = r_lo + k0; r < r_lo + (k0 + CH < n ? k0 + CH : n); ++r) {
+        int64_t a, b, len;
+        if (!span(r, a, b, len)) continue;
+        const int64_t bases = (len < 4 * b ? len : 4 * b) - 4 * a;
+        if (!pack_read(seq4 + seq4_offs[r] + 2 * a, bases, stage + (pk_offs[r] + a - base))) bad_reads[t].push_back(r);
+      }
+    }
+  };
+  if (nt == 1 || n <= CH) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(worker, t);
+    for (auto& x : th) x.join();
+  }
+  // the rare reads with other codes: their positions inside the chunk, base by base
+  int64_t m = 0;
+  for (auto& v : bad_reads)
+    for (int64_t r : v) {
+      const uint8_t* in = seq4 + seq4_offs[r];
+      const int64_t j0 = o > offs[r] ? o - offs[r] : 0, j1 = (o + nb < offs[r + 1] ? o + nb : offs[r + 1]) - offs[r];
+      for (int64_t j = j0; j < j1; ++j) {
+        const unsigned c = (j & 1) ? (in[j >> 1] & 15u) : (unsigned)(in[j >> 1] >> 4);
+        if (C2[c] & 0x80) { if (exc_pos && m < exc_cap) exc_pos[m] = offs[r] + j; ++m; }
+      }
+    }
+  *n_exc = m;
+  return SVB_OK;
+}

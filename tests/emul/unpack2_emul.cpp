@@ -23,3 +23,17 @@ extern "C" int emul_unpack2(const uint8_t* pk, const int64_t* pk_offs, const int
   blockDim.x = 32; blockIdx.x = 0; gridDim.x = 1;
   return emu::run_warp(body, &j) ? 0 : -1;
 }
+
+// one chunk of the streamed pipeline: reads r_lo..r_hi against output positions [A, B)
+struct RangeJob { const uint8_t* pk; const int64_t* pk_offs; const int64_t* offs; int64_t r_lo, r_hi, A, B; uint8_t* out; };
+static void range_body(void* a) {
+  RangeJob* j = static_cast<RangeJob*>(a);
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = j->r_lo; r <= j->r_hi; ++r) svb::unpack2_read(j->pk, j->pk_offs, j->offs, r, j->A, j->B, j->out, lane);
+}
+extern "C" int emul_unpack2_range(const uint8_t* pk, const int64_t* pk_offs, const int64_t* offs, int64_t r_lo, int64_t r_hi, int64_t A, int64_t B,
+                                  uint8_t* out) {
+  RangeJob j = {pk, pk_offs, offs, r_lo, r_hi, A, B, out};
+  blockDim.x = 32; blockIdx.x = 0; gridDim.x = 1;
+  return emu::run_warp(range_body, &j) ? 0 : -1;
+}
