@@ -409,11 +409,39 @@ def run_ours(args):
             out["call_stage"] = call_stage_sample(capi)
         except Exception as e:
             out["call_stage"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            out["host_pack2"] = host_pack2_rate(capi, host4.numpy(), seq4_offs, l_qseq)
+        except Exception as e:
+            out["host_pack2"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def host_pack2_rate(capi, host4_np, seq4_offs, l_qseq, n=60000):
+    """How fast this host re-packs 4-bit reads to 2 bits (svb_pack2_host, all threads): GB/s of 4-bit input on
+    the first n reads of the batch.  The number the 2-bit transport stands or falls with:
+    above the PCIe rate of the e2e arm it gains, at twice that rate it halves the copy."""
+    n = int(min(n, len(l_qseq)))
+    lq = np.ascontiguousarray(l_qseq[:n], np.int32)
+    so = np.ascontiguousarray(seq4_offs[:n + 1], np.int64)
+    oo = np.zeros(n + 1, np.int64)
+    oo[1:] = np.cumsum((lq.astype(np.int64) + 3) // 4)
+    out = np.ones(max(1, int(oo[-1])), np.uint8)          # touched before the timed calls
+    exc = np.ones(max(1, n), np.uint8)
+    L = capi.lib()
+    best = None
+    for _ in range(3):
+        t = time.perf_counter()
+        rc = L.svb_pack2_host(capi._ptr(host4_np), capi._ptr(so), capi._ptr(lq), n, capi._ptr(out), capi._ptr(oo), capi._ptr(exc), 0)
+        dt = time.perf_counter() - t
+        if rc != 0:
+            raise RuntimeError("svb_pack2_host failed: %d" % rc)
+        best = dt if best is None else min(best, dt)
+    nbytes = int(so[-1] - so[0])
+    return {"GB_s_of_4bit_input": nbytes / best / 1e9, "sample_bytes": nbytes, "threads": os.cpu_count(), "reads_with_other_codes": int(exc[:n].sum())}
 
 
 def call_stage_sample(capi, n_clusters=1500, n_pairs=20000):
