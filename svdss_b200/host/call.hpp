@@ -402,9 +402,9 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
   // filter_sv_chains / sort (stable here; the reference's std::sort leaves ties unspecified)
   std::vector<SV> svs;
   std::vector<std::string> sam;
-  for (size_t t = 0; t < T; ++t) {
-    svs.insert(svs.begin(), p_svs[t].begin(), p_svs[t].end());
-    sam.insert(sam.begin(), p_sam[t].begin(), p_sam[t].end());
+  for (size_t slot = 0; slot < T; ++slot) {
+    svs.insert(svs.begin(), p_svs[slot].begin(), p_svs[slot].end());
+    sam.insert(sam.begin(), p_sam[slot].begin(), p_sam[slot].end());
   }
   std::stable_sort(svs.begin(), svs.end());
   {  // clean_dups, caller.cpp:409-427

@@ -25,6 +25,7 @@
 // gtq; sv.cpp:7-27) print as 0.
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <map>
 #include <string>
