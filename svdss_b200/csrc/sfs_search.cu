@@ -106,6 +106,16 @@ struct SearchParams {
   uint8_t* seq_w;            // = seq, writable
   int64_t total;
   int n_chunks, n_unpack;
+  // 2-bit transport (SVB_STREAM_PACK2, k_sfs_search_mop<.., .., true>): the host re-packs every chunk to 2 bits per
+  // base (svb_pack2_chunk) before it crosses PCIe; chunk_mode[c], written before arrived[c], says what arrived:
+  // 2 = 2-bit bytes in pk2 (read r at pk2_offs[r]) plus exc_n[c] positions in exc_pos[c * exc_cap ...] to patch to
+  // N once the chunk is decoded, 1 = the 4-bit bytes in seq4 as above (a chunk with too many such positions)
+  const uint8_t* pk2;
+  const int64_t* pk2_offs;
+  const unsigned int* chunk_mode;
+  const int64_t* exc_pos;
+  const unsigned int* exc_n;
+  int exc_cap;
   // two-phase launch of k_sfs_search_mop: when the work queue runs dry the main kernel parks every
   // unfinished walk in cont[] and ends; the tail kernel finishes them one per WARP (see Cont)
   struct Cont* cont;
@@ -978,6 +988,45 @@ __device__ void unpack_cta_loop(const SearchParams& P) {
   }
 }
 
+// the same for the 2-bit transport: per chunk the decoder the host chose, and the last CTA to finish a chunk
+// patches the positions that have no 2-bit form before it raises the flag
+__device__ void unpack_cta_loop2(const SearchParams& P) {
+  __shared__ unsigned int s_last;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)P.n_unpack * (blockDim.x >> 5);
+  const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (int c = 0; c < P.n_chunks; ++c) {
+    if (!wait_chunk(P.arrived + c, P.stats + 3)) return;
+    __threadfence();
+    const unsigned int mode = __ldcg(P.chunk_mode + c);
+    const int64_t A = (int64_t)c * P.chunk_bytes, B = min(A + P.chunk_bytes, P.total);
+    for (int64_t r = P.chunk_r0[c] + w0; r <= P.chunk_r1[c]; r += nwarps) {
+      if (mode == 2u) unpack2_read(P.pk2, P.pk2_offs, P.offs, r, A, B, P.seq_w, lane);
+      else unpack4_read(P.seq4, P.seq4_offs, P.offs, r, A, B, P.seq_w, lane);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(P.chunk_done + c, 1u) == (unsigned)P.n_unpack - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {   // every other CTA has stored and fenced its share of the chunk
+      __threadfence();
+      if (mode == 2u) {
+        const unsigned int n = __ldcg(P.exc_n + c);
+        const int64_t* ep = P.exc_pos + (int64_t)c * P.exc_cap;
+        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) P.seq_w[__ldcg(ep + i)] = 5;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(P.ready_w + c) = 1u;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // 32-byte window at an arbitrary byte address: three aligned 16-byte loads
 struct Win32 { uint4 q0, q1, q2; int sh; };   // sh = byte offset of the window inside q0 (0..15)
 __device__ __forceinline__ void load32(const uint8_t* base, int64_t a, Win32& w, int64_t min_q) {
@@ -1180,7 +1229,7 @@ enum : int { ST_START = 0, ST_WALK = 1, ST_KMT = 2 };
 // TAIL = true: the tail kernel: TAIL_OWNERS lanes of a warp own one parked walk each, the other lanes
 // only serve the cooperative steps (located-match compare, sprint, block staging) -- few walks per warp
 // keep an iteration short, which is what a long serial walk needs.
-template <int MINB, bool TAIL>
+template <int MINB, bool TAIL, bool PK2 = false>   // PK2: the unpacking CTAs speak the 2-bit transport (a separate instantiation)
 __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const SearchParams P) {
   __shared__ __align__(128) uint4 stage[TMA_WARPS * 32 * 16];  // [warp][lane][2 blocks][8 slices]
   __shared__ uint8_t pend_all[TMA_WARPS * 32];                  // per warp: lanes with an extension pending
@@ -1192,7 +1241,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
   // inside the hot loops -- 31 % of the tail kernel's instructions in profiles/r01k_sfs_tail_lines.txt
   if (TAIL) asm volatile("" : "+r"(lane), "+r"(warp_stage_s), "+l"(my));
   if (P.n_unpack > 0 && (int)blockIdx.x < P.n_unpack) {   // packed streamed batch: this CTA feeds the others
-    unpack_cta_loop(P);
+    if (PK2) unpack_cta_loop2(P); else unpack_cta_loop(P);
     return;
   }
   if (!TAIL && threadIdx.x == 0) atomicMin(P.stats + 4, globaltimer_ns());
@@ -1792,7 +1841,28 @@ struct StreamSrc {
   unsigned int* d_done = nullptr;       // per chunk: unpacking CTAs finished
   int64_t* d_chunk_r = nullptr;         // [2][n_chunks] first / last read of each chunk
   int n_unpack = 0;
+  // 2-bit transport (SVB_STREAM_PACK2=1): every chunk is re-packed on the host (svb_pack2_chunk) into one of two
+  // pinned staging buffers while the previous chunk is on the wire
+  bool pack2 = false;
+  uint8_t* d_pk2 = nullptr;             // device: 2-bit bytes of the whole batch
+  int64_t* d_pk2_offs = nullptr;
+  const int64_t* h_pk2_offs = nullptr;  // n_reads + 1 (host)
+  unsigned int* d_mode = nullptr;       // per chunk: 2 = 2-bit bytes arrived, 1 = 4-bit bytes arrived
+  int64_t* d_exc_pos = nullptr;         // [n_chunks][exc_cap]
+  unsigned int* d_exc_n = nullptr;
+  int exc_cap = 0;
+  uint8_t* h_stage[2] = {nullptr, nullptr};   // pinned
+  int64_t stage_cap = 0;
+  int64_t* h_exc[2] = {nullptr, nullptr};     // pinned, exc_cap positions each
+  unsigned int* h_mode = nullptr;             // pinned, per chunk (the copy engine reads them later)
+  unsigned int* h_exc_n = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};     // staging buffer k is free again
+  mutable int64_t sent_bytes = 0;             // payload that crossed PCIe in this mode
 };
+
+extern "C" int svb_pack2_chunk(const uint8_t* seq4, const int64_t* seq4_offs, const int64_t* offs, const int64_t* pk_offs,
+                               int64_t r_lo, int64_t r_hi, int64_t o, int64_t nb, uint8_t* stage, int64_t stage_cap,
+                               int64_t* pa2, int64_t* pe2, int64_t* exc_pos, int64_t exc_cap, int64_t* n_exc, int threads);
 
 static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int assemble, svb_sfs_out_t* out,
                       cudaStream_t st, const StreamSrc* src = nullptr) {
@@ -1824,6 +1894,11 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   const bool two_phase = !(e2p && *e2p == '0');
   if (cfgG == -2) {
     SVB_TRY(persistent_grid(k_sfs_search_mop<tma_minb, false>, TMA_WARPS * 32, d.device, &grid));
+    if (src && src->pack2) {   // its own instantiation: its own occupancy
+      int grid2 = 0;
+      SVB_TRY(persistent_grid(k_sfs_search_mop<tma_minb, false, true>, TMA_WARPS * 32, d.device, &grid2));
+      grid = std::min(grid, grid2);
+    }
     SVB_TRY(persistent_grid(k_sfs_search_mop<tail_minb, true>, TMA_WARPS * 32, d.device, &tail_grid));
   } else if (cfgG == 0) {
     SVB_TRY(persistent_grid(k_sfs_search_tma<tma_minb, 0>, TMA_WARPS * 32, d.device, &grid));
@@ -1855,6 +1930,10 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
         P.seq4 = src->d_seq4; P.seq4_offs = src->d_seq4_offs; P.arrived = src->d_arrived; P.ready_w = src->d_ready;
         P.chunk_done = src->d_done; P.chunk_r0 = src->d_chunk_r; P.chunk_r1 = src->d_chunk_r + src->n_chunks;
         P.seq_w = R->d_seq; P.total = src->total; P.n_chunks = (int)src->n_chunks; P.n_unpack = src->n_unpack;
+        if (src->pack2) {
+          P.pk2 = src->d_pk2; P.pk2_offs = src->d_pk2_offs; P.chunk_mode = src->d_mode; P.exc_pos = src->d_exc_pos;
+          P.exc_n = src->d_exc_n; P.exc_cap = src->exc_cap;
+        }
       }
     }
     SVB_CUDA(cudaEventRecord(e0, st));
@@ -1864,7 +1943,8 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
         P.cont = static_cast<Cont*>(S.d_cont); P.n_cont = S.d_ctr + 10; P.dry = reinterpret_cast<unsigned int*>(S.d_ctr + 11);
         P.last_ready = (src && attempt == 0) ? src->d_ready + (src->n_chunks - 1) : nullptr;
       }
-      k_sfs_search_mop<tma_minb, false><<<grid, TMA_WARPS * 32, 0, st>>>(P);
+      if (src && attempt == 0 && src->pack2) k_sfs_search_mop<tma_minb, false, true><<<grid, TMA_WARPS * 32, 0, st>>>(P);
+      else k_sfs_search_mop<tma_minb, false><<<grid, TMA_WARPS * 32, 0, st>>>(P);
       if (two_phase) {
         SearchParams Q = P;
         Q.work = S.d_ctr + 12; Q.ready = nullptr; Q.n_unpack = 0; Q.dry = nullptr;
@@ -1898,7 +1978,33 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
           const int64_t pa = src->h_seq4_offs[r_lo] + (std::max<int64_t>(o - ho[r_lo], 0) >> 1);
           const int64_t last = std::min(o + nb, ho[r_hi + 1]) - 1 - ho[r_hi];   // last base of r_hi in the chunk
           const int64_t pe = last >= 0 ? src->h_seq4_offs[r_hi] + (last >> 1) + 1 : src->h_seq4_offs[r_hi];
-          if (pe > pa) SVB_CUDA(cudaMemcpyAsync(src->d_seq4 + pa, src->host + pa, pe - pa, cudaMemcpyHostToDevice, src->copy_stream));
+          bool sent = false;
+          if (src->pack2) {
+            // re-pack this chunk to 2 bits per base into the staging buffer the copy before last has released
+            const int k = (int)(c & 1);
+            SVB_CUDA(cudaEventSynchronize(src->ev[k]));
+            int64_t pa2 = 0, pe2 = 0, n_exc = 0;
+            const int prc = svb_pack2_chunk(src->host, src->h_seq4_offs, ho, src->h_pk2_offs, r_lo, r_hi, o, nb, src->h_stage[k], src->stage_cap,
+                                            &pa2, &pe2, src->h_exc[k], src->exc_cap, &n_exc, 0);
+            if (prc == SVB_OK && n_exc <= src->exc_cap) {
+              src->h_mode[c] = 2u; src->h_exc_n[c] = (unsigned int)n_exc;
+              if (pe2 > pa2) SVB_CUDA(cudaMemcpyAsync(src->d_pk2 + pa2, src->h_stage[k], pe2 - pa2, cudaMemcpyHostToDevice, src->copy_stream));
+              if (n_exc) SVB_CUDA(cudaMemcpyAsync(src->d_exc_pos + c * src->exc_cap, src->h_exc[k], n_exc * 8, cudaMemcpyHostToDevice, src->copy_stream));
+              SVB_CUDA(cudaEventRecord(src->ev[k], src->copy_stream));
+              src->sent_bytes += (pe2 - pa2) + n_exc * 8 + 12;
+              sent = true;
+            } else {   // too many such positions (or a chunk larger than the staging buffer): this chunk travels as it is
+              src->h_mode[c] = 1u; src->h_exc_n[c] = 0u;
+            }
+          }
+          if (!sent) {
+            if (pe > pa) SVB_CUDA(cudaMemcpyAsync(src->d_seq4 + pa, src->host + pa, pe - pa, cudaMemcpyHostToDevice, src->copy_stream));
+            src->sent_bytes += (pe - pa) + 12;
+          }
+          if (src->pack2) {
+            SVB_CUDA(cudaMemcpyAsync(src->d_mode + c, src->h_mode + c, sizeof(unsigned int), cudaMemcpyHostToDevice, src->copy_stream));
+            SVB_CUDA(cudaMemcpyAsync(src->d_exc_n + c, src->h_exc_n + c, sizeof(unsigned int), cudaMemcpyHostToDevice, src->copy_stream));
+          }
           SVB_CUDA(cudaMemcpyAsync(src->d_arrived + c, src->h_one, sizeof(unsigned int), cudaMemcpyHostToDevice, src->copy_stream));
         }
       }
@@ -2062,7 +2168,7 @@ static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const 
   src.packed = seq4_offs != nullptr;
   src.n_reads = n_reads;
   int64_t* d_s4o = nullptr;
-  std::vector<int64_t> s4rb, chunk_r;
+  std::vector<int64_t> s4rb, chunk_r, pk2o;
   const int64_t packed_total = seq4_offs ? seq4_offs[n_reads] - seq4_offs[0] : 0;
   src.chunk_bytes = (int64_t)128 << 20;
   if (const char* e = getenv("SVB_STREAM_CHUNK_BYTES")) { long long v = atoll(e); if (v >= 4096) src.chunk_bytes = (v + 63) & ~63LL; }
@@ -2125,6 +2231,32 @@ static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const 
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device);
       src.n_unpack = sms;   // one CTA in nine: ~23 GB of streaming traffic per 1 M reads, far below their share
       if (const char* e = getenv("SVB_UNPACK_CTAS")) src.n_unpack = std::max(1, atoi(e));
+      if (const char* e = getenv("SVB_STREAM_PACK2")) src.pack2 = atoi(e) != 0;
+      if (src.pack2) {
+        // 2-bit transport: packed layout (read r at pk2_offs[r], (l + 3) / 4 bytes), staging, per-chunk mode / patch lists
+        pk2o.resize((size_t)n_reads + 1);
+        pk2o[0] = 0;
+        int64_t lmax = 0;
+        for (int64_t i = 0; i < n_reads; ++i) { const int64_t l = rb[i + 1] - rb[i]; pk2o[i + 1] = pk2o[i] + (l + 3) / 4; lmax = std::max(lmax, l); }
+        src.h_pk2_offs = pk2o.data();
+        src.exc_cap = 1 << 16;   // positions a chunk may patch before it falls back to the 4-bit form (SVB_PACK2_EXC_CAP: tests)
+        if (const char* e = getenv("SVB_PACK2_EXC_CAP")) src.exc_cap = std::max(1, atoi(e));
+        src.stage_cap = src.chunk_bytes / 4 + 2 * ((lmax + 3) / 4) + 4096 + (chunk_r.empty() ? 0 : [&]() { int64_t m = 0; for (int64_t c = 0; c < src.n_chunks; ++c) m = std::max(m, chunk_r[src.n_chunks + c] - chunk_r[c] + 1); return m; }());
+        SCHECK(pmalloc((void**)&src.d_pk2, (size_t)pk2o[n_reads] + 16, comp));
+        SCHECK(pmalloc((void**)&src.d_pk2_offs, (n_reads + 1) * 8, comp));
+        SCHECK(pmalloc((void**)&src.d_mode, src.n_chunks * 4, comp));
+        SCHECK(pmalloc((void**)&src.d_exc_n, src.n_chunks * 4, comp));
+        SCHECK(pmalloc((void**)&src.d_exc_pos, (size_t)src.n_chunks * src.exc_cap * 8, comp));
+        SCHECK(cudaMemcpyAsync(src.d_pk2_offs, pk2o.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, comp));
+        SCHECK(cudaMemsetAsync(src.d_pk2 + pk2o[n_reads], 0, 16, comp));
+        for (int k = 0; k < 2; ++k) {
+          SCHECK(cudaHostAlloc((void**)&src.h_stage[k], (size_t)src.stage_cap, cudaHostAllocDefault));
+          SCHECK(cudaHostAlloc((void**)&src.h_exc[k], (size_t)src.exc_cap * 8, cudaHostAllocDefault));
+          SCHECK(cudaEventCreateWithFlags(&src.ev[k], cudaEventDisableTiming));
+        }
+        SCHECK(cudaHostAlloc((void**)&src.h_mode, (size_t)src.n_chunks * 4, cudaHostAllocDefault));
+        SCHECK(cudaHostAlloc((void**)&src.h_exc_n, (size_t)src.n_chunks * 4, cudaHostAllocDefault));
+      }
     }
   }
   if (!stream) {   // small packed batch: copy, unpack, then search the resident reads
@@ -2142,7 +2274,7 @@ static int sfs_batch_streamed(const svb_index_t* idx, const uint8_t* seq, const 
   if (rc == SVB_OK) rc = run_search(d, &R, overlap, assemble, out, comp, &src);
   if (rc == SVB_OK) {
     SCHECK(cudaStreamSynchronize(src.copy_stream));
-    out->h2d_bytes = (src.packed ? packed_total + (n_reads + 1) * 8 : R.total) + (n_reads + 1) * 8 + src.n_chunks * 4;
+    out->h2d_bytes = (src.pack2 ? src.sent_bytes + (n_reads + 1) * 16 : src.packed ? packed_total + (n_reads + 1) * 8 : R.total) + (n_reads + 1) * 8 + src.n_chunks * 4;
     out->launches += 2;  // read keys + order sort
   }
 done:
@@ -2151,10 +2283,18 @@ done:
   if (comp) {
     pfree(R.d_seq, comp); pfree(R.d_offs, comp); pfree(R.d_order, comp); pfree(R.d_sched, comp); pfree(src.d_ready, comp);
     pfree(src.d_seq4, comp); pfree(d_s4o, comp); pfree(src.d_chunk_r, comp); pfree(src.d_arrived, comp); pfree(src.d_done, comp);
+    pfree(src.d_pk2, comp); pfree(src.d_pk2_offs, comp); pfree(src.d_mode, comp); pfree(src.d_exc_n, comp); pfree(src.d_exc_pos, comp);
     cudaStreamSynchronize(comp);
     cudaStreamDestroy(comp);
   }
   if (src.h_one) cudaFreeHost(src.h_one);
+  for (int k = 0; k < 2; ++k) {
+    if (src.h_stage[k]) cudaFreeHost(src.h_stage[k]);
+    if (src.h_exc[k]) cudaFreeHost(src.h_exc[k]);
+    if (src.ev[k]) cudaEventDestroy(src.ev[k]);
+  }
+  if (src.h_mode) cudaFreeHost(src.h_mode);
+  if (src.h_exc_n) cudaFreeHost(src.h_exc_n);
   return rc;
 }
 
