@@ -405,10 +405,9 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(idx, host_np, read_offs, res[-1], assemble, args)
     if rank == 0 and world == 1 and not args.no_call_stage:
-        try:     # after everything the line is judged on; a failure here must not cost the line
-            out["call_stage"] = call_stage_sample(capi)
-        except Exception as e:
-            out["call_stage"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        # after everything the line is judged on, in a child process with a time limit: neither an exception
+        # nor a crash or a hang of these kernels may cost the line
+        out["call_stage"] = call_stage_child(local)
         try:
             out["host_pack2"] = host_pack2_rate(capi, host4.numpy(), seq4_offs, l_qseq)
         except Exception as e:
@@ -442,6 +441,24 @@ def host_pack2_rate(capi, host4_np, seq4_offs, l_qseq, n=60000):
         best = dt if best is None else min(best, dt)
     nbytes = int(so[-1] - so[0])
     return {"GB_s_of_4bit_input": nbytes / best / 1e9, "sample_bytes": nbytes, "threads": os.cpu_count(), "reads_with_other_codes": int(exc[:n].sum())}
+
+
+def call_stage_child(local, limit_s=240):
+    """call_stage_sample() in a child process on the same GPU (`bench.py --call-stage-only`)."""
+    try:     # device 0 of the child = the only GPU this (world == 1) run uses
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--call-stage-only"], capture_output=True, text=True,
+                           timeout=limit_s, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"error": "call-stage sample did not finish within %d s" % limit_s}
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+    for line in reversed(r.stdout.splitlines()):
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except ValueError:
+                break
+    return {"error": "child exit %d: %s" % (r.returncode, (r.stderr or r.stdout)[-400:])}
 
 
 def call_stage_sample(capi, n_clusters=1500, n_pairs=20000):
@@ -577,7 +594,16 @@ def main():
     ap.add_argument("--no-call-stage", action="store_true", help="skip the POA / ksw2 samples of the call stage")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-sample", type=int, default=20000)
+    ap.add_argument("--call-stage-only", action="store_true", help="print the call_stage object alone (the child of the main run)")
     args = ap.parse_args()
+    if args.call_stage_only:
+        from svdss_b200 import capi
+        try:
+            obj = call_stage_sample(capi)
+        except Exception as e:
+            obj = {"error": "%s: %s" % (type(e).__name__, e)}
+        print(json.dumps(obj), flush=True)
+        return
     _, world, _ = dist_env()
     if world != args.gpus and args.impl == "ours" and world == 1 and args.gpus > 1:
         # convenience: relaunch under torchrun

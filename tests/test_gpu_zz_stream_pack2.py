@@ -49,6 +49,6 @@ print("STREAM_PACK2_OK h2d bytes 4-bit %d, 2-bit %d" % (a.h2d_bytes, b.h2d_bytes
 
 def test_two_bit_transport_equals_four_bit_transport():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", CHILD], cwd=root, capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, "-c", CHILD], cwd=root, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0 and "STREAM_PACK2_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     print(r.stdout.strip())
