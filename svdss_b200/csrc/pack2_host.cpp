@@ -1,7 +1,7 @@
 // Host-side re-packing of BAM-native 4-bit reads to 2 bits per base (building block for the next e2e step:
 // the search is PCIe-bound end to end -- 7.6 GB of 4-bit reads per million 15 kb reads at ~46 GB/s -- so the
 // lever left is fewer bytes on the wire).  Host threads pack chunk k+1 while chunk k is in
-// flight; the GPU side (not wired in yet) decodes 2 bits -> nt6 where it decodes 4 bits today.
+// flight; the GPU side (unpack2.cuh, used by the streamed search when SVB_STREAM_PACK2=1) decodes 2 bits -> nt6.
 //
 // Layout: read r occupies (l + 3) / 4 packed bytes at out_offs[r] (every read starts on an output byte): every
 // input byte (two bases, first in the high nibble, htslib nt16 codes) becomes one nibble (c2(first) << 2 |

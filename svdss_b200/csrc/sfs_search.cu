@@ -23,7 +23,7 @@
 #include <cstring>
 
 #include "common.cuh"
-#include "unpack2.cuh"   // 2-bit read transport, device side (compiled and emulator-tested; not wired in yet)
+#include "unpack2.cuh"   // 2-bit read transport, device side (emulator-tested; used by unpack_cta_loop2 when SVB_STREAM_PACK2=1)
 
 struct svb_reads {
   int device = 0;

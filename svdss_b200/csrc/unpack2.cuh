@@ -4,7 +4,7 @@
 // unpack of sfs_search.cu (unpack16 / unpack4_read / k_unpack4): a warp per read, lanes own 16-byte aligned
 // groups of the OUTPUT so that stores are coalesced 16-byte stores, the ragged head and tail of a range go base
 // by base, and a range [A, B) of output positions can be requested so that the streamed pipeline can decode
-// chunk by chunk.  Not wired into svb_sfs_batch_bam4 yet; free of host code so that
+// chunk by chunk (unpack_cta_loop2 of sfs_search.cu does, with SVB_STREAM_PACK2=1; off by default).  Free of host code so that
 // tests/emul compiles it for the CPU.
 #pragma once
 #include <stdint.h>
