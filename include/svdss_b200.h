@@ -161,6 +161,16 @@ SVB_API int svb_pack2_chunk(const uint8_t* seq4, const int64_t* seq4_offs, const
 SVB_API int svb_unpack2_device(const uint8_t* packed, const int64_t* packed_offs /* n_reads+1 */,
                                const int64_t* offs /* n_reads+1, bases */, int64_t n_reads, int device, uint8_t* out_host);
 
+/* BGZF members inflated on the GPU (the reference inflates through htslib's bgzf_mt threads,
+ * ping_pong.cpp:249, clusterer.cpp:13).  The caller walks the gzip headers and passes the raw-deflate payloads of
+ * n_members members back to back (member m = comp[in_offs[m], in_offs[m+1])) and where their ISIZE bytes go
+ * (out_host[out_offs[m], out_offs[m+1]), at most 64 KiB each); both offset arrays start at 0.  status_host (optional, one per member): 0 or
+ * the reason a member did not inflate; any non-zero status makes the call return SVB_EIO after the copies.
+ * kernel_ms (optional): device time of the inflate kernel.  Building block: host/io.hpp still inflates on the host. */
+SVB_API int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_offs /* n_members+1 */,
+                                    const int64_t* out_offs /* n_members+1 */, int64_t n_members, int device,
+                                    uint8_t* out_host, int32_t* status_host, float* kernel_ms);
+
 /* Same search with the batch already resident in HBM (kernel-only measurement; multi-batch reuse). */
 SVB_API int svb_reads_upload(const uint8_t* nt6_concat, const int64_t* offs, int64_t n_reads,
                              int mem, int device, svb_reads_t** out);

@@ -56,7 +56,7 @@ EXPORTS = [
     "svb_index_build", "svb_index_from_bwt", "svb_index_load", "svb_index_save", "svb_index_free",
     "svb_index_info", "svb_index_get_bwt", "svb_suffix_array",
     "svb_rank2a", "svb_rank_bench",
-    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_pack2_chunk", "svb_unpack2_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
+    "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_pack2_chunk", "svb_unpack2_device", "svb_bgzf_inflate_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
     "svb_poa_batch", "svb_poa_out_free",
 ]
@@ -414,6 +414,53 @@ def pack2_host(seq4, seq4_offs, l_qseq, threads=0):
     check(lib().svb_pack2_host(_ptr(seq4 if len(seq4) else np.zeros(1, np.uint8)), _ptr(seq4_offs), _ptr(l_qseq if n else np.zeros(1, np.int32)), n,
                                _ptr(out), _ptr(out_offs), _ptr(exc), int(threads)))
     return out[:int(out_offs[-1])], out_offs, exc[:n]
+
+
+def bgzf_members(raw):
+    """Walk the gzip members of a BGZF file image (bytes): the raw-deflate payloads and their ISIZE fields
+    (SAM spec 4.1: extra subfield BC = member size - 1).  What a caller of svb_bgzf_inflate_device does first."""
+    import struct
+    comps, sizes, o = [], [], 0
+    while o < len(raw):
+        if raw[o:o + 4] != b"\x1f\x8b\x08\x04":
+            raise ValueError("not a BGZF member at byte %d" % o)
+        xlen = struct.unpack_from("<H", raw, o + 10)[0]
+        bsize, x = None, o + 12
+        while x + 4 <= o + 12 + xlen:
+            sl = struct.unpack_from("<H", raw, x + 2)[0]
+            if raw[x:x + 2] == b"BC" and sl == 2:
+                bsize = struct.unpack_from("<H", raw, x + 4)[0]
+            x += 4 + sl
+        if bsize is None:
+            raise ValueError("gzip member without a BC subfield at byte %d" % o)
+        total = bsize + 1
+        comps.append(raw[o + 12 + xlen:o + total - 8])
+        sizes.append(struct.unpack_from("<I", raw, o + total - 4)[0])
+        o += total
+    return comps, sizes
+
+
+class InflateResult:
+    pass
+
+
+def bgzf_inflate_device(comps, sizes, device=0, check_status=True):
+    """svb_bgzf_inflate_device: inflate the members (list of payload bytes, list of ISIZE) on the GPU."""
+    n = len(comps)
+    io = np.zeros(n + 1, np.int64)
+    io[1:] = np.cumsum([len(c) for c in comps])
+    oo = np.zeros(n + 1, np.int64)
+    oo[1:] = np.cumsum(sizes)
+    comp = np.frombuffer(b"".join(comps) + b"\0", np.uint8)
+    out = np.zeros(max(1, int(oo[-1])), np.uint8)
+    status = np.zeros(max(1, n), np.int32)
+    ms = C.c_float(0)
+    rc = lib().svb_bgzf_inflate_device(_ptr(comp), _ptr(io), _ptr(oo), C.c_int64(n), C.c_int(device), _ptr(out), _ptr(status), C.byref(ms))
+    if check_status:
+        check(rc)
+    r = InflateResult()
+    r.rc, r.out, r.out_offs, r.status, r.kernel_ms = rc, out[:int(oo[-1])], oo, status[:n], float(ms.value)
+    return r
 
 
 def unpack2_device(packed, packed_offs, offs, device=0):

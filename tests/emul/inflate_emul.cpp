@@ -1,0 +1,24 @@
+// inflate_kernel.cuh (BGZF members inflated on the device, one thread per member) compiled for the CPU with the
+// warp emulator: warps of 32 members at a time, as the kernel's grid would run them.
+#include <string.h>
+
+#include "warp_emul.hpp"
+#include "../../svdss_b200/csrc/inflate_kernel.cuh"
+
+struct Job { const uint8_t* comp; const int64_t* in_offs; const int64_t* out_offs; int64_t n; uint8_t* out; int32_t* status; };
+
+static void body(void* a) {
+  Job* j = static_cast<Job*>(a);
+  svb::k_bgzf_inflate(j->comp, j->in_offs, j->out_offs, j->n, j->out, j->status);
+}
+
+extern "C" int emul_bgzf_inflate(const uint8_t* comp, const int64_t* in_offs, const int64_t* out_offs, int64_t n, uint8_t* out, int32_t* status) {
+  Job j = {comp, in_offs, out_offs, n, out, status};
+  blockDim.x = 32;
+  gridDim.x = (unsigned)((n + 31) / 32);
+  for (unsigned b = 0; b < gridDim.x; ++b) {
+    blockIdx.x = b;
+    if (!emu::run_warp(body, &j)) return -1;
+  }
+  return 0;
+}

@@ -36,6 +36,9 @@ def test_no_cpu_fallback_without_gpu(L):
     assert ei.value.code == -5 and "no CPU fallback" in str(ei.value)
     with pytest.raises(capi.SvbError):
         capi.suffix_array(np.array([1, 2, 0], np.uint8))
+    with pytest.raises(capi.SvbError) as ei:                                 # the device inflate has no host twin behind it either
+        capi.bgzf_inflate_device([b"\x03\x00"], [0])
+    assert ei.value.code == -5
 
 
 def test_product_does_not_import_oracle():
