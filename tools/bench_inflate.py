@@ -1,0 +1,47 @@
+"""GB/s of svb_bgzf_inflate_device (k_bgzf_inflate, one thread per BGZF member) on a BAM-shaped window: records of
+~15 kb reads (4-bit bases, 0xff qualities as the smoothed BAMs of this repo carry, or --quals for random ones),
+cut into 0xff00-byte members like htslib does, deflated at --level.  Next to it: zlib on one host core for the same
+members (what BgzfSource::fill does per thread).  Prints one JSON line.
+  python tools/bench_inflate.py [--mb 256] [--level 6] [--quals]"""
+import argparse, json, os, sys, time, zlib
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from svdss_b200 import capi
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mb", type=int, default=256, help="inflated size of the window")
+    ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--quals", action="store_true")
+    a = ap.parse_args()
+    rng = np.random.default_rng(1)
+    body = bytearray()
+    while len(body) < a.mb << 20:
+        l = int(rng.integers(10000, 20000))
+        seq = rng.integers(0, 256, size=(l + 1) // 2, dtype=np.uint8)
+        seq = (1 << (seq & 3)) | ((1 << ((seq >> 2) & 3)) << 4)                    # two of A C G T (1 2 4 8) per byte
+        qual = rng.integers(0, 42, size=l, dtype=np.uint8).tobytes() if a.quals else b"\xff" * l
+        body += b"\0" * 36 + b"read/%d/ccs\0" % len(body) + seq.astype(np.uint8).tobytes() + qual + b"XFC\0"
+    comps, sizes = [], []
+    for o in range(0, len(body), 0xff00):
+        d = bytes(body[o:o + 0xff00])
+        c = zlib.compressobj(a.level, zlib.DEFLATED, -15)
+        comps.append(c.compress(d) + c.flush()); sizes.append(len(d))
+    t = time.perf_counter()
+    for c in comps:
+        zlib.decompress(c, -15)
+    host_s = time.perf_counter() - t
+    capi.bgzf_inflate_device(comps[:64], sizes[:64])                               # warm-up
+    best = None
+    for _ in range(3):
+        r = capi.bgzf_inflate_device(comps, sizes)
+        best = r.kernel_ms if best is None else min(best, r.kernel_ms)
+    ok = r.out.tobytes() == bytes(body)
+    print(json.dumps({"kernel": "k_bgzf_inflate", "members": len(comps), "inflated_bytes": len(body), "compressed_bytes": sum(map(len, comps)),
+                      "level": a.level, "random_quals": a.quals, "kernel_ms": best, "GB_s_inflated": len(body) / (best * 1e-3) / 1e9,
+                      "zlib_one_core_GB_s": len(body) / host_s / 1e9, "identical_to_input": ok}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

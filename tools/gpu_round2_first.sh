@@ -14,5 +14,7 @@ SVB_STREAM_PACK2=1 timeout 900 python bench.py --no-cpu-baseline --no-rank-walk 
 import json, sys
 d = json.loads(sys.stdin.read().strip().splitlines()[-1]); e = d['e2e']
 print('pack2 e2e %.0f reads/s, %.1f ms/step, h2d %.2f GB/step' % (e['value'], e['ms_per_step'], e['h2d_bytes_per_step'] / 1e9))"
+# device inflate of BGZF members (building block): GB/s with and without random qualities
+for q in "" "--quals"; do timeout 600 python tools/bench_inflate.py --mb 256 $q 2>&1 | tail -1; done | tee gpurun_out/inflate_$TAG.txt
 TAG=$TAG N=${N:-12000} bash tools/gpu_poa_variants.sh
 ls -la gpurun_out | tail -12
