@@ -37,9 +37,13 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
   int64_t *d_io = nullptr, *d_oo = nullptr;
   int32_t* d_st = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  // a stream of its own that does not synchronise with the legacy default stream: a reader thread may call this
+  // while another thread of the process has a streamed search in flight on the same device
+  cudaStream_t sq = nullptr;
   std::vector<int32_t> st((size_t)n_members, 0);
   int rc = SVB_OK;
   auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == SVB_OK) { set_error("svb_bgzf_inflate_device: %s", cudaGetErrorString(e)); rc = SVB_ECUDA; } };
+  fail(cudaStreamCreateWithFlags(&sq, cudaStreamNonBlocking));
   fail(cudaMalloc((void**)&d_in, (size_t)in_total + 16));
   fail(cudaMalloc((void**)&d_out, (size_t)out_total + 16));
   fail(cudaMalloc((void**)&d_io, (size_t)(n_members + 1) * 8));
@@ -48,24 +52,26 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
   fail(cudaEventCreate(&e0));
   fail(cudaEventCreate(&e1));
   if (rc == SVB_OK) {
-    if (in_total) fail(cudaMemcpy(d_in, comp, (size_t)in_total, cudaMemcpyHostToDevice));
-    fail(cudaMemcpy(d_io, in_offs, (size_t)(n_members + 1) * 8, cudaMemcpyHostToDevice));
-    fail(cudaMemcpy(d_oo, out_offs, (size_t)(n_members + 1) * 8, cudaMemcpyHostToDevice));
+    if (in_total) fail(cudaMemcpyAsync(d_in, comp, (size_t)in_total, cudaMemcpyHostToDevice, sq));
+    fail(cudaMemcpyAsync(d_io, in_offs, (size_t)(n_members + 1) * 8, cudaMemcpyHostToDevice, sq));
+    fail(cudaMemcpyAsync(d_oo, out_offs, (size_t)(n_members + 1) * 8, cudaMemcpyHostToDevice, sq));
   }
   if (rc == SVB_OK) {
     // one warp per CTA: members differ in length by an order of magnitude, small CTAs retire independently
-    fail(cudaEventRecord(e0));
-    k_bgzf_inflate<<<(unsigned)((n_members + 31) / 32), 32>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
+    fail(cudaEventRecord(e0, sq));
+    k_bgzf_inflate<<<(unsigned)((n_members + 31) / 32), 32, 0, sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
     fail(cudaGetLastError());
-    fail(cudaEventRecord(e1));
-    fail(cudaDeviceSynchronize());
+    fail(cudaEventRecord(e1, sq));
+    if (out_total) fail(cudaMemcpyAsync(out_host, d_out, (size_t)out_total, cudaMemcpyDeviceToHost, sq));
+    fail(cudaMemcpyAsync(st.data(), d_st, (size_t)n_members * 4, cudaMemcpyDeviceToHost, sq));
+    fail(cudaStreamSynchronize(sq));
     if (rc == SVB_OK && kernel_ms) fail(cudaEventElapsedTime(kernel_ms, e0, e1));
-    if (out_total) fail(cudaMemcpy(out_host, d_out, (size_t)out_total, cudaMemcpyDeviceToHost));
-    fail(cudaMemcpy(st.data(), d_st, (size_t)n_members * 4, cudaMemcpyDeviceToHost));
   }
+  if (sq) cudaStreamSynchronize(sq);
   cudaFree(d_in); cudaFree(d_out); cudaFree(d_io); cudaFree(d_oo); cudaFree(d_st);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
+  if (sq) cudaStreamDestroy(sq);
   if (rc != SVB_OK) return rc;
   if (status_host) memcpy(status_host, st.data(), (size_t)n_members * 4);
   for (int64_t m = 0; m < n_members; ++m)
