@@ -7,6 +7,8 @@ mkdir -p gpurun_out
 TAG=${TAG:-r02a}
 timeout 1500 python -m pytest tests -q -m gpu -s 2>&1 | tail -25 | tee gpurun_out/gpu_tests_$TAG.txt
 python __graft_entry__.py smoke 2>&1 | tail -2
+# the streamed 2-bit transport is skipped by default (its first run in round 1 did not finish in 38 s): look at it here, bounded
+SVB_TEST_STREAM_PACK2=1 SVB_SEARCH_STATS=1 timeout 240 python -m pytest tests/test_gpu_zz_stream_pack2.py -q -s 2>&1 | tail -15 | tee gpurun_out/stream_pack2_$TAG.txt
 SVB_SEARCH_STATS=1 timeout 1200 python bench.py 2>gpurun_out/bench_full_$TAG.err | tee gpurun_out/bench_full_$TAG.txt | cut -c1-600
 # e2e through svb_sfs_batch_bam4 with every chunk re-packed to 2 bits on the host (the line's e2e object is the one to read)
 SVB_STREAM_PACK2=1 timeout 900 python bench.py --no-cpu-baseline --no-rank-walk --no-call-stage 2>gpurun_out/bench_pack2_$TAG.err | \
