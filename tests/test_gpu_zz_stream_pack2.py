@@ -22,7 +22,7 @@ reads += synth.make_reads(contigs, 40, seed=53, mean_len=3001, sd_len=400, min_l
 reads.insert(5, np.zeros(0, np.uint8))
 reads.insert(77, reads[10][:1].copy())
 reads[20] = reads[20].copy(); reads[20][100:104] = 5
-reads[300] = reads[300].copy(); reads[300][:] = 5                     # a read of N only
+reads[300] = np.full(260, 5, np.uint8)                                # a read of N only -- short: against the reference's 200 bp N runs every base of such a read is its own ~400-extension walk by one lane (an 8 kb one costs 3.2 M serial extensions per call)
 cat, offs = oracle.concat(contigs)
 idx = capi.Index.build(cat, offs, block_bytes=128)
 seq4, s4o, lq = capi.pack_bam4(reads)
@@ -48,9 +48,10 @@ print("STREAM_PACK2_OK h2d bytes 4-bit %d, 2-bit %d" % (a.h2d_bytes, b.h2d_bytes
 
 
 @pytest.mark.skipif(os.environ.get("SVB_TEST_STREAM_PACK2") != "1",
-                    reason="SVB_STREAM_PACK2 is experimental: its first contact with a B200 (last GPU seconds of round 1) did not "
-                           "finish within 38 s -- a stall is suspected (the kernel gives up on a chunk flag after 60 s) and there was "
-                           "no GPU time left to look; set SVB_TEST_STREAM_PACK2=1 to run it (DESIGN.md section 8, item 2)")
+                    reason="SVB_STREAM_PACK2 is experimental and unverified: its first contact with a B200 (last GPU seconds of round 1) "
+                           "did not finish within 38 s.  The test then held an 8 kb read of N only -- 3.2 M serial extensions by one lane in "
+                           "each of its 13 calls, which alone explains the time -- so no verdict either way; that read is short now.  "
+                           "Set SVB_TEST_STREAM_PACK2=1 to run it (DESIGN.md section 8, item 2)")
 def test_two_bit_transport_equals_four_bit_transport():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", CHILD], cwd=root, capture_output=True, text=True, timeout=200)
