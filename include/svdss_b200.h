@@ -235,6 +235,78 @@ SVB_API int svb_poa_batch(const uint8_t* seqs_concat, const int64_t* seq_offs /*
                           svb_poa_out_t* out);
 SVB_API void svb_poa_out_free(svb_poa_out_t* out);
 
+/* ------------------------------------------------------------------ Clusterer (8f #1) -- */
+
+/* What Clusterer::run (clusterer.cpp:8-52) keeps of the BAM: the records that pass its filters (not unmapped /
+ * secondary / supplementary, mapq >= --min-mapq, clusterer.cpp:116-122) in file order, which must be coordinate
+ * order (the reference needs the .bai, i.e. a sorted BAM, for fill_clusters' region queries).  All HOST arrays. */
+typedef struct {
+  int64_t n_aln;
+  const int32_t* tid;          /* bam1_core_t::tid, non-decreasing                                          */
+  const int32_t* pos;          /* bam1_core_t::pos, non-decreasing inside a tid                              */
+  const int32_t* hp;           /* HP:i aux value, 0 when absent                                              */
+  const int64_t* cigar_offs;   /* n_aln + 1                                                                  */
+  const uint32_t* cigar;       /* bam_get_cigar: len << 4 | op                                               */
+  const int64_t* sfs_offs;     /* n_aln + 1: SFSs->at(qname) of the record's read, in .sfs order (empty if none) */
+  const int32_t* sfs_qs;       /* SFS::qs                                                                    */
+  const int32_t* sfs_len;      /* SFS::l                                                                     */
+} svb_alns_t;
+
+#define SVB_SEQ_ASCII 0        /* upper-case characters, as load_chromosomes keeps them (chromosomes.cpp:10-27) */
+#define SVB_SEQ_NT6 1          /* nt6 codes, one byte per base                                                */
+#define SVB_SEQ_BAM4 2         /* reads only: 4 bits per base as BAM stores them, every read on a byte boundary */
+
+/* chromosome_seqs (chromosomes.hpp): contig c = seq[start[c], start[c] + len[c]).  `mem` says where seq lives;
+ * start / len / name_rank are HOST arrays.  name_rank[tid] orders the chromosome NAMES (SFS::operator< compares
+ * strings, sfs.hpp:64-72); NULL = tid order. */
+typedef struct {
+  int64_t n_contigs;
+  const uint8_t* seq;
+  const int64_t* start;
+  const int64_t* len;
+  const int32_t* name_rank;
+  int fmt;                     /* SVB_SEQ_ASCII or SVB_SEQ_NT6 */
+  int mem;
+} svb_ref_t;
+
+typedef struct {
+  /* Clusterer::clusters in the reference's order for `threads` (clusterer.cpp:33-36); a cluster with fewer than
+   * min_cluster_weight reads has placed = 0 and no coordinates (the reference leaves them uninitialised) */
+  int64_t n_clusters;
+  int32_t* tid;                /* Cluster::chrom                                                             */
+  int32_t* s;                  /* Cluster::s, ::e (clusterer.cpp:520)                                        */
+  int32_t* e;
+  int32_t* cov0;               /* Cluster::cov0..2; cov = their sum (clusterer.cpp:592-596)                  */
+  int32_t* cov1;
+  int32_t* cov2;
+  uint8_t* placed;
+  int64_t* sub_offs;           /* n_clusters + 1: Cluster::subreads, in BAM order                            */
+  int32_t* sub_aln;            /* index into the alignments                                                  */
+  int32_t* sub_qs;             /* SubRead::seq = read bases [qs, qe] (empty when qe < qs)                    */
+  int32_t* sub_qe;
+  int32_t* sub_hp;             /* SubRead::htag: 1, 2 or 0                                                   */
+  int64_t* rvec_offs;          /* n_clusters + 1: Cluster::reads, one byte each: has-SFS | hap code << 1 (1, 2, 3 = untagged) */
+  uint8_t* rvec;
+  int32_t* clip;               /* with clipped: 4 per alignment (left pos, left bases, right pos, right bases; bases 0 = none), else NULL */
+  /* bookkeeping of clusterer.hpp:150-160, as logged by Caller::run */
+  int64_t unplaced, s_unplaced, e_unplaced, unknown, unextended, small_clusters, small_clusters_2, n_extended;
+  int32_t max_ext_len, dist;
+  float kernel_ms;             /* the two kernels, CUDA events                                               */
+  float device_ms;             /* uploads + kernels + downloads                                              */
+  float host_ms;               /* the sort + sweep between them (cluster_by_proximity)                       */
+  int32_t launches;
+  int64_t h2d_bytes, d2h_bytes;
+} svb_clusters_t;
+
+/* Clusterer::run (clusterer.cpp:8-52) on the GPU: extend_alignment (:156-345, one thread per read that carries
+ * SFSs: placement through the CIGAR, unique 7-mers of the 100-bp flanks, per-read merge) and fill_clusters
+ * (:478-610, one thread per cluster: coverage, RVEC, sub-read windows) are kernels; cluster_by_proximity (:405-475)
+ * is a sort + two sequential sweeps over the extended SFSs on the host between them.  flank / ksize are
+ * config.hpp:85-86 (100 / 7; ksize <= 8, flank <= 128).  `threads` only fixes the output order. */
+SVB_API int svb_cluster_batch(const svb_alns_t* alns, const svb_ref_t* ref, int threads, int min_cluster_weight,
+                              int flank, int ksize, int clipped, int device, svb_clusters_t* out);
+SVB_API void svb_clusters_free(svb_clusters_t* out);
+
 #ifdef __cplusplus
 }
 #endif

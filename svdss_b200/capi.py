@@ -48,6 +48,30 @@ class PoaOut(C.Structure):
                 ("launches", C.c_int32), ("reruns", C.c_int32)]
 
 
+class Alns(C.Structure):
+    _fields_ = [("n_aln", C.c_int64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("hp", C.c_void_p), ("cigar_offs", C.c_void_p),
+                ("cigar", C.c_void_p), ("sfs_offs", C.c_void_p), ("sfs_qs", C.c_void_p), ("sfs_len", C.c_void_p)]
+
+
+class Ref(C.Structure):
+    _fields_ = [("n_contigs", C.c_int64), ("seq", C.c_void_p), ("start", C.c_void_p), ("len", C.c_void_p), ("name_rank", C.c_void_p),
+                ("fmt", C.c_int), ("mem", C.c_int)]
+
+
+class ClustersOut(C.Structure):
+    _fields_ = [("n_clusters", C.c_int64), ("tid", C.POINTER(C.c_int32)), ("s", C.POINTER(C.c_int32)), ("e", C.POINTER(C.c_int32)),
+                ("cov0", C.POINTER(C.c_int32)), ("cov1", C.POINTER(C.c_int32)), ("cov2", C.POINTER(C.c_int32)), ("placed", C.POINTER(C.c_uint8)),
+                ("sub_offs", C.POINTER(C.c_int64)), ("sub_aln", C.POINTER(C.c_int32)), ("sub_qs", C.POINTER(C.c_int32)),
+                ("sub_qe", C.POINTER(C.c_int32)), ("sub_hp", C.POINTER(C.c_int32)), ("rvec_offs", C.POINTER(C.c_int64)),
+                ("rvec", C.POINTER(C.c_uint8)), ("clip", C.POINTER(C.c_int32)),
+                ("unplaced", C.c_int64), ("s_unplaced", C.c_int64), ("e_unplaced", C.c_int64), ("unknown", C.c_int64),
+                ("unextended", C.c_int64), ("small_clusters", C.c_int64), ("small_clusters_2", C.c_int64), ("n_extended", C.c_int64),
+                ("max_ext_len", C.c_int32), ("dist", C.c_int32), ("kernel_ms", C.c_float), ("device_ms", C.c_float), ("host_ms", C.c_float),
+                ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+SVB_SEQ_ASCII, SVB_SEQ_NT6, SVB_SEQ_BAM4 = 0, 1, 2
+
 _lib = None
 
 # every symbol include/svdss_b200.h declares (tests check the .so exports all of them)
@@ -59,6 +83,7 @@ EXPORTS = [
     "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_pack2_chunk", "svb_unpack2_device", "svb_bgzf_inflate_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
     "svb_poa_batch", "svb_poa_out_free",
+    "svb_cluster_batch", "svb_clusters_free",
 ]
 
 
@@ -101,6 +126,9 @@ def lib():
     L.svb_poa_batch.argtypes = [vp, vp, vp, i64, i32, C.POINTER(PoaOut)]
     L.svb_poa_out_free.argtypes = [C.POINTER(PoaOut)]
     L.svb_poa_out_free.restype = None
+    L.svb_cluster_batch.argtypes = [C.POINTER(Alns), C.POINTER(Ref), i32, i32, i32, i32, i32, i32, C.POINTER(ClustersOut)]
+    L.svb_clusters_free.argtypes = [C.POINTER(ClustersOut)]
+    L.svb_clusters_free.restype = None
     _lib = L
     return L
 
@@ -476,3 +504,98 @@ def unpack2_device(packed, packed_offs, offs, device=0):
 def pack4_device(d_seq_ptr, d_offs_ptr, d_seq4_offs_ptr, n_reads, d_out_ptr, device=0):
     check(lib().svb_pack4_device(C.c_void_p(d_seq_ptr), C.c_void_p(d_offs_ptr), C.c_void_p(d_seq4_offs_ptr), n_reads,
                                  device, C.c_void_p(d_out_ptr)))
+
+
+class AlnBatch:
+    """svb_alns_t over numpy arrays (kept alive here): the records Clusterer::run keeps of a BAM, with the SFSs of
+    each record's read.  cigars: list of [(len, op char)] or (cigar_offs, cigar u32) arrays."""
+    OPS = "MIDNSHP=X"
+
+    def __init__(self, tid, pos, hp, cigar_offs, cigar, sfs_offs, sfs_qs, sfs_len):
+        self.tid = np.ascontiguousarray(tid, np.int32); self.pos = np.ascontiguousarray(pos, np.int32)
+        self.hp = np.ascontiguousarray(hp, np.int32)
+        self.cigar_offs = np.ascontiguousarray(cigar_offs, np.int64); self.cigar = np.ascontiguousarray(cigar, np.uint32)
+        self.sfs_offs = np.ascontiguousarray(sfs_offs, np.int64)
+        self.sfs_qs = np.ascontiguousarray(sfs_qs, np.int32); self.sfs_len = np.ascontiguousarray(sfs_len, np.int32)
+        self.n = len(self.tid)
+        self.c = Alns(self.n, *[a.ctypes.data for a in (self.tid, self.pos, self.hp, self.cigar_offs, self.cigar, self.sfs_offs,
+                                                          self.sfs_qs, self.sfs_len)])
+
+    @classmethod
+    def from_records(cls, records, sfs_by_index):
+        """records: dicts with tid, pos, hp (or None), cigar [(len, op)]; sfs_by_index[i] = [(qs, len), ...]"""
+        co, cg, so, qs, ln = [0], [], [0], [], []
+        for i, r in enumerate(records):
+            cg += [(l << 4) | cls.OPS.index(op) for l, op in r["cigar"]]
+            co.append(len(cg))
+            for q, l in sfs_by_index.get(i, []):
+                qs.append(q); ln.append(l)
+            so.append(len(qs))
+        return cls([r["tid"] for r in records], [r["pos"] for r in records], [r.get("hp") or 0 for r in records], co, cg, so, qs, ln)
+
+
+class RefSeqs:
+    """svb_ref_t over a host numpy byte array (ASCII or nt6) or a device pointer."""
+
+    def __init__(self, seq, start, length, fmt=SVB_SEQ_ASCII, mem=SVB_MEM_HOST, name_rank=None):
+        self.seq = seq if isinstance(seq, (int, np.integer)) else np.ascontiguousarray(seq, np.uint8)
+        self.start = np.ascontiguousarray(start, np.int64); self.len = np.ascontiguousarray(length, np.int64)
+        self.name_rank = None if name_rank is None else np.ascontiguousarray(name_rank, np.int32)
+        self.c = Ref(len(self.start), int(self.seq) if isinstance(self.seq, (int, np.integer)) else self.seq.ctypes.data,
+                     self.start.ctypes.data, self.len.ctypes.data, None if self.name_rank is None else self.name_rank.ctypes.data, fmt, mem)
+
+    @classmethod
+    def from_strings(cls, names, seqs):
+        """ASCII chromosomes in tid order; name_rank = order of the names as byte strings"""
+        cat = np.frombuffer("".join(seqs).encode(), np.uint8)
+        ln = np.array([len(x) for x in seqs], np.int64)
+        st = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.int64)
+        order = sorted(range(len(names)), key=lambda i: names[i].encode())
+        rank = np.empty(len(names), np.int32)
+        rank[order] = np.arange(len(names), dtype=np.int32)
+        return cls(cat, st, ln, SVB_SEQ_ASCII, SVB_MEM_HOST, rank)
+
+
+class Clusters:
+    """svb_clusters_t copied out."""
+
+    def __init__(self, o):
+        n = o.n_clusters
+
+        def arr(p, m, dt):
+            return np.ctypeslib.as_array(p, shape=(m,)).copy() if m and p else np.zeros(0, dt)
+        self.n = n
+        self.tid, self.s, self.e = arr(o.tid, n, np.int32), arr(o.s, n, np.int32), arr(o.e, n, np.int32)
+        self.cov0, self.cov1, self.cov2 = arr(o.cov0, n, np.int32), arr(o.cov1, n, np.int32), arr(o.cov2, n, np.int32)
+        self.placed = arr(o.placed, n, np.uint8)
+        self.sub_offs = np.ctypeslib.as_array(o.sub_offs, shape=(n + 1,)).copy() if o.sub_offs else np.zeros(1, np.int64)
+        m = int(self.sub_offs[-1])
+        self.sub_aln, self.sub_qs, self.sub_qe, self.sub_hp = (arr(p, m, np.int32) for p in (o.sub_aln, o.sub_qs, o.sub_qe, o.sub_hp))
+        self.rvec_offs = np.ctypeslib.as_array(o.rvec_offs, shape=(n + 1,)).copy() if o.rvec_offs else np.zeros(1, np.int64)
+        self.rvec = arr(o.rvec, int(self.rvec_offs[-1]), np.uint8)
+        self.clip = None
+        for k in ("unplaced", "s_unplaced", "e_unplaced", "unknown", "unextended", "small_clusters", "small_clusters_2", "n_extended",
+                  "max_ext_len", "dist", "kernel_ms", "device_ms", "host_ms", "launches", "h2d_bytes", "d2h_bytes"):
+            setattr(self, k, getattr(o, k))
+
+
+def cluster_batch(alns, ref, threads=4, min_cluster_weight=2, flank=100, ksize=7, clipped=False, device=0, emul=None):
+    """svb_cluster_batch; `emul` = a CDLL of tests/emul/cluster_emul.cpp runs the same per-item code on the CPU (tests only)."""
+    o = ClustersOut()
+    if emul is not None:
+        emul.emul_cluster_batch.argtypes = [C.POINTER(Alns), C.POINTER(Ref), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ClustersOut)]
+        emul.emul_clusters_free.argtypes = [C.POINTER(ClustersOut)]
+        rc = emul.emul_cluster_batch(C.byref(alns.c), C.byref(ref.c), threads, min_cluster_weight, flank, ksize, int(clipped), C.byref(o))
+        if rc != 0:
+            raise SvbError(rc, "emul_cluster_batch")
+        free = emul.emul_clusters_free
+    else:
+        check(lib().svb_cluster_batch(C.byref(alns.c), C.byref(ref.c), threads, min_cluster_weight, flank, ksize, int(clipped), device, C.byref(o)))
+        free = lib().svb_clusters_free
+    try:
+        res = Clusters(o)
+        if clipped and o.clip:
+            res.clip = np.ctypeslib.as_array(o.clip, shape=(alns.n, 4)).copy()
+    finally:
+        free(C.byref(o))
+    return res

@@ -206,4 +206,31 @@ SVB_HD void cl_window_on_read(const uint32_t* cig, int n_cig, int pos, int min_s
   }
 }
 
+// fill_clusters (clusterer.cpp:485-607) for one cluster that has enough reads: every alignment of its chromosome
+// overlapping chrom:min_s-max_e (htslib region: pos < max_e and bam_endpos > min_s - 1) counts into the coverage of
+// its haplotype and into the RVEC list; those that carry one of the cluster's SFSs (`members`, ascending alignment
+// indices) are cut to the window.  Alignments [lo, hi) = the candidates (BAM order).  sub_*[] need n_members slots,
+// rvec[] hi - lo.  rvec byte = has-SFS | haplotype code << 1 (1, 2, or 3 for untagged: Cluster::reads).
+SVB_HD void cl_fill_cluster(const int32_t* pos, const int32_t* endp, const int32_t* hp, const int64_t* cigar_offs, const uint32_t* cigar,
+                            int lo, int hi, int min_s, int max_e, const int32_t* members, int n_members,
+                            int32_t* sub_aln, int32_t* sub_qs, int32_t* sub_qe, int32_t* sub_hp, int& n_sub,
+                            uint8_t* rvec, int& n_rv, int* cov, unsigned& unextended) {
+  const int beg = min_s - 1 < 0 ? 0 : min_s - 1, end = max_e;
+  n_sub = 0; n_rv = 0; cov[0] = cov[1] = cov[2] = 0;
+  int m = 0;   // members[] and the candidates are both ascending: one merge pass
+  for (int a = lo; a < hi; ++a) {
+    if (!(pos[a] < end && endp[a] > beg)) continue;
+    const int hp_t = (hp[a] == 1 || hp[a] == 2) ? hp[a] : 0;   // other values index out of range in the reference
+    ++cov[hp_t];
+    while (m < n_members && members[m] < a) ++m;
+    const bool mine = m < n_members && members[m] == a;
+    rvec[n_rv++] = (uint8_t)((mine ? 1 : 0) | ((hp_t == 0 ? 3 : hp_t) << 1));
+    if (!mine) continue;
+    int qs, qe;
+    cl_window_on_read(cigar + cigar_offs[a], (int)(cigar_offs[a + 1] - cigar_offs[a]), pos[a], min_s, max_e, qs, qe);
+    if (qs == -1 || qe == -1) { ++unextended; continue; }
+    sub_aln[n_sub] = a; sub_qs[n_sub] = qs; sub_qe[n_sub] = qe; sub_hp[n_sub] = hp_t; ++n_sub;
+  }
+}
+
 }  // namespace svb

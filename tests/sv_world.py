@@ -16,12 +16,12 @@ def dec(a):
     return "".join(L[int(x)] for x in a)
 
 
-def make_world(d, ref_bp=90_000, n_svs=12, coverage=8, seed=71, tag_hp=True, mean_len=4000):
+def make_world(d, ref_bp=90_000, n_svs=12, coverage=8, seed=71, tag_hp=True, mean_len=4000, sub_rate=0.0, indel_rate=0.0):
     contigs = synth.make_reference(ref_bp, seed=seed, contigs=2, n_repeats=4, n_nruns=1, nrun_len=50)
     names = ["chrA", "chrB"]
     cat = synth.make_sv_catalogue(contigs, n_svs, seed=seed + 1, min_len=50, max_len=600, margin=1500, spacing=1500)
     alns = synth.make_sample_alignments(contigs, cat, coverage=coverage, seed=seed + 2, mean_len=mean_len, sd_len=800,
-                                        min_len=1000, max_len=8000, tag_hp=tag_hp)
+                                        min_len=1000, max_len=8000, tag_hp=tag_hp, sub_rate=sub_rate, indel_rate=indel_rate)
     fa = os.path.join(d, "ref.fa")
     with open(fa, "w") as f:
         for n, c in zip(names, contigs):
