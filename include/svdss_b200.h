@@ -307,6 +307,65 @@ SVB_API int svb_cluster_batch(const svb_alns_t* alns, const svb_ref_t* ref, int 
                               int flank, int ksize, int clipped, int device, svb_clusters_t* out);
 SVB_API void svb_clusters_free(svb_clusters_t* out);
 
+/* ------------------------------------------------------------------ Caller::pcall (a8, a9) -- */
+
+/* The sequences sub-reads are cut from: sequence i = seq[offs[i] ...) -- offs in BYTES for SVB_SEQ_BAM4 (every read
+ * starts on a byte boundary, l_qseq bases each, bam_get_seq), in bases for SVB_SEQ_NT6 / SVB_SEQ_ASCII; offs[i] < 0 =
+ * sequence not available (a read that was never searched cannot carry an SFS, hence never yields a sub-read).
+ * `mem` says where seq lives (SVB_MEM_DEVICE: SVB_SEQ_NT6 only); offs is a HOST array of n entries. */
+typedef struct {
+  int64_t n;
+  const uint8_t* seq;
+  const int64_t* offs;
+  int fmt;
+  int mem;
+} svb_seqs_t;
+
+typedef struct {
+  /* one job = one sub-cluster that split_cluster kept (caller.cpp:100-255, at most two per cluster), cluster order */
+  int64_t n_jobs;
+  int32_t* job_cluster;        /* index into the clusters                                                      */
+  int32_t* job_cov;            /* Cluster::cov, cov0, cov1, cov2 of the sub-cluster (-1 = not applicable), 4 per job */
+  int64_t* job_sub_offs;       /* n_jobs + 1: the sub-reads of the job = indices into the clusters' sub_* arrays */
+  int32_t* job_sub;
+  int64_t* cons_offs;          /* n_jobs + 1: run_poa's consensus, codes 0..4 = ACGTN (caller.cpp:292-297)     */
+  uint8_t* cons;
+  int32_t* score;              /* ez.score (caller.cpp:351)                                                    */
+  int64_t* cigar_offs;         /* n_jobs + 1: ez.cigar, len << 4 | op with op 0 1 2 = M I D                    */
+  uint32_t* cigar;
+  /* SV records of the CIGAR walk (caller.cpp:359-401), job order then CIGAR order */
+  int64_t n_svs;
+  int32_t* sv_job;
+  uint8_t* sv_type;            /* 0 INS, 1 DEL                                                                 */
+  int32_t* sv_pos;             /* SV::s = rpos (1-based position of the anchor base)                           */
+  int32_t* sv_len;             /* SV::l                                                                        */
+  int32_t* sv_cpos;            /* INS: the inserted bases are cons[cpos, cpos + l) of the job                  */
+  int32_t* job_nv;             /* SV::ngaps of every record of the job                                         */
+  int64_t skipped_outside;     /* clusters whose window leaves the chromosome (the reference would read out of bounds) */
+  /* measurement */
+  int64_t poa_cells, ksw_cells;
+  float poa_kernel_ms, ksw_kernel_ms, gather_ms;
+  float device_ms;             /* all device work of the call                                                  */
+  float host_ms;               /* split_cluster + CIGAR walk on the host                                       */
+  int32_t launches, poa_reruns, ksw_waves;
+  int64_t h2d_bytes, d2h_bytes;
+} svb_calls_t;
+
+/* Caller::pcall (caller.cpp:311-406) for the clusters of svb_cluster_batch (or any svb_clusters_t a caller fills:
+ * tid, s, e, cov0..2, placed, sub_offs, sub_aln, sub_qs, sub_qe, sub_hp): clusters with fewer than
+ * min_cluster_weight sub-reads are skipped (:316), split_cluster (host: it looks at lengths and haplotype tags
+ * only), then for every sub-cluster run_poa over its sub-reads (gathered on the GPU when the reads live there,
+ * k_poa), ksw_extd2 of the consensus against chromosome[s, e] (k_ksw_extd2) and the CIGAR walk to INS / DEL
+ * records of at least min_sv_length bases.  min_ratio is config->min_ratio (0.97), useht = !--noht. */
+SVB_API int svb_call_batch(const svb_clusters_t* clusters, const svb_seqs_t* reads, const svb_ref_t* ref, int min_cluster_weight,
+                           int min_sv_length, float min_ratio, int useht, int device, svb_calls_t* out);
+SVB_API void svb_calls_free(svb_calls_t* out);
+
+/* The indexed sequences as an svb_ref_t that lives on the index's device (the text the located-match mode keeps
+ * next to the BWT): contig c = nt6 codes of the forward strand.  start_buf / len_buf: caller-owned HOST arrays of
+ * n_contigs entries that `out` points into.  Fails for an index without text (svb_index_from_bwt). */
+SVB_API int svb_index_ref(const svb_index_t* idx, svb_ref_t* out, int64_t* start_buf, int64_t* len_buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -302,3 +302,51 @@ def poa_consensus(seqs, band=False, return_stats=False, **kw):
 
 def edit_distance(a, b):
     return _poa_lib().orc_edit_distance(_z(a), len(a), _z(b), len(b))
+
+
+# ------------------------------------------------------------------ Clusterer + pcall (oracle/call_oracle.c)
+def _call_lib():
+    L = lib()
+    if not hasattr(L, "_call_ready"):
+        from svdss_b200 import capi as K      # struct layouts of include/svdss_b200.h only; the library is not loaded
+        ci = C.c_int
+        L.orc_cluster.restype = ci
+        L.orc_cluster.argtypes = [C.POINTER(K.Alns), C.POINTER(K.Ref), ci, ci, ci, ci, ci, ci, C.POINTER(K.ClustersOut)]
+        L.orc_clusters_free.restype = None
+        L.orc_clusters_free.argtypes = [C.POINTER(K.ClustersOut)]
+        L.orc_call.restype = ci
+        L.orc_call.argtypes = [C.POINTER(K.ClustersOut), C.POINTER(K.Seqs), C.POINTER(K.Ref), ci, ci, C.c_float, ci, ci, C.POINTER(K.CallsOut)]
+        L.orc_calls_free.restype = None
+        L.orc_calls_free.argtypes = [C.POINTER(K.CallsOut)]
+        L._call_ready = True
+    return L
+
+
+def cluster(alns, ref, threads=4, min_cluster_weight=2, flank=100, ksize=7, clipped=False, omp_threads=0):
+    """Clusterer::run on the CPU (literal restatement over aligned-pair vectors); alns / ref: capi.AlnBatch / capi.RefSeqs (host)"""
+    from svdss_b200 import capi as K
+    L = _call_lib()
+    o = K.ClustersOut()
+    rc = L.orc_cluster(C.byref(alns.c), C.byref(ref.c), threads, min_cluster_weight, flank, ksize, int(clipped), omp_threads, C.byref(o))
+    assert rc == 0
+    try:
+        res = K.Clusters(o)
+        if clipped and o.clip:
+            res.clip = np.ctypeslib.as_array(o.clip, shape=(alns.n, 4)).copy()
+    finally:
+        L.orc_clusters_free(C.byref(o))
+    return res
+
+
+def call(clusters, reads, ref, min_cluster_weight=2, min_sv_length=25, min_ratio=0.97, useht=True, omp_threads=0):
+    """Caller::pcall on the CPU over the oracle's POA and ksw2 (OpenMP over jobs); host buffers only"""
+    from svdss_b200 import capi as K
+    L = _call_lib()
+    co, keep = K._clusters_struct(clusters)
+    o = K.CallsOut()
+    rc = L.orc_call(C.byref(co), C.byref(reads.c), C.byref(ref.c), min_cluster_weight, min_sv_length, min_ratio, int(useht), omp_threads, C.byref(o))
+    assert rc == 0
+    try:
+        return K.Calls(o)
+    finally:
+        L.orc_calls_free(C.byref(o))

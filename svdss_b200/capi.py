@@ -70,6 +70,22 @@ class ClustersOut(C.Structure):
                 ("launches", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
+class Seqs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("seq", C.c_void_p), ("offs", C.c_void_p), ("fmt", C.c_int), ("mem", C.c_int)]
+
+
+class CallsOut(C.Structure):
+    _fields_ = [("n_jobs", C.c_int64), ("job_cluster", C.POINTER(C.c_int32)), ("job_cov", C.POINTER(C.c_int32)),
+                ("job_sub_offs", C.POINTER(C.c_int64)), ("job_sub", C.POINTER(C.c_int32)), ("cons_offs", C.POINTER(C.c_int64)),
+                ("cons", C.POINTER(C.c_uint8)), ("score", C.POINTER(C.c_int32)), ("cigar_offs", C.POINTER(C.c_int64)),
+                ("cigar", C.POINTER(C.c_uint32)), ("n_svs", C.c_int64), ("sv_job", C.POINTER(C.c_int32)), ("sv_type", C.POINTER(C.c_uint8)),
+                ("sv_pos", C.POINTER(C.c_int32)), ("sv_len", C.POINTER(C.c_int32)), ("sv_cpos", C.POINTER(C.c_int32)),
+                ("job_nv", C.POINTER(C.c_int32)), ("skipped_outside", C.c_int64), ("poa_cells", C.c_int64), ("ksw_cells", C.c_int64),
+                ("poa_kernel_ms", C.c_float), ("ksw_kernel_ms", C.c_float), ("gather_ms", C.c_float), ("device_ms", C.c_float),
+                ("host_ms", C.c_float), ("launches", C.c_int32), ("poa_reruns", C.c_int32), ("ksw_waves", C.c_int32),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
 SVB_SEQ_ASCII, SVB_SEQ_NT6, SVB_SEQ_BAM4 = 0, 1, 2
 
 _lib = None
@@ -83,7 +99,7 @@ EXPORTS = [
     "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_pack2_chunk", "svb_unpack2_device", "svb_bgzf_inflate_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
     "svb_poa_batch", "svb_poa_out_free",
-    "svb_cluster_batch", "svb_clusters_free",
+    "svb_cluster_batch", "svb_clusters_free", "svb_call_batch", "svb_calls_free", "svb_index_ref",
 ]
 
 
@@ -129,6 +145,10 @@ def lib():
     L.svb_cluster_batch.argtypes = [C.POINTER(Alns), C.POINTER(Ref), i32, i32, i32, i32, i32, i32, C.POINTER(ClustersOut)]
     L.svb_clusters_free.argtypes = [C.POINTER(ClustersOut)]
     L.svb_clusters_free.restype = None
+    L.svb_call_batch.argtypes = [C.POINTER(ClustersOut), C.POINTER(Seqs), C.POINTER(Ref), i32, i32, C.c_float, i32, i32, C.POINTER(CallsOut)]
+    L.svb_calls_free.argtypes = [C.POINTER(CallsOut)]
+    L.svb_calls_free.restype = None
+    L.svb_index_ref.argtypes = [vp, C.POINTER(Ref), vp, vp]
     _lib = L
     return L
 
@@ -216,6 +236,16 @@ class Index:
 
     def save(self, path):
         check(lib().svb_index_save(self._h, os.fsencode(path)))
+
+    def ref(self):
+        """the indexed contigs as a device-resident RefSeqs (nt6 codes, forward strands)"""
+        info = IndexInfo()
+        check(lib().svb_index_info(self._h, C.byref(info)))
+        st = np.zeros(info.n_contigs, np.int64)
+        ln = np.zeros(info.n_contigs, np.int64)
+        r = Ref()
+        check(lib().svb_index_ref(self._h, C.byref(r), _ptr(st), _ptr(ln)))
+        return RefSeqs(int(r.seq), st, ln, SVB_SEQ_NT6, SVB_MEM_DEVICE)
 
     def bwt(self):
         out = np.empty(self.n, np.uint8)
@@ -599,3 +629,73 @@ def cluster_batch(alns, ref, threads=4, min_cluster_weight=2, flank=100, ksize=7
     finally:
         free(C.byref(o))
     return res
+
+
+class ReadSeqs:
+    """svb_seqs_t: sequence i of the batch = seq[offs[i] ...) (offs < 0: not available).  seq: numpy bytes or a device pointer."""
+
+    def __init__(self, seq, offs, fmt=SVB_SEQ_NT6, mem=SVB_MEM_HOST):
+        self.seq = seq if isinstance(seq, (int, np.integer)) else np.ascontiguousarray(seq, np.uint8)
+        self.offs = np.ascontiguousarray(offs, np.int64)
+        self.c = Seqs(len(self.offs), int(self.seq) if isinstance(self.seq, (int, np.integer)) else self.seq.ctypes.data,
+                      self.offs.ctypes.data, fmt, mem)
+
+
+class Calls:
+    """svb_calls_t copied out."""
+
+    def __init__(self, o):
+        nj, ns = o.n_jobs, o.n_svs
+
+        def arr(p, m, dt):
+            return np.ctypeslib.as_array(p, shape=(m,)).copy() if m and p else np.zeros(0, dt)
+        self.n_jobs, self.n_svs = nj, ns
+        self.job_cluster = arr(o.job_cluster, nj, np.int32)
+        self.job_cov = arr(o.job_cov, nj * 4, np.int32).reshape(-1, 4)
+        self.job_sub_offs = np.ctypeslib.as_array(o.job_sub_offs, shape=(nj + 1,)).copy()
+        self.job_sub = arr(o.job_sub, int(self.job_sub_offs[-1]), np.int32)
+        self.cons_offs = np.ctypeslib.as_array(o.cons_offs, shape=(nj + 1,)).copy()
+        self.cons = arr(o.cons, int(self.cons_offs[-1]), np.uint8)
+        self.score = arr(o.score, nj, np.int32)
+        self.cigar_offs = np.ctypeslib.as_array(o.cigar_offs, shape=(nj + 1,)).copy()
+        self.cigar = arr(o.cigar, int(self.cigar_offs[-1]), np.uint32)
+        self.sv_job, self.sv_pos, self.sv_len, self.sv_cpos = (arr(p, ns, np.int32) for p in (o.sv_job, o.sv_pos, o.sv_len, o.sv_cpos))
+        self.sv_type = arr(o.sv_type, ns, np.uint8)
+        self.job_nv = arr(o.job_nv, nj, np.int32)
+        for k in ("skipped_outside", "poa_cells", "ksw_cells", "poa_kernel_ms", "ksw_kernel_ms", "gather_ms", "device_ms", "host_ms",
+                  "launches", "poa_reruns", "ksw_waves", "h2d_bytes", "d2h_bytes"):
+            setattr(self, k, getattr(o, k))
+
+    def consensus(self, j):
+        return self.cons[int(self.cons_offs[j]):int(self.cons_offs[j + 1])]
+
+    def cigar_of(self, j):
+        return [(int(x) >> 4, "MID"[int(x) & 0xf]) for x in self.cigar[int(self.cigar_offs[j]):int(self.cigar_offs[j + 1])]]
+
+
+def _clusters_struct(cl):
+    """a ClustersOut over the numpy arrays of a Clusters object (kept alive by the returned tuple)"""
+    o = ClustersOut()
+    keep = []
+    o.n_clusters = cl.n
+    for name, dt in (("tid", np.int32), ("s", np.int32), ("e", np.int32), ("cov0", np.int32), ("cov1", np.int32), ("cov2", np.int32),
+                     ("placed", np.uint8), ("sub_offs", np.int64), ("sub_aln", np.int32), ("sub_qs", np.int32), ("sub_qe", np.int32),
+                     ("sub_hp", np.int32), ("rvec_offs", np.int64), ("rvec", np.uint8)):
+        a = np.ascontiguousarray(getattr(cl, name), dt)
+        if a.size == 0:
+            a = np.zeros(1, dt)
+        keep.append(a)
+        setattr(o, name, a.ctypes.data_as(C.POINTER(np.ctypeslib.as_ctypes_type(dt))))
+    return o, keep
+
+
+def call_batch(clusters, reads, ref, min_cluster_weight=2, min_sv_length=25, min_ratio=0.97, useht=True, device=0):
+    """svb_call_batch on a Clusters object (from cluster_batch, or any object with the same array attributes)"""
+    co, keep = _clusters_struct(clusters)
+    o = CallsOut()
+    check(lib().svb_call_batch(C.byref(co), C.byref(reads.c), C.byref(ref.c), min_cluster_weight, min_sv_length, min_ratio, int(useht),
+                               device, C.byref(o)))
+    try:
+        return Calls(o)
+    finally:
+        lib().svb_calls_free(C.byref(o))

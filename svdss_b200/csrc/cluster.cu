@@ -285,3 +285,17 @@ extern "C" int svb_cluster_batch(const svb_alns_t* A, const svb_ref_t* R, int th
   }
   return SVB_OK;
 }
+
+extern "C" int svb_index_ref(const svb_index_t* idx, svb_ref_t* out, int64_t* start_buf, int64_t* len_buf) {
+  if (!idx || !out || !start_buf || !len_buf) { set_error("svb_index_ref: null argument"); return SVB_EINVAL; }
+  const IndexDev& d = idx->dev;
+  if (!d.d_text || !d.d_tstart) { set_error("svb_index_ref: this index carries no text (built from a bare BWT)"); return SVB_EINVAL; }
+  SVB_TRY(check_device(d.device));
+  std::vector<int64_t> ts((size_t)d.n_contigs + 1);
+  SVB_CUDA(cudaMemcpy(ts.data(), d.d_tstart, ts.size() * 8, cudaMemcpyDeviceToHost));
+  for (int64_t c = 0; c < d.n_contigs; ++c) { start_buf[c] = ts[(size_t)c]; len_buf[c] = (ts[(size_t)c + 1] - ts[(size_t)c] - 2) / 2; }
+  memset(out, 0, sizeof(*out));
+  out->n_contigs = d.n_contigs; out->seq = d.d_text; out->start = start_buf; out->len = len_buf; out->name_rank = nullptr;
+  out->fmt = SVB_SEQ_NT6; out->mem = SVB_MEM_DEVICE;
+  return SVB_OK;
+}

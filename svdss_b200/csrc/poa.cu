@@ -25,13 +25,17 @@
 namespace svb {
 
 int check_device(int device);
+int poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_offs, const int64_t* cluster_offs,
+                   int64_t n_clusters, int device, svb_poa_out_t* out);
 
 }  // namespace svb
 
 using namespace svb;
 
-extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const int64_t* cluster_offs,
-                             int64_t n_clusters, int device, svb_poa_out_t* out) {
+// svb_poa_batch with the sequences either in host memory or already on `device` (the call pipeline gathers the
+// sub-reads of all clusters on the GPU, call_batch.cu); the offset arrays are always host arrays
+int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_offs, const int64_t* cluster_offs,
+                        int64_t n_clusters, int device, svb_poa_out_t* out) {
   if (!out) { set_error("svb_poa_batch: null out"); return SVB_EINVAL; }
   memset(out, 0, sizeof(*out));
   if (!seq_offs || !cluster_offs || n_clusters < 0 || n_clusters > 0x7fffffff) { set_error("svb_poa_batch: bad arguments"); return SVB_EINVAL; }
@@ -88,7 +92,8 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
     PCHECK(cudaEventCreate(&e0));
     PCHECK(cudaEventCreate(&e1));
     PCHECK(cudaEventRecord(e0, 0));
-    PCHECK(cudaMalloc((void**)&d_seqs, std::max<int64_t>(s_total, 1)));
+    if (seqs_mem == SVB_MEM_DEVICE) d_seqs = const_cast<uint8_t*>(seqs) + s_first;
+    else PCHECK(cudaMalloc((void**)&d_seqs, std::max<int64_t>(s_total, 1)));
     PCHECK(cudaMalloc((void**)&d_soff, (n_seqs + 1) * 8));
     PCHECK(cudaMalloc((void**)&d_coff, (n_clusters + 1) * 8));
     PCHECK(cudaMalloc((void**)&d_capoff, (n_clusters + 1) * 8));
@@ -100,11 +105,11 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
     PCHECK(cudaMalloc((void**)&d_cells, 8));
     PCHECK(cudaMemset(d_cells, 0, 8));
     if (getenv("SVB_POA_TIMING")) { PCHECK(cudaMalloc((void**)&d_phase, 40)); PCHECK(cudaMemset(d_phase, 0, 40)); }
-    if (s_total) PCHECK(cudaMemcpy(d_seqs, seqs + s_first, s_total, cudaMemcpyHostToDevice));
+    if (s_total && seqs_mem != SVB_MEM_DEVICE) PCHECK(cudaMemcpy(d_seqs, seqs + s_first, s_total, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_soff, so.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_coff, cluster_offs, (n_clusters + 1) * 8, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_capoff, cap_off.data(), (n_clusters + 1) * 8, cudaMemcpyHostToDevice));
-    out->h2d_bytes = s_total + (n_seqs + 1) * 8 + (n_clusters + 1) * 16;
+    out->h2d_bytes = (seqs_mem == SVB_MEM_DEVICE ? 0 : s_total) + (n_seqs + 1) * 8 + (n_clusters + 1) * 16;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     // pass 0: heuristic capacities; pass 1: worst-case capacities for the clusters that overflowed
@@ -264,12 +269,18 @@ extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const
   }
 done:
 #undef PCHECK
-  cudaFree(d_seqs); cudaFree(d_ws); cudaFree(d_cons); cudaFree(d_soff); cudaFree(d_coff); cudaFree(d_capoff);
+  if (seqs_mem != SVB_MEM_DEVICE) cudaFree(d_seqs);
+  cudaFree(d_ws); cudaFree(d_cons); cudaFree(d_soff); cudaFree(d_coff); cudaFree(d_capoff);
   cudaFree(d_order); cudaFree(d_len); cudaFree(d_status); cudaFree(d_work); cudaFree(d_cells); cudaFree(d_phase);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (rc != SVB_OK) svb_poa_out_free(out);
   return rc;
+}
+
+extern "C" int svb_poa_batch(const uint8_t* seqs, const int64_t* seq_offs, const int64_t* cluster_offs,
+                             int64_t n_clusters, int device, svb_poa_out_t* out) {
+  return poa_batch_impl(seqs, SVB_MEM_HOST, seq_offs, cluster_offs, n_clusters, device, out);
 }
 
 extern "C" void svb_poa_out_free(svb_poa_out_t* out) {

@@ -198,7 +198,10 @@ def materialize_segments_numpy(ref_cat, segs):
     is_ref = segs["kind"][seg_id] == 0
     b = ref_cat[np.where(is_ref, src, 0)]
     b = np.where(rv, comp6(b), b)
-    out[:] = np.where(is_ref, b, _hash_bases_np(gidx, segs["seed"]))
+    hidx = gidx
+    if "key" in segs:      # kind 2: bases hashed from key + offset in the segment (the same allele in every read)
+        hidx = np.where(segs["kind"][seg_id] == 2, segs["key"][seg_id] + w, gidx)
+    out[:] = np.where(is_ref, b, _hash_bases_np(hidx, segs["seed"]))
     return out
 
 
@@ -231,7 +234,11 @@ def materialize_segments_torch(ref_cat_t, segs, out_t=None, chunk_segs=40_000):
         b = ref_cat_t[torch.where(is_ref, src, torch.zeros_like(src))]
         cb = torch.where((b >= 1) & (b <= 4), 5 - b, b)
         b = torch.where(rvv, cb, b)
-        h = (gidx + int(segs["seed"])) * M1
+        hidx = gidx
+        if "key" in segs:
+            ky = torch.from_numpy(segs["key"][s0:s1]).to(dev)
+            hidx = torch.where(kd[seg_id] == 2, ky[seg_id] + w, gidx)
+        h = (hidx + int(segs["seed"])) * M1
         h = h ^ ((h >> 29) & 0x7FFFFFFFF)
         h = h * M2
         rb = (((h >> 33) & 3) + 1).to(torch.uint8)
@@ -390,3 +397,107 @@ def gen_pairs(rng, n, lo=100, hi=10000):
         q[m] = (q[m] + rng.integers(1, 4, size=int(m.sum()))) % 4
         out.append((q, t))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Config 3 at scale: a 30x coordinate-sorted smoothed BAM over the config-2 reference with a
+# planted SV catalogue, described as arrays (no per-read Python): what `search` + `call` see of it.
+# ---------------------------------------------------------------------------------------------
+def make_sv_catalogue_arrays(contig_offs, n_svs=20000, seed=5, min_len=50, max_len=5000):
+    """Planted het/hom INS/DEL over the whole reference, one per equal-sized cell of the concatenated contigs
+    (inside the cell's central half, so two SVs never share a read), cells touching a contig end dropped.
+    Returns dict of arrays sorted by position: gpos (global 0-based base AFTER which the event happens),
+    contig, pos (contig-relative), is_del, len, hapmask (bit 0 / 1 = carried by haplotype 1 / 2), id."""
+    rng = np.random.default_rng(seed)
+    contig_offs = np.asarray(contig_offs, np.int64)
+    total = int(contig_offs[-1])
+    cell = total // n_svs
+    g = (np.arange(n_svs, dtype=np.int64) * cell + cell // 4 + (rng.random(n_svs) * (cell // 2)).astype(np.int64))
+    ln = np.exp(rng.uniform(np.log(min_len), np.log(max_len), n_svs)).astype(np.int64)
+    is_del = rng.random(n_svs) < 0.5
+    u = rng.random(n_svs)
+    hapmask = np.where(u < 0.4, 3, np.where(u < 0.7, 1, 2)).astype(np.int8)
+    ci = np.searchsorted(contig_offs, g, side="right") - 1
+    keep = (g - contig_offs[ci] > 30000) & (contig_offs[ci + 1] - g - ln > 30000)
+    idx = np.nonzero(keep)[0]
+    return dict(gpos=g[idx], contig=ci[idx].astype(np.int32), pos=(g - contig_offs[ci])[idx], is_del=is_del[idx], len=ln[idx],
+                hapmask=hapmask[idx], id=idx.astype(np.int64))
+
+
+def make_sample_region(contig_offs, cat, n_reads, g_start, coverage=30.0, seed=6, mean_len=15000, sd_len=2000, min_len=5000,
+                       max_len=25000, clip_rate=0.05, tag_hp=True):
+    """`n_reads` records of a coordinate-sorted `coverage`x smoothed BAM starting at global position g_start (a slice of
+    config 3: rank r of N takes the r-th slice).  Reads are forward-strand copies of one haplotype of the sample (the
+    reference with the catalogue's SVs of that haplotype applied); a read carries an SV when the event lies >= 150
+    reference bases inside it; `clip_rate` of the reads get a 100-2000 bp random soft-clipped tail.  XF = 0 for reads
+    with an event or a clip (what the Smoother tags as worth searching), 2 otherwise (smoother.cpp:213-231).
+    Returns dict: tid, pos, hp, xf, l_qseq, cigar_offs, cigar (BAM encoding), and `segs` -- the segment recipe of
+    materialize_segments_* for the XF == 0 reads only (`searched` = their record indices): kind 0 reference slice,
+    kind 1 bases hashed from the output position (clips), kind 2 bases hashed from key + offset (the inserted
+    allele: identical in every read that carries it)."""
+    rng = np.random.default_rng(seed)
+    contig_offs = np.asarray(contig_offs, np.int64)
+    total = int(contig_offs[-1])
+    span = int(n_reads * mean_len / coverage)
+    L = np.clip(rng.normal(mean_len, sd_len, n_reads), min_len, max_len).astype(np.int64)
+    a = np.sort((g_start + (rng.random(n_reads) * span).astype(np.int64)) % max(1, total - max_len - 1))
+    ci = np.searchsorted(contig_offs, a, side="right") - 1
+    L = np.minimum(L, contig_offs[ci + 1] - a)          # never across a contig end
+    short = L < min_len
+    a[short] = contig_offs[ci[short] + 1] - min_len
+    L[short] = min_len
+    o = np.lexsort((a, ci))
+    a, L, ci = a[o], L[o], ci[o]
+    b = a + L
+    hap = (rng.random(n_reads) < 0.5).astype(np.int8)   # 0 / 1
+    # the (at most one) SV inside each read: first catalogue entry with gpos + 1 - a >= 150
+    k = np.searchsorted(cat["gpos"], a + 149, side="left")
+    k = np.minimum(k, len(cat["gpos"]) - 1)
+    lo = cat["gpos"][k] + 1
+    hi = lo + np.where(cat["is_del"][k], cat["len"][k], 0)
+    carries = (lo - a >= 150) & (b - hi >= 150) & (((cat["hapmask"][k] >> hap) & 1) == 1)
+    is_ins = carries & ~cat["is_del"][k]
+    is_del = carries & cat["is_del"][k]
+    evlen = np.where(carries, cat["len"][k], 0)
+    clip = rng.random(n_reads) < clip_rate
+    clip_front = clip & (rng.random(n_reads) < 0.5)
+    clip_back = clip & ~clip_front
+    cliplen = np.where(clip, rng.integers(100, 2001, n_reads), 0).astype(np.int64)
+    xf = np.where(carries | clip, 0, 2).astype(np.int32)
+    # CIGAR: [S] M [I|D M] [S]
+    m1 = np.where(carries, lo - a, L)
+    m2 = np.where(carries, b - hi, 0)
+    n_ops = 1 + clip.astype(np.int64) + 2 * carries.astype(np.int64)
+    cigar_offs = np.zeros(n_reads + 1, np.int64)
+    cigar_offs[1:] = np.cumsum(n_ops)
+    cigar = np.zeros(int(cigar_offs[-1]), np.uint32)
+    p = cigar_offs[:-1].copy()
+    f = np.nonzero(clip_front)[0]; cigar[p[f]] = (cliplen[f] << 4) | 4; p[f] += 1
+    cigar[p] = (m1 << 4) | 0; p += 1
+    f = np.nonzero(carries)[0]
+    cigar[p[f]] = (evlen[f] << 4) | np.where(is_del[f], 2, 1); p[f] += 1
+    cigar[p[f]] = (m2[f] << 4) | 0; p[f] += 1
+    f = np.nonzero(clip_back)[0]; cigar[p[f]] = (cliplen[f] << 4) | 4
+    l_qseq = (m1 + m2 + np.where(is_ins, evlen, 0) + cliplen).astype(np.int64)
+    # segments of the searched (XF == 0) reads, in read order
+    s_idx = np.nonzero(xf == 0)[0]
+    ns = len(s_idx)
+    slot_kind = np.stack([np.where(clip_front[s_idx], 1, -1), np.zeros(ns, np.int64), np.where(is_ins[s_idx], 2, -1),
+                          np.where(carries[s_idx], 0, -1), np.where(clip_back[s_idx], 1, -1)], axis=1)
+    slot_len = np.stack([cliplen[s_idx], m1[s_idx], evlen[s_idx], m2[s_idx], cliplen[s_idx]], axis=1)
+    slot_start = np.stack([np.zeros(ns, np.int64), a[s_idx], np.zeros(ns, np.int64), hi[s_idx], np.zeros(ns, np.int64)], axis=1)
+    slot_key = np.zeros((ns, 5), np.int64)
+    slot_key[:, 2] = (cat["id"][k[s_idx]] + 1) * 8192
+    use = (slot_kind >= 0) & (slot_len > 0)
+    seg_read = np.repeat(np.arange(ns), 5).reshape(ns, 5)[use]
+    seg_kind = slot_kind[use].astype(np.int8)
+    seg_len = slot_len[use]
+    seg_out = np.zeros(len(seg_len) + 1, np.int64)
+    seg_out[1:] = np.cumsum(seg_len)
+    read_offs = np.zeros(ns + 1, np.int64)
+    read_offs[1:] = np.cumsum(l_qseq[s_idx])
+    segs = {"kind": seg_kind, "start": slot_start[use], "len": seg_len, "rev": np.zeros(len(seg_len), bool), "read": seg_read,
+            "key": slot_key[use], "out": seg_out, "read_offs": read_offs, "seed": seed}
+    return dict(tid=ci.astype(np.int32), pos=(a - contig_offs[ci]).astype(np.int32), hp=(hap + 1 if tag_hp else 0 * hap).astype(np.int32),
+                xf=xf, l_qseq=l_qseq.astype(np.int32), cigar_offs=cigar_offs, cigar=cigar, searched=s_idx, segs=segs,
+                sv_of_read=np.where(carries, k, -1), span=span, g_start=int(g_start))
