@@ -350,3 +350,61 @@ def call(clusters, reads, ref, min_cluster_weight=2, min_sv_length=25, min_ratio
         return K.Calls(o)
     finally:
         L.orc_calls_free(C.byref(o))
+
+
+def _batch_lib():
+    L = _call_lib()
+    if not hasattr(L, "_batch_ready"):
+        ci, i64 = C.c_int, C.c_int64
+        L.orc_poa_batch.restype = i64
+        L.orc_poa_batch.argtypes = [_u8p, _i64p, _i64p, i64, ci, _u8p, _i64p, _i32p]
+        L.orc_ksw_batch.restype = i64
+        L.orc_ksw_batch.argtypes = [_u8p, _i64p, _u8p, _i64p, i64, ci, _i32p]
+        L.orc_assemble_batch.restype = i64
+        L.orc_assemble_batch.argtypes = [_i64p, _i32p, _i32p, i64, _i32p, _i32p, _i64p]
+        L._batch_ready = True
+    return L
+
+
+def poa_batch(seqs, seq_offs, cluster_offs, threads=0):
+    """banded POA consensus of every cluster (orc_poa under OpenMP): list of code arrays"""
+    seq_offs = np.ascontiguousarray(seq_offs, np.int64)
+    cluster_offs = np.ascontiguousarray(cluster_offs, np.int64)
+    n = len(cluster_offs) - 1
+    lens = np.diff(seq_offs)
+    cap = np.zeros(n + 1, np.int64)
+    for c in range(n):
+        a, b = int(cluster_offs[c]), int(cluster_offs[c + 1])
+        cap[c + 1] = cap[c] + 2 * int(lens[a:b].max() if b > a else 0) + 64
+    cons = np.zeros(int(cap[-1]) + 1, np.uint8)
+    ln = np.zeros(n + 1, np.int32)
+    _batch_lib().orc_poa_batch(_z(seqs), seq_offs, cluster_offs, n, threads, cons, cap, ln)
+    return [cons[int(cap[c]):int(cap[c]) + int(ln[c])].copy() for c in range(n)]
+
+
+def ksw_batch(q, q_offs, t, t_offs, threads=0):
+    """scores of orc_ksw_extd2 for every pair under OpenMP; returns (scores int32, cells)"""
+    q_offs = np.ascontiguousarray(q_offs, np.int64)
+    t_offs = np.ascontiguousarray(t_offs, np.int64)
+    n = len(q_offs) - 1
+    sc = np.zeros(n + 1, np.int32)
+    cells = _batch_lib().orc_ksw_batch(_z(q), q_offs, _z(t), t_offs, n, threads, sc)
+    return sc[:n], int(cells)
+
+
+def assemble_batch(offs, qs, ln):
+    """Assembler::assemble for every read of a search_batch result (records in emit order, descending qs).
+    Returns (qs, len, count per read) with ascending qs inside a read."""
+    offs = np.ascontiguousarray(offs, np.int64)
+    n = len(offs) - 1
+    qs = np.ascontiguousarray(qs, np.int32)
+    ln = np.ascontiguousarray(ln, np.int32)
+    oq = np.zeros(len(qs) + 1, np.int32)
+    ol = np.zeros(len(qs) + 1, np.int32)
+    cnt = np.zeros(n + 1, np.int64)
+    m = _batch_lib().orc_assemble_batch(offs, _z32(qs), _z32(ln), n, oq, ol, cnt)
+    return oq[:m].copy(), ol[:m].copy(), cnt[:n].copy()
+
+
+def _z32(a):
+    return a if len(a) else np.zeros(1, np.int32)

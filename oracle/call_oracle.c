@@ -633,3 +633,66 @@ ORC_API int orc_call(const svb_clusters_t *CL, const svb_seqs_t *RD, const svb_r
   free(J.v); free(jc); free(len); free(p_cons); free(p_cig); free(p_ncons); free(p_ncig);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------ batch helpers
+ * (the CPU legs of bench.py: the same scalar restatements, one item per OpenMP task) */
+
+ORC_API int64_t orc_poa_batch(const uint8_t *seqs, const int64_t *seq_offs, const int64_t *cluster_offs, int64_t n_clusters, int omp_threads,
+                              uint8_t *cons, const int64_t *cons_offs /* n_clusters + 1: capacity slots */, int32_t *cons_len) {
+#ifdef _OPENMP
+  if (omp_threads <= 0) omp_threads = omp_get_max_threads();
+#else
+  omp_threads = 1;
+#endif
+  int64_t cells = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(omp_threads) reduction(+ : cells)
+  for (int64_t c = 0; c < n_clusters; ++c) {
+    const int64_t a = cluster_offs[c], b = cluster_offs[c + 1];
+    int64_t st[3] = {0, 0, 0};
+    const int cap = (int)(cons_offs[c + 1] - cons_offs[c]);
+    int l = orc_poa(seqs, seq_offs + a, (int)(b - a), 1, 2, 4, 4, 2, 24, 1, 10, 0.01, cons + cons_offs[c], cap, st);
+    cons_len[c] = l > cap ? cap : l;
+    cells += st[0];
+  }
+  return cells;
+}
+
+ORC_API int64_t orc_ksw_batch(const uint8_t *q, const int64_t *qo, const uint8_t *t, const int64_t *to, int64_t n, int omp_threads, int32_t *score) {
+#ifdef _OPENMP
+  if (omp_threads <= 0) omp_threads = omp_get_max_threads();
+#else
+  omp_threads = 1;
+#endif
+  int64_t cells = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(omp_threads) reduction(+ : cells)
+  for (int64_t p = 0; p < n; ++p) {
+    const int ql = (int)(qo[p + 1] - qo[p]), tl = (int)(to[p + 1] - to[p]);
+    uint32_t *cg = (uint32_t *)malloc((size_t)(ql + tl + 2) * 4);
+    int ncg = 0;
+    score[p] = orc_ksw_extd2(ql, q + qo[p], tl, t + to[p], 1, -9, -1, 16, 2, 41, 1, cg, ql + tl + 2, &ncg);
+    free(cg);
+    cells += (int64_t)ql * tl;
+  }
+  return cells;
+}
+
+/* Assembler::assemble (assembler.cpp:34-56) for every read of a batch: records of read r = (qs, len)[offs[r] .. offs[r + 1]) in emit
+ * order (descending qs); out_* hold the assembled records in ascending qs, out_cnt the count per read */
+ORC_API int64_t orc_assemble_batch(const int64_t *offs, const int32_t *qs, const int32_t *len, int64_t n_reads, int32_t *out_qs, int32_t *out_len,
+                                   int64_t *out_cnt) {
+  int64_t m = 0;
+  for (int64_t r = 0; r < n_reads; ++r) {
+    const int64_t a = offs[r], b = offs[r + 1];
+    int64_t i = b - 1, c = 0;          /* descending input: walk it backwards = ascending qs (stable for equal qs is moot: qs strictly decrease) */
+    while (i >= a) {
+      int64_t j = i - 1;
+      int end = qs[i] + len[i];
+      int prev_q = qs[i], prev_l = len[i];
+      while (j >= a && prev_q + prev_l > qs[j]) { end = qs[j] + len[j]; prev_q = qs[j]; prev_l = len[j]; --j; }
+      out_qs[m] = qs[i]; out_len[m] = end - qs[i]; ++m; ++c;
+      i = j;
+    }
+    out_cnt[r] = c;
+  }
+  return m;
+}

@@ -440,6 +440,21 @@ def poa_batch(clusters, device=0):
         lib().svb_poa_out_free(C.byref(out))
 
 
+def poa_batch_arrays(cat, seq_offs, cl_offs, device=0):
+    """svb_poa_batch on ready arrays: codes 0..4 concatenated, int64 offsets of the sequences and of the clusters"""
+    cat = np.ascontiguousarray(cat, np.uint8)
+    if len(cat) == 0:
+        cat = np.zeros(1, np.uint8)
+    seq_offs = np.ascontiguousarray(seq_offs, np.int64)
+    cl_offs = np.ascontiguousarray(cl_offs, np.int64)
+    out = PoaOut()
+    check(lib().svb_poa_batch(_ptr(cat), _ptr(seq_offs), _ptr(cl_offs), len(cl_offs) - 1, device, C.byref(out)))
+    try:
+        return PoaResult(out)
+    finally:
+        lib().svb_poa_out_free(C.byref(out))
+
+
 NT16_OF_NT6 = np.array([15, 1, 2, 4, 8, 15], np.uint8)   # nt6 code -> htslib nt16 code (N for $ / N)
 
 

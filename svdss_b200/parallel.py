@@ -25,35 +25,42 @@ def shard_reads_by_bases(offs, world):
     return [min(max(c, cuts[i - 1] if i else 0), len(offs) - 1) for i, c in enumerate(cuts)]
 
 
-def gather_sfs(local_counts, local_qs, local_len, dist, dst=0, device="cpu"):
-    """Gather per-read SFS tables on rank `dst` in global read order.
-    local_counts: int64[n_local_reads]; local_qs/local_len: int32[sum(counts)].
-    Two collectives: all_gather of the (fixed-size) shard sizes, then a padded all_gather of the
-    payload -- the payload is tiny (12 B per SFS), latency- not bandwidth-bound."""
+def gather_rows(local, dist, dst=0, device="cpu"):
+    """Gather int32 tables of shape [n_r, k] (k equal on every rank) on rank `dst`, rank order; None elsewhere.
+    One tiny all_gather of the row counts, then ONE padded gather to `dst` -- nobody but `dst` receives payload."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
-    sizes = torch.tensor([len(local_counts), len(local_qs)], dtype=torch.int64, device=device)
-    all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes)
-    all_sizes = [tuple(int(x) for x in s.cpu()) for s in all_sizes]
-    max_r = max(s[0] for s in all_sizes)
-    max_s = max(s[1] for s in all_sizes)
-    pad = torch.zeros(max_r + 2 * max_s, dtype=torch.int64, device=device)
-    pad[:len(local_counts)] = torch.as_tensor(np.asarray(local_counts, np.int64), device=device)
-    pad[max_r:max_r + len(local_qs)] = torch.as_tensor(np.asarray(local_qs, np.int64), device=device)
-    pad[max_r + max_s:max_r + max_s + len(local_len)] = torch.as_tensor(np.asarray(local_len, np.int64), device=device)
-    out = [torch.zeros_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad)
+    local = np.ascontiguousarray(local, np.int32)
+    if local.ndim == 1:
+        local = local.reshape(-1, 1)
+    k = local.shape[1]
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.cpu()[0]) for c in counts]
+    m = max(max(counts), 1)
+    pad = torch.zeros((m, k), dtype=torch.int32, device=device)
+    if local.shape[0]:
+        pad[:local.shape[0]] = torch.as_tensor(local, device=device)
+    out = [torch.zeros_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, out, dst=dst)
     if rank != dst:
         return None
-    counts, qs, ln = [], [], []
-    for (nr, ns), t in zip(all_sizes, out):
-        t = t.cpu().numpy()
-        counts.append(t[:nr]); qs.append(t[max_r:max_r + ns].astype(np.int32)); ln.append(t[max_r + max_s:max_r + max_s + ns].astype(np.int32))
-    counts = np.concatenate(counts)
+    return np.concatenate([t.cpu().numpy()[:c] for t, c in zip(out, counts)], axis=0)
+
+
+def gather_sfs(local_counts, local_qs, local_len, dist, dst=0, device="cpu"):
+    """Gather per-read SFS tables on rank `dst` in global read order (the path's only exchange).
+    local_counts: int[n_local_reads]; local_qs/local_len: int32[sum(counts)].  int32 on the wire, payload to `dst` only."""
+    counts = gather_rows(np.asarray(local_counts, np.int32), dist, dst, device)
+    recs = gather_rows(np.stack([np.asarray(local_qs, np.int32), np.asarray(local_len, np.int32)], axis=1) if len(local_qs)
+                       else np.zeros((0, 2), np.int32), dist, dst, device)
+    if counts is None:
+        return None
+    counts = counts[:, 0].astype(np.int64)
     offs = np.zeros(len(counts) + 1, np.int64)
     offs[1:] = np.cumsum(counts)
-    return offs, np.concatenate(qs), np.concatenate(ln)
+    return offs, recs[:, 0].copy(), recs[:, 1].copy()
 
 
 # ---- `call`: clusters are independent (caller.cpp:312-313); shard them by cost, gather the ragged results

@@ -501,3 +501,74 @@ def make_sample_region(contig_offs, cat, n_reads, g_start, coverage=30.0, seed=6
     return dict(tid=ci.astype(np.int32), pos=(a - contig_offs[ci]).astype(np.int32), hp=(hap + 1 if tag_hp else 0 * hap).astype(np.int32),
                 xf=xf, l_qseq=l_qseq.astype(np.int32), cigar_offs=cigar_offs, cigar=cigar, searched=s_idx, segs=segs,
                 sv_of_read=np.where(carries, k, -1), span=span, g_start=int(g_start))
+
+
+def _hash_codes(idx, seed):
+    """codes 0..3 hashed from 64-bit indices"""
+    return (_hash_bases_np(np.asarray(idx, np.int64), seed) - 1).astype(np.uint8)
+
+
+def gen_clusters_fast(n, seed=6, lo=200, hi=2000):
+    """Config 4 at scale, vectorised: the recipe of gen_clusters (template of log-uniform length, 20-60 reads per cluster,
+    0.1 % substitutions, half the reads with one INS or DEL of up to 3 % of the template) as arrays.
+    Returns (codes uint8 concatenated, seq_offs int64[n_reads + 1], cluster_offs int64[n + 1])."""
+    rng = np.random.default_rng(seed)
+    tlen = np.exp(rng.uniform(np.log(lo), np.log(hi), n)).astype(np.int64)
+    nr = rng.integers(20, 61, n)
+    toff = np.zeros(n + 1, np.int64)
+    toff[1:] = np.cumsum(tlen)
+    pool = rng.integers(0, 4, int(toff[-1]), dtype=np.uint8)
+    co = np.zeros(n + 1, np.int64)
+    co[1:] = np.cumsum(nr)
+    R = int(co[-1])
+    cl = np.repeat(np.arange(n), nr)
+    tl = tlen[cl]
+    ev = rng.random(R) < 0.5
+    is_ins = ev & (rng.random(R) < 0.5)
+    is_del = ev & ~is_ins
+    L = np.where(ev, (rng.random(R) * np.maximum(1, (tl * 0.03).astype(np.int64) - 1)).astype(np.int64) + 1, 0)
+    p = (rng.random(R) * np.maximum(1, tl - L - 2)).astype(np.int64) + 1
+    L = np.minimum(L, np.maximum(tl - p - 1, 0))
+    rl = tl + np.where(is_ins, L, 0) - np.where(is_del, L, 0)
+    so = np.zeros(R + 1, np.int64)
+    so[1:] = np.cumsum(rl)
+    tot = int(so[-1])
+    rid = np.repeat(np.arange(R), rl)
+    w = np.arange(tot, dtype=np.int64) - so[rid]                    # offset in the read
+    pr, Lr = p[rid], L[rid]
+    in_ins = is_ins[rid] & (w >= pr) & (w < pr + Lr)
+    src = np.where(w < pr, w, np.where(is_ins[rid], w - Lr, np.where(is_del[rid], w + Lr, w)))
+    out = pool[toff[cl[rid]] + np.where(in_ins, 0, src)]
+    gi = np.arange(tot, dtype=np.int64)
+    out = np.where(in_ins, _hash_codes(gi, seed + 1), out)
+    sub = rng.random(tot) < 0.001
+    out = np.where(sub, (out + 1 + _hash_codes(gi, seed + 2) % 3) % 4, out).astype(np.uint8)
+    return np.ascontiguousarray(out), so, co
+
+
+def gen_pairs_fast(n, seed=7, lo=100, hi=10000):
+    """Config 5 at scale, vectorised: target of log-uniform length, query = target with one planted INS or DEL of 50-1000 bp
+    (at most half the target) + 0.2 % substitutions.  Returns (q codes, q_offs, t codes, t_offs)."""
+    rng = np.random.default_rng(seed)
+    tl = np.exp(rng.uniform(np.log(lo), np.log(hi), n)).astype(np.int64)
+    to = np.zeros(n + 1, np.int64)
+    to[1:] = np.cumsum(tl)
+    t = rng.integers(0, 4, int(to[-1]), dtype=np.uint8)
+    L = np.minimum(rng.integers(50, 1001, n), np.maximum(1, tl // 2))
+    p = (rng.random(n) * np.maximum(1, tl - L - 2)).astype(np.int64) + 1
+    is_ins = rng.random(n) < 0.5
+    ql = tl + np.where(is_ins, L, -L)
+    qo = np.zeros(n + 1, np.int64)
+    qo[1:] = np.cumsum(ql)
+    tot = int(qo[-1])
+    rid = np.repeat(np.arange(n), ql)
+    w = np.arange(tot, dtype=np.int64) - qo[rid]
+    pr, Lr, ins = p[rid], L[rid], is_ins[rid]
+    in_ins = ins & (w >= pr) & (w < pr + Lr)
+    src = np.where(w < pr, w, np.where(ins, w - Lr, w + Lr))
+    q = t[to[rid] + np.where(in_ins, 0, src)]
+    gi = np.arange(tot, dtype=np.int64)
+    q = np.where(in_ins, _hash_codes(gi, seed + 1), q)
+    sub = rng.random(tot) < 0.002
+    q = np.where(sub, (q + 1 + _hash_codes(gi, seed + 2) % 3) % 4, q).astype(np.uint8)
+    return np.ascontiguousarray(q), qo, t, to

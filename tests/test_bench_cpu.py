@@ -56,7 +56,7 @@ def test_call_stage_child_always_returns_an_object():
     if capi.lib().svb_device_count() < 1:
         assert "no CUDA device" in r["error"] and "no CPU fallback" in r["error"]   # the product path fails loudly
     else:
-        assert r["poa"]["clusters"] > 0 and r["ksw2"]["pairs"] > 0
+        assert r["poa"]["clusters"] > 0 and r["ksw2"]["pairs"] > 0 and r["poa"]["cpu_oracle"]["identical_consensus"]
     r = bench.call_stage_child(0, limit_s=0.01)                                     # a hang costs the time limit, not the line
     assert "did not finish" in r["error"]
 
@@ -73,9 +73,19 @@ def test_host_pack2_rate_on_a_small_batch():
     assert r["GB_s_of_4bit_input"] > 0 and r["sample_bytes"] == int(s4o[150] - s4o[0]) and r["reads_with_other_codes"] == with_n
 
 
+def test_sv_scoring_and_host_threads(monkeypatch):
+    truth = {(0, False, 300, 1000), (1, True, 80, 5000)}
+    tab = np.array([[0, 0, 1001, 300], [1, 1, 5060, 80], [1, 1, 9000, 80]], np.int32)
+    s = bench.score_calls(tab, truth)
+    assert s == {"planted_with_two_carriers": 2, "recovered_exact_type_and_length": 2, "records": 3, "records_matching_no_planted_sv": 1}
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")          # what torchrun exports: the CPU arms must not shrink to one thread
+    assert bench.host_threads() == len(os.sched_getaffinity(0))
+
+
 def test_the_line_carries_the_contract_keys():
     src = open(os.path.join(ROOT, "bench.py")).read()
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                 "dtype", "data", "config", "workload", "e2e", "h2d_bytes_per_step", "d2h_bytes_per_step", "gpu_launches", "roofline",
                 "bound", "achieved", "peak", "frac", "traffic", "cpu_baseline", "cores", "kind", "sample", "clocks", "impl"):
         assert '"%s"' % key in src, key
+    assert "(search+call)" in src

@@ -92,3 +92,36 @@ def test_config3_generator_through_the_oracle_pipeline():
     for tid, is_del, l, pos in want:
         assert any(g[0] == tid and g[1] == is_del and g[2] == l and abs(g[3] - (pos + 1)) <= l + 2 for g in got), (tid, is_del, l, pos, sorted(got))
     assert len(got) <= len(want) + 2
+
+
+def test_batch_helpers_equal_their_scalar_forms():
+    rng = np.random.default_rng(5)
+    seqs, so, co = synth.gen_clusters_fast(12, seed=9, lo=60, hi=300)
+    assert len(co) == 13 and (np.diff(co) >= 20).all() and seqs.max() <= 3
+    cons = oracle.poa_batch(seqs, so, co, threads=2)
+    for c in range(12):
+        one = [seqs[so[i]:so[i + 1]] for i in range(co[c], co[c + 1])]
+        assert np.array_equal(cons[c], oracle.poa_consensus(one, band=True))
+        # half the reads differ from the template by one planted event: lengths within 3 %
+        ls = np.diff(so)[co[c]:co[c + 1]]
+        assert ls.max() - ls.min() <= 0.07 * ls.max() + 2
+    qc, qo, tc, to = synth.gen_pairs_fast(40, seed=10, lo=100, hi=900)
+    sc, cells = oracle.ksw_batch(qc, qo, tc, to, threads=2)
+    assert cells == int((np.diff(qo) * np.diff(to)).sum())
+    for p in range(40):
+        s1, cig = oracle.ksw_extd2(qc[qo[p]:qo[p + 1]], tc[to[p]:to[p + 1]])
+        assert s1 == sc[p]
+        big = [l for l, op in cig if op != "M" and l >= 40]
+        assert len(big) >= 1                                   # the planted INS / DEL shows in the alignment
+    # assemble_batch on emit-order records
+    offs, qs, ln = [0], [], []
+    for _ in range(50):
+        k = int(rng.integers(0, 6))
+        q = np.sort(rng.choice(500, size=k, replace=False))[::-1]
+        qs += q.tolist(); ln += rng.integers(1, 80, k).tolist(); offs.append(len(qs))
+    aq, al, cnt = oracle.assemble_batch(offs, qs, ln)
+    m = 0
+    for r in range(50):
+        exp = oracle.assemble(list(zip(qs[offs[r]:offs[r + 1]], ln[offs[r]:offs[r + 1]])))
+        assert list(zip(aq[m:m + cnt[r]].tolist(), al[m:m + cnt[r]].tolist())) == exp
+        m += int(cnt[r])
