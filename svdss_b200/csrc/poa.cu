@@ -174,7 +174,7 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
         PCHECK(cudaMemGetInfo(&free_b, &total_b));
         const char* eg = getenv("SVB_POA_GROUP");
         const int group = eg ? atoi(eg) : 32;
-        if (group != 32 && group != 16 && group != 8) { set_error("SVB_POA_GROUP must be 32, 16 or 8"); rc = SVB_EINVAL; goto done; }
+        if (group != 32) { set_error("SVB_POA_GROUP: only 32 lanes per cluster are built (16 and 8 were measured slower, profiles/r02a_variants_sweep.txt)"); rc = SVB_EINVAL; goto done; }
         const int per_cta = 128 / group;   // clusters in flight per CTA
         int64_t slots = std::min<int64_t>((int64_t)part.size(), (int64_t)sms * per_cta * SVB_POA_MINB);
         const char* eb = getenv("SVB_POA_WS_BYTES");
@@ -211,13 +211,9 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       break;
   #define POA_LAUNCH(VV) POA_LAUNCH_G(VV, 32)
         switch (group * 100 + variant) {
-          POA_LAUNCH(0) POA_LAUNCH(1) POA_LAUNCH(2) POA_LAUNCH(3) POA_LAUNCH(4) POA_LAUNCH(6) POA_LAUNCH(7)
-          POA_LAUNCH(8) POA_LAUNCH(14) POA_LAUNCH(15) POA_LAUNCH(16) POA_LAUNCH(18) POA_LAUNCH(30) POA_LAUNCH(31)
-          POA_LAUNCH(32) POA_LAUNCH(33) POA_LAUNCH(39) POA_LAUNCH(63)
-          POA_LAUNCH_G(0, 16) POA_LAUNCH_G(7, 16) POA_LAUNCH_G(31, 16) POA_LAUNCH_G(63, 16)
-          POA_LAUNCH_G(0, 8) POA_LAUNCH_G(7, 8) POA_LAUNCH_G(31, 8) POA_LAUNCH_G(63, 8)
+          POA_LAUNCH(0) POA_LAUNCH(7) POA_LAUNCH(63) POA_LAUNCH(71) POA_LAUNCH(135) POA_LAUNCH(263) POA_LAUNCH(199) POA_LAUNCH(455) POA_LAUNCH(487)
           default:
-            set_error("SVB_POA_VARIANT=%d with SVB_POA_GROUP=%d is not built (group 32: 0 1 2 3 4 6 7 8 14 15 16 18 30 31 32 33 39 63; 16 and 8: 0 7 31 63)", variant, group);
+            set_error("SVB_POA_VARIANT=%d is not built (0 7 63 71 135 199 263 455 487)", variant);
             rc = SVB_EINVAL;
             goto done;
         }

@@ -41,6 +41,7 @@ struct PoaWs {
   int *op_node, *op_q, *new_anchor, *new_id;
   int *H, *E1, *E2;
   unsigned* TB;
+  int4* rowinfo;   // per rank: (node, in1, c = ql - remain + 1, base) of the read being added (POA_V_ROWS)
 };
 
 __host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
@@ -56,6 +57,7 @@ __host__ __device__ inline int64_t poa_ws_carve(uint8_t* p, int ncap, int ecap, 
   TAKE_I(beg, ncap); TAKE_I(end, ncap); TAKE_I(cnt, ncap + 2); TAKE_I(in1, ncap);
   TAKE_I(efrom, ecap); TAKE_I(eto, ecap); TAKE_I(ew, ecap); TAKE_I(enin, ecap); TAKE_I(enout, ecap);
   TAKE_I(op_node, ncap + lmax + 4); TAKE_I(op_q, ncap + lmax + 4); TAKE_I(new_anchor, lmax + 2); TAKE_I(new_id, lmax + 2);
+  a = take((int64_t)ncap * 16); if (w) w->rowinfo = reinterpret_cast<int4*>(p + a);
   TAKE_I(H, (int64_t)ncap * wcap); TAKE_I(E1, (int64_t)ncap * wcap); TAKE_I(E2, (int64_t)ncap * wcap);
   a = take((int64_t)ncap * wcap * 4); if (w) w->TB = reinterpret_cast<unsigned*>(p + a);
 #undef TAKE_I
@@ -114,7 +116,17 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane, unsigned gmask) {
 // 32 LEAN   DP rows with fewer dependent shuffles: the row maximum and its first / last column through REDUX
 //           (__reduce_max_sync / __reduce_min_sync, 3 instructions instead of 15 shuffle steps), the two
 //           "gap was extended" comparisons handed to the next lane as two bits instead of their four operands
-constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, POA_V_TBPF = 16, POA_V_LEAN = 32;
+//  64 ROWS    (needs PARN) the per-read setup leaves one 16-byte record per rank -- node, first predecessor, band
+//            centre, base -- and the row loop fetches 32 of them with one coalesced load per lane, a block ahead,
+//            handing them out by shuffle: no dependent order[] -> in1[] / remain[] / base[] chain per row any more
+// 128 TBSPEC traceback by speculation: 32 lanes read the traceback words of the next 32 steps assuming the path
+//            keeps running down the diagonal of a chain of consecutive node ids (the common case by far); a ballot
+//            finds how many steps the guess holds for, those are emitted at once, lane 0 takes the odd step
+// 256 UPDPAR graph update in windows of 32 alignment ops: every lane checks "its node carries the read's base and the
+//            edge from the previous op's node exists" and bumps that edge's weight; lane 0 handles the first op of a
+//            window that is not of that kind (new node, new edge, aligned-ring lookup) and the window restarts after it
+constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, POA_V_TBPF = 16, POA_V_LEAN = 32, POA_V_ROWS = 64,
+              POA_V_TBSPEC = 128, POA_V_UPDPAR = 256;
 
 __device__ __forceinline__ void poa_prefetch(const void* p) {
 #ifdef __CUDA_ARCH__
@@ -133,7 +145,10 @@ template <int V, int G = 32>
 __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   extern __shared__ int poa_smem[];
   constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0,
-                 TBPF = (V & POA_V_TBPF) != 0, LEAN = (V & POA_V_LEAN) != 0;
+                 TBPF = (V & POA_V_TBPF) != 0, LEAN = (V & POA_V_LEAN) != 0, ROWS = (V & POA_V_ROWS) != 0, TBSPEC = (V & POA_V_TBSPEC) != 0,
+                 UPDPAR = (V & POA_V_UPDPAR) != 0;
+  static_assert(!ROWS || PARN, "ROWS builds its records in the warp-parallel setup");
+  static_assert(!(TBSPEC && TBPF) && !(UPDPAR && PREF), "TBSPEC / UPDPAR replace TBPF / PREF");
   static_assert(G == 32 || G == 16 || G == 8, "group width");
   const int lane = threadIdx.x & (G - 1);
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
@@ -220,6 +235,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
             if (lane > s && valid && bv == vs) rem = rs;
           }
           if (valid) W.remain[v] = rem + 1;
+          if (ROWS && valid && r >= 0) W.rowinfo[r] = make_int4(v, W.in1[v], ql - (rem + 1) + 1, (int)W.base[v]);
           __syncwarp(gmask);
         }
       } else if (lane == 0) {
@@ -259,16 +275,29 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       // computed, the first predecessor sits next to them (in1 = pred << 1 | has-more-in-edges), and a
       // predecessor that is the row just finished hands its band over in registers: the common row
       // (one in-edge, from the previous row) waits for its predecessor's scores only.
-      int v_next = n_ord > 0 ? W.order[0] : 0;
-      int nx_in1 = W.in1[v_next], nx_remain = W.remain[v_next], nx_base = W.base[v_next];
+      int v_next = (!ROWS && n_ord > 0) ? W.order[0] : 0;
+      int nx_in1 = ROWS ? 0 : W.in1[v_next], nx_remain = ROWS ? 0 : W.remain[v_next], nx_base = ROWS ? 0 : W.base[v_next];
+      int4 ri_cur = make_int4(0, 0, 0, 0), ri_nxt = make_int4(0, 0, 0, 0);   // ROWS: this lane's record of the current / next block of G rows
+      if (ROWS && lane < n_ord) ri_nxt = W.rowinfo[lane];
       int v_prev = 0, b_prev = 0, en_prev = W.end[0], l_prev = 1, r_prev = 1;   // the source row
       prev_sm = SMEM && en_prev < Ws;
       for (int r = 0; r < n_ord; ++r) {
-        const int v = v_next, in1 = nx_in1, bv = nx_base;
-        const int c = ql - nx_remain + 1;
-        if (r + 1 < n_ord) {                          // in flight while this row is computed
-          v_next = W.order[r + 1];
-          nx_in1 = W.in1[v_next]; nx_remain = W.remain[v_next]; nx_base = W.base[v_next];
+        int v, in1, bv, c;
+        if (ROWS) {
+          const int src = r & (G - 1);
+          if (src == 0) {                               // a new block: the records fetched a block ago, and the next fetch goes out
+            ri_cur = ri_nxt;
+            if (r + G + lane < n_ord) ri_nxt = W.rowinfo[r + G + lane];
+          }
+          v = __shfl_sync(gmask, ri_cur.x, src, G); in1 = __shfl_sync(gmask, ri_cur.y, src, G);
+          c = __shfl_sync(gmask, ri_cur.z, src, G); bv = __shfl_sync(gmask, ri_cur.w, src, G);
+        } else {
+          v = v_next; in1 = nx_in1; bv = nx_base;
+          c = ql - nx_remain + 1;
+          if (r + 1 < n_ord) {                          // in flight while this row is computed
+            v_next = W.order[r + 1];
+            nx_in1 = W.in1[v_next]; nx_remain = W.remain[v_next]; nx_base = W.base[v_next];
+          }
         }
         const bool single = !(in1 & 1);
         const int p0 = in1 >> 1;
@@ -492,7 +521,46 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
           if (val > best) { best = val; best_p = p; }
         }
         t_v = best_p; t_j = ql; t_state = 0;
-        if (!TBPF) while (t_v != 0 || t_j > 0) tb_step();
+        if (!TBPF && !TBSPEC) while (t_v != 0 || t_j > 0) tb_step();
+      }
+      if (TBSPEC) {
+        for (;;) {
+          const int cv = __shfl_sync(gmask, t_v, 0, G), cj = __shfl_sync(gmask, t_j, 0, G), cs = __shfl_sync(gmask, t_state, 0, G);
+          const int cnop = __shfl_sync(gmask, nop, 0, G);
+          if (cv == 0 && cj <= 0) break;
+          int m = 0, nv = 0;
+          if (cs == 0 && cv >= 2) {
+            // lane k guesses step k: node cv - k, column cj - k, arriving in state H.  The guess holds when the cell's
+            // H came from the diagonal through in-edge 0 (then the step emits (node, column - 1) and moves to the first
+            // predecessor); the NEXT guess holds only if that predecessor is node - 1.
+            const int pv = cv - lane, pj = cj - lane;
+            bool ok = pv >= 2 && pj >= 1;
+            int pred = 0;
+            if (ok) {
+              const int in1v = W.in1[pv], bg = W.beg[pv], en_ = W.end[pv];
+              ok = pj >= bg && pj <= en_;
+              if (ok) {
+                const unsigned t = W.TB[(int64_t)pv * Wc + pj - bg];
+                ok = (t & 7u) == 0u && ((t >> 12) & 0xffu) == 0u;
+                pred = in1v >> 1;
+              }
+            }
+            const unsigned low = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+            const unsigned shift = (threadIdx.x & 31) & ~(G - 1);
+            const unsigned okm = (__ballot_sync(gmask, ok) >> shift) & low, chm = (__ballot_sync(gmask, ok && pred == pv - 1) >> shift) & low;
+            const int bad_ok = (~okm & low) ? __ffs((int)(~okm & low)) - 1 : G, bad_ch = (~chm & low) ? __ffs((int)(~chm & low)) - 1 : G;
+            m = min(bad_ok, bad_ch + 1);
+            if (m > G) m = G;
+            if (lane < m) { W.op_node[cnop + lane] = pv; W.op_q[cnop + lane] = pj - 1; }
+            nv = __shfl_sync(gmask, pred, m > 0 ? m - 1 : 0, G);
+          }
+          __syncwarp(gmask);
+          if (lane == 0) {
+            if (m > 0) { nop += m; t_v = nv; t_j = cj - m; t_state = 0; }
+            if (m < G && (t_v != 0 || t_j > 0)) tb_step();
+          }
+          __syncwarp(gmask);
+        }
       }
       if (TBPF) {
         // The traceback words were written rows ago and have left the caches: every step of the walk is a DRAM
@@ -521,10 +589,52 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       if (lane == 0) {
         PHASE(t_tb);
         nop_b = nop;
-        if (!PREF) {
+        if (!PREF && !UPDPAR) {
           for (int k = nop - 1; k >= 0; --k) if (!add_op(k)) break;
           finish_update();
         }
+      }
+      if (UPDPAR) {
+        const int nop_all = __shfl_sync(gmask, nop_b, 0, G);
+        const unsigned low = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+        const unsigned shift = (threadIdx.x & 31) & ~(G - 1);
+        int lastv = -1;                       // lane 0: node of the last fast op; its anchor is computed when a slow op needs it
+        int k0 = nop_all - 1;
+        while (k0 >= 0) {
+          const int kk = k0 - lane;
+          const int v = kk >= 0 ? W.op_node[kk] : -2, qi = kk >= 0 ? W.op_q[kk] : -1;
+          const bool reg = kk >= 0 && v >= 0 && qi >= 0 && W.base[v] == q[qi];
+          const unsigned rm = (__ballot_sync(gmask, reg) >> shift) & low;
+          const int m1 = (~rm & low) ? __ffs((int)(~rm & low)) - 1 : G;
+          int u = __shfl_up_sync(gmask, v, 1, G);
+          const int up = __shfl_sync(gmask, u_prev, 0, G);
+          if (lane == 0) u = up;
+          int e = -1;
+          if (lane < m1) for (e = W.first_out[u]; e >= 0; e = W.enout[e]) if (W.eto[e] == v) break;
+          const unsigned fm = (__ballot_sync(gmask, lane < m1 && e >= 0) >> shift) & low;
+          const int m2 = (~fm & low) ? __ffs((int)(~fm & low)) - 1 : G;
+          if (lane < m2) W.ew[e]++;
+          const int vlast = __shfl_sync(gmask, v, m2 > 0 ? m2 - 1 : 0, G);
+          __syncwarp(gmask);
+          bool stop = false;
+          if (lane == 0) {
+            if (m2 > 0) { u_prev = vlast; lastv = vlast; }
+            if (m2 < G && k0 - m2 >= 0) {
+              if (lastv >= 0) {               // abpoa's anchor of the last aligned op: 1 + the highest old rank in its aligned ring
+                int mr = W.rank[lastv];
+                for (int x = W.ring[lastv]; x != lastv; x = W.ring[x]) if (x < n_old && W.rank[x] > mr) mr = W.rank[x];
+                u_anchor = mr + 1;
+                lastv = -1;
+              }
+              stop = !add_op(k0 - m2);
+            }
+          }
+          stop = __shfl_sync(gmask, (int)stop, 0, G) != 0;
+          __syncwarp(gmask);
+          if (stop) break;
+          k0 -= m2 + (m2 < G ? 1 : 0);
+        }
+        if (lane == 0) finish_update();
       }
       if (PREF) {
         // the same update in windows of 32 ops: first all lanes touch what lane 0 is about to read

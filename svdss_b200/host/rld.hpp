@@ -15,7 +15,7 @@
 // catches coding slips but not a misremembered detail.
 //
 // Layout (little endian):
-//   "RLD\3" | u32 asize<<16 | sbits | u64 n_words | u64 n_frames | u64 mcnt[asize] (symbols per code)
+//   "RLD\3" | u32 asize<<16 | sbits | u64 reserved (0) | u64 n_bytes = 8 * n_words | u64 n_frames | u64 mcnt[asize] (symbols per code)
 //   | u64 words[n_words] | u64 frame[n_frames][asize+1]
 // words[] is cut into chunks of 2^23 words whose last word is never used, and into blocks of
 // 2^sbits words.  A block starts with asize+1 counters -- [0] = symbols, [1+c] = symbols of code c
@@ -93,8 +93,17 @@ class Rld {
     char m[4];
     uint32_t a = 0;
     uint64_t n_words = 0;
-    bool ok = fread(m, 1, 4, f) == 4 && memcmp(m, "RLD\3", 4) == 0 && fread(&a, 4, 1, f) == 1 && fread(&n_words, 8, 1, f) == 1 &&
-              fread(&r.n_frames, 8, 1, f) == 1;
+    // rld_dump (rld0.c): magic, u32 asize << 16 | sbits, 8 bytes reserved for future use (written as 0), n_bytes of the
+    // word stream (always a multiple of 8), n_frames; rld_restore_header reads the three 64-bit words in one go and
+    // ignores the first.  Round 1 of this file wrote (n_words, n_frames) without the reserved word: a first word that is
+    // not 0 marks such a file, which is still read (restated from memory like the rest -- ropebwt3 is not vendored).
+    uint64_t h[3] = {0, 0, 0};
+    long header_bytes = 32;
+    bool ok = fread(m, 1, 4, f) == 4 && memcmp(m, "RLD\3", 4) == 0 && fread(&a, 4, 1, f) == 1 && fread(h, 8, 3, f) == 3;
+    if (ok) {
+      if (h[0] == 0) { ok = (h[1] & 7) == 0; n_words = h[1] >> 3; r.n_frames = h[2]; }
+      else { n_words = h[0]; r.n_frames = h[1]; header_bytes = 24; ok = fseek(f, 24, SEEK_SET) == 0; }
+    }
     if (ok) {
       r.asize = (int)(a >> 16); r.sbits = (int)(a & 0xffff);
       ok = r.asize >= 1 && r.asize <= 15 && r.sbits >= 3 && r.sbits <= 16 && n_words < ((uint64_t)1 << 40) && r.n_frames < ((uint64_t)1 << 40);
@@ -104,7 +113,7 @@ class Rld {
       ok = at >= 0 && fseek(f, 0, SEEK_END) == 0;
       const long fsize = ok ? ftell(f) : -1;
       ok = ok && fsize >= 0 && fseek(f, at, SEEK_SET) == 0 &&
-           (unsigned long long)fsize >= 24ull + 8ull * (unsigned)r.asize + 8ull * n_words + 8ull * r.n_frames * (unsigned)(r.asize + 1);
+           (unsigned long long)fsize >= (unsigned long long)header_bytes + 8ull * (unsigned)r.asize + 8ull * n_words + 8ull * r.n_frames * (unsigned)(r.asize + 1);
     }
     if (ok) {
       r.mcnt.resize((size_t)r.asize);
@@ -172,8 +181,9 @@ class Rld {
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) { err = "cannot write " + path; return false; }
     const uint32_t a = (uint32_t)asize << 16 | (uint32_t)sbits;
-    const uint64_t n_words = e.n_words, n_frames = e.n_frames;
-    bool ok = fwrite("RLD\3", 1, 4, f) == 4 && fwrite(&a, 4, 1, f) == 1 && fwrite(&n_words, 8, 1, f) == 1 && fwrite(&n_frames, 8, 1, f) == 1 &&
+    const uint64_t n_words = e.n_words, n_frames = e.n_frames, reserved = 0, n_bytes = 8 * e.n_words;
+    bool ok = fwrite("RLD\3", 1, 4, f) == 4 && fwrite(&a, 4, 1, f) == 1 && fwrite(&reserved, 8, 1, f) == 1 && fwrite(&n_bytes, 8, 1, f) == 1 &&
+              fwrite(&n_frames, 8, 1, f) == 1 &&
               fwrite(e.mcnt.data() + 1, 8, (size_t)asize, f) == (size_t)asize &&
               fwrite(e.z.data(), 8, (size_t)n_words, f) == (size_t)n_words &&
               fwrite(e.frame.data(), 8, e.frame.size(), f) == e.frame.size();

@@ -164,6 +164,9 @@ inline void __syncwarp(unsigned m = 0xffffffffu) { emu::barrier(m); }
 // REDUX (sm_80+): reduction over the lanes of the mask, every lane gets the result
 inline int __reduce_max_sync(unsigned m, int v) { int r = v; bool any = false; for (int l = 0; l < 32; ++l) if ((m >> l) & 1u) { const int u = emu::xchg(m, v, l); r = any ? (u > r ? u : r) : u; any = true; } return r; }
 inline int __reduce_min_sync(unsigned m, int v) { int r = v; bool any = false; for (int l = 0; l < 32; ++l) if ((m >> l) & 1u) { const int u = emu::xchg(m, v, l); r = any ? (u < r ? u : r) : u; any = true; } return r; }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+struct int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
 inline unsigned __ballot_sync(unsigned m, int pred) { unsigned r = 0; for (int l = 0; l < 32; ++l) if ((m >> l) & 1u) r |= (emu::exchange(m, pred ? 1u : 0u, l) & 1u) << l; return r; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }

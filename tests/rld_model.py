@@ -44,9 +44,12 @@ def header(words, o, asize):
 def parse(path):
     data = open(path, "rb").read()
     assert data[:4] == b"RLD\3"
-    a, n_words, n_frames = struct.unpack_from("<IQQ", data, 4)
+    # rld_dump: magic, u32 asize << 16 | sbits, 8 reserved bytes (zero), n_bytes (a multiple of 8), n_frames, then mcnt[1..asize]
+    a, reserved, n_bytes, n_frames = struct.unpack_from("<IQQQ", data, 4)
+    assert reserved == 0 and n_bytes % 8 == 0
+    n_words = n_bytes // 8
     asize, sbits = a >> 16, a & 0xffff
-    o = 24
+    o = 32
     mcnt = list(struct.unpack_from("<%dQ" % asize, data, o)); o += 8 * asize
     words = list(struct.unpack_from("<%dQ" % n_words, data, o)); o += 8 * n_words
     frame = list(struct.unpack_from("<%dQ" % (n_frames * (asize + 1)), data, o)); o += 8 * n_frames * (asize + 1)
@@ -184,5 +187,5 @@ def encode(path, bwt, asize=6, sbits=3):
     n_words = st["bitpos"] // 64
     del words[n_words:]
     with open(path, "wb") as f:
-        f.write(b"RLD\3" + struct.pack("<IQQ", asize << 16 | sbits, n_words, 0) + struct.pack("<%dQ" % asize, *cnt[1:]) +
+        f.write(b"RLD\3" + struct.pack("<IQQQ", asize << 16 | sbits, 0, 8 * n_words, 0) + struct.pack("<%dQ" % asize, *cnt[1:]) +
                 struct.pack("<%dQ" % n_words, *words))

@@ -154,7 +154,7 @@ def test_stream_longer_than_one_chunk(exe, tmp_path):
     cxx(exe, "encode", raw, fmd)
     assert os.path.getsize(fmd) > (1 << 23) * 8 + 4096
     with open(fmd, "rb") as f:
-        f.seek(24 + 48 + ((1 << 23) - 1) * 8)
+        f.seek(32 + 48 + ((1 << 23) - 1) * 8)                        # header: magic, u32, reserved u64, n_bytes, n_frames, mcnt[6]
         assert f.read(8) == b"\0" * 8                               # the unused word at the end of chunk 0
     cxx(exe, "decode", fmd, back)
     assert np.array_equal(np.fromfile(back, np.uint8), sym)
