@@ -245,9 +245,9 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
     if (RD->mem == SVB_MEM_DEVICE) {
       int64_t *d_src = nullptr, *d_off = nullptr;
       for (int64_t i = 0; i < n_js; ++i) src[(size_t)i] += CL->sub_qs[out->job_sub[i]];
-      QCHECK(cudaMalloc((void**)&d_sub, (size_t)std::max<int64_t>(tot, 1)));
-      cudaError_t e = cudaMalloc((void**)&d_src, (size_t)n_js * 8);
-      if (e == cudaSuccess) e = cudaMalloc((void**)&d_off, ((size_t)n_js + 1) * 8);
+      QCHECK(pmalloc((void**)&d_sub, (size_t)std::max<int64_t>(tot, 1), 0));
+      cudaError_t e = pmalloc((void**)&d_src, (size_t)n_js * 8, 0);
+      if (e == cudaSuccess) e = pmalloc((void**)&d_off, ((size_t)n_js + 1) * 8, 0);
       if (e == cudaSuccess) e = cudaMemcpy(d_src, src.data(), (size_t)n_js * 8, cudaMemcpyHostToDevice);
       if (e == cudaSuccess) e = cudaMemcpy(d_off, seq_offs.data(), ((size_t)n_js + 1) * 8, cudaMemcpyHostToDevice);
       if (e == cudaSuccess) {
@@ -256,7 +256,7 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
         e = cudaGetLastError();
         out->launches += 1;
       }
-      cudaFree(d_src); cudaFree(d_off);
+      pfree(d_src, 0); pfree(d_off, 0);
       QCHECK(e);
       out->h2d_bytes += n_js * 16 + 8;
     } else {
@@ -289,9 +289,9 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
         for (int64_t j = 0; j < nj; ++j) { const int c = out->job_cluster[j]; wsrc[(size_t)j] = R->start[CL->tid[c]] + CL->s[c]; }
         int64_t *d_src = nullptr, *d_off = nullptr;
         uint8_t* d_tw = nullptr;
-        cudaError_t e = cudaMalloc((void**)&d_src, (size_t)nj * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_off, ((size_t)nj + 1) * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&d_tw, tw.size());
+        cudaError_t e = pmalloc((void**)&d_src, (size_t)nj * 8, 0);
+        if (e == cudaSuccess) e = pmalloc((void**)&d_off, ((size_t)nj + 1) * 8, 0);
+        if (e == cudaSuccess) e = pmalloc((void**)&d_tw, tw.size(), 0);
         if (e == cudaSuccess) e = cudaMemcpy(d_src, wsrc.data(), (size_t)nj * 8, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(d_off, to.data(), ((size_t)nj + 1) * 8, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) {
@@ -300,7 +300,7 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
           out->launches += 1;
         }
         if (e == cudaSuccess) e = cudaMemcpy(tw.data(), d_tw, (size_t)to[(size_t)nj], cudaMemcpyDeviceToHost);
-        cudaFree(d_src); cudaFree(d_off); cudaFree(d_tw);
+        pfree(d_src, 0); pfree(d_off, 0); pfree(d_tw, 0);
         QCHECK(e);
         out->d2h_bytes += to[(size_t)nj];
       } else {
@@ -367,7 +367,7 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
   }
 done:
 #undef QCHECK
-  cudaFree(d_sub);
+  pfree(d_sub, 0);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (e2) cudaEventDestroy(e2);

@@ -88,14 +88,14 @@ struct DevArena {   // every device allocation of one call, released together
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   ~DevArena() {
-    for (void* p : ptrs) cudaFree(p);
+    for (void* p : ptrs) pfree(p, stream);
     for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
   template <class T>
   cudaError_t alloc(T** p, size_t n) {
     *p = nullptr;
-    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+    cudaError_t e = pmalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T), stream);
     if (e == cudaSuccess) ptrs.push_back(*p);
     return e;
   }

@@ -28,6 +28,42 @@ void set_error(const char* fmt, ...);
     if (_r != SVB_OK) return _r; \
   } while (0)
 
+// Stream-ordered allocations from the device's default memory pool with an unbounded release
+// threshold: repeated batches reuse the same physical memory instead of paying cudaMalloc/cudaFree
+// (tens of ms per call for multi-GB buffers on some hosts) inside every svb_sfs_* call.
+inline cudaError_t pmalloc(void** p, size_t bytes, cudaStream_t st) {
+  static thread_local int tuned_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (tuned_dev != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    tuned_dev = dev;
+  }
+  return cudaMallocAsync(p, bytes ? bytes : 1, st);
+}
+inline void pfree(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
+// bytes a pmalloc can still get: what the driver reports free plus what the pool holds without using it
+inline cudaError_t pool_available(size_t* avail) {
+  size_t free_b = 0, total_b = 0;
+  cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t pool;
+  uint64_t reserved = 0, used = 0;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+    free_b += (size_t)(reserved - used);
+  *avail = free_b;
+  return cudaSuccess;
+}
+
 // ---------------------------------------------------------------------------------------------
 // FM-index block array ("sampled-Occ BWT blocks") in HBM.
 //

@@ -55,8 +55,8 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
     total_cells += (double)cells[p];
   }
   std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cells[x] > cells[y]; });
-  size_t free_b = 0, total_b = 0;
-  SVB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t free_b = 0;
+  SVB_CUDA(pool_available(&free_b));
   const char* eb = getenv("SVB_KSW_TB_BYTES");
   // one traceback byte per cell: the budget bounds the cells in flight, hence -- for 10 kb x 10 kb pairs of
   // 100 MB each -- the number of warps that have work.  Most of the free HBM by default (round 1 used
@@ -91,14 +91,14 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
   {
     KCHECK(cudaEventCreate(&e0));
     KCHECK(cudaEventCreate(&e1));
-    KCHECK(cudaMalloc((void**)&d_q, std::max<int64_t>(qtot, 1)));
-    KCHECK(cudaMalloc((void**)&d_t, std::max<int64_t>(ttot, 1)));
-    KCHECK(cudaMalloc((void**)&d_qoff, (n_pairs + 1) * 8));
-    KCHECK(cudaMalloc((void**)&d_toff, (n_pairs + 1) * 8));
-    KCHECK(cudaMalloc((void**)&d_order, n_pairs * 4));
-    KCHECK(cudaMalloc((void**)&d_cgn, n_pairs * 4));
-    KCHECK(cudaMalloc((void**)&d_score, n_pairs * 4));
-    KCHECK(cudaMalloc((void**)&d_work, 4));
+    KCHECK(pmalloc((void**)&d_q, (size_t)(std::max<int64_t>(qtot, 1)), 0));
+    KCHECK(pmalloc((void**)&d_t, (size_t)(std::max<int64_t>(ttot, 1)), 0));
+    KCHECK(pmalloc((void**)&d_qoff, (size_t)((n_pairs + 1) * 8), 0));
+    KCHECK(pmalloc((void**)&d_toff, (size_t)((n_pairs + 1) * 8), 0));
+    KCHECK(pmalloc((void**)&d_order, (size_t)(n_pairs * 4), 0));
+    KCHECK(pmalloc((void**)&d_cgn, (size_t)(n_pairs * 4), 0));
+    KCHECK(pmalloc((void**)&d_score, (size_t)(n_pairs * 4), 0));
+    KCHECK(pmalloc((void**)&d_work, (size_t)(4), 0));
     KCHECK(cudaEventRecord(e0, 0));
     if (qtot) KCHECK(cudaMemcpy(d_q, q_concat + q_offs[0], qtot, cudaMemcpyHostToDevice));
     if (ttot) KCHECK(cudaMemcpy(d_t, t_concat + t_offs[0], ttot, cudaMemcpyHostToDevice));
@@ -131,10 +131,10 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
     int64_t max_tb = 1, max_bnd = 1, max_cg = 1, max_cnt = 1;
     for (auto& wv : waves) { max_tb = std::max(max_tb, wv.tb); max_bnd = std::max(max_bnd, wv.bnd); max_cg = std::max(max_cg, wv.cg); max_cnt = std::max(max_cnt, wv.count); }
     max_tb = std::max<int64_t>(max_tb, max_cg * 4 + (max_cnt + 1) * 8 + 512);
-    KCHECK(cudaMalloc((void**)&d_tb, max_tb));
-    KCHECK(cudaMalloc((void**)&d_bnd, max_bnd * 4));
-    KCHECK(cudaMalloc((void**)&d_cg, max_cg * 4));
-    KCHECK(cudaMalloc((void**)&d_woff, max_cnt * 3 * 8));
+    KCHECK(pmalloc((void**)&d_tb, (size_t)(max_tb), 0));
+    KCHECK(pmalloc((void**)&d_bnd, (size_t)(max_bnd * 4), 0));
+    KCHECK(pmalloc((void**)&d_cg, (size_t)(max_cg * 4), 0));
+    KCHECK(pmalloc((void**)&d_woff, (size_t)(max_cnt * 3 * 8), 0));
     // cigar ops are first collected per wave on the device (reverse order), sizes come back to the
     // host, which lays out the final dense table wave by wave
     std::vector<std::vector<uint32_t>> wave_ops(waves.size());
@@ -229,9 +229,9 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
   }
 done:
 #undef KCHECK
-  cudaFree(d_q); cudaFree(d_t); cudaFree(d_tb); cudaFree(d_qoff); cudaFree(d_toff); cudaFree(d_woff);
-  cudaFree(d_outoff); cudaFree(d_order); cudaFree(d_cg); cudaFree(d_out); cudaFree(d_bnd); cudaFree(d_cgn);
-  cudaFree(d_score); cudaFree(d_work);
+  pfree(d_q, 0); pfree(d_t, 0); pfree(d_tb, 0); pfree(d_qoff, 0); pfree(d_toff, 0); pfree(d_woff, 0);
+  pfree(d_outoff, 0); pfree(d_order, 0); pfree(d_cg, 0); pfree(d_out, 0); pfree(d_bnd, 0); pfree(d_cgn, 0);
+  pfree(d_score, 0); pfree(d_work, 0);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (rc != SVB_OK) svb_ksw_out_free(out);

@@ -22,6 +22,10 @@
 
 #include "poa_kernel.cuh"
 
+#ifndef SVB_POA_DEFAULT_VARIANT
+#define SVB_POA_DEFAULT_VARIANT 0
+#endif
+
 namespace svb {
 
 int check_device(int device);
@@ -67,8 +71,9 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
     cap_off[c + 1] = cap_off[c] + ((2 * (int64_t)s.lmax + 64 + 15) & ~15LL);
   }
   uint8_t *d_seqs = nullptr, *d_ws = nullptr, *d_cons = nullptr;
-  int64_t *d_soff = nullptr, *d_coff = nullptr, *d_capoff = nullptr;
+  int64_t *d_soff = nullptr, *d_coff = nullptr, *d_capoff = nullptr, *d_slotoff = nullptr;
   uint32_t* d_order = nullptr;
+  int4* d_dims = nullptr;
   int32_t *d_len = nullptr, *d_status = nullptr;
   unsigned int* d_work = nullptr;
   unsigned long long* d_cells = nullptr;
@@ -89,22 +94,25 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
     }                                                                                       \
   } while (0)
   {
+    // every buffer comes from the device's stream-ordered pool (common.cuh pmalloc): a caller that works through batch
+    // after batch pays for the workspace once, not cudaMalloc + cudaFree of tens of GB in every call
     PCHECK(cudaEventCreate(&e0));
     PCHECK(cudaEventCreate(&e1));
     PCHECK(cudaEventRecord(e0, 0));
     if (seqs_mem == SVB_MEM_DEVICE) d_seqs = const_cast<uint8_t*>(seqs) + s_first;
-    else PCHECK(cudaMalloc((void**)&d_seqs, std::max<int64_t>(s_total, 1)));
-    PCHECK(cudaMalloc((void**)&d_soff, (n_seqs + 1) * 8));
-    PCHECK(cudaMalloc((void**)&d_coff, (n_clusters + 1) * 8));
-    PCHECK(cudaMalloc((void**)&d_capoff, (n_clusters + 1) * 8));
-    PCHECK(cudaMalloc((void**)&d_order, n_clusters * 4));
-    PCHECK(cudaMalloc((void**)&d_len, n_clusters * 4));
-    PCHECK(cudaMalloc((void**)&d_status, n_clusters * 4));
-    PCHECK(cudaMalloc((void**)&d_cons, std::max<int64_t>(cap_off[n_clusters], 1)));
-    PCHECK(cudaMalloc((void**)&d_work, 4));
-    PCHECK(cudaMalloc((void**)&d_cells, 8));
-    PCHECK(cudaMemset(d_cells, 0, 8));
-    if (getenv("SVB_POA_TIMING")) { PCHECK(cudaMalloc((void**)&d_phase, 40)); PCHECK(cudaMemset(d_phase, 0, 40)); }
+    else PCHECK(pmalloc((void**)&d_seqs, (size_t)std::max<int64_t>(s_total, 1), 0));
+    PCHECK(pmalloc((void**)&d_soff, (size_t)(n_seqs + 1) * 8, 0));
+    PCHECK(pmalloc((void**)&d_coff, (size_t)(n_clusters + 1) * 8, 0));
+    PCHECK(pmalloc((void**)&d_capoff, (size_t)(n_clusters + 1) * 8, 0));
+    PCHECK(pmalloc((void**)&d_order, (size_t)n_clusters * 4, 0));
+    PCHECK(pmalloc((void**)&d_dims, (size_t)n_clusters * sizeof(int4), 0));
+    PCHECK(pmalloc((void**)&d_len, (size_t)n_clusters * 4, 0));
+    PCHECK(pmalloc((void**)&d_status, (size_t)n_clusters * 4, 0));
+    PCHECK(pmalloc((void**)&d_cons, (size_t)std::max<int64_t>(cap_off[n_clusters], 1), 0));
+    PCHECK(pmalloc((void**)&d_work, 4, 0));
+    PCHECK(pmalloc((void**)&d_cells, 8, 0));
+    PCHECK(cudaMemsetAsync(d_cells, 0, 8, 0));
+    if (getenv("SVB_POA_TIMING")) { PCHECK(pmalloc((void**)&d_phase, 40, 0)); PCHECK(cudaMemsetAsync(d_phase, 0, 40, 0)); }
     if (s_total && seqs_mem != SVB_MEM_DEVICE) PCHECK(cudaMemcpy(d_seqs, seqs + s_first, s_total, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_soff, so.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_coff, cluster_offs, (n_clusters + 1) * 8, cudaMemcpyHostToDevice));
@@ -112,50 +120,26 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
     out->h2d_bytes = (seqs_mem == SVB_MEM_DEVICE ? 0 : s_total) + (n_seqs + 1) * 8 + (n_clusters + 1) * 16;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const char* eg = getenv("SVB_POA_GROUP");
+    if (eg && atoi(eg) != 32) { set_error("SVB_POA_GROUP: only 32 lanes per cluster are built (16 and 8 were measured slower, profiles/r02a_variants_sweep.txt)"); rc = SVB_EINVAL; goto done; }
+    // kernel variant (poa_kernel.cuh): SVB_POA_VARIANT = bit mask; 0 = the kernel measured in round 1
+    const char* ev = getenv("SVB_POA_VARIANT");
+    const int variant = ev ? atoi(ev) : SVB_POA_DEFAULT_VARIANT;
     // pass 0: heuristic capacities; pass 1: worst-case capacities for the clusters that overflowed
     std::vector<uint32_t> todo((size_t)n_clusters);
     for (int64_t c = 0; c < n_clusters; ++c) todo[c] = (uint32_t)c;
+    std::vector<int4> dims((size_t)n_clusters);
+    std::vector<int64_t> foot((size_t)n_clusters);
     float kms = 0.f;
     for (int pass = 0; pass < 2 && !todo.empty(); ++pass) {
-      std::stable_sort(todo.begin(), todo.end(), [&](uint32_t a, uint32_t b) { return shp[a].cost > shp[b].cost; });
-      // One launch sizes every workspace slot for its largest cluster.  SVB_POA_BUCKETS=K (default 1) cuts the
-      // clusters of a pass into up to K launches by footprint (nodes x band columns, geometric thresholds), so
-      // that small clusters get small slots: more of them fit the workspace budget (what narrow groups need)
-      // and a warp's rows lie closer together.  Results do not depend on it.
-      std::vector<std::vector<uint32_t>> parts;
-      {
-        const char* ek = getenv("SVB_POA_BUCKETS");
-        const int K = std::max(1, std::min(16, ek ? atoi(ek) : 1));
-        auto foot = [&](uint32_t c) {
-          const Shape& s = shp[c];
-          if (!s.nreads) return 1.0;
-          const int w = 10 + (int)(0.01 * s.lmax);
-          const double nc = pass == 0 ? (double)std::min<int64_t>(s.sum + 2, 2 * (int64_t)s.lmax + 32 * s.nreads + 64) : (double)(s.sum + 2);
-          const double wc = pass == 0 ? (double)std::min<int64_t>(s.lmax + 1, 2 * w + 1 + 4 * (s.lmax - s.lmin) + 96) : (double)(s.lmax + 1);
-          return nc * wc;
-        };
-        double fmax = 1.0, fmin = 1e300;
-        for (uint32_t c : todo) { const double f = foot(c); fmax = std::max(fmax, f); fmin = std::min(fmin, f); }
-        const double ratio = K > 1 && fmax > fmin ? pow(fmax / fmin, 1.0 / K) : 0.0;
-        parts.assign((size_t)K, std::vector<uint32_t>());
-        for (uint32_t c : todo) {   // todo is cost-sorted; every part keeps that order
-          int b = 0;
-          if (ratio > 1.0) b = std::min(K - 1, (int)(log(fmax / foot(c)) / log(ratio)));
-          parts[(size_t)b].push_back(c);
-        }
-      }
-      std::vector<uint32_t> again;
-      for (const std::vector<uint32_t>& part : parts) {
-        if (part.empty()) continue;
-        int ncap = 0, wcap = 0, lmax = 1;
-        int64_t ecap = 0;
-        for (uint32_t c : part) {
-          const Shape& s = shp[c];
-          if (!s.nreads) continue;
-          lmax = std::max(lmax, s.lmax);
+      // capacities of every cluster of this pass (nodes, edges, band columns, longest read) and the bytes they carve
+      int wmax = 4;
+      for (uint32_t c : todo) {
+        const Shape& s = shp[c];
+        int64_t nc = 4, wc = 4;
+        if (s.nreads) {
           const int w = 10 + (int)(0.01 * s.lmax);
           const int diff = s.lmax - s.lmin;
-          int64_t nc, wc;
           if (pass == 0) {
             nc = std::min<int64_t>(s.sum + 2, 2 * (int64_t)s.lmax + 32 * s.nreads + 64);
             wc = std::min<int64_t>(s.lmax + 1, 2 * w + 1 + 4 * diff + 96);
@@ -163,75 +147,85 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
             nc = s.sum + 2;
             wc = s.lmax + 1;
           }
-          ncap = (int)std::max<int64_t>(ncap, nc);
-          wcap = (int)std::max<int64_t>(wcap, wc);
         }
-        if (ncap == 0) { ncap = 4; wcap = 4; }
-        wcap = (wcap + 31) & ~31;
-        ecap = 3 * (int64_t)ncap + 64;
-        const int64_t stride = poa_ws_carve(nullptr, ncap, (int)ecap, wcap, lmax, nullptr);
-        size_t free_b = 0, total_b = 0;
-        PCHECK(cudaMemGetInfo(&free_b, &total_b));
-        const char* eg = getenv("SVB_POA_GROUP");
-        const int group = eg ? atoi(eg) : 32;
-        if (group != 32) { set_error("SVB_POA_GROUP: only 32 lanes per cluster are built (16 and 8 were measured slower, profiles/r02a_variants_sweep.txt)"); rc = SVB_EINVAL; goto done; }
-        const int per_cta = 128 / group;   // clusters in flight per CTA
-        int64_t slots = std::min<int64_t>((int64_t)part.size(), (int64_t)sms * per_cta * SVB_POA_MINB);
-        const char* eb = getenv("SVB_POA_WS_BYTES");
-        const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
-        slots = std::min<int64_t>(slots, std::max<int64_t>(1, budget / stride));
-        slots = (slots + per_cta - 1) / per_cta * per_cta;
-        if ((int64_t)slots * stride > (int64_t)free_b) { set_error("POA workspace of %lld bytes per cluster does not fit", (long long)stride); rc = SVB_ENOMEM; goto done; }
-        cudaFree(d_ws); d_ws = nullptr;
-        PCHECK(cudaMalloc((void**)&d_ws, (size_t)slots * stride));
-        PCHECK(cudaMemcpy(d_order, part.data(), part.size() * 4, cudaMemcpyHostToDevice));
-        PCHECK(cudaMemset(d_work, 0, 4));
-        PoaParams P;
-        memset(&P, 0, sizeof(P));
-        P.seqs = d_seqs; P.seq_offs = d_soff; P.cluster_offs = d_coff; P.order = d_order; P.n = (int)part.size();
-        P.work = d_work; P.ws = d_ws; P.ws_stride = stride; P.ncap = ncap; P.ecap = (int)ecap; P.wcap = wcap; P.lmax = lmax;
-        P.cons = d_cons; P.cons_off = d_capoff; P.cons_len = d_len; P.status = d_status; P.cells = d_cells; P.phase = d_phase;
-        P.match = 2; P.mismatch = 4; P.o1 = 4; P.e1 = 2; P.o2 = 24; P.e2 = 1; P.wb = 10; P.wf = 0.01f;  // abpoa_init_para
-        cudaEvent_t k0, k1;
-        PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
-        PCHECK(cudaEventRecord(k0, 0));
-        // kernel variant (poa_kernel.cuh): SVB_POA_VARIANT = bit mask, 0 = the kernel measured in round 1 (default);
-        // SVB_POA_GROUP = lanes per cluster (32 default, 16, 8).  Variants with the shared-memory copy of the
-        // previous row use 2 buffers x 3 arrays x swcap ints per cluster in flight.
-        const char* ev = getenv("SVB_POA_VARIANT");
-        int variant = ev ? atoi(ev) : 0;
-        if (const char* es = getenv("SVB_POA_SMEM")) if (atoi(es) != 0) variant |= POA_V_SMEM | POA_V_TBIN1 | POA_V_PARN;   // round-1 name of variant 7
-        P.swcap = std::min(wcap, 128);
-        const size_t smem = (variant & POA_V_SMEM) ? (size_t)(128 / group) * 6 * (size_t)P.swcap * sizeof(int) : 0;
-        const unsigned grid = (unsigned)((slots * group + 127) / 128);
-  #define POA_LAUNCH_G(VV, GG)                                                                                        \
-    case (GG) * 100 + (VV):                                                                                           \
-      if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<VV, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      k_poa<VV, GG><<<grid, 128, smem>>>(P);                                                                          \
-      break;
-  #define POA_LAUNCH(VV) POA_LAUNCH_G(VV, 32)
-        switch (group * 100 + variant) {
-          POA_LAUNCH(0) POA_LAUNCH(7) POA_LAUNCH(63) POA_LAUNCH(71) POA_LAUNCH(135) POA_LAUNCH(263) POA_LAUNCH(199) POA_LAUNCH(455) POA_LAUNCH(487)
-          default:
-            set_error("SVB_POA_VARIANT=%d is not built (0 7 63 71 135 199 263 455 487)", variant);
-            rc = SVB_EINVAL;
-            goto done;
+        const int wcap = (int)((wc + 31) & ~31LL);
+        const int64_t ecap = 3 * nc + 64;
+        if (nc > 0x3fffffff || ecap > 0x7fffffff) { set_error("cluster %u is too large for the POA workspace", c); rc = SVB_ERANGE; goto done; }
+        dims[c] = make_int4((int)nc, (int)ecap, wcap, std::max(1, s.lmax));
+        foot[c] = poa_ws_carve(nullptr, (int)nc, (int)ecap, wcap, std::max(1, s.lmax), nullptr);
+        wmax = std::max(wmax, wcap);
+      }
+      // Hand-out order = footprint, largest first (footprint ~ nodes x band ~ work: also the longest-processing-time-first
+      // order).  Slot s is sized for the s-th cluster handed out; every cluster handed out later is no bigger than the
+      // smallest slot, so it fits whichever warp picks it up -- and the workspace is the sum of the biggest `slots`
+      // footprints instead of slots x the biggest one.
+      std::stable_sort(todo.begin(), todo.end(), [&](uint32_t a, uint32_t b) { return foot[a] > foot[b]; });
+      size_t free_b = 0;
+      PCHECK(pool_available(&free_b));
+      const char* eb = getenv("SVB_POA_WS_BYTES");
+      const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
+      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * 4 * SVB_POA_MINB);
+      std::vector<int64_t> slot_off((size_t)slots + 1, 0);
+      {
+        int64_t s_ok = 0;
+        for (int64_t s_ = 0; s_ < slots; ++s_) {
+          if (s_ > 0 && slot_off[(size_t)s_] + foot[todo[(size_t)s_]] > budget) break;
+          slot_off[(size_t)s_ + 1] = slot_off[(size_t)s_] + foot[todo[(size_t)s_]];
+          s_ok = s_ + 1;
         }
-  #undef POA_LAUNCH_G
-  #undef POA_LAUNCH
-        PCHECK(cudaGetLastError());
-        PCHECK(cudaEventRecord(k1, 0));
-        PCHECK(cudaEventSynchronize(k1));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, k0, k1);
-        cudaEventDestroy(k0); cudaEventDestroy(k1);
-        kms += ms;
-        out->launches += 1;
-        PCHECK(cudaMemcpy(h_status.data(), d_status, n_clusters * 4, cudaMemcpyDeviceToHost));
-        for (uint32_t c : part) {
-          // clamped band (pass 0 only) or capacity overflow: redo with worst-case capacities
-          if ((h_status[c] & POA_OVERFLOW) || (pass == 0 && (h_status[c] & POA_CLAMPED))) again.push_back(c);
-        }
+        slots = s_ok;
+      }
+      // a CTA is four warps: round the slot count up to whole CTAs by repeating the smallest slot size
+      while (slots % 4) { slot_off.resize((size_t)slots + 2); slot_off[(size_t)slots + 1] = slot_off[(size_t)slots] + foot[todo[(size_t)std::min<int64_t>(slots, (int64_t)todo.size() - 1)]]; ++slots; }
+      slot_off.resize((size_t)slots + 1);
+      if (slot_off[(size_t)slots] > (int64_t)free_b) { set_error("POA workspace of %lld bytes does not fit", (long long)slot_off[(size_t)slots]); rc = SVB_ENOMEM; goto done; }
+      pfree(d_ws, 0); d_ws = nullptr;
+      pfree(d_slotoff, 0); d_slotoff = nullptr;
+      PCHECK(pmalloc((void**)&d_ws, (size_t)slot_off[(size_t)slots], 0));
+      PCHECK(pmalloc((void**)&d_slotoff, (size_t)(slots + 1) * 8, 0));
+      PCHECK(cudaMemcpy(d_slotoff, slot_off.data(), (size_t)(slots + 1) * 8, cudaMemcpyHostToDevice));
+      PCHECK(cudaMemcpy(d_order, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice));
+      PCHECK(cudaMemcpy(d_dims, dims.data(), (size_t)n_clusters * sizeof(int4), cudaMemcpyHostToDevice));
+      PCHECK(cudaMemsetAsync(d_work, 0, 4, 0));
+      PoaParams P;
+      memset(&P, 0, sizeof(P));
+      P.seqs = d_seqs; P.seq_offs = d_soff; P.cluster_offs = d_coff; P.order = d_order; P.n = (int)todo.size();
+      P.work = d_work; P.ws = d_ws; P.slot_off = d_slotoff; P.dims = d_dims; P.n_slots = (int)slots;
+      P.cons = d_cons; P.cons_off = d_capoff; P.cons_len = d_len; P.status = d_status; P.cells = d_cells; P.phase = d_phase;
+      P.match = 2; P.mismatch = 4; P.o1 = 4; P.e1 = 2; P.o2 = 24; P.e2 = 1; P.wb = 10; P.wf = 0.01f;  // abpoa_init_para
+      cudaEvent_t k0, k1;
+      PCHECK(cudaEventCreate(&k0)); PCHECK(cudaEventCreate(&k1));
+      PCHECK(cudaEventRecord(k0, 0));
+      // variants with the shared-memory copy of the previous row use 2 buffers x 3 arrays x swcap ints per warp
+      P.swcap = std::min(wmax, 128);
+      const size_t smem = (variant & POA_V_SMEM) ? (size_t)4 * 6 * (size_t)P.swcap * sizeof(int) : 0;
+      const unsigned grid = (unsigned)(slots / 4);
+#define POA_LAUNCH(VV)                                                                                              \
+  case (VV):                                                                                                        \
+    if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<VV, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_poa<VV, 32><<<grid, 128, smem>>>(P);                                                                          \
+    break;
+      switch (variant) {
+        POA_LAUNCH(0) POA_LAUNCH(7) POA_LAUNCH(63) POA_LAUNCH(71) POA_LAUNCH(135) POA_LAUNCH(263) POA_LAUNCH(199) POA_LAUNCH(455) POA_LAUNCH(487)
+        default:
+          set_error("SVB_POA_VARIANT=%d is not built (0 7 63 71 135 199 263 455 487)", variant);
+          rc = SVB_EINVAL;
+          goto done;
+      }
+#undef POA_LAUNCH
+      PCHECK(cudaGetLastError());
+      PCHECK(cudaEventRecord(k1, 0));
+      PCHECK(cudaEventSynchronize(k1));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, k0, k1);
+      cudaEventDestroy(k0); cudaEventDestroy(k1);
+      kms += ms;
+      out->launches += 1;
+      PCHECK(cudaMemcpy(h_status.data(), d_status, n_clusters * 4, cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> again;
+      for (uint32_t c : todo) {
+        // clamped band (pass 0 only) or capacity overflow: redo with worst-case capacities
+        if ((h_status[c] & POA_OVERFLOW) || (pass == 0 && (h_status[c] & POA_CLAMPED))) again.push_back(c);
       }
       if (pass == 1 && !again.empty()) { set_error("POA workspace overflow persisted for %zu clusters", again.size()); rc = SVB_ERANGE; goto done; }
       todo.swap(again);
@@ -265,9 +259,9 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
   }
 done:
 #undef PCHECK
-  if (seqs_mem != SVB_MEM_DEVICE) cudaFree(d_seqs);
-  cudaFree(d_ws); cudaFree(d_cons); cudaFree(d_soff); cudaFree(d_coff); cudaFree(d_capoff);
-  cudaFree(d_order); cudaFree(d_len); cudaFree(d_status); cudaFree(d_work); cudaFree(d_cells); cudaFree(d_phase);
+  if (seqs_mem != SVB_MEM_DEVICE) pfree(d_seqs, 0);
+  pfree(d_ws, 0); pfree(d_cons, 0); pfree(d_soff, 0); pfree(d_coff, 0); pfree(d_capoff, 0); pfree(d_slotoff, 0); pfree(d_dims, 0);
+  pfree(d_order, 0); pfree(d_len, 0); pfree(d_status, 0); pfree(d_work, 0); pfree(d_cells, 0); pfree(d_phase, 0);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (rc != SVB_OK) svb_poa_out_free(out);

@@ -16,11 +16,14 @@ struct PoaParams {
   const int64_t* __restrict__ cluster_offs;  // n_clusters + 1 (indexes seq_offs)
   const uint32_t* __restrict__ order;        // clusters of this launch, biggest first
   int n;                                     // clusters in this launch
+  int n_slots;                               // workspace slots = warps: slot s takes cluster order[s] first, the rest are handed out by `work`
   unsigned int* work;
-  // workspace, one slot per resident warp
+  // workspace: slot s (one per resident warp) = ws + slot_off[s]; a warp carves its slot anew for every cluster from that
+  // cluster's own capacities dims[cluster] = (ncap, ecap, wcap, lmax) -- slots are sized for the biggest clusters in
+  // hand-out order, every later cluster is smaller than any slot (poa.cu)
   uint8_t* ws;
-  int64_t ws_stride;  // bytes per slot
-  int ncap, ecap, wcap, lmax;
+  const int64_t* __restrict__ slot_off;
+  const int4* __restrict__ dims;
   int swcap;          // columns per array of the shared-memory row copy (variants with POA_V_SMEM)
   // outputs
   uint8_t* cons;                   // cons_cap bytes per cluster, at cons_off[cluster]
@@ -153,12 +156,9 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   const int lane = threadIdx.x & (G - 1);
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
   const int slot = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  uint8_t* wsp = P.ws + (int64_t)slot * P.ws_stride;
+  uint8_t* wsp = P.ws + P.slot_off[slot];
   Graph g;
-  poa_ws_carve(wsp, P.ncap, P.ecap, P.wcap, P.lmax, &g.w);
-  g.ncap = P.ncap; g.ecap = P.ecap;
   const PoaWs& W = g.w;
-  const int Wc = P.wcap;
   const int mm = P.mismatch < 0 ? -P.mismatch : P.mismatch;
   // shared copy of the row just finished: [2 buffers][H, E1, E2][Ws] per group.  Ws = P.swcap may be smaller than
   // the workspace row (wcap is a worst-case bound, a band is usually 35-60 columns): a row wider than Ws is simply
@@ -166,12 +166,19 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
   const int Ws = SMEM ? P.swcap : 0;
   int* const sbuf = SMEM ? poa_smem + (threadIdx.x / G) * 6 * Ws : nullptr;
   bool prev_sm = false;
-  for (;;) {
+  for (bool first_item = true;; first_item = false) {
     unsigned wi = 0;
-    if (lane == 0) wi = atomicAdd(P.work, 1u);
-    wi = __shfl_sync(gmask, wi, 0, G);
-    if (wi >= (unsigned)P.n) break;
+    if (first_item) wi = (unsigned)slot;             // slot s is sized for cluster order[s] (poa.cu): it takes that one first
+    else {
+      if (lane == 0) wi = (unsigned)P.n_slots + atomicAdd(P.work, 1u);
+      wi = __shfl_sync(gmask, wi, 0, G);
+    }
+    if (wi >= (unsigned)P.n) { if (first_item) continue; break; }
     const uint32_t cid = P.order[wi];
+    const int4 dm = P.dims[cid];
+    poa_ws_carve(wsp, dm.x, dm.y, dm.z, dm.w, &g.w);
+    g.ncap = dm.x; g.ecap = dm.y;
+    const int Wc = dm.z, Lmax = dm.w;
     const int64_t s0 = P.cluster_offs[cid], s1 = P.cluster_offs[cid + 1];
     g.n = 0; g.ne = 0; g.overflow = false;
     int status = POA_OK;
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
       const uint8_t* q = P.seqs + P.seq_offs[si];
       const int ql = (int)(P.seq_offs[si + 1] - P.seq_offs[si]);
       if (ql <= 0) continue;
-      if (ql > P.lmax) { g.overflow = true; break; }
+      if (ql > Lmax) { g.overflow = true; break; }
       const int N = g.n;
       if (N == 2) {  // first read: a chain (warp-parallel)
         if (ql + 2 > g.ncap || ql + 1 > g.ecap) { g.overflow = true; break; }

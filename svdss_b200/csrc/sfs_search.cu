@@ -39,27 +39,6 @@ struct svb_reads {
 
 namespace svb {
 
-// Stream-ordered allocations from the device's default memory pool with an unbounded release
-// threshold: repeated batches reuse the same physical memory instead of paying cudaMalloc/cudaFree
-// (tens of ms per call for multi-GB buffers on some hosts) inside every svb_sfs_* call.
-static cudaError_t pmalloc(void** p, size_t bytes, cudaStream_t st) {
-  static thread_local int tuned_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (tuned_dev != dev) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    tuned_dev = dev;
-  }
-  return cudaMallocAsync(p, bytes ? bytes : 1, st);
-}
-static void pfree(void* p, cudaStream_t st) {
-  if (p) cudaFreeAsync(p, st);
-}
-
 struct SearchParams {
   const uint4* __restrict__ blocks;
   const uint32_t* __restrict__ cntN;

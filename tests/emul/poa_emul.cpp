@@ -31,6 +31,9 @@ extern "C" int emul_poa(const uint8_t* seqs, const int64_t* seq_offs, const int6
   if ((smem & 1) && 6 * (long long)swcap * groups > (long long)(sizeof(svb::poa_smem) / sizeof(int))) return -2;
   for (size_t i = 0; i < sizeof(svb::poa_smem) / sizeof(int); ++i) svb::poa_smem[i] = 0x7badbad;   // shared memory starts undefined
   const int64_t stride = svb::poa_ws_carve(nullptr, ncap, ecap, wcap, lmax, nullptr);
+  std::vector<int64_t> slot_off((size_t)groups + 1);
+  for (int i = 0; i <= groups; ++i) slot_off[(size_t)i] = stride * i;
+  std::vector<int4> dims((size_t)(n_clusters > 0 ? n_clusters : 1), make_int4(ncap, ecap, wcap, lmax));
   std::vector<uint8_t> ws((size_t)stride * (size_t)groups + 256, 0xA5);   // not zeroed, like a cudaMalloc'ed workspace
   std::vector<uint32_t> order((size_t)n_clusters);
   for (int i = 0; i < n_clusters; ++i) order[(size_t)i] = (uint32_t)i;
@@ -40,7 +43,7 @@ extern "C" int emul_poa(const uint8_t* seqs, const int64_t* seq_offs, const int6
   l.variant = smem; l.group = group;
   svb::PoaParams& P = l.P;
   P.seqs = seqs; P.seq_offs = seq_offs; P.cluster_offs = cluster_offs; P.order = order.data(); P.n = n_clusters;
-  P.work = &work; P.ws = ws.data(); P.ws_stride = stride; P.ncap = ncap; P.ecap = ecap; P.wcap = wcap; P.lmax = lmax; P.swcap = swcap;
+  P.work = &work; P.ws = ws.data(); P.slot_off = slot_off.data(); P.dims = dims.data(); P.n_slots = groups; P.swcap = swcap;
   P.cons = cons; P.cons_off = cons_off; P.cons_len = cons_len; P.status = status; P.cells = cells; P.phase = nullptr;
   P.match = 2; P.mismatch = 4; P.o1 = 4; P.e1 = 2; P.o2 = 24; P.e2 = 1; P.wb = 10; P.wf = 0.01f;   // as svb_poa_batch sets them
   blockDim.x = 32; blockIdx.x = 0;
