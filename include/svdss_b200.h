@@ -258,7 +258,8 @@ typedef struct {
 
 /* chromosome_seqs (chromosomes.hpp): contig c = seq[start[c], start[c] + len[c]).  `mem` says where seq lives;
  * start / len / name_rank are HOST arrays.  name_rank[tid] orders the chromosome NAMES (SFS::operator< compares
- * strings, sfs.hpp:64-72); NULL = tid order. */
+ * strings, sfs.hpp:64-72); NULL = tid order.  len[c] < 0: chromosome c of the BAM header has no sequence
+ * (reads on it are skipped, clusterer.cpp:162-163). */
 typedef struct {
   int64_t n_contigs;
   const uint8_t* seq;

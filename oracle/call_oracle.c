@@ -91,7 +91,7 @@ typedef struct { int aln, rs, re, qs, qe; } ext_t;
 static int extend_alignment(const svb_alns_t *A, const svb_ref_t *R, int a, int flank, int ksize, int clipped, ext_t *out, int64_t *cnt,
                             int32_t *clip) {
   const int t = A->tid[a];
-  if (t < 0 || t >= R->n_contigs) return 0;
+  if (t < 0 || t >= R->n_contigs || R->len[t] < 0) return 0;
   const uint8_t *chrom = R->seq + R->start[t];
   const int64_t clen = R->len[t];
   const uint32_t *cig = A->cigar + A->cigar_offs[a];

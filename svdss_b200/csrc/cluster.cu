@@ -46,7 +46,7 @@ __global__ void k_cl_extend(const int32_t* __restrict__ accepted, int n_acc, con
   unsigned c4[4] = {0, 0, 0, 0};
   int cl4[4] = {0, 0, 0, 0};
   int n = 0;
-  if (t >= 0 && t < ref.n_contigs) {      // clusterer.cpp:162-163: a chromosome without sequence is skipped
+  if (t >= 0 && t < ref.n_contigs && ref.len[t] >= 0) {      // clusterer.cpp:162-163: a chromosome without sequence is skipped
     ClAln A;
     A.cig = cigar + cigar_offs[a]; A.n_cig = (int)(cigar_offs[a + 1] - cigar_offs[a]); A.pos = pos[a];
     A.chrom = ref.seq + ref.start[t]; A.chrom_len = ref.len[t];
@@ -145,7 +145,8 @@ extern "C" int svb_cluster_batch(const svb_alns_t* A, const svb_ref_t* R, int th
   if ((n && (A->cigar_offs[0] != 0 || A->sfs_offs[0] != 0)) || n_sfs > 0x7ffffff0) { set_error("svb_cluster_batch: offsets must start at 0"); return SVB_EINVAL; }
   int64_t ref_bytes = 0;
   for (int64_t c = 0; c < R->n_contigs; ++c) {
-    if (R->start[c] < 0 || R->len[c] < 0) { set_error("svb_cluster_batch: bad contig %lld", (long long)c); return SVB_EINVAL; }
+    if (R->len[c] < 0) continue;            // a chromosome of the BAM header without sequence (clusterer.cpp:162-163)
+    if (R->start[c] < 0) { set_error("svb_cluster_batch: bad contig %lld", (long long)c); return SVB_EINVAL; }
     ref_bytes = std::max(ref_bytes, R->start[c] + R->len[c]);
   }
   out->n_clusters = 0;

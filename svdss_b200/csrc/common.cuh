@@ -116,7 +116,10 @@ constexpr uint64_t KMT_SAT = (1ull << 24) - 1;
 int build_kmer_table(IndexDev* idx);
 
 constexpr uint8_t TEXT_SENTINEL = 0xF0;
-constexpr int TEXT_PAD = 64;
+// pad bytes (TEXT_SENTINEL) either side of d_text: the warp-cooperative compare of the located-match mode (coop_text_step)
+// lets all 32 lanes load 48-byte text windows up to 32 * 31 + 48 bytes past the current match whenever the READ still has
+// bases there -- also when the match sits at the very end of the text (64 bytes were not enough)
+constexpr int TEXT_PAD = 1152;
 
 }  // namespace svb
 

@@ -164,7 +164,10 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       PCHECK(pool_available(&free_b));
       const char* eb = getenv("SVB_POA_WS_BYTES");
       const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
-      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * 4 * SVB_POA_MINB);
+      // bit 2048 of the variant: the build with 2 CTAs per SM (255 registers, no spills) -- for batches with fewer clusters than
+      // warp slots, where the time is the chain of rows of the biggest cluster and occupancy buys nothing
+      const int mb = (variant & 2048) ? 2 : SVB_POA_MINB;
+      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * 4 * mb);
       std::vector<int64_t> slot_off((size_t)slots + 1, 0);
       {
         int64_t s_ok = 0;
@@ -206,9 +209,17 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
     k_poa<VV, 32><<<grid, 128, smem>>>(P);                                                                          \
     break;
       switch (variant) {
-        POA_LAUNCH(0) POA_LAUNCH(7) POA_LAUNCH(63) POA_LAUNCH(71) POA_LAUNCH(135) POA_LAUNCH(263) POA_LAUNCH(199) POA_LAUNCH(455) POA_LAUNCH(487)
+        POA_LAUNCH(0) POA_LAUNCH(7) POA_LAUNCH(455) POA_LAUNCH(487) POA_LAUNCH(967) POA_LAUNCH(1479)
+        case 2048 + 1479:
+          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<1479, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_poa<1479, 32, 2><<<grid, 128, smem>>>(P);
+          break;
+        case 2048 + 967:
+          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<967, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_poa<967, 32, 2><<<grid, 128, smem>>>(P);
+          break;
         default:
-          set_error("SVB_POA_VARIANT=%d is not built (0 7 63 71 135 199 263 455 487)", variant);
+          set_error("SVB_POA_VARIANT=%d is not built (0 7 455 487 967 1479 3015 3527)", variant);
           rc = SVB_EINVAL;
           goto done;
       }

@@ -128,8 +128,13 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane, unsigned gmask) {
 // 256 UPDPAR graph update in windows of 32 alignment ops: every lane checks "its node carries the read's base and the
 //            edge from the previous op's node exists" and bumps that edge's weight; lane 0 handles the first op of a
 //            window that is not of that kind (new node, new edge, aligned-ring lookup) and the window restarts after it
+// 512 / 1024 ILP2 / ILP4: a DP row is cut into chunks of 2 (4) x 32 columns and a lane works on its 2 (4) columns of a
+//            chunk at once: the predecessor loads, the per-column recurrences and the two max-plus scans of the chunk's
+//            column groups are independent instruction streams (the groups meet only in the carries), so a warp that
+//            runs alone on its scheduler -- the tail of a batch is one big cluster, 30 reads x 5 000 rows of 121 columns
+//            -- no longer pays one dependent-issue latency per instruction
 constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, POA_V_TBPF = 16, POA_V_LEAN = 32, POA_V_ROWS = 64,
-              POA_V_TBSPEC = 128, POA_V_UPDPAR = 256;
+              POA_V_TBSPEC = 128, POA_V_UPDPAR = 256, POA_V_ILP2 = 512, POA_V_ILP4 = 1024;
 
 __device__ __forceinline__ void poa_prefetch(const void* p) {
 #ifdef __CUDA_ARCH__
@@ -144,12 +149,13 @@ __device__ __forceinline__ void poa_prefetch(const void* p) {
 // is bound by the latency of dependent loads at a quarter of the issue rate, a band is 35-60 columns wide, and
 // the sequential walks use one lane -- so more, narrower instruction streams per warp hide more latency with
 // the same registers.  Everything below is written for a "group" of G lanes; `lane` is the lane in the group.
-template <int V, int G = 32>
-__global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
+template <int V, int G = 32, int MB = SVB_POA_MINB>
+__global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
   extern __shared__ int poa_smem[];
   constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0,
                  TBPF = (V & POA_V_TBPF) != 0, LEAN = (V & POA_V_LEAN) != 0, ROWS = (V & POA_V_ROWS) != 0, TBSPEC = (V & POA_V_TBSPEC) != 0,
                  UPDPAR = (V & POA_V_UPDPAR) != 0;
+  constexpr int S = (V & POA_V_ILP4) ? 4 : (V & POA_V_ILP2) ? 2 : 0;   // column groups per chunk of the ILP row (0 = the one-group loop)
   static_assert(!ROWS || PARN, "ROWS builds its records in the warp-parallel setup");
   static_assert(!(TBSPEC && TBPF) && !(UPDPAR && PREF), "TBSPEC / UPDPAR replace TBPF / PREF");
   static_assert(G == 32 || G == 16 || G == 8, "group width");
@@ -331,6 +337,85 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         int prevX1 = PNEG, prevB1 = PNEG, prevX2 = PNEG, prevB2 = PNEG;  // column j-1 of lane 0
         int prevflags = 0;                                               // LEAN: the same as two bits
         int rmax = PNEG - 1, rleft = 0, rright = 0;
+        if (S > 0) {
+          constexpr int SS = S > 0 ? S : 1;
+          for (int jc = b; jc <= en; jc += G * SS) {
+            int hp_[SS], x1_[SS], x2_[SS], inc1_[SS], inc2_[SS], B1_[SS], B2_[SS];
+            unsigned tb_[SS];
+#pragma unroll
+            for (int g_ = 0; g_ < SS; ++g_) {          // independent per column group: loads + recurrences
+              const int j = jc + g_ * G + lane;
+              const bool act = j <= en;
+              int m = PNEG, x1 = PNEG, x2 = PNEG, pm = 0, p1 = 0, p2 = 0, x1ext = 0, x2ext = 0;
+              const int qb = (act && j >= 1) ? q[j - 1] : 4;
+              auto consider = [&](int p, int bp, int ep, int ord) {
+                const int* ph = W.H + (int64_t)p * Wc;
+                const int* pe1 = W.E1 + (int64_t)p * Wc;
+                const int* pe2 = W.E2 + (int64_t)p * Wc;
+                if (SMEM && prev_sm && p == v_prev) { ph = sprev; pe1 = sprev + Ws; pe2 = sprev + 2 * Ws; }
+                if (act && j >= 1 && j - 1 >= bp && j - 1 <= ep) {
+                  const int sc_ = (bv >= 4 || qb >= 4) ? 0 : (bv == qb ? P.match : -mm);
+                  const int cval = ph[j - 1 - bp] + sc_;
+                  if (cval > m) { m = cval; pm = ord; }
+                }
+                if (act && j >= bp && j <= ep) {
+                  const int hj = ph[j - bp];
+                  int op = hj - P.o1, ex = pe1[j - bp];
+                  int cval = max(op, ex) - P.e1;
+                  if (cval > x1) { x1 = cval; p1 = ord; x1ext = ex > op; }
+                  op = hj - P.o2; ex = pe2[j - bp];
+                  cval = max(op, ex) - P.e2;
+                  if (cval > x2) { x2 = cval; p2 = ord; x2ext = ex > op; }
+                }
+              };
+              if (single) consider(p0, p0b, p0e, 0);
+              else {
+                int ord = 0;
+                for (int e = W.first_in[v]; e >= 0; e = W.enin[e], ++ord) {
+                  const int p = W.efrom[e];
+                  consider(p, W.beg[p], W.end[p], ord);
+                }
+              }
+              m = max(m, PNEG); x1 = max(x1, PNEG); x2 = max(x2, PNEG);
+              int hp = m; unsigned hps = 0;
+              if (x1 > hp) { hp = x1; hps = 1; }
+              if (x2 > hp) { hp = x2; hps = 2; }
+              hp_[g_] = hp; x1_[g_] = x1; x2_[g_] = x2;
+              tb_[g_] = (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) |
+                        ((unsigned)(p2 & 0x3f) << 26);
+              B1_[g_] = act ? hp + j * P.e1 : PNEG; B2_[g_] = act ? hp + j * P.e2 : PNEG;
+            }
+#pragma unroll
+            for (int g_ = 0; g_ < SS; ++g_) { inc1_[g_] = warp_incl_max<G>(B1_[g_], lane, gmask); inc2_[g_] = warp_incl_max<G>(B2_[g_], lane, gmask); }
+#pragma unroll
+            for (int g_ = 0; g_ < SS; ++g_) {          // the groups meet in the carries only
+              const int j = jc + g_ * G + lane;
+              const bool act = j <= en;
+              int ex1 = __shfl_up_sync(gmask, inc1_[g_], 1, G), ex2 = __shfl_up_sync(gmask, inc2_[g_], 1, G);
+              if (lane == 0) { ex1 = PNEG; ex2 = PNEG; }
+              const int X1 = max(carry1, ex1), X2 = max(carry2, ex2);
+              int f1 = PNEG, f2 = PNEG;
+              if (j > b) { f1 = max(X1 - P.o1 - j * P.e1, PNEG); f2 = max(X2 - P.o2 - j * P.e2, PNEG); }
+              const int myflags = (X1 > B1_[g_] ? 1 : 0) | (X2 > B2_[g_] ? 2 : 0);
+              int pf = __shfl_up_sync(gmask, myflags, 1, G);
+              if (lane == 0) pf = prevflags;
+              const int f1ext = (j > b) && (pf & 1), f2ext = (j > b) && (pf & 2);
+              int hh = hp_[g_]; unsigned hs = (tb_[g_] >> 3) & 3u;
+              if (f1 > hh) { hh = f1; hs = 3; }
+              if (f2 > hh) { hh = f2; hs = 4; }
+              if (act) {
+                hrow[j - b] = hh; e1row[j - b] = x1_[g_]; e2row[j - b] = x2_[g_];
+                if (cur_sm) { scur[j - b] = hh; scur[Ws + j - b] = x1_[g_]; scur[2 * Ws + j - b] = x2_[g_]; }
+                tbrow[j - b] = hs | tb_[g_] | ((unsigned)f1ext << 7) | ((unsigned)f2ext << 8);
+                if (hh > rmax) { rmax = hh; rleft = j; rright = j; }
+                else if (hh == rmax) rright = j;
+              }
+              carry1 = max(carry1, __shfl_sync(gmask, inc1_[g_], G - 1, G));
+              carry2 = max(carry2, __shfl_sync(gmask, inc2_[g_], G - 1, G));
+              prevflags = __shfl_sync(gmask, myflags, G - 1, G);
+            }
+          }
+        } else
         for (int j0 = b; j0 <= en; j0 += G) {
           const int j = j0 + lane;
           const bool act = j <= en;
@@ -413,7 +498,7 @@ __global__ void __launch_bounds__(128, SVB_POA_MINB) k_poa(const PoaParams P) {
         cells += (unsigned long long)(en - b + 1);
         // row maximum, its first and last column (lanes hold strided columns: reduce)
         int gmax = rmax, l_, r_;
-        if (LEAN) {   // REDUX: one instruction per reduction instead of log2(G) shuffle steps
+        if (LEAN || S > 0) {   // REDUX: one instruction per reduction instead of log2(G) shuffle steps
           gmax = __reduce_max_sync(gmask, rmax);
           l_ = __reduce_min_sync(gmask, (rmax == gmax) ? rleft : 0x7fffffff);
           r_ = __reduce_max_sync(gmask, (rmax == gmax) ? rright : -1);

@@ -266,7 +266,7 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     ClusterConfig cc;
     cc.bam = c.bam; cc.clusters_out = c.clusters_out; cc.threads = c.threads; cc.batch_size = c.batch_size;
     cc.min_mapq = c.min_mapq; cc.min_cluster_weight = c.min_cluster_weight;
-    cc.clipped = c.clipped; cc.clips_out = c.clips_out;
+    cc.clipped = c.clipped; cc.clips_out = c.clips_out; cc.device = c.device;
     Clusterer C(cc, &sfss, &seqs);
     log("info", "Placing SFSs on reference genome");
     if (!C.run()) { log("critical", C.error.empty() ? "cannot write " + c.clusters_out : C.error); return 1; }
@@ -308,96 +308,90 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     }
   }
   log("info", "Calling SVs from " + std::to_string(clusters.size()) + " clusters..");
-  // pcall: collect sub-clusters (caller.cpp:311-330)
-  std::vector<Cluster> jobs;
-  std::vector<size_t> parent;   // index into clusters (thread slot = parent % threads, RVEC source)
+  // Caller::pcall (caller.cpp:311-406) through svb_call_batch: the clusters as arrays, the sub-reads and the chromosomes as
+  // ASCII in one buffer each; split_cluster, POA, ksw2 and the CIGAR walk happen behind the call
+  std::unordered_map<std::string, int32_t> tid_of;
+  std::string refcat;
+  std::vector<int64_t> rstart, rlen;
+  for (size_t t = 0; t < chroms.size(); ++t) {
+    if (!tid_of.emplace(chroms[t], (int32_t)t).second) { rstart.push_back(0); rlen.push_back(-1); continue; }   // a repeated name: the first one wins (std::map semantics)
+    rstart.push_back((int64_t)refcat.size()); rlen.push_back((int64_t)seqs[chroms[t]].size());
+    refcat += seqs[chroms[t]];
+  }
+  std::vector<int32_t> c_tid, c_s, c_e, c_cov0, c_cov1, c_cov2, sub_aln, sub_qs, sub_qe, sub_hp;
+  std::vector<uint8_t> c_placed;
+  std::vector<int64_t> sub_offs(1, 0), seq_offs;
+  std::string seqcat;
   for (size_t ci = 0; ci < clusters.size(); ++ci) {
     const Cluster& cl = clusters[ci];
-    if (cl.size() < c.min_cluster_weight) continue;   // :316
-    const std::string& cs = seqs[cl.chrom];
-    if (cl.s < 1 || cl.e < cl.s || (size_t)cl.e >= cs.size()) {   // the reference would read outside the chromosome
+    auto it = tid_of.find(cl.chrom);
+    const bool inside = it != tid_of.end() && !(cl.s < 1 || cl.e < cl.s || (size_t)cl.e >= seqs[cl.chrom].size());
+    if (cl.size() >= c.min_cluster_weight && !inside)   // the reference would read outside the chromosome
       log("warning", "cluster " + cl.chrom + ":" + std::to_string(cl.s + 1) + "-" + std::to_string(cl.e + 1) + " is outside the reference, skipped");
-      continue;
+    c_tid.push_back(it == tid_of.end() ? -1 : it->second); c_s.push_back(cl.s); c_e.push_back(cl.e);
+    c_cov0.push_back(cl.cov0); c_cov1.push_back(cl.cov1); c_cov2.push_back(cl.cov2);
+    c_placed.push_back(1);
+    for (const SubRead& sr : cl.subreads) {
+      sub_aln.push_back((int32_t)seq_offs.size()); sub_qs.push_back(0); sub_qe.push_back((int32_t)sr.seq.size() - 1); sub_hp.push_back(sr.htag);
+      seq_offs.push_back((int64_t)seqcat.size());
+      seqcat += sr.seq;
     }
-    for (const Cluster& sc : split_cluster(cl, c.min_ratio, c.useht)) { jobs.push_back(sc); parent.push_back(ci); }
+    sub_offs.push_back((int64_t)sub_aln.size());
   }
-  const uint8_t* t26 = char26_table();
-  // run_poa for all jobs (caller.cpp:257-308)
-  std::vector<uint8_t> seqcat; std::vector<int64_t> soff(1, 0), coff(1, 0);
-  for (const Cluster& j : jobs) {
-    for (const SubRead& sr : j.subreads) { for (char ch : sr.seq) seqcat.push_back(t26[(uint8_t)ch]); soff.push_back((int64_t)seqcat.size()); }
-    coff.push_back((int64_t)soff.size() - 1);
-  }
-  svb_poa_out_t poa;
-  if (seqcat.empty()) seqcat.push_back(0);
-  if (svb_poa_batch(seqcat.data(), soff.data(), coff.data(), (int64_t)jobs.size(), c.device, &poa) != SVB_OK) { log("critical", std::string("svb_poa_batch: ") + svb_last_error()); return 1; }
-  std::vector<std::string> cons(jobs.size()), refs(jobs.size());
-  std::vector<uint8_t> q, t; std::vector<int64_t> qo(1, 0), to(1, 0);
-  for (size_t k = 0; k < jobs.size(); ++k) {
-    for (int64_t i = poa.cons_offs[k]; i < poa.cons_offs[k + 1]; ++i) cons[k] += "ACGTN"[poa.cons[i]];   // :295-297
-    refs[k] = seqs[jobs[k].chrom].substr((size_t)jobs[k].s, (size_t)(jobs[k].e - jobs[k].s + 1));         // :329
-    for (char ch : cons[k]) q.push_back(t26[(uint8_t)ch]);
-    for (char ch : refs[k]) t.push_back(t26[(uint8_t)ch]);
-    qo.push_back((int64_t)q.size()); to.push_back((int64_t)t.size());
-  }
-  svb_poa_out_free(&poa);
-  svb_ksw_out_t ez;
-  if (q.empty()) q.push_back(0);
-  if (t.empty()) t.push_back(0);
-  if (svb_ksw_extd2_batch(q.data(), qo.data(), t.data(), to.data(), (int64_t)jobs.size(), 1, -9, -1, 16, 2, 41, 1, c.device, &ez) != SVB_OK) {  // :333-349
-    log("critical", std::string("svb_ksw_extd2_batch: ") + svb_last_error());
+  if (seq_offs.empty()) seq_offs.push_back(0);
+  if (sub_aln.empty()) { sub_aln.push_back(0); sub_qs.push_back(0); sub_qe.push_back(-1); sub_hp.push_back(0); }
+  svb_clusters_t CL;
+  memset(&CL, 0, sizeof(CL));
+  CL.n_clusters = (int64_t)clusters.size();
+  CL.tid = c_tid.data(); CL.s = c_s.data(); CL.e = c_e.data(); CL.cov0 = c_cov0.data(); CL.cov1 = c_cov1.data(); CL.cov2 = c_cov2.data();
+  CL.placed = c_placed.data(); CL.sub_offs = sub_offs.data(); CL.sub_aln = sub_aln.data(); CL.sub_qs = sub_qs.data(); CL.sub_qe = sub_qe.data();
+  CL.sub_hp = sub_hp.data();
+  svb_seqs_t RD;
+  RD.n = (int64_t)seq_offs.size(); RD.seq = reinterpret_cast<const uint8_t*>(seqcat.data()); RD.offs = seq_offs.data(); RD.fmt = SVB_SEQ_ASCII; RD.mem = SVB_MEM_HOST;
+  svb_ref_t RF;
+  RF.n_contigs = (int64_t)chroms.size(); RF.seq = reinterpret_cast<const uint8_t*>(refcat.data()); RF.start = rstart.data(); RF.len = rlen.data();
+  RF.name_rank = nullptr; RF.fmt = SVB_SEQ_ASCII; RF.mem = SVB_MEM_HOST;
+  svb_calls_t K;
+  if (svb_call_batch(&CL, &RD, &RF, (int)c.min_cluster_weight, (int)c.min_sv_length, c.min_ratio, c.useht ? 1 : 0, c.device, &K) != SVB_OK) {
+    log("critical", std::string("svb_call_batch: ") + svb_last_error());
     return 1;
   }
   const size_t T = (size_t)std::max(1, c.threads);
   std::vector<std::vector<SV>> p_svs(T);
   std::vector<std::vector<std::string>> p_sam(T);
-  for (size_t k = 0; k < jobs.size(); ++k) {
-    std::vector<SV>& svs = p_svs[parent[k] % T];            // schedule(static, 1), caller.cpp:312-314
-    std::vector<std::string>& sam = p_sam[parent[k] % T];
+  int64_t sv_k = 0;
+  for (int64_t k = 0; k < K.n_jobs; ++k) {
+    const size_t parent = (size_t)K.job_cluster[k];
+    std::vector<SV>& svs = p_svs[parent % T];            // schedule(static, 1), caller.cpp:312-314
+    std::vector<std::string>& sam = p_sam[parent % T];
     std::string rvec;                                        // SV::set_rvec, sv.cpp:42-46
-    for (const auto& r : clusters[parent[k]].reads) rvec += std::to_string(r.first) + ":" + std::to_string(r.second) + "-";
+    for (const auto& r : clusters[parent].reads) rvec += std::to_string(r.first) + ":" + std::to_string(r.second) + "-";
     if (!rvec.empty()) rvec.pop_back();
-    const Cluster& cl = jobs[k];
+    const Cluster& cl = clusters[parent];
     const std::string& chromseq = seqs[cl.chrom];
-    const int score = ez.score[k];
-    std::string cigar_str;
-    for (int64_t i = ez.cigar_offs[k]; i < ez.cigar_offs[k + 1]; ++i) cigar_str += std::to_string(ez.cigar[i] >> 4) + "MID"[ez.cigar[i] & 0xf];  // :352-355
+    const int score = K.score[k];
+    std::string cons, cigar_str, reads;
+    for (int64_t i = K.cons_offs[k]; i < K.cons_offs[k + 1]; ++i) cons += "ACGTN"[K.cons[i]];   // :295-297
+    for (int64_t i = K.cigar_offs[k]; i < K.cigar_offs[k + 1]; ++i) cigar_str += std::to_string(K.cigar[i] >> 4) + "MID"[K.cigar[i] & 0xf];  // :352-355
     sam.push_back(cl.chrom + ":" + std::to_string(cl.s + 1) + "-" + std::to_string(cl.e + 1) + "\t0\t" + cl.chrom + "\t" +
-                  std::to_string(cl.s + 1) + "\t60\t" + cigar_str + "\t*\t0\t0\t" + cons[k] + "\t*");        // caller.hpp:56-70
-    std::vector<SV> _svs;
-    unsigned rpos = (unsigned)cl.s, cpos = 0;
-    int nv = 0;
-    std::string reads;
-    for (const SubRead& sr : cl.subreads) reads += sr.name + ",";
+                  std::to_string(cl.s + 1) + "\t60\t" + cigar_str + "\t*\t0\t0\t" + cons + "\t*");        // caller.hpp:56-70
+    const int64_t n_sub = K.job_sub_offs[k + 1] - K.job_sub_offs[k];
+    for (int64_t i = K.job_sub_offs[k]; i < K.job_sub_offs[k + 1]; ++i) reads += cl.subreads[(size_t)(K.job_sub[i] - sub_offs[parent])].name + ",";
     if (!reads.empty()) reads.pop_back();
-    for (int64_t i = ez.cigar_offs[k]; i < ez.cigar_offs[k + 1]; ++i) {  // :359-395
-      const unsigned l = ez.cigar[i] >> 4;
-      const char op = "MID"[ez.cigar[i] & 0xf];
-      if (op == 'M') { rpos += l; cpos += l; }
-      else if (op == 'I') {
-        if (l >= c.min_sv_length) {
-          SV sv("INS", cl.chrom, rpos, chromseq.substr(rpos - 1, 1), chromseq.substr(rpos - 1, 1) + cons[k].substr(cpos, l),
-                (unsigned)cl.size(), (unsigned)cl.cov, nv, score, false, l, cigar_str);
-          sv.reads = reads; _svs.push_back(sv); nv++;
-        }
-        cpos += l;
-      } else {
-        if (l >= c.min_sv_length) {
-          SV sv("DEL", cl.chrom, rpos, chromseq.substr(rpos - 1, l + 1), chromseq.substr(rpos - 1, 1), (unsigned)cl.size(),
-                (unsigned)cl.cov, nv, score, false, l, cigar_str);
-          sv.reads = reads; _svs.push_back(sv); nv++;
-        }
-        rpos += l;
-      }
-    }
-    for (SV& sv : _svs) {  // :396-401
-      sv.ngaps = nv; sv.gt = "0/1"; sv.gtq = 100;
-      sv.cov = cl.cov; sv.cov0 = cl.cov0; sv.cov1 = cl.cov1; sv.cov2 = cl.cov2;
+    const int cov = K.job_cov[k * 4], cov0 = K.job_cov[k * 4 + 1], cov1 = K.job_cov[k * 4 + 2], cov2 = K.job_cov[k * 4 + 3];
+    for (; sv_k < K.n_svs && K.sv_job[sv_k] == k; ++sv_k) {  // :359-401
+      const unsigned rpos = (unsigned)K.sv_pos[sv_k], l = (unsigned)K.sv_len[sv_k], cpos = (unsigned)K.sv_cpos[sv_k];
+      SV sv = K.sv_type[sv_k] == 0
+                  ? SV("INS", cl.chrom, rpos, chromseq.substr(rpos - 1, 1), chromseq.substr(rpos - 1, 1) + cons.substr(cpos, l), (unsigned)n_sub, (unsigned)cov, 0, score, false, l, cigar_str)
+                  : SV("DEL", cl.chrom, rpos, chromseq.substr(rpos - 1, l + 1), chromseq.substr(rpos - 1, 1), (unsigned)n_sub, (unsigned)cov, 0, score, false, l, cigar_str);
+      sv.reads = reads;
+      sv.ngaps = K.job_nv[k]; sv.gt = "0/1"; sv.gtq = 100;
+      sv.cov = cov; sv.cov0 = cov0; sv.cov1 = cov1; sv.cov2 = cov2;
       sv.rvec = rvec;
       svs.push_back(sv);
     }
   }
-  svb_ksw_out_free(&ez);
+  svb_calls_free(&K);
   // caller.cpp:17-29: per-thread vectors are inserted at the front, then sort / clean_dups /
   // filter_sv_chains / sort (stable here; the reference's std::sort leaves ties unspecified)
   std::vector<SV> svs;

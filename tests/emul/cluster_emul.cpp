@@ -24,7 +24,7 @@ extern "C" int emul_cluster_batch(const svb_alns_t* A, const svb_ref_t* R, int t
     const int a = accepted[i], t = A->tid[a];
     int cl4[4] = {0, 0, 0, 0};
     int m = 0;
-    if (t >= 0 && t < R->n_contigs) {
+    if (t >= 0 && t < R->n_contigs && R->len[t] >= 0) {
       ClAln al;
       al.cig = A->cigar + A->cigar_offs[a]; al.n_cig = (int)(A->cigar_offs[a + 1] - A->cigar_offs[a]); al.pos = A->pos[a];
       al.chrom = R->seq + R->start[t]; al.chrom_len = R->len[t];

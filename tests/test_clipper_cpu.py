@@ -1,7 +1,8 @@
 """CPU: `SVDSS call --clipped` (reference clipper.cpp, clusterer.cpp:211-226,339-345, caller.cpp:37-55)
 against the literal Python transcriptions in tests/cluster_model.py and tests/clipper_model.py.
-The clip extraction runs through `call --cluster-only --clipped --clips FILE`; Clipper::call runs
-through the `_clipper` hook of the shell, so neither needs a GPU."""
+The clip extraction runs through `call --cluster-only --clipped --clips FILE` (svb_cluster_batch: those two tests
+carry the gpu marker; tests/test_cluster_emul.py holds the same kernel source against the same world on the CPU);
+Clipper::call runs through the `_clipper` hook of the shell and needs no GPU."""
 import os
 import subprocess
 
@@ -82,6 +83,7 @@ def _clip_lines(clips):
     return "".join("%s\t%s\t%d\t%d\t%s\n" % (n, c, p, l, "L" if st else "R") for n, c, p, l, st in clips)
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("threads", [1, 3, 4])
 def test_clips_match_the_transcription(exe, clip_world, threads):
     w = clip_world
@@ -96,6 +98,7 @@ def test_clips_match_the_transcription(exe, clip_world, threads):
     assert "1/1/1 unplaced SFSs. 0 erroneus SFSs. %d clipped SFSs." % len(exp) in r.stderr   # whole / hardL / hardR
 
 
+@pytest.mark.gpu
 def test_without_clipped_the_same_sfss_count_as_unplaced(exe, clip_world):
     w = clip_world
     out = os.path.join(w["d"], "clips_off.tsv")

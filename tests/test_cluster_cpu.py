@@ -1,6 +1,7 @@
-"""CPU: the host-side Clusterer of `SVDSS call` (svdss_b200/host/clusterer.hpp, reference
-clusterer.cpp) against the literal Python transcription in tests/cluster_model.py, through the CLI:
-`SVDSS call --cluster-only --clusters FILE` stops before the GPU stages."""
+"""The Clusterer of `SVDSS call` through the CLI (`SVDSS call --cluster-only --clusters FILE`: BAM scan on the host,
+svb_cluster_batch on the GPU) against the literal Python transcription in tests/cluster_model.py -- those tests
+carry the gpu marker; the rest of the file (usage errors, the oracle pipeline as a checker, fuzz_ratio, and that the
+stage fails loudly without a device) runs on the CPU."""
 import os
 import subprocess
 
@@ -31,6 +32,7 @@ def run_clusterer(exe, w, threads, extra=()):
     return open(out).read(), r.stderr
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("threads", [1, 3, 4])
 def test_clusters_match_the_transcription(exe, world, threads):
     got, log = run_clusterer(exe, world, threads)
@@ -40,6 +42,7 @@ def test_clusters_match_the_transcription(exe, world, threads):
     assert "Placing SFSs on reference genome" in log
 
 
+@pytest.mark.gpu
 def test_every_planted_sv_has_a_cluster(exe, world):
     got, _ = run_clusterer(exe, world, 4)
     spans = []
@@ -67,6 +70,7 @@ def test_every_planted_sv_has_a_cluster(exe, world):
     assert n_checked >= 8
 
 
+@pytest.mark.gpu
 def test_min_mapq_and_weight_flags(exe, world):
     # mapq 0 keeps the low-mapq reads; weight 100 leaves no cluster with sub-reads
     got0, _ = run_clusterer(exe, world, 2, ["--min-mapq", "0"])
@@ -82,6 +86,15 @@ def test_call_usage_needs_inputs(exe, world):
     r = subprocess.run([exe, "call", "--reference", world["fa"], "--bam", os.path.join(world["d"], "none.bam"), "--sfs", world["sfs"],
                         "--cluster-only"], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot read BAM" in r.stderr
+
+
+def test_cluster_stage_fails_loudly_without_a_device(exe, world):
+    from svdss_b200 import capi
+    if capi.lib().svb_device_count() >= 1:
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, "call", "--reference", world["fa"], "--bam", world["bam"], "--sfs", world["sfs"], "--cluster-only",
+                        "--clusters", os.path.join(world["d"], "x.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "svb_cluster_batch" in r.stderr and r.stdout == ""        # no CPU fallback in the product
 
 
 def test_oracle_pipeline_recovers_planted_svs(world):
@@ -123,6 +136,7 @@ def test_fuzz_ratio_matches_lcs_definition(exe):
     assert abs(call_model.fuzz_ratio(*cases[0]) - 96.5517241) < 1e-6
 
 
+@pytest.mark.gpu
 def test_bam_reader_records_across_inflate_windows(exe, world, tmp_path):
     """The BAM reader parses records in place inside an inflated window and copies only the ones that
     straddle two windows; a one-block window forces that path on (nearly) every record. Same clusters,

@@ -12,6 +12,7 @@ import pytest
 import cluster_model
 from cluster_common import aln_batch, compare, ref_of
 from sv_world import make_world
+from test_clipper_cpu import clip_world  # noqa: F401  (fixture: SFSs inside soft / hard clips, a chromosome without sequence)
 from svdss_b200 import capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -100,3 +101,34 @@ def test_raw_reads_with_indel_columns_in_the_flanks(emul, tmp_path):
     exp = cluster_model.run(w["records"], w["names"], w["ref_seqs"], w["sfs_by_read"], threads=4)
     assert len(exp) >= 5
     compare(res, exp, recs, w["names"])
+
+
+@pytest.mark.parametrize("threads,clipped", [(1, True), (3, True), (4, False)])
+def test_clip_world_counters_and_clips(emul, clip_world, threads, clipped):
+    w = clip_world
+    recs = [r for r in w["records"] if cluster_model.primary(r) and r.get("mapq", 60) >= 20]
+    sfs = {i: [(q, l) for q, l, _ in w["sfs_by_read"][r["qname"]]] for i, r in enumerate(recs) if r["qname"] in w["sfs_by_read"]}
+    alns = capi.AlnBatch.from_records(recs, sfs)
+    seqs = [w["ref_seqs"].get(n, "") for n in w["names"]]
+    ref = capi.RefSeqs.from_strings(w["names"], seqs)
+    ref.len[[i for i, n in enumerate(w["names"]) if n not in w["ref_seqs"]]] = -1        # chrC: in the BAM header, not in the FASTA
+    res = capi.cluster_batch(alns, ref, threads=threads, clipped=clipped, emul=emul)
+    clips = [] if clipped else None
+    exp = cluster_model.run(w["records"], w["names"], w["ref_seqs"], w["sfs_by_read"], threads=threads, clips_out=clips)
+    compare(res, exp, recs, w["names"])
+    if clipped:
+        assert (res.unplaced, res.s_unplaced, res.e_unplaced, res.unknown) == (1, 1, 1, 0)      # whole / hardL / hardR
+        acc = [i for i in range(alns.n) if alns.sfs_offs[i + 1] > alns.sfs_offs[i]]
+        slots = [[] for _ in range(threads)]
+        for n, i in enumerate(acc):
+            lp, ll, rp, rl = (int(x) for x in res.clip[i])
+            if ll > 0:
+                slots[n % threads].append((recs[i]["qname"], w["names"][recs[i]["tid"]], lp, ll, True))
+            if rl > 0:
+                slots[n % threads].append((recs[i]["qname"], w["names"][recs[i]["tid"]], rp, rl, False))
+        got = []
+        for t in range(threads):
+            got[0:0] = slots[t]
+        assert got == clips and len(clips) == 4 + 3 + 6 + 5 + 2 + 1
+    else:
+        assert (res.unplaced, res.s_unplaced, res.e_unplaced) == (1, 11, 18)
