@@ -109,6 +109,9 @@ struct IndexDev {
   // K-1 extensions (all of which succeed when the K-mer occurs) by one 8-byte lookup.
   uint64_t* d_kmt = nullptr;
   int kmer_k = 0;
+  // longest run of N in the text (-1: unknown, no text): a restart of the walk inside a longer run of N in a READ has a
+  // closed form (sfs_search.cu, k_sfs_search_mop)
+  int64_t max_nrun = -1;
 };
 constexpr uint64_t KMT_SAT = (1ull << 24) - 1;
 

@@ -674,6 +674,43 @@ __global__ void k_unpack_fwd(const uint8_t* __restrict__ packed, int64_t tot, ui
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) out[i] = (packed[i >> 1] >> (4 * (i & 1))) & 15;
 }
 
+// longest run of `code` in T: per chunk the run touching its left end, the run touching its right end, the best run and
+// whether the chunk is all `code`; the host stitches the chunks
+constexpr int RUN_CHUNK = 4096;
+__global__ void k_chunk_runs(const uint8_t* __restrict__ T, int64_t n, uint8_t code, int64_t n_chunks, int32_t* __restrict__ out /* 3 per chunk */) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const int64_t a = c * RUN_CHUNK, b = min(n, a + RUN_CHUNK);
+  int lead = -1, cur = 0, best = 0;
+  for (int64_t i = a; i < b; ++i) {
+    if (T[i] == code) { ++cur; if (cur > best) best = cur; }
+    else { if (lead < 0) lead = cur; cur = 0; }
+  }
+  if (lead < 0) lead = (int)(b - a);      // the whole chunk
+  out[c * 3] = lead; out[c * 3 + 1] = cur; out[c * 3 + 2] = best;
+}
+static int longest_run(const uint8_t* d_T, int64_t n, uint8_t code, int64_t* out) {
+  const int64_t nc = (n + RUN_CHUNK - 1) / RUN_CHUNK;
+  *out = 0;
+  if (nc == 0) return SVB_OK;
+  int32_t* d = nullptr;
+  SVB_CUDA(cudaMalloc((void**)&d, (size_t)nc * 12));
+  k_chunk_runs<<<(unsigned)((nc + 127) / 128), 128>>>(d_T, n, code, nc, d);
+  std::vector<int32_t> h((size_t)nc * 3);
+  cudaError_t e = cudaMemcpy(h.data(), d, (size_t)nc * 12, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  SVB_CUDA(e);
+  int64_t best = 0, open = 0;             // open = run reaching the end of the previous chunk
+  for (int64_t c = 0; c < nc; ++c) {
+    const int64_t len = std::min<int64_t>(RUN_CHUNK, n - c * RUN_CHUNK);
+    const int64_t lead = h[(size_t)c * 3], trail = h[(size_t)c * 3 + 1], inner = h[(size_t)c * 3 + 2];
+    best = std::max(best, std::max(inner, open + lead));
+    open = lead == len ? open + len : trail;
+  }
+  *out = best;
+  return SVB_OK;
+}
+
 // keeps T (device, n bytes) as IndexDev::d_text and uploads the contig-pair starts
 static int attach_text(IndexDev* idx, const uint8_t* d_T, const std::vector<int64_t>& offs0 /* m+1, offs0[0] == 0 */) {
   const int64_t n = idx->n, m = (int64_t)offs0.size() - 1;
@@ -686,6 +723,7 @@ static int attach_text(IndexDev* idx, const uint8_t* d_T, const std::vector<int6
   SVB_CUDA(cudaMalloc((void**)&idx->d_tstart, (size_t)(m + 1) * 8));
   SVB_CUDA(cudaMemcpy(idx->d_tstart, ts.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice));
   SVB_CUDA(cudaDeviceSynchronize());
+  SVB_TRY(longest_run(d_T, n, 5, &idx->max_nrun));
   return SVB_OK;
 }
 

@@ -22,9 +22,6 @@
 
 #include "poa_kernel.cuh"
 
-#ifndef SVB_POA_DEFAULT_VARIANT
-#define SVB_POA_DEFAULT_VARIANT 0
-#endif
 
 namespace svb {
 
@@ -124,7 +121,21 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
     if (eg && atoi(eg) != 32) { set_error("SVB_POA_GROUP: only 32 lanes per cluster are built (16 and 8 were measured slower, profiles/r02a_variants_sweep.txt)"); rc = SVB_EINVAL; goto done; }
     // kernel variant (poa_kernel.cuh): SVB_POA_VARIANT = bit mask; 0 = the kernel measured in round 1
     const char* ev = getenv("SVB_POA_VARIANT");
-    const int variant = ev ? atoi(ev) : SVB_POA_DEFAULT_VARIANT;
+    int variant = ev ? atoi(ev) : -1;
+    if (variant < 0) {
+      // Two builds of the same kernel (identical results): 455 = 4 CTAs per SM, one column group per step -- the most clusters
+      // in flight, 37 GCUPS on 12 000 clusters of 20-60 reads (profiles/r02d_*); 3527 = 2 CTAs per SM, 255 registers, four
+      // column groups per step -- 1.65x shorter rows for a warp that runs alone.  A batch whose biggest cluster is a longer
+      // chain of rows (reads x nodes, ~1.2 us each) than the whole batch is work (cells at ~37 GCUPS) is bound by that chain.
+      double chain = 0, cells_est = 0;
+      for (int64_t c = 0; c < n_clusters; ++c) {
+        const Shape& s = shp[c];
+        if (!s.nreads) continue;
+        chain = std::max(chain, (double)(s.nreads - 1) * (double)s.lmax);
+        cells_est += (double)(s.sum - s.lmax) * (2.0 * (10 + 0.01 * s.lmax) + 1.0);
+      }
+      variant = (chain * 1.2e-6 > cells_est / 37e9) ? 2048 + 1479 : 455;
+    }
     // pass 0: heuristic capacities; pass 1: worst-case capacities for the clusters that overflowed
     std::vector<uint32_t> todo((size_t)n_clusters);
     for (int64_t c = 0; c < n_clusters; ++c) todo[c] = (uint32_t)c;

