@@ -178,7 +178,9 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       // bit 2048 of the variant: the build with 2 CTAs per SM (255 registers, no spills) -- for batches with fewer clusters than
       // warp slots, where the time is the chain of rows of the biggest cluster and occupancy buys nothing
       const int mb = (variant & 2048) ? 2 : SVB_POA_MINB;
-      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * 4 * mb);
+      const bool cta = (variant & 4096) != 0;          // bit 4096: a CTA (four warps) per cluster, the DP rows cut across its warps
+      const int per_cta = cta ? 1 : 4;                 // clusters in flight per CTA
+      int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * per_cta * mb);
       std::vector<int64_t> slot_off((size_t)slots + 1, 0);
       {
         int64_t s_ok = 0;
@@ -190,7 +192,7 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
         slots = s_ok;
       }
       // a CTA is four warps: round the slot count up to whole CTAs by repeating the smallest slot size
-      while (slots % 4) { slot_off.resize((size_t)slots + 2); slot_off[(size_t)slots + 1] = slot_off[(size_t)slots] + foot[todo[(size_t)std::min<int64_t>(slots, (int64_t)todo.size() - 1)]]; ++slots; }
+      while (slots % per_cta) { slot_off.resize((size_t)slots + 2); slot_off[(size_t)slots + 1] = slot_off[(size_t)slots] + foot[todo[(size_t)std::min<int64_t>(slots, (int64_t)todo.size() - 1)]]; ++slots; }
       slot_off.resize((size_t)slots + 1);
       if (slot_off[(size_t)slots] > (int64_t)free_b) { set_error("POA workspace of %lld bytes does not fit", (long long)slot_off[(size_t)slots]); rc = SVB_ENOMEM; goto done; }
       pfree(d_ws, 0); d_ws = nullptr;
@@ -212,8 +214,9 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       PCHECK(cudaEventRecord(k0, 0));
       // variants with the shared-memory copy of the previous row use 2 buffers x 3 arrays x swcap ints per warp
       P.swcap = std::min(wmax, 128);
-      const size_t smem = (variant & POA_V_SMEM) ? (size_t)4 * 6 * (size_t)P.swcap * sizeof(int) : 0;
-      const unsigned grid = (unsigned)(slots / 4);
+      const size_t smem = cta ? ((size_t)6 * (size_t)P.swcap + 9 * 4 * 2 + 8) * sizeof(int)
+                              : (variant & POA_V_SMEM) ? (size_t)4 * 6 * (size_t)P.swcap * sizeof(int) : 0;
+      const unsigned grid = (unsigned)(slots / per_cta);
 #define POA_LAUNCH(VV)                                                                                              \
   case (VV):                                                                                                        \
     if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<VV, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -225,12 +228,20 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
           if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<1479, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           k_poa<1479, 32, 2><<<grid, 128, smem>>>(P);
           break;
+        case 4096 + 455:
+          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<455, 32, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_poa<455, 32, 4, 4><<<grid, 128, smem>>>(P);
+          break;
+        case 4096 + 2048 + 455:
+          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<455, 32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_poa<455, 32, 2, 4><<<grid, 128, smem>>>(P);
+          break;
         case 2048 + 967:
           if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<967, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           k_poa<967, 32, 2><<<grid, 128, smem>>>(P);
           break;
         default:
-          set_error("SVB_POA_VARIANT=%d is not built (0 7 455 487 967 1479 3015 3527)", variant);
+          set_error("SVB_POA_VARIANT=%d is not built (0 7 455 487 967 1479 3015 3527 4551 6599)", variant);
           rc = SVB_EINVAL;
           goto done;
       }

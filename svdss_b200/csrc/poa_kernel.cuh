@@ -100,6 +100,156 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane, unsigned gmask) {
   return v;
 }
 
+// ---- DP rows of one read by the four warps of a CTA (k_poa<.., NW = 4>): warp w owns column group w of every chunk of
+// 128 columns, all warps run the same row loop (same band arithmetic from the same inputs) and meet twice per chunk-row:
+// once to hand the scans' carries and the last lane's flags across the groups (six ints per group through shared
+// memory), once at the end of the row for the row maximum and the shared-memory copy of the row.  Same values, same
+// comparisons as the one-warp row: the serial chain of a big cluster (30 reads x 5 000 rows of 121 columns) gets four
+// schedulers instead of one.  xch: 9 * NW * 2 ints of shared memory.
+template <int NW>
+__device__ __forceinline__ void poa_cta_sync() {
+#ifdef __CUDA_ARCH__
+  __syncthreads();
+#endif
+}
+template <int NW>
+__device__ void poa_dp_rows_cta(const PoaParams& P, const PoaWs& W, const uint8_t* __restrict__ q, const int ql, const int n_ord, const int Wc,
+                                const int Ws, int* const sbuf, int* const xch, const int wid, const int lane, const int mm, int& status,
+                                unsigned long long& cells) {
+  constexpr int G = 32;
+  const unsigned gmask = 0xffffffffu;
+  const int w = P.wb + (int)(P.wf * (float)ql);
+  int4 ri_cur = make_int4(0, 0, 0, 0), ri_nxt = make_int4(0, 0, 0, 0);
+  if (lane < n_ord) ri_nxt = W.rowinfo[lane];
+  int v_prev = 0, b_prev = 0, en_prev = W.end[0], l_prev = 1, r_prev = 1;   // the source row
+  bool prev_sm = en_prev < Ws;
+  for (int r = 0; r < n_ord; ++r) {
+    const int src = r & (G - 1);
+    if (src == 0) {
+      ri_cur = ri_nxt;
+      if (r + G + lane < n_ord) ri_nxt = W.rowinfo[r + G + lane];
+    }
+    const int v = __shfl_sync(gmask, ri_cur.x, src, G), in1 = __shfl_sync(gmask, ri_cur.y, src, G);
+    const int c = __shfl_sync(gmask, ri_cur.z, src, G), bv = __shfl_sync(gmask, ri_cur.w, src, G);
+    const bool single = !(in1 & 1);
+    const int p0 = in1 >> 1;
+    int p0b, p0e, pl, pr;
+    if (single) {
+      if (p0 == v_prev) { p0b = b_prev; p0e = en_prev; pl = l_prev; pr = r_prev; }
+      else { p0b = W.beg[p0]; p0e = W.end[p0]; pl = W.mpl[p0]; pr = W.mpr[p0]; }
+    } else {
+      p0b = 0; p0e = -1; pl = 0x7fffffff; pr = -1;
+      for (int e = W.first_in[v]; e >= 0; e = W.enin[e]) {
+        const int p = W.efrom[e];
+        // the row just finished hands its band over in registers (its stores are ordered by the NEXT barrier only)
+        pl = min(pl, p == v_prev ? l_prev : W.mpl[p]); pr = max(pr, p == v_prev ? r_prev : W.mpr[p]);
+      }
+    }
+    int b = max(0, min(pl, c) - w), en = min(ql, max(pr, c) + w);
+    if (b > en) b = en;
+    if (en - b + 1 > Wc) { en = b + Wc - 1; status |= POA_CLAMPED; }
+    int* hrow = W.H + (int64_t)v * Wc; int* e1row = W.E1 + (int64_t)v * Wc; int* e2row = W.E2 + (int64_t)v * Wc;
+    unsigned* tbrow = W.TB + (int64_t)v * Wc;
+    const int* const sprev = sbuf + (r & 1) * 3 * Ws;
+    int* const scur = sbuf + ((r + 1) & 1) * 3 * Ws;
+    const bool cur_sm = en - b + 1 <= Ws;
+    int carry1 = PNEG, carry2 = PNEG, prevflags = 0;
+    int rmax = PNEG - 1, rleft = 0, rright = 0;
+    int par = 0;
+    for (int jc = b; jc <= en; jc += G * NW, par ^= 1) {
+      const int j = jc + wid * G + lane;
+      const bool act = j <= en;
+      int m = PNEG, x1 = PNEG, x2 = PNEG, pm = 0, p1 = 0, p2 = 0, x1ext = 0, x2ext = 0;
+      const int qb = (act && j >= 1) ? q[j - 1] : 4;
+      auto consider = [&](int p, int bp, int ep, int ord) {
+        const int* ph = W.H + (int64_t)p * Wc;
+        const int* pe1 = W.E1 + (int64_t)p * Wc;
+        const int* pe2 = W.E2 + (int64_t)p * Wc;
+        if (prev_sm && p == v_prev) { ph = sprev; pe1 = sprev + Ws; pe2 = sprev + 2 * Ws; }
+        if (act && j >= 1 && j - 1 >= bp && j - 1 <= ep) {
+          const int sc_ = (bv >= 4 || qb >= 4) ? 0 : (bv == qb ? P.match : -mm);
+          const int cval = ph[j - 1 - bp] + sc_;
+          if (cval > m) { m = cval; pm = ord; }
+        }
+        if (act && j >= bp && j <= ep) {
+          const int hj = ph[j - bp];
+          int op = hj - P.o1, ex = pe1[j - bp];
+          int cval = max(op, ex) - P.e1;
+          if (cval > x1) { x1 = cval; p1 = ord; x1ext = ex > op; }
+          op = hj - P.o2; ex = pe2[j - bp];
+          cval = max(op, ex) - P.e2;
+          if (cval > x2) { x2 = cval; p2 = ord; x2ext = ex > op; }
+        }
+      };
+      if (single) consider(p0, p0b, p0e, 0);
+      else {
+        int ord = 0;
+        for (int e = W.first_in[v]; e >= 0; e = W.enin[e], ++ord) {
+          const int p = W.efrom[e];
+          consider(p, p == v_prev ? b_prev : W.beg[p], p == v_prev ? en_prev : W.end[p], ord);
+        }
+      }
+      m = max(m, PNEG); x1 = max(x1, PNEG); x2 = max(x2, PNEG);
+      int hp = m; unsigned hps = 0;
+      if (x1 > hp) { hp = x1; hps = 1; }
+      if (x2 > hp) { hp = x2; hps = 2; }
+      const int B1 = act ? hp + j * P.e1 : PNEG, B2 = act ? hp + j * P.e2 : PNEG;
+      const int inc1 = warp_incl_max<G>(B1, lane, gmask), inc2 = warp_incl_max<G>(B2, lane, gmask);
+      int* const X = xch + (par * NW + wid) * 6;
+      if (lane == G - 1) { X[0] = inc1; X[1] = inc2; X[4] = B1; X[5] = B2; }
+      if (lane == G - 2) { X[2] = inc1; X[3] = inc2; }
+      poa_cta_sync<NW>();
+      // every warp replays the carries of all groups of the chunk: its own carry-in and flag-in, and the chunk's carry-out
+      int cin1 = carry1, cin2 = carry2, pfl = prevflags;
+#pragma unroll
+      for (int g_ = 0; g_ < NW; ++g_) {
+        if (g_ == wid) { cin1 = carry1; cin2 = carry2; pfl = prevflags; }
+        const int* Y = xch + (par * NW + g_) * 6;
+        const int x1_31 = max(carry1, Y[2]), x2_31 = max(carry2, Y[3]);       // lane 31 of group g_: X = max(carry, inclusive scan at lane 30)
+        prevflags = (x1_31 > Y[4] ? 1 : 0) | (x2_31 > Y[5] ? 2 : 0);
+        carry1 = max(carry1, Y[0]); carry2 = max(carry2, Y[1]);
+      }
+      int ex1 = __shfl_up_sync(gmask, inc1, 1, G), ex2 = __shfl_up_sync(gmask, inc2, 1, G);
+      if (lane == 0) { ex1 = PNEG; ex2 = PNEG; }
+      const int X1 = max(cin1, ex1), X2 = max(cin2, ex2);
+      int f1 = PNEG, f2 = PNEG;
+      if (j > b) { f1 = max(X1 - P.o1 - j * P.e1, PNEG); f2 = max(X2 - P.o2 - j * P.e2, PNEG); }
+      const int myflags = (X1 > B1 ? 1 : 0) | (X2 > B2 ? 2 : 0);
+      int pf = __shfl_up_sync(gmask, myflags, 1, G);
+      if (lane == 0) pf = pfl;
+      const int f1ext = (j > b) && (pf & 1), f2ext = (j > b) && (pf & 2);
+      int hh = hp; unsigned hs = hps;
+      if (f1 > hh) { hh = f1; hs = 3; }
+      if (f2 > hh) { hh = f2; hs = 4; }
+      if (act) {
+        hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2;
+        if (cur_sm) { scur[j - b] = hh; scur[Ws + j - b] = x1; scur[2 * Ws + j - b] = x2; }
+        tbrow[j - b] = hs | (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)f1ext << 7) | ((unsigned)f2ext << 8) |
+                       ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) | ((unsigned)(p2 & 0x3f) << 26);
+        if (hh > rmax) { rmax = hh; rleft = j; rright = j; }
+        else if (hh == rmax) rright = j;
+      }
+    }
+    cells += (unsigned long long)(en - b + 1);
+    // row maximum with its first and last column: inside the warp, then across the warps
+    int gmax = __reduce_max_sync(gmask, rmax);
+    int l_ = __reduce_min_sync(gmask, (rmax == gmax) ? rleft : 0x7fffffff);
+    int r_ = __reduce_max_sync(gmask, (rmax == gmax) ? rright : -1);
+    int* const XR = xch + 12 * NW + (r & 1) * 3 * NW;
+    if (lane == 0) { XR[wid * 3] = gmax; XR[wid * 3 + 1] = l_; XR[wid * 3 + 2] = r_; }
+    poa_cta_sync<NW>();
+    gmax = XR[0];
+#pragma unroll
+    for (int g_ = 1; g_ < NW; ++g_) gmax = max(gmax, XR[g_ * 3]);
+    l_ = 0x7fffffff; r_ = -1;
+#pragma unroll
+    for (int g_ = 0; g_ < NW; ++g_) if (XR[g_ * 3] == gmax) { l_ = min(l_, XR[g_ * 3 + 1]); r_ = max(r_, XR[g_ * 3 + 2]); }
+    if (wid == 0 && lane == 0) { W.beg[v] = b; W.end[v] = en; W.mpl[v] = l_ + 1; W.mpr[v] = r_ + 1; }
+    v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1; prev_sm = cur_sm;
+  }
+  poa_cta_sync<NW>();   // every store of the rows is done (and visible) before the master walks back through them
+}
+
 #ifndef SVB_POA_MINB
 #define SVB_POA_MINB 4
 #endif
@@ -149,9 +299,11 @@ __device__ __forceinline__ void poa_prefetch(const void* p) {
 // is bound by the latency of dependent loads at a quarter of the issue rate, a band is 35-60 columns wide, and
 // the sequential walks use one lane -- so more, narrower instruction streams per warp hide more latency with
 // the same registers.  Everything below is written for a "group" of G lanes; `lane` is the lane in the group.
-template <int V, int G = 32, int MB = SVB_POA_MINB>
+template <int V, int G = 32, int MB = SVB_POA_MINB, int NW = 1>
 __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
   extern __shared__ int poa_smem[];
+  static_assert(NW == 1 || (NW == 4 && G == 32), "one warp per cluster, or the four warps of a CTA");
+  static_assert(NW == 1 || ((V & (POA_V_SMEM | POA_V_ROWS | POA_V_PARN)) == (POA_V_SMEM | POA_V_ROWS | POA_V_PARN)), "the CTA rows need SMEM, ROWS and PARN");
   constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0,
                  TBPF = (V & POA_V_TBPF) != 0, LEAN = (V & POA_V_LEAN) != 0, ROWS = (V & POA_V_ROWS) != 0, TBSPEC = (V & POA_V_TBSPEC) != 0,
                  UPDPAR = (V & POA_V_UPDPAR) != 0;
@@ -161,16 +313,38 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
   static_assert(G == 32 || G == 16 || G == 8, "group width");
   const int lane = threadIdx.x & (G - 1);
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int slot = NW > 1 ? (int)blockIdx.x : (int)((blockIdx.x * blockDim.x + threadIdx.x) / G);
+  const int wid = NW > 1 ? (int)(threadIdx.x >> 5) : 0;
   uint8_t* wsp = P.ws + P.slot_off[slot];
   Graph g;
   const PoaWs& W = g.w;
   const int mm = P.mismatch < 0 ? -P.mismatch : P.mismatch;
+  // NW = 4: warp 0 is the master and runs everything below; warps 1-3 only join the DP rows of every read.  ctl (shared):
+  // [0] command (1 = rows of a read, 2 = exit), [1] cluster, [2..3] sequence index, [4] nodes in rank order
+  int* const xch = NW > 1 ? poa_smem + 6 * P.swcap : nullptr;
+  volatile int* const ctl = NW > 1 ? poa_smem + 6 * P.swcap + 9 * NW * 2 : nullptr;
+  if (NW > 1 && wid != 0) {
+#ifdef __CUDA_ARCH__
+    for (;;) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ctl[0] == 2) return;
+      const uint32_t cid_h = (uint32_t)ctl[1];
+      const int64_t si_h = ((int64_t)(uint32_t)ctl[3] << 32) | (uint32_t)ctl[2];
+      const int4 dmh = P.dims[cid_h];
+      PoaWs Wh;
+      poa_ws_carve(wsp, dmh.x, dmh.y, dmh.z, dmh.w, &Wh);
+      int st_h = 0;
+      unsigned long long cells_h = 0;
+      poa_dp_rows_cta<NW>(P, Wh, P.seqs + P.seq_offs[si_h], (int)(P.seq_offs[si_h + 1] - P.seq_offs[si_h]), ctl[4], dmh.z, P.swcap, poa_smem, xch,
+                          wid, (int)(threadIdx.x & 31), mm, st_h, cells_h);
+    }
+#endif
+  }
   // shared copy of the row just finished: [2 buffers][H, E1, E2][Ws] per group.  Ws = P.swcap may be smaller than
   // the workspace row (wcap is a worst-case bound, a band is usually 35-60 columns): a row wider than Ws is simply
   // not copied and its successor reads the workspace (prev_sm says which).
   const int Ws = SMEM ? P.swcap : 0;
-  int* const sbuf = SMEM ? poa_smem + (threadIdx.x / G) * 6 * Ws : nullptr;
+  int* const sbuf = SMEM ? poa_smem + (NW > 1 ? 0 : (int)(threadIdx.x / G) * 6 * Ws) : nullptr;
   bool prev_sm = false;
   for (bool first_item = true;; first_item = false) {
     unsigned wi = 0;
@@ -288,6 +462,14 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
       // computed, the first predecessor sits next to them (in1 = pred << 1 | has-more-in-edges), and a
       // predecessor that is the row just finished hands its band over in registers: the common row
       // (one in-edge, from the previous row) waits for its predecessor's scores only.
+      if (NW > 1) {
+#ifdef __CUDA_ARCH__
+        if (lane == 0) { ctl[1] = (int)cid; ctl[2] = (int)(uint32_t)(si & 0xffffffffll); ctl[3] = (int)(uint32_t)((uint64_t)si >> 32); ctl[4] = n_ord; ctl[0] = 1; }
+        __syncwarp(gmask);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        poa_dp_rows_cta<NW>(P, W, q, ql, n_ord, Wc, Ws, sbuf, xch, 0, lane, mm, status, cells);
+#endif
+      } else {
       int v_next = (!ROWS && n_ord > 0) ? W.order[0] : 0;
       int nx_in1 = ROWS ? 0 : W.in1[v_next], nx_remain = ROWS ? 0 : W.remain[v_next], nx_base = ROWS ? 0 : W.base[v_next];
       int4 ri_cur = make_int4(0, 0, 0, 0), ri_nxt = make_int4(0, 0, 0, 0);   // ROWS: this lane's record of the current / next block of G rows
@@ -516,6 +698,7 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
         v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1; prev_sm = cur_sm;
         __syncwarp(gmask);
       }
+      }   // NW == 1
       PHASE(t_dp);
       // ---- end point, traceback, graph update, re-rank: lane 0
       int n_new_b = 0, nop_b = 0;
@@ -820,6 +1003,13 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
       }
     }
     __syncwarp(gmask);
+  }
+  if (NW > 1) {   // release the helpers for good
+#ifdef __CUDA_ARCH__
+    if (lane == 0) ctl[0] = 2;
+    __syncwarp(gmask);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#endif
   }
 }
 

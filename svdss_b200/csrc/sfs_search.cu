@@ -1647,8 +1647,9 @@ static void fill_params(SearchParams& P, const IndexDev& d) {
   const char* e = getenv("SVB_SEARCH_TEXT");   // SVB_SEARCH_TEXT=0: rank walk only (the pure FMD kernel)
   if (d.d_text && !(e && *e == '0')) {
     P.text = d.d_text; P.ssa = d.d_ssa; P.tstart = d.d_tstart; P.n_contigs = d.n_contigs; P.ss_log = d.ss_log;
-    P.max_nrun = (d.max_nrun >= 0 && d.max_nrun < 0x3fffffff && !getenv("SVB_SEARCH_NO_NRUN")) ? (int)d.max_nrun : -1;
   }
+  // a property of the indexed text, whichever way the extensions are answered; -1 (an index built from a bare BWT) switches the closed form off
+  P.max_nrun = (d.max_nrun >= 0 && d.max_nrun < 0x3fffffff && !getenv("SVB_SEARCH_NO_NRUN")) ? (int)d.max_nrun : -1;
   P.stats_on = getenv("SVB_SEARCH_STATS") != nullptr;
   P.sprint_budget = SPRINT_BUDGET;
   if (const char* eb = getenv("SVB_SPRINT_BUDGET")) P.sprint_budget = atoi(eb);
