@@ -426,7 +426,9 @@ def run_ours(args):
     launches = int(sum(x.search.launches + x.cl.launches + x.calls.launches for x in res + res_e))
     stages = {"search_ms": mean(lambda x: x.t_search), "cluster_ms": mean(lambda x: x.t_cluster), "call_ms": mean(lambda x: x.t_call),
               "cluster_host_sweep_ms": mean(lambda x: x.cl.host_ms), "call_host_ms": mean(lambda x: x.calls.host_ms),
-              "poa_kernel_ms": kern["k_poa"]["ms"], "ksw_kernel_ms": kern["k_ksw_extd2"]["ms"], "search_kernel_ms": search_kernel_ms}
+              "poa_kernel_ms": kern["k_poa"]["ms"], "ksw_kernel_ms": kern["k_ksw_extd2"]["ms"], "search_kernel_ms": search_kernel_ms,
+              "call_gather_ms": mean(lambda x: x.calls.gather_ms), "call_poa_stage_ms": mean(lambda x: x.calls.poa_ms), "call_ksw_stage_ms": mean(lambda x: x.calls.ksw_ms),
+              "call_device_ms": mean(lambda x: x.calls.device_ms), "poa_reruns": mean(lambda x: x.calls.poa_reruns)}
     stages_e = {"search_ms": mean(lambda x: x.t_search, res_e), "cluster_ms": mean(lambda x: x.t_cluster, res_e), "call_ms": mean(lambda x: x.t_call, res_e),
                 "gather_ms": mean(lambda x: x.t_gather, res_e)}
     h2d = int(res_e[-1].search.h2d_bytes + res_e[-1].cl.h2d_bytes + res_e[-1].calls.h2d_bytes)

@@ -350,6 +350,7 @@ typedef struct {
   float host_ms;               /* split_cluster + CIGAR walk on the host                                       */
   int32_t launches, poa_reruns, ksw_waves;
   int64_t h2d_bytes, d2h_bytes;
+  float poa_ms, ksw_ms;        /* wall clock of the whole POA / ksw2 stage of the call (uploads, workspace, kernels, downloads) */
 } svb_calls_t;
 
 /* Caller::pcall (caller.cpp:311-406) for the clusters of svb_cluster_batch (or any svb_clusters_t a caller fills:

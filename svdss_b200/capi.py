@@ -83,7 +83,7 @@ class CallsOut(C.Structure):
                 ("job_nv", C.POINTER(C.c_int32)), ("skipped_outside", C.c_int64), ("poa_cells", C.c_int64), ("ksw_cells", C.c_int64),
                 ("poa_kernel_ms", C.c_float), ("ksw_kernel_ms", C.c_float), ("gather_ms", C.c_float), ("device_ms", C.c_float),
                 ("host_ms", C.c_float), ("launches", C.c_int32), ("poa_reruns", C.c_int32), ("ksw_waves", C.c_int32),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("poa_ms", C.c_float), ("ksw_ms", C.c_float)]
 
 
 SVB_SEQ_ASCII, SVB_SEQ_NT6, SVB_SEQ_BAM4 = 0, 1, 2
@@ -678,7 +678,7 @@ class Calls:
         self.sv_type = arr(o.sv_type, ns, np.uint8)
         self.job_nv = arr(o.job_nv, nj, np.int32)
         for k in ("skipped_outside", "poa_cells", "ksw_cells", "poa_kernel_ms", "ksw_kernel_ms", "gather_ms", "device_ms", "host_ms",
-                  "launches", "poa_reruns", "ksw_waves", "h2d_bytes", "d2h_bytes"):
+                  "launches", "poa_reruns", "ksw_waves", "h2d_bytes", "d2h_bytes", "poa_ms", "ksw_ms"):
             setattr(self, k, getattr(o, k))
 
     def consensus(self, j):

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -261,21 +262,39 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
       out->h2d_bytes += n_js * 16 + 8;
     } else {
       h_sub.resize((size_t)std::max<int64_t>(tot, 1));
-      for (int64_t i = 0; i < n_js; ++i) {
-        const int s = out->job_sub[i];
-        const int qs = CL->sub_qs[s], len = sub_len[(size_t)s];
-        uint8_t* d = h_sub.data() + seq_offs[(size_t)i];
-        const uint8_t* base = RD->seq + src[(size_t)i];
-        if (RD->fmt == SVB_SEQ_BAM4) for (int k = 0; k < len; ++k) { const int p = qs + k; const uint8_t b = base[p >> 1]; d[k] = code_of_nt16((p & 1) ? (b & 0xf) : (b >> 4)); }
-        else if (RD->fmt == SVB_SEQ_NT6) for (int k = 0; k < len; ++k) d[k] = code_of_nt6(base[qs + k]);
-        else for (int k = 0; k < len; ++k) d[k] = code_of_ascii(base[qs + k]);
+      // the cut + decode of ~10^4..10^5 sub-reads from the caller's buffer: host threads over contiguous ranges of them
+      auto cut = [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) {
+          const int s = out->job_sub[i];
+          const int qs = CL->sub_qs[s], len = sub_len[(size_t)s];
+          uint8_t* d = h_sub.data() + seq_offs[(size_t)i];
+          const uint8_t* base = RD->seq + src[(size_t)i];
+          if (RD->fmt == SVB_SEQ_BAM4) for (int k = 0; k < len; ++k) { const int p = qs + k; const uint8_t b = base[p >> 1]; d[k] = code_of_nt16((p & 1) ? (b & 0xf) : (b >> 4)); }
+          else if (RD->fmt == SVB_SEQ_NT6) for (int k = 0; k < len; ++k) d[k] = code_of_nt6(base[qs + k]);
+          else for (int k = 0; k < len; ++k) d[k] = code_of_ascii(base[qs + k]);
+        }
+      };
+      const int nth = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, tot >> 20}));
+      if (nth == 1) cut(0, n_js);
+      else {
+        std::vector<std::thread> th;
+        int64_t a = 0;
+        for (int t = 0; t < nth; ++t) {      // ranges of equal bases
+          int64_t b = t + 1 == nth ? n_js : (int64_t)(std::upper_bound(seq_offs.begin(), seq_offs.begin() + n_js, tot * (t + 1) / nth) - seq_offs.begin());
+          b = std::max(a, std::min(b, n_js));
+          th.emplace_back(cut, a, b);
+          a = b;
+        }
+        for (auto& x : th) x.join();
       }
     }
     QCHECK(cudaEventRecord(e1, 0));
     // ---- run_poa for every job (caller.cpp:257-308)
+    const auto t_poa0 = std::chrono::steady_clock::now();
     rc = poa_batch_impl(RD->mem == SVB_MEM_DEVICE ? d_sub : h_sub.data(), RD->mem == SVB_MEM_DEVICE ? SVB_MEM_DEVICE : SVB_MEM_HOST, seq_offs.data(),
                         coffs.data(), nj, device, &poa);
     if (rc != SVB_OK) goto done;
+    out->poa_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_poa0).count();
     out->poa_cells = poa.cells; out->poa_kernel_ms = poa.kernel_ms; out->poa_reruns = poa.reruns; out->launches += poa.launches;
     out->h2d_bytes += poa.h2d_bytes; out->d2h_bytes += poa.d2h_bytes;
     // ---- ksw_extd2 of every consensus against its reference window (caller.cpp:329-355)
@@ -313,8 +332,10 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
       else for (auto& b : tw) b = code_of_ascii(b);
       std::vector<uint8_t> q((size_t)std::max<int64_t>(poa.cons_offs[nj], 1));
       memcpy(q.data(), poa.cons, (size_t)poa.cons_offs[nj]);
+      const auto t_ksw0 = std::chrono::steady_clock::now();
       rc = svb_ksw_extd2_batch(q.data(), poa.cons_offs, tw.data(), to.data(), nj, 1, -9, -1, 16, 2, 41, 1, device, &ez);   // caller.cpp:333-349
       if (rc != SVB_OK) goto done;
+      out->ksw_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_ksw0).count();
       out->ksw_cells = ez.cells; out->ksw_kernel_ms = ez.kernel_ms; out->ksw_waves = ez.waves; out->launches += ez.launches;
       out->h2d_bytes += ez.h2d_bytes; out->d2h_bytes += ez.d2h_bytes;
     }

@@ -123,10 +123,11 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
     const char* ev = getenv("SVB_POA_VARIANT");
     int variant = ev ? atoi(ev) : -1;
     if (variant < 0) {
-      // Two builds of the same kernel (identical results): 455 = 4 CTAs per SM, one column group per step -- the most clusters
-      // in flight, 37 GCUPS on 12 000 clusters of 20-60 reads (profiles/r02d_*); 3527 = 2 CTAs per SM, 255 registers, four
-      // column groups per step -- 1.65x shorter rows for a warp that runs alone.  A batch whose biggest cluster is a longer
-      // chain of rows (reads x nodes, ~1.2 us each) than the whole batch is work (cells at ~37 GCUPS) is bound by that chain.
+      // Two builds of the same kernel (identical results): 455 = a warp per cluster, 4 CTAs per SM -- the most clusters in
+      // flight, 37 GCUPS on 12 000 clusters of 20-60 reads (profiles/r02d_poa_variants.txt); 6599 = a CTA per cluster, its DP
+      // rows cut across the four warps, 2 CTAs per SM (217 registers, no spills) -- 2.7x shorter rows for a cluster that
+      // runs alone (profiles/r02f_*).  A batch whose biggest cluster is a longer chain of rows (reads x nodes, ~1 us each)
+      // than the whole batch is work (cells at ~37 GCUPS) is bound by that chain.
       double chain = 0, cells_est = 0;
       for (int64_t c = 0; c < n_clusters; ++c) {
         const Shape& s = shp[c];
@@ -134,7 +135,7 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
         chain = std::max(chain, (double)(s.nreads - 1) * (double)s.lmax);
         cells_est += (double)(s.sum - s.lmax) * (2.0 * (10 + 0.01 * s.lmax) + 1.0);
       }
-      variant = (chain * 1.2e-6 > cells_est / 37e9) ? 2048 + 1479 : 455;
+      variant = (chain * 1.0e-6 > cells_est / 37e9) ? 4096 + 2048 + 455 : 455;
     }
     // pass 0: heuristic capacities; pass 1: worst-case capacities for the clusters that overflowed
     std::vector<uint32_t> todo((size_t)n_clusters);

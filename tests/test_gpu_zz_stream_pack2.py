@@ -1,7 +1,9 @@
 """GPU: the 2-bit transport of the streamed search (SVB_STREAM_PACK2=1: every chunk re-packed on the host by
 svb_pack2_chunk, decoded by the unpacking CTAs of k_sfs_search_mop<.., .., true>, N positions patched before the
 chunk's flag goes up) gives the same SFS tables and extension counts as the 4-bit transport, with about half
-the bytes across PCIe.  Written without a GPU at hand and off by default: child process with a time limit."""
+the bytes across PCIe.  Green on a B200 since round 2 (profiles/r02a_variants_sweep.txt); the transport itself stays
+opt-in: on the bench host (16 cores per GPU) re-packing 7.6 GB per million reads on the host costs more than the PCIe
+time it saves (2.0 M against 5.6 M reads/s end to end, profiles/r02b_bench_full.txt).  Child process with a time limit."""
 import os
 import subprocess
 import sys
@@ -22,7 +24,7 @@ reads += synth.make_reads(contigs, 40, seed=53, mean_len=3001, sd_len=400, min_l
 reads.insert(5, np.zeros(0, np.uint8))
 reads.insert(77, reads[10][:1].copy())
 reads[20] = reads[20].copy(); reads[20][100:104] = 5
-reads[300] = np.full(260, 5, np.uint8)                                # a read of N only -- short: against the reference's 200 bp N runs every base of such a read is its own ~400-extension walk by one lane (an 8 kb one costs 3.2 M serial extensions per call)
+reads[300] = np.full(2600, 5, np.uint8)                               # a read of N only (restarts inside it have a closed form since round 2)
 cat, offs = oracle.concat(contigs)
 idx = capi.Index.build(cat, offs, block_bytes=128)
 seq4, s4o, lq = capi.pack_bam4(reads)
@@ -47,11 +49,6 @@ print("STREAM_PACK2_OK h2d bytes 4-bit %d, 2-bit %d" % (a.h2d_bytes, b.h2d_bytes
 """
 
 
-@pytest.mark.skipif(os.environ.get("SVB_TEST_STREAM_PACK2") != "1",
-                    reason="SVB_STREAM_PACK2 is experimental and unverified: its first contact with a B200 (last GPU seconds of round 1) "
-                           "did not finish within 38 s.  The test then held an 8 kb read of N only -- 3.2 M serial extensions by one lane in "
-                           "each of its 13 calls, which alone explains the time -- so no verdict either way; that read is short now.  "
-                           "Set SVB_TEST_STREAM_PACK2=1 to run it (DESIGN.md section 8, item 2)")
 def test_two_bit_transport_equals_four_bit_transport():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", CHILD], cwd=root, capture_output=True, text=True, timeout=200)

@@ -121,3 +121,38 @@ def test_two_rank_call_gather_matches_single_process():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert status == "ok" and sizes == [7, 7]
+
+
+def _rows_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from svdss_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the SV tables of bench.py's e2e step: [n, 4] int32 per rank, ragged, one rank with nothing to report
+    tabs = [np.arange(12, dtype=np.int32).reshape(3, 4) + 100 * r for r in range(world)]
+    tabs[1] = np.zeros((0, 4), np.int32)
+    got = parallel.gather_rows(tabs[rank], dist, dst=0)
+    got1 = parallel.gather_rows(np.array([7 + rank, 9 + rank], np.int32), dist, dst=0)      # 1-D tables become one column
+    if rank == 0:
+        ok = np.array_equal(got, np.concatenate(tabs, axis=0)) and got1.shape == (2 * world, 1) and got1[:, 0].tolist() == [7 + r + k * 2 for r in range(world) for k in (0, 1)]
+        q.put("ok" if ok else "mismatch")
+    else:
+        assert got is None and got1 is None                                               # payload goes to rank 0 only
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_rows_is_ragged_and_lands_on_rank0_only():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_rows_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    status = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=120)
+    assert status == "ok" and all(p.exitcode == 0 for p in procs)
