@@ -8,7 +8,7 @@ CPU implementation.
                                                 the search path assembles on the device)
   PingPong.process_batch ping_pong.cpp:176-209 (whole batch at once instead of one thread slot)
   PingPong.output_batch  ping_pong.cpp:213-236 (.sfs text, byte-compatible incl. the trailing TAB)
-  PingPong.search        ping_pong.cpp:239-397 (FASTX mode; BAM mode needs the BAM reader, next round)
+  PingPong.search        ping_pong.cpp:239-397 (FASTX mode only: BAM input is the C++ shell's job, svdss_b200/host/io.hpp + svdss_main.cpp)
 """
 import gzip
 import sys
