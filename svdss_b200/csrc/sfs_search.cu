@@ -1377,15 +1377,27 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, MINB) k_sfs_search_mop(const S
           // 2 L serial rank extensions per base on one lane.  [nr_lo, nr_hi] = bases already known to be N.
           const int L = P.max_nrun;
           if (!(nr_lo <= pos && pos <= nr_hi)) { nr_hi = pos; nr_lo = pos; nr_closed = pos == 0; }
-          const int need = pos - L;
-          while (!nr_closed && nr_lo > need) {
-            if (P.seq[roff + nr_lo - 1] == 5) { --nr_lo; if (nr_lo == 0) nr_closed = true; } else nr_closed = true;
+          if (nr_lo > pos - L) {   // not known yet: find the start of the run (once per run: later restarts inside it reuse [nr_lo, nr_hi])
+            while (!nr_closed) {
+              if (P.seq[roff + nr_lo - 1] == 5) { --nr_lo; if (nr_lo == 0) nr_closed = true; } else nr_closed = true;
+            }
           }
-          if (nr_lo <= need) {
-            n_ext += 2u * (unsigned)L;
-            on_sfs(need, L + 1);
+          if (nr_lo <= pos - L) {
+            // restarts pos, pos - 1, .., nr_lo + L all have the closed form: n SFSs (p - L, L + 1), each overlapping the next
+            const int n = pos - L - nr_lo + 1;
+            n_ext += 2u * (unsigned)L * (unsigned)n;
+            if (P.assemble) {
+              on_sfs(pos - L, L + 1);
+              chain_qs = nr_lo;                       // what on_sfs would leave after the other n - 1 (each starts one base lower)
+            } else {
+              const unsigned long long o0 = atomicAdd(P.out_count, (unsigned long long)n);
+              for (int i = 0; i < n; ++i) {
+                const unsigned long long o = o0 + (unsigned long long)i;
+                if (o < P.out_cap) { P.out_key[o] = ((uint64_t)ridx << 32) | (uint32_t)~(uint32_t)(pos - L - i); P.out_len[o] = (uint32_t)(L + 1); }
+              }
+            }
             hv = 0; tmode = false; spr = false;
-            if (need == 0) finish_read(); else --pos;
+            if (nr_lo == 0) finish_read(); else pos = nr_lo + L - 1;
             continue;
           }
         }
