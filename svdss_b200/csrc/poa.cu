@@ -224,18 +224,10 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
     k_poa<VV, 32><<<grid, 128, smem>>>(P);                                                                          \
     break;
       switch (variant) {
-        POA_LAUNCH(0) POA_LAUNCH(7) POA_LAUNCH(455) POA_LAUNCH(487) POA_LAUNCH(967) POA_LAUNCH(1479)
+        POA_LAUNCH(0) POA_LAUNCH(455)
         case 2048 + 1479:
           if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<1479, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           k_poa<1479, 32, 2><<<grid, 128, smem>>>(P);
-          break;
-        case 8192 + 455:
-          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<8192 + 455, 32, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_poa<8192 + 455, 32, 4, 1><<<grid, 128, smem>>>(P);
-          break;
-        case 8192 + 2048 + 455:
-          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<8192 + 455, 32, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_poa<8192 + 455, 32, 2, 1><<<grid, 128, smem>>>(P);
           break;
         case 4096 + 455:
           if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<455, 32, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -245,12 +237,8 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
           if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<455, 32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           k_poa<455, 32, 2, 4><<<grid, 128, smem>>>(P);
           break;
-        case 2048 + 967:
-          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<967, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_poa<967, 32, 2><<<grid, 128, smem>>>(P);
-          break;
         default:
-          set_error("SVB_POA_VARIANT=%d is not built (0 7 455 487 967 1479 3015 3527 4551 6599 8647 10695)", variant);
+          set_error("SVB_POA_VARIANT=%d is not built (0 = round 1, 455 = a warp per cluster, 3527 = the same with four column groups per step at 2 CTAs per SM, 4551 / 6599 = a CTA per cluster at 4 / 2 CTAs per SM)", variant);
           rc = SVB_EINVAL;
           goto done;
       }

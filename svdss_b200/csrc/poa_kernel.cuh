@@ -130,7 +130,9 @@ __device__ void poa_dp_rows_cta(const PoaParams& P, const PoaWs& W, const uint8_
       if (r + G + lane < n_ord) ri_nxt = W.rowinfo[r + G + lane];
     }
     const int v = __shfl_sync(gmask, ri_cur.x, src, G), in1 = __shfl_sync(gmask, ri_cur.y, src, G);
-    const int c = __shfl_sync(gmask, ri_cur.z, src, G), bv = __shfl_sync(gmask, ri_cur.w, src, G);
+    const int c = __shfl_sync(gmask, ri_cur.z, src, G), bvw = __shfl_sync(gmask, ri_cur.w, src, G);
+    const int bv = bvw & 0xff;
+    const bool need_g = (bvw >> 8) != 0;     // some reader of this row's scores is not the next row (poa_kernel.cuh, setup)
     const bool single = !(in1 & 1);
     const int p0 = in1 >> 1;
     int p0b, p0e, pl, pr;
@@ -222,7 +224,7 @@ __device__ void poa_dp_rows_cta(const PoaParams& P, const PoaWs& W, const uint8_
       if (f1 > hh) { hh = f1; hs = 3; }
       if (f2 > hh) { hh = f2; hs = 4; }
       if (act) {
-        hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2;
+        if (need_g || !cur_sm) { hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2; }
         if (cur_sm) { scur[j - b] = hh; scur[Ws + j - b] = x1; scur[2 * Ws + j - b] = x2; }
         tbrow[j - b] = hs | (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)f1ext << 7) | ((unsigned)f2ext << 8) |
                        ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) | ((unsigned)(p2 & 0x3f) << 26);
@@ -248,170 +250,6 @@ __device__ void poa_dp_rows_cta(const PoaParams& P, const PoaWs& W, const uint8_
     v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1; prev_sm = cur_sm;
   }
   poa_cta_sync<NW>();   // every store of the rows is done (and visible) before the master walks back through them
-}
-
-// ---- DP rows of one read by ONE warp with four ADJACENT columns per lane (k_poa<V | POA_V_BLK4>): a chunk is 128 columns,
-// lane l owns columns 4l .. 4l+3 of it.  The predecessor row comes in as one 16-byte shared-memory load per array, the four
-// recurrences are independent instruction streams, and each of the two max-plus scans is three in-lane steps plus ONE
-// five-step warp scan over the lane totals (instead of one warp scan per 32 columns): the shortest dependent chain per row
-// of all the builds, and no barrier.  Same values, same comparisons as the one-group row.
-__device__ __forceinline__ void poa_dp_rows_blk4(const PoaParams& P, const PoaWs& W, const uint8_t* __restrict__ q, const int ql, const int n_ord,
-                                                 const int Wc, const int Ws, int* const sbuf, const int lane, const int mm, int& status,
-                                                 unsigned long long& cells) {
-  constexpr int G = 32, C = 4;
-  const unsigned gmask = 0xffffffffu;
-  const int w = P.wb + (int)(P.wf * (float)ql);
-  int4 ri_cur = make_int4(0, 0, 0, 0), ri_nxt = make_int4(0, 0, 0, 0);
-  if (lane < n_ord) ri_nxt = W.rowinfo[lane];
-  int v_prev = 0, b_prev = 0, en_prev = W.end[0], l_prev = 1, r_prev = 1;   // the source row
-  bool prev_sm = en_prev < Ws;
-  for (int r = 0; r < n_ord; ++r) {
-    const int src = r & (G - 1);
-    if (src == 0) {
-      ri_cur = ri_nxt;
-      if (r + G + lane < n_ord) ri_nxt = W.rowinfo[r + G + lane];
-    }
-    const int v = __shfl_sync(gmask, ri_cur.x, src, G), in1 = __shfl_sync(gmask, ri_cur.y, src, G);
-    const int c = __shfl_sync(gmask, ri_cur.z, src, G), bv = __shfl_sync(gmask, ri_cur.w, src, G);
-    const bool single = !(in1 & 1);
-    const int p0 = in1 >> 1;
-    int p0b, p0e, pl, pr;
-    if (single) {
-      if (p0 == v_prev) { p0b = b_prev; p0e = en_prev; pl = l_prev; pr = r_prev; }
-      else { p0b = W.beg[p0]; p0e = W.end[p0]; pl = W.mpl[p0]; pr = W.mpr[p0]; }
-    } else {
-      p0b = 0; p0e = -1; pl = 0x7fffffff; pr = -1;
-      for (int e = W.first_in[v]; e >= 0; e = W.enin[e]) {
-        const int p = W.efrom[e];
-        pl = min(pl, W.mpl[p]); pr = max(pr, W.mpr[p]);
-      }
-    }
-    int b = max(0, min(pl, c) - w), en = min(ql, max(pr, c) + w);
-    if (b > en) b = en;
-    if (en - b + 1 > Wc) { en = b + Wc - 1; status |= POA_CLAMPED; }
-    int* hrow = W.H + (int64_t)v * Wc; int* e1row = W.E1 + (int64_t)v * Wc; int* e2row = W.E2 + (int64_t)v * Wc;
-    unsigned* tbrow = W.TB + (int64_t)v * Wc;
-    const int* const sprev = sbuf + (r & 1) * 3 * Ws;
-    int* const scur = sbuf + ((r + 1) & 1) * 3 * Ws;
-    const bool cur_sm = en - b + 1 <= Ws;
-    int carry1 = PNEG, carry2 = PNEG, prevflags = 0;
-    int rmax = PNEG - 1, rleft = 0, rright = 0;
-    for (int jc = b; jc <= en; jc += G * C) {
-      const int j0 = jc + lane * C;                    // this lane's first column
-      int hp_[C], x1_[C], x2_[C], B1_[C], B2_[C];
-      unsigned tb_[C];
-#pragma unroll
-      for (int k = 0; k < C; ++k) {
-        const int j = j0 + k;
-        const bool act = j <= en;
-        int m = PNEG, x1 = PNEG, x2 = PNEG, pm = 0, p1 = 0, p2 = 0, x1ext = 0, x2ext = 0;
-        const int qb = (act && j >= 1) ? q[j - 1] : 4;
-        auto consider = [&](int p, int bp, int ep, int ord) {
-          const int* ph = W.H + (int64_t)p * Wc;
-          const int* pe1 = W.E1 + (int64_t)p * Wc;
-          const int* pe2 = W.E2 + (int64_t)p * Wc;
-          if (prev_sm && p == v_prev) { ph = sprev; pe1 = sprev + Ws; pe2 = sprev + 2 * Ws; }
-          if (act && j >= 1 && j - 1 >= bp && j - 1 <= ep) {
-            const int sc_ = (bv >= 4 || qb >= 4) ? 0 : (bv == qb ? P.match : -mm);
-            const int cval = ph[j - 1 - bp] + sc_;
-            if (cval > m) { m = cval; pm = ord; }
-          }
-          if (act && j >= bp && j <= ep) {
-            const int hj = ph[j - bp];
-            int op = hj - P.o1, ex = pe1[j - bp];
-            int cval = max(op, ex) - P.e1;
-            if (cval > x1) { x1 = cval; p1 = ord; x1ext = ex > op; }
-            op = hj - P.o2; ex = pe2[j - bp];
-            cval = max(op, ex) - P.e2;
-            if (cval > x2) { x2 = cval; p2 = ord; x2ext = ex > op; }
-          }
-        };
-        if (single) consider(p0, p0b, p0e, 0);
-        else {
-          int ord = 0;
-          for (int e = W.first_in[v]; e >= 0; e = W.enin[e], ++ord) {
-            const int p = W.efrom[e];
-            consider(p, W.beg[p], W.end[p], ord);
-          }
-        }
-        m = max(m, PNEG); x1 = max(x1, PNEG); x2 = max(x2, PNEG);
-        int hp = m; unsigned hps = 0;
-        if (x1 > hp) { hp = x1; hps = 1; }
-        if (x2 > hp) { hp = x2; hps = 2; }
-        hp_[k] = hp; x1_[k] = x1; x2_[k] = x2;
-        tb_[k] = (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) |
-                 ((unsigned)(p2 & 0x3f) << 26);
-        B1_[k] = act ? hp + j * P.e1 : PNEG; B2_[k] = act ? hp + j * P.e2 : PNEG;
-      }
-      // in-lane inclusive maxima, then one warp scan over the lane totals
-      int I1[C], I2[C];
-      I1[0] = B1_[0]; I2[0] = B2_[0];
-#pragma unroll
-      for (int k = 1; k < C; ++k) { I1[k] = max(I1[k - 1], B1_[k]); I2[k] = max(I2[k - 1], B2_[k]); }
-      const int inc1 = warp_incl_max<G>(I1[C - 1], lane, gmask), inc2 = warp_incl_max<G>(I2[C - 1], lane, gmask);
-      int ex1 = __shfl_up_sync(gmask, inc1, 1, G), ex2 = __shfl_up_sync(gmask, inc2, 1, G);
-      if (lane == 0) { ex1 = PNEG; ex2 = PNEG; }
-      const int in1_ = max(carry1, ex1), in2_ = max(carry2, ex2);   // everything left of this lane's first column
-      int fl_[C];
-#pragma unroll
-      for (int k = 0; k < C; ++k) {
-        const int X1 = k ? max(in1_, I1[k - 1]) : in1_, X2 = k ? max(in2_, I2[k - 1]) : in2_;
-        fl_[k] = (X1 > B1_[k] ? 1 : 0) | (X2 > B2_[k] ? 2 : 0);
-        // reuse the B arrays for X (the B values are not needed past this point)
-        B1_[k] = X1; B2_[k] = X2;
-      }
-      int pf0 = __shfl_up_sync(gmask, fl_[C - 1], 1, G);            // flags of the column left of this lane's first
-      if (lane == 0) pf0 = prevflags;
-      int hh_[C]; unsigned tw_[C];
-#pragma unroll
-      for (int k = 0; k < C; ++k) {
-        const int j = j0 + k;
-        const bool act = j <= en;
-        int f1 = PNEG, f2 = PNEG;
-        if (j > b) { f1 = max(B1_[k] - P.o1 - j * P.e1, PNEG); f2 = max(B2_[k] - P.o2 - j * P.e2, PNEG); }
-        const int pf = k ? fl_[k - 1] : pf0;
-        const int f1ext = (j > b) && (pf & 1), f2ext = (j > b) && (pf & 2);
-        int hh = hp_[k]; unsigned hs = (tb_[k] >> 3) & 3u;
-        if (f1 > hh) { hh = f1; hs = 3; }
-        if (f2 > hh) { hh = f2; hs = 4; }
-        hh_[k] = hh; tw_[k] = hs | tb_[k] | ((unsigned)f1ext << 7) | ((unsigned)f2ext << 8);
-        if (act) {
-          if (hh > rmax) { rmax = hh; rleft = j; rright = j; }
-          else if (hh == rmax) rright = j;
-        }
-      }
-      // stores: four columns per lane, 16 bytes where the whole group lies inside the band
-      const int o = j0 - b;
-      if (j0 + C - 1 <= en) {
-        *reinterpret_cast<int4*>(hrow + o) = make_int4(hh_[0], hh_[1], hh_[2], hh_[3]);
-        *reinterpret_cast<int4*>(e1row + o) = make_int4(x1_[0], x1_[1], x1_[2], x1_[3]);
-        *reinterpret_cast<int4*>(e2row + o) = make_int4(x2_[0], x2_[1], x2_[2], x2_[3]);
-        *reinterpret_cast<int4*>(tbrow + o) = make_int4((int)tw_[0], (int)tw_[1], (int)tw_[2], (int)tw_[3]);
-        if (cur_sm) {
-          *reinterpret_cast<int4*>(scur + o) = make_int4(hh_[0], hh_[1], hh_[2], hh_[3]);
-          *reinterpret_cast<int4*>(scur + Ws + o) = make_int4(x1_[0], x1_[1], x1_[2], x1_[3]);
-          *reinterpret_cast<int4*>(scur + 2 * Ws + o) = make_int4(x2_[0], x2_[1], x2_[2], x2_[3]);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < C; ++k)
-          if (j0 + k <= en) {
-            hrow[o + k] = hh_[k]; e1row[o + k] = x1_[k]; e2row[o + k] = x2_[k]; tbrow[o + k] = tw_[k];
-            if (cur_sm) { scur[o + k] = hh_[k]; scur[Ws + o + k] = x1_[k]; scur[2 * Ws + o + k] = x2_[k]; }
-          }
-      }
-      carry1 = max(carry1, __shfl_sync(gmask, inc1, G - 1, G));
-      carry2 = max(carry2, __shfl_sync(gmask, inc2, G - 1, G));
-      prevflags = __shfl_sync(gmask, fl_[C - 1], G - 1, G);
-    }
-    cells += (unsigned long long)(en - b + 1);
-    const int gmax = __reduce_max_sync(gmask, rmax);
-    const int l_ = __reduce_min_sync(gmask, (rmax == gmax) ? rleft : 0x7fffffff);
-    const int r_ = __reduce_max_sync(gmask, (rmax == gmax) ? rright : -1);
-    if (lane == 0) { W.beg[v] = b; W.end[v] = en; W.mpl[v] = l_ + 1; W.mpr[v] = r_ + 1; }
-    v_prev = v; b_prev = b; en_prev = en; l_prev = l_ + 1; r_prev = r_ + 1; prev_sm = cur_sm;
-    __syncwarp(gmask);
-  }
 }
 
 #ifndef SVB_POA_MINB
@@ -448,7 +286,7 @@ __device__ __forceinline__ void poa_dp_rows_blk4(const PoaParams& P, const PoaWs
 //            runs alone on its scheduler -- the tail of a batch is one big cluster, 30 reads x 5 000 rows of 121 columns
 //            -- no longer pays one dependent-issue latency per instruction
 constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, POA_V_TBPF = 16, POA_V_LEAN = 32, POA_V_ROWS = 64,
-              POA_V_TBSPEC = 128, POA_V_UPDPAR = 256, POA_V_ILP2 = 512, POA_V_ILP4 = 1024, POA_V_BLK4 = 8192;
+              POA_V_TBSPEC = 128, POA_V_UPDPAR = 256, POA_V_ILP2 = 512, POA_V_ILP4 = 1024;
 
 __device__ __forceinline__ void poa_prefetch(const void* p) {
 #ifdef __CUDA_ARCH__
@@ -573,11 +411,15 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
           const int r = r0 - lane;
           const bool valid = r >= -1;
           int v = -1, bv = 1;
+          int need_g = 0;   // ROWS: some successor is not the next row in rank order (or is the sink): the row's scores must reach the workspace
           if (valid) {
             v = r >= 0 ? W.order[r] : 0;
             int bw = -1;
-            for (int e = W.first_out[v]; e >= 0; e = W.enout[e])
-              if (W.ew[e] > bw) { bw = W.ew[e]; bv = W.eto[e]; }
+            for (int e = W.first_out[v]; e >= 0; e = W.enout[e]) {
+              const int o_ = W.eto[e];
+              if (W.ew[e] > bw) { bw = W.ew[e]; bv = o_; }
+              if (ROWS && (o_ == 1 || W.rank[o_] != r + 1)) need_g = 1;
+            }
           }
           int rem = valid ? W.remain[bv] : 0;      // final unless bv sits in this chunk (then replaced below)
           for (int s = 0; s < G; ++s) {
@@ -586,7 +428,7 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
             if (lane > s && valid && bv == vs) rem = rs;
           }
           if (valid) W.remain[v] = rem + 1;
-          if (ROWS && valid && r >= 0) W.rowinfo[r] = make_int4(v, W.in1[v], ql - (rem + 1) + 1, (int)W.base[v]);
+          if (ROWS && valid && r >= 0) W.rowinfo[r] = make_int4(v, W.in1[v], ql - (rem + 1) + 1, (int)W.base[v] | (need_g << 8));
           __syncwarp(gmask);
         }
       } else if (lane == 0) {
@@ -626,9 +468,7 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
       // computed, the first predecessor sits next to them (in1 = pred << 1 | has-more-in-edges), and a
       // predecessor that is the row just finished hands its band over in registers: the common row
       // (one in-edge, from the previous row) waits for its predecessor's scores only.
-      if (NW == 1 && (V & POA_V_BLK4)) {
-        poa_dp_rows_blk4(P, W, q, ql, n_ord, Wc, Ws, sbuf, lane, mm, status, cells);
-      } else if (NW > 1) {
+      if (NW > 1) {
 #ifdef __CUDA_ARCH__
         if (lane == 0) { ctl[1] = (int)cid; ctl[2] = (int)(uint32_t)(si & 0xffffffffll); ctl[3] = (int)(uint32_t)((uint64_t)si >> 32); ctl[4] = n_ord; ctl[0] = 1; }
         __syncwarp(gmask);
@@ -644,6 +484,7 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
       prev_sm = SMEM && en_prev < Ws;
       for (int r = 0; r < n_ord; ++r) {
         int v, in1, bv, c;
+        bool need_g = true;            // ROWS: false when the only reader of this row's scores is the next row, through shared memory
         if (ROWS) {
           const int src = r & (G - 1);
           if (src == 0) {                               // a new block: the records fetched a block ago, and the next fetch goes out
@@ -652,6 +493,7 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
           }
           v = __shfl_sync(gmask, ri_cur.x, src, G); in1 = __shfl_sync(gmask, ri_cur.y, src, G);
           c = __shfl_sync(gmask, ri_cur.z, src, G); bv = __shfl_sync(gmask, ri_cur.w, src, G);
+          need_g = (bv >> 8) != 0; bv &= 0xff;
         } else {
           v = v_next; in1 = nx_in1; bv = nx_base;
           c = ql - nx_remain + 1;
@@ -752,7 +594,7 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
               if (f1 > hh) { hh = f1; hs = 3; }
               if (f2 > hh) { hh = f2; hs = 4; }
               if (act) {
-                hrow[j - b] = hh; e1row[j - b] = x1_[g_]; e2row[j - b] = x2_[g_];
+                if (need_g || !cur_sm) { hrow[j - b] = hh; e1row[j - b] = x1_[g_]; e2row[j - b] = x2_[g_]; }
                 if (cur_sm) { scur[j - b] = hh; scur[Ws + j - b] = x1_[g_]; scur[2 * Ws + j - b] = x2_[g_]; }
                 tbrow[j - b] = hs | tb_[g_] | ((unsigned)f1ext << 7) | ((unsigned)f2ext << 8);
                 if (hh > rmax) { rmax = hh; rleft = j; rright = j; }
@@ -827,7 +669,7 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
           if (f1 > hh) { hh = f1; hs = 3; }
           if (f2 > hh) { hh = f2; hs = 4; }
           if (act) {
-            hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2;
+            if (need_g || !cur_sm) { hrow[j - b] = hh; e1row[j - b] = x1; e2row[j - b] = x2; }
             if (cur_sm) { scur[j - b] = hh; scur[Ws + j - b] = x1; scur[2 * Ws + j - b] = x2; }
             tbrow[j - b] = hs | (hps << 3) | ((unsigned)x1ext << 5) | ((unsigned)x2ext << 6) | ((unsigned)f1ext << 7) |
                            ((unsigned)f2ext << 8) | ((unsigned)(pm & 0xff) << 12) | ((unsigned)(p1 & 0x3f) << 20) |
