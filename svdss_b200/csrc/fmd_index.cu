@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 
@@ -444,6 +445,8 @@ int build_suffix_array(const uint8_t* d_T, int64_t n, uint64_t* d_SA, cudaStream
 
   // ---- 3. prefix doubling on the unresolved set
   int64_t h = 21;
+  const bool stats = getenv("SVB_INDEX_STATS") != nullptr;
+  if (stats) fprintf(stderr, "[index] first pass (21-symbol keys): %lld of %lld suffixes unresolved (limit 2^31 = %lld)\n", (long long)u, (long long)n, 1LL << 31);
   if (u >= (1LL << 31)) {
     set_error("%lld unresolved suffixes after the first pass exceed the 2^31 limit", (long long)u);
     return SVB_ERANGE;
@@ -486,6 +489,7 @@ int build_suffix_array(const uint8_t* d_T, int64_t n, uint64_t* d_SA, cudaStream
         std::swap(pU, pU2);
         // pUg now holds compacted ranks
       }
+      if (stats) fprintf(stderr, "[index] doubling round %d (h = %lld): %lld -> %lld unresolved, %u groups\n", iter, (long long)h, (long long)u, (long long)nun, ngroups);
       u = nun;
       h *= 2;
     }

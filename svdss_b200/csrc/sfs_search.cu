@@ -1823,6 +1823,13 @@ static int pick_cfg(int slices, int* G) {
     }                                                                             \
   } while (0)
 
+// a pair of timing events that early returns cannot leak
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
 struct SearchScratch {
   unsigned long long* d_ctr = nullptr;  // [0] work [1] out_count [2] ext [3] blocks [4] text extensions [5] stream stalled
   uint64_t* d_key = nullptr; uint64_t* d_key2 = nullptr;
@@ -1929,8 +1936,9 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   }
   if (src && src->packed && cfgG != -2) { set_error("packed streamed batches need the default search kernel"); return SVB_EINVAL; }
   cudaEvent_t e0, e1;
-  SVB_CUDA(cudaEventCreate(&e0));
-  SVB_CUDA(cudaEventCreate(&e1));
+  EventPair evp_;
+  SVB_CUDA(evp_.create());
+  e0 = evp_.a; e1 = evp_.b;
   unsigned long long ctr[16] = {0};
   float kms = 0.f;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -2033,12 +2041,16 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
     SVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     kms += ms;
     out->launches += 1;
-    if (ctr[5]) { set_error("the read stream stalled: chunks queued behind the search kernel never arrived"); return SVB_ECUDA; }
+    if (ctr[5]) {
+      // copies queued on the copy stream still read the caller's staging buffers: let them drain before the caller gets its buffers back
+      if (src && src->copy_stream) cudaStreamSynchronize(src->copy_stream);
+      set_error("the read stream stalled: chunks queued behind the search kernel never arrived");
+      return SVB_ECUDA;
+    }
     if (ctr[1] <= cap) break;
     cap = ctr[1];
     if (attempt == 1) { set_error("output overflow persisted"); return SVB_ERANGE; }
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   out->kernel_ms = kms;
   out->n_ext = (int64_t)ctr[2];
   out->n_blocks_touched = (int64_t)ctr[3];
@@ -2154,14 +2166,14 @@ int svb_sfs_resident(const svb_index_t* idx, const svb_reads_t* reads, int overl
   SVB_TRY(check_device(idx->dev.device));
   if (reads->device != idx->dev.device) { set_error("reads and index live on different devices"); return SVB_EINVAL; }
   cudaEvent_t e0, e1;
-  SVB_CUDA(cudaEventCreate(&e0));
-  SVB_CUDA(cudaEventCreate(&e1));
+  EventPair evp_;
+  SVB_CUDA(evp_.create());
+  e0 = evp_.a; e1 = evp_.b;
   SVB_CUDA(cudaEventRecord(e0, 0));
   int rc = run_search(idx->dev, reads, overlap, assemble, out, 0);
   cudaEventRecord(e1, 0);
   cudaEventSynchronize(e1);
   cudaEventElapsedTime(&out->device_ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (rc != SVB_OK) svb_sfs_out_free(out);
   return rc;
 }
@@ -2322,8 +2334,9 @@ int svb_sfs_batch(const svb_index_t* idx, const uint8_t* seq, const int64_t* off
   memset(out, 0, sizeof(*out));
   SVB_TRY(check_device(idx->dev.device));
   cudaEvent_t e0, e1;
-  SVB_CUDA(cudaEventCreate(&e0));
-  SVB_CUDA(cudaEventCreate(&e1));
+  EventPair evp_;
+  SVB_CUDA(evp_.create());
+  e0 = evp_.a; e1 = evp_.b;
   SVB_CUDA(cudaEventRecord(e0, 0));
   int rc = SVB_OK, cfgG = 0;
   rc = pick_cfg(idx->dev.G, &cfgG);
@@ -2346,7 +2359,6 @@ int svb_sfs_batch(const svb_index_t* idx, const uint8_t* seq, const int64_t* off
   cudaEventRecord(e1, 0);
   cudaEventSynchronize(e1);
   cudaEventElapsedTime(&out->device_ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (rc != SVB_OK) svb_sfs_out_free(out);
   return rc;
 }
@@ -2367,8 +2379,9 @@ int svb_sfs_batch_bam4(const svb_index_t* idx, const uint8_t* seq4, const int64_
   }
   if (offs[n_reads] > 0 && !seq4) { set_error("svb_sfs_batch_bam4: null sequence buffer"); return SVB_EINVAL; }
   cudaEvent_t e0, e1;
-  SVB_CUDA(cudaEventCreate(&e0));
-  SVB_CUDA(cudaEventCreate(&e1));
+  EventPair evp_;
+  SVB_CUDA(evp_.create());
+  e0 = evp_.a; e1 = evp_.b;
   SVB_CUDA(cudaEventRecord(e0, 0));
   const char* ns = getenv("SVB_NO_STREAM");
   int64_t stream_min = (int64_t)32 << 20;
@@ -2385,7 +2398,6 @@ int svb_sfs_batch_bam4(const svb_index_t* idx, const uint8_t* seq4, const int64_
   cudaEventRecord(e1, 0);
   cudaEventSynchronize(e1);
   cudaEventElapsedTime(&out->device_ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (rc != SVB_OK) svb_sfs_out_free(out);
   return rc;
 }
@@ -2509,8 +2521,9 @@ int svb_rank_bench(const svb_index_t* idx, int64_t nq, int64_t delta, uint64_t s
 #undef SVB_GRID
   }
   cudaEvent_t e0, e1;
-  SVB_CUDA(cudaEventCreate(&e0));
-  SVB_CUDA(cudaEventCreate(&e1));
+  EventPair evp_;
+  SVB_CUDA(evp_.create());
+  e0 = evp_.a; e1 = evp_.b;
   // one untimed warm-up launch, then `iters` timed launches with distinct seeds
   for (int it = -1; it < iters; ++it) {
     if (it == 0) { SVB_CUDA(cudaMemset(dctr, 0, 16)); SVB_CUDA(cudaEventRecord(e0, 0)); }
@@ -2534,7 +2547,6 @@ int svb_rank_bench(const svb_index_t* idx, int64_t nq, int64_t delta, uint64_t s
   unsigned long long ctr[2];
   SVB_CUDA(cudaMemcpy(ctr, dctr, 16, cudaMemcpyDeviceToHost));
   if (blocks_touched) *blocks_touched = (int64_t)(ctr[1] / (unsigned long long)iters);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(dctr);
   return SVB_OK;
 }

@@ -273,6 +273,8 @@ struct BamRecord {
   std::vector<uint32_t> cigar; // len<<4 | op (MIDNSHP=X), as stored
   std::vector<uint8_t> seq4;   // 4-bit packed sequence, as stored (Clusterer decodes it on demand)
   bool has_xf = false, has_hp = false;
+  bool cg_cigar = false;       // `cigar` came from the CG:B,I tag of a record with more than 65535 ops
+  size_t cg_off = 0, cg_len = 0;   // where that tag sits in `raw` (offset of its two-letter name, bytes incl. name and type)
   int64_t xf = 0, hp = 0;
   // raw mode (`smooth`): the record body as stored (without its 4-byte length) and where its parts start
   std::vector<uint8_t> raw;
@@ -362,7 +364,7 @@ class BamReader {
     o += seq_bytes + (size_t)r.l_qseq;
     r.off_aux = o;
     if (want_raw_) r.raw.assign(p, p + bs);
-    r.has_xf = r.has_hp = false; r.xf = r.hp = 0;
+    r.has_xf = r.has_hp = false; r.xf = r.hp = 0; r.cg_cigar = false; r.cg_off = r.cg_len = 0;
     // aux fields (bam_aux_get + bam_aux2i for XF / HP, ping_pong.cpp:196-201)
     while (o + 3 <= (size_t)bs) {
       const char t0 = (char)p[o], t1 = (char)p[o + 1], ty = (char)p[o + 2];
@@ -383,7 +385,17 @@ class BamReader {
           if (o + 5 > (size_t)bs) return -1;
           const char st = (char)p[o]; int32_t cnt; memcpy(&cnt, p + o + 1, 4);
           const size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
-          o += 5 + es * (size_t)(cnt < 0 ? 0 : cnt);
+          const size_t bytes = es * (size_t)(cnt < 0 ? 0 : cnt);
+          if (o + 5 + bytes > (size_t)bs) return -1;
+          // CG:B,I -- the real CIGAR of a record with more than 65535 ops, whose CIGAR field then holds the placeholder
+          // <l_seq>S<ref_len>N (SAM spec 4.2.2; htslib's sam_read1 swaps it in transparently, bam_tag2cigar).  ADVICE r1.
+          if (want_align_ && t0 == 'C' && t1 == 'G' && st == 'I' && cnt > 0 && r.cigar.size() == 2 && (r.cigar[0] & 0xf) == 4 &&
+              (int32_t)(r.cigar[0] >> 4) == r.l_qseq && (r.cigar[1] & 0xf) == 3) {
+            r.cigar.resize((size_t)cnt);
+            memcpy(r.cigar.data(), p + o + 5, (size_t)cnt * 4);
+            r.cg_cigar = true; r.cg_off = o - 3; r.cg_len = 3 + 5 + bytes;
+          }
+          o += 5 + bytes;
           break;
         }
         default: return -1;

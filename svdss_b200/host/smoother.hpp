@@ -166,17 +166,39 @@ inline std::vector<uint8_t> rebuild_record(const BamRecord& r, const SmoothOut& 
   if (!init) { memset(nt16_of, 15, sizeof(nt16_of)); const char* t = "=ACMGRSVTWYHKDBN"; for (int i = 0; i < 16; ++i) { nt16_of[(uint8_t)t[i]] = (uint8_t)i; nt16_of[(uint8_t)tolower(t[i])] = (uint8_t)i; } init = true; }
   const size_t l = s.seq.size();
   std::vector<uint8_t> b(r.raw.begin(), r.raw.begin() + (std::ptrdiff_t)r.off_cigar);   // core + qname
-  const uint16_t n_cigar = (uint16_t)s.cigar.size();
+  // more than 65535 ops do not fit bam1_core_t::n_cigar: the CIGAR field then holds <l_seq>S<ref_len>N and the real one
+  // travels in a CG:B,I tag (SAM spec 4.2.2; what htslib's bam_write1 does)
+  const bool long_cigar = s.cigar.size() > 65535;
+  uint32_t placeholder[2] = {0, 0};
+  if (long_cigar) {
+    uint32_t span = 0;
+    for (uint32_t c : s.cigar) { const uint32_t op = c & 0xf; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4; }
+    placeholder[0] = (uint32_t)l << 4 | 4; placeholder[1] = span << 4 | 3;
+  }
+  const uint16_t n_cigar = long_cigar ? 2 : (uint16_t)s.cigar.size();
   const int32_t l_qseq = (int32_t)l;
   memcpy(&b[12], &n_cigar, 2);
   memcpy(&b[16], &l_qseq, 4);
-  const uint8_t* cp = reinterpret_cast<const uint8_t*>(s.cigar.data());
-  b.insert(b.end(), cp, cp + 4 * s.cigar.size());
+  const uint8_t* cp = long_cigar ? reinterpret_cast<const uint8_t*>(placeholder) : reinterpret_cast<const uint8_t*>(s.cigar.data());
+  b.insert(b.end(), cp, cp + 4 * (size_t)n_cigar);
   const size_t so = b.size();
   b.resize(so + (l + 1) / 2, 0);
   for (size_t i = 0; i < l; ++i) b[so + (i >> 1)] |= (uint8_t)(nt16_of[(uint8_t)s.seq[i]] << ((i & 1) ? 0 : 4));   // encode_bam_seq, bam.cpp:47-63
   b.insert(b.end(), s.qual.begin(), s.qual.end());
-  b.insert(b.end(), r.raw.begin() + (std::ptrdiff_t)r.off_aux, r.raw.end());
+  // the aux block as it was, minus a CG tag the reader resolved (its CIGAR is stale now)
+  if (r.cg_cigar && r.cg_off >= r.off_aux && r.cg_off + r.cg_len <= r.raw.size()) {
+    b.insert(b.end(), r.raw.begin() + (std::ptrdiff_t)r.off_aux, r.raw.begin() + (std::ptrdiff_t)r.cg_off);
+    b.insert(b.end(), r.raw.begin() + (std::ptrdiff_t)(r.cg_off + r.cg_len), r.raw.end());
+  } else b.insert(b.end(), r.raw.begin() + (std::ptrdiff_t)r.off_aux, r.raw.end());
+  if (long_cigar) {
+    const uint8_t hd[4] = {'C', 'G', 'B', 'I'};
+    const int32_t cnt = (int32_t)s.cigar.size();
+    b.insert(b.end(), hd, hd + 4);
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(&cnt);
+    b.insert(b.end(), q, q + 4);
+    const uint8_t* c2 = reinterpret_cast<const uint8_t*>(s.cigar.data());
+    b.insert(b.end(), c2, c2 + 4 * s.cigar.size());
+  }
   return b;
 }
 

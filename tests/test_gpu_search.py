@@ -361,3 +361,37 @@ def test_runs_of_n_longer_than_any_in_the_text_have_a_closed_form():
         del os.environ["SVB_SEARCH_NO_NRUN"]
     assert got2 == exp and res2.n_ext == ext
     print("N-run closed form: kernel %.2f ms (call %.1f ms; the all-N read alone %.2f ms) vs %.1f ms walking" % (res.kernel_ms, dt * 1e3, res1.kernel_ms, res2.kernel_ms))
+
+
+def test_index_builder_on_a_repeat_rich_reference():
+    """Segmental duplications (exact and 1 %-diverged copies, either strand) and tandem arrays: most suffixes stay
+    unresolved after the first pass of the suffix sort and go through prefix doubling.  SA and BWT must equal the
+    oracle's, and the search on that index must agree with the oracle port."""
+    rng = np.random.default_rng(31)
+    n = 400_000
+    ref = rng.integers(1, 5, n).astype(np.uint8)
+    for _ in range(12):                                          # segmental duplications, half reverse-complemented
+        L = int(rng.integers(5_000, 30_000))
+        src, dst = int(rng.integers(0, n - L)), int(rng.integers(0, n - L))
+        seg = ref[src:src + L].copy()
+        if rng.random() < 0.5:
+            seg = synth.revcomp6(seg)
+        if rng.random() < 0.7:
+            m = rng.random(L) < 0.01
+            seg[m] = (seg[m] % 4) + 1
+        ref[dst:dst + L] = seg
+    for _ in range(10):                                          # tandem arrays
+        unit = rng.integers(1, 5, int(rng.integers(1, 40))).astype(np.uint8)
+        L = int(rng.integers(500, 6_000))
+        dst = int(rng.integers(0, n - L))
+        ref[dst:dst + L] = np.tile(unit, L // len(unit) + 1)[:L]
+    contigs = [ref[:150_000].copy(), ref[150_000:].copy()]
+    T, SA, bwt = oracle_index(contigs)
+    cat, offs = oracle.concat(contigs)
+    idx = capi.Index.build(cat, offs)
+    assert np.array_equal(idx.bwt(), bwt)
+    assert np.array_equal(capi.suffix_array(T), SA)
+    reads = synth.make_reads(contigs, 150, seed=32, mean_len=4000, sd_len=1500, min_len=300, max_len=9000)
+    exp, ext = fm_results(oracle.FMIndex(bwt), reads)
+    got, res = _gpu_sfs(idx, reads, assemble=False)
+    assert got == exp and res.n_ext == ext
