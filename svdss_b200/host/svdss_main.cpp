@@ -350,8 +350,13 @@ static int run_search(const Config& c) {
     return EXIT_FAILURE;
   }
   const double t_loaded = now_s();
-  // GPU submissions cover as many logical batches as fit ~4 Gbases of reads
-  const size_t gpu_bases = (size_t)4 << 30;
+  // A GPU submission covers as many logical batches (--bsize) as fit ~1 Gbases of reads (SVB_SEARCH_SUBMIT_BASES): output
+  // flows after every submission, like the reference's per-batch output (--omax); round 1 waited for 4 Gbases.
+  // One deviation from the reference stays: when the same qname lands in one thread slot twice, the reference's
+  // std::map<qname, vector<SFS>> lets Assembler::assemble merge the SFSs of both records; here every record is assembled
+  // on its own (primary alignments carry unique names, so this needs a malformed BAM).
+  size_t gpu_bases = (size_t)1 << 30;
+  if (const char* e = getenv("SVB_SEARCH_SUBMIT_BASES")) { const long long v = atoll(e); if (v > 0) gpu_bases = (size_t)v; }
   vector<PendingRead> reads;
   vector<uint8_t> cat;
   uint64_t total_sfs = 0, processed = 0;
