@@ -269,14 +269,36 @@ class Slice:
             torch.cuda.synchronize(dev)
             self.host4_np = self.host4.numpy()
 
+    def pin(self, torch):
+        """the record arrays the Clusterer gets every step, in pinned host memory (what a loader that fills them once per
+        slice would use): the uploads inside svb_cluster_batch then run at PCIe speed instead of through bounce buffers"""
+        S = self.S
+        self._pinned = {}
+        for k, dt in (("tid", np.int32), ("pos", np.int32), ("hp", np.int32), ("cigar_offs", np.int64), ("cigar", np.uint32)):
+            a = np.ascontiguousarray(S[k], dt)
+            t = torch.empty(max(1, a.nbytes), dtype=torch.uint8, pin_memory=True)
+            v = t.numpy()[:a.nbytes].view(dt)
+            v[:] = a
+            self._pinned[k] = (t, v)
+        t = torch.empty((self.n + 1) * 8, dtype=torch.uint8, pin_memory=True)
+        self._so = (t, t.numpy().view(np.int64))
+        self._cnt = np.zeros(self.n, np.int64)
+
     def alns(self, capi, r):
         """svb_alns_t of the slice with the SFS table of search result r (reads of r = self.searched, ascending)"""
-        cnt = np.zeros(self.n, np.int64)
-        cnt[self.searched] = np.diff(r.offs)
-        so = np.zeros(self.n + 1, np.int64)
-        np.cumsum(cnt, out=so[1:])
-        S = self.S
-        return capi.AlnBatch(S["tid"], S["pos"], S["hp"], S["cigar_offs"], S["cigar"], so, r.qs, r.len)
+        if getattr(self, "_pinned", None) is None:
+            cnt = np.zeros(self.n, np.int64)
+            cnt[self.searched] = np.diff(r.offs)
+            so = np.zeros(self.n + 1, np.int64)
+            np.cumsum(cnt, out=so[1:])
+            S = self.S
+            return capi.AlnBatch(S["tid"], S["pos"], S["hp"], S["cigar_offs"], S["cigar"], so, r.qs, r.len)
+        self._cnt[self.searched] = np.diff(r.offs)
+        so = self._so[1]
+        so[0] = 0
+        np.cumsum(self._cnt, out=so[1:])
+        P = self._pinned
+        return capi.AlnBatch(P["tid"][1], P["pos"][1], P["hp"][1], P["cigar_offs"][1], P["cigar"][1], so, r.qs, r.len)
 
     def truth(self):
         """planted SVs at least two searched reads of the slice carry: set of (tid, is_del, len, pos)"""
@@ -316,6 +338,7 @@ def run_ours(args):
     idx, ref, offs, setup = build_reference_and_index(args, rank, local, torch, capi)
     t0 = time.time()
     sl = Slice(args, rank, local, ref, offs, torch, capi, synth)
+    sl.pin(torch)
     dref = idx.ref()
     log("[rank %d] slice: %d records (%d searched = %.1f %%, %.2f Gbases), %d planted SVs genome-wide, generated in %.1fs" %
         (rank, sl.n, sl.ns, 100.0 * sl.ns / sl.n, sl.bases / 1e9, len(sl.cat["gpos"]), time.time() - t0))

@@ -24,18 +24,27 @@ struct ClRaw {               // one raw cluster = the extended SFSs under one (l
   std::vector<ClExtSfs> sfs;
 };
 
-// `per_aln[k]` = merged extended SFSs of the k-th accepted read (accepted = carries SFSs, in BAM order).  The
+// ext_of[sfs_offs[a] .. + n_ext[k]) = merged extended SFSs of the k-th accepted read (alignment a = accepted[k]; accepted =
+// carries SFSs, in BAM order).  The
 // reference deals accepted reads round robin to `threads` slots (clusterer.cpp:109-133) and concatenates the slots
 // (:21-25); then std::sort by (chrom name, rs) -- stable here, the reference's tie order is unspecified -- and
 // cluster_by_proximity (:405-475).  `rank_of_tid` orders the chromosome NAMES (SFS::operator<, sfs.hpp:64-72).
-inline void cl_cluster_by_proximity(const std::vector<std::vector<ClExtSfs>>& per_aln, const int32_t* tid_of_aln,
-                                    const int32_t* rank_of_tid, int threads, std::vector<ClRaw>& out,
+inline void cl_cluster_by_proximity(const int32_t* accepted, int n_acc, const int32_t* n_ext, const ClExt* ext_of, const int64_t* sfs_offs,
+                                    const int32_t* tid_of_aln, const int32_t* rank_of_tid, int threads, std::vector<ClRaw>& out,
                                     int64_t& n_extended, int& max_ext_len, int& dist) {
   const size_t T = (size_t)std::max(1, threads);
   std::vector<ClExtSfs> ext;
+  {
+    size_t tot = 0;
+    for (int i = 0; i < n_acc; ++i) tot += (size_t)n_ext[i];
+    ext.reserve(tot);
+  }
   for (size_t t = 0; t < T; ++t)
-    for (size_t k = t; k < per_aln.size(); k += T)
-      for (const ClExtSfs& s : per_aln[k]) ext.push_back(s);
+    for (size_t k = t; k < (size_t)n_acc; k += T) {
+      const int a = accepted[k];
+      const ClExt* e = ext_of + sfs_offs[a];
+      for (int x = 0; x < n_ext[k]; ++x) ext.push_back(ClExtSfs{a, e[x].rs, e[x].re, e[x].qs, e[x].qe});
+    }
   n_extended = (int64_t)ext.size();
   max_ext_len = 0; dist = 0;
   out.clear();
@@ -119,14 +128,8 @@ struct ClPlan {
 inline void cl_plan_fill(const int32_t* accepted, int n_acc, const int32_t* n_ext, const ClExt* ext, const int64_t* sfs_offs,
                          const int32_t* tid, const int32_t* pos, const int32_t* endp, int64_t n_aln, const int32_t* rank_of_tid,
                          int threads, int min_cluster_weight, ClPlan& P) {
-  std::vector<std::vector<ClExtSfs>> per_aln((size_t)n_acc);
-  for (int i = 0; i < n_acc; ++i) {
-    const int a = accepted[i];
-    const ClExt* e = ext + sfs_offs[a];
-    for (int k = 0; k < n_ext[i]; ++k) per_aln[(size_t)i].push_back(ClExtSfs{a, e[k].rs, e[k].re, e[k].qs, e[k].qe});
-  }
   std::vector<ClRaw> raw;
-  cl_cluster_by_proximity(per_aln, tid, rank_of_tid, threads, raw, P.n_extended, P.max_ext_len, P.dist);
+  cl_cluster_by_proximity(accepted, n_acc, n_ext, ext, sfs_offs, tid, rank_of_tid, threads, raw, P.n_extended, P.max_ext_len, P.dist);
   // candidate alignments of a cluster: [lo, hi) in BAM order, through the prefix maximum of the end positions
   // (the in-memory stand-in for the .bai query of clusterer.cpp:485-492)
   std::vector<int32_t> pmax((size_t)n_aln);
