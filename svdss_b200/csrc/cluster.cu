@@ -26,11 +26,18 @@ struct ClRefDev {
   int64_t n_contigs;
 };
 
+// bam_endpos of every record, and the longest reference span of any (the host's region queries need only that)
 __global__ void k_cl_endpos(const int64_t* __restrict__ cigar_offs, const uint32_t* __restrict__ cigar, const int32_t* __restrict__ pos,
-                            int64_t n, int32_t* __restrict__ endp) {
+                            int64_t n, int32_t* __restrict__ endp, unsigned* __restrict__ max_span) {
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n) return;
-  endp[a] = cl_endpos(cigar + cigar_offs[a], (int)(cigar_offs[a + 1] - cigar_offs[a]), pos[a]);
+  int span = 0;
+  if (a < n) {
+    const int e = cl_endpos(cigar + cigar_offs[a], (int)(cigar_offs[a + 1] - cigar_offs[a]), pos[a]);
+    endp[a] = e;
+    span = e - pos[a];
+  }
+  span = __reduce_max_sync(0xffffffffu, span);
+  if ((threadIdx.x & 31) == 0 && span > 0) atomicMax(max_span, (unsigned)span);
 }
 
 // one thread per accepted read (a read that carries SFSs)
@@ -201,7 +208,7 @@ extern "C" int svb_cluster_batch(const svb_alns_t* A, const svb_ref_t* R, int th
   if (clipped) { CCHECK(D.alloc(&d_clip, (size_t)n * 4)); CCHECK(cudaMemsetAsync(d_clip, 0, (size_t)n * 16, st)); }
   const int n_acc = (int)accepted.size();
   CCHECK(cudaEventRecord(D.ev[1], st));
-  k_cl_endpos<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_coff, d_cig, d_pos, n, d_endp);
+  k_cl_endpos<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_coff, d_cig, d_pos, n, d_endp, d_cnt + 5);
   ClRefDev rd{d_ref, d_rstart, d_rlen, R->n_contigs};
   k_cl_extend<<<(unsigned)((n_acc + 63) / 64), 64, 0, st>>>(d_acc, n_acc, d_tid, d_pos, d_endp, d_coff, d_cig, d_soff, d_qs, d_len, rd, flank, ksize,
                                                            clipped, d_ext, d_next, d_cnt, d_clip);
@@ -209,10 +216,11 @@ extern "C" int svb_cluster_batch(const svb_alns_t* A, const svb_ref_t* R, int th
   CCHECK(cudaEventRecord(D.ev[2], st));
   out->launches = 2;
   std::vector<ClExt> h_ext((size_t)n_sfs);
-  std::vector<int32_t> h_next((size_t)n_acc), h_endp((size_t)n);
+  std::vector<int32_t> h_next((size_t)n_acc);
+  unsigned h_span = 0;
   CCHECK(cudaMemcpyAsync(h_ext.data(), d_ext, (size_t)n_sfs * sizeof(ClExt), cudaMemcpyDeviceToHost, st));
   CCHECK(cudaMemcpyAsync(h_next.data(), d_next, (size_t)n_acc * 4, cudaMemcpyDeviceToHost, st));
-  CCHECK(cudaMemcpyAsync(h_endp.data(), d_endp, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CCHECK(cudaMemcpyAsync(&h_span, d_cnt + 5, 4, cudaMemcpyDeviceToHost, st));
   if (clipped) {
     out->clip = host_alloc<int32_t>((size_t)n * 4);
     if (!out->clip) { set_error("out of host memory"); return SVB_ENOMEM; }
@@ -222,11 +230,11 @@ extern "C" int svb_cluster_batch(const svb_alns_t* A, const svb_ref_t* R, int th
   float ms = 0.f, kms = 0.f;
   cudaEventElapsedTime(&ms, D.ev[1], D.ev[2]);
   kms += ms;
-  out->d2h_bytes = n_sfs * (int64_t)sizeof(ClExt) + n_acc * 4 + n * 4 + (clipped ? n * 16 : 0);
+  out->d2h_bytes = n_sfs * (int64_t)sizeof(ClExt) + n_acc * 4 + 4 + (clipped ? n * 16 : 0);
   // ---- cluster_by_proximity on the host
   const auto h0 = std::chrono::steady_clock::now();
   ClPlan P;
-  cl_plan_fill(accepted.data(), n_acc, h_next.data(), h_ext.data(), A->sfs_offs, A->tid, A->pos, h_endp.data(), n, R->name_rank, threads,
+  cl_plan_fill(accepted.data(), n_acc, h_next.data(), h_ext.data(), A->sfs_offs, A->tid, A->pos, (int)h_span, n, R->name_rank, threads,
                min_cluster_weight, P);
   const std::vector<int32_t>&f_cluster = P.f_cluster, &f_min_s = P.f_min_s, &f_max_e = P.f_max_e, &f_lo = P.f_lo, &f_hi = P.f_hi, &f_members = P.f_members;
   const std::vector<int64_t>&f_moff = P.f_moff, &f_rvoff = P.f_rvoff;

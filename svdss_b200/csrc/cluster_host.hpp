@@ -126,25 +126,13 @@ struct ClPlan {
 
 // ext[sfs_offs[a] .. + n_ext[i]) = merged extended SFSs of accepted read i (alignment a = accepted[i])
 inline void cl_plan_fill(const int32_t* accepted, int n_acc, const int32_t* n_ext, const ClExt* ext, const int64_t* sfs_offs,
-                         const int32_t* tid, const int32_t* pos, const int32_t* endp, int64_t n_aln, const int32_t* rank_of_tid,
+                         const int32_t* tid, const int32_t* pos, int max_span, int64_t n_aln, const int32_t* rank_of_tid,
                          int threads, int min_cluster_weight, ClPlan& P) {
   std::vector<ClRaw> raw;
   cl_cluster_by_proximity(accepted, n_acc, n_ext, ext, sfs_offs, tid, rank_of_tid, threads, raw, P.n_extended, P.max_ext_len, P.dist);
-  // candidate alignments of a cluster: [lo, hi) in BAM order, through the prefix maximum of the end positions
-  // (the in-memory stand-in for the .bai query of clusterer.cpp:485-492)
-  std::vector<int32_t> pmax((size_t)n_aln);
-  std::vector<int64_t> tid_lo, tid_hi;
-  int64_t ntid = 0;
-  for (int64_t a = 0; a < n_aln; ++a) ntid = std::max<int64_t>(ntid, (int64_t)tid[a] + 1);
-  tid_lo.assign((size_t)ntid, 0); tid_hi.assign((size_t)ntid, 0);
-  for (int64_t a = 0; a < n_aln; ++a) {
-    const int t = tid[a];
-    if (t < 0) continue;
-    const bool first = a == 0 || tid[a - 1] != t;
-    if (first) tid_lo[(size_t)t] = a;
-    tid_hi[(size_t)t] = a + 1;
-    pmax[(size_t)a] = first ? endp[a] : std::max(pmax[(size_t)a - 1], endp[a]);
-  }
+  // candidate alignments of a cluster: [lo, hi) in BAM order = the records of its chromosome with beg - max_span <= pos < end
+  // (the in-memory stand-in for the .bai query of clusterer.cpp:485-492; max_span = the longest reference span of any
+  // record, so nothing that overlaps is left out, and the fill stage tests every candidate's own end)
   P.desc.resize(raw.size());
   P.f_moff.assign(1, 0); P.f_rvoff.assign(1, 0);
   for (size_t c = 0; c < raw.size(); ++c) {
@@ -152,12 +140,16 @@ inline void cl_plan_fill(const int32_t* accepted, int n_acc, const int32_t* n_ex
     const ClDesc& d = P.desc[c];
     if (d.n_reads < min_cluster_weight) { ++P.small_clusters; continue; }
     int64_t lo = 0, hi = 0;
-    if (d.tid >= 0 && (size_t)d.tid < tid_hi.size() && tid_hi[(size_t)d.tid] > tid_lo[(size_t)d.tid]) {
-      const int64_t t0 = tid_lo[(size_t)d.tid], t1 = tid_hi[(size_t)d.tid];
-      const int beg = std::max(0, d.min_s - 1), end = d.max_e;   // region "chrom:min_s-max_e", 1-based inclusive for htslib
-      lo = std::upper_bound(pmax.begin() + t0, pmax.begin() + t1, beg) - pmax.begin();
-      hi = std::lower_bound(pos + t0, pos + t1, end) - pos;
-      if (hi < lo) hi = lo;
+    {
+      const int32_t* t0p = std::lower_bound(tid, tid + n_aln, d.tid);
+      const int32_t* t1p = std::upper_bound(t0p, tid + n_aln, d.tid);
+      const int64_t t0 = t0p - tid, t1 = t1p - tid;
+      if (t1 > t0) {
+        const int beg = std::max(0, d.min_s - 1), end = d.max_e;   // region "chrom:min_s-max_e", 1-based inclusive for htslib
+        lo = std::lower_bound(pos + t0, pos + t1, beg - max_span) - pos;
+        hi = std::lower_bound(pos + t0, pos + t1, end) - pos;
+        if (hi < lo) hi = lo;
+      }
     }
     P.f_cluster.push_back((int32_t)c);
     P.f_min_s.push_back(d.min_s); P.f_max_e.push_back(d.max_e); P.f_lo.push_back((int32_t)lo); P.f_hi.push_back((int32_t)hi);

@@ -265,9 +265,8 @@ __device__ void poa_dp_rows_cta(const PoaParams& P, const PoaWs& W, const uint8_
 //  2 TBIN1  traceback: the first predecessor comes from in1[v], loaded next to beg[v], instead of through
 //           first_in -> efrom after the traceback word: two dependent loads per step, not four
 //  4 PARN   the two per-read loops over all nodes (remain[], re-rank) are done by the whole warp
-//  8 PREF   graph update: before lane 0 walks a window of 32 alignment ops, all lanes touch the node and
-//           edge fields it is going to read (prefetch.global.L1), so its dependent loads hit L1
-// 16 TBPF   traceback in windows of 32 steps whose traceback words all lanes prefetch along the predicted path
+//  8, 16   (round 1: prefetching windows for the graph update and the traceback; measured without effect in round 2 --
+//           profiles/r02a_variants_sweep.txt -- and replaced by UPDPAR / TBSPEC below; the bits are ignored now)
 // 32 LEAN   DP rows with fewer dependent shuffles: the row maximum and its first / last column through REDUX
 //           (__reduce_max_sync / __reduce_min_sync, 3 instructions instead of 15 shuffle steps), the two
 //           "gap was extended" comparisons handed to the next lane as two bits instead of their four operands
@@ -285,16 +284,9 @@ __device__ void poa_dp_rows_cta(const PoaParams& P, const PoaWs& W, const uint8_
 //            column groups are independent instruction streams (the groups meet only in the carries), so a warp that
 //            runs alone on its scheduler -- the tail of a batch is one big cluster, 30 reads x 5 000 rows of 121 columns
 //            -- no longer pays one dependent-issue latency per instruction
-constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_PREF = 8, POA_V_TBPF = 16, POA_V_LEAN = 32, POA_V_ROWS = 64,
+constexpr int POA_V_SMEM = 1, POA_V_TBIN1 = 2, POA_V_PARN = 4, POA_V_LEAN = 32, POA_V_ROWS = 64,
               POA_V_TBSPEC = 128, POA_V_UPDPAR = 256, POA_V_ILP2 = 512, POA_V_ILP4 = 1024;
 
-__device__ __forceinline__ void poa_prefetch(const void* p) {
-#ifdef __CUDA_ARCH__
-  asm volatile("{ .reg .u64 a; cvta.to.global.u64 a, %0; prefetch.global.L1 [a]; }" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
 
 // G = lanes per cluster (32, 16 or 8; SVB_POA_GROUP on the host).  With G < 32 a warp carries 32/G clusters,
 // each on its own group of lanes with its own control flow (group-masked shuffles and __syncwarp): the kernel
@@ -306,12 +298,11 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
   extern __shared__ int poa_smem[];
   static_assert(NW == 1 || (NW == 4 && G == 32), "one warp per cluster, or the four warps of a CTA");
   static_assert(NW == 1 || ((V & (POA_V_SMEM | POA_V_ROWS | POA_V_PARN)) == (POA_V_SMEM | POA_V_ROWS | POA_V_PARN)), "the CTA rows need SMEM, ROWS and PARN");
-  constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0, PREF = (V & POA_V_PREF) != 0,
-                 TBPF = (V & POA_V_TBPF) != 0, LEAN = (V & POA_V_LEAN) != 0, ROWS = (V & POA_V_ROWS) != 0, TBSPEC = (V & POA_V_TBSPEC) != 0,
+  constexpr bool SMEM = (V & POA_V_SMEM) != 0, TBIN1 = (V & POA_V_TBIN1) != 0, PARN = (V & POA_V_PARN) != 0,
+                 LEAN = (V & POA_V_LEAN) != 0, ROWS = (V & POA_V_ROWS) != 0, TBSPEC = (V & POA_V_TBSPEC) != 0,
                  UPDPAR = (V & POA_V_UPDPAR) != 0;
   constexpr int S = (V & POA_V_ILP4) ? 4 : (V & POA_V_ILP2) ? 2 : 0;   // column groups per chunk of the ILP row (0 = the one-group loop)
   static_assert(!ROWS || PARN, "ROWS builds its records in the warp-parallel setup");
-  static_assert(!(TBSPEC && TBPF) && !(UPDPAR && PREF), "TBSPEC / UPDPAR replace TBPF / PREF");
   static_assert(G == 32 || G == 16 || G == 8, "group width");
   const int lane = threadIdx.x & (G - 1);
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
@@ -804,7 +795,7 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
           if (val > best) { best = val; best_p = p; }
         }
         t_v = best_p; t_j = ql; t_state = 0;
-        if (!TBPF && !TBSPEC) while (t_v != 0 || t_j > 0) tb_step();
+        if (!TBSPEC) while (t_v != 0 || t_j > 0) tb_step();
       }
       if (TBSPEC) {
         for (;;) {
@@ -845,34 +836,10 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
           __syncwarp(gmask);
         }
       }
-      if (TBPF) {
-        // The traceback words were written rows ago and have left the caches: every step of the walk is a DRAM
-        // round trip.  The path mostly runs down a chain of consecutive node ids one column per row, so before
-        // lane 0 walks 32 steps all lanes prefetch the words (and predecessor fields) the path would touch 32..63
-        // steps ahead if it stayed on that diagonal (and 0..31 ahead for the first window).  A wrong guess costs
-        // a wasted prefetch, nothing else.
-        bool first = true;
-        for (;;) {
-          const int cv = __shfl_sync(gmask, t_v, 0, G), cj = __shfl_sync(gmask, t_j, 0, G);
-          if (cv == 0 && cj <= 0) break;
-          for (int d = first ? lane : G + lane; d < 2 * G; d += G) {
-            const int pv = cv - d, pj = cj - d;
-            if (pv >= 2 && pv < N && pj >= 0) {
-              const int ix = pj - W.beg[pv];
-              if (ix >= 0 && ix < Wc) poa_prefetch(&W.TB[(int64_t)pv * Wc + ix]);
-              poa_prefetch(&W.in1[pv]);
-            }
-          }
-          first = false;
-          __syncwarp(gmask);
-          if (lane == 0) for (int st = 0; st < G && (t_v != 0 || t_j > 0); ++st) tb_step();
-          __syncwarp(gmask);
-        }
-      }
       if (lane == 0) {
         PHASE(t_tb);
         nop_b = nop;
-        if (!PREF && !UPDPAR) {
+        if (!UPDPAR) {
           for (int k = nop - 1; k >= 0; --k) if (!add_op(k)) break;
           finish_update();
         }
@@ -916,25 +883,6 @@ __global__ void __launch_bounds__(128, MB) k_poa(const PoaParams P) {
           __syncwarp(gmask);
           if (stop) break;
           k0 -= m2 + (m2 < G ? 1 : 0);
-        }
-        if (lane == 0) finish_update();
-      }
-      if (PREF) {
-        // the same update in windows of 32 ops: first all lanes touch what lane 0 is about to read
-        const int nop_all = __shfl_sync(gmask, nop_b, 0, G);
-        for (int k0 = nop_all - 1; k0 >= 0; k0 -= G) {
-          const int kk = k0 - lane;
-          if (kk >= 0) {
-            const int v = W.op_node[kk];
-            if (v >= 0) {
-              poa_prefetch(&W.rank[v]); poa_prefetch(&W.ring[v]); poa_prefetch(&W.base[v]); poa_prefetch(&W.last_out[v]);
-              const int e = W.first_out[v];
-              if (e >= 0) { poa_prefetch(&W.eto[e]); poa_prefetch(&W.ew[e]); poa_prefetch(&W.enout[e]); }
-            }
-          }
-          __syncwarp(gmask);
-          if (lane == 0) for (int k = k0; k > k0 - G && k >= 0; --k) if (!add_op(k)) break;
-          __syncwarp(gmask);
         }
         if (lane == 0) finish_update();
       }

@@ -2,6 +2,8 @@
 // half of cluster_host.hpp, compiled as they are, with the two kernels of cluster.cu replaced by plain loops over the
 // same functions.  Same signature and output as svb_cluster_batch (reference in HOST memory), so one Python wrapper
 // serves both and the CPU suite can hold the GPU path's logic against tests/cluster_model.py without a GPU.
+#include <chrono>
+#include <cstdio>
 #include <vector>
 
 #include "../../svdss_b200/csrc/cluster_host.hpp"
@@ -19,7 +21,11 @@ extern "C" int emul_cluster_batch(const svb_alns_t* A, const svb_ref_t* R, int t
   std::vector<ClExt> ext((size_t)n_sfs + 1);
   unsigned cnt[8] = {0};
   if (clipped) out->clip = cl_host_alloc<int32_t>((size_t)n * 4);
-  for (int64_t a = 0; a < n; ++a) endp[(size_t)a] = cl_endpos(A->cigar + A->cigar_offs[a], (int)(A->cigar_offs[a + 1] - A->cigar_offs[a]), A->pos[a]);
+  int max_span = 0;
+  for (int64_t a = 0; a < n; ++a) {
+    endp[(size_t)a] = cl_endpos(A->cigar + A->cigar_offs[a], (int)(A->cigar_offs[a + 1] - A->cigar_offs[a]), A->pos[a]);
+    if (endp[(size_t)a] - A->pos[a] > max_span) max_span = endp[(size_t)a] - A->pos[a];
+  }
   for (size_t i = 0; i < accepted.size(); ++i) {      // k_cl_extend
     const int a = accepted[i], t = A->tid[a];
     int cl4[4] = {0, 0, 0, 0};
@@ -35,9 +41,11 @@ extern "C" int emul_cluster_batch(const svb_alns_t* A, const svb_ref_t* R, int t
     n_ext[i] = m;
     if (clipped) for (int k = 0; k < 4; ++k) out->clip[(int64_t)a * 4 + k] = cl4[k];
   }
+  const auto t0_ = std::chrono::steady_clock::now();
   ClPlan P;
-  cl_plan_fill(accepted.data(), (int)accepted.size(), n_ext.data(), ext.data(), A->sfs_offs, A->tid, A->pos, endp.data(), n, R->name_rank,
+  cl_plan_fill(accepted.data(), (int)accepted.size(), n_ext.data(), ext.data(), A->sfs_offs, A->tid, A->pos, max_span, n, R->name_rank,
                threads, min_cluster_weight, P);
+  if (getenv("SVB_EMUL_TIMING")) fprintf(stderr, "[cluster_emul] cl_plan_fill %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_).count());
   const int nf = (int)P.f_cluster.size();
   std::vector<int32_t> sa(P.f_members.size() + 1), sq(P.f_members.size() + 1), se(P.f_members.size() + 1), sh(P.f_members.size() + 1);
   std::vector<int32_t> nsub((size_t)nf + 1), nrv((size_t)nf + 1), cov((size_t)nf * 3 + 3);

@@ -14,10 +14,10 @@ static void body(void* a) {
   Launch* l = static_cast<Launch*>(a);
   switch (l->group * 100 + l->variant) {
 #define CASE(V) case 3200 + V: svb::k_poa<V, 32>(l->P); break;
-    CASE(0) CASE(1) CASE(2) CASE(4) CASE(7) CASE(8) CASE(16) CASE(31) CASE(32) CASE(63) CASE(68) CASE(71) CASE(135) CASE(199) CASE(263) CASE(455) CASE(487) CASE(967) CASE(1479) CASE(512) CASE(1024)
+    CASE(0) CASE(1) CASE(2) CASE(4) CASE(7) CASE(32) CASE(39) CASE(68) CASE(71) CASE(135) CASE(199) CASE(263) CASE(455) CASE(487) CASE(967) CASE(1479) CASE(512) CASE(1024)
 #undef CASE
 #define CASE(V) case 1600 + V: svb::k_poa<V, 16>(l->P); break; case 800 + V: svb::k_poa<V, 8>(l->P); break;
-    CASE(0) CASE(7) CASE(31) CASE(63) CASE(455) CASE(487)
+    CASE(0) CASE(7) CASE(39) CASE(455) CASE(487)
 #undef CASE
     default: fprintf(stderr, "poa_emul: variant %d / group %d not built\n", l->variant, l->group); abort();
   }
