@@ -505,6 +505,26 @@ int main(int argc, char** argv) {
     printf("%.6f\n", fuzz_ratio(pos[0], pos[1]));
     return 0;
   }
+  if (mode == "_bamread") {   // measurement hook: what the BAM reader hands `search` per second (tools/bench_bamread.py), no GPU
+    if (pos.size() != 1) return EXIT_FAILURE;
+    BamReader bam(pos[0]);
+    if (!bam.ok()) return EXIT_FAILURE;
+    bam.want_alignment(true);
+    BamRecord r;
+    int st;
+    uint64_t n = 0, bases = 0, kept = 0;
+    vector<uint8_t> cat;
+    const double t0 = now_s();
+    while ((st = bam.next(r)) == 1) {
+      ++n; bases += (uint64_t)r.l_qseq;
+      if (!(r.has_xf && r.xf != 0)) { cat.insert(cat.end(), r.seq4.begin(), r.seq4.end()); ++kept; }   // what run_search keeps of a record
+      if (cat.size() > ((size_t)1 << 30)) cat.clear();
+    }
+    const double dt = now_s() - t0;
+    printf("{\"records\": %llu, \"kept\": %llu, \"bases\": %llu, \"seconds\": %.3f, \"records_per_s\": %.0f, \"Gbases_per_s\": %.3f}\n",
+           (unsigned long long)n, (unsigned long long)kept, (unsigned long long)bases, dt, n / dt, bases / dt / 1e9);
+    return st < 0 ? EXIT_FAILURE : EXIT_SUCCESS;
+  }
   if (mode == "_fmd") return run_fmd_hook(pos);
   if (mode == "_clipper") return run_clipper_hook(c);   // test hook: Clipper::call without the GPU stages (tests/test_clipper_cpu.py)
   if (mode == "index") rc = run_index(c, pos);

@@ -1,0 +1,57 @@
+"""What the shell's own BAM reader (host/io.hpp: parallel BGZF inflate one window ahead + in-place record parse) hands
+`SVDSS search` per second, without a GPU: writes a smoothed-shaped BAM of --records 15 kb reads (qualities 0xff as the
+Smoother writes them, XF tags, level-6 BGZF) and runs the `_bamread` hook of the shell on it.
+  python tools/bench_bamread.py [--records 20000]"""
+import argparse, json, os, subprocess, sys, tempfile, time, zlib, struct
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from svdss_b200 import build
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--records", type=int, default=20000)
+    a = ap.parse_args()
+    exe = build.build_host()
+    rng = np.random.default_rng(3)
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "s.bam")
+    text = "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chr1\tLN:400000000\n"
+    head = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", 1) + struct.pack("<i", 5) + b"chr1\0" + struct.pack("<i", 400000000)
+    out = open(path, "wb")
+    buf = bytearray(head)
+
+    def flush(final=False):
+        nonlocal buf
+        while len(buf) >= 0xff00 or (final and buf):
+            blk = bytes(buf[:0xff00]); del buf[:0xff00]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15); comp = c.compress(blk) + c.flush()
+            out.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp + struct.pack("<II", zlib.crc32(blk), len(blk)))
+    pos = 0
+    for i in range(a.records):
+        l = int(rng.integers(10000, 20000))
+        seq = rng.integers(0, 256, (l + 1) // 2, dtype=np.uint8)
+        seq = ((1 << (seq & 3)) | ((1 << ((seq >> 2) & 3)) << 4)).astype(np.uint8).tobytes()
+        qn = b"read/%d/ccs\0" % i
+        pos += int(rng.integers(1, 1000))
+        core = struct.pack("<iiBBHHHiiii", 0, pos, len(qn), 60, 4680, 1, 0, l, -1, -1, 0)
+        body = core + qn + struct.pack("<I", l << 4) + seq + b"\xff" * l + b"XFC" + bytes([0 if i % 9 == 0 else 2])
+        buf += struct.pack("<i", len(body)) + body
+        flush()
+    flush(True)
+    out.write(bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
+    out.close()
+    best = None
+    for _ in range(3):
+        r = subprocess.run([exe, "_bamread", path], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        if best is None or j["seconds"] < best["seconds"]:
+            best = j
+    best["file_bytes"] = os.path.getsize(path)
+    best["host_threads"] = len(os.sched_getaffinity(0))
+    print(json.dumps(best))
+
+
+if __name__ == "__main__":
+    main()
