@@ -462,6 +462,7 @@ def run_ours(args):
         "unit": "reads/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step,
+        "ms_per_step_cuda_events": ms_dev / args.steps,   # events on the launch stream around the same K steps (every call is synchronous at return: the two agree)
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": workload_config(args, world),

@@ -166,10 +166,15 @@ SVB_API int svb_unpack2_device(const uint8_t* packed, const int64_t* packed_offs
  * n_members members back to back (member m = comp[in_offs[m], in_offs[m+1])) and where their ISIZE bytes go
  * (out_host[out_offs[m], out_offs[m+1]), at most 64 KiB each); both offset arrays start at 0.  status_host (optional, one per member): 0 or
  * the reason a member did not inflate; any non-zero status makes the call return SVB_EIO after the copies.
- * kernel_ms (optional): device time of the inflate kernel.  Building block: host/io.hpp still inflates on the host. */
+ * kernel_ms (optional): device time of the inflate kernel.  host/io.hpp uses it with `--gpu-inflate`. */
 SVB_API int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_offs /* n_members+1 */,
                                     const int64_t* out_offs /* n_members+1 */, int64_t n_members, int device,
                                     uint8_t* out_host, int32_t* status_host, float* kernel_ms);
+
+/* Pinned host memory for a reader's windows (svb_bgzf_inflate_device copies at PCIe speed only from / to pinned
+ * buffers).  NULL when there is no device or the allocation fails. */
+SVB_API void* svb_host_alloc_pinned(size_t bytes);
+SVB_API void svb_host_free_pinned(void* p);
 
 /* Same search with the batch already resident in HBM (kernel-only measurement; multi-batch reuse). */
 SVB_API int svb_reads_upload(const uint8_t* nt6_concat, const int64_t* offs, int64_t n_reads,

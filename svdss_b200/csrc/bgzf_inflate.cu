@@ -4,8 +4,11 @@
 // (the reference: htslib bgzf_mt, ping_pong.cpp:249, clusterer.cpp:13) -- and hands over the raw-deflate payloads
 // back to back with their offsets and the offsets of their inflated bytes.  Round 1: a measured-later building
 // block with its own parity tests (tests/test_inflate_emul.py on the CPU, tests/test_gpu_zz_inflate.py on the GPU);
-// BgzfSource still inflates on the host.
+// Round 2: timed -- the kernel takes ~200 ms whatever the window holds up to ~75 k members (one 64 KiB member per
+// thread is a latency, not a throughput), i.e. 1.4 GB/s on a 256 MB window and 10.4 GB/s on a 2 GB one
+// (profiles/r02p_inflate.txt) -- and wired into BgzfSource as an opt-in (`--gpu-inflate`: half-gigabyte compressed windows).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -44,11 +47,12 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
   int rc = SVB_OK;
   auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == SVB_OK) { set_error("svb_bgzf_inflate_device: %s", cudaGetErrorString(e)); rc = SVB_ECUDA; } };
   fail(cudaStreamCreateWithFlags(&sq, cudaStreamNonBlocking));
-  fail(cudaMalloc((void**)&d_in, (size_t)in_total + 16));
-  fail(cudaMalloc((void**)&d_out, (size_t)out_total + 16));
-  fail(cudaMalloc((void**)&d_io, (size_t)(n_members + 1) * 8));
-  fail(cudaMalloc((void**)&d_oo, (size_t)(n_members + 1) * 8));
-  fail(cudaMalloc((void**)&d_st, (size_t)n_members * 4));
+  // window after window of a file: the buffers come from the stream-ordered pool (no cudaMalloc / cudaFree of GBs per window)
+  if (rc == SVB_OK) fail(pmalloc((void**)&d_in, (size_t)in_total + 16, sq));
+  if (rc == SVB_OK) fail(pmalloc((void**)&d_out, (size_t)out_total + 16, sq));
+  if (rc == SVB_OK) fail(pmalloc((void**)&d_io, (size_t)(n_members + 1) * 8, sq));
+  if (rc == SVB_OK) fail(pmalloc((void**)&d_oo, (size_t)(n_members + 1) * 8, sq));
+  if (rc == SVB_OK) fail(pmalloc((void**)&d_st, (size_t)n_members * 4, sq));
   fail(cudaEventCreate(&e0));
   fail(cudaEventCreate(&e1));
   if (rc == SVB_OK) {
@@ -57,9 +61,16 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
     fail(cudaMemcpyAsync(d_oo, out_offs, (size_t)(n_members + 1) * 8, cudaMemcpyHostToDevice, sq));
   }
   if (rc == SVB_OK) {
-    // one warp per CTA: members differ in length by an order of magnitude, small CTAs retire independently
+    // one warp per CTA: members differ in length by an order of magnitude, small CTAs retire independently.
+    // Members per warp: as few as still fill the warp slots of the device (lanes on different streams diverge)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int64_t slots = (int64_t)sms * 32;
+    if (const char* e = getenv("SVB_INFLATE_WARPS_PER_SM")) { const int v = atoi(e); if (v > 0) slots = (int64_t)sms * v; }
+    int mpw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (n_members + slots - 1) / slots));
+    if (const char* e = getenv("SVB_INFLATE_MPW")) { const int v = atoi(e); if (v >= 1 && v <= 32) mpw = v; }
     fail(cudaEventRecord(e0, sq));
-    k_bgzf_inflate<<<(unsigned)((n_members + 31) / 32), 32, 0, sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
+    k_bgzf_inflate<<<(unsigned)((n_members + mpw - 1) / mpw), 32, 0, sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st, mpw);
     fail(cudaGetLastError());
     fail(cudaEventRecord(e1, sq));
     if (out_total) fail(cudaMemcpyAsync(out_host, d_out, (size_t)out_total, cudaMemcpyDeviceToHost, sq));
@@ -67,8 +78,7 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
     fail(cudaStreamSynchronize(sq));
     if (rc == SVB_OK && kernel_ms) fail(cudaEventElapsedTime(kernel_ms, e0, e1));
   }
-  if (sq) cudaStreamSynchronize(sq);
-  cudaFree(d_in); cudaFree(d_out); cudaFree(d_io); cudaFree(d_oo); cudaFree(d_st);
+  if (sq) { pfree(d_in, sq); pfree(d_out, sq); pfree(d_io, sq); pfree(d_oo, sq); pfree(d_st, sq); cudaStreamSynchronize(sq); }
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
   if (sq) cudaStreamDestroy(sq);
@@ -77,4 +87,15 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
   for (int64_t m = 0; m < n_members; ++m)
     if (st[(size_t)m] != 0) { set_error("BGZF member %lld does not inflate (code %d): truncated or corrupt file", (long long)m, st[(size_t)m]); return SVB_EIO; }
   return SVB_OK;
+}
+
+// Pinned host memory for the windows a reader hands to / gets back from svb_bgzf_inflate_device (a pageable
+// destination would halve the copy rate).  NULL without a device or when the allocation fails.
+extern "C" void* svb_host_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void svb_host_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
 }

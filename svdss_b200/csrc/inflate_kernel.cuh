@@ -5,7 +5,7 @@
 // build: 16 counts + the symbols in code order, 1.3 KB of local memory per thread), output written straight to
 // its place in the window, back-references read from there (a member never refers across its own start).
 // Round-1 state: a building block, checked on the CPU through tests/emul against zlib and on the GPU by
-// svb_bgzf_inflate_device; not wired into host/io.hpp's BgzfSource yet.  Free of host
+// svb_bgzf_inflate_device; round 2: BgzfSource uses it with `--gpu-inflate` (host/io.hpp).  Free of host
 // code so that tests/emul compiles it for the CPU.
 //
 // RFC 1951 restated: a stream is a sequence of blocks, each with a 3-bit header (BFINAL, BTYPE).  BTYPE 0:
@@ -184,11 +184,15 @@ __device__ __forceinline__ int inflate_member(const uint8_t* __restrict__ in, in
   return o == out_len ? INF_OK : INF_ESIZE;
 }
 
-// member m: deflate payload comp[in_offs[m], in_offs[m+1]) -> out[out_offs[m], out_offs[m+1]); status[m] = INF_*
+// member m: deflate payload comp[in_offs[m], in_offs[m+1]) -> out[out_offs[m], out_offs[m+1]); status[m] = INF_*.
+// One warp per CTA, `mpw` (1..32) of its lanes take a member each: the lanes of a warp walk different streams and
+// diverge, so a window with fewer members than the machine has warp slots spreads over more warps instead
+// (svb_bgzf_inflate_device picks mpw).
 __global__ void __launch_bounds__(32) k_bgzf_inflate(const uint8_t* __restrict__ comp, const int64_t* __restrict__ in_offs,
                                                      const int64_t* __restrict__ out_offs, int64_t n_members,
-                                                     uint8_t* __restrict__ out, int32_t* __restrict__ status) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                     uint8_t* __restrict__ out, int32_t* __restrict__ status, int mpw) {
+  if ((int)threadIdx.x >= mpw) return;
+  const int64_t m = (int64_t)blockIdx.x * mpw + threadIdx.x;
   if (m >= n_members) return;
   const int64_t a = in_offs[m], b = in_offs[m + 1], oa = out_offs[m], ob = out_offs[m + 1];
   status[m] = (ob == oa && b == a) ? INF_OK : inflate_member(comp + a, b - a, out + oa, ob - oa);

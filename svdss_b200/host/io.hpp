@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include "../../include/svdss_b200.h"
+
 namespace svdss {
 
 // ping_pong.hpp:46-52 seq_nt6_table ($=0 A=1 C=2 G=3 T=4 other=5); rb3_char2nt6 is the same map
@@ -63,14 +65,57 @@ class GzSource {
   gzFile f_;
 };
 
+// Where BgzfSource inflates: -1 = host threads (zlib), d >= 0 = device d through svb_bgzf_inflate_device
+// (`--gpu-inflate` / SVB_BGZF_GPU=<device> in the CLI).  Process-wide; set before the readers are opened.
+inline int& bgzf_gpu_device() { static int d = -1; return d; }
+
+// window buffer of BgzfSource: like a byte vector without the zero fill, in pinned host memory when the
+// device inflates (the copies run at PCIe speed only from / to pinned buffers)
+class ByteBuf {
+ public:
+  ByteBuf() = default;
+  ByteBuf(const ByteBuf&) = delete;
+  ByteBuf& operator=(const ByteBuf&) = delete;
+  ~ByteBuf() { release(p_, pinned_); }
+  void pin(bool on) { if (on != want_pin_ && cap_ == 0) want_pin_ = on; }
+  uint8_t* data() { return p_; }
+  const uint8_t* data() const { return p_; }
+  size_t size() const { return n_; }
+  void clear() { n_ = 0; }
+  // keeps the first min(size, n) bytes; false when memory runs out
+  bool resize(size_t n) {
+    if (n > cap_) {
+      const size_t cap = std::max(n, cap_ + cap_ / 2);
+      bool pinned = want_pin_;
+      uint8_t* q = pinned ? static_cast<uint8_t*>(svb_host_alloc_pinned(cap)) : nullptr;
+      if (!q) { pinned = false; q = static_cast<uint8_t*>(malloc(cap)); }   // unpinned still works, the copies are slower
+      if (!q) return false;
+      if (n_) memcpy(q, p_, n_);
+      release(p_, pinned_);
+      p_ = q; cap_ = cap; pinned_ = pinned;
+    }
+    n_ = n;
+    return true;
+  }
+  void swap(ByteBuf& o) { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(cap_, o.cap_); std::swap(pinned_, o.pinned_); std::swap(want_pin_, o.want_pin_); }
+ private:
+  static void release(uint8_t* p, bool pinned) { if (!p) return; if (pinned) svb_host_free_pinned(p); else free(p); }
+  uint8_t* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+  bool pinned_ = false, want_pin_ = false;
+};
+
 // BGZF byte source with parallel inflate: BGZF members (<= 64 KiB each, size in the BC extra field)
 // are independent deflate streams, so a window of them is read sequentially and inflated by all
 // host threads at once -- the reference does the same through htslib's bgzf_mt(.., 8, ..)
-// (ping_pong.cpp:249, clusterer.cpp:13).  Files that are not BGZF go through plain zlib.
+// (ping_pong.cpp:249, clusterer.cpp:13).  With bgzf_gpu_device() >= 0 the window goes to the device instead:
+// half a gigabyte of members per launch (one thread per member pays only with tens of thousands of members,
+// profiles/r02p_inflate.txt), pinned window buffers.  Files that are not BGZF go through plain zlib.
 class BgzfSource {
  public:
-  explicit BgzfSource(const std::string& path) : f_(fopen(path.c_str(), "rb")) {
+  explicit BgzfSource(const std::string& path) : f_(fopen(path.c_str(), "rb")), gpu_(bgzf_gpu_device()) {
     if (!f_) return;
+    if (gpu_ >= 0) { out_.pin(true); in_next_.pin(true); out_next_.pin(true); }
     uint8_t h[18];
     const size_t got = fread(h, 1, 18, f_);
     bgzf_ = got == 18 && h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
@@ -109,13 +154,13 @@ class BgzfSource {
   }
   // one window: up to 64 MiB of BGZF members read sequentially, inflated in parallel.  false at EOF
   // (no payload left) or on a malformed file.
-  bool fill(std::vector<uint8_t>& in, std::vector<uint8_t>& out) {
+  bool fill(ByteBuf& in, ByteBuf& out) {
     struct Blk { size_t in_off, in_len, out_off, out_len; };
     for (;;) {
       std::vector<Blk> blks;
       in.clear();
       size_t out_total = 0;
-      size_t window = (size_t)64 << 20;         // compressed bytes per window
+      size_t window = gpu_ >= 0 ? (size_t)512 << 20 : (size_t)64 << 20;         // compressed bytes per window
       if (const char* e = getenv("SVB_BGZF_WINDOW")) { const long long v = atoll(e); if (v > 0) window = (size_t)v; }   // tests: force records across windows
       while (in.size() < window) {
         uint8_t h[18];
@@ -138,7 +183,7 @@ class BgzfSource {
         if (total < head + 8) return false;
         const size_t body = total - head;       // deflate data + CRC32 + ISIZE
         const size_t at = in.size();
-        in.resize(at + body);
+        if (!in.resize(at + body)) return false;
         if (fread(in.data() + at, 1, body, f_) != body) return false;
         uint32_t isize;
         memcpy(&isize, in.data() + at + body - 4, 4);
@@ -147,7 +192,20 @@ class BgzfSource {
         out_total += isize;
       }
       if (blks.empty()) return false;
-      out.resize(out_total);
+      if (!out.resize(out_total)) return false;
+      if (gpu_ >= 0) {
+        // the members as they lie in the window, CRC32 + ISIZE still behind every deflate stream (the kernel stops
+        // at the final block of a stream and checks the payload size)
+        std::vector<int64_t> io(blks.size() + 1), oo(blks.size() + 1);
+        for (size_t i = 0; i < blks.size(); ++i) { io[i] = (int64_t)blks[i].in_off; oo[i] = (int64_t)blks[i].out_off; }
+        io[blks.size()] = (int64_t)in.size(); oo[blks.size()] = (int64_t)out_total;
+        if (svb_bgzf_inflate_device(in.data(), io.data(), oo.data(), (int64_t)blks.size(), gpu_, out.data(), nullptr, nullptr) != SVB_OK) {
+          fprintf(stderr, "[svdss] BGZF inflate on device %d: %s\n", gpu_, svb_last_error());
+          return false;
+        }
+        if (out_total > 0) return true;
+        continue;
+      }
       int bad = 0;
 #pragma omp parallel for schedule(dynamic, 8) reduction(+ : bad)
       for (long long i = 0; i < (long long)blks.size(); ++i) {
@@ -170,7 +228,8 @@ class BgzfSource {
   FILE* f_ = nullptr;
   bool bgzf_ = false;
   std::unique_ptr<GzSource> plain_;
-  std::vector<uint8_t> out_, in_next_, out_next_;
+  int gpu_ = -1;
+  ByteBuf out_, in_next_, out_next_;
   std::future<bool> pending_;
   size_t pos_ = 0;
 };

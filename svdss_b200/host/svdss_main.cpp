@@ -68,6 +68,7 @@ struct Config {
   float min_ratio = 0.97f, accp = 0.98f;
   bool noht = false, clipped = false, cluster_only = false, line_input = false;
   int threads = 4, bsize = 10000, omax = 100000, device = 0;
+  bool gpu_inflate = false;
   bool assemble = true, putative = true, verbose = false, help = false, version = false;
   int overlap = -1;  // config.hpp:82: never settable from the command line
 };
@@ -120,6 +121,7 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
     else if (a == "--append") { string unused; ok = val(unused); }   // registered by the reference (config.cpp:35), read nowhere
     else if (a == "--binary") {}                                       // config.cpp:51,96: parsed, never used
     else if (a == "--device") ok = ival(c.device);
+    else if (a == "--gpu-inflate") c.gpu_inflate = true;               // BGZF windows inflated on the device (io.hpp)
     else if (a == "-o") ok = val(c.out);
     else if (a == "-d") {}
     else if (a == "--noassemble") c.assemble = false;
@@ -132,6 +134,8 @@ static bool parse_common(int argc, char** argv, Config& c, vector<string>& posit
     if (!ok) { logmsg("critical", "option " + a + " needs a value"); return false; }
   }
   if (c.threads < 1) c.threads = 1;
+  if (const char* e = getenv("SVB_BGZF_GPU")) c.gpu_inflate = c.gpu_inflate || atoi(e) != 0;
+  if (c.gpu_inflate) bgzf_gpu_device() = c.device;
   c.bsize = (c.bsize / c.threads) * c.threads;  // config.cpp:106
   if (c.bsize < c.threads) c.bsize = c.threads;
   return true;
@@ -512,17 +516,18 @@ int main(int argc, char** argv) {
     bam.want_alignment(true);
     BamRecord r;
     int st;
-    uint64_t n = 0, bases = 0, kept = 0;
+    uint64_t n = 0, bases = 0, kept = 0, seq_sum = 0;
     vector<uint8_t> cat;
     const double t0 = now_s();
     while ((st = bam.next(r)) == 1) {
       ++n; bases += (uint64_t)r.l_qseq;
+      for (size_t k = 0; k < r.seq4.size(); k += 97) seq_sum = seq_sum * 31 + r.seq4[k];   // a checksum the host and the device inflate must agree on
       if (!(r.has_xf && r.xf != 0)) { cat.insert(cat.end(), r.seq4.begin(), r.seq4.end()); ++kept; }   // what run_search keeps of a record
       if (cat.size() > ((size_t)1 << 30)) cat.clear();
     }
     const double dt = now_s() - t0;
-    printf("{\"records\": %llu, \"kept\": %llu, \"bases\": %llu, \"seconds\": %.3f, \"records_per_s\": %.0f, \"Gbases_per_s\": %.3f}\n",
-           (unsigned long long)n, (unsigned long long)kept, (unsigned long long)bases, dt, n / dt, bases / dt / 1e9);
+    printf("{\"records\": %llu, \"kept\": %llu, \"bases\": %llu, \"seq_sum\": %llu, \"seconds\": %.3f, \"records_per_s\": %.0f, \"Gbases_per_s\": %.3f}\n",
+           (unsigned long long)n, (unsigned long long)kept, (unsigned long long)bases, (unsigned long long)seq_sum, dt, n / dt, bases / dt / 1e9);
     return st < 0 ? EXIT_FAILURE : EXIT_SUCCESS;
   }
   if (mode == "_fmd") return run_fmd_hook(pos);

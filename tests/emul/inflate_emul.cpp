@@ -5,20 +5,25 @@
 #include "warp_emul.hpp"
 #include "../../svdss_b200/csrc/inflate_kernel.cuh"
 
-struct Job { const uint8_t* comp; const int64_t* in_offs; const int64_t* out_offs; int64_t n; uint8_t* out; int32_t* status; };
+struct Job { const uint8_t* comp; const int64_t* in_offs; const int64_t* out_offs; int64_t n; uint8_t* out; int32_t* status; int mpw; };
 
 static void body(void* a) {
   Job* j = static_cast<Job*>(a);
-  svb::k_bgzf_inflate(j->comp, j->in_offs, j->out_offs, j->n, j->out, j->status);
+  svb::k_bgzf_inflate(j->comp, j->in_offs, j->out_offs, j->n, j->out, j->status, j->mpw);
 }
 
-extern "C" int emul_bgzf_inflate(const uint8_t* comp, const int64_t* in_offs, const int64_t* out_offs, int64_t n, uint8_t* out, int32_t* status) {
-  Job j = {comp, in_offs, out_offs, n, out, status};
+// mpw: members per warp (1..32), the launch parameter svb_bgzf_inflate_device picks from the window size
+extern "C" int emul_bgzf_inflate_mpw(const uint8_t* comp, const int64_t* in_offs, const int64_t* out_offs, int64_t n, uint8_t* out, int32_t* status, int mpw) {
+  Job j = {comp, in_offs, out_offs, n, out, status, mpw};
   blockDim.x = 32;
-  gridDim.x = (unsigned)((n + 31) / 32);
+  gridDim.x = (unsigned)((n + mpw - 1) / mpw);
   for (unsigned b = 0; b < gridDim.x; ++b) {
     blockIdx.x = b;
     if (!emu::run_warp(body, &j)) return -1;
   }
   return 0;
+}
+
+extern "C" int emul_bgzf_inflate(const uint8_t* comp, const int64_t* in_offs, const int64_t* out_offs, int64_t n, uint8_t* out, int32_t* status) {
+  return emul_bgzf_inflate_mpw(comp, in_offs, out_offs, n, out, status, 32);
 }

@@ -125,7 +125,24 @@ def test_search_bam_filters_and_tags(world):
         assert r.returncode == 0, r.stderr
         want = expected_sfs_text(names, exp, htags, searched if putative else [True] * len(names), 4, 40, True)
         assert r.stdout == want
+        # the same file with its BGZF windows inflated on the device (k_bgzf_inflate), one window and many small ones
+        for window in (None, "3000"):
+            env = dict(os.environ)
+            if window:
+                env["SVB_BGZF_WINDOW"] = window
+            g = subprocess.run(args + ["--gpu-inflate"], capture_output=True, text=True, env=env)
+            assert g.returncode == 0, g.stderr
+            assert g.stdout == want
     assert "\t1\t\n" in want or "\t2\t\n" in want    # some HP tag made it to the output
+    # a damaged member is an error with the device inflate too, not a shorter output
+    raw = bytearray(open(bam, "rb").read())
+    for k in range(len(raw) // 2, len(raw) // 2 + 64):
+        raw[k] ^= 0x5A
+    bad = os.path.join(world["d"], "damaged.bam")
+    open(bad, "wb").write(bytes(raw))
+    for extra in ([], ["--gpu-inflate"]):
+        r = subprocess.run([world["exe"], "search", "--index", world["idx"], "--bam", bad] + extra, capture_output=True, text=True)
+        assert r.returncode != 0 or r.stdout != want, extra
 
 
 def test_call_core_from_clusters_file(world):

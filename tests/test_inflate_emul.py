@@ -24,6 +24,7 @@ def emul():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
     lib = C.CDLL(out)
     lib.emul_bgzf_inflate.restype = C.c_int
+    lib.emul_bgzf_inflate_mpw.restype = C.c_int
     return lib
 
 
@@ -61,14 +62,14 @@ def payloads():
     return out
 
 
-def run(lib, comps, out_lens, pad=64):
+def run(lib, comps, out_lens, pad=64, mpw=32):
     io = np.zeros(len(comps) + 1, np.int64); io[1:] = np.cumsum([len(c) for c in comps])
     oo = np.zeros(len(comps) + 1, np.int64); oo[1:] = np.cumsum(out_lens)
     comp = np.frombuffer(b"".join(comps) + b"\xff" * 16, np.uint8).copy()   # what follows the last member is not zero
     out = np.full(int(oo[-1]) + pad, 0xEE, np.uint8)
     status = np.full(len(comps), -7, np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    assert lib.emul_bgzf_inflate(p(comp), p(io), p(oo), len(comps), p(out), p(status)) == 0
+    assert lib.emul_bgzf_inflate_mpw(p(comp), p(io), p(oo), len(comps), p(out), p(status), mpw) == 0
     return out, oo, status
 
 
@@ -82,6 +83,27 @@ def test_every_block_type_equals_zlib(emul):
     for k, (d, _) in enumerate(cases):
         assert out[int(oo[k]):int(oo[k + 1])].tobytes() == d, k
     assert (out[int(oo[-1]):] == 0xEE).all()
+
+
+@pytest.mark.parametrize("mpw", [1, 5])
+def test_fewer_members_per_warp(emul, mpw):
+    """small windows spread over more warps (svb_bgzf_inflate_device picks 1..32 members per warp)"""
+    cases = payloads()[:23]
+    out, oo, status = run(emul, [c for _, c in cases], [len(d) for d, _ in cases], mpw=mpw)
+    assert (status == 0).all(), status
+    for k, (d, _) in enumerate(cases):
+        assert out[int(oo[k]):int(oo[k + 1])].tobytes() == d, k
+    assert (out[int(oo[-1]):] == 0xEE).all()
+
+
+def test_members_with_their_gzip_trailer_attached(emul):
+    """BgzfSource hands the members over as they lie in the file, CRC32 + ISIZE still behind every deflate stream"""
+    cases = payloads()[:12]
+    comps = [c + zlib.crc32(d).to_bytes(4, "little") + len(d).to_bytes(4, "little") for d, c in cases]
+    out, oo, status = run(emul, comps, [len(d) for d, _ in cases])
+    assert (status == 0).all(), status
+    for k, (d, _) in enumerate(cases):
+        assert out[int(oo[k]):int(oo[k + 1])].tobytes() == d, k
 
 
 def test_members_of_a_bam_file(emul, tmp_path):

@@ -1,7 +1,9 @@
 """What the shell's own BAM reader (host/io.hpp: parallel BGZF inflate one window ahead + in-place record parse) hands
 `SVDSS search` per second, without a GPU: writes a smoothed-shaped BAM of --records 15 kb reads (qualities 0xff as the
 Smoother writes them, XF tags, level-6 BGZF) and runs the `_bamread` hook of the shell on it.
-  python tools/bench_bamread.py [--records 20000]"""
+  python tools/bench_bamread.py [--records 20000] [--repeat 5] [--gpu-inflate]
+--repeat writes the record members k times (a longer file for the price of one deflate pass); --gpu-inflate times the
+reader with its BGZF windows inflated on the device (k_bgzf_inflate, half a gigabyte of members per launch) next to the host one."""
 import argparse, json, os, subprocess, sys, tempfile, time, zlib, struct
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -11,6 +13,8 @@ from svdss_b200 import build
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--records", type=int, default=20000)
+    ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--gpu-inflate", action="store_true")
     a = ap.parse_args()
     exe = build.build_host()
     rng = np.random.default_rng(3)
@@ -20,13 +24,16 @@ def main():
     head = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", 1) + struct.pack("<i", 5) + b"chr1\0" + struct.pack("<i", 400000000)
     out = open(path, "wb")
     buf = bytearray(head)
+    members = []
 
     def flush(final=False):
         nonlocal buf
         while len(buf) >= 0xff00 or (final and buf):
             blk = bytes(buf[:0xff00]); del buf[:0xff00]
             c = zlib.compressobj(6, zlib.DEFLATED, -15); comp = c.compress(blk) + c.flush()
-            out.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp + struct.pack("<II", zlib.crc32(blk), len(blk)))
+            members.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp + struct.pack("<II", zlib.crc32(blk), len(blk)))
+    flush(True)                                    # the header in a member of its own: the record members can repeat
+    out.write(members.pop())
     pos = 0
     for i in range(a.records):
         l = int(rng.integers(10000, 20000))
@@ -39,17 +46,27 @@ def main():
         buf += struct.pack("<i", len(body)) + body
         flush()
     flush(True)
+    body_bytes = b"".join(members)
+    for _ in range(a.repeat):
+        out.write(body_bytes)
     out.write(bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0]))
     out.close()
-    best = None
-    for _ in range(3):
-        r = subprocess.run([exe, "_bamread", path], capture_output=True, text=True)
-        assert r.returncode == 0, r.stderr
-        j = json.loads(r.stdout.strip().splitlines()[-1])
-        if best is None or j["seconds"] < best["seconds"]:
-            best = j
+    res = {}
+    for arm in (["host"] + (["device"] if a.gpu_inflate else [])):
+        best = None
+        for _ in range(3):
+            r = subprocess.run([exe, "_bamread", path] + (["--gpu-inflate"] if arm == "device" else []), capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            if best is None or j["seconds"] < best["seconds"]:
+                best = j
+        res[arm] = best
+    best = res["host"]
     best["file_bytes"] = os.path.getsize(path)
     best["host_threads"] = len(os.sched_getaffinity(0))
+    if "device" in res:
+        assert res["device"]["records"] == best["records"] and res["device"]["bases"] == best["bases"] and res["device"]["seq_sum"] == best["seq_sum"]
+        best["gpu_inflate"] = {k: res["device"][k] for k in ("seconds", "records_per_s", "Gbases_per_s")}
     print(json.dumps(best))
 
 

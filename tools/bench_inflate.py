@@ -14,6 +14,7 @@ def main():
     ap.add_argument("--mb", type=int, default=256, help="inflated size of the window")
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--quals", action="store_true")
+    ap.add_argument("--mpw", default="", help="comma list of members-per-warp values to time (SVB_INFLATE_MPW); default: the library's choice only")
     a = ap.parse_args()
     rng = np.random.default_rng(1)
     body = bytearray()
@@ -38,7 +39,20 @@ def main():
         r = capi.bgzf_inflate_device(comps, sizes)
         best = r.kernel_ms if best is None else min(best, r.kernel_ms)
     ok = r.out.tobytes() == bytes(body)
-    print(json.dumps({"kernel": "k_bgzf_inflate", "members": len(comps), "inflated_bytes": len(body), "compressed_bytes": sum(map(len, comps)),
+    sweep = {}
+    for m in [x for x in a.mpw.split(",") if x]:
+        os.environ["SVB_INFLATE_MPW"] = m
+        ms, wall = None, None
+        for _ in range(2):
+            t = time.perf_counter()
+            r = capi.bgzf_inflate_device(comps, sizes)
+            w = time.perf_counter() - t
+            ms = r.kernel_ms if ms is None else min(ms, r.kernel_ms)
+            wall = w if wall is None else min(wall, w)
+        ok = ok and r.out.tobytes() == bytes(body)
+        sweep[m] = {"kernel_ms": round(ms, 2), "call_ms_with_copies_and_python_packing": round(wall * 1e3, 1)}
+    os.environ.pop("SVB_INFLATE_MPW", None)
+    print(json.dumps({"mpw_sweep": sweep, "kernel": "k_bgzf_inflate", "members": len(comps), "inflated_bytes": len(body), "compressed_bytes": sum(map(len, comps)),
                       "level": a.level, "random_quals": a.quals, "kernel_ms": best, "GB_s_inflated": len(body) / (best * 1e-3) / 1e9,
                       "zlib_one_core_GB_s": len(body) / host_s / 1e9, "identical_to_input": ok}), flush=True)
 
