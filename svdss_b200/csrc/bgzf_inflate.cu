@@ -6,7 +6,8 @@
 // block with its own parity tests (tests/test_inflate_emul.py on the CPU, tests/test_gpu_zz_inflate.py on the GPU);
 // Round 2: timed -- the kernel takes ~200 ms whatever the window holds up to ~75 k members (one 64 KiB member per
 // thread is a latency, not a throughput), i.e. 1.4 GB/s on a 256 MB window and 10.4 GB/s on a 2 GB one
-// (profiles/r02p_inflate.txt) -- and wired into BgzfSource as an opt-in (`--gpu-inflate`: half-gigabyte compressed windows).
+// (profiles/r02p_inflate.txt): 32 lanes on 32 different streams diverge (one member per warp: 16 ms, profiles/r02q_inflate.txt).
+// Hence k_bgzf_inflate_warp, the default now, and BgzfSource's opt-in `--gpu-inflate` (128 MiB compressed windows).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -69,8 +70,13 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
     if (const char* e = getenv("SVB_INFLATE_WARPS_PER_SM")) { const int v = atoi(e); if (v > 0) slots = (int64_t)sms * v; }
     int mpw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (n_members + slots - 1) / slots));
     if (const char* e = getenv("SVB_INFLATE_MPW")) { const int v = atoi(e); if (v >= 1 && v <= 32) mpw = v; }
+    // default: the warp-per-member kernel (tables in shared memory, copies spread over the lanes); SVB_INFLATE_KERNEL=thread
+    // keeps the first one measurable
+    const char* kind = getenv("SVB_INFLATE_KERNEL");
+    const bool by_thread = kind && strcmp(kind, "thread") == 0;
     fail(cudaEventRecord(e0, sq));
-    k_bgzf_inflate<<<(unsigned)((n_members + mpw - 1) / mpw), 32, 0, sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st, mpw);
+    if (by_thread) k_bgzf_inflate<<<(unsigned)((n_members + mpw - 1) / mpw), 32, 0, sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st, mpw);
+    else k_bgzf_inflate_warp<<<(unsigned)((n_members + 1) / 2), 64, 2 * sizeof(InfWarpMem), sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
     fail(cudaGetLastError());
     fail(cudaEventRecord(e1, sq));
     if (out_total) fail(cudaMemcpyAsync(out_host, d_out, (size_t)out_total, cudaMemcpyDeviceToHost, sq));

@@ -198,4 +198,232 @@ __global__ void __launch_bounds__(32) k_bgzf_inflate(const uint8_t* __restrict__
   status[m] = (ob == oa && b == a) ? INF_OK : inflate_member(comp + a, b - a, out + oa, ob - oa);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second kernel, one WARP per member (round 2: the thread-per-member kernel above takes ~200 ms for a member whatever
+// the window holds -- 32 diverging lanes, a bit-by-bit code walk through local memory, one L2 round trip per copied
+// byte).  Lane 0 walks the stream; the warp shares
+//   * look-up tables in shared memory: the next INF_LBITS (INF_DBITS) bits of the stream index an entry
+//     (symbol << 4 | code length), one shared load per symbol; longer codes (rare) fall back to the canonical walk;
+//     all 32 lanes fill the tables of a block from the canonical code lane 0 derived (code of the i-th symbol in
+//     code order = first[len] + i - offs[len], bit-reversed because codes are packed most significant bit first);
+//   * the copies: a match of length l at distance d is l loads then l stores spread over the lanes, source byte
+//     k of an overlapping match (d < l) being k mod d -- all of them lie before the match, so no copy waits for another.
+// The other lanes wait in the shuffle that broadcasts lane 0's next event (match / end of block / error).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int INF_LBITS = 10, INF_DBITS = 8;
+
+struct InfWarpMem {
+  uint16_t ltab[1 << INF_LBITS];
+  uint16_t dtab[1 << INF_DBITS];
+  InfHuff lc, dc;
+  uint16_t first[2][16], offs[2][16];   // first code / first index in code order of every length, literal-length and distance
+  uint8_t len[320];
+};
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned inf_rev(unsigned code, int l) { return __brev(code) >> (32 - l); }
+#else
+inline unsigned inf_rev(unsigned code, int l) { unsigned r = 0; for (int i = 0; i < l; ++i) r |= ((code >> i) & 1u) << (l - 1 - i); return r; }
+#endif
+
+// four more bytes into the bit buffer (cnt <= 32 on entry): independent loads, one latency
+__device__ __forceinline__ void inf_refill4(InfBits& b) {
+  uint32_t w = 0;
+  if (b.pos + 4 <= b.n) w = (uint32_t)b.p[b.pos] | ((uint32_t)b.p[b.pos + 1] << 8) | ((uint32_t)b.p[b.pos + 2] << 16) | ((uint32_t)b.p[b.pos + 3] << 24);
+  else {
+    for (int i = 0; i < 4; ++i) if (b.pos + i < b.n) w |= (uint32_t)b.p[b.pos + i] << (8 * i);
+    if (b.pos >= b.n + 8) b.over = true;
+  }
+  b.buf |= (uint64_t)w << b.cnt;
+  b.cnt += 32; b.pos += 4;
+}
+
+// lane 0: first[] / offs[] of a canonical code (counts already in h)
+__device__ __forceinline__ void inf_code_starts(const InfHuff& h, uint16_t* first, uint16_t* offs) {
+  unsigned f = 0, o = 0;
+  first[0] = 0; offs[0] = 0;
+  for (int l = 1; l < 16; ++l) {
+    first[l] = (uint16_t)f; offs[l] = (uint16_t)o;
+    f = (f + h.count[l]) << 1; o += h.count[l];
+  }
+}
+
+// all lanes: table of the next `bits` bits -> (symbol << 4 | length); 0 where the code is longer or unassigned
+__device__ __forceinline__ void inf_fill_table(uint16_t* tab, int bits, const InfHuff& h, const uint8_t* len, const uint16_t* first,
+                                               const uint16_t* offs, int lane) {
+  for (int i = lane; i < (1 << bits); i += 32) tab[i] = 0;
+  __syncwarp();
+  int coded = 0;
+  for (int l = 1; l < 16; ++l) coded += h.count[l];
+  for (int i = lane; i < coded; i += 32) {
+    const int s = h.symbol[i], l = len[s];
+    if (l > bits) continue;
+    const unsigned code = (unsigned)first[l] + (unsigned)(i - offs[l]);
+    for (unsigned r = inf_rev(code, l); r < (1u << bits); r += 1u << l) tab[r] = (uint16_t)((s << 4) | l);
+  }
+  __syncwarp();
+}
+
+enum : int { INF_EV_END = 0, INF_EV_MATCH = 1, INF_EV_ERR = 2 };
+
+// the whole warp; returns INF_* (the same on every lane)
+__device__ __forceinline__ int inflate_member_warp(const uint8_t* __restrict__ in, int64_t in_len, uint8_t* __restrict__ out, int out_len,
+                                                   InfWarpMem& M, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  InfBits b;
+  b.p = in; b.n = in_len; b.pos = 0; b.buf = 0; b.cnt = 0; b.over = false;
+  int o = 0;
+  for (;;) {
+    // ---- block header (lane 0): st = error, type, last; stored blocks: n bytes from `at`; coded blocks: the canonical codes
+    int st = INF_OK, type = 0, last = 0, nlen = 288, n = 0, at = 0;
+    if (lane == 0) {
+      last = (int)inf_bits(b, 1); type = (int)inf_bits(b, 2);
+      if (type == 0) {
+        b.buf >>= (b.cnt & 7); b.cnt -= (b.cnt & 7);
+        const unsigned a = inf_bits(b, 16), na = inf_bits(b, 16);
+        n = (int)a; at = (int)inf_consumed(b);
+        if (b.over || (a ^ na) != 0xffffu || (int64_t)at + n > in_len) st = INF_EINPUT;
+        else if (o + n > out_len) st = INF_EOUTPUT;
+      } else if (type == 1) {
+        int s = 0;
+        for (; s < 144; ++s) M.len[s] = 8;
+        for (; s < 256; ++s) M.len[s] = 9;
+        for (; s < 280; ++s) M.len[s] = 7;
+        for (; s < 288; ++s) M.len[s] = 8;
+        for (; s < 318; ++s) M.len[s] = 5;
+        inf_construct(M.lc, M.len, 288);
+        inf_construct(M.dc, M.len + 288, 30);
+      } else if (type == 2) {
+        nlen = (int)inf_bits(b, 5) + 257;
+        const int ndist = (int)inf_bits(b, 5) + 1, ncode = (int)inf_bits(b, 4) + 4;
+        if (nlen > 286 || ndist > 30) st = INF_ECODE;
+        else {
+          int i = 0;
+          for (; i < ncode; ++i) M.len[order[i]] = (uint8_t)inf_bits(b, 3);
+          for (; i < 19; ++i) M.len[order[i]] = 0;
+          if (!inf_construct(M.lc, M.len, 19)) st = INF_ECODE;   // lc holds the code length code for a moment
+          i = 0;
+          while (st == INF_OK && i < nlen + ndist) {
+            const int sym = inf_decode(b, M.lc);
+            if (sym < 0 || b.over) { st = INF_ECODE; break; }
+            if (sym < 16) M.len[i++] = (uint8_t)sym;
+            else {
+              int prev = 0, rep;
+              if (sym == 16) {
+                if (i == 0) { st = INF_ECODE; break; }
+                prev = M.len[i - 1];
+                rep = 3 + (int)inf_bits(b, 2);
+              } else if (sym == 17) rep = 3 + (int)inf_bits(b, 3);
+              else rep = 11 + (int)inf_bits(b, 7);
+              if (i + rep > nlen + ndist) { st = INF_ECODE; break; }
+              while (rep--) M.len[i++] = (uint8_t)prev;
+            }
+          }
+          if (st == INF_OK && M.len[256] == 0) st = INF_ECODE;   // no end-of-block code
+          if (st == INF_OK && !inf_construct(M.dc, M.len + nlen, ndist)) st = INF_ECODE;
+          if (st == INF_OK && !inf_construct(M.lc, M.len, nlen)) st = INF_ECODE;
+        }
+      } else st = INF_ECODE;
+      if (st == INF_OK && type != 0) {
+        inf_code_starts(M.lc, M.first[0], M.offs[0]);
+        inf_code_starts(M.dc, M.first[1], M.offs[1]);
+      }
+    }
+    st = __shfl_sync(FULL, st, 0);
+    if (st != INF_OK) return st;
+    type = __shfl_sync(FULL, type, 0); last = __shfl_sync(FULL, last, 0);
+    __syncwarp();
+    if (type == 0) {
+      n = __shfl_sync(FULL, n, 0); at = __shfl_sync(FULL, at, 0);
+      for (int i = lane; i < n; i += 32) out[o + i] = in[at + i];
+      o += n;
+      if (lane == 0) { b.pos = (int64_t)at + n; b.buf = 0; b.cnt = 0; }
+      __syncwarp();
+    } else {
+      nlen = __shfl_sync(FULL, nlen, 0);
+      inf_fill_table(M.ltab, INF_LBITS, M.lc, M.len, M.first[0], M.offs[0], lane);
+      inf_fill_table(M.dtab, INF_DBITS, M.dc, M.len + nlen, M.first[1], M.offs[1], lane);
+      for (;;) {
+        int ev = INF_EV_END, l = 0, d = 0;
+        if (lane == 0) {
+          for (;;) {
+            if (b.cnt < 32) inf_refill4(b);
+            unsigned e = M.ltab[(unsigned)b.buf & ((1u << INF_LBITS) - 1u)];
+            int sym;
+            if (e & 15u) { sym = (int)(e >> 4); b.buf >>= (e & 15u); b.cnt -= (int)(e & 15u); }
+            else sym = inf_decode(b, M.lc);
+            if (sym < 0 || b.over) { ev = INF_EV_ERR; st = sym < 0 ? INF_ECODE : INF_EINPUT; break; }
+            if (sym < 256) {
+              if (o >= out_len) { ev = INF_EV_ERR; st = INF_EOUTPUT; break; }
+              out[o++] = (uint8_t)sym;
+              continue;
+            }
+            if (sym == 256) break;
+            const int ls = sym - 257;
+            if (ls >= 29) { ev = INF_EV_ERR; st = INF_ECODE; break; }
+            // RFC 1951 3.2.5 by formula: lengths 3..10 one by one, then four codes per extra bit, 258 on its own
+            const int le = ls < 8 ? 0 : (ls == 28 ? 0 : (ls - 4) >> 2);
+            l = (ls < 8 ? 3 + ls : (ls == 28 ? 258 : 3 + ((4 + (ls & 3)) << le))) + (int)inf_bits(b, le);
+            if (b.cnt < 32) inf_refill4(b);
+            e = M.dtab[(unsigned)b.buf & ((1u << INF_DBITS) - 1u)];
+            int ds;
+            if (e & 15u) { ds = (int)(e >> 4); b.buf >>= (e & 15u); b.cnt -= (int)(e & 15u); }
+            else ds = inf_decode(b, M.dc);
+            if (ds < 0 || ds >= 30) { ev = INF_EV_ERR; st = INF_ECODE; break; }
+            const int de = ds < 4 ? 0 : (ds - 2) >> 1;
+            d = (ds < 4 ? 1 + ds : 1 + ((2 + (ds & 1)) << de)) + (int)inf_bits(b, de);
+            if (d > o) { ev = INF_EV_ERR; st = INF_EDIST; break; }
+            if (o + l > out_len) { ev = INF_EV_ERR; st = INF_EOUTPUT; break; }
+            ev = INF_EV_MATCH;
+            break;
+          }
+        }
+        ev = __shfl_sync(FULL, ev, 0);
+        if (ev == INF_EV_ERR) return __shfl_sync(FULL, st, 0);
+        o = __shfl_sync(FULL, o, 0);
+        if (ev == INF_EV_END) break;
+        l = __shfl_sync(FULL, l, 0); d = __shfl_sync(FULL, d, 0);
+        __syncwarp();                                   // lane 0's literals are visible to the lanes that copy them
+        uint8_t* dst = out + o;
+        const uint8_t* src = dst - d;
+        uint8_t v[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int k = lane + 32 * j;
+          if (k < l) v[j] = src[d >= l ? k : k % d];
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int k = lane + 32 * j;
+          if (k < l) dst[k] = v[j];
+        }
+        o += l;
+        __syncwarp();
+      }
+    }
+    st = __shfl_sync(FULL, (int)(lane == 0 && b.over), 0);
+    if (st) return INF_EINPUT;
+    if (last) break;
+  }
+  int rc = INF_OK;
+  if (lane == 0) rc = inf_consumed(b) > in_len ? INF_EINPUT : (o == out_len ? INF_OK : INF_ESIZE);
+  return __shfl_sync(FULL, rc, 0);
+}
+
+extern __shared__ unsigned long long inf_smem[];
+
+// blockDim.x / 32 warps per CTA, warp w of CTA c takes member c * warps + w
+__global__ void __launch_bounds__(64, 16) k_bgzf_inflate_warp(const uint8_t* __restrict__ comp, const int64_t* __restrict__ in_offs,
+                                                          const int64_t* __restrict__ out_offs, int64_t n_members,
+                                                          uint8_t* __restrict__ out, int32_t* __restrict__ status) {
+  const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31, warps = (int)blockDim.x >> 5;
+  const int64_t m = (int64_t)blockIdx.x * warps + warp;
+  if (m >= n_members) return;
+  InfWarpMem& M = reinterpret_cast<InfWarpMem*>(inf_smem)[warp];
+  const int64_t a = in_offs[m], b = in_offs[m + 1], oa = out_offs[m], ob = out_offs[m + 1];
+  const int rc = (ob == oa && b == a) ? INF_OK : inflate_member_warp(comp + a, b - a, out + oa, (int)(ob - oa), M, lane);
+  if (lane == 0) status[m] = rc;
+}
+
 }  // namespace svb

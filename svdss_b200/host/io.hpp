@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <future>
@@ -82,6 +83,8 @@ class ByteBuf {
   const uint8_t* data() const { return p_; }
   size_t size() const { return n_; }
   void clear() { n_ = 0; }
+  // capacity up front: growing a pinned buffer step by step would pin it again every time
+  bool reserve(size_t n) { const size_t keep = n_; if (n > cap_ && !resize(n)) return false; n_ = keep; return true; }
   // keeps the first min(size, n) bytes; false when memory runs out
   bool resize(size_t n) {
     if (n > cap_) {
@@ -108,9 +111,9 @@ class ByteBuf {
 // BGZF byte source with parallel inflate: BGZF members (<= 64 KiB each, size in the BC extra field)
 // are independent deflate streams, so a window of them is read sequentially and inflated by all
 // host threads at once -- the reference does the same through htslib's bgzf_mt(.., 8, ..)
-// (ping_pong.cpp:249, clusterer.cpp:13).  With bgzf_gpu_device() >= 0 the window goes to the device instead:
-// half a gigabyte of members per launch (one thread per member pays only with tens of thousands of members,
-// profiles/r02p_inflate.txt), pinned window buffers.  Files that are not BGZF go through plain zlib.
+// (ping_pong.cpp:249, clusterer.cpp:13).  With bgzf_gpu_device() >= 0 the window goes to the device instead
+// (k_bgzf_inflate_warp, one warp per member): 128 MiB of members per launch, pinned window buffers.  Files that
+// are not BGZF go through plain zlib.
 class BgzfSource {
  public:
   explicit BgzfSource(const std::string& path) : f_(fopen(path.c_str(), "rb")), gpu_(bgzf_gpu_device()) {
@@ -122,7 +125,13 @@ class BgzfSource {
     if (bgzf_) fseek(f_, 0, SEEK_SET);
     else { fclose(f_); f_ = nullptr; plain_.reset(new GzSource(path)); }
   }
-  ~BgzfSource() { if (pending_.valid()) pending_.wait(); if (f_) fclose(f_); }
+  ~BgzfSource() {
+    if (pending_.valid()) pending_.wait();
+    if (f_) fclose(f_);
+    if (bgzf_ && getenv("SVB_BGZF_STATS"))
+      fprintf(stderr, "[svdss] BGZF reader: %llu windows, %.3f s reading members, %.3f s inflating (%s), %.3f s the consumer waited\n",
+              (unsigned long long)n_windows_, t_read_, t_inflate_, gpu_ >= 0 ? "device" : "host threads", t_wait_);
+  }
   bool ok() const { return bgzf_ ? f_ != nullptr : (plain_ && plain_->ok()); }
   bool read_exact(void* dst, size_t n) {
     if (!bgzf_) return plain_->read_exact(dst, n);
@@ -144,34 +153,46 @@ class BgzfSource {
   // the next window is read and inflated by a background task while the caller consumes this one
   bool refill() {
     bool ok;
+    const auto w0 = std::chrono::steady_clock::now();
     if (pending_.valid()) ok = pending_.get();
     else ok = fill(in_next_, out_next_);
+    t_wait_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
     if (!ok) { out_.clear(); pos_ = 0; return false; }
     out_.swap(out_next_);
     pos_ = 0;
     pending_ = std::async(std::launch::async, [this]() { return fill(in_next_, out_next_); });
     return true;
   }
-  // one window: up to 64 MiB of BGZF members read sequentially, inflated in parallel.  false at EOF
-  // (no payload left) or on a malformed file.
+  // one window: up to 64 MiB of the file in one read, its BGZF members found in memory (a member the read cut in
+  // two waits in carry_ for the next window), inflated in parallel.  false at EOF (no payload left) or on a
+  // malformed file.
   bool fill(ByteBuf& in, ByteBuf& out) {
     struct Blk { size_t in_off, in_len, out_off, out_len; };
     for (;;) {
+      const auto c0 = std::chrono::steady_clock::now();
       std::vector<Blk> blks;
-      in.clear();
       size_t out_total = 0;
-      size_t window = gpu_ >= 0 ? (size_t)512 << 20 : (size_t)64 << 20;         // compressed bytes per window
+      // compressed bytes per window; the device wants >= ~10 k members per launch (one warp each, 148 SMs x 32 warps)
+      size_t window = gpu_ >= 0 ? (size_t)128 << 20 : (size_t)64 << 20;
       if (const char* e = getenv("SVB_BGZF_WINDOW")) { const long long v = atoll(e); if (v > 0) window = (size_t)v; }   // tests: force records across windows
-      while (in.size() < window) {
-        uint8_t h[18];
-        const size_t got = fread(h, 1, 18, f_);
-        if (got == 0) break;
-        if (got != 18 || h[0] != 31 || h[1] != 139 || !(h[3] & 4)) return false;
+      size_t have = carry_.size();
+      in.clear(); out.clear();                      // nothing of the last window is kept (a growing buffer would copy it)
+      if (!in.resize(have + window + 16)) return false;
+      if (have) memcpy(in.data(), carry_.data(), have);
+      carry_.clear();
+      if (!eof_) {
+        const size_t got = fread(in.data() + have, 1, window, f_);
+        if (got < window) eof_ = true;
+        have += got;
+      }
+      size_t p = 0;
+      while (p + 18 <= have) {
+        const uint8_t* h = in.data() + p;
+        if (h[0] != 31 || h[1] != 139 || !(h[3] & 4)) return false;
         // walk the extra field for the BC subfield (SAM spec 4.1)
-        const unsigned xlen = h[10] | (h[11] << 8);
-        std::vector<uint8_t> extra(xlen);
-        memcpy(extra.data(), h + 12, std::min<size_t>(6, xlen));
-        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != xlen - 6) return false;
+        const size_t xlen = h[10] | (h[11] << 8);
+        if (p + 12 + xlen > have) break;
+        const uint8_t* extra = h + 12;
         int bsize = -1;
         for (size_t o = 0; o + 4 <= xlen;) {
           const unsigned sl = extra[o + 2] | (extra[o + 3] << 8);
@@ -181,25 +202,37 @@ class BgzfSource {
         if (bsize < 0) return false;
         const size_t total = (size_t)bsize + 1, head = 12 + xlen;
         if (total < head + 8) return false;
-        const size_t body = total - head;       // deflate data + CRC32 + ISIZE
-        const size_t at = in.size();
-        if (!in.resize(at + body)) return false;
-        if (fread(in.data() + at, 1, body, f_) != body) return false;
+        if (p + total > have) break;
         uint32_t isize;
-        memcpy(&isize, in.data() + at + body - 4, 4);
+        memcpy(&isize, h + total - 4, 4);
         if (isize > (1u << 16)) return false;
-        blks.push_back(Blk{at, body - 8, out_total, isize});
+        blks.push_back(Blk{p + head, total - head - 8, out_total, isize});   // deflate data; CRC32 + ISIZE follow
         out_total += isize;
+        p += total;
       }
+      if (p < have) {                               // the read ended inside a member
+        if (eof_) return false;                     // truncated file
+        carry_.assign(in.data() + p, in.data() + have);
+      }
+      if (blks.empty()) {
+        if (eof_) return false;
+        continue;                                   // a window smaller than one member (tests): read on
+      }
+      const size_t in_end = p;
       if (blks.empty()) return false;
       if (!out.resize(out_total)) return false;
+      const auto c1 = std::chrono::steady_clock::now();
+      t_read_ += std::chrono::duration<double>(c1 - c0).count();
+      ++n_windows_;
+      struct Tick { std::chrono::steady_clock::time_point a; double& acc; ~Tick() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); } } tick{c1, t_inflate_};
       if (gpu_ >= 0) {
-        // the members as they lie in the window, CRC32 + ISIZE still behind every deflate stream (the kernel stops
-        // at the final block of a stream and checks the payload size)
+        // the members as they lie in the window, gzip trailer and the next header still behind every deflate stream
+        // (the kernel stops at the final block of a stream and checks the payload size)
         std::vector<int64_t> io(blks.size() + 1), oo(blks.size() + 1);
-        for (size_t i = 0; i < blks.size(); ++i) { io[i] = (int64_t)blks[i].in_off; oo[i] = (int64_t)blks[i].out_off; }
-        io[blks.size()] = (int64_t)in.size(); oo[blks.size()] = (int64_t)out_total;
-        if (svb_bgzf_inflate_device(in.data(), io.data(), oo.data(), (int64_t)blks.size(), gpu_, out.data(), nullptr, nullptr) != SVB_OK) {
+        const size_t base = blks[0].in_off;         // member m: from its deflate data to the next member's (trailer and header ride along)
+        for (size_t i = 0; i < blks.size(); ++i) { io[i] = (int64_t)(blks[i].in_off - base); oo[i] = (int64_t)blks[i].out_off; }
+        io[blks.size()] = (int64_t)(in_end - base); oo[blks.size()] = (int64_t)out_total;
+        if (svb_bgzf_inflate_device(in.data() + base, io.data(), oo.data(), (int64_t)blks.size(), gpu_, out.data(), nullptr, nullptr) != SVB_OK) {
           fprintf(stderr, "[svdss] BGZF inflate on device %d: %s\n", gpu_, svb_last_error());
           return false;
         }
@@ -229,7 +262,11 @@ class BgzfSource {
   bool bgzf_ = false;
   std::unique_ptr<GzSource> plain_;
   int gpu_ = -1;
+  double t_read_ = 0, t_inflate_ = 0, t_wait_ = 0;   // SVB_BGZF_STATS=1
+  unsigned long long n_windows_ = 0;
   ByteBuf out_, in_next_, out_next_;
+  std::vector<uint8_t> carry_;                      // head of the member the last read cut
+  bool eof_ = false;
   std::future<bool> pending_;
   size_t pos_ = 0;
 };

@@ -71,3 +71,35 @@ def test_index_takes_ropebwt3_build_options(exe, tmp_path):
         assert r.returncode == 1 and "indexing" not in r.stderr, bad
     r = subprocess.run([exe, "index", "-i", str(fa)], capture_output=True, text=True)
     assert r.returncode == 1 and "not a ropebwt3 FMD" in r.stderr
+
+
+def test_bam_reader_windows_and_truncated_files(exe, tmp_path):
+    """host/io.hpp BgzfSource: the file is read a window at a time and the members are found in memory -- the records
+    come out the same whatever the window (smaller than a member, cutting members in two, one for all), and a
+    file that ends inside a member is an error, not a shorter file."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import numpy as np
+    from bam_writer import write_bam
+    rng = np.random.default_rng(5)
+    recs = [dict(qname="r%d" % i, flag=0, tid=0, pos=100 * i, mapq=60, seq="".join("ACGT"[int(x)] for x in rng.integers(0, 4, 2500)),
+                 cigar=[(2500, "M")], tags={"XF": ("C", i % 2)}) for i in range(150)]
+    path = str(tmp_path / "t.bam")
+    write_bam(path, [("chr1", 1_000_000)], recs)
+    seen = set()
+    for window in ("7", "3000", "40000", str(64 << 20)):
+        r = subprocess.run([exe, "_bamread", path], capture_output=True, text=True, env=dict(os.environ, SVB_BGZF_WINDOW=window))
+        assert r.returncode == 0, r.stderr
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        assert j["records"] == 150 and j["kept"] == 75 and j["bases"] == 150 * 2500
+        seen.add(j["seq_sum"])
+    assert len(seen) == 1
+    raw = open(path, "rb").read()
+    assert len(raw) > 50000
+    cut = str(tmp_path / "cut.bam")
+    open(cut, "wb").write(raw[:len(raw) * 2 // 3])
+    for window in ("3000", str(64 << 20)):
+        r = subprocess.run([exe, "_bamread", cut], capture_output=True, text=True, env=dict(os.environ, SVB_BGZF_WINDOW=window))
+        assert r.returncode != 0

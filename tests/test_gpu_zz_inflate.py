@@ -1,4 +1,5 @@
-"""GPU: svb_bgzf_inflate_device (inflate_kernel.cuh, one thread per BGZF member) against zlib -- every block
+"""GPU: svb_bgzf_inflate_device (inflate_kernel.cuh: one warp per BGZF member, and the first kernel with one
+thread per member behind SVB_INFLATE_KERNEL=thread) against zlib -- every block
 type, a BAM written by the test writer, and corrupt members, which must be reported (SVB_EIO, per-member status)
 while the healthy members of the same call still come out right.  CPU twin through the warp emulator:
 tests/test_inflate_emul.py.  New at the end of round 1 and never run on a GPU: last in the suite."""
@@ -11,6 +12,36 @@ from svdss_b200 import capi
 from test_inflate_emul import payloads, raw_deflate
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["warp", "thread"])
+def kernel(request, monkeypatch):
+    """the library reads SVB_INFLATE_KERNEL at every call"""
+    monkeypatch.setenv("SVB_INFLATE_KERNEL", request.param)
+    return request.param
+
+
+def test_random_damage_never_leaves_its_range():
+    """three flipped bits per member: any status, but a member reported good equals zlib and no member touches its neighbours"""
+    rng = np.random.default_rng(19)
+    d = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), size=30000)) + bytes(20000)
+    good = raw_deflate(d, 6)
+    comps = [good]
+    for _ in range(200):
+        b = bytearray(good)
+        for _ in range(3):
+            b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        comps.append(bytes(b))
+    comps.append(good)
+    r = capi.bgzf_inflate_device(comps, [len(d)] * len(comps), check_status=False)
+    assert r.status[0] == 0 and r.status[-1] == 0
+    assert r.out[:len(d)].tobytes() == d and r.out[int(r.out_offs[-2]):].tobytes() == d
+    n_good = 0
+    for k in range(1, len(comps) - 1):
+        if r.status[k] == 0:
+            assert r.out[int(r.out_offs[k]):int(r.out_offs[k + 1])].tobytes() == zlib.decompress(comps[k], -15)
+            n_good += 1
+    print("damaged members that still inflate: %d of 200" % n_good)
 
 
 def test_every_block_type_equals_zlib():

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 
 
 @pytest.fixture(scope="module")
-def emul():
+def emul_lib():
     src = os.path.join(HERE, "emul", "inflate_emul.cpp")
     out = os.path.join(HERE, "emul", "_build", "libinflate_emul.so")
     deps = [src, os.path.join(HERE, "emul", "warp_emul.hpp"), os.path.join(ROOT, "svdss_b200", "csrc", "inflate_kernel.cuh")]
@@ -25,7 +25,19 @@ def emul():
     lib = C.CDLL(out)
     lib.emul_bgzf_inflate.restype = C.c_int
     lib.emul_bgzf_inflate_mpw.restype = C.c_int
+    lib.emul_bgzf_inflate_warp.restype = C.c_int
     return lib
+
+
+class Emul:
+    def __init__(self, lib, kernel):
+        self.lib, self.kernel = lib, kernel
+
+
+@pytest.fixture(params=["thread", "warp"])
+def emul(emul_lib, request):
+    """both kernels: one thread per member (k_bgzf_inflate) and one warp per member (k_bgzf_inflate_warp)"""
+    return Emul(emul_lib, request.param)
 
 
 def raw_deflate(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, flush_every=0):
@@ -69,7 +81,10 @@ def run(lib, comps, out_lens, pad=64, mpw=32):
     out = np.full(int(oo[-1]) + pad, 0xEE, np.uint8)
     status = np.full(len(comps), -7, np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    assert lib.emul_bgzf_inflate_mpw(p(comp), p(io), p(oo), len(comps), p(out), p(status), mpw) == 0
+    if lib.kernel == "warp":
+        assert lib.lib.emul_bgzf_inflate_warp(p(comp), p(io), p(oo), len(comps), p(out), p(status)) == 0
+    else:
+        assert lib.lib.emul_bgzf_inflate_mpw(p(comp), p(io), p(oo), len(comps), p(out), p(status), mpw) == 0
     return out, oo, status
 
 

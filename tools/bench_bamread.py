@@ -3,7 +3,7 @@
 Smoother writes them, XF tags, level-6 BGZF) and runs the `_bamread` hook of the shell on it.
   python tools/bench_bamread.py [--records 20000] [--repeat 5] [--gpu-inflate]
 --repeat writes the record members k times (a longer file for the price of one deflate pass); --gpu-inflate times the
-reader with its BGZF windows inflated on the device (k_bgzf_inflate, half a gigabyte of members per launch) next to the host one."""
+reader with its BGZF windows inflated on the device (k_bgzf_inflate_warp, 128 MiB of members per launch) next to the host one."""
 import argparse, json, os, subprocess, sys, tempfile, time, zlib, struct
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -55,18 +55,21 @@ def main():
     for arm in (["host"] + (["device"] if a.gpu_inflate else [])):
         best = None
         for _ in range(3):
-            r = subprocess.run([exe, "_bamread", path] + (["--gpu-inflate"] if arm == "device" else []), capture_output=True, text=True)
+            r = subprocess.run([exe, "_bamread", path] + (["--gpu-inflate"] if arm == "device" else []), capture_output=True, text=True,
+                               env=dict(os.environ, SVB_BGZF_STATS="1"))
             assert r.returncode == 0, r.stderr
             j = json.loads(r.stdout.strip().splitlines()[-1])
+            j["reader"] = [l.split("BGZF reader: ")[1] for l in r.stderr.splitlines() if "BGZF reader: " in l][-1:]
             if best is None or j["seconds"] < best["seconds"]:
                 best = j
         res[arm] = best
     best = res["host"]
     best["file_bytes"] = os.path.getsize(path)
+    os.remove(path); os.rmdir(d)
     best["host_threads"] = len(os.sched_getaffinity(0))
     if "device" in res:
         assert res["device"]["records"] == best["records"] and res["device"]["bases"] == best["bases"] and res["device"]["seq_sum"] == best["seq_sum"]
-        best["gpu_inflate"] = {k: res["device"][k] for k in ("seconds", "records_per_s", "Gbases_per_s")}
+        best["gpu_inflate"] = {k: res["device"][k] for k in ("seconds", "records_per_s", "Gbases_per_s", "reader")}
     print(json.dumps(best))
 
 

@@ -52,7 +52,7 @@ def main():
         ok = ok and r.out.tobytes() == bytes(body)
         sweep[m] = {"kernel_ms": round(ms, 2), "call_ms_with_copies_and_python_packing": round(wall * 1e3, 1)}
     os.environ.pop("SVB_INFLATE_MPW", None)
-    print(json.dumps({"mpw_sweep": sweep, "kernel": "k_bgzf_inflate", "members": len(comps), "inflated_bytes": len(body), "compressed_bytes": sum(map(len, comps)),
+    print(json.dumps({"mpw_sweep": sweep, "kernel": "k_bgzf_inflate" if os.environ.get("SVB_INFLATE_KERNEL") == "thread" else "k_bgzf_inflate_warp", "members": len(comps), "inflated_bytes": len(body), "compressed_bytes": sum(map(len, comps)),
                       "level": a.level, "random_quals": a.quals, "kernel_ms": best, "GB_s_inflated": len(body) / (best * 1e-3) / 1e9,
                       "zlib_one_core_GB_s": len(body) / host_s / 1e9, "identical_to_input": ok}), flush=True)
 
