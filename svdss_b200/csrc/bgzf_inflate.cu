@@ -76,7 +76,8 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
     const bool by_thread = kind && strcmp(kind, "thread") == 0;
     fail(cudaEventRecord(e0, sq));
     if (by_thread) k_bgzf_inflate<<<(unsigned)((n_members + mpw - 1) / mpw), 32, 0, sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st, mpw);
-    else k_bgzf_inflate_warp<<<(unsigned)((n_members + 1) / 2), 64, 2 * sizeof(InfWarpMem), sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
+    else if (getenv("SVB_INFLATE_OCC12")) k_bgzf_inflate_warp<12><<<(unsigned)((n_members + 1) / 2), 64, 2 * sizeof(InfWarpMem), sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
+    else k_bgzf_inflate_warp<16><<<(unsigned)((n_members + 1) / 2), 64, 2 * sizeof(InfWarpMem), sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
     fail(cudaGetLastError());
     fail(cudaEventRecord(e1, sq));
     if (out_total) fail(cudaMemcpyAsync(out_host, d_out, (size_t)out_total, cudaMemcpyDeviceToHost, sq));

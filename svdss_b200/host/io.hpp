@@ -168,24 +168,34 @@ class BgzfSource {
   // malformed file.
   bool fill(ByteBuf& in, ByteBuf& out) {
     struct Blk { size_t in_off, in_len, out_off, out_len; };
+    bool starved = false;
     for (;;) {
       const auto c0 = std::chrono::steady_clock::now();
       std::vector<Blk> blks;
       size_t out_total = 0;
-      // compressed bytes per window; the device wants >= ~10 k members per launch (one warp each, 148 SMs x 32 warps)
-      size_t window = gpu_ >= 0 ? (size_t)128 << 20 : (size_t)64 << 20;
+      // compressed bytes per window (~5 k members: one wave of warps on the device)
+      size_t window = (size_t)64 << 20;
       if (const char* e = getenv("SVB_BGZF_WINDOW")) { const long long v = atoll(e); if (v > 0) window = (size_t)v; }   // tests: force records across windows
       size_t have = carry_.size();
       in.clear(); out.clear();                      // nothing of the last window is kept (a growing buffer would copy it)
-      if (!in.resize(have + window + 16)) return false;
+      // device: pinned buffers of a fixed size, pinned once (pinning costs ~0.3 s per GB); a window ends where its
+      // payload would not fit and the rest of the read waits in carry_
+      size_t out_cap = gpu_ >= 0 ? std::max<size_t>(window * 8, (size_t)1 << 20) : ~(size_t)0;
+      if (const char* e = getenv("SVB_BGZF_PAYLOAD")) { const long long v = atoll(e); if (v >= (1 << 16)) out_cap = (size_t)v; }   // tests: the limit on the host path too
+      if (gpu_ >= 0 && (!in.reserve(2 * window + ((size_t)1 << 20)) || !out.reserve(out_cap))) return false;
+      // a carry as long as a window (payload limit hit early): no read this time -- unless it holds no whole member
+      const size_t want = starved ? window : (window > have ? window - have : 0);
+      starved = false;
+      if (!in.resize(have + want + 16)) return false;
       if (have) memcpy(in.data(), carry_.data(), have);
       carry_.clear();
-      if (!eof_) {
-        const size_t got = fread(in.data() + have, 1, window, f_);
-        if (got < window) eof_ = true;
+      if (!eof_ && want) {
+        const size_t got = fread(in.data() + have, 1, want, f_);
+        if (got < want) eof_ = true;
         have += got;
       }
       size_t p = 0;
+      bool full = false;                            // the payload limit ended the window, not the read
       while (p + 18 <= have) {
         const uint8_t* h = in.data() + p;
         if (h[0] != 31 || h[1] != 139 || !(h[3] & 4)) return false;
@@ -206,16 +216,18 @@ class BgzfSource {
         uint32_t isize;
         memcpy(&isize, h + total - 4, 4);
         if (isize > (1u << 16)) return false;
+        if (out_total + isize > out_cap) { full = true; break; }
         blks.push_back(Blk{p + head, total - head - 8, out_total, isize});   // deflate data; CRC32 + ISIZE follow
         out_total += isize;
         p += total;
       }
-      if (p < have) {                               // the read ended inside a member
-        if (eof_) return false;                     // truncated file
+      if (p < have) {                               // the window ends inside a member, or at the payload limit
+        if (eof_ && !full) return false;            // truncated file
         carry_.assign(in.data() + p, in.data() + have);
       }
       if (blks.empty()) {
         if (eof_) return false;
+        starved = true;
         continue;                                   // a window smaller than one member (tests): read on
       }
       const size_t in_end = p;

@@ -32,7 +32,7 @@ extern "C" int emul_bgzf_inflate(const uint8_t* comp, const int64_t* in_offs, co
 // the warp-per-member kernel: one warp per CTA here
 static void body_warp(void* a) {
   Job* j = static_cast<Job*>(a);
-  svb::k_bgzf_inflate_warp(j->comp, j->in_offs, j->out_offs, j->n, j->out, j->status);
+  svb::k_bgzf_inflate_warp<16>(j->comp, j->in_offs, j->out_offs, j->n, j->out, j->status);
 }
 extern "C" int emul_bgzf_inflate_warp(const uint8_t* comp, const int64_t* in_offs, const int64_t* out_offs, int64_t n, uint8_t* out, int32_t* status) {
   static_assert(sizeof(svb::InfWarpMem) <= sizeof(svb::inf_smem), "shared memory of one warp");

@@ -95,6 +95,13 @@ def test_bam_reader_windows_and_truncated_files(exe, tmp_path):
         j = json.loads(r.stdout.strip().splitlines()[-1])
         assert j["records"] == 150 and j["kept"] == 75 and j["bases"] == 150 * 2500
         seen.add(j["seq_sum"])
+    # the payload limit of a window (the device path's pinned buffers have a fixed size): the rest of the read is carried over
+    for window, payload in (("50000", "65536"), (str(64 << 20), "70000"), (str(64 << 20), "200000")):
+        r = subprocess.run([exe, "_bamread", path], capture_output=True, text=True, env=dict(os.environ, SVB_BGZF_WINDOW=window, SVB_BGZF_PAYLOAD=payload))
+        assert r.returncode == 0, r.stderr
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        assert j["records"] == 150 and j["kept"] == 75
+        seen.add(j["seq_sum"])
     assert len(seen) == 1
     raw = open(path, "rb").read()
     assert len(raw) > 50000
