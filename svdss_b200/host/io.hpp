@@ -129,8 +129,8 @@ class BgzfSource {
     if (pending_.valid()) pending_.wait();
     if (f_) fclose(f_);
     if (bgzf_ && getenv("SVB_BGZF_STATS"))
-      fprintf(stderr, "[svdss] BGZF reader: %llu windows, %.3f s reading members, %.3f s inflating (%s), %.3f s the consumer waited\n",
-              (unsigned long long)n_windows_, t_read_, t_inflate_, gpu_ >= 0 ? "device" : "host threads", t_wait_);
+      fprintf(stderr, "[svdss] BGZF reader: %llu windows, %.3f s reading members (%.3f s of it pinning the window buffers), %.3f s inflating (%s), %.3f s the consumer waited\n",
+              (unsigned long long)n_windows_, t_read_, t_pin_, t_inflate_, gpu_ >= 0 ? "device" : "host threads", t_wait_);
   }
   bool ok() const { return bgzf_ ? f_ != nullptr : (plain_ && plain_->ok()); }
   bool read_exact(void* dst, size_t n) {
@@ -182,7 +182,11 @@ class BgzfSource {
       // payload would not fit and the rest of the read waits in carry_
       size_t out_cap = gpu_ >= 0 ? std::max<size_t>(window * 8, (size_t)1 << 20) : ~(size_t)0;
       if (const char* e = getenv("SVB_BGZF_PAYLOAD")) { const long long v = atoll(e); if (v >= (1 << 16)) out_cap = (size_t)v; }   // tests: the limit on the host path too
-      if (gpu_ >= 0 && (!in.reserve(2 * window + ((size_t)1 << 20)) || !out.reserve(out_cap))) return false;
+      if (gpu_ >= 0) {
+        const auto p0 = std::chrono::steady_clock::now();
+        if (!in.reserve(2 * window + ((size_t)1 << 20)) || !out.reserve(out_cap)) return false;
+        t_pin_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - p0).count();
+      }
       // a carry as long as a window (payload limit hit early): no read this time -- unless it holds no whole member
       const size_t want = starved ? window : (window > have ? window - have : 0);
       starved = false;
@@ -274,7 +278,7 @@ class BgzfSource {
   bool bgzf_ = false;
   std::unique_ptr<GzSource> plain_;
   int gpu_ = -1;
-  double t_read_ = 0, t_inflate_ = 0, t_wait_ = 0;   // SVB_BGZF_STATS=1
+  double t_read_ = 0, t_inflate_ = 0, t_wait_ = 0, t_pin_ = 0;   // SVB_BGZF_STATS=1
   unsigned long long n_windows_ = 0;
   ByteBuf out_, in_next_, out_next_;
   std::vector<uint8_t> carry_;                      // head of the member the last read cut

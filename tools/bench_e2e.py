@@ -58,6 +58,7 @@ def main():
     ap.add_argument("--svs", type=int, default=200)
     ap.add_argument("--threads", type=int, default=4)
     ap.add_argument("--keep", default="")
+    ap.add_argument("--gpu-inflate", action="store_true", help="run smooth / search / call a second time with --gpu-inflate: same bytes out, wall clock next to the host inflate")
     ap.add_argument("--raw", action="store_true", help="raw-HiFi-shaped input: run `SVDSS smooth` first (0.1%% substitutions, 0.05%% 1-bp indels)")
     a = ap.parse_args()
     build.build_lib(); exe = build.build_host()
@@ -97,6 +98,19 @@ def main():
     t_index, _ = stage([exe, "index", "-t", str(a.threads), "-d", "-o", idx, fa])
     t_search, _ = stage([exe, "search", "--index", idx, "--bam", bam, "--threads", str(a.threads)], sfs)
     t_call, log_call = stage([exe, "call", "--reference", fa, "--bam", bam, "--sfs", sfs, "--threads", str(a.threads)], vcf)
+    dev = None
+    if a.gpu_inflate:
+        g = ["--gpu-inflate"]
+        dev = {}
+        if a.raw:
+            dev["smooth_s"], _ = stage([exe, "smooth", "--reference", fa, "--bam", os.path.join(d, "sample.bam"), "--threads", str(a.threads)] + g, smoothed + ".dev")
+            dev["smoothed_bam_identical"] = open(smoothed, "rb").read() == open(smoothed + ".dev", "rb").read()
+            os.remove(smoothed + ".dev")
+        dev["search_s"], _ = stage([exe, "search", "--index", idx, "--bam", bam, "--threads", str(a.threads)] + g, sfs + ".dev")
+        dev["call_s"], _ = stage([exe, "call", "--reference", fa, "--bam", bam, "--sfs", sfs, "--threads", str(a.threads)] + g, vcf + ".dev")
+        dev["sfs_identical"] = open(sfs, "rb").read() == open(sfs + ".dev", "rb").read()
+        dev["vcf_identical"] = open(vcf, "rb").read() == open(vcf + ".dev", "rb").read()
+        dev = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in dev.items()}
     calls = [l.split("\t") for l in open(vcf) if not l.startswith("#")]
     hit = 0
     used = set()
@@ -117,6 +131,8 @@ def main():
            "calls": len(calls), "planted": len(cat), "recall": round(hit / max(1, len(cat)), 3),
            "precision": round(len(used) / max(1, len(calls)), 3), "generate_s": round(gen_s, 1),
            "note": "wall clock of the CLI stages (process start, BGZF inflate, index load, GPU work, text output)"}
+    if dev is not None:
+        out["with_gpu_inflate"] = dev
     print(json.dumps(out), flush=True)
     sys.stderr.write(log_call)
 
