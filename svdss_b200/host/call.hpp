@@ -187,6 +187,18 @@ inline double fuzz_ratio(const std::string& a, const std::string& b) {
   return 100.0 * 2.0 * (double)lcs / (double)(n + m);
 }
 
+// caller.hpp:39-71: a sub-cluster's POA consensus placed on the reference; sam_line() is its operator<<
+struct Consensus {
+  std::string seq, chrom, cigar;
+  int s = 0, e = 0;
+  Consensus(std::string seq_, std::string cigar_, std::string chrom_, int s_, int e_)
+      : seq(std::move(seq_)), chrom(std::move(chrom_)), cigar(std::move(cigar_)), s(s_), e(e_) {}
+  std::string sam_line() const {
+    return chrom + ":" + std::to_string(s + 1) + "-" + std::to_string(e + 1) + "\t0\t" + chrom + "\t" + std::to_string(s + 1) + "\t60\t" + cigar +
+           "\t*\t0\t0\t" + seq + "\t*";
+  }
+};
+
 struct CallConfig {
   std::string reference, clusters_in, poa_out, bam, sfs, clusters_out, clips_out;
   unsigned min_cluster_weight = 2, min_sv_length = 25, min_mapq = 20;
@@ -358,12 +370,12 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
   }
   const size_t T = (size_t)std::max(1, c.threads);
   std::vector<std::vector<SV>> p_svs(T);
-  std::vector<std::vector<std::string>> p_sam(T);
+  std::vector<std::vector<Consensus>> p_sam(T);          // _p_alignments, caller.cpp:312-314
   int64_t sv_k = 0;
   for (int64_t k = 0; k < K.n_jobs; ++k) {
     const size_t parent = (size_t)K.job_cluster[k];
     std::vector<SV>& svs = p_svs[parent % T];            // schedule(static, 1), caller.cpp:312-314
-    std::vector<std::string>& sam = p_sam[parent % T];
+    std::vector<Consensus>& sam = p_sam[parent % T];
     std::string rvec;                                        // SV::set_rvec, sv.cpp:42-46
     for (const auto& r : clusters[parent].reads) rvec += std::to_string(r.first) + ":" + std::to_string(r.second) + "-";
     if (!rvec.empty()) rvec.pop_back();
@@ -373,8 +385,7 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     std::string cons, cigar_str, reads;
     for (int64_t i = K.cons_offs[k]; i < K.cons_offs[k + 1]; ++i) cons += "ACGTN"[K.cons[i]];   // :295-297
     for (int64_t i = K.cigar_offs[k]; i < K.cigar_offs[k + 1]; ++i) cigar_str += std::to_string(K.cigar[i] >> 4) + "MID"[K.cigar[i] & 0xf];  // :352-355
-    sam.push_back(cl.chrom + ":" + std::to_string(cl.s + 1) + "-" + std::to_string(cl.e + 1) + "\t0\t" + cl.chrom + "\t" +
-                  std::to_string(cl.s + 1) + "\t60\t" + cigar_str + "\t*\t0\t0\t" + cons + "\t*");        // caller.hpp:56-70
+    sam.emplace_back(cons, cigar_str, cl.chrom, cl.s, cl.e);                                              // caller.cpp:357
     const int64_t n_sub = K.job_sub_offs[k + 1] - K.job_sub_offs[k];
     for (int64_t i = K.job_sub_offs[k]; i < K.job_sub_offs[k + 1]; ++i) reads += cl.subreads[(size_t)(K.job_sub[i] - sub_offs[parent])].name + ",";
     if (!reads.empty()) reads.pop_back();
@@ -395,7 +406,7 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
   // caller.cpp:17-29: per-thread vectors are inserted at the front, then sort / clean_dups /
   // filter_sv_chains / sort (stable here; the reference's std::sort leaves ties unspecified)
   std::vector<SV> svs;
-  std::vector<std::string> sam;
+  std::vector<Consensus> sam;
   for (size_t slot = 0; slot < T; ++slot) {
     svs.insert(svs.begin(), p_svs[slot].begin(), p_svs[slot].end());
     sam.insert(sam.begin(), p_sam[slot].begin(), p_sam[slot].end());
@@ -447,7 +458,7 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     if (!f) { log("critical", "cannot write " + c.poa_out); return 1; }
     fprintf(f, "@HD\tVN:1.4\n");
     for (const auto& ch : chroms) fprintf(f, "@SQ\tSN:%s\tLN:%zu\n", ch.c_str(), seqs[ch].size());
-    for (const auto& a : sam) fprintf(f, "%s\n", a.c_str());
+    for (const Consensus& a : sam) fprintf(f, "%s\n", a.sam_line().c_str());
     fclose(f);
   }
   if (c.clipped) {  // caller.cpp:37-55

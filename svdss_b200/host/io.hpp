@@ -112,25 +112,31 @@ class ByteBuf {
 // are independent deflate streams, so a window of them is read sequentially and inflated by all
 // host threads at once -- the reference does the same through htslib's bgzf_mt(.., 8, ..)
 // (ping_pong.cpp:249, clusterer.cpp:13).  With bgzf_gpu_device() >= 0 the window goes to the device instead
-// (k_bgzf_inflate_warp, one warp per member): 128 MiB of members per launch, pinned window buffers.  Files that
-// are not BGZF go through plain zlib.
+// (k_bgzf_inflate_warp, one warp per member), pinned window buffers.  Files that are not BGZF go through plain zlib.
 class BgzfSource {
  public:
   explicit BgzfSource(const std::string& path) : f_(fopen(path.c_str(), "rb")), gpu_(bgzf_gpu_device()) {
     if (!f_) return;
-    if (gpu_ >= 0) { out_.pin(true); in_next_.pin(true); out_next_.pin(true); }
     uint8_t h[18];
     const size_t got = fread(h, 1, 18, f_);
     bgzf_ = got == 18 && h[0] == 31 && h[1] == 139 && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
+    if (bgzf_ && gpu_ >= 0) {
+      // pinning the window buffers and the first CUDA call cost ~1.5 s: below a gigabyte of file the host threads win
+      long long min_bytes = 1ll << 30;
+      if (const char* e = getenv("SVB_BGZF_GPU_MIN_BYTES")) min_bytes = atoll(e);
+      fseek(f_, 0, SEEK_END);
+      if ((long long)ftell(f_) < min_bytes) gpu_ = -1;
+    }
     if (bgzf_) fseek(f_, 0, SEEK_SET);
     else { fclose(f_); f_ = nullptr; plain_.reset(new GzSource(path)); }
   }
   ~BgzfSource() {
     if (pending_.valid()) pending_.wait();
+    if (reading_.valid()) reading_.wait();
     if (f_) fclose(f_);
     if (bgzf_ && getenv("SVB_BGZF_STATS"))
       fprintf(stderr, "[svdss] BGZF reader: %llu windows, %.3f s reading members (%.3f s of it pinning the window buffers), %.3f s inflating (%s), %.3f s the consumer waited\n",
-              (unsigned long long)n_windows_, t_read_, t_pin_, t_inflate_, gpu_ >= 0 ? "device" : "host threads", t_wait_);
+              (unsigned long long)n_windows_, t_read_ + t_pin_out_, t_pin_ + t_pin_out_, t_inflate_, gpu_ >= 0 ? "device" : "host threads", t_wait_);
   }
   bool ok() const { return bgzf_ ? f_ != nullptr : (plain_ && plain_->ok()); }
   bool read_exact(void* dst, size_t n) {
@@ -150,43 +156,76 @@ class BgzfSource {
   const uint8_t* peek(size_t n) const { return bgzf_ && out_.size() - pos_ >= n ? out_.data() + pos_ : nullptr; }
   void skip(size_t n) { pos_ += n; }
  private:
-  // the next window is read and inflated by a background task while the caller consumes this one
+  struct Blk { size_t in_off, in_len, out_off, out_len; };
+  // a window of the file as read: whole BGZF members, blks[] = where their deflate data lie and where their payload goes
+  struct Window {
+    ByteBuf in;
+    std::vector<Blk> blks;
+    size_t in_end = 0, out_total = 0;
+  };
+  using Clock = std::chrono::steady_clock;
+  static double since(Clock::time_point t) { return std::chrono::duration<double>(Clock::now() - t).count(); }
+
+  // Three stages run side by side: the caller parses window k, a background task inflates window k + 1, and that
+  // task's own helper reads window k + 2 from the file.
   bool refill() {
     bool ok;
-    const auto w0 = std::chrono::steady_clock::now();
+    const auto w0 = Clock::now();
     if (pending_.valid()) ok = pending_.get();
-    else ok = fill(in_next_, out_next_);
-    t_wait_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+    else ok = next_window(out_next_);
+    t_wait_ += since(w0);
     if (!ok) { out_.clear(); pos_ = 0; return false; }
     out_.swap(out_next_);
     pos_ = 0;
-    pending_ = std::async(std::launch::async, [this]() { return fill(in_next_, out_next_); });
+    pending_ = std::async(std::launch::async, [this]() { return next_window(out_next_); });
     return true;
   }
+  // the next window with any payload, inflated into `out`.  false at EOF (no payload left) or on a malformed file.
+  bool next_window(ByteBuf& out) {
+    for (;;) {
+      Window& w = win_[seq_ & 1];
+      const bool have = reading_.valid() ? reading_.get() : read_window(w);
+      if (!have) return false;
+      ++seq_;
+      // the other buffer held the window before this one, inflated long ago: read the window after this one into it
+      Window& next = win_[seq_ & 1];
+      reading_ = std::async(std::launch::async, [this, &next]() { return read_window(next); });
+      if (!inflate_window(w, out)) return false;
+      if (w.out_total > 0) return true;
+      // a window holding only empty members (the EOF marker): keep reading
+    }
+  }
+  size_t window_bytes() const {
+    size_t window = (size_t)64 << 20;             // compressed bytes per window (~5 k members: one wave of warps on the device)
+    if (const char* e = getenv("SVB_BGZF_WINDOW")) { const long long v = atoll(e); if (v > 0) window = (size_t)v; }   // tests: force records across windows
+    return window;
+  }
+  // device: pinned buffers of a fixed size, pinned once (pinning costs ~1 s per GB here); a window ends where its
+  // payload would not fit and the rest of the read waits in carry_
+  size_t payload_limit(size_t window) const {
+    size_t cap = gpu_ >= 0 ? std::max<size_t>(window * 8, (size_t)1 << 20) : ~(size_t)0;
+    if (const char* e = getenv("SVB_BGZF_PAYLOAD")) { const long long v = atoll(e); if (v >= (1 << 16)) cap = (size_t)v; }   // tests: the limit on the host path too
+    return cap;
+  }
   // one window: up to 64 MiB of the file in one read, its BGZF members found in memory (a member the read cut in
-  // two waits in carry_ for the next window), inflated in parallel.  false at EOF (no payload left) or on a
-  // malformed file.
-  bool fill(ByteBuf& in, ByteBuf& out) {
-    struct Blk { size_t in_off, in_len, out_off, out_len; };
+  // two waits in carry_ for the next window).  false at EOF or on a malformed file.  Only one call at a time
+  // (next_window waits for a read before it starts the next): carry_, eof_ and the file position are its own.
+  bool read_window(Window& w) {
+    const auto c0 = Clock::now();
+    ByteBuf& in = w.in;
+    const size_t window = window_bytes(), out_cap = payload_limit(window);
+    if (gpu_ >= 0) {
+      const auto p0 = Clock::now();
+      in.pin(true);
+      if (!in.reserve(2 * window + ((size_t)1 << 20))) return false;
+      t_pin_ += since(p0);
+    }
     bool starved = false;
     for (;;) {
-      const auto c0 = std::chrono::steady_clock::now();
-      std::vector<Blk> blks;
-      size_t out_total = 0;
-      // compressed bytes per window (~5 k members: one wave of warps on the device)
-      size_t window = (size_t)64 << 20;
-      if (const char* e = getenv("SVB_BGZF_WINDOW")) { const long long v = atoll(e); if (v > 0) window = (size_t)v; }   // tests: force records across windows
+      w.blks.clear();
+      w.out_total = 0;
       size_t have = carry_.size();
-      in.clear(); out.clear();                      // nothing of the last window is kept (a growing buffer would copy it)
-      // device: pinned buffers of a fixed size, pinned once (pinning costs ~0.3 s per GB); a window ends where its
-      // payload would not fit and the rest of the read waits in carry_
-      size_t out_cap = gpu_ >= 0 ? std::max<size_t>(window * 8, (size_t)1 << 20) : ~(size_t)0;
-      if (const char* e = getenv("SVB_BGZF_PAYLOAD")) { const long long v = atoll(e); if (v >= (1 << 16)) out_cap = (size_t)v; }   // tests: the limit on the host path too
-      if (gpu_ >= 0) {
-        const auto p0 = std::chrono::steady_clock::now();
-        if (!in.reserve(2 * window + ((size_t)1 << 20)) || !out.reserve(out_cap)) return false;
-        t_pin_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - p0).count();
-      }
+      in.clear();                                   // nothing of the last window is kept (a growing buffer would copy it)
       // a carry as long as a window (payload limit hit early): no read this time -- unless it holds no whole member
       const size_t want = starved ? window : (window > have ? window - have : 0);
       starved = false;
@@ -220,70 +259,82 @@ class BgzfSource {
         uint32_t isize;
         memcpy(&isize, h + total - 4, 4);
         if (isize > (1u << 16)) return false;
-        if (out_total + isize > out_cap) { full = true; break; }
-        blks.push_back(Blk{p + head, total - head - 8, out_total, isize});   // deflate data; CRC32 + ISIZE follow
-        out_total += isize;
+        if (w.out_total + isize > out_cap) { full = true; break; }
+        w.blks.push_back(Blk{p + head, total - head - 8, w.out_total, isize});   // deflate data; CRC32 + ISIZE follow
+        w.out_total += isize;
         p += total;
       }
       if (p < have) {                               // the window ends inside a member, or at the payload limit
         if (eof_ && !full) return false;            // truncated file
         carry_.assign(in.data() + p, in.data() + have);
       }
-      if (blks.empty()) {
+      if (w.blks.empty()) {
         if (eof_) return false;
         starved = true;
         continue;                                   // a window smaller than one member (tests): read on
       }
-      const size_t in_end = p;
-      if (blks.empty()) return false;
-      if (!out.resize(out_total)) return false;
-      const auto c1 = std::chrono::steady_clock::now();
-      t_read_ += std::chrono::duration<double>(c1 - c0).count();
+      w.in_end = p;
+      t_read_ += since(c0);
       ++n_windows_;
-      struct Tick { std::chrono::steady_clock::time_point a; double& acc; ~Tick() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count(); } } tick{c1, t_inflate_};
-      if (gpu_ >= 0) {
-        // the members as they lie in the window, gzip trailer and the next header still behind every deflate stream
-        // (the kernel stops at the final block of a stream and checks the payload size)
-        std::vector<int64_t> io(blks.size() + 1), oo(blks.size() + 1);
-        const size_t base = blks[0].in_off;         // member m: from its deflate data to the next member's (trailer and header ride along)
-        for (size_t i = 0; i < blks.size(); ++i) { io[i] = (int64_t)(blks[i].in_off - base); oo[i] = (int64_t)blks[i].out_off; }
-        io[blks.size()] = (int64_t)(in_end - base); oo[blks.size()] = (int64_t)out_total;
-        if (svb_bgzf_inflate_device(in.data() + base, io.data(), oo.data(), (int64_t)blks.size(), gpu_, out.data(), nullptr, nullptr) != SVB_OK) {
-          fprintf(stderr, "[svdss] BGZF inflate on device %d: %s\n", gpu_, svb_last_error());
-          return false;
-        }
-        if (out_total > 0) return true;
-        continue;
-      }
-      int bad = 0;
-#pragma omp parallel for schedule(dynamic, 8) reduction(+ : bad)
-      for (long long i = 0; i < (long long)blks.size(); ++i) {
-        const Blk& b = blks[(size_t)i];
-        if (b.out_len == 0) continue;
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) { ++bad; continue; }
-        zs.next_in = in.data() + b.in_off; zs.avail_in = (uInt)b.in_len;
-        zs.next_out = out.data() + b.out_off; zs.avail_out = (uInt)b.out_len;
-        const int rc = inflate(&zs, Z_FINISH);
-        if (rc != Z_STREAM_END || zs.avail_out != 0) ++bad;
-        inflateEnd(&zs);
-      }
-      if (bad) return false;
-      if (out_total > 0) return true;
-      // a window holding only empty members (the EOF marker): keep reading
+      return true;
     }
+  }
+  // the members of a window inflated in parallel: by the device, or by all host threads
+  bool inflate_window(Window& w, ByteBuf& out) {
+    const auto c0 = Clock::now();
+    struct Tick { Clock::time_point a; double& acc; ~Tick() { acc += since(a); } } tick{c0, t_inflate_};
+    ByteBuf& in = w.in;
+    const std::vector<Blk>& blks = w.blks;
+    out.clear();
+    if (gpu_ >= 0) {
+      const auto p0 = Clock::now();
+      out.pin(true);
+      if (!out.reserve(payload_limit(window_bytes()))) return false;
+      const double pin_s = since(p0);
+      t_pin_out_ += pin_s; t_inflate_ -= pin_s;
+    }
+    if (!out.resize(w.out_total)) return false;
+    if (gpu_ >= 0) {
+      // the members as they lie in the window, gzip trailer and the next header still behind every deflate stream
+      // (the kernel stops at the final block of a stream and checks the payload size)
+      std::vector<int64_t> io(blks.size() + 1), oo(blks.size() + 1);
+      const size_t base = blks[0].in_off;         // member m: from its deflate data to the next member's (trailer and header ride along)
+      for (size_t i = 0; i < blks.size(); ++i) { io[i] = (int64_t)(blks[i].in_off - base); oo[i] = (int64_t)blks[i].out_off; }
+      io[blks.size()] = (int64_t)(w.in_end - base); oo[blks.size()] = (int64_t)w.out_total;
+      if (svb_bgzf_inflate_device(in.data() + base, io.data(), oo.data(), (int64_t)blks.size(), gpu_, out.data(), nullptr, nullptr) != SVB_OK) {
+        fprintf(stderr, "[svdss] BGZF inflate on device %d: %s\n", gpu_, svb_last_error());
+        return false;
+      }
+      return true;
+    }
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : bad)
+    for (long long i = 0; i < (long long)blks.size(); ++i) {
+      const Blk& b = blks[(size_t)i];
+      if (b.out_len == 0) continue;
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, -15) != Z_OK) { ++bad; continue; }
+      zs.next_in = in.data() + b.in_off; zs.avail_in = (uInt)b.in_len;
+      zs.next_out = out.data() + b.out_off; zs.avail_out = (uInt)b.out_len;
+      const int rc = inflate(&zs, Z_FINISH);
+      if (rc != Z_STREAM_END || zs.avail_out != 0) ++bad;
+      inflateEnd(&zs);
+    }
+    return bad == 0;
   }
   FILE* f_ = nullptr;
   bool bgzf_ = false;
   std::unique_ptr<GzSource> plain_;
   int gpu_ = -1;
-  double t_read_ = 0, t_inflate_ = 0, t_wait_ = 0, t_pin_ = 0;   // SVB_BGZF_STATS=1
+  double t_read_ = 0, t_pin_ = 0, t_inflate_ = 0, t_pin_out_ = 0, t_wait_ = 0;   // SVB_BGZF_STATS=1 (the first two written by the reading task, the next two by the inflating one)
   unsigned long long n_windows_ = 0;
-  ByteBuf out_, in_next_, out_next_;
+  ByteBuf out_, out_next_;
+  Window win_[2];                                   // window being inflated / window being read
+  unsigned long long seq_ = 0;                      // windows handed to inflate_window so far
   std::vector<uint8_t> carry_;                      // head of the member the last read cut
   bool eof_ = false;
-  std::future<bool> pending_;
+  std::future<bool> pending_, reading_;
   size_t pos_ = 0;
 };
 

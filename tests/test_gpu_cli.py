@@ -127,12 +127,13 @@ def test_search_bam_filters_and_tags(world):
         assert r.stdout == want
         # the same file with its BGZF windows inflated on the device (k_bgzf_inflate), one window and many small ones
         for window in (None, "3000"):
-            env = dict(os.environ)
+            env = dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0", SVB_BGZF_STATS="1")   # small files stay on the host threads by default
             if window:
                 env["SVB_BGZF_WINDOW"] = window
             g = subprocess.run(args + ["--gpu-inflate"], capture_output=True, text=True, env=env)
             assert g.returncode == 0, g.stderr
             assert g.stdout == want
+            assert "inflating (device)" in g.stderr
     assert "\t1\t\n" in want or "\t2\t\n" in want    # some HP tag made it to the output
     # a damaged member is an error with the device inflate too, not a shorter output
     raw = bytearray(open(bam, "rb").read())
@@ -141,7 +142,8 @@ def test_search_bam_filters_and_tags(world):
     bad = os.path.join(world["d"], "damaged.bam")
     open(bad, "wb").write(bytes(raw))
     for extra in ([], ["--gpu-inflate"]):
-        r = subprocess.run([world["exe"], "search", "--index", world["idx"], "--bam", bad] + extra, capture_output=True, text=True)
+        r = subprocess.run([world["exe"], "search", "--index", world["idx"], "--bam", bad] + extra, capture_output=True, text=True,
+                           env=dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0"))
         assert r.returncode != 0 or r.stdout != want, extra
 
 

@@ -56,7 +56,7 @@ def main():
         best = None
         for _ in range(3):
             r = subprocess.run([exe, "_bamread", path] + (["--gpu-inflate"] if arm == "device" else []), capture_output=True, text=True,
-                               env=dict(os.environ, SVB_BGZF_STATS="1"))
+                               env=dict(os.environ, SVB_BGZF_STATS="1", SVB_BGZF_GPU_MIN_BYTES="0"))
             assert r.returncode == 0, r.stderr
             j = json.loads(r.stdout.strip().splitlines()[-1])
             j["reader"] = [l.split("BGZF reader: ")[1] for l in r.stderr.splitlines() if "BGZF reader: " in l][-1:]
