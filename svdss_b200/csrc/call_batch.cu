@@ -221,6 +221,8 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
     out->job_sub_offs[nj] = i;
   }
   float host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+  StageLog slog("call");
+  slog.lap("(since the lap clock started)");
   if (nj == 0) { out->host_ms = host_ms; return SVB_OK; }
   const int64_t tot = seq_offs[(size_t)n_js];
   // ---- gather the sub-reads
@@ -288,6 +290,7 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
         for (auto& x : th) x.join();
       }
     }
+    slog.lap("sub-read gather");
     QCHECK(cudaEventRecord(e1, 0));
     // ---- run_poa for every job (caller.cpp:257-308)
     const auto t_poa0 = std::chrono::steady_clock::now();
@@ -295,6 +298,7 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
                         coffs.data(), nj, device, &poa);
     if (rc != SVB_OK) goto done;
     out->poa_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_poa0).count();
+    slog.lap("poa_batch_impl");
     out->poa_cells = poa.cells; out->poa_kernel_ms = poa.kernel_ms; out->poa_reruns = poa.reruns; out->launches += poa.launches;
     out->h2d_bytes += poa.h2d_bytes; out->d2h_bytes += poa.d2h_bytes;
     // ---- ksw_extd2 of every consensus against its reference window (caller.cpp:329-355)
@@ -332,10 +336,12 @@ extern "C" int svb_call_batch(const svb_clusters_t* CL, const svb_seqs_t* RD, co
       else for (auto& b : tw) b = code_of_ascii(b);
       std::vector<uint8_t> q((size_t)std::max<int64_t>(poa.cons_offs[nj], 1));
       memcpy(q.data(), poa.cons, (size_t)poa.cons_offs[nj]);
+      slog.lap("reference windows + consensus copy");
       const auto t_ksw0 = std::chrono::steady_clock::now();
       rc = svb_ksw_extd2_batch(q.data(), poa.cons_offs, tw.data(), to.data(), nj, 1, -9, -1, 16, 2, 41, 1, device, &ez);   // caller.cpp:333-349
       if (rc != SVB_OK) goto done;
       out->ksw_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_ksw0).count();
+      slog.lap("svb_ksw_extd2_batch");
       out->ksw_cells = ez.cells; out->ksw_kernel_ms = ez.kernel_ms; out->ksw_waves = ez.waves; out->launches += ez.launches;
       out->h2d_bytes += ez.h2d_bytes; out->d2h_bytes += ez.d2h_bytes;
     }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -63,6 +65,22 @@ inline cudaError_t pool_available(size_t* avail) {
   *avail = free_b;
   return cudaSuccess;
 }
+
+// SVB_STAGE_STATS=1: host-side lap times of a batch call on stderr (where does a stage spend what its kernel does not?).
+// A lap synchronises the device, so the lines are a diagnosis, not a measurement of the unperturbed call.
+struct StageLog {
+  bool on;
+  const char* who;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageLog(const char* w) : on(getenv("SVB_STAGE_STATS") != nullptr), who(w), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[svb-stage] %s: %s %.3f ms\n", who, what, std::chrono::duration<double, std::milli>(t - t0).count());
+    t0 = t;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // FM-index block array ("sampled-Occ BWT blocks") in HBM.

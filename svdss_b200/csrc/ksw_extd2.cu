@@ -54,9 +54,12 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
     cells[p] = ql * tl;
     total_cells += (double)cells[p];
   }
+  StageLog slog("ksw");
   std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cells[x] > cells[y]; });
+  slog.lap("sort pairs");
   size_t free_b = 0;
   SVB_CUDA(pool_available(&free_b));
+  slog.lap("pool_available");
   const char* eb = getenv("SVB_KSW_TB_BYTES");
   // one traceback byte per cell: the budget bounds the cells in flight, hence -- for 10 kb x 10 kb pairs of
   // 100 MB each -- the number of warps that have work.  Most of the free HBM by default (round 1 used
@@ -106,6 +109,7 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
     KCHECK(cudaMemcpy(d_toff, to.data(), (n_pairs + 1) * 8, cudaMemcpyHostToDevice));
     KCHECK(cudaMemcpy(d_order, order.data(), n_pairs * 4, cudaMemcpyHostToDevice));
     out->h2d_bytes = qtot + ttot + (n_pairs + 1) * 16 + n_pairs * 4;
+    slog.lap("buffers + H2D");
     // wave plan
     struct Wave { int64_t first, count, tb, bnd, cg; };
     std::vector<Wave> waves;
@@ -135,6 +139,7 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
     KCHECK(pmalloc((void**)&d_bnd, (size_t)(max_bnd * 4), 0));
     KCHECK(pmalloc((void**)&d_cg, (size_t)(max_cg * 4), 0));
     KCHECK(pmalloc((void**)&d_woff, (size_t)(max_cnt * 3 * 8), 0));
+    slog.lap("wave plan + traceback buffers");
     // cigar ops are first collected per wave on the device (reverse order), sizes come back to the
     // host, which lays out the final dense table wave by wave
     std::vector<std::vector<uint32_t>> wave_ops(waves.size());
@@ -179,6 +184,7 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
       cudaEventDestroy(k0); cudaEventDestroy(k1);
       kms_total += ms;
       out->launches += 1;
+      slog.lap("wave kernel");
       // op counts of this wave -> dense layout -> gather on the device -> one dense D2H
       KCHECK(cudaMemcpy(cgn.data() + wv.first, d_cgn + wv.first, wv.count * 4, cudaMemcpyDeviceToHost));
       std::vector<int64_t> dense_off((size_t)wv.count + 1, 0);
@@ -198,6 +204,7 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
         out->launches += 1;
       }
       out->d2h_bytes += nd * 4 + wv.count * 4;
+      slog.lap("wave cigar gather + D2H");
     }
     KCHECK(cudaMemcpy(out->score, d_score, n_pairs * 4, cudaMemcpyDeviceToHost));
     out->d2h_bytes += n_pairs * 4;
@@ -220,6 +227,7 @@ extern "C" int svb_ksw_extd2_batch(const uint8_t* q_concat, const int64_t* q_off
         o += n;
       }
     }
+    slog.lap("cigar table on the host");
     KCHECK(cudaEventRecord(e1, 0));
     KCHECK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&out->device_ms, e0, e1);

@@ -76,6 +76,7 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
   unsigned long long* d_cells = nullptr;
   unsigned long long* d_phase = nullptr;
   int rc = SVB_OK;
+  StageLog slog("poa");
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   std::vector<int64_t> so((size_t)n_seqs + 1);
   for (int64_t i = 0; i <= n_seqs; ++i) so[i] = seq_offs[i] - s_first;
@@ -110,10 +111,12 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
     PCHECK(pmalloc((void**)&d_cells, 8, 0));
     PCHECK(cudaMemsetAsync(d_cells, 0, 8, 0));
     if (getenv("SVB_POA_TIMING")) { PCHECK(pmalloc((void**)&d_phase, 40, 0)); PCHECK(cudaMemsetAsync(d_phase, 0, 40, 0)); }
+    slog.lap("small buffers");
     if (s_total && seqs_mem != SVB_MEM_DEVICE) PCHECK(cudaMemcpy(d_seqs, seqs + s_first, s_total, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_soff, so.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_coff, cluster_offs, (n_clusters + 1) * 8, cudaMemcpyHostToDevice));
     PCHECK(cudaMemcpy(d_capoff, cap_off.data(), (n_clusters + 1) * 8, cudaMemcpyHostToDevice));
+    slog.lap("sequences + offsets H2D");
     out->h2d_bytes = (seqs_mem == SVB_MEM_DEVICE ? 0 : s_total) + (n_seqs + 1) * 8 + (n_clusters + 1) * 16;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -172,8 +175,10 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       // smallest slot, so it fits whichever warp picks it up -- and the workspace is the sum of the biggest `slots`
       // footprints instead of slots x the biggest one.
       std::stable_sort(todo.begin(), todo.end(), [&](uint32_t a, uint32_t b) { return foot[a] > foot[b]; });
+      slog.lap("footprints + order");
       size_t free_b = 0;
       PCHECK(pool_available(&free_b));
+      slog.lap("pool_available");
       const char* eb = getenv("SVB_POA_WS_BYTES");
       const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
       // bit 2048 of the variant: the build with 2 CTAs per SM (255 registers, no spills) -- for batches with fewer clusters than
@@ -199,11 +204,13 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       pfree(d_ws, 0); d_ws = nullptr;
       pfree(d_slotoff, 0); d_slotoff = nullptr;
       PCHECK(pmalloc((void**)&d_ws, (size_t)slot_off[(size_t)slots], 0));
+      slog.lap("workspace from the pool");
       PCHECK(pmalloc((void**)&d_slotoff, (size_t)(slots + 1) * 8, 0));
       PCHECK(cudaMemcpy(d_slotoff, slot_off.data(), (size_t)(slots + 1) * 8, cudaMemcpyHostToDevice));
       PCHECK(cudaMemcpy(d_order, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice));
       PCHECK(cudaMemcpy(d_dims, dims.data(), (size_t)n_clusters * sizeof(int4), cudaMemcpyHostToDevice));
       PCHECK(cudaMemsetAsync(d_work, 0, 4, 0));
+      slog.lap("slot table + order + dims H2D");
       PoaParams P;
       memset(&P, 0, sizeof(P));
       P.seqs = d_seqs; P.seq_offs = d_soff; P.cluster_offs = d_coff; P.order = d_order; P.n = (int)todo.size();
@@ -261,11 +268,13 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       todo.swap(again);
       out->reruns += (int32_t)todo.size();
     }
+    slog.lap("kernel launches + status checks");
     PCHECK(cudaMemcpy(h_len.data(), d_len, n_clusters * 4, cudaMemcpyDeviceToHost));
     PCHECK(cudaMemcpy(h_status.data(), d_status, n_clusters * 4, cudaMemcpyDeviceToHost));
     PCHECK(cudaMemcpy(h_cons.data(), d_cons, cap_off[n_clusters], cudaMemcpyDeviceToHost));
     unsigned long long cells = 0;
     PCHECK(cudaMemcpy(&cells, d_cells, 8, cudaMemcpyDeviceToHost));
+    slog.lap("consensus D2H");
     out->cells = (int64_t)cells;
     if (d_phase) {
       unsigned long long ph[5];
