@@ -350,9 +350,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+    def timed(fn, steps, warmup, many=False):
+        """K steps between two barriers; many=True: fn(n) runs n steps itself (the two-stage pipeline) and returns their results"""
+        if many:
+            fn(warmup)
+        else:
+            for _ in range(warmup):
+                fn()
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
@@ -363,8 +367,11 @@ def run_ours(args):
         res = []
         t0 = time.perf_counter()
         ev0.record()
-        for _ in range(steps):
-            res.append(fn())
+        if many:
+            res = fn(steps)
+        else:
+            for _ in range(steps):
+                res.append(fn())
         ev1.record()
         barrier()
         wall = (time.perf_counter() - t0) * 1e3
@@ -380,12 +387,15 @@ def run_ours(args):
     class Step:
         pass
 
-    def call_side(r, reads, gather):
+    def cluster_side(r):
         st = Step()
         st.search = r
         t = time.perf_counter()
         st.cl = capi.cluster_batch(sl.alns(capi, r), dref, threads=threads, device=local)
         st.t_cluster = (time.perf_counter() - t) * 1e3
+        return st
+
+    def call_side(st, reads, gather):
         t = time.perf_counter()
         st.calls = capi.call_batch(st.cl, reads, dref, device=local)
         st.t_call = (time.perf_counter() - t) * 1e3
@@ -400,33 +410,69 @@ def run_ours(args):
     reads_dev = capi.ReadSeqs(sl.reads_t.data_ptr(), sl.seq_offs_dev, capi.SVB_SEQ_NT6, capi.SVB_MEM_DEVICE)
     reads_host = capi.ReadSeqs(sl.host4_np, sl.seq_offs_host4, capi.SVB_SEQ_BAM4, capi.SVB_MEM_HOST)
 
-    def step_resident():
+    def front_resident():
         t = time.perf_counter()
         r = idx.sfs_resident(sl.dreads, assemble=assemble)
         ts = (time.perf_counter() - t) * 1e3
-        st = call_side(r, reads_dev, gather=False)
+        st = cluster_side(r)
         st.t_search = ts
         return st
 
-    def step_e2e():
+    def front_e2e():
         t = time.perf_counter()
         r = idx.sfs_batch_bam4(sl.host4.data_ptr(), sl.seq4_offs, sl.l_qseq, assemble=assemble)
         ts = (time.perf_counter() - t) * 1e3
-        st = call_side(r, reads_host, gather=True)
+        st = cluster_side(r)
         st.t_search = ts
         return st
 
+    def step_resident():
+        return call_side(front_resident(), reads_dev, gather=False)
+
+    def step_e2e():
+        return call_side(front_e2e(), reads_host, gather=True)
+
+    # Two-stage pipeline over consecutive batches: a worker thread searches and clusters batch k + 1 while this thread
+    # calls batch k.  The library's stream 0 is the calling thread's own stream (--default-stream per-thread), so the two
+    # overlap on the device: k_poa on a config-3 batch is bound by the row chain of its biggest clusters and leaves most
+    # SMs idle for most of its time.  n fronts and n backs complete inside the timed region.
+    from concurrent.futures import ThreadPoolExecutor
+    worker = ThreadPoolExecutor(1)
+
+    def pipelined(front, reads, gather):
+        def run(n):
+            res = []
+            if n <= 0:
+                return res
+            fut = worker.submit(front)
+            for k in range(n):
+                st = fut.result()
+                if k + 1 < n:
+                    fut = worker.submit(front)
+                res.append(call_side(st, reads, gather))
+            return res
+        return run
+
     # ---- value: searched reads + reference resident in HBM
-    res, ms_dev, ms_wall, clocks = timed(step_resident, args.steps, args.warmup)
+    res_seq, ms_dev_seq, ms_wall_seq, clocks_seq = timed(step_resident, args.steps, args.warmup)
+    if args.no_pipeline:
+        res, ms_dev, ms_wall, clocks = res_seq, ms_dev_seq, ms_wall_seq, clocks_seq
+    else:
+        res, ms_dev, ms_wall, clocks = timed(pipelined(front_resident, reads_dev, False), args.steps, args.warmup, many=True)
     ms_step = ms_wall / args.steps
 
     def mean(f, rs=res):
         return float(np.mean([f(x) for x in rs]))
     last = res[-1]
     # ---- e2e: host buffers through the C ABI
-    res_e, ms_dev_e, ms_wall_e, clocks_e = timed(step_e2e, args.steps, args.warmup)
+    res_e_seq, ms_dev_e_seq, ms_wall_e_seq, clocks_e_seq = timed(step_e2e, args.steps, args.warmup)
+    if args.no_pipeline:
+        res_e, ms_dev_e, ms_wall_e, clocks_e = res_e_seq, ms_dev_e_seq, ms_wall_e_seq, clocks_e_seq
+    else:
+        res_e, ms_dev_e, ms_wall_e, clocks_e = timed(pipelined(front_e2e, reads_host, True), args.steps, args.warmup, many=True)
     ms_step_e = ms_wall_e / args.steps
-    assert np.array_equal(res_e[-1].table, last.table), "resident and host paths disagree"
+    for x in res + res_e + res_seq + res_e_seq:      # every step of every pass: the same SV table
+        assert np.array_equal(x.table, last.table), "two passes of the step disagree"
     peak, peak_src = hbm_peak()
     r0 = last.search
     search_kernel_ms = mean(lambda x: x.search.kernel_ms)
@@ -446,7 +492,7 @@ def run_ours(args):
     dom = max(kern, key=lambda k: kern[k]["ms"])
     dk = kern[dom]
     achieved = dk["achieved_GB_s"] or 0.0
-    launches = int(sum(x.search.launches + x.cl.launches + x.calls.launches for x in res + res_e))
+    launches = int(sum(x.search.launches + x.cl.launches + x.calls.launches for x in res + res_e))   # the two timed regions the line's value / e2e come from
     stages = {"search_ms": mean(lambda x: x.t_search), "cluster_ms": mean(lambda x: x.t_cluster), "call_ms": mean(lambda x: x.t_call),
               "cluster_host_sweep_ms": mean(lambda x: x.cl.host_ms), "call_host_ms": mean(lambda x: x.calls.host_ms),
               "poa_kernel_ms": kern["k_poa"]["ms"], "ksw_kernel_ms": kern["k_ksw_extd2"]["ms"], "search_kernel_ms": search_kernel_ms,
@@ -474,6 +520,12 @@ def run_ours(args):
                            "unplaced_sfs": [int(last.cl.unplaced), int(last.cl.s_unplaced), int(last.cl.e_unplaced)]},
         "parity_vs_planted": score_calls(last.table, sl.truth()),
         "stages_ms": stages,
+        "pipeline": None if args.no_pipeline else {
+            "what": "search + cluster of batch k+1 on a worker thread while this thread calls batch k (stream 0 = per-thread default stream); K of each inside the timed region; stage times are those seen while overlapped",
+            "sequential": {"value": world * sl.n / (ms_wall_seq / args.steps * 1e-3), "ms_per_step": ms_wall_seq / args.steps,
+                           "stages_ms": {"search_ms": mean(lambda x: x.t_search, res_seq), "cluster_ms": mean(lambda x: x.t_cluster, res_seq), "call_ms": mean(lambda x: x.t_call, res_seq),
+                                         "poa_kernel_ms": mean(lambda x: x.calls.poa_kernel_ms, res_seq), "search_kernel_ms": mean(lambda x: x.search.kernel_ms, res_seq)},
+                           "e2e_value": world * sl.n / (ms_wall_e_seq / args.steps * 1e-3), "e2e_ms_per_step": ms_wall_e_seq / args.steps}},
         "e2e": {"value": world * sl.n / (ms_step_e * 1e-3), "unit": "reads/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_step_e, "stages_ms": stages_e,
                 "searched_reads_per_s": world * sl.ns / (ms_step_e * 1e-3),
@@ -819,6 +871,7 @@ def main():
     ap.add_argument("--block-bytes", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config2", action="store_true", help="skip the configs[1] search-only measurement")
+    ap.add_argument("--no-pipeline", action="store_true", help="steps strictly one after the other (no overlap of batch k+1's search with batch k's call)")
     ap.add_argument("--no-rank-walk", action="store_true", help="skip the extra pure-rank-walk pass")
     ap.add_argument("--no-call-stage", action="store_true", help="skip the POA / ksw2 shapes of configs[3] / [4]")
     ap.add_argument("--full-call-stage", action="store_true", help="configs[4] at its full 1 M pairs (about a minute)")

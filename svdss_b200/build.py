@@ -10,7 +10,10 @@ LIB = os.path.join(HERE, "libsvdss_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "--expt-relaxed-constexpr",
-         "-Xptxas", "-v", "-ccbin", "/usr/bin/g++"]
+         "-Xptxas", "-v", "-ccbin", "/usr/bin/g++",
+         # stream 0 in the library = the calling thread's own default stream: two host threads (one searching batch k + 1,
+         # one calling batch k; a BAM reader inflating ahead) overlap on the device instead of queueing on the legacy stream
+         "--default-stream", "per-thread"]
 
 
 def sources():
@@ -29,6 +32,7 @@ def stale():
     deps = sources() + host_sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     deps.append(os.path.join(HERE, "host", "rld.hpp"))
     deps.append(os.path.join(HERE, "..", "include", "svdss_b200.h"))
+    deps.append(os.path.abspath(__file__))          # the compiler flags live here
     return any(os.path.getmtime(d) > t for d in deps)
 
 
