@@ -140,6 +140,29 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       }
       variant = (chain * 1.0e-6 > cells_est / 37e9) ? 4096 + 2048 + 455 : 455;
     }
+    if (slog.on) {
+      // SVB_STAGE_STATS: how the row chains (reads x nodes) of the batch are spread -- the config-3 slice of bench.py has its
+      // longest chain at 101 k rows and 265 x that in total: with 296 CTA slots the hand-out (biggest first) packs well and the
+      // launch is bound by row throughput (1.24 us per row and CTA at 2 CTAs per SM; 1.03 alone, 2.06 at 3 per SM), not by
+      // the longest chain (profiles/r03a_poa_occupancy.txt)
+      double chain = 0, rows = 0;
+      for (int64_t c = 0; c < n_clusters; ++c) {
+        const Shape& s = shp[c];
+        if (s.nreads < 2) continue;
+        const double r = (double)(s.nreads - 1) * (double)s.lmax;
+        chain = std::max(chain, r); rows += r;
+      }
+      int64_t cnt[10] = {0}; double sum[10] = {0};
+      for (int64_t c = 0; c < n_clusters; ++c) {
+        const Shape& s = shp[c];
+        if (s.nreads < 2) continue;
+        const double r = (double)(s.nreads - 1) * (double)s.lmax;
+        const int b = std::min(9, (int)(10.0 * r / std::max(chain, 1.0)));
+        cnt[b]++; sum[b] += r;
+      }
+      for (int b = 0; b < 10; ++b) fprintf(stderr, "[svb-stage] poa: chains of %d0-%d0 %% of the longest: %lld clusters, %.1f %% of all rows\n", b, b + 1, (long long)cnt[b], 100.0 * sum[b] / std::max(rows, 1.0));
+      fprintf(stderr, "[svb-stage] poa: row chains: longest %.0f, all %.0f (%.1f x)\n", chain, rows, rows / std::max(chain, 1.0));
+    }
     // pass 0: heuristic capacities; pass 1: worst-case capacities for the clusters that overflowed
     std::vector<uint32_t> todo((size_t)n_clusters);
     for (int64_t c = 0; c < n_clusters; ++c) todo[c] = (uint32_t)c;
@@ -183,7 +206,10 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       const int64_t budget = eb ? atoll(eb) : (int64_t)(free_b * 0.8);
       // bit 2048 of the variant: the build with 2 CTAs per SM (255 registers, no spills) -- for batches with fewer clusters than
       // warp slots, where the time is the chain of rows of the biggest cluster and occupancy buys nothing
-      const int mb = (variant & 2048) ? 2 : SVB_POA_MINB;
+      int mb = (variant & 8192) ? 3 : (variant & 2048) ? 2 : SVB_POA_MINB;   // bit 8192: 3 CTAs per SM (168 registers), CTA rows only
+      // experiment knob: fewer resident CTAs per SM than the build allows (the launch pads its shared memory request)
+      int ctas_per_sm = 0;
+      if (const char* ec = getenv("SVB_POA_CTAS_PER_SM")) { ctas_per_sm = atoi(ec); if (ctas_per_sm >= 1 && ctas_per_sm < mb) mb = ctas_per_sm; else ctas_per_sm = 0; }
       const bool cta = (variant & 4096) != 0;          // bit 4096: a CTA (four warps) per cluster, the DP rows cut across its warps
       const int per_cta = cta ? 1 : 4;                 // clusters in flight per CTA
       int64_t slots = std::min<int64_t>((int64_t)todo.size(), (int64_t)sms * per_cta * mb);
@@ -224,6 +250,8 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
       P.swcap = std::min(wmax, 128);
       const size_t smem = cta ? ((size_t)6 * (size_t)P.swcap + 9 * 4 * 2 + 8) * sizeof(int)
                               : (variant & POA_V_SMEM) ? (size_t)4 * 6 * (size_t)P.swcap * sizeof(int) : 0;
+      size_t smem_pad = smem;
+      if (ctas_per_sm) smem_pad = std::max(smem, (size_t)(227 * 1024) / (size_t)(ctas_per_sm + 1) + 1024);   // ctas_per_sm fit, one more does not
       const unsigned grid = (unsigned)(slots / per_cta);
 #define POA_LAUNCH(VV)                                                                                              \
   case (VV):                                                                                                        \
@@ -240,9 +268,13 @@ int svb::poa_batch_impl(const uint8_t* seqs, int seqs_mem, const int64_t* seq_of
           if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<455, 32, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           k_poa<455, 32, 4, 4><<<grid, 128, smem>>>(P);
           break;
+        case 8192 + 4096 + 455:
+          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<455, 32, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_poa<455, 32, 3, 4><<<grid, 128, smem>>>(P);
+          break;
         case 4096 + 2048 + 455:
-          if (smem > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<455, 32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_poa<455, 32, 2, 4><<<grid, 128, smem>>>(P);
+          if (smem_pad > 48 * 1024) PCHECK(cudaFuncSetAttribute(k_poa<455, 32, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pad));
+          k_poa<455, 32, 2, 4><<<grid, 128, smem_pad>>>(P);
           break;
         default:
           set_error("SVB_POA_VARIANT=%d is not built (0 = round 1, 455 = a warp per cluster, 3527 = the same with four column groups per step at 2 CTAs per SM, 4551 / 6599 = a CTA per cluster at 4 / 2 CTAs per SM)", variant);

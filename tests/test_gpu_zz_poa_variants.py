@@ -25,7 +25,7 @@ clusters.append([rng.integers(0, 4, size=int(rng.integers(150, 260))).astype(np.
 os.environ["SVB_POA_VARIANT"] = "0"
 a = capi.poa_batch(clusters)
 times = ["0: %.2f" % a.kernel_ms]
-for variant, group in ((455, 32), (3527, 32), (4551, 32), (6599, 32)):
+for variant, group in ((455, 32), (3527, 32), (4551, 32), (6599, 32), (12743, 32)):
     os.environ["SVB_POA_VARIANT"] = str(variant)
     b = capi.poa_batch(clusters)
     assert a.cells == b.cells, (variant, a.cells, b.cells)
