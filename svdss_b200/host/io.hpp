@@ -435,6 +435,7 @@ struct BamRecord {
   std::vector<uint8_t> nt6;   // decoded sequence, nt6 codes (ping_pong.cpp:90-94)
   std::vector<uint32_t> cigar; // len<<4 | op (MIDNSHP=X), as stored
   std::vector<uint8_t> seq4;   // 4-bit packed sequence, as stored (Clusterer decodes it on demand)
+  const uint8_t* seq4_view = nullptr;   // view mode (BamReader::want_view): the packed sequence where it lies in the window; valid until the next next()
   bool has_xf = false, has_hp = false;
   bool cg_cigar = false;       // `cigar` came from the CG:B,I tag of a record with more than 65535 ops
   size_t cg_off = 0, cg_len = 0;   // where that tag sits in `raw` (offset of its two-letter name, bytes incl. name and type)
@@ -478,6 +479,8 @@ class BamReader {
   const std::vector<std::string>& ref_names() const { return ref_names_; }
   // alignment mode (`call`): keep CIGAR + packed sequence instead of decoding nt6 codes
   void want_alignment(bool on) { want_align_ = on; }
+  // view mode (`search`): no copy of the packed sequence at all -- BamRecord::seq4_view points into the inflated window
+  void want_view(bool on) { want_view_ = on; if (on) want_align_ = true; }
   // raw mode (`smooth`): additionally keep the whole record body
   void want_raw(bool on) { want_raw_ = on; if (on) want_align_ = true; }
   const std::string& header_text() const { return text_; }
@@ -514,7 +517,9 @@ class BamReader {
     if (r.l_qseq < 0 || o + seq_bytes + (size_t)r.l_qseq > (size_t)bs) return -1;
     static const char nt16[] = "=ACMGRSVTWYHKDBN";  // htslib seq_nt16_str
     const uint8_t* t6 = nt6_table();
-    if (want_align_) {
+    if (want_view_) {
+      r.seq4_view = p + o;            // `search` copies only the reads it submits (1 in 9 of a smoothed BAM)
+    } else if (want_align_) {
       r.seq4.assign(p + o, p + o + seq_bytes);
     } else {
       r.nt6.resize((size_t)r.l_qseq);
@@ -571,7 +576,7 @@ class BamReader {
   }
  private:
   BgzfSource src_;
-  bool ok_ = false, want_align_ = false, want_raw_ = false;
+  bool ok_ = false, want_align_ = false, want_raw_ = false, want_view_ = false;
   std::string text_;
   std::vector<std::string> ref_names_;
   std::vector<int32_t> ref_lens_;
