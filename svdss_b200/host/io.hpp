@@ -203,7 +203,7 @@ class BgzfSource {
   // device: pinned buffers of a fixed size, pinned once (pinning costs ~1 s per GB here); a window ends where its
   // payload would not fit and the rest of the read waits in carry_
   size_t payload_limit(size_t window) const {
-    size_t cap = gpu_ >= 0 ? std::max<size_t>(window * 8, (size_t)1 << 20) : ~(size_t)0;
+    size_t cap = gpu_ >= 0 ? std::max<size_t>(window * 6, (size_t)1 << 20) : ~(size_t)0;   // BAM inflates 3-6x
     if (const char* e = getenv("SVB_BGZF_PAYLOAD")) { const long long v = atoll(e); if (v >= (1 << 16)) cap = (size_t)v; }   // tests: the limit on the host path too
     return cap;
   }
@@ -217,7 +217,7 @@ class BgzfSource {
     if (gpu_ >= 0) {
       const auto p0 = Clock::now();
       in.pin(true);
-      if (!in.reserve(2 * window + ((size_t)1 << 20))) return false;
+      if (!in.reserve(window + ((size_t)4 << 20))) return false;   // a longer carry (payload limit hit early) pins a bigger buffer once
       t_pin_ += since(p0);
     }
     bool starved = false;
