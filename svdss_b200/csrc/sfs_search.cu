@@ -1913,10 +1913,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
   int grid = 0, cfgG = 0;
   SVB_TRY(pick_cfg(d.G, &cfgG));
   const int tma_minb = 9;
-  const int tail_minb = 6;   // the tail kernel carries the sprint: more registers, 18 warps per SM
-  // experiment knob: the tail kernel built for 8 CTAs per SM (80 registers, 24 warps per SM)
-  const char* etm = getenv("SVB_SEARCH_TAIL_MINB");
-  const bool tail8 = etm && atoi(etm) == 8;
+  const int tail_minb = 6;   // the tail kernel carries the sprint: more registers, 18 warps per SM (8 CTAs per SM = 80 registers with spills: 27.3 vs 27.5 ms on the config-3 step, 70.2 vs 69.8 ms on configs[1] -- occupancy is not what bounds it)
   int tail_grid = 0;
   const char* e2p = getenv("SVB_SEARCH_TAIL");   // SVB_SEARCH_TAIL=0: one kernel, every walk finished where it started
   const bool two_phase = !(e2p && *e2p == '0');
@@ -1927,8 +1924,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
       SVB_TRY(persistent_grid(k_sfs_search_mop<tma_minb, false, true>, TMA_WARPS * 32, d.device, &grid2));
       grid = std::min(grid, grid2);
     }
-    if (tail8) SVB_TRY(persistent_grid(k_sfs_search_mop<8, true>, TMA_WARPS * 32, d.device, &tail_grid));
-    else SVB_TRY(persistent_grid(k_sfs_search_mop<tail_minb, true>, TMA_WARPS * 32, d.device, &tail_grid));
+    SVB_TRY(persistent_grid(k_sfs_search_mop<tail_minb, true>, TMA_WARPS * 32, d.device, &tail_grid));
   } else if (cfgG == 0) {
     SVB_TRY(persistent_grid(k_sfs_search_tma<tma_minb, 0>, TMA_WARPS * 32, d.device, &grid));
   } else if (cfgG == -1) {
@@ -1978,8 +1974,7 @@ static int run_search(const IndexDev& d, const svb_reads* R, int overlap, int as
       if (two_phase) {
         SearchParams Q = P;
         Q.work = S.d_ctr + 12; Q.ready = nullptr; Q.n_unpack = 0; Q.dry = nullptr;
-        if (tail8) k_sfs_search_mop<8, true><<<tail_grid, TMA_WARPS * 32, 0, st>>>(Q);
-        else k_sfs_search_mop<tail_minb, true><<<tail_grid, TMA_WARPS * 32, 0, st>>>(Q);
+        k_sfs_search_mop<tail_minb, true><<<tail_grid, TMA_WARPS * 32, 0, st>>>(Q);
         out->launches += 1;
       }
     } else if (cfgG == 0) {
