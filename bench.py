@@ -454,22 +454,36 @@ def run_ours(args):
         return run
 
     # ---- value: searched reads + reference resident in HBM
+    def pick_mode(step, pipe):
+        """Sequential or pipelined?  Decided BEFORE the timed passes by a short probe of both (max over ranks, so every rank
+        decides alike): at 8 ranks on one 32-core host the end-to-end leg loses to the contention for host memory what the
+        overlap hides (25.3 vs 28.8 M records/s), on one or two ranks it gains 7-8 %."""
+        if args.no_pipeline:
+            return False, None
+        _, _, w_seq, _ = timed(step, 3, 1)
+        _, _, w_pipe, _ = timed(pipe, 3, 1, many=True)
+        return w_pipe < w_seq, {"sequential_ms_per_step": w_seq / 3, "pipelined_ms_per_step": w_pipe / 3}
+
+    pipe_res = pipelined(front_resident, reads_dev, False)
+    use_pipe, probe = pick_mode(step_resident, pipe_res)
     res_seq, ms_dev_seq, ms_wall_seq, clocks_seq = timed(step_resident, args.steps, args.warmup)
-    if args.no_pipeline:
+    if not use_pipe:
         res, ms_dev, ms_wall, clocks = res_seq, ms_dev_seq, ms_wall_seq, clocks_seq
     else:
-        res, ms_dev, ms_wall, clocks = timed(pipelined(front_resident, reads_dev, False), args.steps, args.warmup, many=True)
+        res, ms_dev, ms_wall, clocks = timed(pipe_res, args.steps, args.warmup, many=True)
     ms_step = ms_wall / args.steps
 
     def mean(f, rs=res):
         return float(np.mean([f(x) for x in rs]))
     last = res[-1]
     # ---- e2e: host buffers through the C ABI
+    pipe_e = pipelined(front_e2e, reads_host, True)
+    use_pipe_e, probe_e = pick_mode(step_e2e, pipe_e)
     res_e_seq, ms_dev_e_seq, ms_wall_e_seq, clocks_e_seq = timed(step_e2e, args.steps, args.warmup)
-    if args.no_pipeline:
+    if not use_pipe_e:
         res_e, ms_dev_e, ms_wall_e, clocks_e = res_e_seq, ms_dev_e_seq, ms_wall_e_seq, clocks_e_seq
     else:
-        res_e, ms_dev_e, ms_wall_e, clocks_e = timed(pipelined(front_e2e, reads_host, True), args.steps, args.warmup, many=True)
+        res_e, ms_dev_e, ms_wall_e, clocks_e = timed(pipe_e, args.steps, args.warmup, many=True)
     ms_step_e = ms_wall_e / args.steps
     for x in res + res_e + res_seq + res_e_seq:      # every step of every pass: the same SV table
         assert np.array_equal(x.table, last.table), "two passes of the step disagree"
@@ -522,6 +536,8 @@ def run_ours(args):
         "stages_ms": stages,
         "pipeline": None if args.no_pipeline else {
             "what": "search + cluster of batch k+1 on a worker thread while this thread calls batch k (stream 0 = per-thread default stream); K of each inside the timed region; stage times are those seen while overlapped",
+            "value_pipelined": bool(use_pipe), "e2e_pipelined": bool(use_pipe_e),
+            "chosen_by": "a probe of 3 steps of either mode before the timed passes (max over ranks)", "probe_value": probe, "probe_e2e": probe_e,
             "sequential": {"value": world * sl.n / (ms_wall_seq / args.steps * 1e-3), "ms_per_step": ms_wall_seq / args.steps,
                            "stages_ms": {"search_ms": mean(lambda x: x.t_search, res_seq), "cluster_ms": mean(lambda x: x.t_cluster, res_seq), "call_ms": mean(lambda x: x.t_call, res_seq),
                                          "poa_kernel_ms": mean(lambda x: x.calls.poa_kernel_ms, res_seq), "search_kernel_ms": mean(lambda x: x.search.kernel_ms, res_seq)},
