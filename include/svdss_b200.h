@@ -176,6 +176,41 @@ SVB_API int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_offs 
 SVB_API void* svb_host_alloc_pinned(size_t bytes);
 SVB_API void svb_host_free_pinned(void* p);
 
+/* ---- the BAM loader of `search` on the device (PingPong::load_batch_bam, ping_pong.cpp:53-131, with the filters of
+ * :66-79 and :196-203).  The caller reads the file and finds the BGZF members, as for svb_bgzf_inflate_device; a
+ * stream inflates window after window into HBM, walks the records where they lie (the unfinished record at the end of
+ * a window is completed by the next), parses core fields and the XF / HP tags, and decodes the bases of the reads
+ * that will be searched (nt16 -> nt6, :88-94) into a device batch.  Names, flags and tags come back; bases never do. */
+typedef struct svb_bamstream svb_bamstream_t;
+typedef struct {
+  int64_t n;                 /* records completed by this window, in file order                                    */
+  const uint16_t* flag;      /* bam1_core_t::flag                                                                   */
+  const int32_t* tid;        /* ::tid (the reference exits on a kept record with tid < 0, ping_pong.cpp:76-79)      */
+  const int32_t* l_qseq;     /* ::l_qseq                                                                            */
+  const int32_t* xf;         /* XF:i or 0 (bam_aux_get / bam_aux2i, :196-198)                                       */
+  const int32_t* hp;         /* HP:i or 0 (:199-201)                                                                */
+  const uint8_t* state;      /* 0 dropped (unmapped / secondary / supplementary, :66-69); 3 dropped for l_qseq < 100
+                              * (:70-75); 1 kept, not searched (XF != 0 with the putative filter, :202); 2 searched:
+                              * its bases were appended to the device batch                                         */
+  const int64_t* name_offs;  /* n + 1: qname of record i = names[name_offs[i], name_offs[i+1]) (empty for dropped)  */
+  const char* names;
+  int64_t batch_reads, batch_bases;   /* the device batch after this window                                         */
+  int64_t h2d_bytes, d2h_bytes;
+} svb_bam_recs_t;
+SVB_API int svb_bamstream_open(int device, int putative, svb_bamstream_t** out);
+/* One window: n_members BGZF members as svb_bgzf_inflate_device takes them (host buffers).  skip_bytes (first call
+ * only): inflated bytes to pass over before the first record = the BAM header, which the caller has parsed.
+ * recs points into memory owned by the stream, valid until the next call on it. */
+SVB_API int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, const int64_t* in_offs /* n_members+1 */,
+                                 const int64_t* out_offs /* n_members+1 */, int64_t n_members, int64_t skip_bytes,
+                                 svb_bam_recs_t* recs);
+/* bytes of an unfinished record left behind the last window: not 0 at the end of the file = truncated BAM */
+SVB_API int64_t svb_bamstream_pending_bytes(const svb_bamstream_t* s);
+/* svb_sfs_resident over the reads batched so far (read r of the result = the r-th record of state 2 since the last
+ * search); empties the batch. */
+SVB_API int svb_bamstream_search(svb_bamstream_t* s, const svb_index_t* idx, int overlap, int assemble, svb_sfs_out_t* out);
+SVB_API void svb_bamstream_close(svb_bamstream_t* s);
+
 /* Same search with the batch already resident in HBM (kernel-only measurement; multi-batch reuse). */
 SVB_API int svb_reads_upload(const uint8_t* nt6_concat, const int64_t* offs, int64_t n_reads,
                              int mem, int device, svb_reads_t** out);

@@ -1,0 +1,400 @@
+// svb_bamstream_*: the BAM loader of `search` (PingPong::load_batch_bam, ping_pong.cpp:53-131, and the filters of
+// :66-79,196-203) on the device.  The host only reads the file and finds the BGZF members (host/io.hpp); a window of
+// members is inflated into HBM (k_bgzf_inflate_warp), the records are walked where they lie (a record may start in one
+// window and end in the next: the unfinished tail is carried over), every record is parsed by a thread (core fields,
+// aux walk for XF / HP), and the bases of the reads that will be searched are decoded nt16 -> nt6 straight into the
+// device batch svb_sfs_resident runs on.  What crosses PCIe: the compressed file one way, names / flags / tags the other.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace svb {
+
+int check_device(int device);
+void launch_inflate(const uint8_t* d_in, const int64_t* d_io, const int64_t* d_oo, int64_t n_members, uint8_t* d_out, int32_t* d_st, int device,
+                    cudaStream_t sq);   // bgzf_inflate.cu
+
+// record offsets of a window: one thread follows the block_size fields (each depends on the one before)
+__global__ void k_bam_walk(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t* __restrict__ rec_off, int64_t cap,
+                           int64_t* __restrict__ res) {
+  int64_t p = start, n = 0, err = 0;
+  while (p + 4 <= total && n < cap) {
+    const uint32_t u = (uint32_t)win[p] | ((uint32_t)win[p + 1] << 8) | ((uint32_t)win[p + 2] << 16) | ((uint32_t)win[p + 3] << 24);
+    const int32_t bs = (int32_t)u;
+    if (bs < 32) { err = 1; break; }
+    if (p + 4 + (int64_t)bs > total) break;
+    rec_off[n++] = p + 4;
+    p += 4 + (int64_t)bs;
+  }
+  res[0] = n; res[1] = p; res[2] = err;
+}
+
+struct BamMeta {   // per record, device and host
+  int32_t tid, l_qseq, xf, hp;
+  uint16_t flag;
+  uint8_t state;     // 0 dropped by the flag filter, 3 dropped for l_qseq < 100, 1 kept but not searched, 2 searched
+  uint8_t name_len;  // without the NUL
+};
+
+__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return ld16(p) | (ld16(p + 2) << 16); }
+
+// one thread per record: BAM spec 4.2 core fields, then the aux walk host/io.hpp's BamReader::next does
+__global__ void k_bam_parse(const uint8_t* __restrict__ win, const int64_t* __restrict__ rec_off, int64_t n, int putative,
+                            BamMeta* __restrict__ meta, int64_t* __restrict__ seq_off, int* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* p = win + rec_off[i];
+  const int64_t bs = (int64_t)(int32_t)ld32(p - 4);
+  BamMeta m;
+  m.tid = (int32_t)ld32(p);
+  const unsigned l_read_name = p[8];
+  const unsigned n_cigar = ld16(p + 12);
+  m.flag = (uint16_t)ld16(p + 14);
+  m.l_qseq = (int32_t)ld32(p + 16);
+  m.xf = 0; m.hp = 0;
+  m.name_len = (uint8_t)(l_read_name ? l_read_name - 1 : 0);
+  int64_t o = 32 + (int64_t)l_read_name + 4 * (int64_t)n_cigar;
+  const int64_t seq_bytes = ((int64_t)m.l_qseq + 1) / 2;
+  bool bad = m.l_qseq < 0 || o > bs || o + seq_bytes + (int64_t)m.l_qseq > bs;
+  seq_off[i] = rec_off[i] + o;
+  bool has_xf = false;
+  if (!bad) {
+    o += seq_bytes + m.l_qseq;
+    while (o + 3 <= bs) {
+      const char t0 = (char)p[o], t1 = (char)p[o + 1], ty = (char)p[o + 2];
+      o += 3;
+      int64_t iv = 0;
+      bool is_int = false;
+      switch (ty) {
+        case 'A': o += 1; break;
+        case 'c': iv = (int8_t)p[o]; is_int = true; o += 1; break;
+        case 'C': iv = p[o]; is_int = true; o += 1; break;
+        case 's': iv = (int16_t)ld16(p + o); is_int = true; o += 2; break;
+        case 'S': iv = ld16(p + o); is_int = true; o += 2; break;
+        case 'i': iv = (int32_t)ld32(p + o); is_int = true; o += 4; break;
+        case 'I': iv = ld32(p + o); is_int = true; o += 4; break;
+        case 'f': o += 4; break;
+        case 'd': o += 8; break;
+        case 'Z': case 'H': while (o < bs && p[o]) ++o; ++o; break;
+        case 'B': {
+          if (o + 5 > bs) { bad = true; break; }
+          const char st = (char)p[o];
+          const int32_t cnt = (int32_t)ld32(p + o + 1);
+          const int64_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+          const int64_t bytes = es * (int64_t)(cnt < 0 ? 0 : cnt);
+          if (o + 5 + bytes > bs) { bad = true; break; }
+          o += 5 + bytes;
+          break;
+        }
+        default: bad = true; break;
+      }
+      if (bad || o > bs) { bad = true; break; }
+      if (is_int && t0 == 'X' && t1 == 'F') { has_xf = true; m.xf = (int32_t)iv; }
+      if (is_int && t0 == 'H' && t1 == 'P') m.hp = (int32_t)iv;
+    }
+  }
+  if (bad) { atomicExch(err, 1); m.state = 0; m.name_len = 0; }
+  else if (m.flag & (0x4 | 0x800 | 0x100)) m.state = 0;                 // ping_pong.cpp:66-69
+  else if (m.l_qseq < 100) m.state = 3;                                  // :70-75
+  else m.state = (putative && has_xf && m.xf != 0) ? 1 : 2;              // :196-203
+  if (m.state == 0 || m.state == 3) m.name_len = 0;   // the host hears about them (a warning per short record) but needs no name
+  meta[i] = m;
+}
+
+// exclusive sums over the records of a window: name bytes of the records the host hears about, bases and count of the searched ones
+struct BamSums { long long names, bases, reads; };
+__global__ void __launch_bounds__(1024) k_bam_scan(const BamMeta* __restrict__ meta, int64_t n, int64_t* __restrict__ name_off,
+                                                   int64_t* __restrict__ base_off, int64_t* __restrict__ rank, BamSums* __restrict__ tot) {
+  __shared__ long long sh[3][32];
+  __shared__ long long carry[3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x < 3) carry[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    long long v[3] = {0, 0, 0};
+    if (i < n) {
+      const BamMeta m = meta[i];
+      v[0] = m.name_len;
+      if (m.state == 2) { v[1] = m.l_qseq; v[2] = 1; }
+    }
+    long long inc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      long long x = v[k];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+      inc[k] = x;
+      if (lane == 31) sh[k][wid] = x;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        long long x = sh[k][lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        sh[k][lane] = x;   // inclusive over the warps
+      }
+    }
+    __syncthreads();
+    long long pre[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pre[k] = carry[k] + (wid ? sh[k][wid - 1] : 0) + inc[k] - v[k];
+    if (i < n) { name_off[i] = pre[0]; base_off[i] = pre[1]; rank[i] = pre[2]; }
+    __syncthreads();
+    if (threadIdx.x < 3) carry[threadIdx.x] += sh[threadIdx.x][31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { tot->names = carry[0]; tot->bases = carry[1]; tot->reads = carry[2]; name_off[n] = carry[0]; }
+}
+
+// a CTA per record: its name to the names blob; if it is searched, its bases decoded into the batch
+// (ping_pong.cpp:88-94: seq_nt16_str, then seq_nt6_table -- A C G T -> 1 2 3 4, everything else 5)
+__global__ void __launch_bounds__(128) k_bam_gather(const uint8_t* __restrict__ win, const int64_t* __restrict__ rec_off, const int64_t* __restrict__ seq_off,
+                                                    const BamMeta* __restrict__ meta, const int64_t* __restrict__ name_off,
+                                                    const int64_t* __restrict__ base_off, const int64_t* __restrict__ rank, char* __restrict__ names,
+                                                    uint8_t* __restrict__ batch, int64_t* __restrict__ batch_offs, int64_t batch_reads,
+                                                    int64_t batch_bases) {
+  const int64_t i = blockIdx.x;
+  const BamMeta m = meta[i];
+  if (m.state == 0 || m.state == 3) return;
+  const uint8_t* name = win + rec_off[i] + 32;
+  for (int k = threadIdx.x; k < m.name_len; k += blockDim.x) names[name_off[i] + k] = (char)name[k];
+  if (m.state != 2) return;
+  const uint8_t* s = win + seq_off[i];
+  uint8_t* d = batch + batch_bases + base_off[i];
+  for (int k = threadIdx.x; k < m.l_qseq; k += blockDim.x) {
+    const uint8_t b = s[k >> 1];
+    const unsigned c = (k & 1) ? (b & 0xfu) : (b >> 4);
+    d[k] = c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 5;
+  }
+  if (threadIdx.x == 0) batch_offs[batch_reads + rank[i] + 1] = batch_bases + base_off[i] + m.l_qseq;
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+namespace {
+
+// grow-only device buffer from the stream-ordered pool
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t need(size_t bytes, size_t keep = 0) {
+    if (bytes <= cap) return cudaSuccess;
+    const size_t want = std::max(bytes, cap + cap / 2);
+    void* q = nullptr;
+    cudaError_t e = pmalloc(&q, want, 0);
+    if (e != cudaSuccess) return e;
+    if (keep && p) e = cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, 0);
+    pfree(p, 0);
+    p = q; cap = want;
+    return e;
+  }
+  void release() { pfree(p, 0); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct svb_bamstream {
+  int device = 0;
+  int putative = 1;
+  int64_t skip_left = 0;       // bytes of the BAM header not yet passed
+  bool skip_set = false;
+  int64_t carry = 0;           // bytes of an unfinished record at the front of win
+  DevBuf comp, io, oo, st, win, rec_off, seq_off, meta, name_off, base_off, rank, names, sums, res, err;
+  DevBuf batch, batch_offs;
+  int64_t batch_reads = 0, batch_bases = 0;
+  // host copies handed to the caller, valid until the next call
+  std::vector<BamMeta> h_meta;
+  std::vector<uint16_t> flag;
+  std::vector<int32_t> tid, l_qseq, xf, hp;
+  std::vector<uint8_t> state;
+  std::vector<int64_t> h_name_off;
+  std::vector<char> h_names;
+};
+
+extern "C" int svb_bamstream_open(int device, int putative, svb_bamstream_t** out) {
+  if (!out) { set_error("svb_bamstream_open: null out"); return SVB_EINVAL; }
+  SVB_TRY(check_device(device));
+  svb_bamstream* s = new svb_bamstream();
+  s->device = device;
+  s->putative = putative ? 1 : 0;
+  *out = s;
+  return SVB_OK;
+}
+
+extern "C" void svb_bamstream_close(svb_bamstream_t* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (DevBuf* b : {&s->comp, &s->io, &s->oo, &s->st, &s->win, &s->rec_off, &s->seq_off, &s->meta, &s->name_off, &s->base_off, &s->rank, &s->names,
+                    &s->sums, &s->res, &s->err, &s->batch, &s->batch_offs})
+    b->release();
+  cudaStreamSynchronize(0);
+  delete s;
+}
+
+extern "C" int64_t svb_bamstream_pending_bytes(const svb_bamstream_t* s) { return s ? s->carry : 0; }
+
+extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, const int64_t* in_offs, const int64_t* out_offs, int64_t n_members,
+                                    int64_t skip_bytes, svb_bam_recs_t* recs) {
+  if (!s || !recs || !in_offs || !out_offs || n_members < 0 || n_members > 0x7fffffff) { set_error("svb_bamstream_window: bad arguments"); return SVB_EINVAL; }
+  memset(recs, 0, sizeof(*recs));
+  SVB_TRY(check_device(s->device));
+  if (!s->skip_set) { s->skip_left = skip_bytes < 0 ? 0 : skip_bytes; s->skip_set = true; }
+  const int64_t in_total = n_members ? in_offs[n_members] : 0, out_total = n_members ? out_offs[n_members] : 0;
+  if (n_members && (in_offs[0] != 0 || out_offs[0] != 0 || in_total < 0 || out_total < 0 || (in_total > 0 && !comp))) {
+    set_error("svb_bamstream_window: offsets must start at 0"); return SVB_EINVAL;
+  }
+  for (int64_t m = 0; m < n_members; ++m)
+    if (in_offs[m + 1] < in_offs[m] || out_offs[m + 1] < out_offs[m] || out_offs[m + 1] - out_offs[m] > 65536) {
+      set_error("svb_bamstream_window: member %lld: offsets not ascending or more than 64 KiB of payload", (long long)m); return SVB_EINVAL;
+    }
+  int rc = SVB_OK;
+  auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == SVB_OK) { set_error("svb_bamstream_window: %s", cudaGetErrorString(e)); rc = SVB_ECUDA; } };
+  // ---- inflate behind the carried tail
+  const int64_t total = s->carry + out_total;
+  fail(s->win.need((size_t)total + 64, (size_t)s->carry));
+  if (n_members && rc == SVB_OK) {
+    fail(s->comp.need((size_t)in_total + 16));
+    fail(s->io.need((size_t)(n_members + 1) * 8));
+    fail(s->oo.need((size_t)(n_members + 1) * 8));
+    fail(s->st.need((size_t)n_members * 4));
+    if (rc == SVB_OK) {
+      if (in_total) fail(cudaMemcpyAsync(s->comp.p, comp, (size_t)in_total, cudaMemcpyHostToDevice, 0));
+      fail(cudaMemcpyAsync(s->io.p, in_offs, (size_t)(n_members + 1) * 8, cudaMemcpyHostToDevice, 0));
+      fail(cudaMemcpyAsync(s->oo.p, out_offs, (size_t)(n_members + 1) * 8, cudaMemcpyHostToDevice, 0));
+      launch_inflate(static_cast<const uint8_t*>(s->comp.p), static_cast<const int64_t*>(s->io.p), static_cast<const int64_t*>(s->oo.p), n_members,
+                     static_cast<uint8_t*>(s->win.p) + s->carry, static_cast<int32_t*>(s->st.p), s->device, 0);
+      fail(cudaGetLastError());
+      std::vector<int32_t> st((size_t)n_members);
+      fail(cudaMemcpy(st.data(), s->st.p, (size_t)n_members * 4, cudaMemcpyDeviceToHost));
+      if (rc == SVB_OK)
+        for (int64_t m = 0; m < n_members; ++m)
+          if (st[(size_t)m] != 0) { set_error("BGZF member %lld does not inflate (code %d): truncated or corrupt file", (long long)m, st[(size_t)m]); return SVB_EIO; }
+    }
+  }
+  if (rc != SVB_OK) return rc;
+  // ---- the BAM header (its length comes from the caller, who parsed it) is passed over
+  int64_t start = 0;
+  if (s->skip_left > 0) {
+    start = std::min<int64_t>(s->skip_left, total);
+    s->skip_left -= start;
+  }
+  // ---- walk the records
+  const int64_t cap = std::max<int64_t>(1024, (total - start) / 36 + 1);   // a record is at least 36 bytes
+  fail(s->rec_off.need((size_t)cap * 8));
+  fail(s->res.need(3 * 8));
+  int64_t res[3] = {0, start, 0};
+  if (rc == SVB_OK) {
+    k_bam_walk<<<1, 1>>>(static_cast<const uint8_t*>(s->win.p), start, total, static_cast<int64_t*>(s->rec_off.p), cap, static_cast<int64_t*>(s->res.p));
+    fail(cudaGetLastError());
+    fail(cudaMemcpy(res, s->res.p, sizeof(res), cudaMemcpyDeviceToHost));
+  }
+  if (rc != SVB_OK) return rc;
+  if (res[2]) { set_error("BAM record with a block_size below 32: corrupt file"); return SVB_EIO; }
+  const int64_t n = res[0], p_end = res[1];
+  // ---- parse, lay out, gather
+  BamSums sums = {0, 0, 0};
+  if (n) {
+    fail(s->seq_off.need((size_t)n * 8));
+    fail(s->meta.need((size_t)n * sizeof(BamMeta)));
+    fail(s->name_off.need((size_t)(n + 1) * 8));
+    fail(s->base_off.need((size_t)n * 8));
+    fail(s->rank.need((size_t)n * 8));
+    fail(s->sums.need(sizeof(BamSums)));
+    fail(s->err.need(4));
+    if (rc == SVB_OK) {
+      fail(cudaMemsetAsync(s->err.p, 0, 4, 0));
+      k_bam_parse<<<(unsigned)((n + 127) / 128), 128>>>(static_cast<const uint8_t*>(s->win.p), static_cast<const int64_t*>(s->rec_off.p), n, s->putative,
+                                                          static_cast<BamMeta*>(s->meta.p), static_cast<int64_t*>(s->seq_off.p), static_cast<int*>(s->err.p));
+      k_bam_scan<<<1, 1024>>>(static_cast<const BamMeta*>(s->meta.p), n, static_cast<int64_t*>(s->name_off.p), static_cast<int64_t*>(s->base_off.p),
+                              static_cast<int64_t*>(s->rank.p), static_cast<BamSums*>(s->sums.p));
+      fail(cudaGetLastError());
+      int err = 0;
+      fail(cudaMemcpy(&err, s->err.p, 4, cudaMemcpyDeviceToHost));
+      fail(cudaMemcpy(&sums, s->sums.p, sizeof(sums), cudaMemcpyDeviceToHost));
+      if (rc == SVB_OK && err) { set_error("malformed BAM record (field lengths or aux tags run past its block_size)"); return SVB_EIO; }
+    }
+    if (rc == SVB_OK) {
+      fail(s->names.need((size_t)std::max<long long>(sums.names, 1)));
+      // the batch keeps what earlier windows put there; 64 readable bytes behind the last base for the search kernels
+      fail(s->batch.need((size_t)(s->batch_bases + sums.bases) + 128, (size_t)s->batch_bases));
+      fail(s->batch_offs.need((size_t)(s->batch_reads + sums.reads + 1) * 8, (size_t)(s->batch_reads + 1) * 8));
+      if (rc == SVB_OK && s->batch_reads == 0) fail(cudaMemsetAsync(s->batch_offs.p, 0, 8, 0));
+    }
+    if (rc == SVB_OK) {
+      k_bam_gather<<<(unsigned)n, 128>>>(static_cast<const uint8_t*>(s->win.p), static_cast<const int64_t*>(s->rec_off.p), static_cast<const int64_t*>(s->seq_off.p),
+                                         static_cast<const BamMeta*>(s->meta.p), static_cast<const int64_t*>(s->name_off.p),
+                                         static_cast<const int64_t*>(s->base_off.p), static_cast<const int64_t*>(s->rank.p), static_cast<char*>(s->names.p),
+                                         static_cast<uint8_t*>(s->batch.p), static_cast<int64_t*>(s->batch_offs.p), s->batch_reads, s->batch_bases);
+      fail(cudaGetLastError());
+      s->h_meta.resize((size_t)n);
+      s->h_name_off.resize((size_t)n + 1);
+      s->h_names.resize((size_t)std::max<long long>(sums.names, 1));
+      fail(cudaMemcpy(s->h_meta.data(), s->meta.p, (size_t)n * sizeof(BamMeta), cudaMemcpyDeviceToHost));
+      fail(cudaMemcpy(s->h_name_off.data(), s->name_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost));
+      if (sums.names) fail(cudaMemcpy(s->h_names.data(), s->names.p, (size_t)sums.names, cudaMemcpyDeviceToHost));
+    }
+    if (rc != SVB_OK) return rc;
+    s->batch_reads += sums.reads;
+    s->batch_bases += sums.bases;
+  } else {
+    s->h_meta.clear(); s->h_name_off.assign(1, 0); s->h_names.assign(1, 0);
+  }
+  // ---- what is left of the window is the head of a record the next window completes
+  const int64_t left = total - p_end;
+  if (left > 0 && p_end > 0) {
+    if (left <= p_end) fail(cudaMemcpyAsync(s->win.p, static_cast<uint8_t*>(s->win.p) + p_end, (size_t)left, cudaMemcpyDeviceToDevice, 0));
+    else {   // overlapping ranges: through a scratch buffer
+      void* tmp = nullptr;
+      fail(pmalloc(&tmp, (size_t)left, 0));
+      if (rc == SVB_OK) {
+        fail(cudaMemcpyAsync(tmp, static_cast<uint8_t*>(s->win.p) + p_end, (size_t)left, cudaMemcpyDeviceToDevice, 0));
+        fail(cudaMemcpyAsync(s->win.p, tmp, (size_t)left, cudaMemcpyDeviceToDevice, 0));
+      }
+      pfree(tmp, 0);
+    }
+  }
+  s->carry = left;
+  fail(cudaStreamSynchronize(0));
+  if (rc != SVB_OK) return rc;
+  // ---- the caller's view
+  s->flag.resize((size_t)n); s->tid.resize((size_t)n); s->l_qseq.resize((size_t)n); s->xf.resize((size_t)n); s->hp.resize((size_t)n); s->state.resize((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    const BamMeta& m = s->h_meta[(size_t)i];
+    s->flag[(size_t)i] = m.flag; s->tid[(size_t)i] = m.tid; s->l_qseq[(size_t)i] = m.l_qseq; s->xf[(size_t)i] = m.xf; s->hp[(size_t)i] = m.hp;
+    s->state[(size_t)i] = m.state;
+  }
+  recs->n = n;
+  recs->flag = s->flag.data(); recs->tid = s->tid.data(); recs->l_qseq = s->l_qseq.data(); recs->xf = s->xf.data(); recs->hp = s->hp.data();
+  recs->state = s->state.data(); recs->name_offs = s->h_name_off.data(); recs->names = s->h_names.data();
+  recs->batch_reads = s->batch_reads; recs->batch_bases = s->batch_bases;
+  recs->h2d_bytes = in_total + (n_members + 1) * 16;
+  recs->d2h_bytes = n * (int64_t)sizeof(BamMeta) + (n + 1) * 8 + sums.names + n_members * 4;
+  return SVB_OK;
+}
+
+extern "C" int svb_bamstream_search(svb_bamstream_t* s, const svb_index_t* idx, int overlap, int assemble, svb_sfs_out_t* out) {
+  if (!s || !idx || !out) { set_error("svb_bamstream_search: null argument"); return SVB_EINVAL; }
+  memset(out, 0, sizeof(*out));
+  SVB_TRY(check_device(s->device));
+  if (s->batch_reads == 0) {
+    out->offs = (int64_t*)calloc(1, 8);
+    return out->offs ? SVB_OK : SVB_ENOMEM;
+  }
+  SVB_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(s->batch.p) + s->batch_bases, 0, 64, 0));
+  SVB_CUDA(cudaStreamSynchronize(0));
+  svb_reads_t* R = nullptr;
+  SVB_TRY(svb_reads_upload(static_cast<const uint8_t*>(s->batch.p), static_cast<const int64_t*>(s->batch_offs.p), s->batch_reads, SVB_MEM_DEVICE, s->device, &R));
+  const int rc = svb_sfs_resident(idx, R, overlap, assemble, out);
+  svb_reads_free(R);
+  s->batch_reads = 0;
+  s->batch_bases = 0;
+  return rc;
+}

@@ -23,6 +23,33 @@ int check_device(int device);
 
 using namespace svb;
 
+namespace svb {
+
+// the inflate kernel over members already in HBM (also used by bam_stream.cu): the warp-per-member kernel by default,
+// SVB_INFLATE_KERNEL=thread keeps the first one measurable
+void launch_inflate(const uint8_t* d_in, const int64_t* d_io, const int64_t* d_oo, int64_t n_members, uint8_t* d_out, int32_t* d_st, int device,
+                    cudaStream_t sq) {
+  if (n_members <= 0) return;
+  const char* kind = getenv("SVB_INFLATE_KERNEL");
+  if (kind && strcmp(kind, "thread") == 0) {
+    // one warp per CTA: members differ in length by an order of magnitude, small CTAs retire independently.
+    // Members per warp: as few as still fill the warp slots of the device (lanes on different streams diverge)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int64_t slots = (int64_t)sms * 32;
+    if (const char* e = getenv("SVB_INFLATE_WARPS_PER_SM")) { const int v = atoi(e); if (v > 0) slots = (int64_t)sms * v; }
+    int mpw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (n_members + slots - 1) / slots));
+    if (const char* e = getenv("SVB_INFLATE_MPW")) { const int v = atoi(e); if (v >= 1 && v <= 32) mpw = v; }
+    k_bgzf_inflate<<<(unsigned)((n_members + mpw - 1) / mpw), 32, 0, sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st, mpw);
+  } else if (getenv("SVB_INFLATE_OCC12")) {
+    k_bgzf_inflate_warp<12><<<(unsigned)((n_members + 1) / 2), 64, 2 * sizeof(InfWarpMem), sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
+  } else {
+    k_bgzf_inflate_warp<16><<<(unsigned)((n_members + 1) / 2), 64, 2 * sizeof(InfWarpMem), sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
+  }
+}
+
+}  // namespace svb
+
 extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_offs, const int64_t* out_offs, int64_t n_members,
                                        int device, uint8_t* out_host, int32_t* status_host, float* kernel_ms) {
   if (!in_offs || !out_offs || n_members < 0 || n_members > 0x7fffffff) { set_error("svb_bgzf_inflate_device: bad arguments"); return SVB_EINVAL; }
@@ -62,22 +89,8 @@ extern "C" int svb_bgzf_inflate_device(const uint8_t* comp, const int64_t* in_of
     fail(cudaMemcpyAsync(d_oo, out_offs, (size_t)(n_members + 1) * 8, cudaMemcpyHostToDevice, sq));
   }
   if (rc == SVB_OK) {
-    // one warp per CTA: members differ in length by an order of magnitude, small CTAs retire independently.
-    // Members per warp: as few as still fill the warp slots of the device (lanes on different streams diverge)
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    int64_t slots = (int64_t)sms * 32;
-    if (const char* e = getenv("SVB_INFLATE_WARPS_PER_SM")) { const int v = atoi(e); if (v > 0) slots = (int64_t)sms * v; }
-    int mpw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (n_members + slots - 1) / slots));
-    if (const char* e = getenv("SVB_INFLATE_MPW")) { const int v = atoi(e); if (v >= 1 && v <= 32) mpw = v; }
-    // default: the warp-per-member kernel (tables in shared memory, copies spread over the lanes); SVB_INFLATE_KERNEL=thread
-    // keeps the first one measurable
-    const char* kind = getenv("SVB_INFLATE_KERNEL");
-    const bool by_thread = kind && strcmp(kind, "thread") == 0;
     fail(cudaEventRecord(e0, sq));
-    if (by_thread) k_bgzf_inflate<<<(unsigned)((n_members + mpw - 1) / mpw), 32, 0, sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st, mpw);
-    else if (getenv("SVB_INFLATE_OCC12")) k_bgzf_inflate_warp<12><<<(unsigned)((n_members + 1) / 2), 64, 2 * sizeof(InfWarpMem), sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
-    else k_bgzf_inflate_warp<16><<<(unsigned)((n_members + 1) / 2), 64, 2 * sizeof(InfWarpMem), sq>>>(d_in, d_io, d_oo, n_members, d_out, d_st);
+    launch_inflate(d_in, d_io, d_oo, n_members, d_out, d_st, device, sq);
     fail(cudaGetLastError());
     fail(cudaEventRecord(e1, sq));
     if (out_total) fail(cudaMemcpyAsync(out_host, d_out, (size_t)out_total, cudaMemcpyDeviceToHost, sq));

@@ -151,6 +151,33 @@ class BgzfSource {
     return true;
   }
  public:
+  // Raw mode, for a consumer that inflates elsewhere (svb_bamstream_window: records decoded on the device): the next
+  // window of whole BGZF members as they lie in the file -- base[in_offs[m]] is the first deflate byte of member m
+  // (trailer and next header ride along), out_offs its place in the window's payload.  The window after it is read
+  // by a helper thread meanwhile.  false at EOF or on a malformed file.  Not to be mixed with read_exact / peek.
+  bool next_members(const uint8_t*& base, std::vector<int64_t>& in_offs, std::vector<int64_t>& out_offs) {
+    if (!bgzf_) return false;
+    for (;;) {
+      Window& w = win_[seq_ & 1];
+      const auto w0 = Clock::now();
+      const bool have = reading_.valid() ? reading_.get() : read_window(w);
+      t_wait_ += since(w0);
+      if (!have) return false;
+      ++seq_;
+      Window& next = win_[seq_ & 1];
+      reading_ = std::async(std::launch::async, [this, &next]() { return read_window(next); });
+      if (w.out_total == 0) continue;             // only empty members (the EOF marker)
+      const size_t nb = w.blks.size(), b0 = w.blks[0].in_off;
+      in_offs.resize(nb + 1); out_offs.resize(nb + 1);
+      for (size_t i = 0; i < nb; ++i) { in_offs[i] = (int64_t)(w.blks[i].in_off - b0); out_offs[i] = (int64_t)w.blks[i].out_off; }
+      in_offs[nb] = (int64_t)(w.in_end - b0); out_offs[nb] = (int64_t)w.out_total;
+      base = w.in.data() + b0;
+      return true;
+    }
+  }
+  bool is_bgzf() const { return bgzf_; }
+  bool failed() const { return bad_; }              // the last false of next_members was an error, not the end of the file
+  bool device_inflate() const { return bgzf_ && gpu_ >= 0; }
   // zero-copy access for record parsers: n contiguous bytes of the current window, or nullptr if the
   // window ends before (then read_exact copies across the boundary)
   const uint8_t* peek(size_t n) const { return bgzf_ && out_.size() - pos_ >= n ? out_.data() + pos_ : nullptr; }
@@ -212,6 +239,7 @@ class BgzfSource {
   // (next_window waits for a read before it starts the next): carry_, eof_ and the file position are its own.
   bool read_window(Window& w) {
     const auto c0 = Clock::now();
+    auto bad = [this]() { bad_ = true; return false; };   // malformed or truncated, as opposed to the end of the file
     ByteBuf& in = w.in;
     const size_t window = window_bytes(), out_cap = payload_limit(window);
     if (gpu_ >= 0) {
@@ -241,7 +269,7 @@ class BgzfSource {
       bool full = false;                            // the payload limit ended the window, not the read
       while (p + 18 <= have) {
         const uint8_t* h = in.data() + p;
-        if (h[0] != 31 || h[1] != 139 || !(h[3] & 4)) return false;
+        if (h[0] != 31 || h[1] != 139 || !(h[3] & 4)) return bad();
         // walk the extra field for the BC subfield (SAM spec 4.1)
         const size_t xlen = h[10] | (h[11] << 8);
         if (p + 12 + xlen > have) break;
@@ -252,20 +280,20 @@ class BgzfSource {
           if (extra[o] == 'B' && extra[o + 1] == 'C' && sl == 2 && o + 6 <= xlen) bsize = extra[o + 4] | (extra[o + 5] << 8);
           o += 4 + sl;
         }
-        if (bsize < 0) return false;
+        if (bsize < 0) return bad();
         const size_t total = (size_t)bsize + 1, head = 12 + xlen;
-        if (total < head + 8) return false;
+        if (total < head + 8) return bad();
         if (p + total > have) break;
         uint32_t isize;
         memcpy(&isize, h + total - 4, 4);
-        if (isize > (1u << 16)) return false;
+        if (isize > (1u << 16)) return bad();
         if (w.out_total + isize > out_cap) { full = true; break; }
         w.blks.push_back(Blk{p + head, total - head - 8, w.out_total, isize});   // deflate data; CRC32 + ISIZE follow
         w.out_total += isize;
         p += total;
       }
       if (p < have) {                               // the window ends inside a member, or at the payload limit
-        if (eof_ && !full) return false;            // truncated file
+        if (eof_ && !full) return bad();            // truncated file
         carry_.assign(in.data() + p, in.data() + have);
       }
       if (w.blks.empty()) {
@@ -333,7 +361,7 @@ class BgzfSource {
   Window win_[2];                                   // window being inflated / window being read
   unsigned long long seq_ = 0;                      // windows handed to inflate_window so far
   std::vector<uint8_t> carry_;                      // head of the member the last read cut
-  bool eof_ = false;
+  bool eof_ = false, bad_ = false;
   std::future<bool> pending_, reading_;
   size_t pos_ = 0;
 };
@@ -472,9 +500,13 @@ class BamReader {
       if (!src_.read_exact(&nm[0], (size_t)l_name) || !src_.read_exact(&l_ref, 4)) return;
       nm.resize(strlen(nm.c_str()));
       ref_names_.push_back(nm); ref_lens_.push_back(l_ref);
+      header_bytes_ += 8 + (int64_t)l_name;
     }
+    header_bytes_ += 12 + (int64_t)l_text;
     ok_ = true;
   }
+  // inflated bytes before the first record (magic, text, reference dictionary)
+  int64_t header_bytes() const { return header_bytes_; }
   bool ok() const { return ok_; }
   const std::vector<std::string>& ref_names() const { return ref_names_; }
   // alignment mode (`call`): keep CIGAR + packed sequence instead of decoding nt6 codes
@@ -581,6 +613,7 @@ class BamReader {
   std::vector<std::string> ref_names_;
   std::vector<int32_t> ref_lens_;
   std::vector<uint8_t> buf_;
+  int64_t header_bytes_ = 0;
 };
 
 }  // namespace svdss

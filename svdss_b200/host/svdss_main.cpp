@@ -335,6 +335,99 @@ static bool flush(svb_index_t* idx, const Config& c, vector<PendingRead>& reads,
   return true;
 }
 
+// ---- `search --bam --gpu-inflate`: the BAM loader on the device (svb_bamstream_*, csrc/bam_stream.cu).  The host reads
+// the file and finds the BGZF members; records are inflated, walked, parsed and filtered in HBM, the bases of the reads to
+// search never leave it.  Same output, byte for byte, as the host loader.
+struct DevRead { string qname; int hp; bool search; vector<pair<int32_t, int32_t>> sfs; };
+
+// the reference's output order (ping_pong.cpp:213-236) for reads [0, n): logical batches of --bsize, thread slots, qname order
+static void print_reads(const Config& c, const vector<DevRead>& reads, size_t n, uint64_t& total_sfs) {
+  string line;
+  for (size_t b0 = 0; b0 < n; b0 += (size_t)c.bsize) {
+    const size_t b1 = min(n, b0 + (size_t)c.bsize);
+    for (int t = 0; t < c.threads; ++t) {
+      map<string, vector<size_t>> slot;
+      for (size_t i = b0 + (size_t)t; i < b1; i += (size_t)c.threads)
+        if (reads[i].search) slot[reads[i].qname].push_back(i);
+      for (auto& kv : slot) {
+        bool first = true;
+        for (size_t i : kv.second)
+          for (const auto& f : reads[i].sfs) {
+            line = (first ? kv.first : string("*")) + "\t" + to_string(f.first) + "\t" + to_string(f.second) + "\t" + to_string(reads[i].hp) + "\t\n";
+            fwrite(line.data(), 1, line.size(), stdout);
+            first = false;
+            ++total_sfs;
+          }
+      }
+    }
+  }
+}
+
+// 1 = done, 0 = not applicable (the caller takes the host loader), -1 = failed
+static int search_bam_on_device(svb_index_t* idx, const Config& c, size_t gpu_bases, uint64_t& processed, uint64_t& total_sfs) {
+  BgzfSource src(c.bam);
+  if (!src.ok() || !src.device_inflate()) return 0;   // not BGZF, or a file too small for the device path to pay
+  int64_t header_bytes = 0;
+  {
+    const int dev = bgzf_gpu_device();
+    bgzf_gpu_device() = -1;                            // the header is read by the host reader
+    BamReader hdr(c.bam);
+    bgzf_gpu_device() = dev;
+    if (!hdr.ok()) { logmsg("critical", "cannot read BAM " + c.bam); return -1; }
+    header_bytes = hdr.header_bytes();
+  }
+  svb_bamstream_t* bs = nullptr;
+  if (svb_bamstream_open(c.device, c.putative ? 1 : 0, &bs) != SVB_OK) { logmsg("critical", string("svb_bamstream_open: ") + svb_last_error()); return -1; }
+  vector<DevRead> reads;
+  size_t attached = 0;   // reads [0, attached) carry their results already
+  auto search_and_print = [&](bool final) -> bool {
+    svb_sfs_out_t out;
+    const double t_gpu = now_s();
+    const int rc = svb_bamstream_search(bs, idx, c.overlap, c.assemble ? 1 : 0, &out);
+    g_gpu_s += now_s() - t_gpu;
+    if (rc != SVB_OK) { logmsg("critical", string("svb_bamstream_search: ") + svb_last_error()); return false; }
+    int64_t r = 0;
+    for (size_t i = attached; i < reads.size(); ++i)
+      if (reads[i].search) {
+        for (int64_t k = out.offs[r]; k < out.offs[r + 1]; ++k) reads[i].sfs.emplace_back(out.qs[k], out.len[k]);
+        ++r;
+      }
+    svb_sfs_out_free(&out);
+    attached = reads.size();
+    // whole logical batches only: the rest waits for the reads that complete its batch
+    const size_t n_print = final ? reads.size() : (reads.size() / (size_t)c.bsize) * (size_t)c.bsize;
+    print_reads(c, reads, n_print, total_sfs);
+    reads.erase(reads.begin(), reads.begin() + (long)n_print);
+    attached -= n_print;
+    return true;
+  };
+  const uint8_t* base = nullptr;
+  vector<int64_t> io, oo;
+  bool ok = true;
+  while (ok && src.next_members(base, io, oo)) {
+    svb_bam_recs_t recs;
+    const double t_gpu = now_s();
+    const int rc = svb_bamstream_window(bs, base, io.data(), oo.data(), (int64_t)io.size() - 1, header_bytes, &recs);
+    g_gpu_s += now_s() - t_gpu;
+    if (rc != SVB_OK) { logmsg("critical", string("truncated or corrupt BAM: ") + svb_last_error()); ok = false; break; }
+    for (int64_t i = 0; i < recs.n; ++i) {
+      ++processed;
+      if (recs.state[i] == 0) continue;                                      // ping_pong.cpp:66-69
+      if (recs.state[i] == 3) {                                              // :70-75
+        logmsg("warning", "Alignment filtered due to l_qseq. Why are we here? Please check");
+        continue;
+      }
+      if (recs.tid[i] < 0) { logmsg("critical", "core.tid < 0. Why are we here? Please check"); svb_bamstream_close(bs); svb_index_free(idx); exit(1); }  // :76-79
+      reads.push_back(DevRead{string(recs.names + recs.name_offs[i], (size_t)(recs.name_offs[i + 1] - recs.name_offs[i])), (int)recs.hp[i], recs.state[i] == 2, {}});
+    }
+    if ((size_t)recs.batch_bases >= gpu_bases) ok = search_and_print(false);
+  }
+  if (ok && (src.failed() || svb_bamstream_pending_bytes(bs) != 0)) { logmsg("critical", "truncated or corrupt BAM"); ok = false; }
+  if (ok) ok = search_and_print(true);
+  svb_bamstream_close(bs);
+  return ok ? 1 : -1;
+}
+
 static int run_search(const Config& c) {
   if (c.index.empty() || (c.fastx.empty() && c.bam.empty())) { cerr << SEARCH_USAGE << endl; return EXIT_FAILURE; }
   const double t_start = now_s();
@@ -371,7 +464,14 @@ static int run_search(const Config& c) {
   };
   logmsg("info", "Extracting SFS strings on GPU " + to_string(c.device) + " (ordering as with " + to_string(c.threads) + " threads)..");
   bool ok = true;
-  if (!c.bam.empty()) {
+  int on_device = 0;
+  if (!c.bam.empty() && c.gpu_inflate && !getenv("SVB_BAM_HOST_PARSE")) {
+    on_device = search_bam_on_device(idx, c, gpu_bases, processed, total_sfs);
+    if (on_device < 0) ok = false;
+  }
+  if (on_device != 0) {
+    // done (or failed) above
+  } else if (!c.bam.empty()) {
     BamReader bam(c.bam);
     if (!bam.ok()) { logmsg("critical", "cannot read BAM " + c.bam); svb_index_free(idx); return EXIT_FAILURE; }
     bam.want_view(true);        // the packed sequence stays where it was inflated; no host-side decode, no copy of the reads that are not searched
@@ -511,6 +611,34 @@ int main(int argc, char** argv) {
   }
   if (mode == "_bamread") {   // measurement hook: what the BAM reader hands `search` per second (tools/bench_bamread.py), no GPU
     if (pos.size() != 1) return EXIT_FAILURE;
+    if (c.gpu_inflate && getenv("SVB_BAMREAD_DEVICE")) {   // the device loader of `search` (svb_bamstream_*), without the search
+      const double t0 = now_s();
+      BgzfSource src(pos[0]);
+      if (!src.ok() || !src.device_inflate()) return EXIT_FAILURE;
+      int64_t header_bytes = 0;
+      { const int dev = bgzf_gpu_device(); bgzf_gpu_device() = -1; BamReader hdr(pos[0]); bgzf_gpu_device() = dev; if (!hdr.ok()) return EXIT_FAILURE; header_bytes = hdr.header_bytes(); }
+      svb_bamstream_t* bs = nullptr;
+      if (svb_bamstream_open(c.device, 1, &bs) != SVB_OK) return EXIT_FAILURE;
+      const uint8_t* base = nullptr;
+      vector<int64_t> io, oo;
+      uint64_t n = 0, bases = 0, kept = 0, name_bytes = 0;
+      double t_dev = 0;
+      bool ok = true;
+      while (src.next_members(base, io, oo)) {
+        svb_bam_recs_t recs;
+        const double t1 = now_s();
+        if (svb_bamstream_window(bs, base, io.data(), oo.data(), (int64_t)io.size() - 1, header_bytes, &recs) != SVB_OK) { cerr << svb_last_error() << endl; ok = false; break; }
+        t_dev += now_s() - t1;
+        for (int64_t i = 0; i < recs.n; ++i) { ++n; bases += (uint64_t)recs.l_qseq[i]; if (recs.state[i] == 2) ++kept; }
+        name_bytes += (uint64_t)recs.name_offs[recs.n];
+      }
+      ok = ok && !src.failed() && svb_bamstream_pending_bytes(bs) == 0;
+      const double dt = now_s() - t0;
+      svb_bamstream_close(bs);
+      printf("{\"records\": %llu, \"kept\": %llu, \"bases\": %llu, \"seq_sum\": 0, \"name_bytes\": %llu, \"seconds\": %.3f, \"device_call_seconds\": %.3f, \"records_per_s\": %.0f, \"Gbases_per_s\": %.3f}\n",
+             (unsigned long long)n, (unsigned long long)kept, (unsigned long long)bases, (unsigned long long)name_bytes, dt, t_dev, n / dt, bases / dt / 1e9);
+      return ok ? EXIT_SUCCESS : EXIT_FAILURE;
+    }
     const double t0 = now_s();                     // the first window is inflated by the constructor
     BamReader bam(pos[0]);
     if (!bam.ok()) return EXIT_FAILURE;
