@@ -197,7 +197,9 @@ typedef struct {
   int64_t batch_reads, batch_bases;   /* the device batch after this window                                         */
   int64_t h2d_bytes, d2h_bytes;
 } svb_bam_recs_t;
-SVB_API int svb_bamstream_open(int device, int putative, svb_bamstream_t** out);
+/* putative: the XF rule of ping_pong.cpp:202 (--noputative = 0); n_ref: reference sequences in the BAM header (the record walk
+ * uses it to tell a record start from payload; <= 0 if unknown) */
+SVB_API int svb_bamstream_open(int device, int putative, int n_ref, svb_bamstream_t** out);
 /* One window: n_members BGZF members as svb_bgzf_inflate_device takes them (host buffers).  skip_bytes (first call
  * only): inflated bytes to pass over before the first record = the BAM header, which the caller has parsed.
  * recs points into memory owned by the stream, valid until the next call on it. */

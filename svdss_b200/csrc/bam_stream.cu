@@ -31,6 +31,99 @@ __global__ void k_bam_walk(const uint8_t* __restrict__ win, int64_t start, int64
   res[0] = n; res[1] = p; res[2] = err;
 }
 
+// ---- the same walk in parallel.  The chain of block_size fields is serial (11 ms for the 16 k records of a window:
+// every hop is a round trip to L2), so the window is cut into segments and a thread per segment GUESSES where a record
+// starts in it (first offset that looks like a record whose successors look like records too) and follows the chain to
+// the segment's end.  A second, single thread then links the segments: entering segment s at the true position, it
+// looks that position up in the segment's guessed chain -- found: the rest of the chain is the truth (the walk is
+// deterministic from any true record start); not found: it follows the fields itself until it meets the chain or
+// leaves the segment.  The guess only decides how fast the walk is, never what it returns.
+__device__ __forceinline__ uint32_t bw_ld32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ bool bam_plausible(const uint8_t* __restrict__ win, int64_t q, int64_t total, int n_ref) {
+  if (q + 36 > total) return false;
+  const int64_t bs = (int32_t)bw_ld32(win + q);
+  if (bs < 32 || bs > (1 << 28)) return false;
+  const int32_t tid = (int32_t)bw_ld32(win + q + 4), pos = (int32_t)bw_ld32(win + q + 8);
+  if (tid < -1 || tid >= n_ref || pos < -1) return false;
+  const int64_t l_read_name = win[q + 12], n_cigar = (int64_t)win[q + 16] | ((int64_t)win[q + 17] << 8);
+  const int64_t l_qseq = (int32_t)bw_ld32(win + q + 20);
+  if (l_read_name < 1 || l_qseq < 0) return false;
+  if (32 + l_read_name + 4 * n_cigar + (l_qseq + 1) / 2 + l_qseq > bs) return false;
+  const int64_t nul = q + 36 + l_read_name - 1;
+  if (nul < total && win[nul] != 0) return false;
+  if (l_read_name > 1 && q + 36 < total && win[q + 36] < 33) return false;   // a name starts with a printable character
+  return true;
+}
+
+__global__ void k_bam_walk_seg(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t seg_len, int n_seg, int n_ref,
+                               int64_t* __restrict__ seg_pos, int64_t seg_cap, int64_t* __restrict__ seg_cnt, int64_t* __restrict__ seg_end_pos,
+                               int* __restrict__ seg_end_flag) {
+  const int s = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (s >= n_seg) return;
+  const int64_t a = start + (int64_t)s * seg_len, b = min(total, a + seg_len);
+  int64_t* out = seg_pos + (int64_t)s * seg_cap;
+  int64_t p = -1;
+  if (s == 0) p = a;
+  else
+    for (int64_t q = a; q < b; ++q) {
+      if (!bam_plausible(win, q, total, n_ref)) continue;
+      const int64_t q2 = q + 4 + (int64_t)(int32_t)bw_ld32(win + q);
+      if (q2 + 36 <= total && !bam_plausible(win, q2, total, n_ref)) continue;
+      p = q;
+      break;
+    }
+  int64_t n = 0;
+  int flag = 0;
+  if (p >= 0) {
+    while (p < b && n < seg_cap) {
+      if (p + 4 > total) { flag = 1; break; }
+      const int64_t bs = (int32_t)bw_ld32(win + p);
+      if (bs < 32) { flag = 2; break; }
+      if (p + 4 + bs > total) { flag = 1; break; }
+      out[n++] = p;
+      p += 4 + bs;
+    }
+  }
+  seg_cnt[s] = n; seg_end_pos[s] = p; seg_end_flag[s] = flag;
+}
+
+__global__ void k_bam_walk_link(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t seg_len, int n_seg,
+                                const int64_t* __restrict__ seg_pos, int64_t seg_cap, const int64_t* __restrict__ seg_cnt,
+                                const int64_t* __restrict__ seg_end_pos, const int* __restrict__ seg_end_flag, int64_t* __restrict__ rec_off, int64_t cap,
+                                int64_t* __restrict__ res) {
+  int64_t cur = start, n = 0, err = 0, joined = 0;
+  bool stop = false;
+  for (int s = 0; s < n_seg && !stop; ++s) {
+    const int64_t a = start + (int64_t)s * seg_len, b = min(total, a + seg_len);
+    if (cur >= b) continue;                       // a record longer than the segment
+    const int64_t* chain = seg_pos + (int64_t)s * seg_cap;
+    const int64_t c = seg_cnt[s];
+    while (cur < b) {
+      // is the true position on the guessed chain?
+      int64_t lo = 0, hi = c;
+      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (chain[mid] < cur) lo = mid + 1; else hi = mid; }
+      if (lo < c && chain[lo] == cur && n + (c - lo) <= cap) {
+        for (int64_t k = lo; k < c; ++k) rec_off[n++] = chain[k] + 4;
+        cur = seg_end_pos[s];
+        ++joined;
+        if (seg_end_flag[s] == 1) stop = true;
+        if (seg_end_flag[s] == 2) { err = 1; stop = true; }
+        break;
+      }
+      // no: one hop of the true chain
+      if (cur + 4 > total || n >= cap) { stop = true; break; }
+      const int64_t bs = (int32_t)bw_ld32(win + cur);
+      if (bs < 32) { err = 1; stop = true; break; }
+      if (cur + 4 + bs > total) { stop = true; break; }
+      rec_off[n++] = cur + 4;
+      cur += 4 + bs;
+    }
+  }
+  res[0] = n; res[1] = cur; res[2] = err; res[3] = joined;
+}
+
 struct BamMeta {   // per record, device and host
   int32_t tid, l_qseq, xf, hp;
   uint16_t flag;
@@ -207,7 +300,8 @@ struct svb_bamstream {
   int64_t skip_left = 0;       // bytes of the BAM header not yet passed
   bool skip_set = false;
   int64_t carry = 0;           // bytes of an unfinished record at the front of win
-  DevBuf comp, io, oo, st, win, rec_off, seq_off, meta, name_off, base_off, rank, names, sums, res, err;
+  DevBuf comp, io, oo, st, win, rec_off, seq_off, meta, name_off, base_off, rank, names, sums, res, err, seg_pos, seg_aux;
+  int n_ref = 1 << 30;         // reference sequences of the header (svb_bamstream_set_refs): the walk's plausibility test uses it
   DevBuf batch, batch_offs;
   int64_t batch_reads = 0, batch_bases = 0;
   // host copies handed to the caller, valid until the next call
@@ -219,12 +313,13 @@ struct svb_bamstream {
   std::vector<char> h_names;
 };
 
-extern "C" int svb_bamstream_open(int device, int putative, svb_bamstream_t** out) {
+extern "C" int svb_bamstream_open(int device, int putative, int n_ref, svb_bamstream_t** out) {
   if (!out) { set_error("svb_bamstream_open: null out"); return SVB_EINVAL; }
   SVB_TRY(check_device(device));
   svb_bamstream* s = new svb_bamstream();
   s->device = device;
   s->putative = putative ? 1 : 0;
+  if (n_ref > 0) s->n_ref = n_ref;
   *out = s;
   return SVB_OK;
 }
@@ -233,7 +328,7 @@ extern "C" void svb_bamstream_close(svb_bamstream_t* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   for (DevBuf* b : {&s->comp, &s->io, &s->oo, &s->st, &s->win, &s->rec_off, &s->seq_off, &s->meta, &s->name_off, &s->base_off, &s->rank, &s->names,
-                    &s->sums, &s->res, &s->err, &s->batch, &s->batch_offs})
+                    &s->sums, &s->res, &s->err, &s->seg_pos, &s->seg_aux, &s->batch, &s->batch_offs})
     b->release();
   cudaStreamSynchronize(0);
   delete s;
@@ -256,6 +351,7 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
       set_error("svb_bamstream_window: member %lld: offsets not ascending or more than 64 KiB of payload", (long long)m); return SVB_EINVAL;
     }
   int rc = SVB_OK;
+  StageLog slog("bamstream");
   auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == SVB_OK) { set_error("svb_bamstream_window: %s", cudaGetErrorString(e)); rc = SVB_ECUDA; } };
   // ---- inflate behind the carried tail
   const int64_t total = s->carry + out_total;
@@ -280,6 +376,7 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
     }
   }
   if (rc != SVB_OK) return rc;
+  slog.lap("H2D + inflate");
   // ---- the BAM header (its length comes from the caller, who parsed it) is passed over
   int64_t start = 0;
   if (s->skip_left > 0) {
@@ -289,16 +386,36 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
   // ---- walk the records
   const int64_t cap = std::max<int64_t>(1024, (total - start) / 36 + 1);   // a record is at least 36 bytes
   fail(s->rec_off.need((size_t)cap * 8));
-  fail(s->res.need(3 * 8));
-  int64_t res[3] = {0, start, 0};
-  if (rc == SVB_OK) {
+  fail(s->res.need(4 * 8));
+  int64_t res[4] = {0, start, 0, 0};
+  const char* ew = getenv("SVB_BAM_WALK");
+  const bool serial_walk = (ew && strcmp(ew, "serial") == 0) || (total - start < (1 << 20) && !(ew && strcmp(ew, "parallel") == 0));   // tests force either
+  if (rc == SVB_OK && serial_walk) {
     k_bam_walk<<<1, 1>>>(static_cast<const uint8_t*>(s->win.p), start, total, static_cast<int64_t*>(s->rec_off.p), cap, static_cast<int64_t*>(s->res.p));
     fail(cudaGetLastError());
-    fail(cudaMemcpy(res, s->res.p, sizeof(res), cudaMemcpyDeviceToHost));
+    fail(cudaMemcpy(res, s->res.p, 3 * 8, cudaMemcpyDeviceToHost));
+  } else if (rc == SVB_OK) {
+    const int n_seg = 512;
+    const int64_t seg_len = (total - start + n_seg - 1) / n_seg, seg_cap = seg_len / 36 + 2;
+    fail(s->seg_pos.need((size_t)n_seg * (size_t)seg_cap * 8));
+    fail(s->seg_aux.need((size_t)n_seg * 24));
+    if (rc == SVB_OK) {
+      int64_t* seg_cnt = static_cast<int64_t*>(s->seg_aux.p);
+      int64_t* seg_end = seg_cnt + n_seg;
+      int* seg_flag = reinterpret_cast<int*>(seg_end + n_seg);
+      k_bam_walk_seg<<<(n_seg + 31) / 32, 32>>>(static_cast<const uint8_t*>(s->win.p), start, total, seg_len, n_seg, s->n_ref, static_cast<int64_t*>(s->seg_pos.p), seg_cap,
+                                                seg_cnt, seg_end, seg_flag);
+      k_bam_walk_link<<<1, 1>>>(static_cast<const uint8_t*>(s->win.p), start, total, seg_len, n_seg, static_cast<const int64_t*>(s->seg_pos.p), seg_cap, seg_cnt, seg_end,
+                                seg_flag, static_cast<int64_t*>(s->rec_off.p), cap, static_cast<int64_t*>(s->res.p));
+      fail(cudaGetLastError());
+      fail(cudaMemcpy(res, s->res.p, sizeof(res), cudaMemcpyDeviceToHost));
+      if (slog.on) fprintf(stderr, "[svb-stage] bamstream: %lld of %d segments joined on their guessed chain\n", (long long)res[3], n_seg);
+    }
   }
   if (rc != SVB_OK) return rc;
   if (res[2]) { set_error("BAM record with a block_size below 32: corrupt file"); return SVB_EIO; }
   const int64_t n = res[0], p_end = res[1];
+  slog.lap("record walk");
   // ---- parse, lay out, gather
   BamSums sums = {0, 0, 0};
   if (n) {
@@ -347,6 +464,7 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
   } else {
     s->h_meta.clear(); s->h_name_off.assign(1, 0); s->h_names.assign(1, 0);
   }
+  slog.lap("parse + scan + gather + D2H");
   // ---- what is left of the window is the head of a record the next window completes
   const int64_t left = total - p_end;
   if (left > 0 && p_end > 0) {

@@ -368,6 +368,7 @@ static int search_bam_on_device(svb_index_t* idx, const Config& c, size_t gpu_ba
   BgzfSource src(c.bam);
   if (!src.ok() || !src.device_inflate()) return 0;   // not BGZF, or a file too small for the device path to pay
   int64_t header_bytes = 0;
+  int n_ref = 0;
   {
     const int dev = bgzf_gpu_device();
     bgzf_gpu_device() = -1;                            // the header is read by the host reader
@@ -375,9 +376,10 @@ static int search_bam_on_device(svb_index_t* idx, const Config& c, size_t gpu_ba
     bgzf_gpu_device() = dev;
     if (!hdr.ok()) { logmsg("critical", "cannot read BAM " + c.bam); return -1; }
     header_bytes = hdr.header_bytes();
+    n_ref = (int)hdr.ref_names().size();
   }
   svb_bamstream_t* bs = nullptr;
-  if (svb_bamstream_open(c.device, c.putative ? 1 : 0, &bs) != SVB_OK) { logmsg("critical", string("svb_bamstream_open: ") + svb_last_error()); return -1; }
+  if (svb_bamstream_open(c.device, c.putative ? 1 : 0, n_ref, &bs) != SVB_OK) { logmsg("critical", string("svb_bamstream_open: ") + svb_last_error()); return -1; }
   vector<DevRead> reads;
   size_t attached = 0;   // reads [0, attached) carry their results already
   auto search_and_print = [&](bool final) -> bool {
@@ -425,6 +427,7 @@ static int search_bam_on_device(svb_index_t* idx, const Config& c, size_t gpu_ba
   if (ok && (src.failed() || svb_bamstream_pending_bytes(bs) != 0)) { logmsg("critical", "truncated or corrupt BAM"); ok = false; }
   if (ok) ok = search_and_print(true);
   svb_bamstream_close(bs);
+  if (ok) logmsg("info", "BAM records decoded on GPU " + to_string(c.device) + ": " + to_string(processed));
   return ok ? 1 : -1;
 }
 
@@ -616,9 +619,10 @@ int main(int argc, char** argv) {
       BgzfSource src(pos[0]);
       if (!src.ok() || !src.device_inflate()) return EXIT_FAILURE;
       int64_t header_bytes = 0;
-      { const int dev = bgzf_gpu_device(); bgzf_gpu_device() = -1; BamReader hdr(pos[0]); bgzf_gpu_device() = dev; if (!hdr.ok()) return EXIT_FAILURE; header_bytes = hdr.header_bytes(); }
+      int n_ref = 0;
+      { const int dev = bgzf_gpu_device(); bgzf_gpu_device() = -1; BamReader hdr(pos[0]); bgzf_gpu_device() = dev; if (!hdr.ok()) return EXIT_FAILURE; header_bytes = hdr.header_bytes(); n_ref = (int)hdr.ref_names().size(); }
       svb_bamstream_t* bs = nullptr;
-      if (svb_bamstream_open(c.device, 1, &bs) != SVB_OK) return EXIT_FAILURE;
+      if (svb_bamstream_open(c.device, 1, n_ref, &bs) != SVB_OK) return EXIT_FAILURE;
       const uint8_t* base = nullptr;
       vector<int64_t> io, oo;
       uint64_t n = 0, bases = 0, kept = 0, name_bytes = 0;

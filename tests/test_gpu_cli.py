@@ -126,14 +126,16 @@ def test_search_bam_filters_and_tags(world):
         want = expected_sfs_text(names, exp, htags, searched if putative else [True] * len(names), 4, 40, True)
         assert r.stdout == want
         # the same file with its BGZF windows inflated on the device (k_bgzf_inflate), one window and many small ones
-        for window in (None, "3000"):
+        for window, walk in ((None, None), ("3000", None), (None, "parallel"), ("20000", "parallel")):
             env = dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0", SVB_BGZF_STATS="1")   # small files stay on the host threads by default
             if window:
                 env["SVB_BGZF_WINDOW"] = window
+            if walk:
+                env["SVB_BAM_WALK"] = walk            # the segmented record walk, which windows under 1 MB would not use
             g = subprocess.run(args + ["--gpu-inflate"], capture_output=True, text=True, env=env)
             assert g.returncode == 0, g.stderr
             assert g.stdout == want
-            assert "inflating (device)" in g.stderr
+            assert "BAM records decoded on GPU" in g.stderr      # the device loader (svb_bamstream_*), not the host parser
     assert "\t1\t\n" in want or "\t2\t\n" in want    # some HP tag made it to the output
     # a damaged member is an error with the device inflate too, not a shorter output
     raw = bytearray(open(bam, "rb").read())

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--records", type=int, default=20000)
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--gpu-inflate", action="store_true")
+    ap.add_argument("--laps", action="store_true", help="one more run of the device loader with SVB_STAGE_STATS=1: mean lap times of svb_bamstream_window on stderr")
     a = ap.parse_args()
     exe = build.build_host()
     rng = np.random.default_rng(3)
@@ -74,6 +75,16 @@ def main():
             if bestd is None or j["seconds"] < bestd["seconds"]:
                 bestd = j
         res["device_loader"] = bestd
+    if a.gpu_inflate and a.laps:
+        r = subprocess.run([exe, "_bamread", path, "--gpu-inflate"], capture_output=True, text=True,
+                           env=dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0", SVB_BAMREAD_DEVICE="1", SVB_STAGE_STATS="1"))
+        laps = {}
+        for l in r.stderr.splitlines():
+            if l.startswith("[svb-stage] bamstream: ") and l.endswith(" ms"):
+                k, v = l[len("[svb-stage] bamstream: "):-3].rsplit(" ", 1)
+                laps.setdefault(k, []).append(float(v))
+        sys.stderr.write("laps (mean ms per window): " + json.dumps({k: round(sum(v) / len(v), 2) for k, v in laps.items()}) + "\n")
+        sys.stderr.write("\n".join([l for l in r.stderr.splitlines() if "segments joined" in l][:3]) + "\n")
     best = res["host"]
     best["file_bytes"] = os.path.getsize(path)
     os.remove(path); os.rmdir(d)
