@@ -57,23 +57,28 @@ __device__ __forceinline__ bool bam_plausible(const uint8_t* __restrict__ win, i
   return true;
 }
 
-__global__ void k_bam_walk_seg(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t seg_len, int n_seg, int n_ref,
-                               int64_t* __restrict__ seg_pos, int64_t seg_cap, int64_t* __restrict__ seg_cnt, int64_t* __restrict__ seg_end_pos,
-                               int* __restrict__ seg_end_flag) {
-  const int s = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+// a warp per segment: the lanes test 32 consecutive offsets at a time, lane 0 follows the chain from the first hit
+__global__ void __launch_bounds__(128) k_bam_walk_seg(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t seg_len, int n_seg, int n_ref,
+                                                      int64_t* __restrict__ seg_pos, int64_t seg_cap, int64_t* __restrict__ seg_cnt,
+                                                      int64_t* __restrict__ seg_end_pos, int* __restrict__ seg_end_flag) {
+  const int s = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
   if (s >= n_seg) return;
   const int64_t a = start + (int64_t)s * seg_len, b = min(total, a + seg_len);
   int64_t* out = seg_pos + (int64_t)s * seg_cap;
   int64_t p = -1;
   if (s == 0) p = a;
   else
-    for (int64_t q = a; q < b; ++q) {
-      if (!bam_plausible(win, q, total, n_ref)) continue;
-      const int64_t q2 = q + 4 + (int64_t)(int32_t)bw_ld32(win + q);
-      if (q2 + 36 <= total && !bam_plausible(win, q2, total, n_ref)) continue;
-      p = q;
-      break;
+    for (int64_t q0 = a; q0 < b; q0 += 32) {
+      const int64_t q = q0 + lane;
+      bool hit = q < b && bam_plausible(win, q, total, n_ref);
+      if (hit) {
+        const int64_t q2 = q + 4 + (int64_t)(int32_t)bw_ld32(win + q);
+        if (q2 + 36 <= total && !bam_plausible(win, q2, total, n_ref)) hit = false;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) { p = q0 + (__ffs((int)m) - 1); break; }
     }
+  if (lane != 0) return;
   int64_t n = 0;
   int flag = 0;
   if (p >= 0) {
@@ -89,39 +94,55 @@ __global__ void k_bam_walk_seg(const uint8_t* __restrict__ win, int64_t start, i
   seg_cnt[s] = n; seg_end_pos[s] = p; seg_end_flag[s] = flag;
 }
 
-__global__ void k_bam_walk_link(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t seg_len, int n_seg,
-                                const int64_t* __restrict__ seg_pos, int64_t seg_cap, const int64_t* __restrict__ seg_cnt,
-                                const int64_t* __restrict__ seg_end_pos, const int* __restrict__ seg_end_flag, int64_t* __restrict__ rec_off, int64_t cap,
-                                int64_t* __restrict__ res) {
-  int64_t cur = start, n = 0, err = 0, joined = 0;
-  bool stop = false;
-  for (int s = 0; s < n_seg && !stop; ++s) {
+// one CTA: thread 0 links, everybody copies the chains it accepts
+__global__ void __launch_bounds__(256) k_bam_walk_link(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t seg_len, int n_seg,
+                                                       const int64_t* __restrict__ seg_pos, int64_t seg_cap, const int64_t* __restrict__ seg_cnt,
+                                                       const int64_t* __restrict__ seg_end_pos, const int* __restrict__ seg_end_flag,
+                                                       int64_t* __restrict__ rec_off, int64_t cap, int64_t* __restrict__ res) {
+  __shared__ int64_t sh_cur, sh_n, sh_lo, sh_c;
+  __shared__ int sh_stop, sh_err, sh_joined;
+  if (threadIdx.x == 0) { sh_cur = start; sh_n = 0; sh_stop = 0; sh_err = 0; sh_joined = 0; }
+  __syncthreads();
+  for (int s = 0; s < n_seg; ++s) {
+    if (sh_stop) break;                               // uniform: written before the barrier below
     const int64_t a = start + (int64_t)s * seg_len, b = min(total, a + seg_len);
-    if (cur >= b) continue;                       // a record longer than the segment
     const int64_t* chain = seg_pos + (int64_t)s * seg_cap;
-    const int64_t c = seg_cnt[s];
-    while (cur < b) {
-      // is the true position on the guessed chain?
-      int64_t lo = 0, hi = c;
-      while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (chain[mid] < cur) lo = mid + 1; else hi = mid; }
-      if (lo < c && chain[lo] == cur && n + (c - lo) <= cap) {
-        for (int64_t k = lo; k < c; ++k) rec_off[n++] = chain[k] + 4;
-        cur = seg_end_pos[s];
-        ++joined;
-        if (seg_end_flag[s] == 1) stop = true;
-        if (seg_end_flag[s] == 2) { err = 1; stop = true; }
-        break;
+    if (threadIdx.x == 0) {
+      sh_lo = -1; sh_c = 0;
+      int64_t cur = sh_cur, n = sh_n;
+      const int64_t c = seg_cnt[s];
+      while (cur < b) {
+        // is the true position on the guessed chain?
+        int64_t lo = 0, hi = c;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (chain[mid] < cur) lo = mid + 1; else hi = mid; }
+        if (lo < c && chain[lo] == cur && n + (c - lo) <= cap) {
+          sh_lo = lo; sh_c = c;
+          cur = seg_end_pos[s];
+          ++sh_joined;
+          if (seg_end_flag[s] == 1) sh_stop = 1;
+          if (seg_end_flag[s] == 2) { sh_err = 1; sh_stop = 1; }
+          break;
+        }
+        // no: one hop of the true chain
+        if (cur + 4 > total || n >= cap) { sh_stop = 1; break; }
+        const int64_t bs = (int32_t)bw_ld32(win + cur);
+        if (bs < 32) { sh_err = 1; sh_stop = 1; break; }
+        if (cur + 4 + bs > total) { sh_stop = 1; break; }
+        rec_off[n++] = cur + 4;
+        cur += 4 + bs;
       }
-      // no: one hop of the true chain
-      if (cur + 4 > total || n >= cap) { stop = true; break; }
-      const int64_t bs = (int32_t)bw_ld32(win + cur);
-      if (bs < 32) { err = 1; stop = true; break; }
-      if (cur + 4 + bs > total) { stop = true; break; }
-      rec_off[n++] = cur + 4;
-      cur += 4 + bs;
+      sh_cur = cur; sh_n = n;
     }
+    __syncthreads();
+    if (sh_lo >= 0) {
+      const int64_t lo = sh_lo, c = sh_c, n0 = sh_n;
+      for (int64_t k = lo + threadIdx.x; k < c; k += blockDim.x) rec_off[n0 + (k - lo)] = chain[k] + 4;
+      __syncthreads();
+      if (threadIdx.x == 0) sh_n = n0 + (c - lo);
+    }
+    __syncthreads();
   }
-  res[0] = n; res[1] = cur; res[2] = err; res[3] = joined;
+  if (threadIdx.x == 0) { res[0] = sh_n; res[1] = sh_cur; res[2] = sh_err; res[3] = sh_joined; }
 }
 
 struct BamMeta {   // per record, device and host
@@ -403,9 +424,9 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
       int64_t* seg_cnt = static_cast<int64_t*>(s->seg_aux.p);
       int64_t* seg_end = seg_cnt + n_seg;
       int* seg_flag = reinterpret_cast<int*>(seg_end + n_seg);
-      k_bam_walk_seg<<<(n_seg + 31) / 32, 32>>>(static_cast<const uint8_t*>(s->win.p), start, total, seg_len, n_seg, s->n_ref, static_cast<int64_t*>(s->seg_pos.p), seg_cap,
+      k_bam_walk_seg<<<(n_seg + 3) / 4, 128>>>(static_cast<const uint8_t*>(s->win.p), start, total, seg_len, n_seg, s->n_ref, static_cast<int64_t*>(s->seg_pos.p), seg_cap,
                                                 seg_cnt, seg_end, seg_flag);
-      k_bam_walk_link<<<1, 1>>>(static_cast<const uint8_t*>(s->win.p), start, total, seg_len, n_seg, static_cast<const int64_t*>(s->seg_pos.p), seg_cap, seg_cnt, seg_end,
+      k_bam_walk_link<<<1, 256>>>(static_cast<const uint8_t*>(s->win.p), start, total, seg_len, n_seg, static_cast<const int64_t*>(s->seg_pos.p), seg_cap, seg_cnt, seg_end,
                                 seg_flag, static_cast<int64_t*>(s->rec_off.p), cap, static_cast<int64_t*>(s->res.p));
       fail(cudaGetLastError());
       fail(cudaMemcpy(res, s->res.p, sizeof(res), cudaMemcpyDeviceToHost));

@@ -115,7 +115,8 @@ class ByteBuf {
 // (k_bgzf_inflate_warp, one warp per member), pinned window buffers.  Files that are not BGZF go through plain zlib.
 class BgzfSource {
  public:
-  explicit BgzfSource(const std::string& path) : f_(fopen(path.c_str(), "rb")), gpu_(bgzf_gpu_device()) {
+  // window: compressed bytes per window, 0 = the default (a reader that only wants the BAM header asks for a small one)
+  explicit BgzfSource(const std::string& path, size_t window = 0) : f_(fopen(path.c_str(), "rb")), gpu_(bgzf_gpu_device()), window_(window) {
     if (!f_) return;
     uint8_t h[18];
     const size_t got = fread(h, 1, 18, f_);
@@ -223,7 +224,7 @@ class BgzfSource {
     }
   }
   size_t window_bytes() const {
-    size_t window = (size_t)64 << 20;             // compressed bytes per window (~5 k members: one wave of warps on the device)
+    size_t window = window_ ? window_ : (size_t)64 << 20;   // compressed bytes per window (~5 k members: one wave of warps on the device)
     if (const char* e = getenv("SVB_BGZF_WINDOW")) { const long long v = atoll(e); if (v > 0) window = (size_t)v; }   // tests: force records across windows
     return window;
   }
@@ -355,6 +356,7 @@ class BgzfSource {
   bool bgzf_ = false;
   std::unique_ptr<GzSource> plain_;
   int gpu_ = -1;
+  size_t window_ = 0;
   double t_read_ = 0, t_pin_ = 0, t_inflate_ = 0, t_pin_out_ = 0, t_wait_ = 0;   // SVB_BGZF_STATS=1 (the first two written by the reading task, the next two by the inflating one)
   unsigned long long n_windows_ = 0;
   ByteBuf out_, out_next_;
@@ -484,7 +486,7 @@ inline char nt16_char(unsigned c) { return "=ACMGRSVTWYHKDBN"[c & 15]; }
 
 class BamReader {
  public:
-  explicit BamReader(const std::string& path) : src_(path) {
+  explicit BamReader(const std::string& path, size_t window = 0) : src_(path, window) {
     if (!src_.ok()) return;
     char magic[4];
     int32_t l_text = 0, n_ref = 0;

@@ -372,7 +372,7 @@ static int search_bam_on_device(svb_index_t* idx, const Config& c, size_t gpu_ba
   {
     const int dev = bgzf_gpu_device();
     bgzf_gpu_device() = -1;                            // the header is read by the host reader
-    BamReader hdr(c.bam);
+    BamReader hdr(c.bam, (size_t)1 << 20);
     bgzf_gpu_device() = dev;
     if (!hdr.ok()) { logmsg("critical", "cannot read BAM " + c.bam); return -1; }
     header_bytes = hdr.header_bytes();
@@ -620,7 +620,7 @@ int main(int argc, char** argv) {
       if (!src.ok() || !src.device_inflate()) return EXIT_FAILURE;
       int64_t header_bytes = 0;
       int n_ref = 0;
-      { const int dev = bgzf_gpu_device(); bgzf_gpu_device() = -1; BamReader hdr(pos[0]); bgzf_gpu_device() = dev; if (!hdr.ok()) return EXIT_FAILURE; header_bytes = hdr.header_bytes(); n_ref = (int)hdr.ref_names().size(); }
+      { const int dev = bgzf_gpu_device(); bgzf_gpu_device() = -1; BamReader hdr(pos[0], (size_t)1 << 20); bgzf_gpu_device() = dev; if (!hdr.ok()) return EXIT_FAILURE; header_bytes = hdr.header_bytes(); n_ref = (int)hdr.ref_names().size(); }
       svb_bamstream_t* bs = nullptr;
       if (svb_bamstream_open(c.device, 1, n_ref, &bs) != SVB_OK) return EXIT_FAILURE;
       const uint8_t* base = nullptr;
