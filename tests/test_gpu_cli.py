@@ -126,12 +126,14 @@ def test_search_bam_filters_and_tags(world):
         want = expected_sfs_text(names, exp, htags, searched if putative else [True] * len(names), 4, 40, True)
         assert r.stdout == want
         # the same file with its BGZF windows inflated on the device (k_bgzf_inflate), one window and many small ones
-        for window, walk in ((None, None), ("3000", None), (None, "parallel"), ("20000", "parallel")):
+        for window, walk, submit in ((None, None, None), ("3000", None, None), (None, "parallel", None), ("20000", "parallel", None), ("9000", None, "30000")):
             env = dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0", SVB_BGZF_STATS="1")   # small files stay on the host threads by default
             if window:
                 env["SVB_BGZF_WINDOW"] = window
             if walk:
                 env["SVB_BAM_WALK"] = walk            # the segmented record walk, which windows under 1 MB would not use
+            if submit:
+                env["SVB_SEARCH_SUBMIT_BASES"] = submit   # many searches per file: results wait for the reads that complete their logical batch
             g = subprocess.run(args + ["--gpu-inflate"], capture_output=True, text=True, env=env)
             assert g.returncode == 0, g.stderr
             assert g.stdout == want
