@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "bam_core.cuh"
 
 namespace svb {
 
@@ -19,123 +20,66 @@ void launch_inflate(const uint8_t* d_in, const int64_t* d_io, const int64_t* d_o
 // record offsets of a window: one thread follows the block_size fields (each depends on the one before)
 __global__ void k_bam_walk(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t* __restrict__ rec_off, int64_t cap,
                            int64_t* __restrict__ res) {
-  int64_t p = start, n = 0, err = 0;
-  while (p + 4 <= total && n < cap) {
-    const uint32_t u = (uint32_t)win[p] | ((uint32_t)win[p + 1] << 8) | ((uint32_t)win[p + 2] << 16) | ((uint32_t)win[p + 3] << 24);
-    const int32_t bs = (int32_t)u;
-    if (bs < 32) { err = 1; break; }
-    if (p + 4 + (int64_t)bs > total) break;
-    rec_off[n++] = p + 4;
-    p += 4 + (int64_t)bs;
-  }
-  res[0] = n; res[1] = p; res[2] = err;
+  int64_t end = start;
+  int flag = 0;
+  const int64_t n = bam_chase(win, start, total, total, rec_off, cap, &end, &flag);
+  for (int64_t i = 0; i < n; ++i) rec_off[i] += 4;   // from the block_size field to the record
+  res[0] = n; res[1] = end; res[2] = flag == 2;
 }
 
 // ---- the same walk in parallel.  The chain of block_size fields is serial (11 ms for the 16 k records of a window:
-// every hop is a round trip to L2), so the window is cut into segments and a thread per segment GUESSES where a record
-// starts in it (first offset that looks like a record whose successors look like records too) and follows the chain to
-// the segment's end.  A second, single thread then links the segments: entering segment s at the true position, it
-// looks that position up in the segment's guessed chain -- found: the rest of the chain is the truth (the walk is
-// deterministic from any true record start); not found: it follows the fields itself until it meets the chain or
-// leaves the segment.  The guess only decides how fast the walk is, never what it returns.
-__device__ __forceinline__ uint32_t bw_ld32(const uint8_t* p) {
-  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-}
-__device__ __forceinline__ bool bam_plausible(const uint8_t* __restrict__ win, int64_t q, int64_t total, int n_ref) {
-  if (q + 36 > total) return false;
-  const int64_t bs = (int32_t)bw_ld32(win + q);
-  if (bs < 32 || bs > (1 << 28)) return false;
-  const int32_t tid = (int32_t)bw_ld32(win + q + 4), pos = (int32_t)bw_ld32(win + q + 8);
-  if (tid < -1 || tid >= n_ref || pos < -1) return false;
-  const int64_t l_read_name = win[q + 12], n_cigar = (int64_t)win[q + 16] | ((int64_t)win[q + 17] << 8);
-  const int64_t l_qseq = (int32_t)bw_ld32(win + q + 20);
-  if (l_read_name < 1 || l_qseq < 0) return false;
-  if (32 + l_read_name + 4 * n_cigar + (l_qseq + 1) / 2 + l_qseq > bs) return false;
-  const int64_t nul = q + 36 + l_read_name - 1;
-  if (nul < total && win[nul] != 0) return false;
-  if (l_read_name > 1 && q + 36 < total && win[q + 36] < 33) return false;   // a name starts with a printable character
-  return true;
-}
-
-// a warp per segment: the lanes test 32 consecutive offsets at a time, lane 0 follows the chain from the first hit
+// every hop is a round trip to L2), so the window is cut into segments and a warp per segment GUESSES where a record
+// starts in it (first offset that looks like a record whose successor looks like one too: the lanes test 32 offsets at
+// a time) and lane 0 follows the chain to the segment's end.  One CTA then links the segments: entering segment s at
+// the true position, thread 0 looks that position up in the segment's guessed chain -- found: the rest of the chain is
+// the truth (the walk is deterministic from any true record start) and everybody copies it; not found: it follows the
+// fields itself until it meets the chain or leaves the segment.  The guess only decides how fast the walk is, never
+// what it returns (bam_core.cuh; tests/test_bam_emul.py plants fake records in the payload).
 __global__ void __launch_bounds__(128) k_bam_walk_seg(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t seg_len, int n_seg, int n_ref,
                                                       int64_t* __restrict__ seg_pos, int64_t seg_cap, int64_t* __restrict__ seg_cnt,
                                                       int64_t* __restrict__ seg_end_pos, int* __restrict__ seg_end_flag) {
   const int s = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
   if (s >= n_seg) return;
   const int64_t a = start + (int64_t)s * seg_len, b = min(total, a + seg_len);
-  int64_t* out = seg_pos + (int64_t)s * seg_cap;
   int64_t p = -1;
   if (s == 0) p = a;
   else
     for (int64_t q0 = a; q0 < b; q0 += 32) {
       const int64_t q = q0 + lane;
-      bool hit = q < b && bam_plausible(win, q, total, n_ref);
-      if (hit) {
-        const int64_t q2 = q + 4 + (int64_t)(int32_t)bw_ld32(win + q);
-        if (q2 + 36 <= total && !bam_plausible(win, q2, total, n_ref)) hit = false;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      const unsigned m = __ballot_sync(0xffffffffu, q < b && bam_guess(win, q, total, n_ref));
       if (m) { p = q0 + (__ffs((int)m) - 1); break; }
     }
   if (lane != 0) return;
-  int64_t n = 0;
+  int64_t n = 0, end = p;
   int flag = 0;
-  if (p >= 0) {
-    while (p < b && n < seg_cap) {
-      if (p + 4 > total) { flag = 1; break; }
-      const int64_t bs = (int32_t)bw_ld32(win + p);
-      if (bs < 32) { flag = 2; break; }
-      if (p + 4 + bs > total) { flag = 1; break; }
-      out[n++] = p;
-      p += 4 + bs;
-    }
-  }
-  seg_cnt[s] = n; seg_end_pos[s] = p; seg_end_flag[s] = flag;
+  if (p >= 0) n = bam_chase(win, p, b, total, seg_pos + (int64_t)s * seg_cap, seg_cap, &end, &flag);
+  seg_cnt[s] = n; seg_end_pos[s] = end; seg_end_flag[s] = flag;
 }
 
-// one CTA: thread 0 links, everybody copies the chains it accepts
 __global__ void __launch_bounds__(256) k_bam_walk_link(const uint8_t* __restrict__ win, int64_t start, int64_t total, int64_t seg_len, int n_seg,
                                                        const int64_t* __restrict__ seg_pos, int64_t seg_cap, const int64_t* __restrict__ seg_cnt,
                                                        const int64_t* __restrict__ seg_end_pos, const int* __restrict__ seg_end_flag,
                                                        int64_t* __restrict__ rec_off, int64_t cap, int64_t* __restrict__ res) {
-  __shared__ int64_t sh_cur, sh_n, sh_lo, sh_c;
+  __shared__ int64_t sh_cur, sh_n, sh_join;
   __shared__ int sh_stop, sh_err, sh_joined;
   if (threadIdx.x == 0) { sh_cur = start; sh_n = 0; sh_stop = 0; sh_err = 0; sh_joined = 0; }
   __syncthreads();
   for (int s = 0; s < n_seg; ++s) {
-    if (sh_stop) break;                               // uniform: written before the barrier below
+    if (sh_stop) break;                               // uniform: written before the barrier at the end of the last round
     const int64_t a = start + (int64_t)s * seg_len, b = min(total, a + seg_len);
     const int64_t* chain = seg_pos + (int64_t)s * seg_cap;
+    const int64_t c = seg_cnt[s];
     if (threadIdx.x == 0) {
-      sh_lo = -1; sh_c = 0;
-      int64_t cur = sh_cur, n = sh_n;
-      const int64_t c = seg_cnt[s];
-      while (cur < b) {
-        // is the true position on the guessed chain?
-        int64_t lo = 0, hi = c;
-        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (chain[mid] < cur) lo = mid + 1; else hi = mid; }
-        if (lo < c && chain[lo] == cur && n + (c - lo) <= cap) {
-          sh_lo = lo; sh_c = c;
-          cur = seg_end_pos[s];
-          ++sh_joined;
-          if (seg_end_flag[s] == 1) sh_stop = 1;
-          if (seg_end_flag[s] == 2) { sh_err = 1; sh_stop = 1; }
-          break;
-        }
-        // no: one hop of the true chain
-        if (cur + 4 > total || n >= cap) { sh_stop = 1; break; }
-        const int64_t bs = (int32_t)bw_ld32(win + cur);
-        if (bs < 32) { sh_err = 1; sh_stop = 1; break; }
-        if (cur + 4 + bs > total) { sh_stop = 1; break; }
-        rec_off[n++] = cur + 4;
-        cur += 4 + bs;
-      }
-      sh_cur = cur; sh_n = n;
+      int64_t cur = sh_cur, n = sh_n, join = -1;
+      int err = 0;
+      if (!bam_link_segment(win, b, total, chain, c, seg_end_pos[s], seg_end_flag[s], rec_off, cap, &cur, &n, &join, &err)) sh_stop = 1;
+      if (err) sh_err = 1;
+      if (join >= 0) ++sh_joined;
+      sh_cur = cur; sh_n = n; sh_join = join;
     }
     __syncthreads();
-    if (sh_lo >= 0) {
-      const int64_t lo = sh_lo, c = sh_c, n0 = sh_n;
+    if (sh_join >= 0) {
+      const int64_t lo = sh_join, n0 = sh_n;
       for (int64_t k = lo + threadIdx.x; k < c; k += blockDim.x) rec_off[n0 + (k - lo)] = chain[k] + 4;
       __syncthreads();
       if (threadIdx.x == 0) sh_n = n0 + (c - lo);
@@ -145,76 +89,15 @@ __global__ void __launch_bounds__(256) k_bam_walk_link(const uint8_t* __restrict
   if (threadIdx.x == 0) { res[0] = sh_n; res[1] = sh_cur; res[2] = sh_err; res[3] = sh_joined; }
 }
 
-struct BamMeta {   // per record, device and host
-  int32_t tid, l_qseq, xf, hp;
-  uint16_t flag;
-  uint8_t state;     // 0 dropped by the flag filter, 3 dropped for l_qseq < 100, 1 kept but not searched, 2 searched
-  uint8_t name_len;  // without the NUL
-};
-
-__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
-__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return ld16(p) | (ld16(p + 2) << 16); }
-
-// one thread per record: BAM spec 4.2 core fields, then the aux walk host/io.hpp's BamReader::next does
+// one thread per record (bam_parse_record)
 __global__ void k_bam_parse(const uint8_t* __restrict__ win, const int64_t* __restrict__ rec_off, int64_t n, int putative,
                             BamMeta* __restrict__ meta, int64_t* __restrict__ seq_off, int* __restrict__ err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint8_t* p = win + rec_off[i];
-  const int64_t bs = (int64_t)(int32_t)ld32(p - 4);
   BamMeta m;
-  m.tid = (int32_t)ld32(p);
-  const unsigned l_read_name = p[8];
-  const unsigned n_cigar = ld16(p + 12);
-  m.flag = (uint16_t)ld16(p + 14);
-  m.l_qseq = (int32_t)ld32(p + 16);
-  m.xf = 0; m.hp = 0;
-  m.name_len = (uint8_t)(l_read_name ? l_read_name - 1 : 0);
-  int64_t o = 32 + (int64_t)l_read_name + 4 * (int64_t)n_cigar;
-  const int64_t seq_bytes = ((int64_t)m.l_qseq + 1) / 2;
-  bool bad = m.l_qseq < 0 || o > bs || o + seq_bytes + (int64_t)m.l_qseq > bs;
-  seq_off[i] = rec_off[i] + o;
-  bool has_xf = false;
-  if (!bad) {
-    o += seq_bytes + m.l_qseq;
-    while (o + 3 <= bs) {
-      const char t0 = (char)p[o], t1 = (char)p[o + 1], ty = (char)p[o + 2];
-      o += 3;
-      int64_t iv = 0;
-      bool is_int = false;
-      switch (ty) {
-        case 'A': o += 1; break;
-        case 'c': iv = (int8_t)p[o]; is_int = true; o += 1; break;
-        case 'C': iv = p[o]; is_int = true; o += 1; break;
-        case 's': iv = (int16_t)ld16(p + o); is_int = true; o += 2; break;
-        case 'S': iv = ld16(p + o); is_int = true; o += 2; break;
-        case 'i': iv = (int32_t)ld32(p + o); is_int = true; o += 4; break;
-        case 'I': iv = ld32(p + o); is_int = true; o += 4; break;
-        case 'f': o += 4; break;
-        case 'd': o += 8; break;
-        case 'Z': case 'H': while (o < bs && p[o]) ++o; ++o; break;
-        case 'B': {
-          if (o + 5 > bs) { bad = true; break; }
-          const char st = (char)p[o];
-          const int32_t cnt = (int32_t)ld32(p + o + 1);
-          const int64_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
-          const int64_t bytes = es * (int64_t)(cnt < 0 ? 0 : cnt);
-          if (o + 5 + bytes > bs) { bad = true; break; }
-          o += 5 + bytes;
-          break;
-        }
-        default: bad = true; break;
-      }
-      if (bad || o > bs) { bad = true; break; }
-      if (is_int && t0 == 'X' && t1 == 'F') { has_xf = true; m.xf = (int32_t)iv; }
-      if (is_int && t0 == 'H' && t1 == 'P') m.hp = (int32_t)iv;
-    }
-  }
-  if (bad) { atomicExch(err, 1); m.state = 0; m.name_len = 0; }
-  else if (m.flag & (0x4 | 0x800 | 0x100)) m.state = 0;                 // ping_pong.cpp:66-69
-  else if (m.l_qseq < 100) m.state = 3;                                  // :70-75
-  else m.state = (putative && has_xf && m.xf != 0) ? 1 : 2;              // :196-203
-  if (m.state == 0 || m.state == 3) m.name_len = 0;   // the host hears about them (a warning per short record) but needs no name
+  int64_t rel = 0;
+  if (!bam_parse_record(win + rec_off[i], putative, &m, &rel)) atomicExch(err, 1);
+  seq_off[i] = rec_off[i] + rel;
   meta[i] = m;
 }
 
@@ -284,7 +167,7 @@ __global__ void __launch_bounds__(128) k_bam_gather(const uint8_t* __restrict__ 
   for (int k = threadIdx.x; k < m.l_qseq; k += blockDim.x) {
     const uint8_t b = s[k >> 1];
     const unsigned c = (k & 1) ? (b & 0xfu) : (b >> 4);
-    d[k] = c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 5;
+    d[k] = bam_nt6_of_nt16(c);
   }
   if (threadIdx.x == 0) batch_offs[batch_reads + rank[i] + 1] = batch_bases + base_off[i] + m.l_qseq;
 }
