@@ -142,7 +142,7 @@ SVB_API int svb_sfs_batch_bam4(const svb_index_t* idx, const uint8_t* seq4, cons
 SVB_API int svb_pack4_device(const uint8_t* d_nt6_concat, const int64_t* d_offs /* n_reads+1 */,
                              const int64_t* d_seq4_offs /* n_reads+1 */, int64_t n_reads, int device, uint8_t* d_out);
 
-/* Host utility (building block, not yet on the search path): re-pack reads from BAM's 4 bits per base to
+/* Host utility (used by the streamed search with SVB_STREAM_PACK2=1, off by default: slower on a 16-core host): re-pack reads from BAM's 4 bits per base to
  * 2 bits per base with all host threads (threads <= 0) -- half the bytes again for the H2D copy that bounds
  * the end-to-end search.  Read r goes to (l_qseq[r] + 3) / 4 bytes at out_offs[r], first base in the two high
  * bits, A C G T -> 0 1 2 3; exception[r] = 1 if the read holds any other code (it then has to travel as it is). */

@@ -1,12 +1,13 @@
 // BGZF members inflated on the device (second half: the CLI stages are bound by host inflate --
 // the reference spreads it over htslib's bgzf_mt threads, ping_pong.cpp:249, clusterer.cpp:13).  A BGZF member
 // is an independent raw-deflate stream of at most 64 KiB of payload, so a window of a BAM file is thousands of
-// independent jobs: one THREAD per member, canonical-Huffman decode by code-length counts (no look-up tables to
-// build: 16 counts + the symbols in code order, 1.3 KB of local memory per thread), output written straight to
-// its place in the window, back-references read from there (a member never refers across its own start).
-// Round-1 state: a building block, checked on the CPU through tests/emul against zlib and on the GPU by
-// svb_bgzf_inflate_device; round 2: BgzfSource uses it with `--gpu-inflate` (host/io.hpp).  Free of host
-// code so that tests/emul compiles it for the CPU.
+// independent jobs.  Two kernels: k_bgzf_inflate, one THREAD per member (round 1: canonical-Huffman decode by
+// code-length counts -- no look-up tables to build: 16 counts + the symbols in code order, 1.3 KB of local memory per
+// thread), and k_bgzf_inflate_warp further down, one WARP per member (round 2, the default: look-up tables in shared
+// memory, queued copies).  Output is written straight to its place in the window, back-references are read from there
+// (a member never refers across its own start).  Checked on the CPU through tests/emul against zlib and on the GPU by
+// svb_bgzf_inflate_device; BgzfSource (host/io.hpp) and the device BAM loader (bam_stream.cu) use it with
+// `--gpu-inflate`.  Free of host code so that tests/emul compiles it for the CPU.
 //
 // RFC 1951 restated: a stream is a sequence of blocks, each with a 3-bit header (BFINAL, BTYPE).  BTYPE 0:
 // skip to a byte boundary, LEN, ~LEN, LEN literal bytes.  BTYPE 1: the fixed code (literal/length lengths 8,9,7,8
