@@ -196,8 +196,15 @@ typedef struct {
   const char* names;
   int64_t batch_reads, batch_bases;   /* the device batch after this window                                         */
   int64_t h2d_bytes, d2h_bytes;
+  /* alignment mode only (svb_bamstream_open with putative < 0), else NULL: what the Clusterer's scan reads of a record
+   * (clusterer.cpp:58-153); state is then 0, 3 or 1 and no bases are batched */
+  const int32_t* pos;        /* bam1_core_t::pos                                                                    */
+  const int32_t* endpos;     /* bam_endpos                                                                          */
+  const int32_t* n_cigar;    /* ops of the CIGAR in force (the CG:B,I tag's when the field holds the placeholder)   */
+  const uint8_t* mapq;
 } svb_bam_recs_t;
-/* putative: the XF rule of ping_pong.cpp:202 (--noputative = 0); n_ref: reference sequences in the BAM header (the record walk
+/* putative: 1 = the XF rule of ping_pong.cpp:202, 0 = --noputative, -1 = alignment mode (no search batch: the Clusterer's
+ * scan, see svb_bam_recs_t and svb_bamstream_fetch); n_ref: reference sequences in the BAM header (the record walk
  * uses it to tell a record start from payload; <= 0 if unknown) */
 SVB_API int svb_bamstream_open(int device, int putative, int n_ref, svb_bamstream_t** out);
 /* One window: n_members BGZF members as svb_bgzf_inflate_device takes them (host buffers).  skip_bytes (first call
@@ -206,6 +213,10 @@ SVB_API int svb_bamstream_open(int device, int putative, int n_ref, svb_bamstrea
 SVB_API int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, const int64_t* in_offs /* n_members+1 */,
                                  const int64_t* out_offs /* n_members+1 */, int64_t n_members, int64_t skip_bytes,
                                  svb_bam_recs_t* recs);
+/* Alignment mode: CIGAR ops and packed bases (BAM's 4 bits per base) of n_rec records of the LAST window (indices into
+ * its svb_bam_recs_t, ascending or not), back to back; the arrays belong to the stream until its next call. */
+SVB_API int svb_bamstream_fetch(svb_bamstream_t* s, const int64_t* rec, int64_t n_rec, const uint32_t** cigar,
+                                const int64_t** cigar_offs /* n_rec+1 */, const uint8_t** seq4, const int64_t** seq4_offs /* n_rec+1, bytes */);
 /* bytes of an unfinished record left behind the last window: not 0 at the end of the file = truncated BAM */
 SVB_API int64_t svb_bamstream_pending_bytes(const svb_bamstream_t* s);
 /* svb_sfs_resident over the reads batched so far (read r of the result = the r-th record of state 2 since the last

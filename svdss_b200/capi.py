@@ -99,7 +99,7 @@ EXPORTS = [
     "svb_sfs_batch", "svb_sfs_batch_bam4", "svb_pack4_device", "svb_pack2_host", "svb_pack2_chunk", "svb_unpack2_device", "svb_bgzf_inflate_device", "svb_reads_upload", "svb_reads_free", "svb_sfs_resident", "svb_sfs_out_free",
     "svb_ksw_extd2_batch", "svb_ksw_out_free",
     "svb_poa_batch", "svb_poa_out_free",
-    "svb_cluster_batch", "svb_clusters_free", "svb_call_batch", "svb_calls_free", "svb_index_ref", "svb_host_alloc_pinned", "svb_host_free_pinned", "svb_bamstream_open", "svb_bamstream_window", "svb_bamstream_pending_bytes", "svb_bamstream_search", "svb_bamstream_close",
+    "svb_cluster_batch", "svb_clusters_free", "svb_call_batch", "svb_calls_free", "svb_index_ref", "svb_host_alloc_pinned", "svb_host_free_pinned", "svb_bamstream_open", "svb_bamstream_window", "svb_bamstream_pending_bytes", "svb_bamstream_fetch", "svb_bamstream_search", "svb_bamstream_close",
 ]
 
 

@@ -24,6 +24,13 @@ struct BamMeta {   // per record, device and host
   uint8_t name_len;  // without the NUL; 0 for dropped records
 };
 
+struct BamAln {     // the alignment of a record, for the Clusterer's scan (clusterer.cpp:58-153)
+  int32_t pos, endpos;   // bam1_core_t::pos, bam_endpos (pos + reference span of the CIGAR, pos + 1 for an empty span)
+  int32_t n_cigar;       // ops of the CIGAR in force: the field's, or the CG:B,I tag's when the field holds the placeholder
+  int32_t cigar_rel;     // where those ops lie, relative to the record
+  uint8_t mapq, pad[3];
+};
+
 SVB_HD uint32_t bam_ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 SVB_HD uint32_t bam_ld32(const uint8_t* p) { return bam_ld16(p) | (bam_ld16(p + 2) << 16); }
 
@@ -97,7 +104,7 @@ SVB_HD bool bam_link_segment(const uint8_t* win, int64_t b, int64_t total, const
 // One record (p = its first byte after block_size): BAM spec 4.2 core fields, then the aux walk of host/io.hpp's
 // BamReader::next; the load filters of ping_pong.cpp:66-75 and the XF rule of :196-203.  Returns false for a record
 // whose fields run past its block_size.
-SVB_HD bool bam_parse_record(const uint8_t* p, int putative, BamMeta* out, int64_t* seq_rel) {
+SVB_HD bool bam_parse_record(const uint8_t* p, int putative, BamMeta* out, int64_t* seq_rel, BamAln* aln = nullptr) {
   const int64_t bs = (int64_t)(int32_t)bam_ld32(p - 4);
   BamMeta m;
   m.tid = (int32_t)bam_ld32(p);
@@ -112,6 +119,7 @@ SVB_HD bool bam_parse_record(const uint8_t* p, int putative, BamMeta* out, int64
   bool bad = m.l_qseq < 0 || o > bs || o + seq_bytes + (int64_t)m.l_qseq > bs;
   *seq_rel = o;
   bool has_xf = false;
+  int64_t cg_rel = 32 + (int64_t)l_read_name, cg_n = n_cigar;     // the CIGAR in force
   if (!bad) {
     o += seq_bytes + m.l_qseq;
     while (o + 3 <= bs) {
@@ -137,6 +145,12 @@ SVB_HD bool bam_parse_record(const uint8_t* p, int putative, BamMeta* out, int64
           const int64_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
           const int64_t bytes = es * (int64_t)(cnt < 0 ? 0 : cnt);
           if (o + 5 + bytes > bs) { bad = true; break; }
+          // CG:B,I -- the real CIGAR of a record with more than 65535 ops, whose CIGAR field then holds the placeholder
+          // <l_seq>S<ref_len>N (SAM spec 4.2.2; htslib's sam_read1 swaps it in, as does host/io.hpp)
+          if (t0 == 'C' && t1 == 'G' && st == 'I' && cnt > 0 && n_cigar == 2) {
+            const uint32_t c0 = bam_ld32(p + 32 + l_read_name), c1 = bam_ld32(p + 32 + l_read_name + 4);
+            if ((c0 & 0xf) == 4 && (int32_t)(c0 >> 4) == m.l_qseq && (c1 & 0xf) == 3) { cg_rel = o + 5; cg_n = cnt; }
+          }
           o += 5 + bytes;
           break;
         }
@@ -148,11 +162,26 @@ SVB_HD bool bam_parse_record(const uint8_t* p, int putative, BamMeta* out, int64
     }
   }
   if (bad) m.state = 0;
-  else if (m.flag & (0x4 | 0x800 | 0x100)) m.state = 0;                 // ping_pong.cpp:66-69
+  else if (m.flag & (0x4 | 0x800 | 0x100)) m.state = 0;                 // ping_pong.cpp:66-69 = clusterer.cpp:116-120
+  else if (aln) m.state = 1;                                             // the Clusterer's scan has no length filter and batches nothing
   else if (m.l_qseq < 100) m.state = 3;                                  // :70-75
   else m.state = (putative && has_xf && m.xf != 0) ? 1 : 2;              // :196-203
   if (m.state == 0 || m.state == 3) m.name_len = 0;   // the host hears about them (a warning per short record) but needs no name
   *out = m;
+  if (aln) {
+    BamAln al;
+    al.pos = (int32_t)bam_ld32(p + 4);
+    al.mapq = p[9]; al.pad[0] = al.pad[1] = al.pad[2] = 0;
+    al.n_cigar = bad ? 0 : (int32_t)cg_n;
+    al.cigar_rel = (int32_t)cg_rel;
+    int64_t span = 0;
+    for (int64_t k = 0; k < al.n_cigar; ++k) {
+      const uint32_t c = bam_ld32(p + cg_rel + 4 * k), op = c & 0xf;
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4;
+    }
+    al.endpos = (int32_t)(al.pos + (span ? span : 1));
+    *aln = al;
+  }
   return !bad;
 }
 

@@ -91,14 +91,31 @@ __global__ void __launch_bounds__(256) k_bam_walk_link(const uint8_t* __restrict
 
 // one thread per record (bam_parse_record)
 __global__ void k_bam_parse(const uint8_t* __restrict__ win, const int64_t* __restrict__ rec_off, int64_t n, int putative,
-                            BamMeta* __restrict__ meta, int64_t* __restrict__ seq_off, int* __restrict__ err) {
+                            BamMeta* __restrict__ meta, int64_t* __restrict__ seq_off, BamAln* __restrict__ aln, int* __restrict__ err) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   BamMeta m;
+  BamAln al;
   int64_t rel = 0;
-  if (!bam_parse_record(win + rec_off[i], putative, &m, &rel)) atomicExch(err, 1);
+  if (!bam_parse_record(win + rec_off[i], putative, &m, &rel, aln ? &al : nullptr)) atomicExch(err, 1);
+  if (aln) aln[i] = al;
   seq_off[i] = rec_off[i] + rel;
   meta[i] = m;
+}
+
+// svb_bamstream_fetch: CIGAR words and packed bases of the selected records of the window, back to back
+__global__ void __launch_bounds__(128) k_bam_fetch(const uint8_t* __restrict__ win, const int64_t* __restrict__ rec_off, const int64_t* __restrict__ seq_off,
+                                                   const BamMeta* __restrict__ meta, const BamAln* __restrict__ aln, const int64_t* __restrict__ sel,
+                                                   const int64_t* __restrict__ cig_offs, const int64_t* __restrict__ seq_offs, uint32_t* __restrict__ cig,
+                                                   uint8_t* __restrict__ seq) {
+  const int64_t i = sel[blockIdx.x];
+  const uint8_t* c = win + rec_off[i] + aln[i].cigar_rel;
+  uint32_t* co = cig + cig_offs[blockIdx.x];
+  for (int k = threadIdx.x; k < aln[i].n_cigar; k += blockDim.x) co[k] = bam_ld32(c + 4 * (int64_t)k);
+  const uint8_t* q = win + seq_off[i];
+  uint8_t* so = seq + seq_offs[blockIdx.x];
+  const int nb = (meta[i].l_qseq + 1) / 2;
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) so[k] = q[k];
 }
 
 // exclusive sums over the records of a window: name bytes of the records the host hears about, bases and count of the searched ones
@@ -204,7 +221,16 @@ struct svb_bamstream {
   int64_t skip_left = 0;       // bytes of the BAM header not yet passed
   bool skip_set = false;
   int64_t carry = 0;           // bytes of an unfinished record at the front of win
-  DevBuf comp, io, oo, st, win, rec_off, seq_off, meta, name_off, base_off, rank, names, sums, res, err, seg_pos, seg_aux;
+  DevBuf comp, io, oo, st, win, rec_off, seq_off, meta, name_off, base_off, rank, names, sums, res, err, seg_pos, seg_aux, aln, sel, f_co, f_so, f_cig, f_seq;
+  bool align_mode = false;     // svb_bamstream_open with putative < 0: the Clusterer's scan -- alignments instead of a search batch
+  int64_t n_last = 0;          // records of the last window (what svb_bamstream_fetch indexes)
+  int64_t tail_from = 0, tail_len = 0;   // alignment mode: the unfinished record still sits at win[tail_from, +tail_len)
+  std::vector<BamAln> h_aln;
+  std::vector<int32_t> a_pos, a_end, a_ncig;
+  std::vector<uint8_t> a_mapq;
+  std::vector<uint32_t> f_hcig;
+  std::vector<uint8_t> f_hseq;
+  std::vector<int64_t> f_hco, f_hso;
   int n_ref = 1 << 30;         // reference sequences of the header (svb_bamstream_set_refs): the walk's plausibility test uses it
   DevBuf batch, batch_offs;
   int64_t batch_reads = 0, batch_bases = 0;
@@ -222,7 +248,8 @@ extern "C" int svb_bamstream_open(int device, int putative, int n_ref, svb_bamst
   SVB_TRY(check_device(device));
   svb_bamstream* s = new svb_bamstream();
   s->device = device;
-  s->putative = putative ? 1 : 0;
+  s->putative = putative > 0 ? 1 : 0;
+  s->align_mode = putative < 0;
   if (n_ref > 0) s->n_ref = n_ref;
   *out = s;
   return SVB_OK;
@@ -232,7 +259,7 @@ extern "C" void svb_bamstream_close(svb_bamstream_t* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   for (DevBuf* b : {&s->comp, &s->io, &s->oo, &s->st, &s->win, &s->rec_off, &s->seq_off, &s->meta, &s->name_off, &s->base_off, &s->rank, &s->names,
-                    &s->sums, &s->res, &s->err, &s->seg_pos, &s->seg_aux, &s->batch, &s->batch_offs})
+                    &s->sums, &s->res, &s->err, &s->seg_pos, &s->seg_aux, &s->aln, &s->sel, &s->f_co, &s->f_so, &s->f_cig, &s->f_seq, &s->batch, &s->batch_offs})
     b->release();
   cudaStreamSynchronize(0);
   delete s;
@@ -257,6 +284,20 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
   int rc = SVB_OK;
   StageLog slog("bamstream");
   auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == SVB_OK) { set_error("svb_bamstream_window: %s", cudaGetErrorString(e)); rc = SVB_ECUDA; } };
+  if (s->align_mode && s->tail_len > 0 && s->tail_from > 0) {   // the move deferred by the last call (see below)
+    if (s->tail_len <= s->tail_from) fail(cudaMemcpyAsync(s->win.p, static_cast<uint8_t*>(s->win.p) + s->tail_from, (size_t)s->tail_len, cudaMemcpyDeviceToDevice, 0));
+    else {
+      void* tmp = nullptr;
+      fail(pmalloc(&tmp, (size_t)s->tail_len, 0));
+      if (rc == SVB_OK) {
+        fail(cudaMemcpyAsync(tmp, static_cast<uint8_t*>(s->win.p) + s->tail_from, (size_t)s->tail_len, cudaMemcpyDeviceToDevice, 0));
+        fail(cudaMemcpyAsync(s->win.p, tmp, (size_t)s->tail_len, cudaMemcpyDeviceToDevice, 0));
+      }
+      pfree(tmp, 0);
+    }
+    s->tail_from = 0;
+  }
+  s->n_last = 0;
   // ---- inflate behind the carried tail
   const int64_t total = s->carry + out_total;
   fail(s->win.need((size_t)total + 64, (size_t)s->carry));
@@ -332,8 +373,10 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
     fail(s->err.need(4));
     if (rc == SVB_OK) {
       fail(cudaMemsetAsync(s->err.p, 0, 4, 0));
+      if (s->align_mode) fail(s->aln.need((size_t)n * sizeof(BamAln)));
       k_bam_parse<<<(unsigned)((n + 127) / 128), 128>>>(static_cast<const uint8_t*>(s->win.p), static_cast<const int64_t*>(s->rec_off.p), n, s->putative,
-                                                          static_cast<BamMeta*>(s->meta.p), static_cast<int64_t*>(s->seq_off.p), static_cast<int*>(s->err.p));
+                                                          static_cast<BamMeta*>(s->meta.p), static_cast<int64_t*>(s->seq_off.p),
+                                                          s->align_mode ? static_cast<BamAln*>(s->aln.p) : nullptr, static_cast<int*>(s->err.p));
       k_bam_scan<<<1, 1024>>>(static_cast<const BamMeta*>(s->meta.p), n, static_cast<int64_t*>(s->name_off.p), static_cast<int64_t*>(s->base_off.p),
                               static_cast<int64_t*>(s->rank.p), static_cast<BamSums*>(s->sums.p));
       fail(cudaGetLastError());
@@ -361,6 +404,7 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
       fail(cudaMemcpy(s->h_meta.data(), s->meta.p, (size_t)n * sizeof(BamMeta), cudaMemcpyDeviceToHost));
       fail(cudaMemcpy(s->h_name_off.data(), s->name_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost));
       if (sums.names) fail(cudaMemcpy(s->h_names.data(), s->names.p, (size_t)sums.names, cudaMemcpyDeviceToHost));
+      if (s->align_mode) { s->h_aln.resize((size_t)n); fail(cudaMemcpy(s->h_aln.data(), s->aln.p, (size_t)n * sizeof(BamAln), cudaMemcpyDeviceToHost)); }
     }
     if (rc != SVB_OK) return rc;
     s->batch_reads += sums.reads;
@@ -369,9 +413,13 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
     s->h_meta.clear(); s->h_name_off.assign(1, 0); s->h_names.assign(1, 0);
   }
   slog.lap("parse + scan + gather + D2H");
-  // ---- what is left of the window is the head of a record the next window completes
+  // ---- what is left of the window is the head of a record the next window completes (the move does not touch the
+  // records before p_end when left <= p_end; in alignment mode svb_bamstream_fetch reads them after this call, so there
+  // the tail is moved at the start of the next call instead)
   const int64_t left = total - p_end;
-  if (left > 0 && p_end > 0) {
+  s->n_last = n;
+  if (s->align_mode) { s->tail_from = p_end; s->tail_len = left; s->carry = left; }
+  else if (left > 0 && p_end > 0) {
     if (left <= p_end) fail(cudaMemcpyAsync(s->win.p, static_cast<uint8_t*>(s->win.p) + p_end, (size_t)left, cudaMemcpyDeviceToDevice, 0));
     else {   // overlapping ranges: through a scratch buffer
       void* tmp = nullptr;
@@ -383,7 +431,7 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
       pfree(tmp, 0);
     }
   }
-  s->carry = left;
+  if (!s->align_mode) s->carry = left;
   fail(cudaStreamSynchronize(0));
   if (rc != SVB_OK) return rc;
   // ---- the caller's view
@@ -397,6 +445,14 @@ extern "C" int svb_bamstream_window(svb_bamstream_t* s, const uint8_t* comp, con
   recs->flag = s->flag.data(); recs->tid = s->tid.data(); recs->l_qseq = s->l_qseq.data(); recs->xf = s->xf.data(); recs->hp = s->hp.data();
   recs->state = s->state.data(); recs->name_offs = s->h_name_off.data(); recs->names = s->h_names.data();
   recs->batch_reads = s->batch_reads; recs->batch_bases = s->batch_bases;
+  if (s->align_mode) {
+    s->a_pos.resize((size_t)n); s->a_end.resize((size_t)n); s->a_ncig.resize((size_t)n); s->a_mapq.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      const BamAln& al = s->h_aln[(size_t)i];
+      s->a_pos[(size_t)i] = al.pos; s->a_end[(size_t)i] = al.endpos; s->a_ncig[(size_t)i] = al.n_cigar; s->a_mapq[(size_t)i] = al.mapq;
+    }
+    recs->pos = s->a_pos.data(); recs->endpos = s->a_end.data(); recs->n_cigar = s->a_ncig.data(); recs->mapq = s->a_mapq.data();
+  }
   recs->h2d_bytes = in_total + (n_members + 1) * 16;
   recs->d2h_bytes = n * (int64_t)sizeof(BamMeta) + (n + 1) * 8 + sums.names + n_members * 4;
   return SVB_OK;
@@ -419,4 +475,40 @@ extern "C" int svb_bamstream_search(svb_bamstream_t* s, const svb_index_t* idx, 
   s->batch_reads = 0;
   s->batch_bases = 0;
   return rc;
+}
+
+extern "C" int svb_bamstream_fetch(svb_bamstream_t* s, const int64_t* rec, int64_t n_rec, const uint32_t** cigar, const int64_t** cigar_offs,
+                                   const uint8_t** seq4, const int64_t** seq4_offs) {
+  if (!s || !s->align_mode || n_rec < 0 || (n_rec > 0 && !rec) || !cigar || !cigar_offs || !seq4 || !seq4_offs) {
+    set_error("svb_bamstream_fetch: bad arguments (the stream must be opened for alignments)"); return SVB_EINVAL;
+  }
+  SVB_TRY(check_device(s->device));
+  s->f_hco.assign((size_t)n_rec + 1, 0); s->f_hso.assign((size_t)n_rec + 1, 0);
+  for (int64_t k = 0; k < n_rec; ++k) {
+    if (rec[k] < 0 || rec[k] >= s->n_last) { set_error("svb_bamstream_fetch: record %lld is not of the last window", (long long)rec[k]); return SVB_EINVAL; }
+    s->f_hco[(size_t)k + 1] = s->f_hco[(size_t)k] + s->h_aln[(size_t)rec[k]].n_cigar;
+    s->f_hso[(size_t)k + 1] = s->f_hso[(size_t)k] + ((int64_t)s->h_meta[(size_t)rec[k]].l_qseq + 1) / 2;
+  }
+  const int64_t nc = s->f_hco[(size_t)n_rec], ns = s->f_hso[(size_t)n_rec];
+  s->f_hcig.resize((size_t)std::max<int64_t>(nc, 1)); s->f_hseq.resize((size_t)std::max<int64_t>(ns, 1));
+  if (n_rec) {
+    SVB_CUDA(s->sel.need((size_t)n_rec * 8));
+    SVB_CUDA(s->f_co.need((size_t)(n_rec + 1) * 8));
+    SVB_CUDA(s->f_so.need((size_t)(n_rec + 1) * 8));
+    SVB_CUDA(s->f_cig.need((size_t)std::max<int64_t>(nc, 1) * 4));
+    SVB_CUDA(s->f_seq.need((size_t)std::max<int64_t>(ns, 1)));
+    SVB_CUDA(cudaMemcpyAsync(s->sel.p, rec, (size_t)n_rec * 8, cudaMemcpyHostToDevice, 0));
+    SVB_CUDA(cudaMemcpyAsync(s->f_co.p, s->f_hco.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, 0));
+    SVB_CUDA(cudaMemcpyAsync(s->f_so.p, s->f_hso.data(), (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, 0));
+    k_bam_fetch<<<(unsigned)n_rec, 128>>>(static_cast<const uint8_t*>(s->win.p), static_cast<const int64_t*>(s->rec_off.p), static_cast<const int64_t*>(s->seq_off.p),
+                                          static_cast<const BamMeta*>(s->meta.p), static_cast<const BamAln*>(s->aln.p), static_cast<const int64_t*>(s->sel.p),
+                                          static_cast<const int64_t*>(s->f_co.p), static_cast<const int64_t*>(s->f_so.p), static_cast<uint32_t*>(s->f_cig.p),
+                                          static_cast<uint8_t*>(s->f_seq.p));
+    SVB_CUDA(cudaGetLastError());
+    if (nc) SVB_CUDA(cudaMemcpy(s->f_hcig.data(), s->f_cig.p, (size_t)nc * 4, cudaMemcpyDeviceToHost));
+    if (ns) SVB_CUDA(cudaMemcpy(s->f_hseq.data(), s->f_seq.p, (size_t)ns, cudaMemcpyDeviceToHost));
+    SVB_CUDA(cudaStreamSynchronize(0));
+  }
+  *cigar = s->f_hcig.data(); *cigar_offs = s->f_hco.data(); *seq4 = s->f_hseq.data(); *seq4_offs = s->f_hso.data();
+  return SVB_OK;
 }

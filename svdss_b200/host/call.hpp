@@ -282,6 +282,7 @@ inline int run_call(const CallConfig& c, void (*log)(const char*, const std::str
     Clusterer C(cc, &sfss, &seqs);
     log("info", "Placing SFSs on reference genome");
     if (!C.run()) { log("critical", C.error.empty() ? "cannot write " + c.clusters_out : C.error); return 1; }
+    if (C.scanned_on_device) log("info", "BAM records decoded on GPU " + std::to_string(c.device));
     log("info", std::to_string(C.unplaced) + "/" + std::to_string(C.s_unplaced) + "/" + std::to_string(C.e_unplaced) +
                     " unplaced SFSs. " + std::to_string(C.unknown) + " erroneus SFSs. " + std::to_string(C.clips.size()) + " clipped SFSs.");
     log("info", "Clustered " + std::to_string(C.n_extended) + " SFSs. Maximum extended SFS length: " + std::to_string(C.max_ext_len) +

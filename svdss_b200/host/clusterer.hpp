@@ -113,6 +113,7 @@ class Clusterer {
   size_t n_extended = 0;
   int max_ext_len = 0, dist = 0;
   std::string error;
+  bool scanned_on_device = false;   // the BAM scan ran through svb_bamstream_* (`--gpu-inflate`)
 
   // Clusterer::run (clusterer.cpp:8-52): one sequential scan of the BAM on the host (the records that pass the
   // filters become the arrays of svb_alns_t), then svb_cluster_batch does extend_alignment / cluster_by_proximity /
@@ -140,8 +141,76 @@ class Clusterer {
   std::vector<int64_t> payload_of_;             // per record: index into seq4_ or -1 (read carries no SFS)
   std::vector<std::vector<uint8_t>> seq4_;      // 4-bit sequences of the reads that carry SFSs
 
+  // pass 1 on the device (`--gpu-inflate`, files of 1 GiB or more): the records are inflated, walked and parsed in HBM
+  // (svb_bamstream_*, alignment mode); per record 28 bytes and the name come back, and the CIGAR + packed bases of
+  // the reads that carry SFSs are fetched from the window where they still lie.  1 = done, 0 = not applicable, -1 = failed.
+  int scan_device() {
+    if (bgzf_gpu_device() < 0 || getenv("SVB_BAM_HOST_PARSE")) return 0;
+    BgzfSource src(cfg_.bam);
+    if (!src.ok() || !src.device_inflate()) return 0;
+    int64_t header_bytes = 0;
+    {
+      const int dev = bgzf_gpu_device();
+      bgzf_gpu_device() = -1;                          // the header is read by the host reader
+      BamReader hdr(cfg_.bam, (size_t)1 << 20);
+      bgzf_gpu_device() = dev;
+      if (!hdr.ok()) { error = "cannot read BAM " + cfg_.bam; return -1; }
+      ref_names_ = hdr.ref_names();
+      header_bytes = hdr.header_bytes();
+    }
+    svb_bamstream_t* bs = nullptr;
+    if (svb_bamstream_open(bgzf_gpu_device(), -1, (int)ref_names_.size(), &bs) != SVB_OK) { error = std::string("svb_bamstream_open: ") + svb_last_error(); return -1; }
+    const uint8_t* base = nullptr;
+    std::vector<int64_t> io, oo, want;
+    std::vector<int8_t> keep;
+    std::vector<const std::vector<SFS>*> sfs_of;
+    int rc = 1;
+    while (rc == 1 && src.next_members(base, io, oo)) {
+      svb_bam_recs_t recs;
+      if (svb_bamstream_window(bs, base, io.data(), oo.data(), (int64_t)io.size() - 1, header_bytes, &recs) != SVB_OK) {
+        error = "truncated or corrupt BAM " + cfg_.bam + ": " + svb_last_error(); rc = -1; break;
+      }
+      // which records count (clusterer.cpp:116-125), and which of them carry SFSs
+      keep.assign((size_t)recs.n, 0); sfs_of.assign((size_t)recs.n, nullptr); want.clear();
+      for (int64_t i = 0; i < recs.n; ++i) {
+        if (recs.state[i] == 0) continue;                                        // :116-120
+        if (recs.mapq[i] < cfg_.min_mapq) continue;                               // :121-122
+        if (recs.tid[i] < 0 || (size_t)recs.tid[i] >= ref_names_.size()) continue;
+        keep[(size_t)i] = 1;
+        auto it = SFSs_->find(std::string(recs.names + recs.name_offs[i], (size_t)(recs.name_offs[i + 1] - recs.name_offs[i])));   // :123-125
+        if (it != SFSs_->end()) { sfs_of[(size_t)i] = &it->second; want.push_back(i); }
+      }
+      const uint32_t* f_cig = nullptr; const int64_t* f_co = nullptr; const uint8_t* f_seq = nullptr; const int64_t* f_so = nullptr;
+      if (svb_bamstream_fetch(bs, want.data(), (int64_t)want.size(), &f_cig, &f_co, &f_seq, &f_so) != SVB_OK) { error = std::string("svb_bamstream_fetch: ") + svb_last_error(); rc = -1; break; }
+      size_t w = 0;
+      for (int64_t i = 0; i < recs.n; ++i) {
+        if (!keep[(size_t)i]) continue;
+        tid_.push_back(recs.tid[i]); pos_.push_back(recs.pos[i]); hp_.push_back(recs.hp[i]);
+        qname_.emplace_back(recs.names + recs.name_offs[i], (size_t)(recs.name_offs[i + 1] - recs.name_offs[i]));
+        if (sfs_of[(size_t)i]) {
+          cigar_.insert(cigar_.end(), f_cig + f_co[w], f_cig + f_co[w + 1]);
+          for (const SFS& s : *sfs_of[(size_t)i]) { sfs_qs_.push_back(s.qs); sfs_len_.push_back(s.l); }
+          payload_of_.push_back((int64_t)seq4_.size());
+          seq4_.emplace_back(f_seq + f_so[w], f_seq + f_so[w + 1]);
+          ++w;
+        } else {
+          cigar_.push_back((uint32_t)(recs.endpos[i] - recs.pos[i]) << 4);
+          payload_of_.push_back(-1);
+        }
+        cigar_offs_.push_back((int64_t)cigar_.size());
+        sfs_offs_.push_back((int64_t)sfs_qs_.size());
+      }
+    }
+    if (rc == 1 && (src.failed() || svb_bamstream_pending_bytes(bs) != 0)) { error = "truncated or corrupt BAM " + cfg_.bam; rc = -1; }
+    svb_bamstream_close(bs);
+    if (rc == 1) scanned_on_device = true;
+    return rc;
+  }
+
   // pass 1 (clusterer.cpp:58-153): one sequential scan
   bool scan() {
+    const int on_device = scan_device();
+    if (on_device != 0) return on_device > 0;
     BamReader bam(cfg_.bam);
     if (!bam.ok()) { error = "cannot read BAM " + cfg_.bam; return false; }
     bam.want_alignment(true);

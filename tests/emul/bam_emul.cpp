@@ -72,3 +72,18 @@ extern "C" void emul_bam_decode(const uint8_t* seq4, int32_t l_qseq, uint8_t* ou
     out[k] = bam_nt6_of_nt16((k & 1) ? (b & 0xfu) : (b >> 4));
   }
 }
+
+// alignment mode: state (0 / 1), pos, endpos, ops of the CIGAR in force and where they lie in the window
+extern "C" int emul_bam_parse_aln(const uint8_t* win, const int64_t* rec_off, int64_t n, int32_t* state, int32_t* name_len, int32_t* pos, int32_t* endpos,
+                                  int32_t* n_cigar, int64_t* cigar_off, int32_t* mapq) {
+  int err = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    BamMeta m;
+    BamAln al;
+    int64_t rel = 0;
+    if (!bam_parse_record(win + rec_off[i], 1, &m, &rel, &al)) err = 1;
+    state[i] = m.state; name_len[i] = m.name_len; pos[i] = al.pos; endpos[i] = al.endpos; n_cigar[i] = al.n_cigar;
+    cigar_off[i] = rec_off[i] + al.cigar_rel; mapq[i] = al.mapq;
+  }
+  return err;
+}

@@ -182,3 +182,48 @@ def test_malformed_records_are_reported(emul):
         p = lambda x: x.ctypes.data_as(C.c_void_p)
         assert emul.emul_bam_parse(p(a), p(ro), C.c_int64(2), C.c_int(1), *[p(c) for c in cols], p(so)) == 1
         assert cols[5][0] == 1 and cols[5][1] == 0            # the good record parsed, the bad one dropped
+
+
+def test_alignment_mode_cigar_endpos_and_cg_tag(emul):
+    """the Clusterer's view of a record (clusterer.cpp:58-153): no length filter, bam_endpos, and the CG:B,I convention
+    of records with more than 65535 CIGAR ops (SAM spec 4.2.2)"""
+    M, I, D, N, S, EQ, X = 0, 1, 2, 3, 4, 7, 8
+    op = lambda n, o: (n << 4) | o
+    seq = lambda l: (b"\x12" * ((l + 1) // 2), b"\x20" * l)
+    recs, want = [], []
+    s4, q = seq(150)
+    recs.append(record(b"a", 0, 1, 1000, s4, 150, q, [op(10, S), op(100, M), op(5, I), op(20, D), op(35, EQ)], b"HPc\1", mapq=37))
+    want.append((1, 1000, 1000 + 100 + 20 + 35, 5, 37))
+    s4, q = seq(50)                                                         # short reads stay (the search loader drops them)
+    recs.append(record(b"bb", 16, 0, 7, s4, 50, q, [op(50, M)]))
+    want.append((1, 7, 57, 1, 60))
+    s4, q = seq(120)
+    recs.append(record(b"c", 4, 0, 7, s4, 120, q, [op(120, M)]))            # unmapped: dropped
+    want.append((0, 7, 127, 1, 60))
+    s4, q = seq(120)
+    recs.append(record(b"d", 0, 0, 500, s4, 120, q, []))                     # no CIGAR: bam_endpos = pos + 1
+    want.append((1, 500, 501, 0, 60))
+    real = [op(60, M), op(3, D), op(30, X), op(2, N), op(30, M)]
+    s4, q = seq(120)
+    cg = b"CGBI" + struct.pack("<i", len(real)) + b"".join(struct.pack("<I", c) for c in real)
+    recs.append(record(b"long", 0, 2, 9000, s4, 120, q, [op(120, S), op(125, N)], b"NMI" + struct.pack("<I", 3) + cg + b"XFC\0"))
+    want.append((1, 9000, 9000 + 60 + 3 + 30 + 2 + 30, len(real), 60))
+    s4, q = seq(120)
+    recs.append(record(b"notcg", 0, 2, 9000, s4, 120, q, [op(100, S), op(125, N)], cg))   # the field is not the placeholder: it stands
+    want.append((1, 9000, 9125, 2, 60))
+    win = b"".join(recs) + b"\0" * 64
+    offs, _ = py_walk(win, 0, len(win) - 64)
+    n = len(offs)
+    a = np.frombuffer(win, np.uint8)
+    ro = np.array(offs, np.int64)
+    cols = [np.zeros(n, np.int32) for _ in range(5)]
+    co = np.zeros(n, np.int64)
+    mq = np.zeros(n, np.int32)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    assert emul.emul_bam_parse_aln(p(a), p(ro), C.c_int64(n), p(cols[0]), p(cols[1]), p(cols[2]), p(cols[3]), p(cols[4]), p(co), p(mq)) == 0
+    state, nlen, pos, endpos, ncig = cols
+    for i, (st, ps, en, nc, mapq) in enumerate(want):
+        assert (state[i], pos[i], endpos[i], ncig[i], mq[i]) == (st, ps, en, nc, mapq), i
+    got_real = [struct.unpack_from("<I", win, int(co[4]) + 4 * k)[0] for k in range(len(real))]
+    assert got_real == real
+    assert nlen[1] == 2 and nlen[2] == 0

@@ -1,6 +1,7 @@
 """GPU: `SVDSS call --bam --sfs` end to end (Clusterer on the host, POA + ksw2 on the GPU, CIGAR walk,
 clean_dups / filter_sv_chains, VCF) against the Python restatement over the oracle, byte for byte, on a
 diploid sample with planted INS/DEL; the planted SVs must come back with exact type and length."""
+import os
 import subprocess
 
 import pytest
@@ -46,6 +47,16 @@ def test_call_from_bam_and_sfs(exe, tmp_path, tag_hp, noht, threads):
     r = subprocess.run(args, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     body = vcf_body(r.stdout)
+    # the same with the Clusterer's BAM scan on the device (svb_bamstream_*, alignment mode): whole file in one window, and
+    # windows that cut records
+    for window in (None, "5000"):
+        env = dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0")
+        if window:
+            env["SVB_BGZF_WINDOW"] = window
+        g = subprocess.run(args + ["--gpu-inflate"], capture_output=True, text=True, env=env)
+        assert g.returncode == 0, g.stderr
+        assert "BAM records decoded on GPU" in g.stderr
+        assert g.stdout == r.stdout, window
     clusters = cluster_model.run(w["records"], w["names"], w["ref_seqs"], w["sfs_by_read"], threads=threads)
     want = call_model.call_vcf_lines(w["ref_seqs"], clusters, useht=not noht, threads=threads)
     assert body == want

@@ -21,6 +21,12 @@ def test_call_clipped_appends_the_clipper_records(exe, clip_world):
     clipped = subprocess.run(base + ["--clipped", "--clips", clips], capture_output=True, text=True)
     assert clipped.returncode == 0, clipped.stderr
     assert clipped.stdout.startswith(plain.stdout)
+    # clips come out of the same records when the BAM scan runs on the device
+    dev = subprocess.run(base + ["--clipped", "--clips", clips + ".dev", "--gpu-inflate"], capture_output=True, text=True,
+                         env=dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0", SVB_BGZF_WINDOW="7000"))
+    assert dev.returncode == 0, dev.stderr
+    assert "BAM records decoded on GPU" in dev.stderr and dev.stdout == clipped.stdout
+    assert open(clips + ".dev").read() == open(clips).read()
     tail = clipped.stdout[len(plain.stdout):].splitlines()
     body = [l.split("\t") for l in plain.stdout.splitlines() if not l.startswith("#")]
     regions = os.path.join(w["d"], "gpu_regions.tsv")
