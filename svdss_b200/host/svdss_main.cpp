@@ -628,9 +628,10 @@ int main(int argc, char** argv) {
       int n_ref = 0;
       { const int dev = bgzf_gpu_device(); bgzf_gpu_device() = -1; BamReader hdr(pos[0], (size_t)1 << 20); bgzf_gpu_device() = dev; if (!hdr.ok()) return EXIT_FAILURE; header_bytes = hdr.header_bytes(); n_ref = (int)hdr.ref_names().size(); }
       svb_bamstream_t* bs = nullptr;
-      if (svb_bamstream_open(c.device, 1, n_ref, &bs) != SVB_OK) return EXIT_FAILURE;
+      const bool align = string(getenv("SVB_BAMREAD_DEVICE")) == "align";   // the Clusterer's scan: alignments + a fetch of the reads with XF = 0
+      if (svb_bamstream_open(c.device, align ? -1 : 1, n_ref, &bs) != SVB_OK) return EXIT_FAILURE;
       const uint8_t* base = nullptr;
-      vector<int64_t> io, oo;
+      vector<int64_t> io, oo, want;
       uint64_t n = 0, bases = 0, kept = 0, name_bytes = 0;
       double t_dev = 0;
       bool ok = true;
@@ -640,6 +641,15 @@ int main(int argc, char** argv) {
         if (svb_bamstream_window(bs, base, io.data(), oo.data(), (int64_t)io.size() - 1, header_bytes, &recs) != SVB_OK) { cerr << svb_last_error() << endl; ok = false; break; }
         t_dev += now_s() - t1;
         for (int64_t i = 0; i < recs.n; ++i) { ++n; bases += (uint64_t)recs.l_qseq[i]; if (recs.state[i] == 2) ++kept; }
+        if (align) {
+          want.clear();
+          for (int64_t i = 0; i < recs.n; ++i) if (recs.state[i] == 1 && recs.xf[i] == 0) want.push_back(i);
+          const uint32_t* fc = nullptr; const int64_t* fco = nullptr; const uint8_t* fs = nullptr; const int64_t* fso = nullptr;
+          const double t2 = now_s();
+          if (svb_bamstream_fetch(bs, want.data(), (int64_t)want.size(), &fc, &fco, &fs, &fso) != SVB_OK) { cerr << svb_last_error() << endl; ok = false; break; }
+          t_dev += now_s() - t2;
+          kept += want.size();
+        }
         name_bytes += (uint64_t)recs.name_offs[recs.n];
       }
       ok = ok && !src.failed() && svb_bamstream_pending_bytes(bs) == 0;

@@ -75,6 +75,10 @@ def main():
             if bestd is None or j["seconds"] < bestd["seconds"]:
                 bestd = j
         res["device_loader"] = bestd
+        r = subprocess.run([exe, "_bamread", path, "--gpu-inflate"], capture_output=True, text=True,
+                           env=dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0", SVB_BAMREAD_DEVICE="align"))
+        assert r.returncode == 0, r.stderr
+        res["device_scan"] = json.loads(r.stdout.strip().splitlines()[-1])
     if a.gpu_inflate and a.laps:
         r = subprocess.run([exe, "_bamread", path, "--gpu-inflate"], capture_output=True, text=True,
                            env=dict(os.environ, SVB_BGZF_GPU_MIN_BYTES="0", SVB_BAMREAD_DEVICE="1", SVB_STAGE_STATS="1"))
@@ -94,6 +98,9 @@ def main():
         best["gpu_inflate"] = {k: res["device"][k] for k in ("seconds", "cuda_init_seconds", "records_per_s", "Gbases_per_s", "reader")}
         d = res["device_loader"]
         assert d["records"] == best["records"] and d["bases"] == best["bases"] and d["kept"] == best["kept"]
+        ds = res["device_scan"]
+        assert ds["records"] == best["records"] and ds["kept"] == best["kept"]
+        best["device_scan_for_call"] = {k: ds[k] for k in ("seconds", "cuda_init_seconds", "device_call_seconds", "records_per_s", "Gbases_per_s")}
         best["device_loader"] = {k: d[k] for k in ("seconds", "cuda_init_seconds", "device_call_seconds", "records_per_s", "Gbases_per_s", "name_bytes", "reader")}
     print(json.dumps(best))
 
