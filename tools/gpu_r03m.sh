@@ -2,7 +2,7 @@
 # Round 2, last full validation: whole GPU suite, smoke, the line as the driver runs it (both arms)
 set -x
 mkdir -p gpurun_out
-TAG=r03m
+TAG=${TAG:-r03m}
 timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -6 | tee gpurun_out/gpu_tests_$TAG.txt
 python __graft_entry__.py smoke 2>&1 | tail -1
 ( time timeout 1500 python bench.py 2>gpurun_out/bench_full_$TAG.err > gpurun_out/bench_full_$TAG.txt ) 2>&1 | tail -4
