@@ -83,7 +83,9 @@ SVB_HD bool bam_link_segment(const uint8_t* win, int64_t b, int64_t total, const
                              int64_t* rec_off, int64_t cap, int64_t* cur, int64_t* n, int64_t* join, int* err) {
   *join = -1;
   while (*cur < b) {
+    // the usual case first: the true walk enters at the first record of the segment, which is where a right guess starts
     int64_t lo = 0, hi = c;
+    if (c > 0 && chain[0] == *cur) hi = 0;
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (chain[mid] < *cur) lo = mid + 1; else hi = mid; }
     if (lo < c && chain[lo] == *cur && *n + (c - lo) <= cap) {
       *join = lo;

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--records", type=int, default=20000)
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--gpu-inflate", action="store_true")
+    ap.add_argument("--keep", default="", help="copy the generated BAM here before it is deleted")
     ap.add_argument("--laps", action="store_true", help="one more run of the device loader with SVB_STAGE_STATS=1: mean lap times of svb_bamstream_window on stderr")
     a = ap.parse_args()
     exe = build.build_host()
@@ -91,6 +92,9 @@ def main():
         sys.stderr.write("\n".join([l for l in r.stderr.splitlines() if "segments joined" in l][:3]) + "\n")
     best = res["host"]
     best["file_bytes"] = os.path.getsize(path)
+    if a.keep:
+        import shutil
+        shutil.copyfile(path, a.keep)
     os.remove(path); os.rmdir(d)
     best["host_threads"] = len(os.sched_getaffinity(0))
     if "device" in res:
